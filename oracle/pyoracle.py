@@ -1,0 +1,322 @@
+"""TEST INFRASTRUCTURE: ctypes binding of oracle/liboracle.so (the plain-C restatement,
+oracle/fba_oracle.c). Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this. Never on the product path."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liboracle.so")
+
+MAXF = 16
+
+DOM_TABLE, DOM_TIGER, DOM_FACTORED_TIGER, DOM_SYSADMIN, DOM_GRIDWORLD, DOM_CA = range(6)
+ACT_UNIFORM_INT, ACT_SLOW_INT = 0, 1
+START_CONST, START_BOOL, START_UNIFORM_INT, START_SLOW2, START_CATEGORICAL = range(5)
+MUT_FACTORED_TIGER, MUT_CA, MUT_SYSADMIN, MUT_GRIDWORLD = range(4)
+
+
+class CModel(C.Structure):
+    _fields_ = [
+        ("S", C.c_int32), ("A", C.c_int32), ("O", C.c_int32), ("FS", C.c_int32), ("FO", C.c_int32),
+        ("feat_s", C.c_int32 * MAXF), ("feat_o", C.c_int32 * MAXF),
+        ("tabular", C.c_int32), ("domain", C.c_int32),
+        ("dom_ip", C.c_int32 * 32), ("dom_dp", C.c_double * 8),
+        ("rew_sa", C.c_void_p), ("rew_as2", C.c_void_p), ("term_sa", C.c_void_p),
+        ("term_as2", C.c_void_p),
+        ("action_draw", C.c_int32), ("start_kind", C.c_int32), ("start_ip", C.c_int32 * 4),
+        ("start_values", C.c_void_p), ("start_total", C.c_double), ("start_table", C.c_void_p),
+    ]
+
+
+class CRng(C.Structure):
+    _fields_ = [("words", C.c_void_p), ("n", C.c_int64), ("cur", C.c_int64), ("overrun", C.c_int32)]
+
+
+class CStructs(C.Structure):
+    _fields_ = [("n_structs", C.c_int32), ("cap", C.c_int32), ("t_par", C.c_void_p),
+                ("o_par", C.c_void_p)]
+
+
+class CBelief(C.Structure):
+    _fields_ = [("N", C.c_int64), ("stride", C.c_int64), ("counts", C.c_void_p),
+                ("state", C.c_void_p), ("struct_id", C.c_void_p), ("w", C.c_void_p),
+                ("total_weight", C.c_double)]
+
+
+def build(force=False):
+    """gcc oracle/fba_oracle.c -> oracle/liboracle.so (building the checker is not using it)."""
+    src = os.path.join(_HERE, "fba_oracle.c")
+    hdr = os.path.join(_HERE, "fba_oracle.h")
+    if (not force and os.path.exists(LIB_PATH)
+            and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(src), os.path.getmtime(hdr))):
+        return LIB_PATH
+    subprocess.check_call(["gcc", "-std=c11", "-O2", "-fPIC", "-shared", "-ffp-contract=off",
+                           "-Wall", "-Wextra", "-o", LIB_PATH, src, "-lm"])
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(LIB_PATH)
+        vp, i64, i32, dbl = C.c_void_p, C.c_int64, C.c_int32, C.c_double
+        L.orc_uniform01.restype = dbl
+        L.orc_uniform01.argtypes = [vp]
+        L.orc_boolean.restype = C.c_int
+        L.orc_boolean.argtypes = [vp]
+        L.orc_uniform_int.restype = i32
+        L.orc_uniform_int.argtypes = [vp, C.c_uint32]
+        L.orc_struct_size.restype = i64
+        L.orc_struct_size.argtypes = [vp, vp, vp]
+        L.orc_struct_offsets.restype = i64
+        L.orc_struct_offsets.argtypes = [vp, vp, vp, vp]
+        L.orc_reward.restype = dbl
+        L.orc_reward.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
+        L.orc_sample_start_state.restype = C.c_int
+        L.orc_sample_start_state.argtypes = [vp, vp]
+        L.orc_step.restype = dbl
+        L.orc_step.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp]
+        L.orc_obs_prob.restype = dbl
+        L.orc_obs_prob.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int]
+        L.orc_is_update.restype = dbl
+        L.orc_is_update.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp]
+        L.orc_weighted_sample.restype = i64
+        L.orc_weighted_sample.argtypes = [vp, vp]
+        L.orc_is_resample.argtypes = [vp, vp, vp, vp]
+        L.orc_is_reset_domain_states.argtypes = [vp, vp, vp, vp, vp]
+        L.orc_reject_sample.restype = i64
+        L.orc_reject_sample.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, vp, vp]
+        L.orc_flat_reset_domain_states.argtypes = [vp, vp, vp]
+        L.orc_marginalize_node.argtypes = [vp, C.c_uint32, vp, C.c_uint32, C.c_int, vp]
+        L.orc_reinvigorate.restype = C.c_int
+        L.orc_reinvigorate.argtypes = [vp, vp, vp, vp, i64, C.c_int, vp]
+        L.orc_rollout.restype = dbl
+        L.orc_rollout.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, dbl, vp]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Rng:
+    """A replay stream of mt19937 words."""
+
+    def __init__(self, words):
+        self.words = np.ascontiguousarray(words, np.uint32)
+        self.c = CRng(_p(self.words), len(self.words), 0, 0)
+
+    @property
+    def cur(self):
+        return self.c.cur
+
+    @property
+    def overrun(self):
+        return bool(self.c.overrun)
+
+    def ref(self):
+        return C.byref(self.c)
+
+
+class Model:
+    """Domain + feature description. `desc` is the plain dict stored in fixtures
+    (see oracle/gen_golden.py / tests/golden/*.npz)."""
+
+    def __init__(self, desc):
+        d = self.desc = dict(desc)
+        c = self.c = CModel()
+        c.S, c.A, c.O = int(d["S"]), int(d["A"]), int(d["O"])
+        fs = np.asarray(d["feat_s"], np.int32)
+        fo = np.asarray(d["feat_o"], np.int32)
+        c.FS, c.FO = len(fs), len(fo)
+        for i, v in enumerate(fs):
+            c.feat_s[i] = int(v)
+        for i, v in enumerate(fo):
+            c.feat_o[i] = int(v)
+        c.tabular = int(d["tabular"])
+        c.domain = int(d["domain"])
+        for i, v in enumerate(np.asarray(d.get("dom_ip", []), np.int32)):
+            c.dom_ip[i] = int(v)
+        for i, v in enumerate(np.asarray(d.get("dom_dp", []), np.float64)):
+            c.dom_dp[i] = float(v)
+        self._keep = {}
+        for k, dt in (("rew_sa", np.float64), ("rew_as2", np.float64), ("term_sa", np.uint8),
+                      ("term_as2", np.uint8), ("start_values", np.float32),
+                      ("start_table", np.int32)):
+            v = d.get(k)
+            if v is not None and len(np.atleast_1d(v)):
+                self._keep[k] = np.ascontiguousarray(v, dt)
+                setattr(c, k, _p(self._keep[k]))
+        c.action_draw = int(d.get("action_draw", 0))
+        c.start_kind = int(d.get("start_kind", 0))
+        for i, v in enumerate(np.asarray(d.get("start_ip", []), np.int32)):
+            c.start_ip[i] = int(v)
+        c.start_total = float(d.get("start_total", 0.0))
+        self.S, self.A, self.O, self.FS, self.FO = c.S, c.A, c.O, c.FS, c.FO
+        self.feat_s, self.feat_o = fs, fo
+
+    def ref(self):
+        return C.byref(self.c)
+
+    def struct_size(self, t_par, o_par):
+        t = np.ascontiguousarray(t_par, np.uint32)
+        o = np.ascontiguousarray(o_par, np.uint32)
+        return lib().orc_struct_size(self.ref(), _p(t), _p(o))
+
+    def struct_offsets(self, t_par, o_par):
+        t = np.ascontiguousarray(t_par, np.uint32)
+        o = np.ascontiguousarray(o_par, np.uint32)
+        off = np.zeros(self.A * (self.FS + self.FO), np.int64)
+        n = lib().orc_struct_offsets(self.ref(), _p(t), _p(o), _p(off))
+        return off, n
+
+    def reward(self, s, a, s2):
+        t = C.c_int(0)
+        r = lib().orc_reward(self.ref(), s, a, s2, C.byref(t))
+        return r, bool(t.value)
+
+    def sample_start_state(self, rng):
+        return lib().orc_sample_start_state(self.ref(), rng.ref())
+
+
+class Structs:
+    """Structure table: parent bitmasks per (structure, action, node)."""
+
+    def __init__(self, model, t_par, o_par, cap=None):
+        t_par = np.asarray(t_par, np.uint32).reshape(-1, model.A * model.FS)
+        o_par = np.asarray(o_par, np.uint32).reshape(-1, model.A * model.FO)
+        n = len(t_par)
+        cap = max(cap or n, n)
+        self.model = model
+        self.t_par = np.zeros((cap, model.A * model.FS), np.uint32)
+        self.o_par = np.zeros((cap, model.A * model.FO), np.uint32)
+        self.t_par[:n] = t_par
+        self.o_par[:n] = o_par
+        self.c = CStructs(n, cap, _p(self.t_par), _p(self.o_par))
+
+    @property
+    def n(self):
+        return self.c.n_structs
+
+    def ref(self):
+        return C.byref(self.c)
+
+    def sizes(self):
+        return np.array([self.model.struct_size(self.t_par[i], self.o_par[i])
+                         for i in range(self.n)], np.int64)
+
+
+class Belief:
+    """N particles as flat arrays (the same arrays the CUDA path downloads)."""
+
+    def __init__(self, N, stride, weighted=True):
+        self.N, self.stride = int(N), int(stride)
+        self.counts = np.zeros((self.N, self.stride), np.float32)
+        self.state = np.zeros(self.N, np.int32)
+        self.struct_id = np.zeros(self.N, np.int32)
+        self.w = np.full(self.N, 1.0 / self.N, np.float64) if weighted else None
+        self.c = CBelief(self.N, self.stride, _p(self.counts), _p(self.state), _p(self.struct_id),
+                         _p(self.w), 1.0)
+
+    @property
+    def total_weight(self):
+        return self.c.total_weight
+
+    @total_weight.setter
+    def total_weight(self, v):
+        self.c.total_weight = float(v)
+
+    def ref(self):
+        return C.byref(self.c)
+
+    def clone_empty(self):
+        return Belief(self.N, self.stride, self.w is not None)
+
+    def copy(self):
+        b = self.clone_empty()
+        b.counts[:] = self.counts
+        b.state[:] = self.state
+        b.struct_id[:] = self.struct_id
+        if self.w is not None:
+            b.w[:] = self.w
+        b.total_weight = self.total_weight
+        return b
+
+
+def sequential_uniform_total(n):
+    """WeightedFilter::_total_weight after n add(s, 1/n) calls (WeightedFilter.cpp:60-66)."""
+    w = 1.0 / float(n)
+    return float(np.cumsum(np.full(n, w, np.float64))[-1]) if n else 0.0
+
+
+def step(model, t_par, o_par, counts, state, a, update_counts, rng):
+    st = np.array([state], np.int32)
+    o = C.c_int(0)
+    t = C.c_int(0)
+    tp = np.ascontiguousarray(t_par, np.uint32)
+    op = np.ascontiguousarray(o_par, np.uint32)
+    r = lib().orc_step(model.ref(), _p(tp), _p(op), _p(counts), _p(st), a, int(update_counts),
+                       rng.ref(), C.byref(o), C.byref(t))
+    return int(st[0]), o.value, bool(t.value), r
+
+
+def obs_prob(model, t_par, o_par, counts, state, a, o):
+    tp = np.ascontiguousarray(t_par, np.uint32)
+    op = np.ascontiguousarray(o_par, np.uint32)
+    return lib().orc_obs_prob(model.ref(), _p(tp), _p(op), _p(counts), state, a, o)
+
+
+def is_update(model, structs, belief, a, o, rng):
+    return lib().orc_is_update(model.ref(), structs.ref(), belief.ref(), a, o, rng.ref())
+
+
+def is_resample(src, rng):
+    dst = src.clone_empty()
+    anc = np.zeros(src.N, np.int64)
+    lib().orc_is_resample(src.ref(), dst.ref(), rng.ref(), _p(anc))
+    return dst, anc
+
+
+def is_reset_domain_states(model, src, rng):
+    dst = src.clone_empty()
+    anc = np.zeros(src.N, np.int64)
+    lib().orc_is_reset_domain_states(model.ref(), src.ref(), dst.ref(), rng.ref(), _p(anc))
+    return dst, anc
+
+
+def weighted_sample(belief, rng):
+    return lib().orc_weighted_sample(belief.ref(), rng.ref())
+
+
+def reject_sample(model, structs, src, a, o, rng):
+    dst = src.clone_empty()
+    anc = np.zeros(src.N, np.int64)
+    attempts = lib().orc_reject_sample(model.ref(), structs.ref(), src.ref(), dst.ref(), a, o,
+                                       rng.ref(), _p(anc))
+    return dst, anc, attempts
+
+
+def flat_reset_domain_states(model, belief, rng):
+    lib().orc_flat_reset_domain_states(model.ref(), belief.ref(), rng.ref())
+
+
+def reinvigorate(model, structs, belief, fc, amount, mutate_kind, rng):
+    rc = lib().orc_reinvigorate(model.ref(), structs.ref(), belief.ref(), fc.ref(), amount,
+                                mutate_kind, rng.ref())
+    if rc:
+        raise RuntimeError("orc_reinvigorate failed: %d" % rc)
+
+
+def rollout(model, t_par, o_par, counts, start_state, depth, discount, rng):
+    tp = np.ascontiguousarray(t_par, np.uint32)
+    op = np.ascontiguousarray(o_par, np.uint32)
+    return lib().orc_rollout(model.ref(), _p(tp), _p(op), _p(counts), start_state, depth, discount,
+                             rng.ref())

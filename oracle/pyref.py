@@ -1,0 +1,186 @@
+"""TEST INFRASTRUCTURE: ctypes window onto oracle/_ref/libfba_ref.so (the unmodified reference,
+compiled by oracle/Makefile + oracle/ref_harness.cpp). Only tests/, bench.py's reference/cpu_baseline
+legs and oracle/gen_golden.py may import this. Never on the product path."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libfba_ref.so")
+
+F_IS, F_RS, F_REINV, F_REINV_FC = 0, 1, 2, 3
+
+
+def available():
+    return os.path.exists(LIB_PATH)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(LIB_PATH)
+        L.ref_open.restype = C.c_void_p
+        L.ref_open.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p,
+                               C.c_double, C.c_int, C.c_char_p]
+        L.ref_error.restype = C.c_char_p
+        L.ref_error.argtypes = [C.c_void_p]
+        L.ref_close.argtypes = [C.c_void_p]
+        L.ref_reseed.argtypes = [C.c_void_p, C.c_char_p]
+        L.ref_sizes.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref_feature_sizes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_rng_mark.argtypes = [C.c_void_p]
+        L.ref_rng_words_since_mark.restype = C.c_long
+        L.ref_rng_words_since_mark.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_long]
+        L.ref_rng_draw_words.argtypes = [C.c_void_p, C.c_long]
+        L.ref_belief_init.restype = C.c_int
+        L.ref_belief_init.argtypes = [C.c_void_p, C.c_int, C.c_long, C.c_long]
+        L.ref_filter_size.restype = C.c_long
+        L.ref_filter_size.argtypes = [C.c_void_p, C.c_int]
+        L.ref_filter_states.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_is_weights.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_particle_num_counts.restype = C.c_long
+        L.ref_particle_num_counts.argtypes = [C.c_void_p, C.c_int, C.c_long]
+        L.ref_particle_dump.argtypes = [C.c_void_p, C.c_int, C.c_long, C.c_void_p, C.c_void_p,
+                                        C.c_void_p]
+        L.ref_is_update.restype = C.c_double
+        L.ref_is_update.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.ref_is_resample.argtypes = [C.c_void_p]
+        L.ref_update_estimation.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.ref_reset_domain_states.argtypes = [C.c_void_p, C.c_int]
+        L.ref_reinvigorate_only.argtypes = [C.c_void_p]
+        L.ref_particle_step.restype = C.c_double
+        L.ref_particle_step.argtypes = [C.c_void_p, C.c_int, C.c_long, C.c_int, C.c_int, C.c_void_p]
+        L.ref_particle_obs_prob.restype = C.c_double
+        L.ref_particle_obs_prob.argtypes = [C.c_void_p, C.c_int, C.c_long, C.c_int, C.c_int]
+        L.ref_rollout.restype = C.c_double
+        L.ref_rollout.argtypes = [C.c_void_p, C.c_int, C.c_long, C.c_int, C.c_int]
+        L.ref_reward.restype = C.c_double
+        L.ref_reward.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.ref_env_script.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                     C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Ref:
+    """One reference simulator (BAPOMDP or FBAPOMDP) + its beliefs. NOTE: the reference keeps ONE
+    global RNG, so only one Ref should be active at a time."""
+
+    def __init__(self, domain, size=0, width=0, height=0, factored=False, structure_prior="",
+                 discount=0.95, horizon=20, seed="42"):
+        self.L = lib()
+        self.h = self.L.ref_open(domain.encode(), size, width, height, int(factored),
+                                 structure_prior.encode(), discount, horizon, seed.encode())
+        err = self.L.ref_error(self.h).decode()
+        if err:
+            raise RuntimeError("reference: " + err)
+        sz = np.zeros(5, np.int32)
+        self.L.ref_sizes(self.h, _p(sz))
+        self.S, self.A, self.O, self.FS, self.FO = (int(x) for x in sz)
+        fs, fo = np.zeros(self.FS, np.int32), np.zeros(self.FO, np.int32)
+        self.L.ref_feature_sizes(self.h, _p(fs), _p(fo))
+        self.feat_s, self.feat_o = fs, fo
+        self.factored = factored
+
+    def close(self):
+        if self.h:
+            self.L.ref_close(self.h)
+            self.h = None
+
+    def reseed(self, seed):
+        self.L.ref_reseed(self.h, seed.encode())
+
+    # RNG tap
+    def mark(self):
+        self.L.ref_rng_mark(self.h)
+
+    def words_since_mark(self, limit=1 << 31):
+        n = self.L.ref_rng_words_since_mark(self.h, None, 0, limit)
+        if n < 0:
+            raise RuntimeError("rng tap lost sync")
+        out = np.zeros(n, np.uint32)
+        if n:
+            self.L.ref_rng_words_since_mark(self.h, _p(out), n, limit)
+        return out
+
+    def draw_words(self, n):
+        out = np.zeros(n, np.uint32)
+        self.L.ref_rng_draw_words(_p(out), n)
+        return out
+
+    # beliefs
+    def belief_init(self, kind, n, resample_amount=0):
+        if self.L.ref_belief_init(self.h, kind, n, resample_amount):
+            raise RuntimeError("reference: " + self.L.ref_error(self.h).decode())
+
+    def size(self, filt):
+        return self.L.ref_filter_size(self.h, filt)
+
+    def states(self, filt):
+        out = np.zeros(self.size(filt), np.int32)
+        self.L.ref_filter_states(self.h, filt, _p(out))
+        return out
+
+    def is_weights(self):
+        w = np.zeros(self.size(F_IS), np.float64)
+        tot = np.zeros(1, np.float64)
+        self.L.ref_is_weights(self.h, _p(w), _p(tot))
+        return w, float(tot[0])
+
+    def particle(self, filt, i):
+        """(t_parent_masks [A,FS], o_parent_masks [A,FO], counts float32[C])"""
+        n = self.L.ref_particle_num_counts(self.h, filt, i)
+        tp = np.zeros((self.A, self.FS), np.uint32)
+        op = np.zeros((self.A, self.FO), np.uint32)
+        c = np.zeros(n, np.float32)
+        self.L.ref_particle_dump(self.h, filt, i, _p(tp), _p(op), _p(c))
+        return tp, op, c
+
+    def particles(self, filt):
+        return [self.particle(filt, i) for i in range(self.size(filt))]
+
+    def is_update(self, a, o):
+        return self.L.ref_is_update(self.h, a, o)
+
+    def is_resample(self):
+        self.L.ref_is_resample(self.h)
+
+    def update_estimation(self, kind, a, o):
+        self.L.ref_update_estimation(self.h, kind, a, o)
+
+    def reset_domain_states(self, kind):
+        self.L.ref_reset_domain_states(self.h, kind)
+
+    def reinvigorate_only(self):
+        self.L.ref_reinvigorate_only(self.h)
+
+    def particle_step(self, filt, i, a, keep_counts=False):
+        out = np.zeros(3, np.int32)
+        r = self.L.ref_particle_step(self.h, filt, i, a, int(keep_counts), _p(out))
+        return int(out[0]), int(out[1]), bool(out[2]), r
+
+    def obs_prob(self, filt, i, a, o):
+        return self.L.ref_particle_obs_prob(self.h, filt, i, a, o)
+
+    def rollout(self, filt, i, start_state, depth):
+        return self.L.ref_rollout(self.h, filt, i, start_state, depth)
+
+    def reward(self, s, a, s2):
+        t = np.zeros(1, np.int32)
+        r = self.L.ref_reward(self.h, s, a, s2, _p(t))
+        return r, bool(t[0])
+
+    def env_script(self, steps, horizon):
+        a = np.zeros(steps, np.int32)
+        o = np.zeros(steps, np.int32)
+        f = np.zeros(steps, np.int32)
+        self.L.ref_env_script(self.h, steps, horizon, _p(a), _p(o), _p(f))
+        return a, o, f

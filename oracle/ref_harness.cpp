@@ -1,0 +1,601 @@
+// TEST INFRASTRUCTURE — not shipped, never on the product path.
+//
+// A thin extern "C" window onto the UNMODIFIED reference (samkatt/fba-pomdp), compiled from
+// /root/reference by oracle/Makefile into oracle/_ref/libfba_ref.so. It exists to
+//   (1) pin oracle/fba_oracle.c (the plain-C restatement) against the reference's real classes,
+//   (2) generate the golden fixtures under tests/golden/ (oracle/gen_golden.py), and
+//   (3) be the CPU baseline (`bench.py --impl reference`, cpu_baseline.kind = "reference").
+//
+// It drives the reference exactly as its own callers do:
+//   beliefs::BAImportanceSampling::{initiate,updateEstimation,resetDomainStateDistribution}
+//       (src/beliefs/bayes-adaptive/BAImportanceSampling.cpp:49-111)
+//   beliefs::importance_sampling::{update,resample}
+//       (src/beliefs/particle_filters/ImportanceSampler.hpp:31-94)
+//   beliefs::BARejectionSampling / rejectSample (src/beliefs/particle_filters/RejectionSampling.hpp:26-72)
+//   beliefs::bayes_adaptive::factored::ReinvigoratingRejectionSampling
+//       (src/beliefs/bayes-adaptive/factored/ReinvigoratingRejectionSampling.cpp:89-131)
+//   planners::RBAPOUCT::rollout (src/planners/bayes-adaptive/RBAPOUCT.cpp:295-323)
+// Config structs are filled programmatically, as test/test.cpp:170-179 does.
+//
+// RNG tap: the reference draws from one global std::mt19937 (src/utils/random.cpp:11). The harness
+// never replaces it; it copies the engine before an operation ("mark") and afterwards advances the
+// copy until it equals the live engine, which yields the exact 32-bit words the operation consumed.
+// Those words are the replay stream fed to oracle/fba_oracle.c and to the CUDA path.
+//
+// Built with -fno-access-control (this TU only) so private filters can be dumped.
+
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "easylogging++.h"
+
+#include "bayes-adaptive/models/factored/FBAPOMDP.hpp"
+#include "bayes-adaptive/models/table/BADomainExtension.hpp"
+#include "bayes-adaptive/models/table/BAPOMDP.hpp"
+#include "bayes-adaptive/states/factored/BABNModel.hpp"
+#include "bayes-adaptive/states/factored/FBAPOMDPState.hpp"
+#include "bayes-adaptive/states/table/BAPOMDPState.hpp"
+#include "beliefs/bayes-adaptive/BAImportanceSampling.hpp"
+#include "beliefs/bayes-adaptive/BARejectionSampling.hpp"
+#include "beliefs/bayes-adaptive/factored/ReinvigoratingRejectionSampling.hpp"
+#include "beliefs/particle_filters/ImportanceSampler.hpp"
+#include "beliefs/particle_filters/RejectionSampling.hpp"
+#include "configurations/FBAConf.hpp"
+#include "domains/POMDP.hpp"
+#include "domains/collision-avoidance/CollisionAvoidance.hpp"
+#include "domains/gridworld/GridWorld.hpp"
+#include "domains/sysadmin/SysAdmin.hpp"
+#include "environment/Action.hpp"
+#include "environment/Environment.hpp"
+#include "environment/Observation.hpp"
+#include "environment/Reward.hpp"
+#include "environment/State.hpp"
+#include "environment/Terminal.hpp"
+#include "planners/bayes-adaptive/RBAPOUCT.hpp"
+#include "utils/random.hpp"
+
+INITIALIZE_EASYLOGGINGPP
+
+namespace {
+
+using FBAPOMDP = ::bayes_adaptive::factored::FBAPOMDP;
+using ReinvRS  = ::beliefs::bayes_adaptive::factored::ReinvigoratingRejectionSampling;
+
+struct Handle
+{
+    configurations::FBAConf conf;
+    std::unique_ptr<BAPOMDP> sim; // hyper-state simulator (tabular BAPOMDP or FBAPOMDP)
+    std::unique_ptr<Environment> env; // the true domain, for (a,o) scripts
+    bool factored = false;
+    std::vector<int> feat_s, feat_o;
+
+    std::unique_ptr<beliefs::BAImportanceSampling> is_belief;
+    std::unique_ptr<beliefs::BARejectionSampling> rs_belief;
+    std::unique_ptr<ReinvRS> reinv_belief;
+    std::unique_ptr<planners::RBAPOUCT> planner;
+
+    std::mt19937 mark;
+    std::string err;
+};
+
+bool g_rng_initiated = false;
+
+// which particle container a call refers to
+enum Filter { F_IS = 0, F_RS = 1, F_REINV = 2, F_REINV_FC = 3 };
+
+BAState const* particleOf(Handle* h, int filter, long i)
+{
+    switch (filter)
+    {
+        case F_IS:
+            return static_cast<BAState const*>(h->is_belief->_filter.particle(i)->particle);
+        case F_RS: return static_cast<BAState const*>(h->rs_belief->_filter.particles()[i]);
+        case F_REINV: return h->reinv_belief->_belief.particles()[i];
+        case F_REINV_FC: return h->reinv_belief->_fully_connected_belief.particles()[i];
+    }
+    return nullptr;
+}
+
+long filterSize(Handle* h, int filter)
+{
+    switch (filter)
+    {
+        case F_IS: return h->is_belief ? (long)h->is_belief->_filter.size() : 0;
+        case F_RS: return h->rs_belief ? (long)h->rs_belief->_filter.size() : 0;
+        case F_REINV: return h->reinv_belief ? (long)h->reinv_belief->_belief.size() : 0;
+        case F_REINV_FC:
+            return h->reinv_belief ? (long)h->reinv_belief->_fully_connected_belief.size() : 0;
+    }
+    return 0;
+}
+
+uint32_t maskOf(std::vector<int> const& parents)
+{
+    uint32_t m = 0;
+    for (auto p : parents) m |= (1u << p);
+    return m;
+}
+
+} // namespace
+
+extern "C" {
+
+// domain: reference -D string. factored: 0 = tabular BA-POMDP (makeTBAPOMDP), 1 = FBA-POMDP.
+void* ref_open(
+    char const* domain,
+    int size,
+    int width,
+    int height,
+    int factored,
+    char const* structure_prior,
+    double discount,
+    int horizon,
+    char const* seed)
+{
+    auto h = new Handle();
+    try
+    {
+        if (!g_rng_initiated)
+        {
+            rnd::initiate(); // ziggurat tables (unused in expected mode) + time seed, then:
+            g_rng_initiated = true;
+        }
+        std::string seed_str(seed);
+        rnd::seed(seed_str);
+
+        auto& c                 = h->conf;
+        c.domain_conf.domain    = domain;
+        c.domain_conf.size      = size;
+        c.domain_conf.width     = width;
+        c.domain_conf.height    = height;
+        c.structure_prior       = structure_prior;
+        c.discount              = discount;
+        c.horizon               = horizon;
+        c.bayes_sample_method   = rnd::sample::Dir::Expected; // the reference default (BAConf.hpp:22)
+        c.planner_conf.mcts_max_depth         = horizon;
+        c.planner_conf.mcts_simulation_amount = 16;
+
+        h->factored = factored != 0;
+        h->sim      = factored ? factory::makeFBAPOMDP(c) : factory::makeTBAPOMDP(c);
+        h->env      = factory::makeEnvironment(c.domain_conf);
+
+        if (factored)
+        {
+            auto fs   = static_cast<FBAPOMDP const*>(h->sim.get())->domainFeatureSize();
+            h->feat_s = fs->_S;
+            h->feat_o = fs->_O;
+        } else
+        {
+            h->feat_s = {h->sim->domainSize()->_S};
+            h->feat_o = {h->sim->domainSize()->_O};
+        }
+        h->mark = rnd::rng();
+    } catch (std::string const& e)
+    {
+        h->err = e;
+    } catch (char const* e)
+    {
+        h->err = e;
+    } catch (std::exception const& e)
+    {
+        h->err = e.what();
+    }
+    return h;
+}
+
+char const* ref_error(void* hv)
+{
+    return static_cast<Handle*>(hv)->err.c_str();
+}
+
+void ref_close(void* hv)
+{
+    auto h = static_cast<Handle*>(hv);
+    if (h->sim)
+    {
+        if (h->is_belief) h->is_belief->free(*h->sim);
+        if (h->rs_belief) h->rs_belief->free(*h->sim);
+        if (h->reinv_belief) h->reinv_belief->free(*h->sim);
+    }
+    delete h;
+}
+
+void ref_reseed(void* hv, char const* seed)
+{
+    std::string s(seed);
+    rnd::seed(s);
+    static_cast<Handle*>(hv)->mark = rnd::rng();
+}
+
+// out[0..4] = S, A, O, F_S, F_O
+void ref_sizes(void* hv, int* out)
+{
+    auto h = static_cast<Handle*>(hv);
+    out[0] = h->sim->domainSize()->_S;
+    out[1] = h->sim->domainSize()->_A;
+    out[2] = h->sim->domainSize()->_O;
+    out[3] = (int)h->feat_s.size();
+    out[4] = (int)h->feat_o.size();
+}
+
+void ref_feature_sizes(void* hv, int* fs, int* fo)
+{
+    auto h = static_cast<Handle*>(hv);
+    for (size_t i = 0; i < h->feat_s.size(); ++i) fs[i] = h->feat_s[i];
+    for (size_t i = 0; i < h->feat_o.size(); ++i) fo[i] = h->feat_o[i];
+}
+
+/**** RNG word tap ****/
+void ref_rng_mark(void* hv)
+{
+    static_cast<Handle*>(hv)->mark = rnd::rng();
+}
+
+// words the global mt19937 produced since the last mark; returns the count (copies at most cap).
+// Gives up (returns -1) after `limit` words without meeting the live engine.
+long ref_rng_words_since_mark(void* hv, uint32_t* out, long cap, long limit)
+{
+    auto h    = static_cast<Handle*>(hv);
+    auto twin = h->mark;
+    long n    = 0;
+    while (!(twin == rnd::rng()))
+    {
+        auto w = static_cast<uint32_t>(twin());
+        if (n < cap && out) out[n] = w;
+        ++n;
+        if (n > limit) return -1;
+    }
+    return n;
+}
+
+// raw words straight from the live engine (advances it): used to build streams for the oracle
+void ref_rng_draw_words(uint32_t* out, long n)
+{
+    for (long i = 0; i < n; ++i) out[i] = static_cast<uint32_t>(rnd::rng()());
+}
+
+/**** beliefs ****/
+// kind: F_IS / F_RS / F_REINV. initiate() follows the reference (sampleStartState per particle).
+int ref_belief_init(void* hv, int kind, long n, long resample_amount)
+{
+    auto h = static_cast<Handle*>(hv);
+    try
+    {
+        if (kind == F_IS)
+        {
+            if (h->is_belief) h->is_belief->free(*h->sim);
+            h->is_belief.reset(new beliefs::BAImportanceSampling(n));
+            h->is_belief->initiate(*h->sim);
+        } else if (kind == F_RS)
+        {
+            if (h->rs_belief) h->rs_belief->free(*h->sim);
+            h->rs_belief.reset(new beliefs::BARejectionSampling(n));
+            h->rs_belief->initiate(*h->sim);
+        } else
+        {
+            if (h->reinv_belief) h->reinv_belief->free(*h->sim);
+            h->reinv_belief.reset(new ReinvRS(n, resample_amount));
+            h->reinv_belief->initiate(*h->sim);
+        }
+    } catch (std::string const& e)
+    {
+        h->err = e;
+        return 1;
+    } catch (char const* e)
+    {
+        h->err = e;
+        return 1;
+    }
+    return 0;
+}
+
+long ref_filter_size(void* hv, int filter)
+{
+    return filterSize(static_cast<Handle*>(hv), filter);
+}
+
+void ref_filter_states(void* hv, int filter, int* out)
+{
+    auto h = static_cast<Handle*>(hv);
+    auto n = filterSize(h, filter);
+    for (long i = 0; i < n; ++i) out[i] = particleOf(h, filter, i)->_domain_state->index();
+}
+
+// weights of the importance-sampling filter + its _total_weight
+void ref_is_weights(void* hv, double* w, double* total)
+{
+    auto h = static_cast<Handle*>(hv);
+    auto n = filterSize(h, F_IS);
+    for (long i = 0; i < n; ++i) w[i] = h->is_belief->_filter.particle(i)->w;
+    *total = h->is_belief->_filter._total_weight;
+}
+
+// number of float count cells particle i owns (its structure's total CPT size)
+long ref_particle_num_counts(void* hv, int filter, long i)
+{
+    auto h = static_cast<Handle*>(hv);
+    auto p = particleOf(h, filter, i);
+    auto S = h->sim->domainSize()->_S, A = h->sim->domainSize()->_A, O = h->sim->domainSize()->_O;
+    if (!h->factored) return (long)A * S * S + (long)A * S * O;
+
+    auto m = static_cast<FBAPOMDPState const*>(p)->model();
+    long n = 0;
+    for (auto const& node : m->copyT()) n += (long)node.numParams();
+    for (auto const& node : m->copyO()) n += (long)node.numParams();
+    return n;
+}
+
+// Particle dump in this repo's layout: for a in [0,A): T nodes f = 0..F_S-1, then O nodes
+// g = 0..F_O-1; each node's CPT row-major [parent configuration][output].
+// Tabular: T(a) = phi[s][a][s'] as [s][s'], O(a) = psi[a][s'][o] as [s'][o]; parent masks = 1.
+// t_par: [A*F_S] parent bitmasks, o_par: [A*F_O].
+void ref_particle_dump(void* hv, int filter, long i, uint32_t* t_par, uint32_t* o_par, float* counts)
+{
+    auto h = static_cast<Handle*>(hv);
+    auto p = particleOf(h, filter, i);
+    auto S = h->sim->domainSize()->_S, A = h->sim->domainSize()->_A, O = h->sim->domainSize()->_O;
+    long k = 0;
+
+    if (!h->factored)
+    {
+        auto const& m = *static_cast<BAPOMDPState const*>(p)->model();
+        for (int a = 0; a < A; ++a)
+        {
+            if (t_par) t_par[a] = 1u;
+            if (o_par) o_par[a] = 1u;
+            if (!counts) continue;
+            for (int s = 0; s < S; ++s)
+                for (int s2 = 0; s2 < S; ++s2) counts[k++] = m.phi(s, a, s2);
+            for (int s2 = 0; s2 < S; ++s2)
+                for (int o = 0; o < O; ++o) counts[k++] = m.psi(a, s2, o);
+        }
+        return;
+    }
+
+    auto m        = static_cast<FBAPOMDPState const*>(p)->model();
+    auto const FS = (int)h->feat_s.size(), FO = (int)h->feat_o.size();
+    IndexAction action(0);
+    for (int a = 0; a < A; ++a)
+    {
+        action.index(a);
+        for (int f = 0; f < FS; ++f)
+        {
+            auto const& node = m->transitionNode(&action, f);
+            if (t_par) t_par[a * FS + f] = maskOf(*node.parents());
+            if (counts)
+                for (auto v : node._cpts) counts[k++] = v;
+        }
+        for (int g = 0; g < FO; ++g)
+        {
+            auto const& node = m->observationNode(&action, g);
+            if (o_par) o_par[a * FO + g] = maskOf(*node.parents());
+            if (counts)
+                for (auto v : node._cpts) counts[k++] = v;
+        }
+    }
+}
+
+/**** importance sampling ****/
+// importance_sampling::update only (weights stay un-resampled); returns the step likelihood
+double ref_is_update(void* hv, int a, int o)
+{
+    auto h = static_cast<Handle*>(hv);
+    IndexAction act(a);
+    IndexObservation obs(o);
+    return beliefs::importance_sampling::update(h->is_belief->_filter, &act, &obs, *h->sim);
+}
+
+void ref_is_resample(void* hv)
+{
+    auto h = static_cast<Handle*>(hv);
+    beliefs::importance_sampling::resample(h->is_belief->_filter, *h->sim, h->is_belief->_n);
+}
+
+// the full Belief::updateEstimation of the given belief kind
+void ref_update_estimation(void* hv, int kind, int a, int o)
+{
+    auto h = static_cast<Handle*>(hv);
+    IndexAction act(a);
+    IndexObservation obs(o);
+    if (kind == F_IS) h->is_belief->updateEstimation(&act, &obs, *h->sim);
+    else if (kind == F_RS)
+        h->rs_belief->updateEstimation(&act, &obs, *h->sim);
+    else
+        h->reinv_belief->updateEstimation(&act, &obs, *h->sim);
+}
+
+void ref_reset_domain_states(void* hv, int kind)
+{
+    auto h = static_cast<Handle*>(hv);
+    if (kind == F_IS) h->is_belief->resetDomainStateDistribution(*h->sim);
+    else if (kind == F_RS)
+        h->rs_belief->resetDomainStateDistribution(*h->sim);
+    else
+        h->reinv_belief->resetDomainStateDistribution(*h->sim);
+}
+
+// reinvigorateParticles alone (ReinvigoratingRejectionSampling.cpp:121-131)
+void ref_reinvigorate_only(void* hv)
+{
+    auto h = static_cast<Handle*>(hv);
+    h->reinv_belief->reinvigorateParticles(*h->sim);
+}
+
+// the two rejectSample calls of ReinvigoratingRejectionSampling::updateEstimation (:100-101)
+void ref_reinv_reject_only(void* hv, int a, int o)
+{
+    auto h = static_cast<Handle*>(hv);
+    IndexAction act(a);
+    IndexObservation obs(o);
+    auto& b = *h->reinv_belief;
+    ::beliefs::rejectSample(&act, &obs, *h->sim, b._size, b._belief);
+    ::beliefs::rejectSample(&act, &obs, *h->sim, b._size, b._fully_connected_belief);
+}
+
+/**** one hyper-state step on particle i, in place (BAPOMDP::step, BAPOMDP.cpp:111-143) ****/
+// mode: 0 = UpdateCounts, 1 = KeepCounts. out[0] = new state, out[1] = observation, out[2] = terminal
+double ref_particle_step(void* hv, int filter, long i, int a, int mode, int* out)
+{
+    auto h = static_cast<Handle*>(hv);
+    IndexAction act(a);
+    State const* s = particleOf(h, filter, i);
+    Observation const* o(nullptr);
+    Reward r(0);
+    auto t = h->sim->step(
+        &s, &act, &o, &r, mode ? BAPOMDP::StepType::KeepCounts : BAPOMDP::StepType::UpdateCounts);
+    out[0] = static_cast<BAState const*>(s)->_domain_state->index();
+    out[1] = o->index();
+    out[2] = t.terminated();
+    h->sim->releaseObservation(o);
+    return r.toDouble();
+}
+
+double ref_particle_obs_prob(void* hv, int filter, long i, int a, int o)
+{
+    auto h = static_cast<Handle*>(hv);
+    IndexAction act(a);
+    IndexObservation obs(o);
+    return h->sim->computeObservationProbability(&obs, &act, particleOf(h, filter, i));
+}
+
+/**** rollouts (RBAPOUCT::rollout, RBAPOUCT.cpp:295-323) ****/
+// Mirrors what selectAction does around a simulation (RBAPOUCT.cpp:86-106): KeepCounts, the
+// particle is not copied, its domain state is set to start_state and restored afterwards.
+double ref_rollout(void* hv, int filter, long i, int start_state, int depth)
+{
+    auto h = static_cast<Handle*>(hv);
+    if (!h->planner) h->planner.reset(new planners::RBAPOUCT(h->conf));
+
+    auto particle  = particleOf(h, filter, i);
+    auto old_mode  = h->sim->mode();
+    auto old_state = particle->_domain_state;
+    h->sim->mode(BAPOMDP::StepType::KeepCounts);
+    const_cast<BAState*>(particle)->_domain_state =
+        h->sim->copyDomainState(h->sim->domainState(start_state));
+
+    auto ret = h->planner->rollout(particle, *h->sim, depth);
+
+    h->sim->releaseDomainState(particle->_domain_state);
+    const_cast<BAState*>(particle)->_domain_state = old_state;
+    h->sim->mode(old_mode);
+    return ret.toDouble();
+}
+
+/**** domain functors (BADomainExtension::{reward,terminal}) ****/
+double ref_reward(void* hv, int s, int a, int s2, int* terminal)
+{
+    auto h = static_cast<Handle*>(hv);
+    IndexAction act(a);
+    auto ext  = h->sim->_ba_domain_ext.get();
+    auto st   = ext->getState(s);
+    auto st2  = ext->getState(s2);
+    *terminal = ext->terminal(st, &act, st2).terminated();
+    return ext->reward(st, &act, st2).toDouble();
+}
+
+/**** domain description in this repo's vocabulary (see oracle/fba_oracle.h ORC_DOM_* etc.) ****/
+// out_i: [0] domain kind, [1] action draw kind, [2] start kind, [3..6] start_ip[4], [8..39] dom_ip[32]
+// out_d: [0..7] dom_dp, [8] start_total. start_values: float[S] (categorical), start_table: int[64]
+void ref_domain_desc(void* hv, int* out_i, double* out_d, float* start_values, int* start_table)
+{
+    auto h        = static_cast<Handle*>(hv);
+    auto const& d = h->conf.domain_conf.domain;
+    auto const S  = h->sim->domainSize()->_S;
+    int* ip       = out_i + 8;
+    for (int i = 0; i < 40; ++i) out_i[i] = 0;
+    for (int i = 0; i < 9; ++i) out_d[i] = 0;
+
+    if (d == "episodic-tiger" || d == "continuous-tiger")
+    {
+        out_i[0] = 1;
+        ip[0]    = (d == "episodic-tiger");
+        out_i[2] = 1; // boolean() ? LEFT : RIGHT (Tiger.cpp:18)
+        out_i[3] = 0;
+        out_i[4] = 1;
+    } else if (d == "episodic-factored-tiger" || d == "continuous-factored-tiger")
+    {
+        out_i[0] = 2;
+        ip[0]    = (d == "episodic-factored-tiger");
+        out_i[2] = 2; // uniform_int over S (FactoredTiger.cpp:74)
+        out_i[3] = S;
+    } else if (d == "linear-sysadmin" || d == "independent-sysadmin")
+    {
+        out_i[0] = 3;
+        ip[0]    = (int)h->conf.domain_conf.size;
+        out_d[0] = domains::SysAdmin::param._reboot_cost;
+        out_i[2] = 0; // constant: all computers up (SysAdmin.cpp:102-105)
+        out_i[3] = S - 1;
+    } else if (d == "gridworld")
+    {
+        out_i[0]   = 4;
+        out_i[1]   = 1; // slowRandomInt (GridWorld.cpp:223)
+        auto size  = (int)h->conf.domain_conf.size;
+        auto goals = domains::GridWorld::goalLocations(size);
+        ip[0]      = size;
+        ip[1]      = (int)goals.size();
+        for (size_t g = 0; g < goals.size(); ++g)
+        {
+            ip[2 + 2 * g] = goals[g].x;
+            ip[3 + 2 * g] = goals[g].y;
+        }
+        out_d[0] = domains::GridWorld::goal_reward;
+        out_d[1] = domains::GridWorld::step_reward;
+        out_i[2] = 3; // two slowRandomInt draws (GridWorld.cpp:265-267)
+        out_i[3] = (int)domains::GridWorld::start_locations.size();
+        out_i[4] = (int)goals.size();
+        auto gw  = dynamic_cast<domains::GridWorld const*>(h->env.get());
+        int k    = 0;
+        for (auto const& sl : domains::GridWorld::start_locations)
+            for (auto const& g : goals) start_table[k++] = gw->getState(sl, g)->index();
+    } else if (d == "centered-collision-avoidance" || d == "random-collision-avoidance")
+    {
+        out_i[0] = 5;
+        ip[0]    = (int)h->conf.domain_conf.width;
+        ip[1]    = (int)h->conf.domain_conf.height;
+        ip[2]    = (int)h->conf.domain_conf.size;
+        out_d[0] = domains::CollisionAvoidance::MOVE_PENALTY;
+        out_d[1] = domains::CollisionAvoidance::COLLIDE_PENALTY;
+        out_i[2] = 4; // categorical over S (CollisionAvoidance.cpp:274)
+        out_i[3] = S;
+        auto ca  = dynamic_cast<domains::CollisionAvoidance const*>(h->env.get());
+        for (int i = 0; i < S; ++i) start_values[i] = ca->_state_prior._values[i];
+        out_d[8] = ca->_state_prior._total;
+    } else
+    {
+        out_i[0] = -1;
+    }
+}
+
+/**** (a,o) script from the TRUE environment under a uniformly random policy ****/
+// Runs episodes of at most `horizon` steps until `steps` entries are filled.
+// flags[t] bit0 = terminal after step t, bit1 = first step of an episode.
+void ref_env_script(void* hv, int steps, int horizon, int* actions, int* observations, int* flags)
+{
+    auto h   = static_cast<Handle*>(hv);
+    auto env = h->env.get();
+    auto dom = dynamic_cast<POMDP const*>(env); // every domain here is a POMDP (test/test.cpp:72)
+    int t    = 0;
+    while (t < steps)
+    {
+        State const* s = env->sampleStartState();
+        bool terminal  = false;
+        for (int k = 0; k < horizon && !terminal && t < steps; ++k, ++t)
+        {
+            auto a = dom->generateRandomAction(s);
+            Observation const* o(nullptr);
+            Reward r(0);
+            terminal        = env->step(&s, a, &o, &r).terminated();
+            actions[t]      = a->index();
+            observations[t] = o->index();
+            flags[t]        = (terminal ? 1 : 0) | (k == 0 ? 2 : 0);
+            dom->releaseAction(a);
+            env->releaseObservation(o);
+        }
+        env->releaseState(s);
+    }
+}
+
+} // extern "C"
