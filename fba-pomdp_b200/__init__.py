@@ -1,0 +1,12 @@
+"""fba_pomdp_b200 — B200-native (sm_100a) particle-belief / rollout hot path of samkatt/fba-pomdp.
+
+The product is libfba_b200.so (hand-written CUDA kernels behind the C ABI in
+include/fba_pomdp_b200.h). This package is the thin host-side mirror of the reference's
+Belief / BABelief / rollout interfaces used by the tests and the benchmark."""
+from . import capi  # noqa: F401
+from .beliefs import (BAImportanceSampling, BAPOMDP, BARejectionSampling, Context,  # noqa: F401
+                      ReinvigoratingRejectionSampling, rollouts)
+from .capi import FbaError, Rng  # noqa: F401
+
+__all__ = ["capi", "Context", "BAPOMDP", "BAImportanceSampling", "BARejectionSampling",
+           "ReinvigoratingRejectionSampling", "rollouts", "Rng", "FbaError"]

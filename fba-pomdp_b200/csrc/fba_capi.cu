@@ -1,0 +1,1427 @@
+// Host side of the C ABI declared in include/fba_pomdp_b200.h: owns device memory, feeds the
+// replay stream, launches the kernels in fba_kernels.cuh. No CPU implementation of any operation
+// lives here: without a CUDA device fba_ctx_create fails with FBA_ERR_NO_DEVICE.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "fba_kernels.cuh"
+
+using namespace fba;
+
+// ------------------------------------------------------------------------------------------------
+// handles
+// ------------------------------------------------------------------------------------------------
+struct fba_ctx
+{
+    int device           = 0;
+    cudaStream_t stream  = nullptr;
+    int sm_count         = 148;
+    int64_t launches     = 0;
+    std::string err;
+    // scratch shared by the beliefs of this context
+    uint32_t* d_words    = nullptr;
+    size_t words_cap     = 0;
+    long long* d_offsets = nullptr;
+    size_t offsets_cap   = 0;
+    int* d_flag          = nullptr; // overrun flag
+    int* h_flag          = nullptr; // pinned
+    double* h_scal       = nullptr; // pinned, 4 doubles
+};
+
+struct fba_model
+{
+    fba_ctx* ctx = nullptr;
+    DevModel dev{};
+    int max_structs = 0, n_structs = 0;
+    std::vector<uint32_t> t_par, o_par; // host structure table
+    std::vector<int> sizes;
+    std::vector<Node> h_nodes;
+    std::map<std::string, int> index;
+    Node* d_nodes = nullptr;
+    int* d_sizes  = nullptr;
+    std::vector<void*> owned; // device copies of the descriptor's tables
+};
+
+struct fba_belief
+{
+    fba_ctx* ctx   = nullptr;
+    fba_model* m   = nullptr;
+    long long N    = 0, stride = 0;
+    bool weighted  = true;
+    float* counts[2] = {nullptr, nullptr};
+    int* state[2]    = {nullptr, nullptr};
+    int* sid[2]      = {nullptr, nullptr};
+    int cur          = 0;
+    double* w        = nullptr;
+    double* aux      = nullptr; // R (replay) or cdf (native), N doubles
+    double* tile     = nullptr; // tile sums
+    double* scal     = nullptr; // device scalars: [0] total, [1] total_weight
+    int* anc         = nullptr; // ancestors, max(N, attempts wave)
+    double total_weight = 1.0;  // WeightedFilter::_total_weight (host mirror)
+    double uniform_total = -1;  // sequential sum of N x (1/N), computed on first use
+    bool suffix_valid = false;  // aux holds R for the current weights
+    bool cdf_valid    = false;  // aux holds the native cdf for the current weights
+    // rejection sampling wave buffers
+    long long wave_cap = 0;
+    int *att_src = nullptr, *att_state = nullptr, *att_accept = nullptr, *att_pos = nullptr,
+        *att_rec = nullptr, *d_total = nullptr;
+    // multi-GPU staging
+    char* xport = nullptr;
+    long long xport_cap = 0, xport_count = 0;
+    char* import_buf = nullptr;
+    long long import_cap = 0;
+    long long local_kept = 0;
+};
+
+#define CU(ctx, call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+        {                                                                                          \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                       \
+            return FBA_ERR_CUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+
+#define REQUIRE(ctx, cond, msg)                                                                    \
+    do {                                                                                           \
+        if (!(cond))                                                                               \
+        {                                                                                          \
+            (ctx)->err = (msg);                                                                    \
+            return FBA_ERR_INVALID;                                                                \
+        }                                                                                          \
+    } while (0)
+
+static inline int blocks_for(long long n, int per_block = kThreads)
+{
+    return (int)std::max<long long>(1, (n + per_block - 1) / per_block);
+}
+
+// grid for warp-per-particle streaming kernels: enough CTAs to fill every SM several times over,
+// capped so each warp loops (grid = multiple of the SM count)
+static inline int stream_grid(const fba_ctx* ctx, long long n_particles)
+{
+    long long const need = (n_particles + (kThreads / 32) - 1) / (kThreads / 32);
+    long long const cap  = (long long)ctx->sm_count * 8;
+    return (int)std::max<long long>(1, std::min(need, cap));
+}
+
+#define LAUNCH(ctx, kernel, grid, block, ...)                                                      \
+    do {                                                                                           \
+        kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__);                                \
+        ++(ctx)->launches;                                                                         \
+        CU(ctx, cudaGetLastError());                                                               \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+extern "C" int fba_ctx_create(int device, fba_ctx** out)
+{
+    if (!out) return FBA_ERR_INVALID;
+    *out      = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return FBA_ERR_NO_DEVICE;
+    if (device < 0 || device >= count) return FBA_ERR_INVALID;
+    auto ctx    = new fba_ctx();
+    ctx->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_flag, sizeof(int));
+    if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_flag, sizeof(int));
+    if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_scal, 4 * sizeof(double));
+    if (e != cudaSuccess)
+    {
+        delete ctx;
+        return FBA_ERR_CUDA;
+    }
+    *out = ctx;
+    return FBA_OK;
+}
+
+extern "C" void fba_ctx_destroy(fba_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_words);
+    cudaFree(ctx->d_offsets);
+    cudaFree(ctx->d_flag);
+    cudaFreeHost(ctx->h_flag);
+    cudaFreeHost(ctx->h_scal);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char* fba_last_error(const fba_ctx* ctx)
+{
+    return ctx ? ctx->err.c_str() : "no context";
+}
+extern "C" void* fba_ctx_stream(const fba_ctx* ctx)
+{
+    return (void*)ctx->stream;
+}
+extern "C" int fba_ctx_synchronize(fba_ctx* ctx)
+{
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return FBA_OK;
+}
+extern "C" int64_t fba_ctx_launch_count(const fba_ctx* ctx)
+{
+    return ctx->launches;
+}
+
+// upload words[first, first+n) of the replay stream into the context scratch
+static int stage_words(fba_ctx* ctx, const fba_rng* rng, long long n)
+{
+    if (rng->cursor < 0 || rng->cursor + n > rng->n_words)
+    {
+        ctx->err = "replay stream underrun: need " + std::to_string(n) + " words at cursor "
+                   + std::to_string(rng->cursor) + " of " + std::to_string(rng->n_words);
+        return FBA_ERR_RNG_UNDERRUN;
+    }
+    if ((size_t)n > ctx->words_cap)
+    {
+        cudaFree(ctx->d_words);
+        ctx->words_cap = (size_t)n + (size_t)n / 2 + 1024;
+        CU(ctx, cudaMalloc(&ctx->d_words, ctx->words_cap * sizeof(uint32_t)));
+    }
+    if (n)
+        CU(ctx, cudaMemcpyAsync(ctx->d_words, rng->words + rng->cursor, (size_t)n * sizeof(uint32_t),
+                                cudaMemcpyHostToDevice, ctx->stream));
+    return FBA_OK;
+}
+
+static int stage_offsets(fba_ctx* ctx, const std::vector<long long>& off)
+{
+    if (off.size() > ctx->offsets_cap)
+    {
+        cudaFree(ctx->d_offsets);
+        ctx->offsets_cap = off.size() + off.size() / 2 + 1024;
+        CU(ctx, cudaMalloc(&ctx->d_offsets, ctx->offsets_cap * sizeof(long long)));
+    }
+    // pageable source: the copy is staged before the call returns, so `off` may die afterwards
+    CU(ctx, cudaMemcpyAsync(ctx->d_offsets, off.data(), off.size() * sizeof(long long),
+                            cudaMemcpyHostToDevice, ctx->stream));
+    return FBA_OK;
+}
+
+static int clear_flag(fba_ctx* ctx)
+{
+    CU(ctx, cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+    return FBA_OK;
+}
+
+static int check_flag(fba_ctx* ctx)
+{
+    CU(ctx, cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (*ctx->h_flag)
+    {
+        ctx->err = "replay stream underrun on device";
+        return FBA_ERR_RNG_UNDERRUN;
+    }
+    return FBA_OK;
+}
+
+static RngArgs replay_args(fba_ctx* ctx, long long n_words, long long per_item, bool use_offsets)
+{
+    RngArgs ra{};
+    ra.words          = ctx->d_words;
+    ra.n_words        = n_words;
+    ra.offsets        = use_offsets ? ctx->d_offsets : nullptr;
+    ra.words_per_item = per_item;
+    return ra;
+}
+
+static RngArgs philox_args(fba_rng* rng, unsigned long long stream_base = 0)
+{
+    RngArgs ra{};
+    ra.seed        = rng->seed;
+    ra.offset      = rng->offset++;
+    ra.stream_base = stream_base;
+    return ra;
+}
+
+// ------------------------------------------------------------------------------------------------
+// model
+// ------------------------------------------------------------------------------------------------
+template<class T>
+static int to_device(fba_model* m, const T* host, size_t n, const T** out)
+{
+    *out = nullptr;
+    if (!host || !n) return FBA_OK;
+    T* d = nullptr;
+    CU(m->ctx, cudaMalloc(&d, n * sizeof(T)));
+    CU(m->ctx, cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice));
+    m->owned.push_back(d);
+    *out = d;
+    return FBA_OK;
+}
+
+extern "C" int fba_model_create(fba_ctx* ctx, const fba_model_desc* d, int32_t max_structures,
+                                fba_model** out)
+{
+    if (!ctx || !d || !out) return FBA_ERR_INVALID;
+    *out = nullptr;
+    CU(ctx, cudaSetDevice(ctx->device));
+    REQUIRE(ctx, d->S > 0 && d->A > 0 && d->O > 0, "model: S, A and O must be positive");
+    REQUIRE(ctx, d->n_state_features >= 1 && d->n_state_features <= FBA_MAX_FEATURES
+                     && d->n_obs_features >= 1 && d->n_obs_features <= FBA_MAX_FEATURES,
+            "model: feature counts must be in [1, 16]");
+    REQUIRE(ctx, max_structures >= 1, "model: max_structures must be >= 1");
+    long long ps = 1, po = 1;
+    for (int f = 0; f < d->n_state_features; ++f)
+    {
+        REQUIRE(ctx, d->state_feature_sizes[f] >= 1, "model: state feature size < 1");
+        REQUIRE(ctx, d->n_state_features == 1 || d->state_feature_sizes[f] <= 256,
+                "model: with several state features each must have <= 256 values");
+        ps *= d->state_feature_sizes[f];
+    }
+    for (int f = 0; f < d->n_obs_features; ++f)
+    {
+        REQUIRE(ctx, d->obs_feature_sizes[f] >= 1, "model: observation feature size < 1");
+        REQUIRE(ctx, d->n_obs_features == 1 || d->obs_feature_sizes[f] <= 256,
+                "model: with several observation features each must have <= 256 values");
+        po *= d->obs_feature_sizes[f];
+    }
+    REQUIRE(ctx, ps == d->S && po == d->O, "model: feature sizes do not multiply to S / O");
+    REQUIRE(ctx, !d->tabular || (d->n_state_features == 1 && d->n_obs_features == 1),
+            "model: tabular models have exactly one state and one observation feature");
+
+    auto m         = new fba_model();
+    m->ctx         = ctx;
+    m->max_structs = max_structures;
+    DevModel& D    = m->dev;
+    D.S = d->S, D.A = d->A, D.O = d->O;
+    D.FS = d->n_state_features, D.FO = d->n_obs_features, D.J = D.FS + D.FO;
+    for (int f = 0; f < D.FS; ++f) D.feat_s[f] = d->state_feature_sizes[f];
+    for (int f = 0; f < D.FO; ++f) D.feat_o[f] = d->obs_feature_sizes[f];
+    D.step_s[D.FS - 1] = 1;
+    for (int f = D.FS - 2; f >= 0; --f) D.step_s[f] = D.step_s[f + 1] * D.feat_s[f + 1];
+    D.step_o[D.FO - 1] = 1;
+    for (int f = D.FO - 2; f >= 0; --f) D.step_o[f] = D.step_o[f + 1] * D.feat_o[f + 1];
+    D.tabular = d->tabular, D.domain = d->domain, D.action_draw = d->action_draw;
+    memcpy(D.dom_ip, d->dom_ip, sizeof(D.dom_ip));
+    memcpy(D.dom_dp, d->dom_dp, sizeof(D.dom_dp));
+    D.start_kind = d->start_kind;
+    memcpy(D.start_ip, d->start_ip, sizeof(D.start_ip));
+    D.start_total = d->start_total;
+
+    int rc = FBA_OK;
+    if (d->domain == FBA_DOM_TABLE)
+    {
+        if (!rc) rc = to_device(m, d->rew_sa, (size_t)d->S * d->A, &D.rew_sa);
+        if (!rc) rc = to_device(m, d->rew_as2, (size_t)d->S * d->A, &D.rew_as2);
+        if (!rc) rc = to_device(m, d->term_sa, (size_t)d->S * d->A, &D.term_sa);
+        if (!rc) rc = to_device(m, d->term_as2, (size_t)d->S * d->A, &D.term_as2);
+    }
+    if (!rc && d->start_kind == FBA_START_CATEGORICAL)
+    {
+        if (!d->start_values) ctx->err = "model: categorical start needs start_values", rc = FBA_ERR_INVALID;
+        else
+            rc = to_device(m, d->start_values, (size_t)d->start_ip[0], &D.start_values);
+    }
+    if (!rc && d->start_kind == FBA_START_SLOW2)
+    {
+        if (!d->start_table) ctx->err = "model: slow2 start needs start_table", rc = FBA_ERR_INVALID;
+        else
+            rc = to_device(m, d->start_table, (size_t)d->start_ip[0] * d->start_ip[1], &D.start_table);
+    }
+    if (!rc)
+    {
+        size_t const nn = (size_t)max_structures * D.A * D.J;
+        m->h_nodes.resize(nn);
+        cudaError_t e = cudaMalloc(&m->d_nodes, nn * sizeof(Node));
+        if (e == cudaSuccess) e = cudaMalloc(&m->d_sizes, (size_t)max_structures * sizeof(int));
+        if (e == cudaSuccess) e = cudaMemset(m->d_sizes, 0, (size_t)max_structures * sizeof(int));
+        if (e != cudaSuccess) ctx->err = std::string("model alloc: ") + cudaGetErrorString(e), rc = FBA_ERR_CUDA;
+        D.nodes       = m->d_nodes;
+        D.struct_size = m->d_sizes;
+    }
+    if (rc)
+    {
+        fba_model_destroy(m);
+        return rc;
+    }
+    *out = m;
+    return FBA_OK;
+}
+
+extern "C" void fba_model_destroy(fba_model* m)
+{
+    if (!m) return;
+    cudaSetDevice(m->ctx->device);
+    for (auto p : m->owned) cudaFree(p);
+    cudaFree(m->d_nodes);
+    cudaFree(m->d_sizes);
+    delete m;
+}
+
+extern "C" int fba_model_add_structures(fba_model* m, int32_t n, const uint32_t* t_par,
+                                        const uint32_t* o_par, int32_t* ids_out)
+{
+    if (!m || !t_par || !o_par || n < 0) return FBA_ERR_INVALID;
+    fba_ctx* ctx      = m->ctx;
+    DevModel const& D = m->dev;
+    CU(ctx, cudaSetDevice(ctx->device));
+    int const nT = D.A * D.FS, nO = D.A * D.FO;
+    int const first_new = m->n_structs;
+    uint32_t const full = (D.FS >= 32) ? 0xffffffffu : ((1u << D.FS) - 1u);
+    for (int k = 0; k < n; ++k)
+    {
+        const uint32_t* tp = t_par + (size_t)k * nT;
+        const uint32_t* op = o_par + (size_t)k * nO;
+        std::string key((const char*)tp, nT * sizeof(uint32_t));
+        key.append((const char*)op, nO * sizeof(uint32_t));
+        auto it = m->index.find(key);
+        int id;
+        if (it != m->index.end()) id = it->second;
+        else
+        {
+            if (m->n_structs >= m->max_structs)
+            {
+                ctx->err = "structure table full (" + std::to_string(m->max_structs) + ")";
+                return FBA_ERR_CAPACITY;
+            }
+            id = m->n_structs++;
+            m->index[key] = id;
+            m->t_par.insert(m->t_par.end(), tp, tp + nT);
+            m->o_par.insert(m->o_par.end(), op, op + nO);
+            long long off = 0;
+            Node* nodes   = m->h_nodes.data() + (size_t)id * D.A * D.J;
+            for (int a = 0; a < D.A; ++a)
+                for (int j = 0; j < D.J; ++j)
+                {
+                    uint32_t const par = (j < D.FS) ? tp[a * D.FS + j] : op[a * D.FO + (j - D.FS)];
+                    REQUIRE(ctx, (par & ~full) == 0, "structure: parent mask names a missing feature");
+                    long long cfgs = 1;
+                    for (int f = 0; f < D.FS; ++f)
+                        if (par & (1u << f)) cfgs *= D.feat_s[f];
+                    int const range       = (j < D.FS) ? D.feat_s[j] : D.feat_o[j - D.FS];
+                    nodes[a * D.J + j].par = par;
+                    nodes[a * D.J + j].off = (int32_t)off;
+                    off += cfgs * range;
+                    REQUIRE(ctx, off < (1ll << 31), "structure: count block exceeds 2^31 cells");
+                }
+            m->sizes.push_back((int)off);
+        }
+        if (ids_out) ids_out[k] = id;
+    }
+    if (m->n_structs > first_new)
+    {
+        size_t const per = (size_t)D.A * D.J;
+        CU(ctx, cudaMemcpy(m->d_nodes + first_new * per, m->h_nodes.data() + first_new * per,
+                           (m->n_structs - first_new) * per * sizeof(Node), cudaMemcpyHostToDevice));
+        CU(ctx, cudaMemcpy(m->d_sizes + first_new, m->sizes.data() + first_new,
+                           (m->n_structs - first_new) * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    return FBA_OK;
+}
+
+extern "C" int32_t fba_model_num_structures(const fba_model* m)
+{
+    return m ? m->n_structs : 0;
+}
+extern "C" int64_t fba_model_structure_size(const fba_model* m, int32_t id)
+{
+    return (m && id >= 0 && id < m->n_structs) ? m->sizes[id] : -1;
+}
+extern "C" int fba_model_get_structure(const fba_model* m, int32_t id, uint32_t* t_par, uint32_t* o_par)
+{
+    if (!m || id < 0 || id >= m->n_structs) return FBA_ERR_INVALID;
+    int const nT = m->dev.A * m->dev.FS, nO = m->dev.A * m->dev.FO;
+    if (t_par) memcpy(t_par, m->t_par.data() + (size_t)id * nT, nT * sizeof(uint32_t));
+    if (o_par) memcpy(o_par, m->o_par.data() + (size_t)id * nO, nO * sizeof(uint32_t));
+    return FBA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// belief
+// ------------------------------------------------------------------------------------------------
+extern "C" int fba_belief_create(fba_ctx* ctx, fba_model* m, int64_t N, int64_t stride, int32_t weighted,
+                                 fba_belief** out)
+{
+    if (!ctx || !m || !out) return FBA_ERR_INVALID;
+    *out = nullptr;
+    // the reference's belief constructors throw on n < 1 (BAImportanceSampling.cpp:19-29)
+    REQUIRE(ctx, N >= 1, "cannot initiate belief with n " + std::to_string(N));
+    REQUIRE(ctx, N < (1ll << 31), "belief: at most 2^31-1 particles per GPU");
+    REQUIRE(ctx, m->n_structs >= 1, "belief: register at least one structure first");
+    long long need = 0;
+    for (int s : m->sizes) need = std::max<long long>(need, s);
+    if (stride <= 0) stride = need;
+    stride = (stride + 3) & ~3ll;
+    REQUIRE(ctx, stride >= need, "belief: stride smaller than the largest registered structure");
+    CU(ctx, cudaSetDevice(ctx->device));
+
+    auto b      = new fba_belief();
+    b->ctx      = ctx;
+    b->m        = m;
+    b->N        = N;
+    b->stride   = stride;
+    b->weighted = weighted != 0;
+    cudaError_t e = cudaSuccess;
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k)
+    {
+        e = cudaMalloc(&b->counts[k], (size_t)N * stride * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&b->state[k], (size_t)N * sizeof(int));
+        if (e == cudaSuccess) e = cudaMalloc(&b->sid[k], (size_t)N * sizeof(int));
+    }
+    long long const n_tiles = (N + kTile - 1) / kTile;
+    if (e == cudaSuccess) e = cudaMalloc(&b->w, (size_t)N * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&b->aux, (size_t)N * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&b->tile, (size_t)n_tiles * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&b->scal, 4 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&b->anc, (size_t)N * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_total, sizeof(int));
+    if (e != cudaSuccess)
+    {
+        ctx->err = std::string("belief alloc: ") + cudaGetErrorString(e);
+        fba_belief_destroy(b);
+        return FBA_ERR_CUDA;
+    }
+    *out = b;
+    return FBA_OK;
+}
+
+extern "C" void fba_belief_destroy(fba_belief* b)
+{
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->stream);
+    for (int k = 0; k < 2; ++k)
+    {
+        cudaFree(b->counts[k]);
+        cudaFree(b->state[k]);
+        cudaFree(b->sid[k]);
+    }
+    cudaFree(b->w), cudaFree(b->aux), cudaFree(b->tile), cudaFree(b->scal), cudaFree(b->anc);
+    cudaFree(b->att_src), cudaFree(b->att_state), cudaFree(b->att_accept), cudaFree(b->att_pos);
+    cudaFree(b->att_rec), cudaFree(b->d_total), cudaFree(b->xport), cudaFree(b->import_buf);
+    delete b;
+}
+
+extern "C" int64_t fba_belief_size(const fba_belief* b)
+{
+    return b ? b->N : 0;
+}
+extern "C" int64_t fba_belief_stride(const fba_belief* b)
+{
+    return b ? b->stride : 0;
+}
+extern "C" void* fba_belief_counts_ptr(fba_belief* b)
+{
+    return b->counts[b->cur];
+}
+extern "C" void* fba_belief_state_ptr(fba_belief* b)
+{
+    return b->state[b->cur];
+}
+extern "C" void* fba_belief_weight_ptr(fba_belief* b)
+{
+    return b->w;
+}
+
+// WeightedFilter::_total_weight after N x add(s, 1/N) (WeightedFilter.cpp:60-66): data independent
+static double uniform_total(fba_belief* b)
+{
+    if (b->uniform_total < 0)
+    {
+        double const w = 1.0 / (double)b->N;
+        volatile double acc = 0.0; // volatile: keep the sequential, separately rounded adds
+        for (long long i = 0; i < b->N; ++i) acc = acc + w;
+        b->uniform_total = acc;
+    }
+    return b->uniform_total;
+}
+
+static void weights_became_uniform(fba_belief* b)
+{
+    b->total_weight = uniform_total(b);
+    b->suffix_valid = false;
+    b->cdf_valid    = false;
+}
+
+extern "C" int fba_belief_init(fba_belief* b, int32_t n_protos, const int32_t* proto_struct_id,
+                               const float* proto_counts, const int32_t* particle_proto,
+                               const int32_t* particle_state)
+{
+    if (!b) return FBA_ERR_INVALID;
+    fba_ctx* ctx = b->ctx;
+    REQUIRE(ctx, n_protos >= 1 && proto_struct_id && proto_counts && particle_state,
+            "belief_init: prototypes and particle states are required");
+    for (int p = 0; p < n_protos; ++p)
+        REQUIRE(ctx, proto_struct_id[p] >= 0 && proto_struct_id[p] < b->m->n_structs,
+                "belief_init: unknown structure id");
+    CU(ctx, cudaSetDevice(ctx->device));
+    float* d_protos = nullptr;
+    int *d_psid = nullptr, *d_pp = nullptr, *d_ps = nullptr;
+    size_t const pc = (size_t)n_protos * b->stride;
+    CU(ctx, cudaMalloc(&d_protos, pc * sizeof(float)));
+    CU(ctx, cudaMalloc(&d_psid, n_protos * sizeof(int)));
+    CU(ctx, cudaMalloc(&d_ps, (size_t)b->N * sizeof(int)));
+    CU(ctx, cudaMemcpyAsync(d_protos, proto_counts, pc * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(d_psid, proto_struct_id, n_protos * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(d_ps, particle_state, (size_t)b->N * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    if (particle_proto)
+    {
+        CU(ctx, cudaMalloc(&d_pp, (size_t)b->N * sizeof(int)));
+        CU(ctx, cudaMemcpyAsync(d_pp, particle_proto, (size_t)b->N * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    LAUNCH(ctx, k_init_from_protos, stream_grid(ctx, b->N), kThreads, b->counts[b->cur], b->stride,
+           b->state[b->cur], b->sid[b->cur], b->weighted ? b->w : nullptr, b->N, d_protos, d_psid, d_pp,
+           d_ps);
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_protos), cudaFree(d_psid), cudaFree(d_pp), cudaFree(d_ps);
+    weights_became_uniform(b);
+    return FBA_OK;
+}
+
+extern "C" int fba_belief_init_sampled(fba_belief* b, int32_t n_protos, const int32_t* proto_struct_id,
+                                       const float* proto_counts, const double* proto_probs, fba_rng* rng)
+{
+    if (!b || !rng) return FBA_ERR_INVALID;
+    fba_ctx* ctx = b->ctx;
+    REQUIRE(ctx, rng->mode == FBA_RNG_PHILOX, "belief_init_sampled: PHILOX mode only");
+    REQUIRE(ctx, n_protos >= 1 && proto_struct_id && proto_counts, "belief_init_sampled: prototypes required");
+    CU(ctx, cudaSetDevice(ctx->device));
+    float* d_protos = nullptr;
+    int *d_psid = nullptr, *d_pp = nullptr, *d_ps = nullptr;
+    double* d_cdf   = nullptr;
+    size_t const pc = (size_t)n_protos * b->stride;
+    CU(ctx, cudaMalloc(&d_protos, pc * sizeof(float)));
+    CU(ctx, cudaMalloc(&d_psid, n_protos * sizeof(int)));
+    CU(ctx, cudaMalloc(&d_pp, (size_t)b->N * sizeof(int)));
+    CU(ctx, cudaMalloc(&d_ps, (size_t)b->N * sizeof(int)));
+    CU(ctx, cudaMemcpyAsync(d_protos, proto_counts, pc * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(d_psid, proto_struct_id, n_protos * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<double> cdf;
+    if (proto_probs)
+    {
+        double acc = 0, tot = 0;
+        for (int p = 0; p < n_protos; ++p) tot += proto_probs[p];
+        for (int p = 0; p < n_protos; ++p) cdf.push_back((acc += proto_probs[p]) / tot);
+        CU(ctx, cudaMalloc(&d_cdf, n_protos * sizeof(double)));
+        CU(ctx, cudaMemcpyAsync(d_cdf, cdf.data(), n_protos * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    LAUNCH(ctx, k_draw_init<false>, blocks_for(b->N), kThreads, b->m->dev, b->N, n_protos, d_cdf, d_pp,
+           d_ps, philox_args(rng));
+    LAUNCH(ctx, k_init_from_protos, stream_grid(ctx, b->N), kThreads, b->counts[b->cur], b->stride,
+           b->state[b->cur], b->sid[b->cur], b->weighted ? b->w : nullptr, b->N, d_protos, d_psid, d_pp,
+           d_ps);
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_protos), cudaFree(d_psid), cudaFree(d_pp), cudaFree(d_ps), cudaFree(d_cdf);
+    b->total_weight = 1.0;
+    b->suffix_valid = b->cdf_valid = false;
+    return FBA_OK;
+}
+
+extern "C" int fba_belief_upload(fba_belief* b, int64_t first, int64_t count, const int32_t* state,
+                                 const int32_t* struct_id, const float* counts, const double* w)
+{
+    if (!b) return FBA_ERR_INVALID;
+    fba_ctx* ctx = b->ctx;
+    REQUIRE(ctx, first >= 0 && count >= 0 && first + count <= b->N, "belief_upload: range out of bounds");
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (state)
+        CU(ctx, cudaMemcpyAsync(b->state[b->cur] + first, state, count * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    if (struct_id)
+    {
+        for (int64_t i = 0; i < count; ++i)
+            REQUIRE(ctx, struct_id[i] >= 0 && struct_id[i] < b->m->n_structs, "belief_upload: unknown structure id");
+        CU(ctx, cudaMemcpyAsync(b->sid[b->cur] + first, struct_id, count * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (counts)
+        CU(ctx, cudaMemcpyAsync(b->counts[b->cur] + first * b->stride, counts,
+                                (size_t)count * b->stride * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    if (w && b->weighted)
+    {
+        CU(ctx, cudaMemcpyAsync(b->w + first, w, count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        b->suffix_valid = b->cdf_valid = false;
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return FBA_OK;
+}
+
+extern "C" int fba_belief_download(fba_belief* b, int64_t first, int64_t count, int32_t* state,
+                                   int32_t* struct_id, float* counts, double* w)
+{
+    if (!b) return FBA_ERR_INVALID;
+    fba_ctx* ctx = b->ctx;
+    REQUIRE(ctx, first >= 0 && count >= 0 && first + count <= b->N, "belief_download: range out of bounds");
+    CU(ctx, cudaSetDevice(ctx->device));
+    std::vector<int> sid_tmp;
+    int* sid_host = struct_id;
+    if (counts && !sid_host)
+    {
+        sid_tmp.resize(count);
+        sid_host = sid_tmp.data();
+    }
+    if (state)
+        CU(ctx, cudaMemcpyAsync(state, b->state[b->cur] + first, count * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (sid_host)
+        CU(ctx, cudaMemcpyAsync(sid_host, b->sid[b->cur] + first, count * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (counts)
+        CU(ctx, cudaMemcpyAsync(counts, b->counts[b->cur] + first * b->stride,
+                                (size_t)count * b->stride * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (w && b->weighted)
+        CU(ctx, cudaMemcpyAsync(w, b->w + first, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (counts)
+    { // cells past a particle's own structure are padding: report zeros (copies skip them)
+        for (int64_t i = 0; i < count; ++i)
+        {
+            long long const used = b->m->sizes[sid_host[i]];
+            if (used < b->stride)
+                memset(counts + i * b->stride + used, 0, (size_t)(b->stride - used) * sizeof(float));
+        }
+    }
+    return FBA_OK;
+}
+
+extern "C" int fba_belief_total_weight(fba_belief* b, double* total)
+{
+    if (!b || !total) return FBA_ERR_INVALID;
+    *total = b->total_weight;
+    return FBA_OK;
+}
+
+// ---- importance sampling ---------------------------------------------------------------------
+
+static int propose(fba_belief* b, int a, int o, fba_rng* rng, unsigned long long stream_base)
+{
+    fba_ctx* ctx      = b->ctx;
+    DevModel const& D = b->m->dev;
+    REQUIRE(ctx, b->weighted, "importance sampling needs a weighted belief");
+    REQUIRE(ctx, a >= 0 && a < D.A, "action out of range");
+    REQUIRE(ctx, o >= 0 && o < D.O, "observation out of range");
+    CU(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if (rng->mode == FBA_RNG_REPLAY)
+    {
+        // particle-major: particle i consumes J uniforms = 2J words (SURVEY.md §8 a')
+        long long const per = 2ll * D.J, need = per * b->N;
+        if ((rc = stage_words(ctx, rng, need))) return rc;
+        if ((rc = clear_flag(ctx))) return rc;
+        LAUNCH(ctx, k_propose<true>, blocks_for(b->N), kThreads, D, b->counts[b->cur], b->stride,
+               b->state[b->cur], b->sid[b->cur], b->w, b->N, a, o, replay_args(ctx, need, per, false),
+               ctx->d_flag);
+        rng->cursor += need;
+    } else
+    {
+        LAUNCH(ctx, k_propose<false>, blocks_for(b->N), kThreads, D, b->counts[b->cur], b->stride,
+               b->state[b->cur], b->sid[b->cur], b->w, b->N, a, o, philox_args(rng, stream_base),
+               ctx->d_flag);
+    }
+    b->suffix_valid = b->cdf_valid = false;
+    return FBA_OK;
+}
+
+// native: tile sums -> scan -> (divide, cdf). Leaves the cdf of the normalised weights in aux.
+static int native_normalize(fba_belief* b, bool use_device_total, double divide_by)
+{
+    fba_ctx* ctx      = b->ctx;
+    int const n_tiles = (int)((b->N + kTile - 1) / kTile);
+    LAUNCH(ctx, k_tile_sums, n_tiles, kThreads, b->w, b->N, b->tile);
+    LAUNCH(ctx, k_scan_tile_sums, 1, kThreads, b->tile, n_tiles, b->scal);
+    LAUNCH(ctx, k_scale_and_scan, n_tiles, kThreads, b->w, b->N, b->tile, b->scal, divide_by,
+           use_device_total ? 1 : 0, b->aux);
+    b->cdf_valid    = true;
+    b->suffix_valid = false;
+    return FBA_OK;
+}
+
+static int read_scal(fba_belief* b)
+{
+    fba_ctx* ctx = b->ctx;
+    CU(ctx, cudaMemcpyAsync(ctx->h_scal, b->scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return FBA_OK;
+}
+
+extern "C" int fba_belief_update(fba_belief* b, int32_t a, int32_t o, fba_rng* rng, double* likelihood)
+{
+    if (!b || !rng) return FBA_ERR_INVALID;
+    fba_ctx* ctx = b->ctx;
+    int rc       = propose(b, a, o, rng, 0);
+    if (rc) return rc;
+    if (rng->mode == FBA_RNG_REPLAY)
+    {
+        LAUNCH(ctx, k_seq_normalize, 1, kThreads, b->w, b->N, b->scal, b->aux, 1);
+        if ((rc = read_scal(b))) return rc;
+        if ((rc = check_flag(ctx))) return rc;
+        b->total_weight = ctx->h_scal[1];
+        b->suffix_valid = true;
+        if (likelihood) *likelihood = ctx->h_scal[0];
+    } else
+    {
+        if ((rc = native_normalize(b, true, 1.0))) return rc;
+        b->total_weight = 1.0;
+        if (likelihood)
+        {
+            if ((rc = read_scal(b))) return rc;
+            *likelihood = ctx->h_scal[0];
+        }
+    }
+    return FBA_OK;
+}
+
+static void flip(fba_belief* b)
+{
+    b->cur ^= 1;
+}
+
+// pick N ancestors from the current weights into b->anc
+static int pick_ancestors(fba_belief* b, fba_rng* rng, long long n_out, long long words_per_item,
+                          bool use_offsets, long long n_words)
+{
+    fba_ctx* ctx = b->ctx;
+    int rc;
+    if (rng->mode == FBA_RNG_REPLAY)
+    {
+        if (!b->suffix_valid)
+        { // R for the current weights (e.g. uniform after a resample): chain C only
+            double const tw = b->total_weight;
+            CU(ctx, cudaMemcpyAsync(b->scal + 1, &tw, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            CU(ctx, cudaStreamSynchronize(ctx->stream));
+            LAUNCH(ctx, k_seq_normalize, 1, kThreads, b->w, b->N, b->scal, b->aux, 0);
+            b->suffix_valid = true;
+            b->cdf_valid    = false;
+        }
+        if ((rc = clear_flag(ctx))) return rc;
+        LAUNCH(ctx, k_pick_replay, blocks_for(n_out), kThreads, b->aux, b->N, b->scal,
+               replay_args(ctx, n_words, words_per_item, use_offsets), b->anc, n_out, ctx->d_flag);
+    } else
+    {
+        if (!b->cdf_valid)
+            if ((rc = native_normalize(b, false, 1.0))) return rc;
+        LAUNCH(ctx, k_pick_native, blocks_for(n_out), kThreads, b->aux, b->N, n_out, 1, philox_args(rng), b->anc);
+    }
+    return FBA_OK;
+}
+
+static int gather_into_next(fba_belief* b, long long n_out, bool copy_state)
+{
+    fba_ctx* ctx = b->ctx;
+    int const nx = b->cur ^ 1;
+    LAUNCH(ctx, k_gather, stream_grid(ctx, n_out), kThreads, b->counts[b->cur], b->counts[nx], b->stride,
+           b->state[b->cur], copy_state ? b->state[nx] : nullptr, b->sid[b->cur], b->sid[nx],
+           b->m->d_sizes, b->weighted ? b->w : nullptr, 1.0 / (double)b->N, b->anc, n_out);
+    return FBA_OK;
+}
+
+extern "C" int fba_belief_resample(fba_belief* b, fba_rng* rng)
+{
+    if (!b || !rng) return FBA_ERR_INVALID;
+    fba_ctx* ctx = b->ctx;
+    REQUIRE(ctx, b->weighted, "resample needs a weighted belief");
+    CU(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if (rng->mode == FBA_RNG_REPLAY)
+    {
+        long long const need = 2 * b->N; // N draws of one uniform (ImportanceSampler.hpp:79-82)
+        if ((rc = stage_words(ctx, rng, need))) return rc;
+        if ((rc = pick_ancestors(b, rng, b->N, 2, false, need))) return rc;
+        rng->cursor += need;
+    } else if ((rc = pick_ancestors(b, rng, b->N, 0, false, 0)))
+        return rc;
+    if ((rc = gather_into_next(b, b->N, true))) return rc;
+    flip(b);
+    if (rng->mode == FBA_RNG_REPLAY)
+    {
+        if ((rc = check_flag(ctx))) return rc;
+        weights_became_uniform(b);
+    } else
+    {
+        b->total_weight = 1.0;
+        b->suffix_valid = b->cdf_valid = false;
+    }
+    return FBA_OK;
+}
+
+extern "C" int fba_belief_update_estimation(fba_belief* b, int32_t a, int32_t o, fba_rng* rng, double* likelihood)
+{
+    int rc = fba_belief_update(b, a, o, rng, likelihood);
+    if (rc) return rc;
+    return fba_belief_resample(b, rng);
+}
+
+// words one sampleStartState consumes at stream position `pos` (host-side scan of the replay stream)
+static long long start_state_words(const DevModel& D, const fba_rng* rng, long long pos)
+{
+    switch (D.start_kind)
+    {
+        case FBA_START_CONST: return 0;
+        case FBA_START_BOOL: return 2;
+        case FBA_START_UNIFORM_INT: {
+            ReplayRng g(rng->words, pos, rng->n_words);
+            draw_k(g, (uint32_t)D.start_ip[0]);
+            return g.pos - pos;
+        }
+        case FBA_START_SLOW2: return 4;
+        default: return 2;
+    }
+}
+
+extern "C" int fba_belief_reset_domain_states(fba_belief* b, fba_rng* rng)
+{
+    if (!b || !rng) return FBA_ERR_INVALID;
+    fba_ctx* ctx      = b->ctx;
+    DevModel const& D = b->m->dev;
+    CU(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    int const skip = b->weighted ? 2 : 0; // weighted: one pick uniform precedes the start draws
+    if (rng->mode == FBA_RNG_REPLAY)
+    {
+        // item j: [weighted pick u] + start-state draws; the latter may vary in length
+        std::vector<long long> off((size_t)b->N);
+        long long pos = rng->cursor;
+        for (long long j = 0; j < b->N; ++j)
+        {
+            off[j] = pos - rng->cursor;
+            pos += skip;
+            pos += start_state_words(D, rng, pos);
+        }
+        long long const need = pos - rng->cursor;
+        if ((rc = stage_words(ctx, rng, need))) return rc;
+        if ((rc = stage_offsets(ctx, off))) return rc;
+        CU(ctx, cudaStreamSynchronize(ctx->stream)); // `off` is about to go out of scope
+        if (b->weighted)
+        {
+            if ((rc = pick_ancestors(b, rng, b->N, 0, true, need))) return rc;
+            if ((rc = gather_into_next(b, b->N, false))) return rc;
+            flip(b);
+        } else if ((rc = clear_flag(ctx)))
+            return rc;
+        LAUNCH(ctx, k_reset_states<true>, blocks_for(b->N), kThreads, D, b->state[b->cur], b->N,
+               replay_args(ctx, need, 0, true), skip, ctx->d_flag);
+        rng->cursor += need;
+        if ((rc = check_flag(ctx))) return rc;
+        if (b->weighted) weights_became_uniform(b);
+    } else
+    {
+        if (b->weighted)
+        {
+            if ((rc = pick_ancestors(b, rng, b->N, 0, false, 0))) return rc;
+            if ((rc = gather_into_next(b, b->N, false))) return rc;
+            flip(b);
+            b->total_weight = 1.0;
+            b->suffix_valid = b->cdf_valid = false;
+        }
+        LAUNCH(ctx, k_reset_states<false>, blocks_for(b->N), kThreads, D, b->state[b->cur], b->N,
+               philox_args(rng), 0, ctx->d_flag);
+    }
+    return FBA_OK;
+}
+
+extern "C" int fba_belief_sample(fba_belief* b, fba_rng* rng, int64_t* index)
+{
+    if (!b || !rng || !index) return FBA_ERR_INVALID;
+    fba_ctx* ctx = b->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if (!b->weighted)
+    { // FlatFilter::sample (FlatFilter.cpp:97-102): one uniform int, host side
+        if (rng->mode == FBA_RNG_REPLAY)
+        {
+            ReplayRng g(rng->words, rng->cursor, rng->n_words);
+            int const i = draw_k(g, (uint32_t)b->N);
+            if (g.overrun) return ctx->err = "replay stream underrun", FBA_ERR_RNG_UNDERRUN;
+            rng->cursor = g.pos;
+            *index      = i;
+        } else
+        {
+            PhiloxRng g(rng->seed, 0, rng->offset++);
+            *index = draw_k(g, (uint32_t)b->N);
+        }
+        return FBA_OK;
+    }
+    if (rng->mode == FBA_RNG_REPLAY)
+    {
+        if ((rc = stage_words(ctx, rng, 2))) return rc;
+        if ((rc = pick_ancestors(b, rng, 1, 2, false, 2))) return rc;
+        rng->cursor += 2;
+    } else
+    {
+        if (!b->cdf_valid)
+            if ((rc = native_normalize(b, false, 1.0))) return rc;
+        LAUNCH(ctx, k_pick_native, 1, kThreads, b->aux, b->N, 1ll, 0, philox_args(rng), b->anc);
+    }
+    int h = 0;
+    CU(ctx, cudaMemcpyAsync(&h, b->anc, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    *index = h;
+    return FBA_OK;
+}
+
+// ---- rejection sampling ----------------------------------------------------------------------
+
+static int ensure_wave(fba_belief* b, long long cap)
+{
+    fba_ctx* ctx = b->ctx;
+    if (cap <= b->wave_cap) return FBA_OK;
+    cudaFree(b->att_src), cudaFree(b->att_state), cudaFree(b->att_accept), cudaFree(b->att_pos), cudaFree(b->att_rec);
+    b->att_src = b->att_state = b->att_accept = b->att_pos = b->att_rec = nullptr;
+    b->wave_cap = 0;
+    CU(ctx, cudaMalloc(&b->att_src, cap * sizeof(int)));
+    CU(ctx, cudaMalloc(&b->att_state, cap * sizeof(int)));
+    CU(ctx, cudaMalloc(&b->att_accept, cap * sizeof(int)));
+    CU(ctx, cudaMalloc(&b->att_pos, cap * sizeof(int)));
+    CU(ctx, cudaMalloc(&b->att_rec, cap * b->m->dev.J * sizeof(int)));
+    b->wave_cap = cap;
+    return FBA_OK;
+}
+
+extern "C" int fba_belief_reject_sample(fba_belief* b, int32_t a, int32_t o, fba_rng* rng, int64_t* attempts_out)
+{
+    if (!b || !rng) return FBA_ERR_INVALID;
+    fba_ctx* ctx      = b->ctx;
+    DevModel const& D = b->m->dev;
+    REQUIRE(ctx, a >= 0 && a < D.A, "action out of range");
+    REQUIRE(ctx, o >= 0 && o < D.O, "observation out of range");
+    CU(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    int const nx        = b->cur ^ 1;
+    long long accepted = 0, attempts = 0;
+    long long const cap = 1ll << 22;
+    double rate         = 0.5; // running estimate of the acceptance rate
+    unsigned long long const philox_off = (rng->mode == FBA_RNG_PHILOX) ? rng->offset++ : 0;
+    std::vector<int> h_accept;
+    std::vector<long long> off;
+    int empty_waves = 0;
+
+    while (accepted < b->N)
+    {
+        long long wave = (long long)((double)(b->N - accepted) / rate * 1.05) + 64;
+        wave           = std::min(cap, std::max<long long>(1024, wave));
+        RngArgs ra{};
+        long long n_words = 0;
+        if (rng->mode == FBA_RNG_REPLAY)
+        {
+            // attempt t: one uniform int (1 word, rarely more), then J uniforms (2J words)
+            off.assign((size_t)wave + 1, 0);
+            long long pos = rng->cursor, n_att = 0;
+            for (; n_att < wave; ++n_att)
+            {
+                ReplayRng g(rng->words, pos, rng->n_words);
+                draw_k(g, (uint32_t)b->N);
+                long long const end = g.pos + 2ll * D.J;
+                if (g.overrun || end > rng->n_words) break; // the stream ends inside this attempt
+                off[n_att] = pos - rng->cursor;
+                pos        = end;
+            }
+            if (n_att == 0) return ctx->err = "replay stream underrun in rejection sampling", FBA_ERR_RNG_UNDERRUN;
+            wave      = n_att;
+            n_words   = pos - rng->cursor;
+            off[wave] = n_words;
+            if ((rc = ensure_wave(b, wave))) return rc;
+            if ((rc = stage_words(ctx, rng, n_words))) return rc;
+            if ((rc = stage_offsets(ctx, off))) return rc;
+            ra = replay_args(ctx, n_words, 0, true);
+        } else
+        {
+            if ((rc = ensure_wave(b, wave))) return rc;
+            ra.seed        = rng->seed;
+            ra.offset      = philox_off;
+            ra.stream_base = (unsigned long long)attempts;
+        }
+        if ((rc = clear_flag(ctx))) return rc;
+        if (rng->mode == FBA_RNG_REPLAY)
+            LAUNCH(ctx, k_rs_attempt<true>, blocks_for(wave), kThreads, D, b->counts[b->cur], b->stride,
+                   b->state[b->cur], b->sid[b->cur], b->N, a, o, wave, ra, b->att_src, b->att_state,
+                   b->att_accept, b->att_rec, ctx->d_flag);
+        else
+            LAUNCH(ctx, k_rs_attempt<false>, blocks_for(wave), kThreads, D, b->counts[b->cur], b->stride,
+                   b->state[b->cur], b->sid[b->cur], b->N, a, o, wave, ra, b->att_src, b->att_state,
+                   b->att_accept, b->att_rec, ctx->d_flag);
+        LAUNCH(ctx, k_scan_flags, 1, kThreads, b->att_accept, wave, b->att_pos, b->d_total);
+        LAUNCH(ctx, k_rs_commit, stream_grid(ctx, wave), kThreads, b->counts[b->cur], b->counts[nx], b->stride,
+               b->sid[b->cur], b->sid[nx], b->state[nx], b->m->d_sizes, b->N, D.J, wave, b->att_src,
+               b->att_state, b->att_accept, b->att_pos, b->att_rec, accepted);
+        int got = 0;
+        CU(ctx, cudaMemcpyAsync(&got, b->d_total, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        if ((rc = check_flag(ctx))) return rc; // synchronises
+
+        long long used = wave; // attempts of this wave that count
+        if (accepted + got >= b->N)
+        { // the N-th acceptance happened inside this wave: find the attempt that produced it
+            long long const need = b->N - accepted;
+            h_accept.resize((size_t)wave);
+            CU(ctx, cudaMemcpy(h_accept.data(), b->att_accept, wave * sizeof(int), cudaMemcpyDeviceToHost));
+            long long seen = 0;
+            for (long long t = 0; t < wave; ++t)
+                if (h_accept[t] && ++seen == need)
+                {
+                    used = t + 1;
+                    break;
+                }
+            accepted = b->N;
+        } else
+            accepted += got;
+        attempts += used;
+        if (rng->mode == FBA_RNG_REPLAY)
+        {
+            rng->cursor += off[used];
+            if (accepted < b->N && rng->cursor >= rng->n_words)
+                return ctx->err = "replay stream ended before N particles were accepted", FBA_ERR_RNG_UNDERRUN;
+        }
+        rate = std::max(1e-4, (double)std::max(got, 1) / (double)wave);
+        if (got == 0 && ++empty_waves > 64)
+            return ctx->err = "rejection sampling: observation has (near) zero probability under the belief",
+                   FBA_ERR_INVALID;
+    }
+    flip(b);
+    if (attempts_out) *attempts_out = attempts;
+    return FBA_OK;
+}
+
+// ---- reinvigoration ---------------------------------------------------------------------------
+
+namespace {
+// host-side view of either random source, for the few sequential draws breeding needs
+struct HostDraws
+{
+    fba_rng* rng;
+    ReplayRng replay;
+    PhiloxRng philox;
+    explicit HostDraws(fba_rng* r) :
+            rng(r), replay(r->words, r->cursor, r->n_words), philox(r->seed, 0, r->offset)
+    {
+        if (r->mode == FBA_RNG_PHILOX) ++r->offset;
+    }
+    int k(uint32_t range) { return rng->mode == FBA_RNG_REPLAY ? draw_k(replay, range) : draw_k(philox, range); }
+    int slow(int max) { return rng->mode == FBA_RNG_REPLAY ? draw_slow_int(replay, max) : draw_slow_int(philox, max); }
+    bool overrun() const { return rng->mode == FBA_RNG_REPLAY && replay.overrun; }
+    void commit()
+    {
+        if (rng->mode == FBA_RNG_REPLAY) rng->cursor = replay.pos;
+    }
+};
+} // namespace
+
+extern "C" int fba_belief_reinvigorate(fba_belief* b, fba_belief* fc, int64_t amount, int32_t mutate_kind,
+                                       fba_rng* rng)
+{
+    if (!b || !fc || !rng) return FBA_ERR_INVALID;
+    fba_ctx* ctx      = b->ctx;
+    fba_model* m      = b->m;
+    DevModel const& D = m->dev;
+    REQUIRE(ctx, fc->m == m, "reinvigorate: both beliefs must share one model");
+    REQUIRE(ctx, amount >= 1, "reinvigorate: resample size of < 1 (" + std::to_string(amount) + ")");
+    REQUIRE(ctx, !D.tabular, "reinvigorate: factored models only");
+    CU(ctx, cudaSetDevice(ctx->device));
+
+    // host mirrors of the small per-particle arrays the sequential part reads
+    std::vector<int> sid((size_t)b->N), st((size_t)b->N), fc_sid((size_t)fc->N);
+    CU(ctx, cudaMemcpyAsync(sid.data(), b->sid[b->cur], b->N * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(st.data(), b->state[b->cur], b->N * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(fc_sid.data(), fc->sid[fc->cur], fc->N * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+
+    int const nT = D.A * D.FS, nO = D.A * D.FO;
+    std::vector<uint32_t> tp(nT), op(nO);
+    std::map<int, BreedJob> last_writer; // slot -> job; a later breed overwrites an earlier one
+    HostDraws g(rng);
+    for (int64_t k = 0; k < amount; ++k)
+    {
+        // ReinvigoratingRejectionSampling.cpp:128: breed(fbapomdp, _belief.sample(),
+        // _fully_connected_belief.sample()) — g++ -std=c++11 evaluates right to left
+        int const counts_donor = g.k((uint32_t)fc->N);
+        int const struct_donor = g.k((uint32_t)b->N);
+        memcpy(tp.data(), m->t_par.data() + (size_t)sid[struct_donor] * nT, nT * sizeof(uint32_t));
+        memcpy(op.data(), m->o_par.data() + (size_t)sid[struct_donor] * nO, nO * sizeof(uint32_t));
+        switch (mutate_kind)
+        {
+            case FBA_MUT_FACTORED_TIGER: // FactoredTigerPriors.cpp:374-375: O[listen = 2][0]
+                REQUIRE(ctx, D.A >= 3, "mutate: factored tiger needs 3 actions");
+                op[2 * D.FO] ^= 1u << g.slow(D.FS); // Structure::flip_random_edge, BABNModel.cpp:16-31
+                break;
+            case FBA_MUT_COLLISION_AVOIDANCE: { // CollisionAvoidancePriors.cpp:478-486
+                int const a    = g.k((uint32_t)D.A);
+                int const obst = 2 + g.k((uint32_t)D.dom_ip[2]);
+                tp[a * D.FS + obst] ^= 1u << g.slow(D.FS);
+                break;
+            }
+            case FBA_MUT_SYSADMIN: { // SysAdminFactoredPrior.cpp:51-52: T[action][computer]; the
+                                     // subscripts' draws run right to left under g++ -std=c++11
+                int const comp = g.k((uint32_t)D.FS);
+                int const a    = g.k((uint32_t)D.A);
+                tp[a * D.FS + comp] ^= 1u << g.slow(D.FS);
+                break;
+            }
+            case FBA_MUT_GRIDWORLD: { // GridWorldBAPriors.cpp:200-225: toggle the goal feature
+                int const a = g.slow(D.A);
+                int const f = g.slow(2);
+                tp[a * D.FS + f] ^= 1u << (D.FS - 1);
+                break;
+            }
+            default: ctx->err = "reinvigorate: unknown mutate kind"; return FBA_ERR_INVALID;
+        }
+        int32_t id = -1;
+        int rc     = fba_model_add_structures(m, 1, tp.data(), op.data(), &id);
+        if (rc) return rc;
+        if (m->sizes[id] > b->stride)
+        {
+            ctx->err = "reinvigorate: mutated structure needs " + std::to_string(m->sizes[id])
+                       + " cells, belief stride is " + std::to_string(b->stride);
+            return FBA_ERR_CAPACITY;
+        }
+        int const slot = g.k((uint32_t)b->N); // FlatFilter::replace, FlatFilter.cpp:39-46
+        if (g.overrun()) return ctx->err = "replay stream underrun in reinvigoration", FBA_ERR_RNG_UNDERRUN;
+        BreedJob job{counts_donor, fc_sid[counts_donor], id, slot, st[struct_donor]};
+        last_writer[slot] = job;
+        sid[slot]         = id;
+        st[slot]          = job.state;
+    }
+    g.commit();
+
+    std::vector<BreedJob> jobs;
+    for (auto const& kv : last_writer) jobs.push_back(kv.second);
+    BreedJob* d_jobs = nullptr;
+    CU(ctx, cudaMalloc(&d_jobs, jobs.size() * sizeof(BreedJob)));
+    CU(ctx, cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(BreedJob), cudaMemcpyHostToDevice, ctx->stream));
+    // structures may have been added: the node table pointer is unchanged, its contents were copied
+    LAUNCH(ctx, k_breed, (int)jobs.size(), kThreads, D, fc->counts[fc->cur], fc->stride, b->counts[b->cur],
+           b->stride, b->state[b->cur], b->sid[b->cur], d_jobs);
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_jobs);
+    return FBA_OK;
+}
+
+// ---- rollouts -----------------------------------------------------------------------------------
+
+extern "C" int fba_rollouts(fba_belief* b, int64_t n, const int64_t* particle, const int32_t* start_state,
+                            const int32_t* depth, double discount, fba_rng* rng, const int64_t* word_offset,
+                            double* returns)
+{
+    if (!b || !rng) return FBA_ERR_INVALID;
+    fba_ctx* ctx      = b->ctx;
+    DevModel const& D = b->m->dev;
+    REQUIRE(ctx, n >= 0 && particle && start_state && depth && returns, "rollouts: null argument");
+    REQUIRE(ctx, discount > 0 && discount <= 1, "rollouts: discount must be in (0, 1]");
+    if (n == 0) return FBA_OK;
+    for (int64_t i = 0; i < n; ++i)
+    {
+        REQUIRE(ctx, particle[i] >= 0 && particle[i] < b->N, "rollouts: particle index out of range");
+        REQUIRE(ctx, start_state[i] >= 0 && start_state[i] < D.S, "rollouts: start state out of range");
+        REQUIRE(ctx, depth[i] >= 0, "rollouts: negative depth");
+    }
+    CU(ctx, cudaSetDevice(ctx->device));
+    long long* d_p = nullptr;
+    int *d_s = nullptr, *d_d = nullptr;
+    double* d_r = nullptr;
+    CU(ctx, cudaMalloc(&d_p, n * sizeof(long long)));
+    CU(ctx, cudaMalloc(&d_s, n * sizeof(int)));
+    CU(ctx, cudaMalloc(&d_d, n * sizeof(int)));
+    CU(ctx, cudaMalloc(&d_r, n * sizeof(double)));
+    CU(ctx, cudaMemcpyAsync(d_p, particle, n * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(d_s, start_state, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(d_d, depth, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    int rc = FBA_OK;
+    if (rng->mode == FBA_RNG_REPLAY)
+    {
+        REQUIRE(ctx, word_offset, "rollouts: REPLAY mode needs word_offset");
+        long long const avail = rng->n_words - rng->cursor;
+        std::vector<long long> off(word_offset, word_offset + n);
+        if ((rc = stage_words(ctx, rng, std::max(0ll, avail)))) return rc;
+        if ((rc = stage_offsets(ctx, off))) return rc;
+        if ((rc = clear_flag(ctx))) return rc;
+        LAUNCH(ctx, k_rollouts<true>, blocks_for(n), kThreads, D, b->counts[b->cur], b->stride, b->sid[b->cur],
+               n, d_p, d_s, d_d, discount, replay_args(ctx, avail, 0, true), d_r, ctx->d_flag);
+    } else
+        LAUNCH(ctx, k_rollouts<false>, blocks_for(n), kThreads, D, b->counts[b->cur], b->stride, b->sid[b->cur],
+               n, d_p, d_s, d_d, discount, philox_args(rng), d_r, ctx->d_flag);
+    CU(ctx, cudaMemcpyAsync(returns, d_r, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_p), cudaFree(d_s), cudaFree(d_d), cudaFree(d_r);
+    if (rng->mode == FBA_RNG_REPLAY)
+    {
+        if ((rc = check_flag(ctx))) return rc;
+        rng->cursor = rng->n_words; // the batch owns the rest of the stream it was handed
+    }
+    return FBA_OK;
+}
+
+// ---- multi-GPU phases ---------------------------------------------------------------------------
+
+extern "C" int fba_belief_propose(fba_belief* b, int32_t a, int32_t o, fba_rng* rng, double* local_total)
+{
+    if (!b || !rng || !local_total) return FBA_ERR_INVALID;
+    fba_ctx* ctx = b->ctx;
+    REQUIRE(ctx, rng->mode == FBA_RNG_PHILOX, "sharded beliefs run in PHILOX mode");
+    int rc = propose(b, a, o, rng, 0);
+    if (rc) return rc;
+    int const n_tiles = (int)((b->N + kTile - 1) / kTile);
+    LAUNCH(ctx, k_tile_sums, n_tiles, kThreads, b->w, b->N, b->tile);
+    LAUNCH(ctx, k_scan_tile_sums, 1, kThreads, b->tile, n_tiles, b->scal);
+    if ((rc = read_scal(b))) return rc;
+    *local_total = ctx->h_scal[0];
+    return FBA_OK;
+}
+
+extern "C" int fba_belief_normalize(fba_belief* b, double global_total)
+{
+    if (!b) return FBA_ERR_INVALID;
+    fba_ctx* ctx = b->ctx;
+    REQUIRE(ctx, global_total > 0, "normalize: total weight must be positive");
+    CU(ctx, cudaSetDevice(ctx->device));
+    // tile sums from fba_belief_propose are still in b->tile (exclusive-scanned)
+    int const n_tiles = (int)((b->N + kTile - 1) / kTile);
+    LAUNCH(ctx, k_scale_and_scan, n_tiles, kThreads, b->w, b->N, b->tile, b->scal, global_total, 0, b->aux);
+    b->cdf_valid    = true;
+    b->suffix_valid = false;
+    return FBA_OK;
+}
+
+// record layout of the export / import staging area: [stride floats][state][structure id][pad 8]
+extern "C" int64_t fba_belief_record_bytes(const fba_belief* b)
+{
+    return b->stride * (int64_t)sizeof(float) + 16;
+}
+
+namespace fba {
+__global__ void __launch_bounds__(kThreads)
+    k_export(const float* __restrict__ src, long long stride, const int* __restrict__ state,
+             const int* __restrict__ sid, const int* __restrict__ anc, long long first, long long n,
+             char* __restrict__ out, long long rec_bytes)
+{
+    int const lane        = threadIdx.x & 31;
+    long long const warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    long long const nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r = warp0; r < n; r += nwarp)
+    {
+        long long const i = anc[first + r];
+        char* rec         = out + r * rec_bytes;
+        warp_copy_block(src + i * stride, reinterpret_cast<float*>(rec), (int)(stride >> 2), lane);
+        if (lane == 0)
+        {
+            int* tail = reinterpret_cast<int*>(rec + stride * sizeof(float));
+            tail[0]   = state[i];
+            tail[1]   = sid[i];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+    k_import(float* __restrict__ dst, long long stride, int* __restrict__ state, int* __restrict__ sid,
+             double* __restrict__ w, double w_new, long long first_slot, long long n,
+             const char* __restrict__ in, long long rec_bytes)
+{
+    int const lane        = threadIdx.x & 31;
+    long long const warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    long long const nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r = warp0; r < n; r += nwarp)
+    {
+        const char* rec      = in + r * rec_bytes;
+        long long const slot = first_slot + r;
+        warp_copy_block(reinterpret_cast<const float*>(rec), dst + slot * stride, (int)(stride >> 2), lane);
+        if (lane == 0)
+        {
+            const int* tail = reinterpret_cast<const int*>(rec + stride * sizeof(float));
+            state[slot]     = tail[0];
+            sid[slot]       = tail[1];
+            if (w) w[slot] = w_new;
+        }
+    }
+}
+} // namespace fba
+
+extern "C" int fba_belief_resample_shard(fba_belief* b, int64_t n_offspring, fba_rng* rng)
+{
+    if (!b || !rng) return FBA_ERR_INVALID;
+    fba_ctx* ctx = b->ctx;
+    REQUIRE(ctx, rng->mode == FBA_RNG_PHILOX, "sharded beliefs run in PHILOX mode");
+    REQUIRE(ctx, n_offspring >= 0 && n_offspring < (1ll << 31), "resample_shard: bad offspring count");
+    REQUIRE(ctx, b->cdf_valid, "resample_shard: call fba_belief_normalize first");
+    CU(ctx, cudaSetDevice(ctx->device));
+    long long const kept = std::min<long long>(n_offspring, b->N);
+    long long const surplus = n_offspring - kept;
+    b->local_kept  = kept;
+    b->xport_count = surplus;
+    if (n_offspring == 0)
+    {
+        flip(b);
+        b->cdf_valid = false;
+        return FBA_OK;
+    }
+    int* anc = b->anc;
+    int* big = nullptr;
+    if (n_offspring > b->N)
+    {
+        CU(ctx, cudaMalloc(&big, n_offspring * sizeof(int)));
+        anc = big;
+    }
+    LAUNCH(ctx, k_pick_native, blocks_for(n_offspring), kThreads, b->aux, b->N, (long long)n_offspring, 1,
+           philox_args(rng), anc);
+    int const nx = b->cur ^ 1;
+    LAUNCH(ctx, k_gather, stream_grid(ctx, kept), kThreads, b->counts[b->cur], b->counts[nx], b->stride,
+           b->state[b->cur], b->state[nx], b->sid[b->cur], b->sid[nx], b->m->d_sizes, b->w,
+           1.0 / (double)b->N, anc, kept);
+    if (surplus > 0)
+    {
+        long long const rb = fba_belief_record_bytes(b);
+        if (surplus > b->xport_cap)
+        {
+            cudaFree(b->xport);
+            b->xport_cap = surplus + surplus / 4 + 16;
+            CU(ctx, cudaMalloc(&b->xport, b->xport_cap * rb));
+        }
+        LAUNCH(ctx, k_export, stream_grid(ctx, surplus), kThreads, b->counts[b->cur], b->stride,
+               b->state[b->cur], b->sid[b->cur], anc, kept, surplus, b->xport, rb);
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(big);
+    flip(b);
+    b->total_weight = 1.0;
+    b->cdf_valid = b->suffix_valid = false;
+    return FBA_OK;
+}
+
+extern "C" int64_t fba_belief_export_count(const fba_belief* b)
+{
+    return b ? b->xport_count : 0;
+}
+extern "C" void* fba_belief_export_ptr(fba_belief* b)
+{
+    return b ? b->xport : nullptr;
+}
+extern "C" void* fba_belief_import_ptr(fba_belief* b, int64_t n_records)
+{
+    if (!b || n_records <= 0) return nullptr;
+    cudaSetDevice(b->ctx->device);
+    if (n_records > b->import_cap)
+    {
+        cudaFree(b->import_buf);
+        b->import_buf = nullptr;
+        b->import_cap = n_records + n_records / 4 + 16;
+        if (cudaMalloc(&b->import_buf, b->import_cap * fba_belief_record_bytes(b)) != cudaSuccess)
+        {
+            b->import_cap = 0;
+            return nullptr;
+        }
+    }
+    return b->import_buf;
+}
+
+extern "C" int fba_belief_import(fba_belief* b, int64_t n_records)
+{
+    if (!b) return FBA_ERR_INVALID;
+    fba_ctx* ctx = b->ctx;
+    REQUIRE(ctx, n_records >= 0 && b->local_kept + n_records <= b->N, "import: more records than empty slots");
+    if (n_records == 0) return FBA_OK;
+    REQUIRE(ctx, b->import_buf && n_records <= b->import_cap, "import: call fba_belief_import_ptr first");
+    CU(ctx, cudaSetDevice(ctx->device));
+    LAUNCH(ctx, k_import, stream_grid(ctx, n_records), kThreads, b->counts[b->cur], b->stride, b->state[b->cur],
+           b->sid[b->cur], b->w, 1.0 / (double)b->N, b->local_kept, (long long)n_records, b->import_buf,
+           fba_belief_record_bytes(b));
+    b->local_kept += n_records;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return FBA_OK;
+}

@@ -1,0 +1,453 @@
+// Device-side building blocks of the belief / rollout hot path (sm_100a).
+//
+// Everything here restates arithmetic of the reference (samkatt/fba-pomdp) that replay parity
+// depends on; each function cites the file:line it mirrors. The translation unit is compiled with
+// -fmad=false and the mixed-precision steps use explicit round-to-nearest intrinsics: the reference
+// runs on baseline x86-64 (no FMA), so every multiply and add is separately rounded there.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/fba_pomdp_b200.h"
+
+namespace fba {
+
+struct Node
+{
+    uint32_t par; // parent bitmask over state features
+    int32_t off;  // offset of this node's CPT inside the particle's count block (floats)
+};
+
+// Model description as the kernels see it (passed by value as a kernel parameter).
+struct DevModel
+{
+    int S, A, O, FS, FO, J; // J = FS + FO nodes per action
+    int feat_s[FBA_MAX_FEATURES], feat_o[FBA_MAX_FEATURES];
+    int step_s[FBA_MAX_FEATURES], step_o[FBA_MAX_FEATURES]; // indexing::stepSize (index.cpp:18-49)
+    int tabular, domain, action_draw;
+    int dom_ip[32];
+    double dom_dp[8];
+    const double* rew_sa;
+    const double* rew_as2;
+    const uint8_t* term_sa;
+    const uint8_t* term_as2;
+    int start_kind;
+    int start_ip[4];
+    const float* start_values;
+    double start_total;
+    const int* start_table;
+    const Node* nodes;      // [max_structs][A][J]
+    const int* struct_size; // [max_structs] floats
+};
+
+// ------------------------------------------------------------------------------------------------
+// random sources
+// ------------------------------------------------------------------------------------------------
+
+// uniform_real_distribution<double>(0,1) over two 32-bit words = generate_canonical<double,53>
+// (libstdc++ bits/random.tcc:3349-3381): (w0 + w1*2^32) / 2^64, clamped below 1.
+__host__ __device__ inline double canonical_from_words(uint32_t w0, uint32_t w1)
+{
+#ifdef __CUDA_ARCH__
+    double sum = __dadd_rn((double)w0, __dmul_rn((double)w1, 4294967296.0));
+    double ret = __dmul_rn(sum, 5.421010862427522170037264004349708557128906250e-20); // 2^-64, exact
+#else
+    double sum = (double)w0 + (double)w1 * 4294967296.0;
+    double ret = sum * 5.421010862427522170037264004349708557128906250e-20;
+#endif
+    if (ret >= 1.0) ret = 0.99999999999999988897769753748434595763683319091796875; // nextafter(1,0)
+    return ret;
+}
+
+// REPLAY: a cursor into the reference's mt19937 word stream (device copy).
+struct ReplayRng
+{
+    const uint32_t* w;
+    long long pos, end;
+    int overrun;
+
+    __host__ __device__ ReplayRng(const uint32_t* words, long long p, long long e) :
+            w(words), pos(p), end(e), overrun(0)
+    {
+    }
+    __host__ __device__ uint32_t next()
+    {
+        if (pos >= end)
+        {
+            overrun = 1;
+            ++pos;
+            return 0u;
+        }
+        return w[pos++];
+    }
+};
+
+// PHILOX: Philox4x32-10 (Salmon et al., SC'11), key = seed, counter = (stream id, op offset, block).
+struct PhiloxRng
+{
+    uint32_t k0, k1;
+    uint32_t c0, c1, c2, c3;
+    uint32_t buf[4];
+    int have;
+    int overrun; // never set; keeps the two sources interchangeable
+
+    __host__ __device__ PhiloxRng(uint64_t seed, uint64_t stream, uint64_t offset) :
+            k0((uint32_t)seed), k1((uint32_t)(seed >> 32) ^ (uint32_t)(offset >> 32)), c0(0),
+            c1((uint32_t)stream), c2((uint32_t)(stream >> 32)), c3((uint32_t)offset), have(0),
+            overrun(0)
+    {
+    }
+    __host__ __device__ static inline void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo)
+    {
+        unsigned long long p = (unsigned long long)a * b;
+        hi                   = (uint32_t)(p >> 32);
+        lo                   = (uint32_t)p;
+    }
+    __host__ __device__ void refill()
+    {
+        uint32_t x0 = c0, x1 = c1, x2 = c2, x3 = c3, a = k0, b = k1;
+#pragma unroll
+        for (int r = 0; r < 10; ++r)
+        {
+            uint32_t hi0, lo0, hi1, lo1;
+            mulhilo(0xD2511F53u, x0, hi0, lo0);
+            mulhilo(0xCD9E8D57u, x2, hi1, lo1);
+            uint32_t y0 = hi1 ^ x1 ^ a, y1 = lo1, y2 = hi0 ^ x3 ^ b, y3 = lo0;
+            x0 = y0, x1 = y1, x2 = y2, x3 = y3;
+            a += 0x9E3779B9u;
+            b += 0xBB67AE85u;
+        }
+        buf[0] = x0, buf[1] = x1, buf[2] = x2, buf[3] = x3;
+        ++c0;
+        have = 4;
+    }
+    __host__ __device__ uint32_t next()
+    {
+        if (!have) refill();
+        return buf[--have];
+    }
+};
+
+// the three distributions the reference draws with (src/utils/random.cpp:90-115), over either source
+template<class R>
+__host__ __device__ inline double draw_u(R& g) // rnd::uniform_rand01, random.cpp:100-103
+{
+    uint32_t w0 = g.next();
+    uint32_t w1 = g.next();
+    return canonical_from_words(w0, w1);
+}
+
+template<class R>
+__host__ __device__ inline bool draw_b(R& g) // rnd::boolean, random.cpp:90-93 (bernoulli(0.5))
+{
+    return draw_u(g) < 0.5;
+}
+
+// uniform_int_distribution<int>(0, range-1): Lemire's method as libstdc++ implements it
+// (bits/uniform_int_dist.h:257-281) — 1 word, rarely more
+template<class R>
+__host__ __device__ inline int draw_k(R& g, uint32_t range)
+{
+    unsigned long long product = (unsigned long long)g.next() * range;
+    uint32_t low               = (uint32_t)product;
+    if (low < range)
+    {
+        uint32_t threshold = (0u - range) % range;
+        while (low < threshold && !g.overrun)
+        {
+            product = (unsigned long long)g.next() * range;
+            low     = (uint32_t)product;
+        }
+    }
+    return (int)(product >> 32);
+}
+
+template<class R>
+__host__ __device__ inline int draw_slow_int(R& g, int max) // rnd::slowRandomInt, random.cpp:111-115
+{
+#ifdef __CUDA_ARCH__
+    return (int)floor(__dmul_rn(draw_u(g), (double)max));
+#else
+    return (int)floor(draw_u(g) * (double)max);
+#endif
+}
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------------------------------------
+// Dirichlet rows, expected mode
+// ------------------------------------------------------------------------------------------------
+
+// sampleFromExpectedMult (random.cpp:244-255) -> sampleFromMult<float const> (random.hpp:93-115):
+// DOUBLE total of the float counts, FLOAT running prefix compared against a double threshold.
+__device__ __forceinline__ int sample_expected_mult(const float* row, int n, double u)
+{
+    double total = (double)row[0];
+    for (int i = 1; i < n; ++i) total = __dadd_rn(total, (double)row[i]);
+    double const p = __dmul_rn(u, total);
+    float sum      = row[0];
+    for (int i = 1; i < n; ++i)
+    {
+        if (p < (double)sum) return i - 1;
+        sum = __fadd_rn(sum, row[i]);
+    }
+    return n - 1;
+}
+
+// expectedMult(dir, n)[k] (random.cpp:257-279): FLOAT sum and FLOAT divide
+__device__ __forceinline__ float expected_mult_at(const float* row, int n, int k)
+{
+    float sum = row[0];
+    for (int i = 1; i < n; ++i) sum = __fadd_rn(sum, row[i]);
+    if ((double)sum <= 1e-300) return 0.0f;
+    return __fdiv_rn(row[k], sum);
+}
+
+// ------------------------------------------------------------------------------------------------
+// feature vectors: up to 16 features of <= 256 values packed in two 64-bit words, so that no
+// per-thread array (and no local memory) is needed. A single feature (tabular) keeps its full value.
+// ------------------------------------------------------------------------------------------------
+struct Feat
+{
+    unsigned long long lo, hi;
+    __device__ __forceinline__ int get(int f, bool single) const
+    {
+        if (single) return (int)lo;
+        return (int)(((f < 8) ? (lo >> (8 * f)) : (hi >> (8 * (f - 8)))) & 0xFFull);
+    }
+    __device__ __forceinline__ void set(int f, int v, bool single)
+    {
+        if (single)
+            lo = (unsigned long long)(unsigned)v;
+        else if (f < 8)
+            lo |= (unsigned long long)v << (8 * f);
+        else
+            hi |= (unsigned long long)v << (8 * (f - 8));
+    }
+};
+
+// indexing::projectUsingStepSize (index.cpp:98-119): feature 0 most significant
+__device__ __forceinline__ Feat decode(int v, const int* step, int n)
+{
+    Feat x{0ull, 0ull};
+    if (n == 1)
+    {
+        x.lo = (unsigned long long)(unsigned)v;
+        return x;
+    }
+    for (int f = 0; f < n; ++f)
+    {
+        int const q = v / step[f];
+        v -= q * step[f];
+        x.set(f, q, false);
+    }
+    return x;
+}
+
+// DBNNode::cptIndex (DBNNode.cpp:171-205): mixed radix over the node's parents, ascending features
+__device__ __forceinline__ int parent_config(const DevModel& M, uint32_t par, const Feat& x)
+{
+    bool const single = (M.FS == 1);
+    int cfg           = 0;
+    while (par)
+    {
+        int const f = __ffs(par) - 1;
+        par &= par - 1;
+        cfg = cfg * M.feat_s[f] + x.get(f, single);
+    }
+    return cfg;
+}
+
+// ------------------------------------------------------------------------------------------------
+// domain functors: BADomainExtension::{reward, terminal}
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double domain_reward(const DevModel& M, int s, int a, int s2, bool& terminal)
+{
+    switch (M.domain)
+    {
+        case FBA_DOM_TIGER: // TigerBAExtension.cpp:21-44 (OBSERVE = 2, Tiger.hpp:30)
+            terminal = M.dom_ip[0] && a != 2;
+            if (a == 2) return -1.0;
+            return (a == s) ? 10.0 : -100.0;
+        case FBA_DOM_FACTORED_TIGER: { // FactoredTigerBAExtension.cpp:27-56
+            terminal = M.dom_ip[0] && a != 2;
+            if (a == 2) return -1.0;
+            int const loc = (s < M.S / 2) ? 0 : 1;
+            return (a == loc) ? 10.0 : -100.0;
+        }
+        case FBA_DOM_SYSADMIN: { // SysAdminBAExtension.cpp:27-48 (float arithmetic, exact integers)
+            terminal        = false;
+            float const up  = (float)__popc((unsigned)s2);
+            float const reb = (a >= M.dom_ip[0]) ? 1.0f : 0.0f;
+            return (double)__fsub_rn(up, __fmul_rn((float)M.dom_dp[0], reb));
+        }
+        case FBA_DOM_GRIDWORLD: { // GridWorldBAExtension.cpp:74-100: a function of s alone
+            int const size = M.dom_ip[0], G = M.dom_ip[1];
+            int const g = s % G, y = (s / G) % size, x = s / (G * size);
+            bool const at_goal = (x == M.dom_ip[2 + 2 * g]) && (y == M.dom_ip[3 + 2 * g]);
+            terminal           = at_goal;
+            return at_goal ? M.dom_dp[0] : M.dom_dp[1];
+        }
+        case FBA_DOM_COLLISION_AVOIDANCE: { // CollisionAvoidanceBAExtension.cpp:59-89
+            int const H = M.dom_ip[1], nobs = M.dom_ip[2];
+            int obst_space = 1;
+            for (int i = 0; i < nobs; ++i) obst_space *= H;
+            int const x = s2 / (H * obst_space), y = (s2 / obst_space) % H;
+            bool crashed = false;
+            if (x < nobs)
+            {
+                int pos = s2 % obst_space;
+                for (int i = nobs - 1; i > x; --i) pos /= H;
+                crashed = (y == pos % H);
+            }
+            terminal = crashed || x == 0;
+            if (crashed) return -M.dom_dp[1];
+            return (a == 1) ? 0.0 : -M.dom_dp[0]; // STAY = 1 (CollisionAvoidance.hpp:91)
+        }
+        default: { // FBA_DOM_TABLE
+            double r = 0.0;
+            int t    = 0;
+            if (M.rew_sa) r += M.rew_sa[(long long)s * M.A + a];
+            if (M.rew_as2) r += M.rew_as2[(long long)a * M.S + s2];
+            if (M.term_sa) t |= M.term_sa[(long long)s * M.A + a];
+            if (M.term_as2) t |= M.term_as2[(long long)a * M.S + s2];
+            terminal = t != 0;
+            return r;
+        }
+    }
+}
+
+// the domain's sampleStartState draws (SURVEY.md §8 a')
+template<class R>
+__device__ __forceinline__ int sample_start_state(const DevModel& M, R& g)
+{
+    switch (M.start_kind)
+    {
+        case FBA_START_CONST: return M.start_ip[0]; // SysAdmin.cpp:102-105
+        case FBA_START_BOOL: return draw_b(g) ? M.start_ip[0] : M.start_ip[1]; // Tiger.cpp:16-19
+        case FBA_START_UNIFORM_INT: return draw_k(g, (uint32_t)M.start_ip[0]); // FactoredTiger.cpp:71-75
+        case FBA_START_SLOW2: { // GridWorld.cpp:260-270
+            int const i = draw_slow_int(g, M.start_ip[0]);
+            int const j = draw_slow_int(g, M.start_ip[1]);
+            return M.start_table[i * M.start_ip[1] + j];
+        }
+        default: { // categoricalDistr::sample, distributions.cpp:47-51: sampleFromMult<float const>
+            double const p = __dmul_rn(draw_u(g), M.start_total);
+            int const n    = M.start_ip[0];
+            float sum      = M.start_values[0];
+            for (int i = 1; i < n; ++i)
+            {
+                if (p < (double)sum) return i - 1;
+                sum = __fadd_rn(sum, M.start_values[i]);
+            }
+            return n - 1;
+        }
+    }
+}
+
+template<class R>
+__device__ __forceinline__ int random_action(const DevModel& M, R& g)
+{
+    if (M.action_draw == FBA_ACT_SLOW_INT) return draw_slow_int(g, M.A); // GridWorld.cpp:223
+    return draw_k(g, (uint32_t)M.A); // Tiger.cpp:24, SysAdmin.cpp:170, ...
+}
+
+// ------------------------------------------------------------------------------------------------
+// BAPOMDP::step (BAPOMDP.cpp:111-143) on one particle
+// ------------------------------------------------------------------------------------------------
+enum StepMode {
+    STEP_UPDATE = 0, // UpdateCounts: +1 written into the count block
+    STEP_KEEP   = 1, // KeepCounts: counts read-only (rollouts, planning)
+    STEP_RECORD = 2  // counts read-only, the J incremented cell offsets are recorded (rejection
+                     // sampling applies them to the accepted copy)
+};
+
+// nodes: this particle's structure, action a: J entries. counts: the particle's block.
+// Returns s'; o_out = simulated observation. x_new returns the new state's features.
+template<int MODE, class R>
+__device__ __forceinline__ int hyper_step(const DevModel& M, const Node* __restrict__ nodes,
+                                          float* counts, int s, R& g, int& o_out, Feat& x_new,
+                                          int* rec)
+{
+    bool const single_s = (M.FS == 1), single_o = (M.FO == 1);
+    Feat const x = decode(s, M.step_s, M.FS);
+
+    // sampleStateIndex (BAFlatModel.cpp:83-91 / BABNModel.cpp:292-307): one draw per state
+    // feature in feature order, every node conditioned on the OLD state
+    Feat x2{0ull, 0ull};
+    int s2 = 0;
+    for (int f = 0; f < M.FS; ++f)
+    {
+        Node const nd   = nodes[f];
+        int const range = M.feat_s[f];
+        int const cell  = nd.off + parent_config(M, nd.par, x) * range;
+        int const v     = sample_expected_mult(counts + cell, range, draw_u(g));
+        x2.set(f, v, single_s);
+        s2 += v * M.step_s[f];
+        if (MODE == STEP_UPDATE) counts[cell + v] = __fadd_rn(counts[cell + v], 1.0f);
+        if (MODE == STEP_RECORD) rec[f] = cell + v;
+    }
+    if (single_s) s2 = (int)x2.lo;
+
+    // sampleObservationIndex (BAFlatModel.cpp:93-103 / BABNModel.cpp:309-326): parents = NEW state.
+    // NOTE the transition increments above touch only transition CPTs, so doing them before the
+    // observation draws (instead of after, BAPOMDP.cpp:134-137) changes nothing.
+    int o = 0;
+    Feat of{0ull, 0ull};
+    for (int q = 0; q < M.FO; ++q)
+    {
+        Node const nd   = nodes[M.FS + q];
+        int const range = M.feat_o[q];
+        int const cell  = nd.off + parent_config(M, nd.par, x2) * range;
+        int const v     = sample_expected_mult(counts + cell, range, draw_u(g));
+        of.set(q, v, single_o);
+        o += v * M.step_o[q];
+    }
+    if (single_o) o = (int)of.lo;
+
+    if (MODE != STEP_KEEP)
+    {
+        // incrementCountsOf, observation part. Tabular: psi[a][s'][o] (BAFlatModel.cpp:126-141).
+        // Factored: the observation CPTs are indexed with the OLD state's features
+        // (BABNModel.cpp:366,380) — a reference quirk that replay reproduces.
+        Feat const& xo = M.tabular ? x2 : x;
+        for (int q = 0; q < M.FO; ++q)
+        {
+            Node const nd   = nodes[M.FS + q];
+            int const range = M.feat_o[q];
+            int const cell  = nd.off + parent_config(M, nd.par, xo) * range + of.get(q, single_o);
+            if (MODE == STEP_UPDATE) counts[cell] = __fadd_rn(counts[cell], 1.0f);
+            if (MODE == STEP_RECORD) rec[M.FS + q] = cell;
+        }
+    }
+    o_out = o;
+    x_new = x2;
+    return s2;
+}
+
+// BA{Flat,BN}Model::computeObservationProbability, expected mode
+// (BAFlatModel.cpp:105-124, BABNModel.cpp:328-352), for the state whose features are x
+__device__ __forceinline__ double obs_probability(const DevModel& M, const Node* __restrict__ nodes,
+                                                  const float* counts, const Feat& x, int o)
+{
+    if (M.tabular)
+    {
+        if (M.O == 1) return 1.0;
+        Node const nd = nodes[M.FS];
+        return (double)expected_mult_at(counts + nd.off + (int)x.lo * M.O, M.O, o);
+    }
+    Feat const of       = decode(o, M.step_o, M.FO);
+    bool const single_o = (M.FO == 1);
+    double prob         = 1.0;
+    for (int q = 0; q < M.FO; ++q)
+    {
+        Node const nd   = nodes[M.FS + q];
+        int const range = M.feat_o[q];
+        int const cell  = nd.off + parent_config(M, nd.par, x) * range;
+        prob = __dmul_rn(prob, (double)expected_mult_at(counts + cell, range, of.get(q, single_o)));
+    }
+    return prob;
+}
+#endif // __CUDACC__
+
+} // namespace fba

@@ -1,0 +1,659 @@
+// Kernels of the belief / rollout hot path (sm_100a). See DESIGN.md §Kernels for the roofline of
+// each; the host-side C ABI that launches them is in fba_capi.cu.
+#pragma once
+
+#include "fba_device.cuh"
+
+namespace fba {
+
+constexpr int kThreads = 256;
+
+// How a kernel obtains its random source for work item `idx`.
+struct RngArgs
+{
+    // REPLAY
+    const uint32_t* words; // device copy of the slice this operation consumes
+    long long n_words;
+    const long long* offsets; // per-item word offset (NULL: idx * words_per_item)
+    long long words_per_item;
+    // PHILOX
+    unsigned long long seed, offset, stream_base;
+};
+
+template<bool REPLAY>
+struct RngOf;
+template<>
+struct RngOf<true>
+{
+    using type = ReplayRng;
+    __device__ static ReplayRng make(const RngArgs& r, long long idx)
+    {
+        long long const p = r.offsets ? r.offsets[idx] : idx * r.words_per_item;
+        return ReplayRng(r.words, p, r.n_words);
+    }
+};
+template<>
+struct RngOf<false>
+{
+    using type = PhiloxRng;
+    __device__ static PhiloxRng make(const RngArgs& r, long long idx)
+    {
+        return PhiloxRng(r.seed, r.stream_base + (unsigned long long)idx, r.offset);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// particle block copies: one warp per destination particle, 16-byte vectors, streaming hints
+// (every byte is touched once per update, so nothing should be kept in L1)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld_stream(const float4* p)
+{
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream(float4* p, float4 v)
+{
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+__device__ __forceinline__ void warp_copy_block(const float* __restrict__ src, float* __restrict__ dst,
+                                                int n_vec, int lane)
+{
+    const float4* s = reinterpret_cast<const float4*>(src);
+    float4* d       = reinterpret_cast<float4*>(dst);
+    int i           = lane;
+    // 4 independent 16-byte loads in flight per lane before the first store
+    for (; i + 96 < n_vec; i += 128)
+    {
+        float4 a = ld_stream(s + i), b = ld_stream(s + i + 32), c = ld_stream(s + i + 64),
+               e = ld_stream(s + i + 96);
+        st_stream(d + i, a);
+        st_stream(d + i + 32, b);
+        st_stream(d + i + 64, c);
+        st_stream(d + i + 96, e);
+    }
+    for (; i < n_vec; i += 32) st_stream(d + i, ld_stream(s + i));
+}
+
+// Belief::initiate: particle i clones prototype particle_proto[i]
+__global__ void __launch_bounds__(kThreads)
+    k_init_from_protos(float* __restrict__ counts, long long stride, int* __restrict__ state,
+                       int* __restrict__ sid, double* __restrict__ w, long long N,
+                       const float* __restrict__ protos, const int* __restrict__ proto_sid,
+                       const int* __restrict__ particle_proto, const int* __restrict__ particle_state)
+{
+    int const lane        = threadIdx.x & 31;
+    long long const warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    long long const nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
+    double const w0       = 1.0 / (double)N;
+    for (long long i = warp0; i < N; i += nwarp)
+    {
+        int const p = particle_proto ? particle_proto[i] : 0;
+        warp_copy_block(protos + (long long)p * stride, counts + i * stride, (int)(stride >> 2), lane);
+        if (lane == 0)
+        {
+            sid[i] = proto_sid[p];
+            if (particle_state) state[i] = particle_state[i];
+            if (w) w[i] = w0;
+        }
+    }
+}
+
+// init_sampled: domain start state (and prototype) drawn on device
+template<bool REPLAY>
+__global__ void __launch_bounds__(kThreads)
+    k_draw_init(DevModel M, long long N, int n_protos, const double* __restrict__ proto_cdf,
+                int* __restrict__ particle_proto, int* __restrict__ particle_state, RngArgs ra)
+{
+    long long const i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    auto g = RngOf<REPLAY>::make(ra, i);
+    int p  = 0;
+    if (proto_cdf)
+    {
+        double const u = draw_u(g);
+        while (p < n_protos - 1 && u >= proto_cdf[p]) ++p;
+    }
+    particle_proto[i] = p;
+    particle_state[i] = sample_start_state(M, g);
+}
+
+// importance_sampling::resample's copy (ImportanceSampler.hpp:79-82): new particle j = copy of
+// ancestor anc[j]; uniform weight. Also used by resetDomainStateDistribution (states overwritten).
+// DOMINANT KERNEL: reads and writes every count cell once — HBM-bound.
+__global__ void __launch_bounds__(kThreads)
+    k_gather(const float* __restrict__ src, float* __restrict__ dst, long long stride,
+             const int* __restrict__ src_state, int* __restrict__ dst_state,
+             const int* __restrict__ src_sid, int* __restrict__ dst_sid,
+             const int* __restrict__ struct_size, double* __restrict__ w, double w_new,
+             const int* __restrict__ anc, long long n_out)
+{
+    int const lane        = threadIdx.x & 31;
+    long long const warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    long long const nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long j = warp0; j < n_out; j += nwarp)
+    {
+        long long const i = anc[j];
+        int const id      = src_sid[i];
+        // copy only the cells this particle's structure owns (rounded to 16 bytes)
+        int const n_vec = (struct_size[id] + 3) >> 2;
+        warp_copy_block(src + i * stride, dst + j * stride, n_vec, lane);
+        if (lane == 0)
+        {
+            dst_sid[j] = id;
+            if (dst_state) dst_state[j] = src_state[i];
+            if (w) w[j] = w_new;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// importance_sampling::update, per-particle part (ImportanceSampler.hpp:37-54): step in place,
+// weight *= P(o | a, particle). One thread per particle.
+// ------------------------------------------------------------------------------------------------
+template<bool REPLAY>
+__global__ void __launch_bounds__(kThreads)
+    k_propose(DevModel M, float* counts, long long stride, int* __restrict__ state,
+              const int* __restrict__ sid, double* __restrict__ w, long long N, int a, int o, RngArgs ra,
+              int* __restrict__ overrun)
+{
+    long long const i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    auto g            = RngOf<REPLAY>::make(ra, i);
+    const Node* nodes = M.nodes + ((long long)sid[i] * M.A + a) * M.J;
+    float* c          = counts + i * stride;
+    int sim_o;
+    Feat x2;
+    int const s2      = hyper_step<STEP_UPDATE>(M, nodes, c, state[i], g, sim_o, x2, nullptr);
+    double const prob = obs_probability(M, nodes, c, x2, o);
+    state[i]          = s2;
+    w[i]              = __dmul_rn(w[i], prob);
+    if (g.overrun) *overrun = 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weights: replay (sequential, bit-exact) and native (tree) reductions
+// ------------------------------------------------------------------------------------------------
+
+// REPLAY normalisation. One block; thread 0 carries the three sequential floating-point chains the
+// reference runs, everyone else only moves data:
+//   A  total        = sum_i w_i in index order                 (ImportanceSampler.hpp:51)
+//   B  w_i /= total; total_weight = sum_i w_i in index order   (WeightedFilter.cpp:130-143)
+//   C  R_k = total_weight - w_{N-1} - ... - w_k, k = N-1..1    (WeightedFilter.cpp:168-183)
+// scal[0] = total, scal[1] = total_weight. If !do_normalise only C runs (scal[1] given).
+constexpr int kChunk = 2048;
+__global__ void __launch_bounds__(kThreads)
+    k_seq_normalize(double* __restrict__ w, long long N, double* __restrict__ scal,
+                    double* __restrict__ R, int do_normalise)
+{
+    __shared__ double buf[kChunk];
+    __shared__ double s_total;
+    int const tid = threadIdx.x;
+
+    if (do_normalise)
+    {
+        double acc = 0.0;
+        for (long long base = 0; base < N; base += kChunk)
+        {
+            int const n = (int)min((long long)kChunk, N - base);
+            for (int k = tid; k < n; k += kThreads) buf[k] = w[base + k];
+            __syncthreads();
+            if (tid == 0)
+                for (int k = 0; k < n; ++k) acc = __dadd_rn(acc, buf[k]);
+            __syncthreads();
+        }
+        if (tid == 0) s_total = acc;
+        __syncthreads();
+        double const total = s_total;
+        acc                = 0.0;
+        for (long long base = 0; base < N; base += kChunk)
+        {
+            int const n = (int)min((long long)kChunk, N - base);
+            for (int k = tid; k < n; k += kThreads)
+            {
+                double const v = __ddiv_rn(w[base + k], total);
+                buf[k]         = v;
+                w[base + k]    = v;
+            }
+            __syncthreads();
+            if (tid == 0)
+                for (int k = 0; k < n; ++k) acc = __dadd_rn(acc, buf[k]);
+            __syncthreads();
+        }
+        if (tid == 0)
+        {
+            scal[0] = total;
+            scal[1] = acc;
+            s_total = acc;
+        }
+        __syncthreads();
+    } else
+    {
+        if (tid == 0) s_total = scal[1];
+        __syncthreads();
+    }
+
+    double rem = s_total;
+    for (long long top = N; top > 0; top -= kChunk)
+    {
+        long long const base = max(0ll, top - kChunk);
+        int const n          = (int)(top - base);
+        for (int k = tid; k < n; k += kThreads) buf[k] = w[base + k];
+        __syncthreads();
+        if (tid == 0)
+            for (int k = n - 1; k >= 0; --k)
+            {
+                rem    = __dsub_rn(rem, buf[k]);
+                buf[k] = rem;
+            }
+        __syncthreads();
+        for (int k = tid; k < n; k += kThreads) R[base + k] = buf[k];
+        __syncthreads();
+    }
+}
+
+// REPLAY: WeightedFilter::sample for draw j (WeightedFilter.cpp:163-191): the largest k >= 1 with
+// threshold > R_k, else 0. R is non-decreasing in k, so this is a binary search.
+__device__ __forceinline__ int pick_from_suffix(const double* __restrict__ R, long long N, double thr)
+{
+    long long lo = 1, hi = N; // count k in [1,N) with R[k] < thr; they form a prefix
+    while (lo < hi)
+    {
+        long long const mid = (lo + hi) >> 1;
+        if (R[mid] < thr) lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return (int)(lo - 1);
+}
+
+__global__ void __launch_bounds__(kThreads)
+    k_pick_replay(const double* __restrict__ R, long long N, const double* __restrict__ scal,
+                  RngArgs ra, int* __restrict__ anc, long long n_out, int* __restrict__ overrun)
+{
+    long long const j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_out) return;
+    auto g           = RngOf<true>::make(ra, j);
+    double const thr = __dmul_rn(draw_u(g), scal[1]);
+    anc[j]           = pick_from_suffix(R, N, thr);
+    if (g.overrun) *overrun = 1;
+}
+
+// NATIVE reductions: fixed tile -> deterministic result for a given N.
+constexpr int kTile = 1024; // doubles per block (4 per thread)
+
+__device__ __forceinline__ double block_reduce_sum(double v, double* sh)
+{
+    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    int const lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) sh[wid] = v;
+    __syncthreads();
+    if (wid == 0)
+    {
+        v = (lane < kThreads / 32) ? sh[lane] : 0.0;
+        for (int o = 4; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    }
+    return v; // valid in thread 0
+}
+
+__global__ void __launch_bounds__(kThreads)
+    k_tile_sums(const double* __restrict__ w, long long N, double* __restrict__ tile_sum)
+{
+    __shared__ double sh[kThreads / 32];
+    long long const base = (long long)blockIdx.x * kTile;
+    double v             = 0.0;
+#pragma unroll
+    for (int k = 0; k < kTile / kThreads; ++k)
+    {
+        long long const i = base + threadIdx.x + k * kThreads;
+        if (i < N) v += w[i];
+    }
+    v = block_reduce_sum(v, sh);
+    if (threadIdx.x == 0) tile_sum[blockIdx.x] = v;
+}
+
+// exclusive scan of the tile sums in one block; scal[0] = grand total
+__global__ void __launch_bounds__(kThreads)
+    k_scan_tile_sums(double* __restrict__ tile_sum, int n_tiles, double* __restrict__ scal)
+{
+    __shared__ double sh[kThreads];
+    __shared__ double carry;
+    if (threadIdx.x == 0) carry = 0.0;
+    __syncthreads();
+    for (int base = 0; base < n_tiles; base += kThreads)
+    {
+        int const i    = base + threadIdx.x;
+        double const v = (i < n_tiles) ? tile_sum[i] : 0.0;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < kThreads; o <<= 1)
+        {
+            double const t = (threadIdx.x >= o) ? sh[threadIdx.x - o] : 0.0;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        double const incl = sh[threadIdx.x];
+        if (i < n_tiles) tile_sum[i] = carry + incl - v;
+        __syncthreads();
+        if (threadIdx.x == kThreads - 1) carry += incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) scal[0] = carry;
+}
+
+// w_i /= scal[0] (optionally), inclusive prefix sums into cdf
+__global__ void __launch_bounds__(kThreads)
+    k_scale_and_scan(double* __restrict__ w, long long N, const double* __restrict__ tile_off,
+                     const double* __restrict__ scal, double divide_by, int use_scal,
+                     double* __restrict__ cdf)
+{
+    __shared__ double sh[kThreads];
+    long long const base = (long long)blockIdx.x * kTile + (long long)threadIdx.x * (kTile / kThreads);
+    double const total   = use_scal ? scal[0] : divide_by;
+    double v[kTile / kThreads];
+    double run = 0.0;
+#pragma unroll
+    for (int k = 0; k < kTile / kThreads; ++k)
+    {
+        long long const i = base + k;
+        double x          = (i < N) ? w[i] / total : 0.0;
+        if (i < N) w[i] = x;
+        run += x;
+        v[k] = run;
+    }
+    sh[threadIdx.x] = run;
+    __syncthreads();
+    for (int o = 1; o < kThreads; o <<= 1)
+    {
+        double const t = (threadIdx.x >= o) ? sh[threadIdx.x - o] : 0.0;
+        __syncthreads();
+        sh[threadIdx.x] += t;
+        __syncthreads();
+    }
+    double const off = tile_off[blockIdx.x] / total + sh[threadIdx.x] - run;
+#pragma unroll
+    for (int k = 0; k < kTile / kThreads; ++k)
+    {
+        long long const i = base + k;
+        if (i < N) cdf[i] = off + v[k];
+    }
+}
+
+// NATIVE ancestor selection over the inclusive cdf (cdf[N-1] ~ 1).
+// systematic: threshold_j = (j + u0) / n_out; multinomial: threshold_j = u_j.
+__global__ void __launch_bounds__(kThreads)
+    k_pick_native(const double* __restrict__ cdf, long long N, long long n_out, int systematic,
+                  RngArgs ra, int* __restrict__ anc)
+{
+    long long const j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_out) return;
+    double thr;
+    if (systematic)
+    {
+        auto g = RngOf<false>::make(ra, 0);
+        thr    = ((double)j + draw_u(g)) / (double)n_out;
+    } else
+    {
+        auto g = RngOf<false>::make(ra, j);
+        thr    = draw_u(g);
+    }
+    thr *= cdf[N - 1];
+    long long lo = 0, hi = N - 1; // first i with cdf[i] > thr
+    while (lo < hi)
+    {
+        long long const mid = (lo + hi) >> 1;
+        if (cdf[mid] > thr) hi = mid;
+        else
+            lo = mid + 1;
+    }
+    anc[j] = (int)lo;
+}
+
+__global__ void __launch_bounds__(kThreads) k_fill(double* __restrict__ w, long long N, double v)
+{
+    long long const i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) w[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// resetDomainStateDistribution: fresh domain start state per particle
+// (BAPOMDP::resetDomainState, BAPOMDP.cpp:69-77). Weighted beliefs first pick an ancestor
+// (k_pick_*) and gather; the start-state draws of item j follow its pick in the stream.
+// ------------------------------------------------------------------------------------------------
+template<bool REPLAY>
+__global__ void __launch_bounds__(kThreads)
+    k_reset_states(DevModel M, int* __restrict__ state, long long N, RngArgs ra, int skip_words,
+                   int* __restrict__ overrun)
+{
+    long long const i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    auto g = RngOf<REPLAY>::make(ra, i);
+    for (int k = 0; k < skip_words; ++k) g.next(); // the weighted pick's uniform (2 words)
+    state[i] = sample_start_state(M, g);
+    if (g.overrun) *overrun = 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// rollouts: RBAPOUCT::rollout (RBAPOUCT.cpp:295-323), one thread per rollout, counts read-only
+// ------------------------------------------------------------------------------------------------
+template<bool REPLAY>
+__global__ void __launch_bounds__(kThreads)
+    k_rollouts(DevModel M, const float* counts, long long stride, const int* __restrict__ sid,
+               long long n, const long long* __restrict__ particle, const int* __restrict__ start,
+               const int* __restrict__ depth, double discount, RngArgs ra, double* __restrict__ ret_out,
+               int* __restrict__ overrun)
+{
+    long long const r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    auto g            = RngOf<REPLAY>::make(ra, r);
+    long long const p = particle[r];
+    float* c          = const_cast<float*>(counts) + p * stride; // STEP_KEEP never writes
+    const Node* base  = M.nodes + (long long)sid[p] * M.A * M.J;
+    // Discount(_discount.toDouble()) starts at 1 (Discount.cpp:3-6)
+    double ret = 0.0, disc = 1.0;
+    int s = start[r], d = depth[r];
+    bool terminal = false;
+    while (d > 0 && !terminal)
+    {
+        int const a = random_action(M, g);
+        int o;
+        Feat x2;
+        int const s2   = hyper_step<STEP_KEEP>(M, base + (long long)a * M.J, c, s, g, o, x2, nullptr);
+        double const rew = domain_reward(M, s, a, s2, terminal);
+        ret  = __dadd_rn(ret, __dmul_rn(rew, disc)); // Return::add (Return.cpp:6-9)
+        disc = __dmul_rn(disc, discount);            // Discount::increment (Discount.cpp:8-11)
+        s    = s2;
+        --d;
+    }
+    ret_out[r] = ret;
+    if (g.overrun) *overrun = 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// rejection sampling (RejectionSampling.hpp:26-72) as waves of independent attempts:
+// attempt t picks a particle uniformly, simulates a step on it WITHOUT touching it and records the
+// outcome; the accepted attempts, in attempt order, become the new particles.
+// ------------------------------------------------------------------------------------------------
+template<bool REPLAY>
+__global__ void __launch_bounds__(kThreads)
+    k_rs_attempt(DevModel M, const float* counts, long long stride, const int* __restrict__ state,
+                 const int* __restrict__ sid, long long N, int a, int o, long long n_attempts,
+                 RngArgs ra, int* __restrict__ src_out, int* __restrict__ state_out,
+                 int* __restrict__ accept_out, int* __restrict__ rec_out, int* __restrict__ overrun)
+{
+    long long const t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_attempts) return;
+    auto g            = RngOf<REPLAY>::make(ra, t);
+    int const i       = draw_k(g, (uint32_t)N); // FlatFilter::sample (FlatFilter.cpp:97-102)
+    const Node* nodes = M.nodes + ((long long)sid[i] * M.A + a) * M.J;
+    float* c          = const_cast<float*>(counts) + (long long)i * stride; // STEP_RECORD: read-only
+    int rec[2 * FBA_MAX_FEATURES];
+    int sim_o;
+    Feat x2;
+    int const s2 = hyper_step<STEP_RECORD>(M, nodes, c, state[i], g, sim_o, x2, rec);
+    src_out[t]    = i;
+    state_out[t]  = s2;
+    accept_out[t] = (sim_o == o) ? 1 : 0;
+    for (int k = 0; k < M.J; ++k) rec_out[t * M.J + k] = rec[k];
+    if (g.overrun) *overrun = 1;
+}
+
+// exclusive scan of 0/1 flags in one block (waves are at most a few million attempts)
+__global__ void __launch_bounds__(kThreads)
+    k_scan_flags(const int* __restrict__ flags, long long n, int* __restrict__ pos, int* __restrict__ total)
+{
+    __shared__ int sh[kThreads];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    constexpr int PER = 8;
+    for (long long base = 0; base < n; base += (long long)kThreads * PER)
+    {
+        int v[PER];
+        int run = 0;
+#pragma unroll
+        for (int k = 0; k < PER; ++k)
+        {
+            long long const i = base + (long long)threadIdx.x * PER + k;
+            v[k]              = (i < n) ? flags[i] : 0;
+            run += v[k];
+        }
+        sh[threadIdx.x] = run;
+        __syncthreads();
+        for (int o = 1; o < kThreads; o <<= 1)
+        {
+            int const t = (threadIdx.x >= o) ? sh[threadIdx.x - o] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        int off = carry + sh[threadIdx.x] - run;
+#pragma unroll
+        for (int k = 0; k < PER; ++k)
+        {
+            long long const i = base + (long long)threadIdx.x * PER + k;
+            if (i < n) pos[i] = off;
+            off += v[k];
+        }
+        __syncthreads();
+        if (threadIdx.x == kThreads - 1) carry += sh[kThreads - 1];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+// accepted attempt t with slot = already + pos[t] < N: copy its source block and apply the
+// recorded +1 increments (one warp per attempt)
+__global__ void __launch_bounds__(kThreads)
+    k_rs_commit(const float* __restrict__ src, float* dst, long long stride,
+                const int* __restrict__ src_sid, int* __restrict__ dst_sid, int* __restrict__ dst_state,
+                const int* __restrict__ struct_size, long long N, int J, long long n_attempts,
+                const int* __restrict__ att_src, const int* __restrict__ att_state,
+                const int* __restrict__ accept, const int* __restrict__ pos, const int* __restrict__ rec,
+                long long already)
+{
+    int const lane        = threadIdx.x & 31;
+    long long const warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    long long const nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long t = warp0; t < n_attempts; t += nwarp)
+    {
+        if (!accept[t]) continue;
+        long long const slot = already + pos[t];
+        if (slot >= N) continue;
+        long long const i = att_src[t];
+        int const id      = src_sid[i];
+        float* d          = dst + slot * stride;
+        warp_copy_block(src + i * stride, d, (struct_size[id] + 3) >> 2, lane);
+        __syncwarp();
+        if (lane < J) d[rec[t * J + lane]] = __fadd_rn(src[i * stride + rec[t * J + lane]], 1.0f);
+        if (lane == 0)
+        {
+            dst_sid[slot]   = id;
+            dst_state[slot] = att_state[t];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// reinvigoration: BABNModel::marginalizeOut (BABNModel.cpp:205-229) of a fully connected counts
+// donor onto a mutated structure, written into the replaced slot. One block per bred particle.
+// Each destination cell sums its source rows in ascending source-configuration order — the order
+// DBNNode::marginalizeOut (DBNNode.cpp:40-80) adds them — so the float result is identical.
+// ------------------------------------------------------------------------------------------------
+struct BreedJob
+{
+    int fc_index;   // counts donor in the fully connected belief
+    int fc_struct;  // its structure id
+    int new_struct; // the mutated structure id
+    int slot;       // destination slot in the belief
+    int state;      // domain state of the structure donor
+};
+
+__global__ void __launch_bounds__(kThreads)
+    k_breed(DevModel M, const float* __restrict__ fc_counts, long long fc_stride, float* dst_counts,
+            long long dst_stride, int* __restrict__ dst_state, int* __restrict__ dst_sid,
+            const BreedJob* __restrict__ jobs)
+{
+    BreedJob const job = jobs[blockIdx.x];
+    const float* src   = fc_counts + (long long)job.fc_index * fc_stride;
+    float* dst         = dst_counts + (long long)job.slot * dst_stride;
+    const Node* sn     = M.nodes + (long long)job.fc_struct * M.A * M.J;
+    const Node* dn     = M.nodes + (long long)job.new_struct * M.A * M.J;
+
+    for (int an = 0; an < M.A * M.J; ++an)
+    {
+        int const j     = an % M.J;
+        int const range = (j < M.FS) ? M.feat_s[j] : M.feat_o[j - M.FS];
+        Node const s = sn[an], d = dn[an];
+        int n_src = 1, n_dst = 1;
+        for (int f = 0; f < M.FS; ++f)
+        {
+            if (s.par & (1u << f)) n_src *= M.feat_s[f];
+            if (d.par & (1u << f)) n_dst *= M.feat_s[f];
+        }
+        if (s.par == d.par)
+        {
+            for (int k = threadIdx.x; k < n_src * range; k += blockDim.x) dst[d.off + k] = src[s.off + k];
+            continue;
+        }
+        for (int cell = threadIdx.x; cell < n_dst * range; cell += blockDim.x)
+        {
+            int const dcfg = cell / range, v = cell - dcfg * range;
+            float acc = 0.0f;
+            for (int cfg = 0; cfg < n_src; ++cfg)
+            {
+                // decode cfg over the source parents and project onto the destination parents
+                int rem = cfg, proj = 0, mult = 1;
+                for (int f = M.FS - 1; f >= 0; --f)
+                {
+                    if (!(s.par & (1u << f))) continue;
+                    int const xv = rem % M.feat_s[f];
+                    rem /= M.feat_s[f];
+                    if (d.par & (1u << f))
+                    {
+                        proj += xv * mult;
+                        mult *= M.feat_s[f];
+                    }
+                }
+                if (proj == dcfg) acc = __fadd_rn(acc, src[s.off + cfg * range + v]);
+            }
+            dst[d.off + cell] = acc;
+        }
+    }
+    // zero the padding up to the stride so downloads compare equal
+    int const used = M.struct_size[job.new_struct];
+    for (long long k = used + threadIdx.x; k < dst_stride; k += blockDim.x) dst[k] = 0.0f;
+    if (threadIdx.x == 0)
+    {
+        dst_state[job.slot] = job.state;
+        dst_sid[job.slot]   = job.new_struct;
+    }
+}
+
+} // namespace fba

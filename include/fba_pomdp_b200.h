@@ -1,0 +1,226 @@
+/* fba_pomdp_b200 — C ABI of the B200 (sm_100a) particle-belief / rollout hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, int status codes, no
+ * exceptions, no torch / CUDA types. Each entry point names the reference (samkatt/fba-pomdp)
+ * interface it stands in for; paths are relative to the reference's root.
+ *
+ * Vocabulary
+ *   particle   one BA-/FBA-POMDP hyper-state: a domain state index, a structure id and a private
+ *              block of float32 Dirichlet counts (BAPOMDPState / FBAPOMDPState).
+ *   structure  the parent sets of every DBN node, as bitmasks over state features. A tabular
+ *              BA-POMDP is the one-structure case: one state feature of size S, parent mask 1.
+ *   count block layout: for a in [0,A): transition nodes f = 0..FS-1, then observation nodes
+ *              g = 0..FO-1; each node's CPT row-major [parent configuration][output], parent
+ *              configuration = mixed radix over the node's parents in ascending feature order.
+ *              Tabular: T(a)[s][s'] = phi[s][a][s'], O(a)[s'][o] = psi[a][s'][o].
+ *   belief     N particles on one GPU (+ double weights when weighted).
+ *   rng        REPLAY: the exact 32-bit words the reference's std::mt19937 would produce, consumed
+ *              through the same libstdc++ distributions in the same order (bit-exact parity mode);
+ *              PHILOX: counter-based Philox4x32-10 on device (production mode).
+ *
+ * Threading: one host thread drives one context; every call is synchronous on return unless noted.
+ */
+#ifndef FBA_POMDP_B200_H
+#define FBA_POMDP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FBA_MAX_FEATURES 16
+
+typedef struct fba_ctx fba_ctx;
+typedef struct fba_model fba_model;
+typedef struct fba_belief fba_belief;
+
+enum fba_status {
+    FBA_OK = 0,
+    FBA_ERR_INVALID = 1,      /* bad argument (the reference throws a string here) */
+    FBA_ERR_CUDA = 2,         /* CUDA runtime failure; see fba_last_error */
+    FBA_ERR_RNG_UNDERRUN = 3, /* replay stream too short for the operation */
+    FBA_ERR_CAPACITY = 4,     /* structure table or count stride too small */
+    FBA_ERR_NO_DEVICE = 5     /* no CUDA device: there is no CPU fallback */
+};
+
+/* BADomainExtension::{reward,terminal} and POMDP::generateRandomAction, per domain
+ * (src/bayes-adaptive/models/table/BADomainExtension.hpp:22-47) */
+enum fba_domain_kind {
+    FBA_DOM_TABLE = 0,          /* reward = rew_sa[s*A+a] + rew_as2[a*S+s'], terminal = OR of the two */
+    FBA_DOM_TIGER = 1,          /* ip[0] = episodic          src/domains/tiger/TigerBAExtension.cpp:21-44 */
+    FBA_DOM_FACTORED_TIGER = 2, /* ip[0] = episodic  src/domains/tiger/FactoredTigerBAExtension.cpp:27-56 */
+    FBA_DOM_SYSADMIN = 3,       /* ip[0] = #computers, dp[0] = reboot cost
+                                   src/domains/sysadmin/SysAdminBAExtension.cpp:27-48 */
+    FBA_DOM_GRIDWORLD = 4,      /* ip[0] = size, ip[1] = #goals, ip[2+2g], ip[3+2g] = goal g (x,y);
+                                   dp[0] = goal reward, dp[1] = step reward
+                                   src/domains/gridworld/GridWorldBAExtension.cpp:74-100 */
+    FBA_DOM_COLLISION_AVOIDANCE = 5 /* ip[0] = width, ip[1] = height, ip[2] = #obstacles;
+                                   dp[0] = move penalty, dp[1] = collide penalty
+                                   src/domains/collision-avoidance/CollisionAvoidanceBAExtension.cpp:59-89 */
+};
+
+enum fba_action_draw { FBA_ACT_UNIFORM_INT = 0, FBA_ACT_SLOW_INT = 1 };
+
+/* the domain's sampleStartState (Environment::sampleStartState, src/environment/Environment.hpp:70) */
+enum fba_start_kind {
+    FBA_START_CONST = 0,       /* start_ip[0] */
+    FBA_START_BOOL = 1,        /* rnd::boolean() ? start_ip[0] : start_ip[1] */
+    FBA_START_UNIFORM_INT = 2, /* uniform_int over start_ip[0] states */
+    FBA_START_SLOW2 = 3,       /* start_table[floor(u*ip[0]) * ip[1] + floor(u*ip[1])] */
+    FBA_START_CATEGORICAL = 4  /* categorical over start_values[0..start_ip[0]) with total start_total */
+};
+
+/* domain `mutate` used by reinvigoration (FBAPOMDP::mutate, src/bayes-adaptive/models/factored/FBAPOMDP.cpp:57-61) */
+enum fba_mutate_kind {
+    FBA_MUT_FACTORED_TIGER = 0,
+    FBA_MUT_COLLISION_AVOIDANCE = 1,
+    FBA_MUT_SYSADMIN = 2,
+    FBA_MUT_GRIDWORLD = 3
+};
+
+/* Stands in for what factory::makeTBAPOMDP / makeFBAPOMDP assemble
+ * (src/bayes-adaptive/models/table/BAPOMDP.cpp:189-209, …/factored/FBAPOMDP.cpp:79-101):
+ * Domain_Size, Domain_Feature_Size, the BADomainExtension and the domain's start distribution. */
+typedef struct fba_model_desc {
+    int32_t S, A, O;
+    int32_t n_state_features, n_obs_features;
+    int32_t state_feature_sizes[FBA_MAX_FEATURES];
+    int32_t obs_feature_sizes[FBA_MAX_FEATURES];
+    int32_t tabular; /* 1: BAFlatModel semantics (psi keyed and incremented by the NEW state);
+                        0: BABNModel semantics (observation increment keyed by the OLD state) */
+    int32_t domain;  /* fba_domain_kind */
+    int32_t dom_ip[32];
+    double dom_dp[8];
+    const double* rew_sa;    /* FBA_DOM_TABLE only, host pointers, may be NULL */
+    const double* rew_as2;
+    const uint8_t* term_sa;
+    const uint8_t* term_as2;
+    int32_t action_draw; /* fba_action_draw */
+    int32_t start_kind;  /* fba_start_kind */
+    int32_t start_ip[4];
+    const float* start_values; /* host pointers */
+    double start_total;
+    const int32_t* start_table;
+} fba_model_desc;
+
+enum fba_rng_mode { FBA_RNG_REPLAY = 0, FBA_RNG_PHILOX = 1 };
+
+/* The random source of one call. REPLAY: `words` (host memory) from `cursor` on; the call advances
+ * `cursor` by exactly what the reference would have drawn. PHILOX: (seed, offset); the call
+ * advances `offset`. */
+typedef struct fba_rng {
+    int32_t mode;
+    const uint32_t* words;
+    int64_t n_words;
+    int64_t cursor;
+    uint64_t seed;
+    uint64_t offset;
+} fba_rng;
+
+/* ---- context ---- */
+int fba_ctx_create(int device, fba_ctx** out);
+void fba_ctx_destroy(fba_ctx* ctx);
+const char* fba_last_error(const fba_ctx* ctx);
+/* the cudaStream_t all work of this context is launched on (for event timing by the host) */
+void* fba_ctx_stream(const fba_ctx* ctx);
+int fba_ctx_synchronize(fba_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int64_t fba_ctx_launch_count(const fba_ctx* ctx);
+
+/* ---- model ---- */
+int fba_model_create(fba_ctx* ctx, const fba_model_desc* desc, int32_t max_structures, fba_model** out);
+void fba_model_destroy(fba_model* m);
+/* Registers n structures (t_par: [n][A*FS], o_par: [n][A*FO] parent bitmasks); duplicates map to the
+ * existing id. Stands in for BABNModel::structure() (src/bayes-adaptive/states/factored/BABNModel.cpp:263-290). */
+int fba_model_add_structures(fba_model* m, int32_t n, const uint32_t* t_par, const uint32_t* o_par,
+                             int32_t* ids_out);
+int32_t fba_model_num_structures(const fba_model* m);
+int64_t fba_model_structure_size(const fba_model* m, int32_t id); /* float cells */
+int fba_model_get_structure(const fba_model* m, int32_t id, uint32_t* t_par, uint32_t* o_par);
+
+/* ---- belief ---- */
+/* stride_floats = 0: the largest registered structure, rounded up to 4 floats. weighted: 1 for
+ * WeightedFilter semantics (importance sampling), 0 for FlatFilter (rejection sampling). */
+int fba_belief_create(fba_ctx* ctx, fba_model* m, int64_t n_particles, int64_t stride_floats,
+                      int32_t weighted, fba_belief** out);
+void fba_belief_destroy(fba_belief* b);
+int64_t fba_belief_size(const fba_belief* b);
+int64_t fba_belief_stride(const fba_belief* b);
+
+/* Belief::initiate (src/beliefs/Belief.hpp:24) with the particles the host-side prior produced:
+ * n_protos distinct (structure id, count block) prototypes and, per particle, which prototype it
+ * clones and its domain start state. particle_proto may be NULL (all prototype 0). Weights 1/N. */
+int fba_belief_init(fba_belief* b, int32_t n_protos, const int32_t* proto_struct_id,
+                    const float* proto_counts /* [n_protos][stride] */,
+                    const int32_t* particle_proto, const int32_t* particle_state);
+/* same, but domain start states (and, if proto_probs != NULL, prototypes) drawn on device */
+int fba_belief_init_sampled(fba_belief* b, int32_t n_protos, const int32_t* proto_struct_id,
+                            const float* proto_counts, const double* proto_probs, fba_rng* rng);
+/* raw particle I/O (debugging, oracle diffing, Belief::sample() materialisation); NULLs skipped */
+int fba_belief_upload(fba_belief* b, int64_t first, int64_t count, const int32_t* state,
+                      const int32_t* struct_id, const float* counts, const double* w);
+int fba_belief_download(fba_belief* b, int64_t first, int64_t count, int32_t* state,
+                        int32_t* struct_id, float* counts, double* w);
+int fba_belief_total_weight(fba_belief* b, double* total); /* WeightedFilter::_total_weight */
+
+/* beliefs::importance_sampling::update (src/beliefs/particle_filters/ImportanceSampler.hpp:31-62):
+ * step every particle with `action`, weight by P(observation | action, particle), normalise.
+ * *likelihood = the un-normalised weight total (the function's return value). */
+int fba_belief_update(fba_belief* b, int32_t action, int32_t observation, fba_rng* rng,
+                      double* likelihood);
+/* beliefs::importance_sampling::resample (ImportanceSampler.hpp:71-94). PHILOX mode resamples
+ * systematically (one uniform, sorted ancestors); REPLAY draws the reference's N multinomial picks. */
+int fba_belief_resample(fba_belief* b, fba_rng* rng);
+/* BAImportanceSampling::updateEstimation (src/beliefs/bayes-adaptive/BAImportanceSampling.cpp:74-88) */
+int fba_belief_update_estimation(fba_belief* b, int32_t action, int32_t observation, fba_rng* rng,
+                                 double* likelihood);
+/* BABelief::resetDomainStateDistribution (src/beliefs/bayes-adaptive/BABelief.hpp:30):
+ * weighted: BAImportanceSampling.cpp:90-111; flat: BARejectionSampling.cpp:47-58 */
+int fba_belief_reset_domain_states(fba_belief* b, fba_rng* rng);
+/* Belief::sample (Belief.hpp:34): index of the drawn particle (use fba_belief_download to view it) */
+int fba_belief_sample(fba_belief* b, fba_rng* rng, int64_t* index);
+
+/* beliefs::rejectSample (src/beliefs/particle_filters/RejectionSampling.hpp:26-72) on a flat belief */
+int fba_belief_reject_sample(fba_belief* b, int32_t action, int32_t observation, fba_rng* rng,
+                             int64_t* attempts);
+/* ReinvigoratingRejectionSampling::reinvigorateParticles
+ * (src/beliefs/bayes-adaptive/factored/ReinvigoratingRejectionSampling.cpp:121-131) */
+int fba_belief_reinvigorate(fba_belief* b, fba_belief* fully_connected, int64_t amount,
+                            int32_t mutate_kind, fba_rng* rng);
+
+/* RBAPOUCT::rollout (src/planners/bayes-adaptive/RBAPOUCT.cpp:295-323), n of them at once:
+ * rollout i starts from particle[i]'s counts (read-only, KeepCounts) in domain state
+ * start_state[i] and runs depth[i] steps or to a terminal. REPLAY: rollout i reads words from
+ * rng->cursor + word_offset[i]; PHILOX: word_offset ignored. returns: n doubles (host). */
+int fba_rollouts(fba_belief* b, int64_t n, const int64_t* particle, const int32_t* start_state,
+                 const int32_t* depth, double discount, fba_rng* rng, const int64_t* word_offset,
+                 double* returns);
+
+/* ---- multi-GPU phases (one process per GPU; the host runs the collective between them) ---- */
+/* phase 1: step + weight, no normalisation; *local_total = this shard's weight sum */
+int fba_belief_propose(fba_belief* b, int32_t action, int32_t observation, fba_rng* rng,
+                       double* local_total);
+/* phase 2: divide by the global total (all-gathered by the host) */
+int fba_belief_normalize(fba_belief* b, double global_total);
+/* phase 3: resample this shard to n_offspring particles, the first min(n_offspring, N) stay here,
+ * the surplus lands in an export buffer (fba_belief_export_ptr) for the host to ship over NCCL */
+int fba_belief_resample_shard(fba_belief* b, int64_t n_offspring, fba_rng* rng);
+int64_t fba_belief_export_count(const fba_belief* b);
+/* device pointers of the export / import staging area: particle records of
+ * fba_belief_record_bytes() each (count block, then state, structure id) */
+void* fba_belief_export_ptr(fba_belief* b);
+void* fba_belief_import_ptr(fba_belief* b, int64_t n_records);
+int64_t fba_belief_record_bytes(const fba_belief* b);
+/* phase 4: place n_records imported records into the slots the local resample left empty */
+int fba_belief_import(fba_belief* b, int64_t n_records);
+
+/* device pointers of the current particle arrays, for zero-copy views by the host language */
+void* fba_belief_counts_ptr(fba_belief* b);
+void* fba_belief_state_ptr(fba_belief* b);
+void* fba_belief_weight_ptr(fba_belief* b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FBA_POMDP_B200_H */

@@ -1,0 +1,192 @@
+"""GPU: the CUDA path (through the C ABI) against the golden fixtures generated from the unmodified
+reference, in replay mode: same mt19937 words in; bit-identical domain states, count blocks and
+ancestor choices out; weights within 1e-5 relative (in fact bit-identical here); and the same
+number of words consumed."""
+import numpy as np
+import pytest
+
+import golden_util as G
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL_W = 1e-5  # BASELINE.json north_star: "log-weights agree to 1e-5 relative"
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import fba_pomdp_b200 as fba
+    c = fba.Context(0)
+    yield c
+    c.close()
+
+
+def make_sim(ctx, g, extra_structs=0):
+    import fba_pomdp_b200 as fba
+    return fba.BAPOMDP(ctx, g.desc, g.t_par, g.o_par, max_structures=len(g.t_par) + extra_structs)
+
+
+def count_sums(c):
+    return c.astype(np.float64).sum(1)
+
+
+@pytest.mark.parametrize("name", G.NAMES)
+def test_importance_sampling_replay(ctx, name):
+    import fba_pomdp_b200 as fba
+    g = G.load(name)
+    sim = make_sim(ctx, g)
+    b = fba.BAImportanceSampling(len(g["is/init_state"]))
+    b.initiate(sim, struct_id=g["is/init_struct_id"], counts=g["is/init_counts"], state=g["is/init_state"])
+    n_upd = 0
+    for t in g.steps("is"):
+        a, o, fl = int(g.a[t]), int(g.o[t]), int(g.flags[t])
+        if fl & 2 and t > 0:
+            rng = fba.Rng.replay(g["is/%d/reset_words" % t])
+            b.resetDomainStateDistribution(rng)
+            assert rng.exhausted
+            d = b.download()
+            np.testing.assert_array_equal(d["state"], g["is/%d/reset_state" % t])
+            np.testing.assert_array_equal(count_sums(d["counts"]), g["is/%d/reset_count_sums" % t])
+        if fl & 1:
+            continue
+        rng = fba.Rng.replay(g["is/%d/update_words" % t])
+        lik = b.update(a, o, rng)
+        assert rng.exhausted
+        d = b.download()
+        np.testing.assert_array_equal(d["state"], g["is/%d/state" % t])
+        np.testing.assert_allclose(d["w"], g["is/%d/w" % t], rtol=REL_TOL_W, atol=0)
+        np.testing.assert_array_equal(d["w"], g["is/%d/w" % t])  # and in fact bit-identical
+        assert lik == float(g["is/%d/likelihood" % t])
+        assert d["total_weight"] == float(g["is/%d/total_weight" % t])
+        np.testing.assert_array_equal(count_sums(d["counts"]), g["is/%d/count_sums" % t])
+        if g.has("is/%d/counts" % t):
+            np.testing.assert_array_equal(d["counts"], g["is/%d/counts" % t])
+        rng = fba.Rng.replay(g["is/%d/resample_words" % t])
+        b.resample(rng)
+        assert rng.exhausted
+        d = b.download()
+        np.testing.assert_array_equal(d["state"], g["is/%d/rs_state" % t])
+        np.testing.assert_array_equal(d["struct_id"], g["is/%d/rs_struct_id" % t])
+        np.testing.assert_array_equal(count_sums(d["counts"]), g["is/%d/rs_count_sums" % t])
+        assert d["total_weight"] == float(g["is/%d/rs_total_weight" % t])
+        n_upd += 1
+    assert n_upd >= 2
+    d = b.download()
+    np.testing.assert_array_equal(d["counts"], g["is/final_counts"])
+    np.testing.assert_array_equal(d["state"], g["is/final_state"])
+    b.free()
+    sim.close()
+
+
+@pytest.mark.parametrize("name", G.NAMES)
+def test_rollouts_replay(ctx, name):
+    import fba_pomdp_b200 as fba
+    g = G.load(name)
+    sim = make_sim(ctx, g)
+    b = fba.BAImportanceSampling(len(g["is/final_state"]))
+    b.initiate(sim, struct_id=g["is/final_struct_id"], counts=g["is/final_counts"], state=g["is/final_state"])
+    rng = fba.Rng.replay(g["roll/words"])
+    ret = fba.rollouts(b, g["roll/particle"], g["roll/start"], g["roll/depth"], g.discount, rng,
+                       g["roll/offsets"][:-1])
+    np.testing.assert_array_equal(ret, g["roll/ret"])
+    # rollouts are KeepCounts: the belief is untouched
+    np.testing.assert_array_equal(b.download()["counts"], g["is/final_counts"])
+    b.free()
+    sim.close()
+
+
+@pytest.mark.parametrize("name", [n for n in G.NAMES if G.load(n).has("rs/init_counts")])
+def test_rejection_sampling_replay(ctx, name):
+    import fba_pomdp_b200 as fba
+    g = G.load(name)
+    sim = make_sim(ctx, g)
+    b = fba.BARejectionSampling(len(g["rs/init_state"]))
+    b.initiate(sim, struct_id=g["rs/init_struct_id"], counts=g["rs/init_counts"], state=g["rs/init_state"])
+    done = 0
+    for t in g.steps("rs"):
+        a, o, fl = int(g.a[t]), int(g.o[t]), int(g.flags[t])
+        if fl & 2 and t > 0:
+            rng = fba.Rng.replay(g["rs/%d/reset_words" % t])
+            b.resetDomainStateDistribution(rng)
+            assert rng.exhausted
+            np.testing.assert_array_equal(b.download(counts=False)["state"], g["rs/%d/reset_state" % t])
+        if fl & 1 or not g.has("rs/%d/words" % t):
+            continue
+        rng = fba.Rng.replay(g["rs/%d/words" % t])
+        b.updateEstimation(a, o, rng)
+        assert rng.exhausted
+        d = b.download()
+        np.testing.assert_array_equal(d["state"], g["rs/%d/state" % t])
+        np.testing.assert_array_equal(d["struct_id"], g["rs/%d/struct_id" % t])
+        np.testing.assert_array_equal(count_sums(d["counts"]), g["rs/%d/count_sums" % t])
+        done += 1
+    assert done >= 1
+    np.testing.assert_array_equal(b.download()["counts"], g["rs/final_counts"])
+    b.free()
+    sim.close()
+
+
+def _struct_key_map(sim, g):
+    key = {}
+    for i in range(sim.num_structures):
+        t, o = sim.structure(i)
+        key[(t.tobytes(), o.tobytes())] = i
+    return key
+
+
+@pytest.mark.parametrize("name", [n for n in G.NAMES if G.load(n).has("reinv/K")])
+def test_reinvigoration_replay(ctx, name):
+    import fba_pomdp_b200 as fba
+    g = G.load(name)
+    sim = make_sim(ctx, g, extra_structs=4096)
+    stride = int(g["reinv/stride"])
+    K = int(g["reinv/K"])
+    b = fba.ReinvigoratingRejectionSampling(len(g["reinv/init_b_state"]), K, G.MUTATE_KIND[name])
+    b.initiate(sim, stride=stride,
+               belief=dict(struct_id=g["reinv/init_b_struct_id"], counts=g["reinv/init_b_counts"],
+                           state=g["reinv/init_b_state"]),
+               fully_connected=dict(struct_id=g["reinv/init_fc_struct_id"],
+                                    counts=g["reinv/init_fc_counts"], state=g["reinv/init_fc_state"]))
+    done = 0
+    for t in g.steps("reinv"):
+        a, o, fl = int(g.a[t]), int(g.o[t]), int(g.flags[t])
+        if fl & 2 and t > 0:
+            rng = fba.Rng.replay(g["reinv/%d/reset_words" % t])
+            b.resetDomainStateDistribution(rng)
+            assert rng.exhausted
+            np.testing.assert_array_equal(b.download(counts=False)["state"], g["reinv/%d/reset_b_state" % t])
+            np.testing.assert_array_equal(b.download_fully_connected(False)["state"],
+                                          g["reinv/%d/reset_fc_state" % t])
+        if fl & 1 or not g.has("reinv/%d/breed_words" % t):
+            continue
+        rng = fba.Rng.replay(g["reinv/%d/breed_words" % t])
+        b.reinvigorateParticles(rng)
+        assert rng.exhausted
+        d = b.download()
+        np.testing.assert_array_equal(d["state"], g["reinv/%d/breed_b_state" % t])
+        np.testing.assert_array_equal(d["counts"], g["reinv/%d/breed_b_counts" % t])
+        key = _struct_key_map(sim, g)
+        want = np.array([key[(g.t_par[j].tobytes(), g.o_par[j].tobytes())]
+                         for j in g["reinv/%d/breed_b_struct_id" % t]])
+        np.testing.assert_array_equal(d["struct_id"], want)
+        # the two rejectSample calls share one stream
+        rng = fba.Rng.replay(g["reinv/%d/reject_words" % t])
+        import ctypes as C
+        n = C.c_int64(0)
+        for h in (b.h, b.fc):
+            rc = b.L.fba_belief_reject_sample(h, a, o, C.byref(rng), C.byref(n))
+            assert rc == 0, b.L.fba_last_error(ctx.h)
+        assert rng.exhausted
+        for tag, d in (("b", b.download()), ("fc", b.download_fully_connected())):
+            np.testing.assert_array_equal(d["state"], g["reinv/%d/%s_state" % (t, tag)])
+            np.testing.assert_array_equal(count_sums(d["counts"]), g["reinv/%d/%s_count_sums" % (t, tag)])
+        done += 1
+    assert done >= 1
+    np.testing.assert_array_equal(b.download()["counts"], g["reinv/final_b_counts"])
+    np.testing.assert_array_equal(b.download_fully_connected()["counts"], g["reinv/final_fc_counts"])
+    b.free()
+    sim.close()
+
+
+def test_smoke_entry():
+    import __graft_entry__ as ge
+    ge.smoke()
