@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py — particle belief updates/s on B200 for BASELINE.json's headline configuration.
+
+Workload (config.workload): linear-sysadmin, 10 computers, FBA-POMDP (configs[4]); the belief is
+importance sampling over N particles, one "step" = one full belief update of every particle
+(importance_sampling::update + ::resample) on a fixed (action, observation) script taken from the
+reference's true environment (tests/golden/sysadmin.npz). BASELINE.json shards 10^7 particles over
+8 GPUs; weak scaling keeps that per-GPU shard (1.25e6 particles, 14.8 GB of counts, far above the
+126 MB L2) fixed, so N=1 runs one shard.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N ...             # the reference's own CPU path
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "particle belief updates/s"
+UNIT = "particles/s"
+WORKLOAD = "linear-sysadmin-10 FBA-POMDP, importance-sampling belief update (update+resample)"
+PER_GPU_PARTICLES = 1_250_000  # 10^7 / 8 (BASELINE.json configs[4])
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for k, nm in enumerate(names):
+                if len(r) > 5 + k and r[5 + k].strip().lower().startswith("active"):
+                    reasons.add(nm)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                       samples=len(sm))
+        return out
+
+
+def workload():
+    import golden_util as G
+    g = G.load("sysadmin")
+    steps = [(int(a), int(o)) for a, o, f in zip(g.a, g.o, g.flags) if not (f & 1)]
+    return g, g["is/init_counts"][0].copy(), steps
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's own CPU implementation (cpu_baseline and --impl reference)
+# ------------------------------------------------------------------------------------------------
+def _ref_worker(n, steps, warmup, seed, script, q):
+    try:
+        import pyref
+        kind = "reference"
+        r = pyref.Ref("linear-sysadmin", size=10, factored=True, seed=seed)
+        r.belief_init(pyref.F_IS, n)
+
+        def one(t):
+            a, o = script[t % len(script)]
+            r.update_estimation(pyref.F_IS, a, o)
+    except Exception:  # the compiled reference did not travel: time the C port of it instead
+        kind = "port"
+        import golden_util as G
+        import pyoracle as O
+        g = G.load("sysadmin")
+        m = O.Model(g.desc)
+        st = O.Structs(m, g.t_par, g.o_par)
+        state = {"b": O.Belief(n, g["is/init_counts"].shape[1])}
+        state["b"].counts[:] = g["is/init_counts"][0]
+        state["b"].state[:] = g["is/init_state"][0]
+        state["b"].total_weight = O.sequential_uniform_total(n)
+        words = np.random.RandomState(int(seed)).randint(0, 2**32, size=(2 * 11 + 2) * n + 64,
+                                                         dtype=np.uint64).astype(np.uint32)
+
+        def one(t):
+            a, o = script[t % len(script)]
+            rng = O.Rng(words)
+            O.is_update(m, st, state["b"], a, o, rng)
+            state["b"], _ = O.is_resample(state["b"], rng)
+
+    for t in range(warmup):
+        one(t)
+    t0 = time.perf_counter()
+    for t in range(steps):
+        one(warmup + t)
+    q.put((kind, time.perf_counter() - t0))
+
+
+def run_reference_cpu(n_particles, steps, warmup, replicas):
+    """`replicas` independent single-threaded reference beliefs (the reference has no threads),
+    one per host core; returns (particles/s aggregate, seconds per step, kind)."""
+    import multiprocessing as mp
+    _, _, script = workload()
+    ctxmp = mp.get_context("fork")
+    q = ctxmp.Queue()
+    procs = [ctxmp.Process(target=_ref_worker, args=(n_particles, steps, warmup, str(42 + i), script, q))
+             for i in range(replicas)]
+    for p in procs:
+        p.start()
+    res = [q.get() for _ in procs]
+    for p in procs:
+        p.join()
+    slowest = max(t for _, t in res)
+    return replicas * n_particles * steps / slowest, slowest / steps, res[0][0]
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0  # the CPU arm runs once per box
+    cores = os.cpu_count() or 1
+    n = args.ref_particles
+    value, s_per_step, kind = run_reference_cpu(n, args.steps, args.warmup, cores)
+    sample = ("%d independent single-threaded replicas (one per host core), each a BAImportanceSampling "
+              "belief of %d particles (the reference's resample is O(N^2); BASELINE.md quotes it at "
+              "N=4096), %d updateEstimation steps" % (cores, n, args.steps))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 counts / f64 weights",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "particles_per_replica": n,
+                                        "replicas": cores, "l2": "n/a (CPU)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# this repo's CUDA path
+# ------------------------------------------------------------------------------------------------
+def main_ours(args):
+    import torch
+    import torch.distributed as dist
+    import fba_pomdp_b200 as fba
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the hot path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    g, proto, script = workload()
+    n_local = args.particles
+    ctx = fba.Context(local_rank)
+    sim = fba.BAPOMDP(ctx, g.desc, g.t_par, g.o_par)
+    C = int(sim.structure_size(0))
+    bytes_per_particle = 2 * (4 * C + 4 + 8)  # counts + state + weight, read + written
+
+    if world > 1:
+        b = fba.ShardedBAImportanceSampling(n_local)
+        rng = b.rank_rng(args.seed)
+    else:
+        b = fba.BAImportanceSampling(n_local)
+        rng = fba.Rng.philox(args.seed)
+    b.initiate_sampled(sim, [0], proto[None, :], None, rng)
+    shared = np.random.RandomState(args.seed)  # same on every rank: quota offsets
+
+    def step(t, want_likelihood=False):
+        a, o = script[t % len(script)]
+        if world > 1:
+            return b.updateEstimation(a, o, rng, step_uniform=float(shared.random_sample()))
+        return b.updateEstimation(a, o, rng, want_likelihood=want_likelihood)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.synchronize()
+
+    for t in range(args.warmup):
+        step(t)
+    barrier()
+
+    stream = torch.cuda.ExternalStream(ctx.stream)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ctx.launches
+    ctx.profile_begin()
+    ev0.record(stream)
+    for t in range(args.steps):
+        step(args.warmup + t)
+    ev1.record(stream)
+    barrier()
+    ctx.profile_end()
+    clocks = sampler.stop()
+    launches = ctx.launches - launches0
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    value = n_local * world * args.steps / (ms * 1e-3)
+
+    # dominant kernel: the resample gather (reads + writes every count cell once)
+    g_ms, g_n = ctx.kernel_time("k_gather")
+    p_ms, p_n = ctx.kernel_time("k_propose")
+    peak, peak_src = load_peaks()
+    achieved = bytes_per_particle * n_local / (g_ms / max(g_n, 1) * 1e-3) / 1e9 if g_n else 0.0
+    kernel_share = {k: round(ctx.kernel_time(k)[0] / ms, 4) for k in
+                    ("k_gather", "k_propose", "k_tile_sums", "k_scan_tile_sums", "k_scale_and_scan",
+                     "k_pick_native")}
+
+    # end to end through the public call with host arguments and host results: per step the
+    # (action, observation) pair goes in, the step likelihood comes back, and — what the planner
+    # does next — Belief::sample() materialises one particle on the host.
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for t in range(args.steps):
+        if world > 1:
+            step(args.warmup + args.steps + t)
+        else:
+            step(args.warmup + args.steps + t, want_likelihood=True)
+        d2h = 8
+        if world == 1:
+            i = b.sample(rng)
+            part = b.download(i, 1)
+            d2h += part["counts"].nbytes + 4 + 4 + 8 + 4
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    e2e_value = n_local * world * args.steps / e2e_s
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 counts / f64 weights", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "particles_per_gpu": n_local, "particles_total": n_local * world,
+                   "count_cells_per_particle": C, "rng": "philox4x32-10", "resampling": "systematic",
+                   "parallelism": "particles sharded, %d rank(s)" % world,
+                   "l2": "inputs (%.1f GB of counts per GPU) exceed the 126 MB L2; no flush needed"
+                         % (n_local * C * 4 / 1e9),
+                   "e2e_note": "per step: (a,o) in as call arguments, likelihood (8 B) out, then "
+                               "Belief::sample() + download of that particle"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "k_gather", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_particle": bytes_per_particle,
+                     "kernel_ms": g_ms / max(g_n, 1), "kernel_share_of_step": kernel_share},
+    }
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n = args.ref_particles
+        v, s_per_step, kind = run_reference_cpu(n, 6, 1, 1)
+        line["cpu_baseline"] = {
+            "value": v, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": "the reference's BAImportanceSampling::updateEstimation, 1 thread (it has no "
+                      "threads), %d particles (its resample is O(N^2)), 6 steps after 1 warm-up; "
+                      "host has %d cores" % (n, os.cpu_count() or 1)}
+    elif rank == 0:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line))
+    b.free()
+    sim.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--particles", type=int, default=PER_GPU_PARTICLES, help="particles per GPU")
+    ap.add_argument("--ref-particles", type=int, default=4096)
+    ap.add_argument("--seed", type=int, default=42)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return main_reference(args)
+    return main_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -10,3 +10,4 @@ from .capi import FbaError, Rng  # noqa: F401
 
 __all__ = ["capi", "Context", "BAPOMDP", "BAImportanceSampling", "BARejectionSampling",
            "ReinvigoratingRejectionSampling", "rollouts", "Rng", "FbaError"]
+from .sharded import ShardedBAImportanceSampling, exchange_plan, offspring_quotas  # noqa: F401,E402

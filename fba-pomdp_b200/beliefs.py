@@ -52,6 +52,18 @@ class Context:
     def synchronize(self):
         _check(self.h, self.L.fba_ctx_synchronize(self.h))
 
+    def profile_begin(self):
+        _check(self.h, self.L.fba_ctx_profile_begin(self.h))
+
+    def profile_end(self):
+        _check(self.h, self.L.fba_ctx_profile_end(self.h))
+
+    def kernel_time(self, prefix):
+        """(total ms, launches) of the kernels whose name starts with prefix, from CUDA events."""
+        ms, n = C.c_double(0), C.c_int64(0)
+        _check(self.h, self.L.fba_ctx_profile_get(self.h, prefix.encode(), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def close(self):
         if self.h:
             self.L.fba_ctx_destroy(self.h)
@@ -247,11 +259,13 @@ class BAImportanceSampling(_ParticleBelief):
         """importance_sampling::resample (ImportanceSampler.hpp:71-94)."""
         _check(self.ctx.h, self.L.fba_belief_resample(self.h, C.byref(rng)))
 
-    def updateEstimation(self, a, o, rng):
-        """BAImportanceSampling::updateEstimation (BAImportanceSampling.cpp:74-88)."""
+    def updateEstimation(self, a, o, rng, want_likelihood=True):
+        """BAImportanceSampling::updateEstimation (BAImportanceSampling.cpp:74-88). Without the
+        likelihood read-back a PHILOX-mode call only enqueues work (no host sync)."""
         lik = C.c_double(0)
-        _check(self.ctx.h, self.L.fba_belief_update_estimation(self.h, a, o, C.byref(rng), C.byref(lik)))
-        return lik.value
+        _check(self.ctx.h, self.L.fba_belief_update_estimation(
+            self.h, a, o, C.byref(rng), C.byref(lik) if want_likelihood else None))
+        return lik.value if want_likelihood else None
 
 
 class BARejectionSampling(_ParticleBelief):

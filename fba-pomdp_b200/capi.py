@@ -20,7 +20,8 @@ RNG_REPLAY, RNG_PHILOX = 0, 1
 # every symbol include/fba_pomdp_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "fba_ctx_create", "fba_ctx_destroy", "fba_last_error", "fba_ctx_stream", "fba_ctx_synchronize",
-    "fba_ctx_launch_count", "fba_model_create", "fba_model_destroy", "fba_model_add_structures",
+    "fba_ctx_launch_count", "fba_ctx_profile_begin", "fba_ctx_profile_end", "fba_ctx_profile_get",
+    "fba_model_create", "fba_model_destroy", "fba_model_add_structures",
     "fba_model_num_structures", "fba_model_structure_size", "fba_model_get_structure",
     "fba_belief_create", "fba_belief_destroy", "fba_belief_size", "fba_belief_stride",
     "fba_belief_init", "fba_belief_init_sampled", "fba_belief_upload", "fba_belief_download",
@@ -95,6 +96,9 @@ def lib():
             "fba_ctx_stream": (vp, [vp]),
             "fba_ctx_synchronize": (C.c_int, [vp]),
             "fba_ctx_launch_count": (i64, [vp]),
+            "fba_ctx_profile_begin": (C.c_int, [vp]),
+            "fba_ctx_profile_end": (C.c_int, [vp]),
+            "fba_ctx_profile_get": (C.c_int, [vp, C.c_char_p, vp, vp]),
             "fba_model_create": (C.c_int, [vp, vp, i32, pp]),
             "fba_model_destroy": (None, [vp]),
             "fba_model_add_structures": (C.c_int, [vp, i32, vp, vp, vp]),

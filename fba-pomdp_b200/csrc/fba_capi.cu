@@ -23,6 +23,15 @@ struct fba_ctx
     int sm_count         = 148;
     int64_t launches     = 0;
     std::string err;
+    // optional per-kernel CUDA-event timing (fba_ctx_profile_*)
+    bool profiling       = false;
+    struct Timed
+    {
+        const char* name;
+        cudaEvent_t start, stop;
+    };
+    std::vector<Timed> timed;
+    std::map<std::string, std::pair<double, int64_t>> kernel_ms;
     // scratch shared by the beliefs of this context
     uint32_t* d_words    = nullptr;
     size_t words_cap     = 0;
@@ -111,9 +120,24 @@ static inline int stream_grid(const fba_ctx* ctx, long long n_particles)
     return (int)std::max<long long>(1, std::min(need, cap));
 }
 
+static void profile_mark(fba_ctx* ctx, const char* name, bool begin)
+{
+    if (begin)
+    {
+        fba_ctx::Timed t{name, nullptr, nullptr};
+        cudaEventCreate(&t.start);
+        cudaEventCreate(&t.stop);
+        cudaEventRecord(t.start, ctx->stream);
+        ctx->timed.push_back(t);
+    } else
+        cudaEventRecord(ctx->timed.back().stop, ctx->stream);
+}
+
 #define LAUNCH(ctx, kernel, grid, block, ...)                                                      \
     do {                                                                                           \
+        if ((ctx)->profiling) profile_mark(ctx, #kernel, true);                                    \
         kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__);                                \
+        if ((ctx)->profiling) profile_mark(ctx, #kernel, false);                                   \
         ++(ctx)->launches;                                                                         \
         CU(ctx, cudaGetLastError());                                                               \
     } while (0)
@@ -175,6 +199,47 @@ extern "C" int fba_ctx_synchronize(fba_ctx* ctx)
 extern "C" int64_t fba_ctx_launch_count(const fba_ctx* ctx)
 {
     return ctx->launches;
+}
+
+// Per-kernel timing with CUDA events on the context's stream (bench.py's roofline numbers).
+extern "C" int fba_ctx_profile_begin(fba_ctx* ctx)
+{
+    if (!ctx) return FBA_ERR_INVALID;
+    ctx->kernel_ms.clear();
+    ctx->profiling = true;
+    return FBA_OK;
+}
+
+extern "C" int fba_ctx_profile_end(fba_ctx* ctx)
+{
+    if (!ctx) return FBA_ERR_INVALID;
+    ctx->profiling = false;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto& t : ctx->timed)
+    {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, t.start, t.stop);
+        auto& acc = ctx->kernel_ms[t.name];
+        acc.first += ms;
+        acc.second += 1;
+        cudaEventDestroy(t.start);
+        cudaEventDestroy(t.stop);
+    }
+    ctx->timed.clear();
+    return FBA_OK;
+}
+
+// total milliseconds and launch count of kernels whose name starts with `prefix`
+extern "C" int fba_ctx_profile_get(const fba_ctx* ctx, const char* prefix, double* total_ms, int64_t* count)
+{
+    if (!ctx || !prefix) return FBA_ERR_INVALID;
+    double ms = 0;
+    int64_t n = 0;
+    for (auto const& kv : ctx->kernel_ms)
+        if (kv.first.compare(0, strlen(prefix), prefix) == 0) ms += kv.second.first, n += kv.second.second;
+    if (total_ms) *total_ms = ms;
+    if (count) *count = n;
+    return FBA_OK;
 }
 
 // upload words[first, first+n) of the replay stream into the context scratch

@@ -1,0 +1,122 @@
+"""Particles sharded across the GPUs of one box: one process per GPU, `torch.distributed` for the
+plumbing (NCCL on GPUs, gloo in the CPU tests of the host logic).
+
+Per belief update the ranks exchange:
+  * an all-gather of one double per rank — the shard's un-normalised weight total — so every rank
+    forms the same global total and the same offspring quotas;
+  * particles only where resampling leaves a rank over / under its capacity: the surplus offspring
+    of over-quota ranks are shipped (all-to-all-v of particle records) into the empty slots of
+    under-quota ranks. With balanced weight shares that is O(sqrt(N/G)) particles per update.
+No collective touches the count blocks otherwise: the data path stays local to each GPU's HBM.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .beliefs import BAImportanceSampling, _check
+
+
+def offspring_quotas(shard_totals, n_total, u):
+    """Systematic allocation of n_total offspring to shards in proportion to their weight totals:
+    quota_g = #{j : (j + u) / n_total in (C_{g-1}, C_g]} with C the cumulative weight shares.
+    Deterministic given (shard_totals, n_total, u), so every rank computes the same answer.
+    Unbiased: E[quota_g] = n_total * W_g / W for u ~ U[0,1)."""
+    w = np.asarray(shard_totals, np.float64)
+    if not np.all(np.isfinite(w)) or w.sum() <= 0:
+        raise capi.FbaError(capi.ERR_INVALID, "offspring_quotas: total weight must be positive")
+    c = np.cumsum(w) / w.sum()
+    c[-1] = 1.0
+    edges = np.floor(c * n_total - u + 1.0).astype(np.int64)  # number of j with (j+u)/n <= C_g
+    edges = np.clip(edges, 0, n_total)
+    edges[-1] = n_total
+    q = np.diff(np.concatenate([[0], edges]))
+    return q.astype(np.int64)
+
+
+def exchange_plan(quotas, capacity):
+    """send[g][h] = particles rank g ships to rank h so that every rank ends with `capacity`
+    particles. Greedy in rank order; identical on every rank."""
+    q = np.asarray(quotas, np.int64)
+    G = len(q)
+    if q.sum() != capacity * G:
+        raise capi.FbaError(capi.ERR_INVALID, "exchange_plan: quotas do not sum to the total capacity")
+    surplus = np.maximum(q - capacity, 0)
+    deficit = np.maximum(capacity - q, 0)
+    send = np.zeros((G, G), np.int64)
+    h = 0
+    for g in range(G):
+        while surplus[g] > 0:
+            while deficit[h] == 0:
+                h += 1
+            k = min(surplus[g], deficit[h])
+            send[g, h] += k
+            surplus[g] -= k
+            deficit[h] -= k
+    return send
+
+
+class _RawCuda:
+    """Zero-copy view of a device pointer for torch.as_tensor."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1",
+                                         "data": (int(ptr), False), "version": 3, "strides": None}
+
+
+class ShardedBAImportanceSampling(BAImportanceSampling):
+    """BAImportanceSampling over G shards of n_local particles (PHILOX mode). Rank-local calls go to
+    the C ABI phases fba_belief_{propose,normalize,resample_shard,import}."""
+
+    def __init__(self, n_local, group=None):
+        super().__init__(n_local)
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.moved_last = 0
+
+    def rank_rng(self, seed):
+        """A PHILOX source whose key differs per rank, so shards draw independent streams."""
+        mixed = (int(seed) + (self.rank + 1) * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        return capi.Rng.philox(mixed)
+
+    def _all_gather_totals(self, local_total):
+        import torch
+        if self.world == 1:
+            return np.array([local_total])
+        dev = "cuda" if self.dist.get_backend(self.group) == "nccl" else "cpu"
+        mine = torch.tensor([local_total], dtype=torch.float64, device=dev)
+        out = torch.empty(self.world, dtype=torch.float64, device=dev)
+        self.dist.all_gather_into_tensor(out, mine, group=self.group)
+        return out.cpu().numpy()
+
+    def updateEstimation(self, a, o, rng, step_uniform=0.5):
+        """One global importance-sampling update + resample. `step_uniform` in [0,1) must be the
+        same on every rank (the shared systematic offset of the quota allocation)."""
+        import torch
+        L, h, ctx = self.L, self.h, self.ctx
+        n_local = self._n
+        local = C.c_double(0)
+        # NOTE: every rank must drive its shard with its own Philox seed (see rank_rng)
+        _check(ctx.h, L.fba_belief_propose(h, a, o, C.byref(rng), C.byref(local)))
+        totals = self._all_gather_totals(local.value)
+        total = float(totals.sum())
+        _check(ctx.h, L.fba_belief_normalize(h, total))
+        quotas = offspring_quotas(totals, n_local * self.world, step_uniform)
+        plan = exchange_plan(quotas, n_local)
+        _check(ctx.h, L.fba_belief_resample_shard(h, int(quotas[self.rank]), C.byref(rng)))
+        self.moved_last = int(plan.sum())
+        if self.moved_last:
+            rb = L.fba_belief_record_bytes(h)
+            n_out, n_in = int(plan[self.rank].sum()), int(plan[:, self.rank].sum())
+            assert n_out == L.fba_belief_export_count(h)
+            src = (torch.as_tensor(_RawCuda(L.fba_belief_export_ptr(h), n_out * rb), device="cuda")
+                   if n_out else torch.empty(0, dtype=torch.uint8, device="cuda"))
+            dst = (torch.as_tensor(_RawCuda(L.fba_belief_import_ptr(h, n_in), n_in * rb), device="cuda")
+                   if n_in else torch.empty(0, dtype=torch.uint8, device="cuda"))
+            self.dist.all_to_all_single(dst, src, [int(x) * rb for x in plan[:, self.rank]],
+                                        [int(x) * rb for x in plan[self.rank]], group=self.group)
+            torch.cuda.synchronize()
+            _check(ctx.h, L.fba_belief_import(h, n_in))
+        return total

@@ -128,6 +128,12 @@ int fba_ctx_synchronize(fba_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t fba_ctx_launch_count(const fba_ctx* ctx);
 
+/* per-kernel CUDA-event timing on the context's stream: begin, run calls, end, then query the
+ * summed milliseconds and launch count of the kernels whose name starts with `prefix` */
+int fba_ctx_profile_begin(fba_ctx* ctx);
+int fba_ctx_profile_end(fba_ctx* ctx);
+int fba_ctx_profile_get(const fba_ctx* ctx, const char* prefix, double* total_ms, int64_t* count);
+
 /* ---- model ---- */
 int fba_model_create(fba_ctx* ctx, const fba_model_desc* desc, int32_t max_structures, fba_model** out);
 void fba_model_destroy(fba_model* m);
