@@ -224,6 +224,10 @@ def main_ours(args):
         torch.cuda.synchronize()
         ctx.synchronize()
 
+    # setup (untimed, before the W warm-up steps): first-use costs that are not part of a step —
+    # NCCL communicator / channel setup, growth of the export / import staging buffers
+    for t in range(2):
+        step(t)
     for t in range(args.warmup):
         step(t)
     barrier()
@@ -239,6 +243,7 @@ def main_ours(args):
         step(args.warmup + t)
     ev1.record(stream)
     barrier()
+    phases = dict(getattr(b, "phase_ms", {}), moved=getattr(b, "moved_last", 0))
     ctx.profile_end()
     clocks = sampler.stop()
     launches = ctx.launches - launches0
@@ -289,6 +294,7 @@ def main_ours(args):
         "config": {"workload": WORKLOAD, "particles_per_gpu": n_local, "particles_total": n_local * world,
                    "count_cells_per_particle": C, "rng": "philox4x32-10", "resampling": "systematic",
                    "parallelism": "particles sharded, %d rank(s)" % world,
+                   "last_step_phases_ms_rank0": phases,
                    "l2": "inputs (%.1f GB of counts per GPU) exceed the 126 MB L2; no flush needed"
                          % (n_local * C * 4 / 1e9),
                    "e2e_note": "per step: (a,o) in as call arguments, likelihood (8 B) out, then "

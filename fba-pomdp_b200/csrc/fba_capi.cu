@@ -70,7 +70,8 @@ struct fba_belief
     double* aux      = nullptr; // R (replay) or cdf (native), N doubles
     double* tile     = nullptr; // tile sums
     double* scal     = nullptr; // device scalars: [0] total, [1] total_weight
-    int* anc         = nullptr; // ancestors, max(N, attempts wave)
+    int* anc         = nullptr; // ancestors
+    long long anc_cap = 0;
     double total_weight = 1.0;  // WeightedFilter::_total_weight (host mirror)
     double uniform_total = -1;  // sequential sum of N x (1/N), computed on first use
     bool suffix_valid = false;  // aux holds R for the current weights
@@ -544,7 +545,8 @@ extern "C" int fba_belief_create(fba_ctx* ctx, fba_model* m, int64_t N, int64_t 
     if (e == cudaSuccess) e = cudaMalloc(&b->aux, (size_t)N * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&b->tile, (size_t)n_tiles * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&b->scal, 4 * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&b->anc, (size_t)N * sizeof(int));
+    b->anc_cap = N + N / 8 + 1024; // room for an over-quota shard's surplus offspring
+    if (e == cudaSuccess) e = cudaMalloc(&b->anc, (size_t)b->anc_cap * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_total, sizeof(int));
     if (e != cudaSuccess)
     {
@@ -1416,13 +1418,14 @@ extern "C" int fba_belief_resample_shard(fba_belief* b, int64_t n_offspring, fba
         b->cdf_valid = false;
         return FBA_OK;
     }
-    int* anc = b->anc;
-    int* big = nullptr;
-    if (n_offspring > b->N)
+    if (n_offspring > b->anc_cap)
     {
-        CU(ctx, cudaMalloc(&big, n_offspring * sizeof(int)));
-        anc = big;
+        cudaFree(b->anc);
+        b->anc     = nullptr;
+        b->anc_cap = n_offspring + n_offspring / 8;
+        CU(ctx, cudaMalloc(&b->anc, (size_t)b->anc_cap * sizeof(int)));
     }
+    int* anc = b->anc;
     LAUNCH(ctx, k_pick_native, blocks_for(n_offspring), kThreads, b->aux, b->N, (long long)n_offspring, 1,
            philox_args(rng), anc);
     int const nx = b->cur ^ 1;
@@ -1442,7 +1445,6 @@ extern "C" int fba_belief_resample_shard(fba_belief* b, int64_t n_offspring, fba
                b->state[b->cur], b->sid[b->cur], anc, kept, surplus, b->xport, rb);
     }
     CU(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(big);
     flip(b);
     b->total_weight = 1.0;
     b->cdf_valid = b->suffix_valid = false;

@@ -1,0 +1,462 @@
+// C++ host adapters: the reference's own belief interfaces (samkatt/fba-pomdp) over the C ABI of
+// libfba_b200.so. A maintainer of the reference adds this header to the tree, links
+// libfba_b200.so, and registers the classes in factory::makeBABelief (src/beliefs/bayes-adaptive/
+// BABelief.cpp:16-73) under new --belief names — see INTEGRATION.md.
+//
+//   CudaBAImportanceSampling : beliefs::BABelief   stands in for beliefs::BAImportanceSampling
+//   CudaBARejectionSampling  : beliefs::BABelief   stands in for beliefs::BARejectionSampling
+//
+// Contract kept (src/beliefs/Belief.hpp:17-41, src/beliefs/bayes-adaptive/BABelief.hpp:22-35):
+// initiate / free / sample / updateEstimation / resetDomainStateDistribution with the same
+// argument meaning; errors are thrown as std::string like the reference's own beliefs do;
+// sample() returns a BORROWED BAState* owned by the belief (valid until the next sample / update),
+// whose _domain_state may be poked and restored by RBAPOUCT (RBAPOUCT.cpp:92-106).
+//
+// Everything domain specific is obtained by PROBING the reference's own objects, so any domain the
+// reference supports works unchanged:
+//   * reward / terminal: BADomainExtension::{reward,terminal} evaluated on all (s,a,s') once and
+//     stored as the two separable tables of FBA_DOM_TABLE (an error is thrown if a domain's reward
+//     is not of the form f(s,a) + g(a,s'));
+//   * prior: the reference's BAPrior runs on the host (BAPOMDP::sampleStartState) and its particles
+//     are uploaded — priors stay bit-identical;
+//   * domain start states (initiate, resetDomainStateDistribution): drawn by the reference's own
+//     domain on the host (N cheap calls) and uploaded.
+// The heavy per-particle work — step, likelihood, normalisation, resampling, copies — runs on the GPU.
+//
+// This header only uses the reference's PUBLIC API. It is compiled and exercised by
+// oracle/ref_harness.cpp (ref_adapter_selftest) so that it cannot rot.
+#ifndef FBA_B200_CUDA_BELIEFS_HPP
+#define FBA_B200_CUDA_BELIEFS_HPP
+
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "fba_pomdp_b200.h"
+
+#include "bayes-adaptive/models/factored/FBAPOMDP.hpp"
+#include "bayes-adaptive/models/table/BAPOMDP.hpp"
+#include "bayes-adaptive/states/factored/BABNModel.hpp"
+#include "bayes-adaptive/states/factored/FBAPOMDPState.hpp"
+#include "bayes-adaptive/states/table/BAPOMDPState.hpp"
+#include "beliefs/bayes-adaptive/BABelief.hpp"
+#include "environment/Action.hpp"
+#include "environment/Observation.hpp"
+#include "environment/State.hpp"
+#include "utils/index.hpp"
+#include "utils/random.hpp"
+
+namespace fba_b200 {
+
+inline void check(fba_ctx* ctx, int rc, char const* what)
+{
+    if (rc != FBA_OK)
+        throw std::string("fba_b200: ") + what + ": " + (ctx ? fba_last_error(ctx) : "no context");
+}
+
+// One GPU context + the uploaded description of one BAPOMDP / FBAPOMDP.
+class CudaSimulator
+{
+public:
+    CudaSimulator(BAPOMDP const& sim, int device = 0, int max_structures = 4096) : _sim(sim)
+    {
+        int rc = fba_ctx_create(device, &_ctx);
+        if (rc == FBA_ERR_NO_DEVICE) throw std::string("fba_b200: no CUDA device (there is no CPU fallback)");
+        check(nullptr, rc, "fba_ctx_create");
+
+        auto const* size = sim.domainSize();
+        _fbapomdp        = dynamic_cast<::bayes_adaptive::factored::FBAPOMDP const*>(&sim);
+
+        fba_model_desc d = {};
+        d.S = size->_S, d.A = size->_A, d.O = size->_O;
+        if (_fbapomdp)
+        {
+            _feat_s = _fbapomdp->domainFeatureSize()->_S;
+            _feat_o = _fbapomdp->domainFeatureSize()->_O;
+        } else
+        {
+            _feat_s = {size->_S};
+            _feat_o = {size->_O};
+        }
+        d.tabular          = _fbapomdp ? 0 : 1;
+        d.n_state_features = (int)_feat_s.size();
+        d.n_obs_features   = (int)_feat_o.size();
+        for (size_t i = 0; i < _feat_s.size(); ++i) d.state_feature_sizes[i] = _feat_s[i];
+        for (size_t i = 0; i < _feat_o.size(); ++i) d.obs_feature_sizes[i] = _feat_o[i];
+
+        probeRewards(d);
+        d.domain      = FBA_DOM_TABLE;
+        d.action_draw = FBA_ACT_UNIFORM_INT; // rollouts only; all reference domains draw uniformly
+        d.start_kind  = FBA_START_CONST;     // unused: start states come from the host domain
+
+        check(_ctx, fba_model_create(_ctx, &d, max_structures, &_model), "fba_model_create");
+        _steps.reset(new ::bayes_adaptive::factored::BABNModel::Indexing_Steps(
+            indexing::stepSize(_feat_s), indexing::stepSize(_feat_o)));
+    }
+
+    ~CudaSimulator()
+    {
+        fba_model_destroy(_model);
+        fba_ctx_destroy(_ctx);
+    }
+    CudaSimulator(CudaSimulator const&) = delete;
+    CudaSimulator& operator=(CudaSimulator const&) = delete;
+
+    fba_ctx* ctx() const { return _ctx; }
+    fba_model* model() const { return _model; }
+    BAPOMDP const& sim() const { return _sim; }
+    bool factored() const { return _fbapomdp != nullptr; }
+    int A() const { return _sim.domainSize()->_A; }
+    int S() const { return _sim.domainSize()->_S; }
+    int O() const { return _sim.domainSize()->_O; }
+    int FS() const { return (int)_feat_s.size(); }
+    int FO() const { return (int)_feat_o.size(); }
+
+    // structure id + count block (this repo's layout) of one reference particle
+    int32_t describe(BAState const* p, std::vector<float>* counts) const
+    {
+        std::vector<uint32_t> tp((size_t)A() * FS()), op((size_t)A() * FO());
+        counts->clear();
+        if (!factored())
+        {
+            // BAFlatModel::count is the only public cell accessor; it is non-const because it may
+            // materialise a copy-on-write row (BAFlatModel.cpp:185-252) — values are unchanged
+            auto model = const_cast<BAPOMDPState*>(static_cast<BAPOMDPState const*>(p))->model();
+            IndexAction a(0);
+            IndexState s(0), s2(0);
+            IndexObservation o(0);
+            for (int ai = 0; ai < A(); ++ai)
+            {
+                a.index(ai);
+                tp[ai] = 1u, op[ai] = 1u;
+                for (int si = 0; si < S(); ++si)
+                    for (int ti = 0; ti < S(); ++ti)
+                    {
+                        s.index(si), s2.index(ti);
+                        counts->push_back(model->count(&s, &a, &s2));
+                    }
+                for (int ti = 0; ti < S(); ++ti)
+                    for (int oi = 0; oi < O(); ++oi)
+                    {
+                        s2.index(ti), o.index(oi);
+                        counts->push_back(model->count(&a, &s2, &o));
+                    }
+            }
+        } else
+        {
+            auto model = const_cast<FBAPOMDPState*>(static_cast<FBAPOMDPState const*>(p))->model();
+            IndexAction a(0);
+            for (int ai = 0; ai < A(); ++ai)
+            {
+                a.index(ai);
+                for (int f = 0; f < FS(); ++f)
+                    tp[(size_t)ai * FS() + f] = dumpNode(model->transitionNode(&a, f), _feat_s[f], counts);
+                for (int g = 0; g < FO(); ++g)
+                    op[(size_t)ai * FO() + g] = dumpNode(model->observationNode(&a, g), _feat_o[g], counts);
+            }
+        }
+        int32_t id = -1;
+        check(_ctx, fba_model_add_structures(_model, 1, tp.data(), op.data(), &id), "fba_model_add_structures");
+        return id;
+    }
+
+    // the reverse: a host-side reference particle from a downloaded block (Belief::sample())
+    BAState* materialise(int32_t struct_id, int32_t state, std::vector<float> const& counts) const
+    {
+        auto domain_state = _sim.copyDomainState(_sim.domainState(state));
+        if (!factored())
+        {
+            auto phi = std::make_shared<std::vector<float>>((size_t)S() * A() * S());
+            auto psi = std::make_shared<std::vector<float>>((size_t)A() * S() * O());
+            size_t k = 0;
+            for (int a = 0; a < A(); ++a)
+            {
+                for (int s = 0; s < S(); ++s)
+                    for (int t = 0; t < S(); ++t) (*phi)[indexing::threeToOne(s, a, t, A(), S())] = counts[k++];
+                for (int t = 0; t < S(); ++t)
+                    for (int o = 0; o < O(); ++o) (*psi)[indexing::threeToOne(a, t, o, S(), O())] = counts[k++];
+            }
+            return new BAPOMDPState(
+                domain_state, ::bayes_adaptive::table::BAFlatModel(phi, psi, _sim.domainSize()));
+        }
+        std::vector<uint32_t> tp((size_t)A() * FS()), op((size_t)A() * FO());
+        check(_ctx, fba_model_get_structure(_model, struct_id, tp.data(), op.data()), "fba_model_get_structure");
+        std::vector<DBNNode> T, O_;
+        size_t k = 0;
+        auto const* fsize = _fbapomdp->domainFeatureSize();
+        for (int a = 0; a < A(); ++a)
+        {
+            for (int f = 0; f < FS(); ++f) T.emplace_back(buildNode(fsize, tp[(size_t)a * FS() + f], _feat_s[f], counts, &k));
+            for (int g = 0; g < FO(); ++g) O_.emplace_back(buildNode(fsize, op[(size_t)a * FO() + g], _feat_o[g], counts, &k));
+        }
+        return new FBAPOMDPState(
+            domain_state,
+            ::bayes_adaptive::factored::BABNModel(_sim.domainSize(), fsize, _steps.get(), std::move(T), std::move(O_)));
+    }
+
+private:
+    BAPOMDP const& _sim;
+    ::bayes_adaptive::factored::FBAPOMDP const* _fbapomdp = nullptr;
+    fba_ctx* _ctx     = nullptr;
+    fba_model* _model = nullptr;
+    std::vector<int> _feat_s, _feat_o;
+    std::vector<double> _rew_sa, _rew_as2;
+    std::vector<uint8_t> _term_sa, _term_as2;
+    std::unique_ptr<::bayes_adaptive::factored::BABNModel::Indexing_Steps> _steps;
+
+    std::vector<int> parentsOf(uint32_t mask) const
+    {
+        std::vector<int> p;
+        for (int f = 0; f < FS(); ++f)
+            if (mask & (1u << f)) p.push_back(f);
+        return p;
+    }
+
+    uint32_t dumpNode(DBNNode& node, int range, std::vector<float>* counts) const
+    {
+        auto const& parents = *node.parents();
+        uint32_t mask       = 0;
+        std::vector<int> sizes;
+        for (auto p : parents)
+        {
+            mask |= 1u << p;
+            sizes.push_back(_feat_s[p]);
+        }
+        std::vector<int> values(parents.size(), 0);
+        do {
+            for (int v = 0; v < range; ++v) counts->push_back(node.count(values, v));
+        } while (!parents.empty() && !indexing::increment(values, sizes));
+        return mask;
+    }
+
+    DBNNode buildNode(Domain_Feature_Size const* fsize, uint32_t mask, int range,
+                      std::vector<float> const& counts, size_t* k) const
+    {
+        auto parents = parentsOf(mask);
+        std::vector<int> sizes;
+        for (auto p : parents) sizes.push_back(_feat_s[p]);
+        DBNNode node(&fsize->_S, parents, range);
+        std::vector<int> values(parents.size(), 0);
+        do {
+            for (int v = 0; v < range; ++v) node.count(values, v) = counts[(*k)++];
+        } while (!parents.empty() && !indexing::increment(values, sizes));
+        return node;
+    }
+
+    // BADomainExtension::{reward,terminal} -> separable tables (see the header comment)
+    void probeRewards(fba_model_desc& d)
+    {
+        int const S_ = _sim.domainSize()->_S, A_ = _sim.domainSize()->_A;
+        _rew_sa.assign((size_t)S_ * A_, 0.0), _rew_as2.assign((size_t)A_ * S_, 0.0);
+        _term_sa.assign((size_t)S_ * A_, 1), _term_as2.assign((size_t)A_ * S_, 1);
+        std::vector<double> f((size_t)S_ * A_ * S_);
+        std::vector<uint8_t> t((size_t)S_ * A_ * S_);
+        IndexAction a(0);
+        // the simulator exposes reward / terminal only through step(); the extension's functions are
+        // reached through a KeepCounts-free route: BAPOMDP::domainState + the public extension API
+        for (int s = 0; s < S_; ++s)
+            for (int ai = 0; ai < A_; ++ai)
+                for (int s2 = 0; s2 < S_; ++s2)
+                {
+                    a.index(ai);
+                    size_t const k = ((size_t)s * A_ + ai) * S_ + s2;
+                    f[k]           = rewardOf(s, &a, s2, &t[k]);
+                }
+        for (int ai = 0; ai < A_; ++ai)
+            for (int s2 = 0; s2 < S_; ++s2) _rew_as2[(size_t)ai * S_ + s2] = f[((size_t)0 * A_ + ai) * S_ + s2];
+        for (int s = 0; s < S_; ++s)
+            for (int ai = 0; ai < A_; ++ai)
+                _rew_sa[(size_t)s * A_ + ai] = f[((size_t)s * A_ + ai) * S_] - f[((size_t)0 * A_ + ai) * S_];
+        for (int s = 0; s < S_; ++s)
+            for (int ai = 0; ai < A_; ++ai)
+                for (int s2 = 0; s2 < S_; ++s2)
+                {
+                    size_t const k = ((size_t)s * A_ + ai) * S_ + s2;
+                    if (!t[k]) _term_sa[(size_t)s * A_ + ai] = 0, _term_as2[(size_t)ai * S_ + s2] = 0;
+                }
+        for (int s = 0; s < S_; ++s)
+            for (int ai = 0; ai < A_; ++ai)
+                for (int s2 = 0; s2 < S_; ++s2)
+                {
+                    size_t const k = ((size_t)s * A_ + ai) * S_ + s2;
+                    if (f[k] != _rew_sa[(size_t)s * A_ + ai] + _rew_as2[(size_t)ai * S_ + s2])
+                        throw std::string("fba_b200: this domain's reward is not f(s,a) + g(a,s')");
+                    if ((t[k] != 0) != (_term_sa[(size_t)s * A_ + ai] || _term_as2[(size_t)ai * S_ + s2]))
+                        throw std::string("fba_b200: this domain's terminal is not f(s,a) || g(a,s')");
+                }
+        d.rew_sa = _rew_sa.data(), d.rew_as2 = _rew_as2.data();
+        d.term_sa = _term_sa.data(), d.term_as2 = _term_as2.data();
+    }
+
+    // reward / terminal of (s,a,s') as BAPOMDP::step reports them (BAPOMDP.cpp:131-132), obtained
+    // by stepping a scratch particle whose counts force the transition s -> s2 … too slow; instead
+    // the extension is reached through the friend-free public hook below.
+    double rewardOf(int s, Action const* a, int s2, uint8_t* terminal) const;
+};
+
+// Specialisation point: how to reach BADomainExtension from a BAPOMDP. In the reference the
+// extension is a protected member (BAPOMDP.hpp:129); a maintainer adds the two-line public accessor
+// shown in INTEGRATION.md. Builds that cannot touch the reference (oracle/ref_harness.cpp) compile
+// with -fno-access-control and define FBA_B200_PRIVATE_ACCESS.
+#ifdef FBA_B200_PRIVATE_ACCESS
+inline double CudaSimulator::rewardOf(int s, Action const* a, int s2, uint8_t* terminal) const
+{
+    auto ext  = _sim._ba_domain_ext.get();
+    auto st   = ext->getState(s);
+    auto st2  = ext->getState(s2);
+    *terminal = ext->terminal(st, a, st2).terminated();
+    return ext->reward(st, a, st2).toDouble();
+}
+#else
+inline double CudaSimulator::rewardOf(int s, Action const* a, int s2, uint8_t* terminal) const
+{
+    auto ext  = _sim.domainExtension(); // accessor added per INTEGRATION.md
+    auto st   = ext->getState(s);
+    auto st2  = ext->getState(s2);
+    *terminal = ext->terminal(st, a, st2).terminated();
+    return ext->reward(st, a, st2).toDouble();
+}
+#endif
+
+// Shared plumbing of the two belief adapters.
+class CudaParticleBelief : public beliefs::BABelief
+{
+public:
+    CudaParticleBelief(size_t n, bool weighted, uint64_t seed, int device) :
+            _n(n), _weighted(weighted), _device(device)
+    {
+        _rng.mode   = FBA_RNG_PHILOX;
+        _rng.words  = nullptr;
+        _rng.n_words = _rng.cursor = 0;
+        _rng.seed   = seed;
+        _rng.offset = 0;
+    }
+    ~CudaParticleBelief() override { release(); }
+
+    void initiate(POMDP const& d) override
+    {
+        auto const& sim = dynamic_cast<BAPOMDP const&>(d);
+        _cuda.reset(new CudaSimulator(sim, _device));
+        // Belief::initiate = N x sampleStartState (BAImportanceSampling.cpp:49-60): the reference's
+        // prior and domain run on the host, the particles are uploaded
+        std::vector<int32_t> state(_n), sid(_n);
+        std::vector<std::vector<float>> blocks(_n);
+        size_t stride = 0;
+        for (size_t i = 0; i < _n; ++i)
+        {
+            auto p   = static_cast<BAState const*>(d.sampleStartState());
+            state[i] = p->_domain_state->index();
+            sid[i]   = _cuda->describe(p, &blocks[i]);
+            stride   = std::max(stride, blocks[i].size());
+            d.releaseState(p);
+        }
+        check(_cuda->ctx(), fba_belief_create(_cuda->ctx(), _cuda->model(), (int64_t)_n, (int64_t)stride,
+                                               _weighted ? 1 : 0, &_belief),
+              "fba_belief_create");
+        stride = (size_t)fba_belief_stride(_belief);
+        std::vector<float> flat(_n * stride, 0.0f);
+        for (size_t i = 0; i < _n; ++i) std::copy(blocks[i].begin(), blocks[i].end(), flat.begin() + i * stride);
+        std::vector<double> w(_n, 1.0 / (double)_n);
+        check(_cuda->ctx(),
+              fba_belief_upload(_belief, 0, (int64_t)_n, state.data(), sid.data(), flat.data(),
+                                _weighted ? w.data() : nullptr),
+              "fba_belief_upload");
+    }
+
+    void free(POMDP const& /*d*/) override { release(); }
+
+    State const* sample() const override
+    {
+        int64_t i = 0;
+        check(_cuda->ctx(), fba_belief_sample(_belief, &_rng, &i), "fba_belief_sample");
+        size_t const stride = (size_t)fba_belief_stride(_belief);
+        std::vector<float> counts(stride);
+        int32_t state = 0, sid = 0;
+        check(_cuda->ctx(), fba_belief_download(_belief, i, 1, &state, &sid, counts.data(), nullptr),
+              "fba_belief_download");
+        dropSample();
+        _sample = _cuda->materialise(sid, state, counts);
+        return _sample;
+    }
+
+    void resetDomainStateDistribution(BAPOMDP const& bapomdp) override
+    {
+        // weighted: N weighted draws with replacement first (BAImportanceSampling.cpp:90-111)
+        if (_weighted) check(_cuda->ctx(), fba_belief_resample(_belief, &_rng), "fba_belief_resample");
+        // then a fresh domain start state per particle, drawn by the reference's own domain
+        std::vector<int32_t> state(_n);
+        for (size_t i = 0; i < _n; ++i)
+        {
+            auto s   = bapomdp.sampleDomainState();
+            state[i] = s->index();
+            bapomdp.releaseDomainState(s);
+        }
+        check(_cuda->ctx(), fba_belief_upload(_belief, 0, (int64_t)_n, state.data(), nullptr, nullptr, nullptr),
+              "fba_belief_upload");
+    }
+
+    fba_belief* handle() const { return _belief; }
+    CudaSimulator const& cuda() const { return *_cuda; }
+
+protected:
+    size_t _n;
+    bool _weighted;
+    int _device;
+    mutable fba_rng _rng;
+    std::unique_ptr<CudaSimulator> _cuda;
+    fba_belief* _belief            = nullptr;
+    mutable BAState const* _sample = nullptr;
+
+    void dropSample() const
+    {
+        if (_sample)
+        {
+            _cuda->sim().releaseState(_sample);
+            _sample = nullptr;
+        }
+    }
+    void release()
+    {
+        if (_cuda) dropSample();
+        fba_belief_destroy(_belief);
+        _belief = nullptr;
+        _cuda.reset();
+    }
+};
+
+class CudaBAImportanceSampling : public CudaParticleBelief
+{
+public:
+    explicit CudaBAImportanceSampling(size_t n, uint64_t seed = 42, int device = 0) :
+            CudaParticleBelief(n, true, seed, device)
+    {
+        if (n < 1) throw("cannot initiate BAImportanceSampling with n " + std::to_string(n)); // as :19-22
+    }
+    void updateEstimation(Action const* a, Observation const* o, POMDP const& /*d*/) override
+    {
+        check(_cuda->ctx(), fba_belief_update_estimation(_belief, a->index(), o->index(), &_rng, nullptr),
+              "fba_belief_update_estimation");
+    }
+};
+
+class CudaBARejectionSampling : public CudaParticleBelief
+{
+public:
+    explicit CudaBARejectionSampling(size_t n, uint64_t seed = 42, int device = 0) :
+            CudaParticleBelief(n, false, seed, device)
+    {
+        if (n < 1) throw("cannot initiate RejectionSampling with n = " + std::to_string(n)); // as :13-16
+    }
+    void updateEstimation(Action const* a, Observation const* o, POMDP const& /*d*/) override
+    {
+        int64_t attempts = 0;
+        check(_cuda->ctx(), fba_belief_reject_sample(_belief, a->index(), o->index(), &_rng, &attempts),
+              "fba_belief_reject_sample");
+    }
+};
+
+} // namespace fba_b200
+
+#endif // FBA_B200_CUDA_BELIEFS_HPP

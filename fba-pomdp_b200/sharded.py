@@ -94,19 +94,26 @@ class ShardedBAImportanceSampling(BAImportanceSampling):
     def updateEstimation(self, a, o, rng, step_uniform=0.5):
         """One global importance-sampling update + resample. `step_uniform` in [0,1) must be the
         same on every rank (the shared systematic offset of the quota allocation)."""
+        import time
         import torch
         L, h, ctx = self.L, self.h, self.ctx
         n_local = self._n
         local = C.c_double(0)
+        t0 = time.perf_counter()
         # NOTE: every rank must drive its shard with its own Philox seed (see rank_rng)
         _check(ctx.h, L.fba_belief_propose(h, a, o, C.byref(rng), C.byref(local)))
+        t1 = time.perf_counter()
         totals = self._all_gather_totals(local.value)
         total = float(totals.sum())
+        t2 = time.perf_counter()
         _check(ctx.h, L.fba_belief_normalize(h, total))
         quotas = offspring_quotas(totals, n_local * self.world, step_uniform)
         plan = exchange_plan(quotas, n_local)
         _check(ctx.h, L.fba_belief_resample_shard(h, int(quotas[self.rank]), C.byref(rng)))
+        t3 = time.perf_counter()
         self.moved_last = int(plan.sum())
+        self.phase_ms = {"propose": (t1 - t0) * 1e3, "all_gather": (t2 - t1) * 1e3,
+                         "normalize+resample": (t3 - t2) * 1e3, "exchange": 0.0}
         if self.moved_last:
             rb = L.fba_belief_record_bytes(h)
             n_out, n_in = int(plan[self.rank].sum()), int(plan[:, self.rank].sum())
@@ -119,4 +126,5 @@ class ShardedBAImportanceSampling(BAImportanceSampling):
                                         [int(x) * rb for x in plan[self.rank]], group=self.group)
             torch.cuda.synchronize()
             _check(ctx.h, L.fba_belief_import(h, n_in))
+            self.phase_ms["exchange"] = (time.perf_counter() - t3) * 1e3
         return total
