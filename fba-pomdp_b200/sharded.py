@@ -56,6 +56,19 @@ def exchange_plan(quotas, capacity):
     return send
 
 
+def exchange_records(dist, group, plan, rank, src, record_bytes, dst=None):
+    """Ships particle records according to `plan` (exchange_plan): `src` holds this rank's surplus
+    records (uint8, plan[rank].sum() * record_bytes), returns the records received. Works on CUDA
+    tensors over NCCL and on CPU tensors over gloo."""
+    import torch
+    n_in = int(plan[:, rank].sum())
+    if dst is None:
+        dst = torch.empty(n_in * record_bytes, dtype=torch.uint8, device=src.device)
+    dist.all_to_all_single(dst, src, [int(x) * record_bytes for x in plan[:, rank]],
+                           [int(x) * record_bytes for x in plan[rank]], group=group)
+    return dst
+
+
 class _RawCuda:
     """Zero-copy view of a device pointer for torch.as_tensor."""
 
@@ -122,8 +135,7 @@ class ShardedBAImportanceSampling(BAImportanceSampling):
                    if n_out else torch.empty(0, dtype=torch.uint8, device="cuda"))
             dst = (torch.as_tensor(_RawCuda(L.fba_belief_import_ptr(h, n_in), n_in * rb), device="cuda")
                    if n_in else torch.empty(0, dtype=torch.uint8, device="cuda"))
-            self.dist.all_to_all_single(dst, src, [int(x) * rb for x in plan[:, self.rank]],
-                                        [int(x) * rb for x in plan[self.rank]], group=self.group)
+            exchange_records(self.dist, self.group, plan, self.rank, src, rb, dst)
             torch.cuda.synchronize()
             _check(ctx.h, L.fba_belief_import(h, n_in))
             self.phase_ms["exchange"] = (time.perf_counter() - t3) * 1e3

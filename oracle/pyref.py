@@ -62,6 +62,9 @@ def lib():
         L.ref_reward.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.ref_env_script.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                      C.c_void_p]
+        L.ref_adapter_episodes.restype = C.c_int
+        L.ref_adapter_episodes.argtypes = [C.c_void_p, C.c_int, C.c_long, C.c_char_p, C.c_int, C.c_int,
+                                           C.c_void_p]
         _lib = L
     return _lib
 
@@ -184,3 +187,11 @@ class Ref:
         f = np.zeros(steps, np.int32)
         self.L.ref_env_script(self.h, steps, horizon, _p(a), _p(o), _p(f))
         return a, o, f
+
+    def adapter_episodes(self, kind, n, planner="po-uct", sims=64, episodes=10):
+        """The reference's own episode loop + planner with belief `kind` (0: reference IS, 1: this
+        repo's CudaBAImportanceSampling, 2: reference RS, 3: CudaBARejectionSampling)."""
+        out = np.zeros(episodes, np.float64)
+        if self.L.ref_adapter_episodes(self.h, kind, n, planner.encode(), sims, episodes, _p(out)):
+            raise RuntimeError("reference/adapter: " + self.L.ref_error(self.h).decode())
+        return out

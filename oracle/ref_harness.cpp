@@ -57,6 +57,15 @@
 #include "planners/bayes-adaptive/RBAPOUCT.hpp"
 #include "utils/random.hpp"
 
+// the C++ host adapters of this repo (the drop-in beliefs), compiled against the reference here
+#define FBA_B200_PRIVATE_ACCESS
+#include "CudaBeliefs.hpp"
+#include "environment/Discount.hpp"
+#include "environment/Horizon.hpp"
+#include "environment/Return.hpp"
+#include "experiments/Episode.hpp"
+#include "planners/Planner.hpp"
+
 INITIALIZE_EASYLOGGINGPP
 
 namespace {
@@ -596,6 +605,56 @@ void ref_env_script(void* hv, int steps, int horizon, int* actions, int* observa
         }
         env->releaseState(s);
     }
+}
+
+
+/**** drop-in check: the reference's own episode loop + planner, with this repo's CUDA belief ****/
+// Runs `episodes` episodes of experiment::bapomdp::run's inner loop (BAPOMDPExperiment.cpp:46-75):
+// initiate once, then per episode resetDomainStateDistribution + episode::run with the reference's
+// planner (--planner string). kind: 0 = the reference's BAImportanceSampling (CPU),
+// 1 = fba_b200::CudaBAImportanceSampling, 2 = the reference's BARejectionSampling,
+// 3 = fba_b200::CudaBARejectionSampling. returns[e] = discounted return of episode e.
+// rc: 0 ok, 1 error (see ref_error).
+int ref_adapter_episodes(void* hv, int kind, long n, char const* planner, int sims, int episodes,
+                         double* returns)
+{
+    auto h = static_cast<Handle*>(hv);
+    try
+    {
+        auto conf                                = h->conf;
+        conf.planner                             = planner;
+        conf.planner_conf.mcts_simulation_amount = sims;
+        conf.planner_conf.mcts_max_depth         = conf.horizon;
+        auto plan = factory::makeBAPlanner(conf);
+
+        std::unique_ptr<beliefs::BABelief> belief;
+        if (kind == 0) belief.reset(new beliefs::BAImportanceSampling(n));
+        else if (kind == 1)
+            belief.reset(new fba_b200::CudaBAImportanceSampling(n));
+        else if (kind == 2)
+            belief.reset(new beliefs::BARejectionSampling(n));
+        else
+            belief.reset(new fba_b200::CudaBARejectionSampling(n));
+
+        belief->initiate(*h->sim);
+        for (int e = 0; e < episodes; ++e)
+        {
+            belief->resetDomainStateDistribution(*h->sim);
+            auto r = episode::run(
+                *plan, *belief, *h->env, *h->sim, Horizon(conf.horizon), Discount(conf.discount));
+            returns[e] = r.ret.toDouble();
+        }
+        belief->free(*h->sim);
+    } catch (std::string const& e)
+    {
+        h->err = e;
+        return 1;
+    } catch (char const* e)
+    {
+        h->err = e;
+        return 1;
+    }
+    return 0;
 }
 
 } // extern "C"

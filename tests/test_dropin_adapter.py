@@ -1,0 +1,36 @@
+"""GPU: the C++ host adapters (fba-pomdp_b200/host/CudaBeliefs.hpp) dropped into the reference's OWN
+episode loop and POMCP planner (oracle/ref_harness.cpp:ref_adapter_episodes, compiled against the
+unmodified reference). The adapters run in PHILOX mode, so the check is statistical: episode returns
+under the CUDA belief agree with returns under the reference's CPU belief within 4 standard errors."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+pyref = pytest.importorskip("pyref")
+if not pyref.available():
+    pytest.skip("oracle/_ref/libfba_ref.so not built", allow_module_level=True)
+
+CASES = [
+    # domain, kwargs, belief kinds (reference, cuda), particles, episodes
+    ("episodic-tiger", dict(), (0, 1), 256, 80),
+    ("episodic-tiger", dict(), (2, 3), 256, 80),
+    ("episodic-factored-tiger", dict(size=3, factored=True), (0, 1), 128, 40),
+    ("centered-collision-avoidance", dict(size=1, width=3, height=3, factored=True), (0, 1), 128, 40),
+    ("linear-sysadmin", dict(size=3, factored=True), (0, 1), 64, 20),
+    ("gridworld", dict(size=3), (0, 1), 16, 10),
+]
+
+
+@pytest.mark.parametrize("domain,kw,kinds,n,episodes", CASES)
+def test_reference_episode_loop_with_cuda_belief(domain, kw, kinds, n, episodes):
+    horizon = 8
+    r = pyref.Ref(domain, horizon=horizon, seed="7", **kw)
+    try:
+        ref = r.adapter_episodes(kinds[0], n, "po-uct", 48, episodes)
+        ours = r.adapter_episodes(kinds[1], n, "po-uct", 48, episodes)
+    finally:
+        r.close()
+    assert np.all(np.isfinite(ours))
+    se = np.sqrt(ref.var(ddof=1) / len(ref) + ours.var(ddof=1) / len(ours)) + 1e-9
+    assert abs(ref.mean() - ours.mean()) <= 4.0 * se + 1e-6, (ref.mean(), ours.mean(), se)
