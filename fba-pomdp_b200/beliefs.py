@@ -52,6 +52,9 @@ class Context:
     def synchronize(self):
         _check(self.h, self.L.fba_ctx_synchronize(self.h))
 
+    def set_option(self, name, value):
+        _check(self.h, self.L.fba_ctx_set_option(self.h, name.encode(), int(value)))
+
     def profile_begin(self):
         _check(self.h, self.L.fba_ctx_profile_begin(self.h))
 
@@ -63,6 +66,18 @@ class Context:
         ms, n = C.c_double(0), C.c_int64(0)
         _check(self.h, self.L.fba_ctx_profile_get(self.h, prefix.encode(), C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def kernel_times(self):
+        """{kernel name: (total ms, launches)} since profile_begin."""
+        n = self.L.fba_ctx_profile_list(self.h, None, 0)
+        buf = C.create_string_buffer(int(n))
+        self.L.fba_ctx_profile_list(self.h, buf, n)
+        out = {}
+        for item in buf.value.decode().split(";"):
+            if item:
+                name, ms, cnt = item.rsplit(":", 2)
+                out[name] = (float(ms), int(cnt))
+        return out
 
     def close(self):
         if self.h:
@@ -200,6 +215,12 @@ class _ParticleBelief:
 
     def size(self):
         return self.L.fba_belief_size(self.h)
+
+    def resample_stats(self):
+        """(count blocks copied, resamples run) by the in-place resampler since creation."""
+        c, r = C.c_int64(0), C.c_int64(0)
+        _check(self.ctx.h, self.L.fba_belief_resample_stats(self.h, C.byref(c), C.byref(r)))
+        return c.value, r.value
 
     def free(self, _simulator=None):
         """Belief::free (Belief.hpp:29)."""

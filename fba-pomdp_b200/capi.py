@@ -20,7 +20,7 @@ RNG_REPLAY, RNG_PHILOX = 0, 1
 # every symbol include/fba_pomdp_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "fba_ctx_create", "fba_ctx_destroy", "fba_last_error", "fba_ctx_stream", "fba_ctx_synchronize",
-    "fba_ctx_launch_count", "fba_ctx_profile_begin", "fba_ctx_profile_end", "fba_ctx_profile_get",
+    "fba_ctx_launch_count", "fba_ctx_set_option", "fba_ctx_profile_begin", "fba_ctx_profile_end", "fba_ctx_profile_get", "fba_ctx_profile_list",
     "fba_model_create", "fba_model_destroy", "fba_model_add_structures",
     "fba_model_num_structures", "fba_model_structure_size", "fba_model_get_structure",
     "fba_belief_create", "fba_belief_destroy", "fba_belief_size", "fba_belief_stride",
@@ -28,7 +28,8 @@ SYMBOLS = [
     "fba_belief_total_weight", "fba_belief_update", "fba_belief_resample",
     "fba_belief_update_estimation", "fba_belief_reset_domain_states", "fba_belief_sample",
     "fba_belief_reject_sample", "fba_belief_reinvigorate", "fba_rollouts", "fba_belief_propose",
-    "fba_belief_normalize", "fba_belief_resample_shard", "fba_belief_export_count",
+    "fba_belief_normalize", "fba_belief_resample_shard", "fba_belief_resample_stats",
+    "fba_belief_export_count",
     "fba_belief_export_ptr", "fba_belief_import_ptr", "fba_belief_record_bytes", "fba_belief_import",
     "fba_belief_counts_ptr", "fba_belief_state_ptr", "fba_belief_weight_ptr",
 ]
@@ -96,9 +97,12 @@ def lib():
             "fba_ctx_stream": (vp, [vp]),
             "fba_ctx_synchronize": (C.c_int, [vp]),
             "fba_ctx_launch_count": (i64, [vp]),
+            "fba_ctx_set_option": (C.c_int, [vp, C.c_char_p, i64]),
             "fba_ctx_profile_begin": (C.c_int, [vp]),
             "fba_ctx_profile_end": (C.c_int, [vp]),
             "fba_ctx_profile_get": (C.c_int, [vp, C.c_char_p, vp, vp]),
+            "fba_ctx_profile_list": (i64, [vp, vp, i64]),
+            "fba_belief_resample_stats": (C.c_int, [vp, vp, vp]),
             "fba_model_create": (C.c_int, [vp, vp, i32, pp]),
             "fba_model_destroy": (None, [vp]),
             "fba_model_add_structures": (C.c_int, [vp, i32, vp, vp, vp]),

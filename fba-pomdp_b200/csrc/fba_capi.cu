@@ -24,6 +24,7 @@ struct fba_ctx
     int64_t launches     = 0;
     std::string err;
     // optional per-kernel CUDA-event timing (fba_ctx_profile_*)
+    bool inplace_resample = true; // PHILOX mode: survivors keep their slot (fba_ctx_set_option)
     bool profiling       = false;
     struct Timed
     {
@@ -76,6 +77,11 @@ struct fba_belief
     double uniform_total = -1;  // sequential sum of N x (1/N), computed on first use
     bool suffix_valid = false;  // aux holds R for the current weights
     bool cdf_valid    = false;  // aux holds the native cdf for the current weights
+    // in-place resampling
+    int *noff = nullptr, *escan = nullptr, *dead = nullptr, *totals = nullptr;
+    long long* stats = nullptr; // [0] copies made by in-place resamples, [1] number of resamples
+    int2* tile_pairs = nullptr;
+    bool inplace_last = false; // the last shard resample ran in place (import goes to dead slots)
     // rejection sampling wave buffers
     long long wave_cap = 0;
     int *att_src = nullptr, *att_state = nullptr, *att_accept = nullptr, *att_pos = nullptr,
@@ -202,6 +208,18 @@ extern "C" int64_t fba_ctx_launch_count(const fba_ctx* ctx)
     return ctx->launches;
 }
 
+extern "C" int fba_ctx_set_option(fba_ctx* ctx, const char* name, int64_t value)
+{
+    if (!ctx || !name) return FBA_ERR_INVALID;
+    if (!strcmp(name, "inplace_resample"))
+    {
+        ctx->inplace_resample = value != 0;
+        return FBA_OK;
+    }
+    ctx->err = std::string("unknown option ") + name;
+    return FBA_ERR_INVALID;
+}
+
 // Per-kernel timing with CUDA events on the context's stream (bench.py's roofline numbers).
 extern "C" int fba_ctx_profile_begin(fba_ctx* ctx)
 {
@@ -241,6 +259,22 @@ extern "C" int fba_ctx_profile_get(const fba_ctx* ctx, const char* prefix, doubl
     if (total_ms) *total_ms = ms;
     if (count) *count = n;
     return FBA_OK;
+}
+
+// "name:ms:count;..." for every kernel timed since fba_ctx_profile_begin; returns the length needed
+extern "C" int64_t fba_ctx_profile_list(const fba_ctx* ctx, char* buf, int64_t cap)
+{
+    if (!ctx) return -1;
+    std::string out;
+    for (auto const& kv : ctx->kernel_ms)
+        out += kv.first + ":" + std::to_string(kv.second.first) + ":" + std::to_string(kv.second.second) + ";";
+    if (buf && cap > 0)
+    {
+        size_t const n = std::min<size_t>(out.size(), (size_t)cap - 1);
+        memcpy(buf, out.data(), n);
+        buf[n] = 0;
+    }
+    return (int64_t)out.size() + 1;
 }
 
 // upload words[first, first+n) of the replay stream into the context scratch
@@ -548,6 +582,13 @@ extern "C" int fba_belief_create(fba_ctx* ctx, fba_model* m, int64_t N, int64_t 
     b->anc_cap = N + N / 8 + 1024; // room for an over-quota shard's surplus offspring
     if (e == cudaSuccess) e = cudaMalloc(&b->anc, (size_t)b->anc_cap * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_total, sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&b->noff, (size_t)N * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&b->escan, (size_t)N * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&b->dead, (size_t)N * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&b->totals, 2 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&b->stats, 2 * sizeof(long long));
+    if (e == cudaSuccess) e = cudaMemset(b->stats, 0, 2 * sizeof(long long));
+    if (e == cudaSuccess) e = cudaMalloc(&b->tile_pairs, (size_t)n_tiles * sizeof(int2));
     if (e != cudaSuccess)
     {
         ctx->err = std::string("belief alloc: ") + cudaGetErrorString(e);
@@ -572,6 +613,7 @@ extern "C" void fba_belief_destroy(fba_belief* b)
     cudaFree(b->w), cudaFree(b->aux), cudaFree(b->tile), cudaFree(b->scal), cudaFree(b->anc);
     cudaFree(b->att_src), cudaFree(b->att_state), cudaFree(b->att_accept), cudaFree(b->att_pos);
     cudaFree(b->att_rec), cudaFree(b->d_total), cudaFree(b->xport), cudaFree(b->import_buf);
+    cudaFree(b->stats), cudaFree(b->noff), cudaFree(b->escan), cudaFree(b->dead), cudaFree(b->totals), cudaFree(b->tile_pairs);
     delete b;
 }
 
@@ -884,6 +926,36 @@ static int gather_into_next(fba_belief* b, long long n_out, bool copy_state)
     return FBA_OK;
 }
 
+// PHILOX: systematic resampling to n_out offspring without moving survivors (see fba_kernels.cuh).
+// Surplus offspring beyond the N slots go to the export buffer; missing ones leave dead slots empty.
+static int resample_inplace(fba_belief* b, fba_rng* rng, long long n_out)
+{
+    fba_ctx* ctx = b->ctx;
+    int rc;
+    if (!b->cdf_valid)
+        if ((rc = native_normalize(b, false, 1.0))) return rc;
+    int const n_tiles = (int)((b->N + kTile - 1) / kTile);
+    long long const surplus = std::max(0ll, n_out - b->N);
+    long long const rb      = fba_belief_record_bytes(b);
+    if (surplus > b->xport_cap)
+    {
+        cudaFree(b->xport);
+        b->xport     = nullptr;
+        b->xport_cap = surplus + surplus / 4 + 64;
+        CU(ctx, cudaMalloc(&b->xport, b->xport_cap * rb));
+    }
+    LAUNCH(ctx, k_offspring, n_tiles, kThreads, b->aux, b->N, n_out, philox_args(rng), b->noff, b->tile_pairs);
+    LAUNCH(ctx, k_scan_tile_pairs, 1, kThreads, b->tile_pairs, n_tiles, b->totals, b->stats);
+    LAUNCH(ctx, k_offspring_apply, n_tiles, kThreads, b->noff, b->N, b->tile_pairs, b->dead, b->escan);
+    LAUNCH(ctx, k_copy_inplace, stream_grid(ctx, b->N), kThreads, b->counts[b->cur], b->stride,
+           b->state[b->cur], b->sid[b->cur], b->m->d_sizes, b->escan, b->N, b->dead, b->totals, b->xport, rb);
+    LAUNCH(ctx, k_fill, blocks_for(b->N), kThreads, b->w, b->N, 1.0 / (double)b->N);
+    b->total_weight = 1.0;
+    b->suffix_valid = b->cdf_valid = false;
+    b->inplace_last = true;
+    return FBA_OK;
+}
+
 extern "C" int fba_belief_resample(fba_belief* b, fba_rng* rng)
 {
     if (!b || !rng) return FBA_ERR_INVALID;
@@ -891,6 +963,7 @@ extern "C" int fba_belief_resample(fba_belief* b, fba_rng* rng)
     REQUIRE(ctx, b->weighted, "resample needs a weighted belief");
     CU(ctx, cudaSetDevice(ctx->device));
     int rc;
+    if (rng->mode == FBA_RNG_PHILOX && ctx->inplace_resample) return resample_inplace(b, rng, b->N);
     if (rng->mode == FBA_RNG_REPLAY)
     {
         long long const need = 2 * b->N; // N draws of one uniform (ImportanceSampler.hpp:79-82)
@@ -1412,6 +1485,14 @@ extern "C" int fba_belief_resample_shard(fba_belief* b, int64_t n_offspring, fba
     long long const surplus = n_offspring - kept;
     b->local_kept  = kept;
     b->xport_count = surplus;
+    if (ctx->inplace_resample)
+    {
+        int rc = resample_inplace(b, rng, n_offspring);
+        if (rc) return rc;
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        return FBA_OK;
+    }
+    b->inplace_last = false;
     if (n_offspring == 0)
     {
         flip(b);
@@ -1451,6 +1532,20 @@ extern "C" int fba_belief_resample_shard(fba_belief* b, int64_t n_offspring, fba
     return FBA_OK;
 }
 
+// copies made / resamples run by the in-place resampler since the belief was created
+extern "C" int fba_belief_resample_stats(fba_belief* b, int64_t* copies, int64_t* resamples)
+{
+    if (!b) return FBA_ERR_INVALID;
+    fba_ctx* ctx = b->ctx;
+    long long h[2] = {0, 0};
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaMemcpy(h, b->stats, sizeof(h), cudaMemcpyDeviceToHost));
+    if (copies) *copies = h[0];
+    if (resamples) *resamples = h[1];
+    return FBA_OK;
+}
+
 extern "C" int64_t fba_belief_export_count(const fba_belief* b)
 {
     return b ? b->xport_count : 0;
@@ -1485,6 +1580,15 @@ extern "C" int fba_belief_import(fba_belief* b, int64_t n_records)
     if (n_records == 0) return FBA_OK;
     REQUIRE(ctx, b->import_buf && n_records <= b->import_cap, "import: call fba_belief_import_ptr first");
     CU(ctx, cudaSetDevice(ctx->device));
+    if (b->inplace_last)
+    {
+        LAUNCH(ctx, k_import_inplace, stream_grid(ctx, n_records), kThreads, b->counts[b->cur], b->stride,
+               b->state[b->cur], b->sid[b->cur], b->dead, b->totals, (long long)n_records, b->import_buf,
+               fba_belief_record_bytes(b));
+        b->local_kept += n_records;
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        return FBA_OK;
+    }
     LAUNCH(ctx, k_import, stream_grid(ctx, n_records), kThreads, b->counts[b->cur], b->stride, b->state[b->cur],
            b->sid[b->cur], b->w, 1.0 / (double)b->N, b->local_kept, (long long)n_records, b->import_buf,
            fba_belief_record_bytes(b));

@@ -415,6 +415,217 @@ __global__ void __launch_bounds__(kThreads)
     anc[j] = (int)lo;
 }
 
+// ------------------------------------------------------------------------------------------------
+// NATIVE in-place systematic resampling. Survivors (>= 1 offspring) keep their slot and are never
+// moved; each dead slot receives one of the extra offspring of a multiply-drawn particle. Only the
+// duplicated blocks cross HBM (2 x 4C bytes each) instead of every block.
+//   offspring: n_i = F(cdf_i) - F(cdf_{i-1}),  F(c) = clamp(ceil(c / s - u), 0, n_out),
+//              s = cdf_{N-1} / n_out  (systematic positions (j + u) * s, j = 0..n_out-1)
+//   dead_i = (n_i == 0), extra_i = max(n_i - 1, 0); exclusive scans give the k-th dead slot and,
+//   by binary search over the extra scan, the source of the k-th extra copy.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long sys_count_below(double c, double inv_s, double u, long long n_out)
+{
+    double const v = ceil(c * inv_s - u);
+    if (!(v > 0.0)) return 0;
+    if (v >= (double)n_out) return n_out;
+    return (long long)v;
+}
+
+// per tile: offspring counts -> (dead, extra) tile sums
+__global__ void __launch_bounds__(kThreads)
+    k_offspring(const double* __restrict__ cdf, long long N, long long n_out, RngArgs ra,
+                int* __restrict__ noff, int2* __restrict__ tile_sum)
+{
+    __shared__ int shd[kThreads / 32], she[kThreads / 32];
+    auto g             = RngOf<false>::make(ra, 0);
+    double const u     = draw_u(g);
+    // a shard whose weights all collapsed gets no offspring: every slot is dead
+    double const inv_s = (n_out > 0 && cdf[N - 1] > 0.0) ? (double)n_out / cdf[N - 1] : 0.0;
+    if (inv_s == 0.0) n_out = 0;
+    long long const base = (long long)blockIdx.x * kTile;
+    int d = 0, e = 0;
+#pragma unroll
+    for (int k = 0; k < kTile / kThreads; ++k)
+    {
+        long long const i = base + threadIdx.x + k * kThreads;
+        if (i < N)
+        {
+            long long const hi = (i == N - 1) ? n_out : sys_count_below(cdf[i], inv_s, u, n_out);
+            long long const lo = (i == 0) ? 0 : sys_count_below(cdf[i - 1], inv_s, u, n_out);
+            int const n        = (int)(hi - lo);
+            noff[i]            = n;
+            d += (n == 0);
+            e += (n > 1) ? n - 1 : 0;
+        }
+    }
+    for (int o = 16; o; o >>= 1)
+    {
+        d += __shfl_down_sync(0xffffffffu, d, o);
+        e += __shfl_down_sync(0xffffffffu, e, o);
+    }
+    int const lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) shd[wid] = d, she[wid] = e;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        int td = 0, te = 0;
+        for (int k = 0; k < kThreads / 32; ++k) td += shd[k], te += she[k];
+        tile_sum[blockIdx.x] = make_int2(td, te);
+    }
+}
+
+// exclusive scan of the (dead, extra) tile sums in one block; totals[0] = #dead, totals[1] = #extra
+__global__ void __launch_bounds__(kThreads)
+    k_scan_tile_pairs(int2* __restrict__ tile_sum, int n_tiles, int* __restrict__ totals,
+                      long long* __restrict__ stats)
+{
+    __shared__ int shd[kThreads], she[kThreads];
+    __shared__ int cd, ce;
+    if (threadIdx.x == 0) cd = 0, ce = 0;
+    __syncthreads();
+    for (int base = 0; base < n_tiles; base += kThreads)
+    {
+        int const i  = base + threadIdx.x;
+        int2 const v = (i < n_tiles) ? tile_sum[i] : make_int2(0, 0);
+        shd[threadIdx.x] = v.x, she[threadIdx.x] = v.y;
+        __syncthreads();
+        for (int o = 1; o < kThreads; o <<= 1)
+        {
+            int const a = (threadIdx.x >= o) ? shd[threadIdx.x - o] : 0;
+            int const b = (threadIdx.x >= o) ? she[threadIdx.x - o] : 0;
+            __syncthreads();
+            shd[threadIdx.x] += a, she[threadIdx.x] += b;
+            __syncthreads();
+        }
+        if (i < n_tiles) tile_sum[i] = make_int2(cd + shd[threadIdx.x] - v.x, ce + she[threadIdx.x] - v.y);
+        __syncthreads();
+        if (threadIdx.x == kThreads - 1) cd += shd[kThreads - 1], ce += she[kThreads - 1];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+    {
+        totals[0] = cd, totals[1] = ce;
+        stats[0] += ce; // block copies this resample performs
+        stats[1] += 1;
+    }
+}
+
+// per tile: dead_slot[k] = index of the k-th dead particle; extra_scan[i] = exclusive scan of extra
+__global__ void __launch_bounds__(kThreads)
+    k_offspring_apply(const int* __restrict__ noff, long long N, const int2* __restrict__ tile_off,
+                      int* __restrict__ dead_slot, int* __restrict__ extra_scan)
+{
+    __shared__ int shd[kThreads], she[kThreads];
+    constexpr int PER    = kTile / kThreads;
+    long long const base = (long long)blockIdx.x * kTile + (long long)threadIdx.x * PER;
+    int n[PER];
+    int d = 0, e = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k)
+    {
+        long long const i = base + k;
+        n[k]              = (i < N) ? noff[i] : 1;
+        d += (n[k] == 0);
+        e += (n[k] > 1) ? n[k] - 1 : 0;
+    }
+    shd[threadIdx.x] = d, she[threadIdx.x] = e;
+    __syncthreads();
+    for (int o = 1; o < kThreads; o <<= 1)
+    {
+        int const a = (threadIdx.x >= o) ? shd[threadIdx.x - o] : 0;
+        int const b = (threadIdx.x >= o) ? she[threadIdx.x - o] : 0;
+        __syncthreads();
+        shd[threadIdx.x] += a, she[threadIdx.x] += b;
+        __syncthreads();
+    }
+    int2 const off = tile_off[blockIdx.x];
+    int pd = off.x + shd[threadIdx.x] - d, pe = off.y + she[threadIdx.x] - e;
+#pragma unroll
+    for (int k = 0; k < PER; ++k)
+    {
+        long long const i = base + k;
+        if (i < N)
+        {
+            extra_scan[i] = pe;
+            if (n[k] == 0) dead_slot[pd++] = (int)i;
+            pe += (n[k] > 1) ? n[k] - 1 : 0;
+        }
+    }
+}
+
+// multi-GPU: imported record r fills the (n_extra + r)-th dead slot (those the local extras left)
+__global__ void __launch_bounds__(kThreads)
+    k_import_inplace(float* __restrict__ dst, long long stride, int* __restrict__ state, int* __restrict__ sid,
+                     const int* __restrict__ dead_slot, const int* __restrict__ totals, long long n,
+                     const char* __restrict__ in, long long rec_bytes)
+{
+    int const lane        = threadIdx.x & 31;
+    long long const warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    long long const nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
+    long long const first = totals[1];
+    for (long long r = warp0; r < n; r += nwarp)
+    {
+        const char* rec      = in + r * rec_bytes;
+        long long const slot = dead_slot[first + r];
+        warp_copy_block(reinterpret_cast<const float*>(rec), dst + slot * stride, (int)(stride >> 2), lane);
+        if (lane == 0)
+        {
+            const int* tail = reinterpret_cast<const int*>(rec + stride * sizeof(float));
+            state[slot]     = tail[0];
+            sid[slot]       = tail[1];
+        }
+    }
+}
+
+// copy k in [0, n_copies): source = the last i with extra_scan[i] <= k, destination = dead_slot[k]
+// (k < n_fill) or export record k - n_fill. One warp per copy, within the SAME buffer: sources are
+// survivors (never written), destinations are dead (never read).
+__global__ void __launch_bounds__(kThreads)
+    k_copy_inplace(float* counts, long long stride, int* state, int* sid, const int* __restrict__ struct_size,
+                   const int* __restrict__ extra_scan, long long N, const int* __restrict__ dead_slot,
+                   const int* __restrict__ totals, char* __restrict__ xport, long long rec_bytes)
+{
+    long long const n_dead = totals[0], n_copies = totals[1];
+    long long const n_fill = min(n_dead, n_copies); // the rest (if any) is this shard's surplus
+    int const lane        = threadIdx.x & 31;
+    long long const warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    long long const nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long k = warp0; k < n_copies; k += nwarp)
+    {
+        long long lo = 0, hi = N; // first i with extra_scan[i] > k
+        while (lo < hi)
+        {
+            long long const mid = (lo + hi) >> 1;
+            if (extra_scan[mid] > (int)k) hi = mid;
+            else
+                lo = mid + 1;
+        }
+        long long const i = lo - 1;
+        int const id      = sid[i];
+        if (k < n_fill)
+        {
+            long long const j = dead_slot[k];
+            warp_copy_block(counts + i * stride, counts + j * stride, (struct_size[id] + 3) >> 2, lane);
+            if (lane == 0)
+            {
+                sid[j]   = id;
+                state[j] = state[i];
+            }
+        } else
+        {
+            char* rec = xport + (k - n_fill) * rec_bytes;
+            warp_copy_block(counts + i * stride, reinterpret_cast<float*>(rec), (int)(stride >> 2), lane);
+            if (lane == 0)
+            {
+                int* tail = reinterpret_cast<int*>(rec + stride * sizeof(float));
+                tail[0]   = state[i];
+                tail[1]   = id;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kThreads) k_fill(double* __restrict__ w, long long N, double v)
 {
     long long const i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

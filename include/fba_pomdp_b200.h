@@ -128,11 +128,17 @@ int fba_ctx_synchronize(fba_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t fba_ctx_launch_count(const fba_ctx* ctx);
 
+/* options: "inplace_resample" (default 1): PHILOX-mode resampling keeps surviving particles in
+ * their slot and copies only duplicates; 0 = gather every particle into the second buffer */
+int fba_ctx_set_option(fba_ctx* ctx, const char* name, int64_t value);
+
 /* per-kernel CUDA-event timing on the context's stream: begin, run calls, end, then query the
  * summed milliseconds and launch count of the kernels whose name starts with `prefix` */
 int fba_ctx_profile_begin(fba_ctx* ctx);
 int fba_ctx_profile_end(fba_ctx* ctx);
 int fba_ctx_profile_get(const fba_ctx* ctx, const char* prefix, double* total_ms, int64_t* count);
+/* "name:ms:count;..." of every kernel timed since fba_ctx_profile_begin; returns the bytes needed */
+int64_t fba_ctx_profile_list(const fba_ctx* ctx, char* buf, int64_t cap);
 
 /* ---- model ---- */
 int fba_model_create(fba_ctx* ctx, const fba_model_desc* desc, int32_t max_structures, fba_model** out);
@@ -212,6 +218,8 @@ int fba_belief_normalize(fba_belief* b, double global_total);
 /* phase 3: resample this shard to n_offspring particles, the first min(n_offspring, N) stay here,
  * the surplus lands in an export buffer (fba_belief_export_ptr) for the host to ship over NCCL */
 int fba_belief_resample_shard(fba_belief* b, int64_t n_offspring, fba_rng* rng);
+/* in-place resampler statistics since creation: count blocks copied, resamples run */
+int fba_belief_resample_stats(fba_belief* b, int64_t* copies, int64_t* resamples);
 int64_t fba_belief_export_count(const fba_belief* b);
 /* device pointers of the export / import staging area: particle records of
  * fba_belief_record_bytes() each (count block, then state, structure id) */
