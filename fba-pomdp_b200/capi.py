@@ -32,6 +32,7 @@ SYMBOLS = [
     "fba_belief_export_count",
     "fba_belief_export_ptr", "fba_belief_import_ptr", "fba_belief_record_bytes", "fba_belief_import",
     "fba_belief_counts_ptr", "fba_belief_state_ptr", "fba_belief_weight_ptr",
+    "fba_belief_scalars_ptr",
 ]
 
 
@@ -137,6 +138,7 @@ def lib():
             "fba_belief_counts_ptr": (vp, [vp]),
             "fba_belief_state_ptr": (vp, [vp]),
             "fba_belief_weight_ptr": (vp, [vp]),
+            "fba_belief_scalars_ptr": (vp, [vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)

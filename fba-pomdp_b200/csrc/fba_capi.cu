@@ -637,6 +637,10 @@ extern "C" void* fba_belief_weight_ptr(fba_belief* b)
 {
     return b->w;
 }
+extern "C" void* fba_belief_scalars_ptr(fba_belief* b)
+{
+    return b->scal;
+}
 
 // WeightedFilter::_total_weight after N x add(s, 1/N) (WeightedFilter.cpp:60-66): data independent
 static double uniform_total(fba_belief* b)
@@ -1393,7 +1397,7 @@ extern "C" int fba_rollouts(fba_belief* b, int64_t n, const int64_t* particle, c
 
 extern "C" int fba_belief_propose(fba_belief* b, int32_t a, int32_t o, fba_rng* rng, double* local_total)
 {
-    if (!b || !rng || !local_total) return FBA_ERR_INVALID;
+    if (!b || !rng) return FBA_ERR_INVALID;
     fba_ctx* ctx = b->ctx;
     REQUIRE(ctx, rng->mode == FBA_RNG_PHILOX, "sharded beliefs run in PHILOX mode");
     int rc = propose(b, a, o, rng, 0);
@@ -1401,8 +1405,11 @@ extern "C" int fba_belief_propose(fba_belief* b, int32_t a, int32_t o, fba_rng* 
     int const n_tiles = (int)((b->N + kTile - 1) / kTile);
     LAUNCH(ctx, k_tile_sums, n_tiles, kThreads, b->w, b->N, b->tile);
     LAUNCH(ctx, k_scan_tile_sums, 1, kThreads, b->tile, n_tiles, b->scal);
-    if ((rc = read_scal(b))) return rc;
-    *local_total = ctx->h_scal[0];
+    if (local_total)
+    { // NULL: stay asynchronous; the total is at fba_belief_scalars_ptr()[0] in stream order
+        if ((rc = read_scal(b))) return rc;
+        *local_total = ctx->h_scal[0];
+    }
     return FBA_OK;
 }
 
@@ -1487,10 +1494,7 @@ extern "C" int fba_belief_resample_shard(fba_belief* b, int64_t n_offspring, fba
     b->xport_count = surplus;
     if (ctx->inplace_resample)
     {
-        int rc = resample_inplace(b, rng, n_offspring);
-        if (rc) return rc;
-        CU(ctx, cudaStreamSynchronize(ctx->stream));
-        return FBA_OK;
+        return resample_inplace(b, rng, n_offspring); // asynchronous: export buffer valid in stream order
     }
     b->inplace_last = false;
     if (n_offspring == 0)
@@ -1586,8 +1590,7 @@ extern "C" int fba_belief_import(fba_belief* b, int64_t n_records)
                b->state[b->cur], b->sid[b->cur], b->dead, b->totals, (long long)n_records, b->import_buf,
                fba_belief_record_bytes(b));
         b->local_kept += n_records;
-        CU(ctx, cudaStreamSynchronize(ctx->stream));
-        return FBA_OK;
+        return FBA_OK; // asynchronous
     }
     LAUNCH(ctx, k_import, stream_grid(ctx, n_records), kThreads, b->counts[b->cur], b->stride, b->state[b->cur],
            b->sid[b->cur], b->w, 1.0 / (double)b->N, b->local_kept, (long long)n_records, b->import_buf,

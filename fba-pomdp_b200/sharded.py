@@ -72,14 +72,17 @@ def exchange_records(dist, group, plan, rank, src, record_bytes, dst=None):
 class _RawCuda:
     """Zero-copy view of a device pointer for torch.as_tensor."""
 
-    def __init__(self, ptr, nbytes):
-        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1",
+    def __init__(self, ptr, nbytes, typestr="|u1", itemsize=1):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes) // itemsize,), "typestr": typestr,
                                          "data": (int(ptr), False), "version": 3, "strides": None}
 
 
 class ShardedBAImportanceSampling(BAImportanceSampling):
-    """BAImportanceSampling over G shards of n_local particles (PHILOX mode). Rank-local calls go to
-    the C ABI phases fba_belief_{propose,normalize,resample_shard,import}."""
+    """BAImportanceSampling over G shards of n_local particles (PHILOX mode). Rank-local work goes
+    to the C ABI phases fba_belief_{propose,normalize,resample_shard,import}; NCCL collectives are
+    enqueued on the library's own stream (made torch's current stream), so one update costs a
+    single host synchronisation — the read-back of the G shard totals that the exchange plan
+    (host-known split sizes for the all-to-all) needs."""
 
     def __init__(self, n_local, group=None):
         super().__init__(n_local)
@@ -88,21 +91,22 @@ class ShardedBAImportanceSampling(BAImportanceSampling):
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.moved_last = 0
+        self.phase_ms = {}
+        self._bufs = None
 
     def rank_rng(self, seed):
         """A PHILOX source whose key differs per rank, so shards draw independent streams."""
         mixed = (int(seed) + (self.rank + 1) * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
         return capi.Rng.philox(mixed)
 
-    def _all_gather_totals(self, local_total):
+    def _setup(self):
         import torch
-        if self.world == 1:
-            return np.array([local_total])
-        dev = "cuda" if self.dist.get_backend(self.group) == "nccl" else "cpu"
-        mine = torch.tensor([local_total], dtype=torch.float64, device=dev)
-        out = torch.empty(self.world, dtype=torch.float64, device=dev)
-        self.dist.all_gather_into_tensor(out, mine, group=self.group)
-        return out.cpu().numpy()
+        self._stream = torch.cuda.ExternalStream(self.ctx.stream)
+        scal = self.L.fba_belief_scalars_ptr(self.h)
+        self._local = torch.as_tensor(_RawCuda(scal, 8, "<f8", 8), device="cuda")  # view of scal[0]
+        self._totals = torch.empty(self.world, dtype=torch.float64, device="cuda")
+        self._totals_host = torch.empty(self.world, dtype=torch.float64).pin_memory()
+        self._bufs = True
 
     def updateEstimation(self, a, o, rng, step_uniform=0.5):
         """One global importance-sampling update + resample. `step_uniform` in [0,1) must be the
@@ -111,32 +115,37 @@ class ShardedBAImportanceSampling(BAImportanceSampling):
         import torch
         L, h, ctx = self.L, self.h, self.ctx
         n_local = self._n
-        local = C.c_double(0)
+        if self._bufs is None:
+            self._setup()
         t0 = time.perf_counter()
-        # NOTE: every rank must drive its shard with its own Philox seed (see rank_rng)
-        _check(ctx.h, L.fba_belief_propose(h, a, o, C.byref(rng), C.byref(local)))
-        t1 = time.perf_counter()
-        totals = self._all_gather_totals(local.value)
-        total = float(totals.sum())
-        t2 = time.perf_counter()
-        _check(ctx.h, L.fba_belief_normalize(h, total))
-        quotas = offspring_quotas(totals, n_local * self.world, step_uniform)
-        plan = exchange_plan(quotas, n_local)
-        _check(ctx.h, L.fba_belief_resample_shard(h, int(quotas[self.rank]), C.byref(rng)))
-        t3 = time.perf_counter()
-        self.moved_last = int(plan.sum())
-        self.phase_ms = {"propose": (t1 - t0) * 1e3, "all_gather": (t2 - t1) * 1e3,
-                         "normalize+resample": (t3 - t2) * 1e3, "exchange": 0.0}
-        if self.moved_last:
-            rb = L.fba_belief_record_bytes(h)
-            n_out, n_in = int(plan[self.rank].sum()), int(plan[:, self.rank].sum())
-            assert n_out == L.fba_belief_export_count(h)
-            src = (torch.as_tensor(_RawCuda(L.fba_belief_export_ptr(h), n_out * rb), device="cuda")
-                   if n_out else torch.empty(0, dtype=torch.uint8, device="cuda"))
-            dst = (torch.as_tensor(_RawCuda(L.fba_belief_import_ptr(h, n_in), n_in * rb), device="cuda")
-                   if n_in else torch.empty(0, dtype=torch.uint8, device="cuda"))
-            exchange_records(self.dist, self.group, plan, self.rank, src, rb, dst)
-            torch.cuda.synchronize()
-            _check(ctx.h, L.fba_belief_import(h, n_in))
-            self.phase_ms["exchange"] = (time.perf_counter() - t3) * 1e3
+        with torch.cuda.stream(self._stream):
+            # phase 1 (async): step + weights + shard total, left on the device
+            _check(ctx.h, L.fba_belief_propose(h, a, o, C.byref(rng), None))
+            if self.world > 1:
+                self.dist.all_gather_into_tensor(self._totals, self._local, group=self.group)
+            else:
+                self._totals.copy_(self._local)
+            self._totals_host.copy_(self._totals, non_blocking=True)
+            self._stream.synchronize()  # the one host sync of the update
+            t1 = time.perf_counter()
+            totals = self._totals_host.numpy().copy()
+            total = float(totals.sum())
+            quotas = offspring_quotas(totals, n_local * self.world, step_uniform)
+            plan = exchange_plan(quotas, n_local)
+            # phases 2-3 (async): normalise by the global total, resample this shard to its quota
+            _check(ctx.h, L.fba_belief_normalize(h, total))
+            _check(ctx.h, L.fba_belief_resample_shard(h, int(quotas[self.rank]), C.byref(rng)))
+            self.moved_last = int(plan.sum())
+            if self.moved_last:
+                rb = L.fba_belief_record_bytes(h)
+                n_out, n_in = int(plan[self.rank].sum()), int(plan[:, self.rank].sum())
+                src = (torch.as_tensor(_RawCuda(L.fba_belief_export_ptr(h), n_out * rb), device="cuda")
+                       if n_out else torch.empty(0, dtype=torch.uint8, device="cuda"))
+                dst = (torch.as_tensor(_RawCuda(L.fba_belief_import_ptr(h, n_in), n_in * rb), device="cuda")
+                       if n_in else torch.empty(0, dtype=torch.uint8, device="cuda"))
+                exchange_records(self.dist, self.group, plan, self.rank, src, rb, dst)
+                # phase 4 (async): imported records fill the slots the local resample left dead
+                _check(ctx.h, L.fba_belief_import(h, n_in))
+        self.phase_ms = {"propose+all_gather (1 sync)": (t1 - t0) * 1e3,
+                         "plan+normalize+resample+exchange (enqueue)": (time.perf_counter() - t1) * 1e3}
         return total

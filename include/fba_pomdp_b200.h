@@ -210,7 +210,9 @@ int fba_rollouts(fba_belief* b, int64_t n, const int64_t* particle, const int32_
                  double* returns);
 
 /* ---- multi-GPU phases (one process per GPU; the host runs the collective between them) ---- */
-/* phase 1: step + weight, no normalisation; *local_total = this shard's weight sum */
+/* phase 1: step + weight, no normalisation; *local_total = this shard's weight sum. With
+ * local_total == NULL the call only enqueues work: the total is then the first double at
+ * fba_belief_scalars_ptr(), valid in stream order (for a device-side all-gather). */
 int fba_belief_propose(fba_belief* b, int32_t action, int32_t observation, fba_rng* rng,
                        double* local_total);
 /* phase 2: divide by the global total (all-gathered by the host) */
@@ -233,6 +235,7 @@ int fba_belief_import(fba_belief* b, int64_t n_records);
 void* fba_belief_counts_ptr(fba_belief* b);
 void* fba_belief_state_ptr(fba_belief* b);
 void* fba_belief_weight_ptr(fba_belief* b);
+void* fba_belief_scalars_ptr(fba_belief* b); /* device double[4]: [0] = last un-normalised total */
 
 #ifdef __cplusplus
 }
