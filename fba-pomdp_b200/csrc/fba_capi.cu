@@ -32,6 +32,7 @@ struct fba_ctx
         cudaEvent_t start, stop;
     };
     std::vector<Timed> timed;
+    std::vector<cudaEvent_t> event_pool; // created at profile_begin so launches stay cheap
     std::map<std::string, std::pair<double, int64_t>> kernel_ms;
     // scratch shared by the beliefs of this context
     uint32_t* d_words    = nullptr;
@@ -132,8 +133,15 @@ static void profile_mark(fba_ctx* ctx, const char* name, bool begin)
     if (begin)
     {
         fba_ctx::Timed t{name, nullptr, nullptr};
-        cudaEventCreate(&t.start);
-        cudaEventCreate(&t.stop);
+        for (cudaEvent_t* e : {&t.start, &t.stop})
+        {
+            if (ctx->event_pool.empty()) cudaEventCreate(e);
+            else
+            {
+                *e = ctx->event_pool.back();
+                ctx->event_pool.pop_back();
+            }
+        }
         cudaEventRecord(t.start, ctx->stream);
         ctx->timed.push_back(t);
     } else
@@ -181,6 +189,7 @@ extern "C" void fba_ctx_destroy(fba_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (auto e : ctx->event_pool) cudaEventDestroy(e);
     cudaFree(ctx->d_words);
     cudaFree(ctx->d_offsets);
     cudaFree(ctx->d_flag);
@@ -225,6 +234,12 @@ extern "C" int fba_ctx_profile_begin(fba_ctx* ctx)
 {
     if (!ctx) return FBA_ERR_INVALID;
     ctx->kernel_ms.clear();
+    while (ctx->event_pool.size() < 2048)
+    {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) break;
+        ctx->event_pool.push_back(e);
+    }
     ctx->profiling = true;
     return FBA_OK;
 }
@@ -241,8 +256,8 @@ extern "C" int fba_ctx_profile_end(fba_ctx* ctx)
         auto& acc = ctx->kernel_ms[t.name];
         acc.first += ms;
         acc.second += 1;
-        cudaEventDestroy(t.start);
-        cudaEventDestroy(t.stop);
+        ctx->event_pool.push_back(t.start);
+        ctx->event_pool.push_back(t.stop);
     }
     ctx->timed.clear();
     return FBA_OK;
@@ -1428,6 +1443,61 @@ extern "C" int fba_belief_normalize(fba_belief* b, double global_total)
 }
 
 // record layout of the export / import staging area: [stride floats][state][structure id][pad 8]
+// Phases 2-3 in one call, with the quota allocation and the exchange plan computed here:
+// totals[G] are the all-gathered shard totals, u in [0,1) the shared systematic offset.
+// send_plan (G x G, row-major, may be NULL) receives send[g][h] = records rank g ships to rank h.
+extern "C" int fba_belief_shard_resample(fba_belief* b, const double* totals, int32_t n_ranks, int32_t rank,
+                                         double u, fba_rng* rng, int64_t* send_plan, double* global_total)
+{
+    if (!b || !totals || !rng) return FBA_ERR_INVALID;
+    fba_ctx* ctx = b->ctx;
+    REQUIRE(ctx, n_ranks >= 1 && rank >= 0 && rank < n_ranks, "shard_resample: bad rank");
+    REQUIRE(ctx, u >= 0.0 && u < 1.0, "shard_resample: u must be in [0,1)");
+    double W = 0.0;
+    for (int g = 0; g < n_ranks; ++g)
+    {
+        REQUIRE(ctx, totals[g] >= 0.0 && std::isfinite(totals[g]), "shard_resample: bad shard total");
+        W += totals[g];
+    }
+    REQUIRE(ctx, W > 0.0, "shard_resample: total weight must be positive");
+    // systematic allocation over ranks: quota_g = #{j : (j + u)/n in (C_{g-1}, C_g]}
+    long long const n_total = b->N * n_ranks;
+    std::vector<long long> quota(n_ranks);
+    long long prev = 0;
+    double acc = 0.0;
+    for (int g = 0; g < n_ranks; ++g)
+    {
+        acc += totals[g];
+        long long edge = (g == n_ranks - 1) ? n_total : (long long)std::floor(acc / W * (double)n_total - u + 1.0);
+        edge     = std::min(std::max(edge, prev), n_total);
+        quota[g] = edge - prev;
+        prev     = edge;
+    }
+    if (send_plan)
+    { // greedy matching of surplus to deficit in rank order (identical on every rank)
+        std::fill(send_plan, send_plan + (size_t)n_ranks * n_ranks, 0);
+        std::vector<long long> surplus(n_ranks), deficit(n_ranks);
+        for (int g = 0; g < n_ranks; ++g)
+        {
+            surplus[g] = std::max(0ll, quota[g] - b->N);
+            deficit[g] = std::max(0ll, b->N - quota[g]);
+        }
+        int h = 0;
+        for (int g = 0; g < n_ranks; ++g)
+            while (surplus[g] > 0)
+            {
+                while (deficit[h] == 0) ++h;
+                long long const k = std::min(surplus[g], deficit[h]);
+                send_plan[(size_t)g * n_ranks + h] += k;
+                surplus[g] -= k, deficit[h] -= k;
+            }
+    }
+    if (global_total) *global_total = W;
+    int rc = fba_belief_normalize(b, W);
+    if (rc) return rc;
+    return fba_belief_resample_shard(b, quota[rank], rng);
+}
+
 extern "C" int64_t fba_belief_record_bytes(const fba_belief* b)
 {
     return b->stride * (int64_t)sizeof(float) + 16;

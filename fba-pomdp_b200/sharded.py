@@ -106,7 +106,18 @@ class ShardedBAImportanceSampling(BAImportanceSampling):
         self._local = torch.as_tensor(_RawCuda(scal, 8, "<f8", 8), device="cuda")  # view of scal[0]
         self._totals = torch.empty(self.world, dtype=torch.float64, device="cuda")
         self._totals_host = torch.empty(self.world, dtype=torch.float64).pin_memory()
+        self._plan = np.zeros((self.world, self.world), np.int64)
         self._bufs = True
+
+    def free(self, _simulator=None):
+        """Drops the torch views / buffers tied to the library's stream before the belief (and later
+        the context that owns the stream) goes away."""
+        import torch
+        if self._bufs:
+            torch.cuda.synchronize()
+            self._local = self._totals = self._totals_host = self._stream = None
+            self._bufs = None
+        super().free()
 
     def updateEstimation(self, a, o, rng, step_uniform=0.5):
         """One global importance-sampling update + resample. `step_uniform` in [0,1) must be the
@@ -114,7 +125,6 @@ class ShardedBAImportanceSampling(BAImportanceSampling):
         import time
         import torch
         L, h, ctx = self.L, self.h, self.ctx
-        n_local = self._n
         if self._bufs is None:
             self._setup()
         t0 = time.perf_counter()
@@ -128,13 +138,13 @@ class ShardedBAImportanceSampling(BAImportanceSampling):
             self._totals_host.copy_(self._totals, non_blocking=True)
             self._stream.synchronize()  # the one host sync of the update
             t1 = time.perf_counter()
-            totals = self._totals_host.numpy().copy()
-            total = float(totals.sum())
-            quotas = offspring_quotas(totals, n_local * self.world, step_uniform)
-            plan = exchange_plan(quotas, n_local)
-            # phases 2-3 (async): normalise by the global total, resample this shard to its quota
-            _check(ctx.h, L.fba_belief_normalize(h, total))
-            _check(ctx.h, L.fba_belief_resample_shard(h, int(quotas[self.rank]), C.byref(rng)))
+            # phases 2-3 (async): quotas + exchange plan (computed in the library, identically on
+            # every rank), normalise by the global total, resample this shard to its quota
+            plan, tot = self._plan, C.c_double(0)
+            _check(ctx.h, L.fba_belief_shard_resample(h, self._totals_host.data_ptr(), self.world, self.rank,
+                                                      float(step_uniform), C.byref(rng),
+                                                      plan.ctypes.data_as(C.c_void_p), C.byref(tot)))
+            total = tot.value
             self.moved_last = int(plan.sum())
             if self.moved_last:
                 rb = L.fba_belief_record_bytes(h)

@@ -222,6 +222,11 @@ int fba_belief_normalize(fba_belief* b, double global_total);
 int fba_belief_resample_shard(fba_belief* b, int64_t n_offspring, fba_rng* rng);
 /* in-place resampler statistics since creation: count blocks copied, resamples run */
 int fba_belief_resample_stats(fba_belief* b, int64_t* copies, int64_t* resamples);
+/* phases 2+3 with the quota allocation (systematic over ranks, shared offset u in [0,1)) and the
+ * exchange plan computed inside: totals = the all-gathered shard totals; send_plan (n_ranks x
+ * n_ranks, row-major, may be NULL) receives the records rank g ships to rank h */
+int fba_belief_shard_resample(fba_belief* b, const double* totals, int32_t n_ranks, int32_t rank, double u,
+                              fba_rng* rng, int64_t* send_plan, double* global_total);
 int64_t fba_belief_export_count(const fba_belief* b);
 /* device pointers of the export / import staging area: particle records of
  * fba_belief_record_bytes() each (count block, then state, structure id) */

@@ -183,3 +183,40 @@ def test_rollouts_native_mean_return(ctx):
     assert abs(ours.mean() - ref.mean()) < 4 * se, (ours.mean(), ref.mean(), se)
     b.free()
     sim.close()
+
+
+def test_shard_plan_matches_python(ctx):
+    """fba_belief_shard_resample's quota allocation and exchange plan (C) equal the numpy
+    restatement the gloo tests exercise; the shard resamples to exactly its quota."""
+    import ctypes as C
+    import fba_pomdp_b200 as fba
+    n = 2048
+    g, sim, b = _tiger_belief(ctx, n, fba)
+    rs = np.random.RandomState(8)
+    for trial in range(6):
+        G_ = int(rs.randint(1, 9))
+        rank = int(rs.randint(0, G_))
+        rng = fba.Rng.philox(100 + trial)
+        local = C.c_double(0)
+        assert b.L.fba_belief_propose(b.h, 2, 0, C.byref(rng), C.byref(local)) == 0
+        totals = rs.gamma(2.0, size=G_) * local.value
+        totals[rank] = local.value
+        u = float(rs.random_sample())
+        plan = np.zeros((G_, G_), np.int64)
+        tot = C.c_double(0)
+        rc = b.L.fba_belief_shard_resample(b.h, fba.capi.ptr(np.ascontiguousarray(totals)), G_, rank, u,
+                                           C.byref(rng), fba.capi.ptr(plan), C.byref(tot))
+        assert rc == 0, b.L.fba_last_error(ctx.h)
+        q = fba.offspring_quotas(totals, n * G_, u)
+        np.testing.assert_array_equal(plan, fba.exchange_plan(q, n))
+        assert abs(tot.value - totals.sum()) <= 1e-12 * totals.sum()
+        assert b.L.fba_belief_export_count(b.h) == max(0, q[rank] - n)
+        ctx.synchronize()
+        # refill the dead slots locally so the next trial starts from a full shard
+        d = b.download()
+        rc = b.L.fba_belief_upload(b.h, 0, n, fba.capi.ptr(np.zeros(n, np.int32)), None,
+                                   fba.capi.ptr(np.tile(g["is/init_counts"][0], (n, 1))),
+                                   fba.capi.ptr(np.full(n, 1.0 / n)))
+        assert rc == 0
+    b.free()
+    sim.close()

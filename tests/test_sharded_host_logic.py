@@ -95,3 +95,11 @@ def test_gloo_world2_exchange():
     assert q0 == q1 == [12, 4] and plan0 == plan1 == [[0, 4], [0, 0]]
     assert got0 == []  # rank 0 is over quota: receives nothing
     assert len(got1) == 4 * 24 and got1[::24] == [0, 1, 2, 3]  # rank 1 received rank 0's 4 records
+
+
+def test_python_and_library_plans_agree():
+    """offspring_quotas / exchange_plan (numpy, used by the gloo tests) restate what
+    fba_belief_shard_resample computes in C; the GPU test test_shard_plan_matches_python checks the
+    C side against them. Here: the numpy pair is self-consistent on the edge the C code clamps."""
+    q = fba.offspring_quotas([1e-300, 1.0, 1e-300], 30, 0.999)
+    assert q.sum() == 30 and q[1] >= 29
