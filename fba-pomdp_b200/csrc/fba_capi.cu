@@ -80,7 +80,9 @@ struct fba_belief
     bool cdf_valid    = false;  // aux holds the native cdf for the current weights
     // in-place resampling
     int *noff = nullptr, *escan = nullptr, *dead = nullptr, *totals = nullptr;
-    long long* stats = nullptr; // [0] copies made by in-place resamples, [1] number of resamples
+    long long* stats = nullptr; // [0] copies made by in-place resamples, [1] number of resamples,
+                                // [2] surplus records dropped because the export buffer was full
+    long long* d_quota = nullptr; // device-side offspring quota (fba_belief_shard_resample_async)
     int2* tile_pairs = nullptr;
     bool inplace_last = false; // the last shard resample ran in place (import goes to dead slots)
     // rejection sampling wave buffers
@@ -601,8 +603,9 @@ extern "C" int fba_belief_create(fba_ctx* ctx, fba_model* m, int64_t N, int64_t 
     if (e == cudaSuccess) e = cudaMalloc(&b->escan, (size_t)N * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&b->dead, (size_t)N * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&b->totals, 2 * sizeof(int));
-    if (e == cudaSuccess) e = cudaMalloc(&b->stats, 2 * sizeof(long long));
-    if (e == cudaSuccess) e = cudaMemset(b->stats, 0, 2 * sizeof(long long));
+    if (e == cudaSuccess) e = cudaMalloc(&b->stats, 4 * sizeof(long long));
+    if (e == cudaSuccess) e = cudaMemset(b->stats, 0, 4 * sizeof(long long));
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_quota, sizeof(long long));
     if (e == cudaSuccess) e = cudaMalloc(&b->tile_pairs, (size_t)n_tiles * sizeof(int2));
     if (e != cudaSuccess)
     {
@@ -628,7 +631,7 @@ extern "C" void fba_belief_destroy(fba_belief* b)
     cudaFree(b->w), cudaFree(b->aux), cudaFree(b->tile), cudaFree(b->scal), cudaFree(b->anc);
     cudaFree(b->att_src), cudaFree(b->att_state), cudaFree(b->att_accept), cudaFree(b->att_pos);
     cudaFree(b->att_rec), cudaFree(b->d_total), cudaFree(b->xport), cudaFree(b->import_buf);
-    cudaFree(b->stats), cudaFree(b->noff), cudaFree(b->escan), cudaFree(b->dead), cudaFree(b->totals), cudaFree(b->tile_pairs);
+    cudaFree(b->d_quota), cudaFree(b->stats), cudaFree(b->noff), cudaFree(b->escan), cudaFree(b->dead), cudaFree(b->totals), cudaFree(b->tile_pairs);
     delete b;
 }
 
@@ -859,8 +862,8 @@ static int native_normalize(fba_belief* b, bool use_device_total, double divide_
     int const n_tiles = (int)((b->N + kTile - 1) / kTile);
     LAUNCH(ctx, k_tile_sums, n_tiles, kThreads, b->w, b->N, b->tile);
     LAUNCH(ctx, k_scan_tile_sums, 1, kThreads, b->tile, n_tiles, b->scal);
-    LAUNCH(ctx, k_scale_and_scan, n_tiles, kThreads, b->w, b->N, b->tile, b->scal, divide_by,
-           use_device_total ? 1 : 0, b->aux);
+    LAUNCH(ctx, k_scale_and_scan, n_tiles, kThreads, b->w, b->N, b->tile,
+           use_device_total ? b->scal : (const double*)nullptr, divide_by, b->aux);
     b->cdf_valid    = true;
     b->suffix_valid = false;
     return FBA_OK;
@@ -947,27 +950,37 @@ static int gather_into_next(fba_belief* b, long long n_out, bool copy_state)
 
 // PHILOX: systematic resampling to n_out offspring without moving survivors (see fba_kernels.cuh).
 // Surplus offspring beyond the N slots go to the export buffer; missing ones leave dead slots empty.
-static int resample_inplace(fba_belief* b, fba_rng* rng, long long n_out)
+static int ensure_export(fba_belief* b, long long records)
+{
+    fba_ctx* ctx = b->ctx;
+    if (records <= b->xport_cap) return FBA_OK;
+    cudaFree(b->xport);
+    b->xport     = nullptr;
+    b->xport_cap = 0;
+    long long const cap = records + records / 4 + 64;
+    CU(ctx, cudaMalloc(&b->xport, cap * fba_belief_record_bytes(b)));
+    b->xport_cap = cap;
+    return FBA_OK;
+}
+
+// n_out_dev != NULL: the quota is read from device memory (no host sync needed beforehand)
+static int resample_inplace(fba_belief* b, fba_rng* rng, long long n_out, const long long* n_out_dev = nullptr)
 {
     fba_ctx* ctx = b->ctx;
     int rc;
     if (!b->cdf_valid)
         if ((rc = native_normalize(b, false, 1.0))) return rc;
     int const n_tiles = (int)((b->N + kTile - 1) / kTile);
-    long long const surplus = std::max(0ll, n_out - b->N);
-    long long const rb      = fba_belief_record_bytes(b);
-    if (surplus > b->xport_cap)
-    {
-        cudaFree(b->xport);
-        b->xport     = nullptr;
-        b->xport_cap = surplus + surplus / 4 + 64;
-        CU(ctx, cudaMalloc(&b->xport, b->xport_cap * rb));
-    }
-    LAUNCH(ctx, k_offspring, n_tiles, kThreads, b->aux, b->N, n_out, philox_args(rng), b->noff, b->tile_pairs);
+    long long const rb = fba_belief_record_bytes(b);
+    if (!n_out_dev)
+        if ((rc = ensure_export(b, std::max(0ll, n_out - b->N)))) return rc;
+    LAUNCH(ctx, k_offspring, n_tiles, kThreads, b->aux, b->N, n_out, n_out_dev, philox_args(rng), b->noff,
+           b->tile_pairs);
     LAUNCH(ctx, k_scan_tile_pairs, 1, kThreads, b->tile_pairs, n_tiles, b->totals, b->stats);
     LAUNCH(ctx, k_offspring_apply, n_tiles, kThreads, b->noff, b->N, b->tile_pairs, b->dead, b->escan);
     LAUNCH(ctx, k_copy_inplace, stream_grid(ctx, b->N), kThreads, b->counts[b->cur], b->stride,
-           b->state[b->cur], b->sid[b->cur], b->m->d_sizes, b->escan, b->N, b->dead, b->totals, b->xport, rb);
+           b->state[b->cur], b->sid[b->cur], b->m->d_sizes, b->escan, b->N, b->dead, b->totals, b->xport, rb,
+           b->xport_cap, b->stats);
     LAUNCH(ctx, k_fill, blocks_for(b->N), kThreads, b->w, b->N, 1.0 / (double)b->N);
     b->total_weight = 1.0;
     b->suffix_valid = b->cdf_valid = false;
@@ -1436,35 +1449,31 @@ extern "C" int fba_belief_normalize(fba_belief* b, double global_total)
     CU(ctx, cudaSetDevice(ctx->device));
     // tile sums from fba_belief_propose are still in b->tile (exclusive-scanned)
     int const n_tiles = (int)((b->N + kTile - 1) / kTile);
-    LAUNCH(ctx, k_scale_and_scan, n_tiles, kThreads, b->w, b->N, b->tile, b->scal, global_total, 0, b->aux);
+    LAUNCH(ctx, k_scale_and_scan, n_tiles, kThreads, b->w, b->N, b->tile, (const double*)nullptr, global_total,
+           b->aux);
     b->cdf_valid    = true;
     b->suffix_valid = false;
     return FBA_OK;
 }
 
 // record layout of the export / import staging area: [stride floats][state][structure id][pad 8]
-// Phases 2-3 in one call, with the quota allocation and the exchange plan computed here:
-// totals[G] are the all-gathered shard totals, u in [0,1) the shared systematic offset.
-// send_plan (G x G, row-major, may be NULL) receives send[g][h] = records rank g ships to rank h.
-extern "C" int fba_belief_shard_resample(fba_belief* b, const double* totals, int32_t n_ranks, int32_t rank,
-                                         double u, fba_rng* rng, int64_t* send_plan, double* global_total)
+// quotas + exchange plan from the shard totals (host): shared by the sync and async entry points
+static int shard_plan(fba_belief* b, const double* totals, int n_ranks, double u, std::vector<long long>& quota,
+                      int64_t* send_plan, double* global_total)
 {
-    if (!b || !totals || !rng) return FBA_ERR_INVALID;
     fba_ctx* ctx = b->ctx;
-    REQUIRE(ctx, n_ranks >= 1 && rank >= 0 && rank < n_ranks, "shard_resample: bad rank");
-    REQUIRE(ctx, u >= 0.0 && u < 1.0, "shard_resample: u must be in [0,1)");
+    REQUIRE(ctx, u >= 0.0 && u < 1.0, "shard plan: u must be in [0,1)");
     double W = 0.0;
     for (int g = 0; g < n_ranks; ++g)
     {
-        REQUIRE(ctx, totals[g] >= 0.0 && std::isfinite(totals[g]), "shard_resample: bad shard total");
+        REQUIRE(ctx, totals[g] >= 0.0 && std::isfinite(totals[g]), "shard plan: bad shard total");
         W += totals[g];
     }
-    REQUIRE(ctx, W > 0.0, "shard_resample: total weight must be positive");
-    // systematic allocation over ranks: quota_g = #{j : (j + u)/n in (C_{g-1}, C_g]}
+    REQUIRE(ctx, W > 0.0, "shard plan: total weight must be positive");
     long long const n_total = b->N * n_ranks;
-    std::vector<long long> quota(n_ranks);
+    quota.assign(n_ranks, 0);
     long long prev = 0;
-    double acc = 0.0;
+    double acc     = 0.0;
     for (int g = 0; g < n_ranks; ++g)
     {
         acc += totals[g];
@@ -1493,9 +1502,76 @@ extern "C" int fba_belief_shard_resample(fba_belief* b, const double* totals, in
             }
     }
     if (global_total) *global_total = W;
-    int rc = fba_belief_normalize(b, W);
+    return FBA_OK;
+}
+
+// Asynchronous phases 2+3: the shard totals are read from DEVICE memory (where the all-gather left
+// them), the quota is computed on device, nothing here waits for the GPU. The export buffer must
+// already be large enough (fba_belief_reserve_export); surplus beyond it is dropped and reported by
+// fba_belief_shard_plan as FBA_ERR_CAPACITY.
+extern "C" int fba_belief_shard_resample_async(fba_belief* b, const double* totals_device, int32_t n_ranks,
+                                               int32_t rank, double u, fba_rng* rng)
+{
+    if (!b || !totals_device || !rng) return FBA_ERR_INVALID;
+    fba_ctx* ctx = b->ctx;
+    REQUIRE(ctx, rng->mode == FBA_RNG_PHILOX, "sharded beliefs run in PHILOX mode");
+    REQUIRE(ctx, ctx->inplace_resample, "shard_resample_async needs the in-place resampler");
+    REQUIRE(ctx, n_ranks >= 1 && rank >= 0 && rank < n_ranks, "shard_resample_async: bad rank");
+    REQUIRE(ctx, u >= 0.0 && u < 1.0, "shard_resample_async: u must be in [0,1)");
+    CU(ctx, cudaSetDevice(ctx->device));
+    int const n_tiles = (int)((b->N + kTile - 1) / kTile);
+    LAUNCH(ctx, k_shard_quota, 1, 1, totals_device, n_ranks, rank, u, b->N, b->scal + 2, b->d_quota);
+    // tile sums from fba_belief_propose are still in b->tile (exclusive-scanned)
+    LAUNCH(ctx, k_scale_and_scan, n_tiles, kThreads, b->w, b->N, b->tile, (const double*)(b->scal + 2), 1.0,
+           b->aux);
+    b->cdf_valid    = true;
+    b->suffix_valid = false;
+    return resample_inplace(b, rng, 0, b->d_quota);
+}
+
+// Host half of the asynchronous update: the plan for the totals (now on the host), the export /
+// import bookkeeping of this rank.
+extern "C" int fba_belief_shard_plan(fba_belief* b, const double* totals, int32_t n_ranks, int32_t rank,
+                                     double u, int64_t* send_plan, double* global_total)
+{
+    if (!b || !totals) return FBA_ERR_INVALID;
+    fba_ctx* ctx = b->ctx;
+    REQUIRE(ctx, n_ranks >= 1 && rank >= 0 && rank < n_ranks, "shard_plan: bad rank");
+    std::vector<long long> quota;
+    int rc = shard_plan(b, totals, n_ranks, u, quota, send_plan, global_total);
     if (rc) return rc;
+    b->local_kept  = std::min<long long>(quota[rank], b->N);
+    b->xport_count = std::max(0ll, quota[rank] - b->N);
+    if (b->xport_count > b->xport_cap)
+    {
+        ctx->err = "shard surplus of " + std::to_string(b->xport_count) + " records exceeds the export buffer ("
+                   + std::to_string(b->xport_cap) + "); call fba_belief_reserve_export with a larger count";
+        return FBA_ERR_CAPACITY;
+    }
+    return FBA_OK;
+}
+
+// Phases 2-3 in one synchronous-input call: totals[G] are the all-gathered shard totals on the HOST.
+extern "C" int fba_belief_shard_resample(fba_belief* b, const double* totals, int32_t n_ranks, int32_t rank,
+                                         double u, fba_rng* rng, int64_t* send_plan, double* global_total)
+{
+    if (!b || !totals || !rng) return FBA_ERR_INVALID;
+    fba_ctx* ctx = b->ctx;
+    REQUIRE(ctx, n_ranks >= 1 && rank >= 0 && rank < n_ranks, "shard_resample: bad rank");
+    std::vector<long long> quota;
+    double W = 0.0;
+    int rc   = shard_plan(b, totals, n_ranks, u, quota, send_plan, &W);
+    if (rc) return rc;
+    if (global_total) *global_total = W;
+    if ((rc = fba_belief_normalize(b, W))) return rc;
     return fba_belief_resample_shard(b, quota[rank], rng);
+}
+
+extern "C" int fba_belief_reserve_export(fba_belief* b, int64_t records)
+{
+    if (!b || records < 0) return FBA_ERR_INVALID;
+    cudaSetDevice(b->ctx->device);
+    return ensure_export(b, records);
 }
 
 extern "C" int64_t fba_belief_record_bytes(const fba_belief* b)

@@ -350,12 +350,11 @@ __global__ void __launch_bounds__(kThreads)
 // w_i /= scal[0] (optionally), inclusive prefix sums into cdf
 __global__ void __launch_bounds__(kThreads)
     k_scale_and_scan(double* __restrict__ w, long long N, const double* __restrict__ tile_off,
-                     const double* __restrict__ scal, double divide_by, int use_scal,
-                     double* __restrict__ cdf)
+                     const double* __restrict__ total_ptr, double divide_by, double* __restrict__ cdf)
 {
     __shared__ double sh[kThreads];
     long long const base = (long long)blockIdx.x * kTile + (long long)threadIdx.x * (kTile / kThreads);
-    double const total   = use_scal ? scal[0] : divide_by;
+    double const total   = total_ptr ? *total_ptr : divide_by;
     double v[kTile / kThreads];
     double run = 0.0;
 #pragma unroll
@@ -432,12 +431,38 @@ __device__ __forceinline__ long long sys_count_below(double c, double inv_s, dou
     return (long long)v;
 }
 
+// multi-GPU: this rank's offspring quota from the all-gathered shard totals, on device, so the
+// host need not synchronise before the resampling kernels are enqueued. Systematic allocation over
+// ranks: quota_g = #{j : (j + u)/n_total in (C_{g-1}, C_g]}. out_total[0] = W, out_quota[0] = quota.
+__global__ void k_shard_quota(const double* __restrict__ totals, int n_ranks, int rank, double u,
+                              long long n_local, double* __restrict__ out_total,
+                              long long* __restrict__ out_quota)
+{
+    double W = 0.0;
+    for (int g = 0; g < n_ranks; ++g) W += totals[g];
+    long long const n_total = n_local * n_ranks;
+    long long prev = 0, quota = 0;
+    double acc = 0.0;
+    for (int g = 0; g <= rank; ++g)
+    {
+        acc += totals[g];
+        long long edge = (g == n_ranks - 1) ? n_total : (long long)floor(acc / W * (double)n_total - u + 1.0);
+        edge  = min(max(edge, prev), n_total);
+        quota = edge - prev;
+        prev  = edge;
+    }
+    out_total[0] = W;
+    out_quota[0] = (W > 0.0) ? quota : 0;
+}
+
 // per tile: offspring counts -> (dead, extra) tile sums
 __global__ void __launch_bounds__(kThreads)
-    k_offspring(const double* __restrict__ cdf, long long N, long long n_out, RngArgs ra,
-                int* __restrict__ noff, int2* __restrict__ tile_sum)
+    k_offspring(const double* __restrict__ cdf, long long N, long long n_out,
+                const long long* __restrict__ n_out_ptr, RngArgs ra, int* __restrict__ noff,
+                int2* __restrict__ tile_sum)
 {
     __shared__ int shd[kThreads / 32], she[kThreads / 32];
+    if (n_out_ptr) n_out = *n_out_ptr;
     auto g             = RngOf<false>::make(ra, 0);
     double const u     = draw_u(g);
     // a shard whose weights all collapsed gets no offspring: every slot is dead
@@ -584,10 +609,17 @@ __global__ void __launch_bounds__(kThreads)
 __global__ void __launch_bounds__(kThreads)
     k_copy_inplace(float* counts, long long stride, int* state, int* sid, const int* __restrict__ struct_size,
                    const int* __restrict__ extra_scan, long long N, const int* __restrict__ dead_slot,
-                   const int* __restrict__ totals, char* __restrict__ xport, long long rec_bytes)
+                   const int* __restrict__ totals, char* __restrict__ xport, long long rec_bytes,
+                   long long xport_cap, long long* __restrict__ stats)
 {
-    long long const n_dead = totals[0], n_copies = totals[1];
-    long long const n_fill = min(n_dead, n_copies); // the rest (if any) is this shard's surplus
+    long long const n_dead = totals[0];
+    long long const n_fill = min(n_dead, (long long)totals[1]); // the rest (if any) is this shard's surplus
+    long long n_copies     = totals[1];
+    if (n_copies - n_fill > xport_cap)
+    { // more surplus than the export buffer holds: drop the excess and report it
+        if (blockIdx.x == 0 && threadIdx.x == 0) stats[2] = n_copies - n_fill - xport_cap;
+        n_copies = n_fill + xport_cap;
+    }
     int const lane        = threadIdx.x & 31;
     long long const warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     long long const nwarp = ((long long)gridDim.x * blockDim.x) >> 5;

@@ -101,12 +101,26 @@ class ShardedBAImportanceSampling(BAImportanceSampling):
 
     def _setup(self):
         import torch
+        L, h = self.L, self.h
         self._stream = torch.cuda.ExternalStream(self.ctx.stream)
-        scal = self.L.fba_belief_scalars_ptr(self.h)
+        scal = L.fba_belief_scalars_ptr(h)
         self._local = torch.as_tensor(_RawCuda(scal, 8, "<f8", 8), device="cuda")  # view of scal[0]
         self._totals = torch.empty(self.world, dtype=torch.float64, device="cuda")
         self._totals_host = torch.empty(self.world, dtype=torch.float64).pin_memory()
         self._plan = np.zeros((self.world, self.world), np.int64)
+        self._event = torch.cuda.Event()
+        # export staging for the surplus of an over-quota shard: 1/64 of the shard by default
+        _check(self.ctx.h, L.fba_belief_reserve_export(h, max(1024, self._n // 64)))
+        if self.world > 1:
+            # establish every pairwise NCCL connection now (the exchange plan picks different pairs
+            # from step to step; first use of a pair costs milliseconds)
+            rb = L.fba_belief_record_bytes(h)
+            warm_plan = np.ones((self.world, self.world), np.int64) - np.eye(self.world, dtype=np.int64)
+            src = torch.zeros((self.world - 1) * rb, dtype=torch.uint8, device="cuda")
+            exchange_records(self.dist, self.group, warm_plan, self.rank, src, rb)
+            self.dist.all_gather_into_tensor(self._totals, torch.zeros(1, dtype=torch.float64, device="cuda"),
+                                             group=self.group)
+            torch.cuda.synchronize()
         self._bufs = True
 
     def free(self, _simulator=None):
@@ -115,36 +129,41 @@ class ShardedBAImportanceSampling(BAImportanceSampling):
         import torch
         if self._bufs:
             torch.cuda.synchronize()
-            self._local = self._totals = self._totals_host = self._stream = None
+            self._local = self._totals = self._totals_host = self._stream = self._event = None
             self._bufs = None
         super().free()
 
     def updateEstimation(self, a, o, rng, step_uniform=0.5):
         """One global importance-sampling update + resample. `step_uniform` in [0,1) must be the
-        same on every rank (the shared systematic offset of the quota allocation)."""
+        same on every rank (the shared systematic offset of the quota allocation).
+
+        Everything is enqueued on the library's stream without waiting for the GPU; the host only
+        waits for the G shard totals (a D2H copy ordered BEFORE the resampling kernels), which it
+        needs for the all-to-all's split sizes, while the GPU is already resampling."""
         import time
         import torch
         L, h, ctx = self.L, self.h, self.ctx
         if self._bufs is None:
             self._setup()
+        u = float(step_uniform)
         t0 = time.perf_counter()
         with torch.cuda.stream(self._stream):
-            # phase 1 (async): step + weights + shard total, left on the device
+            # phase 1: step + weights + shard total (left on the device)
             _check(ctx.h, L.fba_belief_propose(h, a, o, C.byref(rng), None))
             if self.world > 1:
                 self.dist.all_gather_into_tensor(self._totals, self._local, group=self.group)
             else:
                 self._totals.copy_(self._local)
             self._totals_host.copy_(self._totals, non_blocking=True)
-            self._stream.synchronize()  # the one host sync of the update
+            self._event.record(self._stream)
+            # phases 2-3: quota on device, normalise, resample in place, surplus -> export buffer
+            _check(ctx.h, L.fba_belief_shard_resample_async(h, self._totals.data_ptr(), self.world, self.rank,
+                                                            u, C.byref(rng)))
+            self._event.synchronize()  # totals are on the host; the GPU keeps resampling
             t1 = time.perf_counter()
-            # phases 2-3 (async): quotas + exchange plan (computed in the library, identically on
-            # every rank), normalise by the global total, resample this shard to its quota
             plan, tot = self._plan, C.c_double(0)
-            _check(ctx.h, L.fba_belief_shard_resample(h, self._totals_host.data_ptr(), self.world, self.rank,
-                                                      float(step_uniform), C.byref(rng),
-                                                      plan.ctypes.data_as(C.c_void_p), C.byref(tot)))
-            total = tot.value
+            _check(ctx.h, L.fba_belief_shard_plan(h, self._totals_host.data_ptr(), self.world, self.rank, u,
+                                                  plan.ctypes.data_as(C.c_void_p), C.byref(tot)))
             self.moved_last = int(plan.sum())
             if self.moved_last:
                 rb = L.fba_belief_record_bytes(h)
@@ -154,8 +173,8 @@ class ShardedBAImportanceSampling(BAImportanceSampling):
                 dst = (torch.as_tensor(_RawCuda(L.fba_belief_import_ptr(h, n_in), n_in * rb), device="cuda")
                        if n_in else torch.empty(0, dtype=torch.uint8, device="cuda"))
                 exchange_records(self.dist, self.group, plan, self.rank, src, rb, dst)
-                # phase 4 (async): imported records fill the slots the local resample left dead
+                # phase 4: imported records fill the slots the local resample left dead
                 _check(ctx.h, L.fba_belief_import(h, n_in))
-        self.phase_ms = {"propose+all_gather (1 sync)": (t1 - t0) * 1e3,
-                         "plan+normalize+resample+exchange (enqueue)": (time.perf_counter() - t1) * 1e3}
-        return total
+        self.phase_ms = {"enqueue propose..resample + wait for totals": (t1 - t0) * 1e3,
+                         "plan + exchange (enqueue)": (time.perf_counter() - t1) * 1e3}
+        return tot.value

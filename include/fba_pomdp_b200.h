@@ -227,6 +227,16 @@ int fba_belief_resample_stats(fba_belief* b, int64_t* copies, int64_t* resamples
  * n_ranks, row-major, may be NULL) receives the records rank g ships to rank h */
 int fba_belief_shard_resample(fba_belief* b, const double* totals, int32_t n_ranks, int32_t rank, double u,
                               fba_rng* rng, int64_t* send_plan, double* global_total);
+/* the same, split so that nothing waits for the GPU before the resampling kernels are enqueued:
+ * _async reads the shard totals from DEVICE memory (where the all-gather left them) and computes
+ * this rank's quota on device; _plan (host, any time later) returns the exchange plan for the same
+ * totals and sets this rank's export / import bookkeeping. The export buffer must have been
+ * reserved (fba_belief_reserve_export); a surplus beyond it makes _plan return FBA_ERR_CAPACITY. */
+int fba_belief_shard_resample_async(fba_belief* b, const double* totals_device, int32_t n_ranks,
+                                    int32_t rank, double u, fba_rng* rng);
+int fba_belief_shard_plan(fba_belief* b, const double* totals_host, int32_t n_ranks, int32_t rank, double u,
+                          int64_t* send_plan, double* global_total);
+int fba_belief_reserve_export(fba_belief* b, int64_t records);
 int64_t fba_belief_export_count(const fba_belief* b);
 /* device pointers of the export / import staging area: particle records of
  * fba_belief_record_bytes() each (count block, then state, structure id) */
