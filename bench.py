@@ -206,7 +206,7 @@ def main_ours(args):
     C = int(sim.structure_size(0))
     bytes_per_particle = 2 * (4 * C + 4 + 8)  # counts + state + weight, read + written
 
-    if world > 1:
+    if world > 1 or args.force_sharded:
         b = fba.ShardedBAImportanceSampling(n_local)
         rng = b.rank_rng(args.seed)
     else:
@@ -217,7 +217,7 @@ def main_ours(args):
 
     def step(t, want_likelihood=False):
         a, o = script[t % len(script)]
-        if world > 1:
+        if world > 1 or args.force_sharded:
             return b.updateEstimation(a, o, rng, step_uniform=float(shared.random_sample()))
         return b.updateEstimation(a, o, rng, want_likelihood=want_likelihood)
 
@@ -295,6 +295,12 @@ def main_ours(args):
 
     # ---- the default path: in-place systematic resampling (survivors are not moved) ----
     ms, table, launches, clocks, copies = timed_region(args.steps, args.warmup + 2)
+    if world > 1 and args.trace:
+        b.trace = []
+        for t in range(10):
+            step(1000 + t)
+        print("trace rank %d: %s" % (rank, b.trace_summary()), file=sys.stderr)
+        b.trace = None
     value = n_local * world * args.steps / (ms * 1e-3)
     dominant = max(table, key=lambda k: table[k]["share_of_step"])
     copied_frac = copies / float(n_local * args.steps)
@@ -312,7 +318,7 @@ def main_ours(args):
     # ---- the full-copy path (every particle gathered into the second buffer): the roofline the
     #      north star names — >= 60 % of HBM peak on the sysadmin shard ----
     full = None
-    if world == 1 and not args.no_full_copy:
+    if world == 1 and not args.no_full_copy and not args.force_sharded:
         ctx.set_option("inplace_resample", 0)
         for t in range(3):
             step(t)
@@ -329,7 +335,7 @@ def main_ours(args):
     t0 = time.perf_counter()
     d2h = 0
     for t in range(args.steps):
-        if world > 1:
+        if world > 1 or args.force_sharded:
             step(args.warmup + args.steps + t)
         else:
             step(args.warmup + args.steps + t, want_likelihood=True)
@@ -400,6 +406,8 @@ def main():
     ap.add_argument("--ref-particles", type=int, default=4096)
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--force-sharded", action="store_true", help="use the sharded code path on 1 GPU")
+    ap.add_argument("--trace", action="store_true", help="per-phase device timing of the sharded update")
     ap.add_argument("--no-full-copy", action="store_true", help="skip the full-copy resampling leg")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -79,9 +79,10 @@ struct fba_belief
     bool suffix_valid = false;  // aux holds R for the current weights
     bool cdf_valid    = false;  // aux holds the native cdf for the current weights
     // in-place resampling
-    int *noff = nullptr, *escan = nullptr, *dead = nullptr, *totals = nullptr;
+    int *noff = nullptr, *escan = nullptr, *dead = nullptr, *totals = nullptr, *src_of = nullptr;
     long long* stats = nullptr; // [0] copies made by in-place resamples, [1] number of resamples,
                                 // [2] surplus records dropped because the export buffer was full
+    long long src_cap = 0;
     long long* d_quota = nullptr; // device-side offspring quota (fba_belief_shard_resample_async)
     int2* tile_pairs = nullptr;
     bool inplace_last = false; // the last shard resample ran in place (import goes to dead slots)
@@ -95,6 +96,7 @@ struct fba_belief
     char* import_buf = nullptr;
     long long import_cap = 0;
     long long local_kept = 0;
+    long long imported   = 0; // records imported since the last shard resample
 };
 
 #define CU(ctx, call)                                                                              \
@@ -602,6 +604,8 @@ extern "C" int fba_belief_create(fba_ctx* ctx, fba_model* m, int64_t N, int64_t 
     if (e == cudaSuccess) e = cudaMalloc(&b->noff, (size_t)N * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&b->escan, (size_t)N * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&b->dead, (size_t)N * sizeof(int));
+    b->src_cap = 2 * N + 1024; // extras <= offspring total; a shard's quota never exceeds 2N here
+    if (e == cudaSuccess) e = cudaMalloc(&b->src_of, (size_t)b->src_cap * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&b->totals, 2 * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&b->stats, 4 * sizeof(long long));
     if (e == cudaSuccess) e = cudaMemset(b->stats, 0, 4 * sizeof(long long));
@@ -631,7 +635,7 @@ extern "C" void fba_belief_destroy(fba_belief* b)
     cudaFree(b->w), cudaFree(b->aux), cudaFree(b->tile), cudaFree(b->scal), cudaFree(b->anc);
     cudaFree(b->att_src), cudaFree(b->att_state), cudaFree(b->att_accept), cudaFree(b->att_pos);
     cudaFree(b->att_rec), cudaFree(b->d_total), cudaFree(b->xport), cudaFree(b->import_buf);
-    cudaFree(b->d_quota), cudaFree(b->stats), cudaFree(b->noff), cudaFree(b->escan), cudaFree(b->dead), cudaFree(b->totals), cudaFree(b->tile_pairs);
+    cudaFree(b->src_of), cudaFree(b->d_quota), cudaFree(b->stats), cudaFree(b->noff), cudaFree(b->escan), cudaFree(b->dead), cudaFree(b->totals), cudaFree(b->tile_pairs);
     delete b;
 }
 
@@ -977,10 +981,12 @@ static int resample_inplace(fba_belief* b, fba_rng* rng, long long n_out, const 
     LAUNCH(ctx, k_offspring, n_tiles, kThreads, b->aux, b->N, n_out, n_out_dev, philox_args(rng), b->noff,
            b->tile_pairs);
     LAUNCH(ctx, k_scan_tile_pairs, 1, kThreads, b->tile_pairs, n_tiles, b->totals, b->stats);
-    LAUNCH(ctx, k_offspring_apply, n_tiles, kThreads, b->noff, b->N, b->tile_pairs, b->dead, b->escan);
+    CU(ctx, cudaMemsetAsync(b->src_of, 0xFF, (size_t)b->src_cap * sizeof(int), ctx->stream));
+    LAUNCH(ctx, k_offspring_apply, n_tiles, kThreads, b->noff, b->N, b->tile_pairs, b->dead, b->escan, b->src_of,
+           b->src_cap);
     LAUNCH(ctx, k_copy_inplace, stream_grid(ctx, b->N), kThreads, b->counts[b->cur], b->stride,
-           b->state[b->cur], b->sid[b->cur], b->m->d_sizes, b->escan, b->N, b->dead, b->totals, b->xport, rb,
-           b->xport_cap, b->stats);
+           b->state[b->cur], b->sid[b->cur], b->m->d_sizes, b->escan, b->src_of, b->N, b->dead, b->totals,
+           b->xport, rb, b->xport_cap, b->stats, b->src_cap);
     LAUNCH(ctx, k_fill, blocks_for(b->N), kThreads, b->w, b->N, 1.0 / (double)b->N);
     b->total_weight = 1.0;
     b->suffix_valid = b->cdf_valid = false;
@@ -1542,6 +1548,7 @@ extern "C" int fba_belief_shard_plan(fba_belief* b, const double* totals, int32_
     if (rc) return rc;
     b->local_kept  = std::min<long long>(quota[rank], b->N);
     b->xport_count = std::max(0ll, quota[rank] - b->N);
+    b->imported    = 0;
     if (b->xport_count > b->xport_cap)
     {
         ctx->err = "shard surplus of " + std::to_string(b->xport_count) + " records exceeds the export buffer ("
@@ -1565,6 +1572,26 @@ extern "C" int fba_belief_shard_resample(fba_belief* b, const double* totals, in
     if (global_total) *global_total = W;
     if ((rc = fba_belief_normalize(b, W))) return rc;
     return fba_belief_resample_shard(b, quota[rank], rng);
+}
+
+// Imports n_records records lying at an arbitrary DEVICE address (e.g. inside an all-gathered
+// window) into the dead slots [already_imported, already_imported + n_records) the local resample
+// left. Asynchronous. Only after an in-place shard resample.
+extern "C" int fba_belief_import_from(fba_belief* b, const void* records_device, int64_t n_records)
+{
+    if (!b) return FBA_ERR_INVALID;
+    fba_ctx* ctx = b->ctx;
+    if (n_records == 0) return FBA_OK;
+    REQUIRE(ctx, records_device && n_records > 0, "import_from: null records");
+    REQUIRE(ctx, b->inplace_last, "import_from: needs a preceding in-place shard resample");
+    REQUIRE(ctx, b->local_kept + n_records <= b->N, "import_from: more records than empty slots");
+    CU(ctx, cudaSetDevice(ctx->device));
+    LAUNCH(ctx, k_import_inplace, stream_grid(ctx, n_records), kThreads, b->counts[b->cur], b->stride,
+           b->state[b->cur], b->sid[b->cur], b->dead, b->totals, b->imported, (long long)n_records,
+           (const char*)records_device, fba_belief_record_bytes(b));
+    b->imported += n_records;
+    b->local_kept += n_records;
+    return FBA_OK;
 }
 
 extern "C" int fba_belief_reserve_export(fba_belief* b, int64_t records)
@@ -1638,6 +1665,7 @@ extern "C" int fba_belief_resample_shard(fba_belief* b, int64_t n_offspring, fba
     long long const surplus = n_offspring - kept;
     b->local_kept  = kept;
     b->xport_count = surplus;
+    b->imported    = 0;
     if (ctx->inplace_resample)
     {
         return resample_inplace(b, rng, n_offspring); // asynchronous: export buffer valid in stream order
@@ -1733,7 +1761,7 @@ extern "C" int fba_belief_import(fba_belief* b, int64_t n_records)
     if (b->inplace_last)
     {
         LAUNCH(ctx, k_import_inplace, stream_grid(ctx, n_records), kThreads, b->counts[b->cur], b->stride,
-               b->state[b->cur], b->sid[b->cur], b->dead, b->totals, (long long)n_records, b->import_buf,
+               b->state[b->cur], b->sid[b->cur], b->dead, b->totals, 0ll, (long long)n_records, b->import_buf,
                fba_belief_record_bytes(b));
         b->local_kept += n_records;
         return FBA_OK; // asynchronous

@@ -539,7 +539,8 @@ __global__ void __launch_bounds__(kThreads)
 // per tile: dead_slot[k] = index of the k-th dead particle; extra_scan[i] = exclusive scan of extra
 __global__ void __launch_bounds__(kThreads)
     k_offspring_apply(const int* __restrict__ noff, long long N, const int2* __restrict__ tile_off,
-                      int* __restrict__ dead_slot, int* __restrict__ extra_scan)
+                      int* __restrict__ dead_slot, int* __restrict__ extra_scan, int* __restrict__ src_of,
+                      long long src_cap)
 {
     __shared__ int shd[kThreads], she[kThreads];
     constexpr int PER    = kTile / kThreads;
@@ -574,6 +575,10 @@ __global__ void __launch_bounds__(kThreads)
         {
             extra_scan[i] = pe;
             if (n[k] == 0) dead_slot[pd++] = (int)i;
+            // source of the copies pe, pe+1 (a particle rarely has more than two extras; further
+            // entries keep the -1 they were memset to and are resolved by binary search)
+            if (n[k] > 1 && pe < src_cap) src_of[pe] = (int)i;
+            if (n[k] > 2 && pe + 1 < src_cap) src_of[pe + 1] = (int)i;
             pe += (n[k] > 1) ? n[k] - 1 : 0;
         }
     }
@@ -582,13 +587,13 @@ __global__ void __launch_bounds__(kThreads)
 // multi-GPU: imported record r fills the (n_extra + r)-th dead slot (those the local extras left)
 __global__ void __launch_bounds__(kThreads)
     k_import_inplace(float* __restrict__ dst, long long stride, int* __restrict__ state, int* __restrict__ sid,
-                     const int* __restrict__ dead_slot, const int* __restrict__ totals, long long n,
-                     const char* __restrict__ in, long long rec_bytes)
+                     const int* __restrict__ dead_slot, const int* __restrict__ totals, long long slot_offset,
+                     long long n, const char* __restrict__ in, long long rec_bytes)
 {
     int const lane        = threadIdx.x & 31;
     long long const warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     long long const nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
-    long long const first = totals[1];
+    long long const first = totals[1] + slot_offset;
     for (long long r = warp0; r < n; r += nwarp)
     {
         const char* rec      = in + r * rec_bytes;
@@ -608,9 +613,9 @@ __global__ void __launch_bounds__(kThreads)
 // survivors (never written), destinations are dead (never read).
 __global__ void __launch_bounds__(kThreads)
     k_copy_inplace(float* counts, long long stride, int* state, int* sid, const int* __restrict__ struct_size,
-                   const int* __restrict__ extra_scan, long long N, const int* __restrict__ dead_slot,
-                   const int* __restrict__ totals, char* __restrict__ xport, long long rec_bytes,
-                   long long xport_cap, long long* __restrict__ stats)
+                   const int* __restrict__ extra_scan, const int* __restrict__ src_of, long long N,
+                   const int* __restrict__ dead_slot, const int* __restrict__ totals, char* __restrict__ xport,
+                   long long rec_bytes, long long xport_cap, long long* __restrict__ stats, long long src_cap)
 {
     long long const n_dead = totals[0];
     long long const n_fill = min(n_dead, (long long)totals[1]); // the rest (if any) is this shard's surplus
@@ -625,16 +630,20 @@ __global__ void __launch_bounds__(kThreads)
     long long const nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
     for (long long k = warp0; k < n_copies; k += nwarp)
     {
-        long long lo = 0, hi = N; // first i with extra_scan[i] > k
-        while (lo < hi)
-        {
-            long long const mid = (lo + hi) >> 1;
-            if (extra_scan[mid] > (int)k) hi = mid;
-            else
-                lo = mid + 1;
+        long long i = (k < src_cap) ? src_of[k] : -1;
+        if (i < 0)
+        { // third or later extra of one particle: the last i with extra_scan[i] <= k
+            long long lo = 0, hi = N;
+            while (lo < hi)
+            {
+                long long const mid = (lo + hi) >> 1;
+                if (extra_scan[mid] > (int)k) hi = mid;
+                else
+                    lo = mid + 1;
+            }
+            i = lo - 1;
         }
-        long long const i = lo - 1;
-        int const id      = sid[i];
+        int const id = sid[i];
         if (k < n_fill)
         {
             long long const j = dead_slot[k];

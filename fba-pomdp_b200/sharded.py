@@ -93,6 +93,24 @@ class ShardedBAImportanceSampling(BAImportanceSampling):
         self.moved_last = 0
         self.phase_ms = {}
         self._bufs = None
+        self.trace = None  # set to [] to record per-phase CUDA events (trace_summary)
+
+    def _trace_events(self):
+        import torch
+        return [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+
+    def trace_summary(self):
+        """Mean device milliseconds per phase over the traced updates."""
+        import torch
+        torch.cuda.synchronize()
+        names = ["propose+sums", "all_gather+D2H", "quota+normalise+resample", "exchange+import"]
+        out = {}
+        for k, nm in enumerate(names):
+            out[nm] = float(np.mean([t[k].elapsed_time(t[k + 1]) for t in self.trace]))
+        out["gap to next update"] = float(np.mean([a[4].elapsed_time(b[0])
+                                                   for a, b in zip(self.trace[:-1], self.trace[1:])])) \
+            if len(self.trace) > 1 else 0.0
+        return out
 
     def rank_rng(self, seed):
         """A PHILOX source whose key differs per rank, so shards draw independent streams."""
@@ -109,19 +127,57 @@ class ShardedBAImportanceSampling(BAImportanceSampling):
         self._totals_host = torch.empty(self.world, dtype=torch.float64).pin_memory()
         self._plan = np.zeros((self.world, self.world), np.int64)
         self._event = torch.cuda.Event()
-        # export staging for the surplus of an over-quota shard: 1/64 of the shard by default
-        _check(self.ctx.h, L.fba_belief_reserve_export(h, max(1024, self._n // 64)))
+        # export staging for the surplus of an over-quota shard: 1/64 of the shard by default;
+        # the exchange window is capped so that the gathered buffer stays <= 1 GiB
+        rb = L.fba_belief_record_bytes(h)
+        cap = max(1024, self._n // 64)
+        self._window_cap = 64
+        while self._window_cap * 2 <= cap and self._window_cap * 2 * rb * self.world <= (1 << 30):
+            self._window_cap *= 2
+        _check(self.ctx.h, L.fba_belief_reserve_export(h, cap + self._window_cap))
+        self._gather_buf = torch.empty(self.world * self._window_cap * rb, dtype=torch.uint8, device="cuda")
         if self.world > 1:
-            # establish every pairwise NCCL connection now (the exchange plan picks different pairs
-            # from step to step; first use of a pair costs milliseconds)
-            rb = L.fba_belief_record_bytes(h)
-            warm_plan = np.ones((self.world, self.world), np.int64) - np.eye(self.world, dtype=np.int64)
-            src = torch.zeros((self.world - 1) * rb, dtype=torch.uint8, device="cuda")
-            exchange_records(self.dist, self.group, warm_plan, self.rank, src, rb)
+            w = 64
+            while w <= self._window_cap:  # touch every window size once (NCCL algorithm selection)
+                src = torch.as_tensor(_RawCuda(L.fba_belief_export_ptr(h), w * rb), device="cuda")
+                self.dist.all_gather_into_tensor(self._gather_buf[:self.world * w * rb], src, group=self.group)
+                w *= 2
             self.dist.all_gather_into_tensor(self._totals, torch.zeros(1, dtype=torch.float64, device="cuda"),
                                              group=self.group)
             torch.cuda.synchronize()
         self._bufs = True
+
+    def _exchange(self, plan):
+        """Ships the surplus records: every rank contributes a fixed-size WINDOW of its export
+        buffer to one all-gather (a ring collective whose connections exist since communicator
+        setup — unlike send/recv pairs, nothing is connected lazily in the timed path), then imports
+        the segments addressed to it. Window = the largest surplus, rounded up to a power of two;
+        plans larger than the reserved staging run in several rounds."""
+        import torch
+        L, h, ctx = self.L, self.h, self.ctx
+        rb = L.fba_belief_record_bytes(h)
+        sent = plan.sum(1)
+        window = 64
+        while window < int(sent.max()):
+            window *= 2
+        window = min(window, self._window_cap)
+        exp_ptr = L.fba_belief_export_ptr(h)
+        rounds = -(-int(sent.max()) // window)
+        for r in range(rounds):
+            lo = r * window
+            src = torch.as_tensor(_RawCuda(exp_ptr + lo * rb, window * rb), device="cuda")
+            out = self._gather_buf[:self.world * window * rb]
+            self.dist.all_gather_into_tensor(out, src, group=self.group)
+            # sender g's records for rank h start at sum(plan[g, :h]) in its export buffer
+            for g in range(self.world):
+                n = int(plan[g, self.rank])
+                if not n:
+                    continue
+                first = int(plan[g, :self.rank].sum())
+                a, b_ = max(first, lo), min(first + n, lo + window)
+                if a < b_:
+                    addr = out.data_ptr() + (g * window + (a - lo)) * rb
+                    _check(ctx.h, L.fba_belief_import_from(h, addr, b_ - a))
 
     def free(self, _simulator=None):
         """Drops the torch views / buffers tied to the library's stream before the belief (and later
@@ -129,7 +185,7 @@ class ShardedBAImportanceSampling(BAImportanceSampling):
         import torch
         if self._bufs:
             torch.cuda.synchronize()
-            self._local = self._totals = self._totals_host = self._stream = self._event = None
+            self._local = self._totals = self._totals_host = self._stream = self._event = self._gather_buf = None
             self._bufs = None
         super().free()
 
@@ -147,18 +203,27 @@ class ShardedBAImportanceSampling(BAImportanceSampling):
             self._setup()
         u = float(step_uniform)
         t0 = time.perf_counter()
+        trace = self._trace_events() if self.trace is not None else None
         with torch.cuda.stream(self._stream):
+            if trace:
+                trace[0].record(self._stream)
             # phase 1: step + weights + shard total (left on the device)
             _check(ctx.h, L.fba_belief_propose(h, a, o, C.byref(rng), None))
+            if trace:
+                trace[1].record(self._stream)
             if self.world > 1:
                 self.dist.all_gather_into_tensor(self._totals, self._local, group=self.group)
             else:
                 self._totals.copy_(self._local)
             self._totals_host.copy_(self._totals, non_blocking=True)
             self._event.record(self._stream)
+            if trace:
+                trace[2].record(self._stream)
             # phases 2-3: quota on device, normalise, resample in place, surplus -> export buffer
             _check(ctx.h, L.fba_belief_shard_resample_async(h, self._totals.data_ptr(), self.world, self.rank,
                                                             u, C.byref(rng)))
+            if trace:
+                trace[3].record(self._stream)
             self._event.synchronize()  # totals are on the host; the GPU keeps resampling
             t1 = time.perf_counter()
             plan, tot = self._plan, C.c_double(0)
@@ -166,15 +231,10 @@ class ShardedBAImportanceSampling(BAImportanceSampling):
                                                   plan.ctypes.data_as(C.c_void_p), C.byref(tot)))
             self.moved_last = int(plan.sum())
             if self.moved_last:
-                rb = L.fba_belief_record_bytes(h)
-                n_out, n_in = int(plan[self.rank].sum()), int(plan[:, self.rank].sum())
-                src = (torch.as_tensor(_RawCuda(L.fba_belief_export_ptr(h), n_out * rb), device="cuda")
-                       if n_out else torch.empty(0, dtype=torch.uint8, device="cuda"))
-                dst = (torch.as_tensor(_RawCuda(L.fba_belief_import_ptr(h, n_in), n_in * rb), device="cuda")
-                       if n_in else torch.empty(0, dtype=torch.uint8, device="cuda"))
-                exchange_records(self.dist, self.group, plan, self.rank, src, rb, dst)
-                # phase 4: imported records fill the slots the local resample left dead
-                _check(ctx.h, L.fba_belief_import(h, n_in))
+                self._exchange(plan)
+            if trace:
+                trace[4].record(self._stream)
+                self.trace.append(trace)
         self.phase_ms = {"enqueue propose..resample + wait for totals": (t1 - t0) * 1e3,
                          "plan + exchange (enqueue)": (time.perf_counter() - t1) * 1e3}
         return tot.value

@@ -237,6 +237,9 @@ int fba_belief_shard_resample_async(fba_belief* b, const double* totals_device, 
 int fba_belief_shard_plan(fba_belief* b, const double* totals_host, int32_t n_ranks, int32_t rank, double u,
                           int64_t* send_plan, double* global_total);
 int fba_belief_reserve_export(fba_belief* b, int64_t records);
+/* phase 4 from an arbitrary device address (e.g. a segment of an all-gathered export window);
+ * successive calls fill successive dead slots. Asynchronous. */
+int fba_belief_import_from(fba_belief* b, const void* records_device, int64_t n_records);
 int64_t fba_belief_export_count(const fba_belief* b);
 /* device pointers of the export / import staging area: particle records of
  * fba_belief_record_bytes() each (count block, then state, structure id) */
