@@ -207,7 +207,7 @@ def main_ours(args):
     bytes_per_particle = 2 * (4 * C + 4 + 8)  # counts + state + weight, read + written
 
     if world > 1 or args.force_sharded:
-        b = fba.ShardedBAImportanceSampling(n_local)
+        b = fba.ShardedBAImportanceSampling(n_local, exchange=args.exchange)
         rng = b.rank_rng(args.seed)
     else:
         b = fba.BAImportanceSampling(n_local)
@@ -361,7 +361,8 @@ def main_ours(args):
                    "resampling": "systematic, in place (survivors keep their slot; duplicates fill dead slots)",
                    "algorithmic_bytes_per_particle_copy": bytes_per_particle,
                    "algorithmic_bytes_per_particle_propose": bytes_propose,
-                   "parallelism": "particles sharded, %d rank(s)" % world,
+                   "parallelism": "particles sharded, %d rank(s)%s" % (
+                       world, ", exchange=%s" % args.exchange if world > 1 else ""),
                    "last_step_phases_ms_rank0": phases,
                    "l2": "inputs (%.1f GB of counts per GPU) exceed the 126 MB L2; no flush needed"
                          % (n_local * C * 4 / 1e9),
@@ -406,6 +407,8 @@ def main():
     ap.add_argument("--ref-particles", type=int, default=4096)
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "allgather"],
+                    help="how sharded beliefs ship surplus particles between GPUs")
     ap.add_argument("--force-sharded", action="store_true", help="use the sharded code path on 1 GPU")
     ap.add_argument("--trace", action="store_true", help="per-phase device timing of the sharded update")
     ap.add_argument("--no-full-copy", action="store_true", help="skip the full-copy resampling leg")

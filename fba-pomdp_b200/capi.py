@@ -30,7 +30,8 @@ SYMBOLS = [
     "fba_belief_reject_sample", "fba_belief_reinvigorate", "fba_rollouts", "fba_belief_propose",
     "fba_belief_normalize", "fba_belief_resample_shard", "fba_belief_resample_stats",
     "fba_belief_shard_resample", "fba_belief_shard_resample_async", "fba_belief_shard_plan",
-    "fba_belief_reserve_export", "fba_belief_import_from", "fba_belief_export_count",
+    "fba_belief_ipc_handle", "fba_belief_ipc_open", "fba_belief_shard_resample_p2p", "fba_belief_import_p2p",
+    "fba_belief_dropped_records", "fba_belief_reserve_export", "fba_belief_import_from", "fba_belief_export_count",
     "fba_belief_export_ptr", "fba_belief_import_ptr", "fba_belief_record_bytes", "fba_belief_import",
     "fba_belief_counts_ptr", "fba_belief_state_ptr", "fba_belief_weight_ptr",
     "fba_belief_scalars_ptr",
@@ -108,6 +109,11 @@ def lib():
             "fba_belief_shard_resample": (C.c_int, [vp, vp, i32, i32, dbl, vp, vp, vp]),
             "fba_belief_shard_resample_async": (C.c_int, [vp, vp, i32, i32, dbl, vp]),
             "fba_belief_shard_plan": (C.c_int, [vp, vp, i32, i32, dbl, vp, vp]),
+            "fba_belief_ipc_handle": (C.c_int, [vp, i64, vp]),
+            "fba_belief_ipc_open": (C.c_int, [vp, vp, i32, i32]),
+            "fba_belief_shard_resample_p2p": (C.c_int, [vp, vp, dbl, vp]),
+            "fba_belief_import_p2p": (C.c_int, [vp]),
+            "fba_belief_dropped_records": (i64, [vp]),
             "fba_belief_reserve_export": (C.c_int, [vp, i64]),
             "fba_belief_import_from": (C.c_int, [vp, vp, i64]),
             "fba_model_create": (C.c_int, [vp, vp, i32, pp]),

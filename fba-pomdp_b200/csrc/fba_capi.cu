@@ -83,6 +83,12 @@ struct fba_belief
     long long* stats = nullptr; // [0] copies made by in-place resamples, [1] number of resamples,
                                 // [2] surplus records dropped because the export buffer was full
     long long src_cap = 0;
+    // peer-to-peer exchange
+    PeerTable peers{};
+    bool peers_open = false;
+    int p2p_ranks = 0, p2p_rank = 0;
+    long long* d_plan = nullptr;
+    std::vector<void*> opened; // cudaIpcOpenMemHandle'd pointers
     long long* d_quota = nullptr; // device-side offspring quota (fba_belief_shard_resample_async)
     int2* tile_pairs = nullptr;
     bool inplace_last = false; // the last shard resample ran in place (import goes to dead slots)
@@ -634,6 +640,8 @@ extern "C" void fba_belief_destroy(fba_belief* b)
     }
     cudaFree(b->w), cudaFree(b->aux), cudaFree(b->tile), cudaFree(b->scal), cudaFree(b->anc);
     cudaFree(b->att_src), cudaFree(b->att_state), cudaFree(b->att_accept), cudaFree(b->att_pos);
+    for (auto p : b->opened) cudaIpcCloseMemHandle(p);
+    cudaFree(b->d_plan);
     cudaFree(b->att_rec), cudaFree(b->d_total), cudaFree(b->xport), cudaFree(b->import_buf);
     cudaFree(b->src_of), cudaFree(b->d_quota), cudaFree(b->stats), cudaFree(b->noff), cudaFree(b->escan), cudaFree(b->dead), cudaFree(b->totals), cudaFree(b->tile_pairs);
     delete b;
@@ -968,7 +976,8 @@ static int ensure_export(fba_belief* b, long long records)
 }
 
 // n_out_dev != NULL: the quota is read from device memory (no host sync needed beforehand)
-static int resample_inplace(fba_belief* b, fba_rng* rng, long long n_out, const long long* n_out_dev = nullptr)
+static int resample_inplace(fba_belief* b, fba_rng* rng, long long n_out, const long long* n_out_dev = nullptr,
+                            bool p2p = false)
 {
     fba_ctx* ctx = b->ctx;
     int rc;
@@ -986,7 +995,8 @@ static int resample_inplace(fba_belief* b, fba_rng* rng, long long n_out, const 
            b->src_cap);
     LAUNCH(ctx, k_copy_inplace, stream_grid(ctx, b->N), kThreads, b->counts[b->cur], b->stride,
            b->state[b->cur], b->sid[b->cur], b->m->d_sizes, b->escan, b->src_of, b->N, b->dead, b->totals,
-           b->xport, rb, b->xport_cap, b->stats, b->src_cap);
+           b->xport, rb, b->xport_cap, b->stats, b->src_cap, p2p ? b->d_plan : (const long long*)nullptr,
+           b->p2p_ranks, b->p2p_rank, b->peers);
     LAUNCH(ctx, k_fill, blocks_for(b->N), kThreads, b->w, b->N, 1.0 / (double)b->N);
     b->total_weight = 1.0;
     b->suffix_valid = b->cdf_valid = false;
@@ -1588,9 +1598,99 @@ extern "C" int fba_belief_import_from(fba_belief* b, const void* records_device,
     CU(ctx, cudaSetDevice(ctx->device));
     LAUNCH(ctx, k_import_inplace, stream_grid(ctx, n_records), kThreads, b->counts[b->cur], b->stride,
            b->state[b->cur], b->sid[b->cur], b->dead, b->totals, b->imported, (long long)n_records,
-           (const char*)records_device, fba_belief_record_bytes(b));
+           (const char*)records_device, fba_belief_record_bytes(b), (const long long*)nullptr, 0, 0);
     b->imported += n_records;
     b->local_kept += n_records;
+    return FBA_OK;
+}
+
+// ---- peer-to-peer exchange over NVLink: surplus records are stored by k_copy_inplace directly
+//      into the destination GPU's import buffer (CUDA IPC mapping); no host-visible plan ----
+
+// Allocates this rank's import buffer (cap_records) and returns its 64-byte CUDA IPC handle.
+extern "C" int fba_belief_ipc_handle(fba_belief* b, int64_t cap_records, void* handle64)
+{
+    if (!b || !handle64 || cap_records < 1) return FBA_ERR_INVALID;
+    fba_ctx* ctx = b->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (b->import_cap < cap_records)
+    {
+        cudaFree(b->import_buf);
+        b->import_buf = nullptr;
+        b->import_cap = 0;
+        CU(ctx, cudaMalloc(&b->import_buf, (size_t)cap_records * fba_belief_record_bytes(b)));
+        b->import_cap = cap_records;
+    }
+    cudaIpcMemHandle_t hnd;
+    CU(ctx, cudaIpcGetMemHandle(&hnd, b->import_buf));
+    memcpy(handle64, &hnd, 64);
+    return FBA_OK;
+}
+
+// handles: n_ranks x 64 bytes (all-gathered); maps every peer's import buffer into this process
+extern "C" int fba_belief_ipc_open(fba_belief* b, const void* handles, int32_t n_ranks, int32_t rank)
+{
+    if (!b || !handles) return FBA_ERR_INVALID;
+    fba_ctx* ctx = b->ctx;
+    REQUIRE(ctx, n_ranks >= 1 && n_ranks <= kMaxRanks && rank >= 0 && rank < n_ranks, "ipc_open: bad rank");
+    REQUIRE(ctx, b->import_buf, "ipc_open: call fba_belief_ipc_handle first");
+    CU(ctx, cudaSetDevice(ctx->device));
+    for (int g = 0; g < n_ranks; ++g)
+    {
+        if (g == rank)
+        {
+            b->peers.import_buf[g] = b->import_buf;
+            continue;
+        }
+        cudaIpcMemHandle_t hnd;
+        memcpy(&hnd, (const char*)handles + (size_t)g * 64, 64);
+        void* p = nullptr;
+        CU(ctx, cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess));
+        b->opened.push_back(p);
+        b->peers.import_buf[g] = (char*)p;
+    }
+    b->peers.cap = b->import_cap;
+    if (!b->d_plan) CU(ctx, cudaMalloc(&b->d_plan, (size_t)kMaxRanks * kMaxRanks * sizeof(long long)));
+    b->p2p_ranks  = n_ranks;
+    b->p2p_rank   = rank;
+    b->peers_open = true;
+    return FBA_OK;
+}
+
+// Phases 2+3 with the plan on device and the surplus stored into peer memory. Asynchronous, and the
+// host never needs the totals. Follow with a cross-rank barrier on the same stream (any small
+// collective), then fba_belief_import_p2p.
+extern "C" int fba_belief_shard_resample_p2p(fba_belief* b, const double* totals_device, double u, fba_rng* rng)
+{
+    if (!b || !totals_device || !rng) return FBA_ERR_INVALID;
+    fba_ctx* ctx = b->ctx;
+    REQUIRE(ctx, b->peers_open, "shard_resample_p2p: call fba_belief_ipc_open first");
+    REQUIRE(ctx, rng->mode == FBA_RNG_PHILOX, "sharded beliefs run in PHILOX mode");
+    REQUIRE(ctx, ctx->inplace_resample, "shard_resample_p2p needs the in-place resampler");
+    REQUIRE(ctx, u >= 0.0 && u < 1.0, "shard_resample_p2p: u must be in [0,1)");
+    CU(ctx, cudaSetDevice(ctx->device));
+    int const n_tiles = (int)((b->N + kTile - 1) / kTile);
+    LAUNCH(ctx, k_shard_plan, 1, 1, totals_device, b->p2p_ranks, b->p2p_rank, u, b->N, b->scal + 2, b->d_quota,
+           b->d_plan);
+    LAUNCH(ctx, k_scale_and_scan, n_tiles, kThreads, b->w, b->N, b->tile, (const double*)(b->scal + 2), 1.0,
+           b->aux);
+    b->cdf_valid    = true;
+    b->suffix_valid = false;
+    return resample_inplace(b, rng, 0, b->d_quota, true);
+}
+
+extern "C" int fba_belief_import_p2p(fba_belief* b)
+{
+    if (!b) return FBA_ERR_INVALID;
+    fba_ctx* ctx = b->ctx;
+    REQUIRE(ctx, b->peers_open && b->inplace_last, "import_p2p: needs fba_belief_shard_resample_p2p first");
+    CU(ctx, cudaSetDevice(ctx->device));
+    // the count is read from the device plan; the grid covers the worst case with a grid-stride loop
+    LAUNCH(ctx, k_import_inplace, stream_grid(ctx, std::min<long long>(b->import_cap, 65536)), kThreads,
+           b->counts[b->cur], b->stride, b->state[b->cur], b->sid[b->cur], b->dead, b->totals, 0ll,
+           b->import_cap, b->import_buf, fba_belief_record_bytes(b), (const long long*)b->d_plan, b->p2p_ranks,
+           b->p2p_rank);
     return FBA_OK;
 }
 
@@ -1711,6 +1811,16 @@ extern "C" int fba_belief_resample_shard(fba_belief* b, int64_t n_offspring, fba
 }
 
 // copies made / resamples run by the in-place resampler since the belief was created
+extern "C" int64_t fba_belief_dropped_records(fba_belief* b)
+{
+    if (!b) return -1;
+    long long h = 0;
+    cudaSetDevice(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->stream);
+    cudaMemcpy(&h, b->stats + 2, sizeof(h), cudaMemcpyDeviceToHost);
+    return h;
+}
+
 extern "C" int fba_belief_resample_stats(fba_belief* b, int64_t* copies, int64_t* resamples)
 {
     if (!b) return FBA_ERR_INVALID;
@@ -1762,7 +1872,7 @@ extern "C" int fba_belief_import(fba_belief* b, int64_t n_records)
     {
         LAUNCH(ctx, k_import_inplace, stream_grid(ctx, n_records), kThreads, b->counts[b->cur], b->stride,
                b->state[b->cur], b->sid[b->cur], b->dead, b->totals, 0ll, (long long)n_records, b->import_buf,
-               fba_belief_record_bytes(b));
+               fba_belief_record_bytes(b), (const long long*)nullptr, 0, 0);
         b->local_kept += n_records;
         return FBA_OK; // asynchronous
     }

@@ -455,6 +455,73 @@ __global__ void k_shard_quota(const double* __restrict__ totals, int n_ranks, in
     out_quota[0] = (W > 0.0) ? quota : 0;
 }
 
+// multi-GPU, peer-to-peer exchange: the whole exchange plan on device (n_ranks <= 16), identical on
+// every rank because it is a pure function of the all-gathered totals and u.
+//   plan[g*G + h] = records rank g ships to rank h (greedy matching in rank order)
+// out_quota[0] = this rank's quota, out_total[0] = W.
+constexpr int kMaxRanks = 16;
+__global__ void k_shard_plan(const double* __restrict__ totals, int n_ranks, int rank, double u,
+                             long long n_local, double* __restrict__ out_total,
+                             long long* __restrict__ out_quota, long long* __restrict__ plan)
+{
+    double W = 0.0;
+    for (int g = 0; g < n_ranks; ++g) W += totals[g];
+    long long const n_total = n_local * n_ranks;
+    long long quota[kMaxRanks], surplus[kMaxRanks], deficit[kMaxRanks];
+    long long prev = 0;
+    double acc     = 0.0;
+    for (int g = 0; g < n_ranks; ++g)
+    {
+        acc += totals[g];
+        long long edge = (g == n_ranks - 1) ? n_total : (long long)floor(acc / W * (double)n_total - u + 1.0);
+        edge     = min(max(edge, prev), n_total);
+        quota[g] = (W > 0.0) ? edge - prev : n_local;
+        prev     = edge;
+        surplus[g] = max(0ll, quota[g] - n_local);
+        deficit[g] = max(0ll, n_local - quota[g]);
+    }
+    for (int k = 0; k < n_ranks * n_ranks; ++k) plan[k] = 0;
+    int h = 0;
+    for (int g = 0; g < n_ranks; ++g)
+        while (surplus[g] > 0)
+        {
+            while (h < n_ranks && deficit[h] == 0) ++h;
+            if (h >= n_ranks) break;
+            long long const k = min(surplus[g], deficit[h]);
+            plan[g * n_ranks + h] += k;
+            surplus[g] -= k, deficit[h] -= k;
+        }
+    out_total[0] = W;
+    out_quota[0] = quota[rank];
+}
+
+// where surplus record r of rank `rank` goes: destination rank and record offset inside that rank's
+// import buffer (incoming records are ordered by sender rank)
+__device__ __forceinline__ void p2p_destination(const long long* __restrict__ plan, int n_ranks, int rank,
+                                                long long r, int& dst_rank, long long& dst_off)
+{
+    long long before = 0;
+    for (int h = 0; h < n_ranks; ++h)
+    {
+        long long const n = plan[rank * n_ranks + h];
+        if (r < before + n)
+        {
+            long long off = r - before;
+            for (int g = 0; g < rank; ++g) off += plan[g * n_ranks + h];
+            dst_rank = h, dst_off = off;
+            return;
+        }
+        before += n;
+    }
+    dst_rank = -1, dst_off = 0;
+}
+
+struct PeerTable
+{
+    char* import_buf[kMaxRanks]; // peer-mapped import buffers (own entry = local)
+    long long cap;               // records each holds
+};
+
 // per tile: offspring counts -> (dead, extra) tile sums
 __global__ void __launch_bounds__(kThreads)
     k_offspring(const double* __restrict__ cdf, long long N, long long n_out,
@@ -588,8 +655,16 @@ __global__ void __launch_bounds__(kThreads)
 __global__ void __launch_bounds__(kThreads)
     k_import_inplace(float* __restrict__ dst, long long stride, int* __restrict__ state, int* __restrict__ sid,
                      const int* __restrict__ dead_slot, const int* __restrict__ totals, long long slot_offset,
-                     long long n, const char* __restrict__ in, long long rec_bytes)
+                     long long n, const char* __restrict__ in, long long rec_bytes,
+                     const long long* __restrict__ plan, int n_ranks, int rank)
 {
+    if (plan)
+    { // peer-to-peer: the number of incoming records is this rank's column of the device plan
+        long long const cap = n; // by-value n carries the import buffer capacity in this mode
+        n = 0;
+        for (int g = 0; g < n_ranks; ++g) n += plan[g * n_ranks + rank];
+        n = min(n, cap);
+    }
     int const lane        = threadIdx.x & 31;
     long long const warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     long long const nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -615,12 +690,13 @@ __global__ void __launch_bounds__(kThreads)
     k_copy_inplace(float* counts, long long stride, int* state, int* sid, const int* __restrict__ struct_size,
                    const int* __restrict__ extra_scan, const int* __restrict__ src_of, long long N,
                    const int* __restrict__ dead_slot, const int* __restrict__ totals, char* __restrict__ xport,
-                   long long rec_bytes, long long xport_cap, long long* __restrict__ stats, long long src_cap)
+                   long long rec_bytes, long long xport_cap, long long* __restrict__ stats, long long src_cap,
+                   const long long* __restrict__ plan, int n_ranks, int rank, PeerTable peers)
 {
     long long const n_dead = totals[0];
     long long const n_fill = min(n_dead, (long long)totals[1]); // the rest (if any) is this shard's surplus
     long long n_copies     = totals[1];
-    if (n_copies - n_fill > xport_cap)
+    if (!plan && n_copies - n_fill > xport_cap)
     { // more surplus than the export buffer holds: drop the excess and report it
         if (blockIdx.x == 0 && threadIdx.x == 0) stats[2] = n_copies - n_fill - xport_cap;
         n_copies = n_fill + xport_cap;
@@ -656,6 +732,18 @@ __global__ void __launch_bounds__(kThreads)
         } else
         {
             char* rec = xport + (k - n_fill) * rec_bytes;
+            if (plan)
+            { // peer-to-peer: store the record straight into the destination GPU's import buffer
+                int dst_rank;
+                long long dst_off;
+                p2p_destination(plan, n_ranks, rank, k - n_fill, dst_rank, dst_off);
+                if (dst_rank < 0 || dst_off >= peers.cap)
+                {
+                    if (lane == 0) atomicAdd((unsigned long long*)&stats[2], 1ull);
+                    continue;
+                }
+                rec = peers.import_buf[dst_rank] + dst_off * rec_bytes;
+            }
             warp_copy_block(counts + i * stride, reinterpret_cast<float*>(rec), (int)(stride >> 2), lane);
             if (lane == 0)
             {

@@ -84,8 +84,15 @@ class ShardedBAImportanceSampling(BAImportanceSampling):
     single host synchronisation — the read-back of the G shard totals that the exchange plan
     (host-known split sizes for the all-to-all) needs."""
 
-    def __init__(self, n_local, group=None):
+    def __init__(self, n_local, group=None, exchange="p2p"):
+        """exchange: "p2p" — surplus records are stored by the resampling kernel directly into the
+        destination GPU's import buffer over NVLink (CUDA IPC), plan on device, no host sync at all;
+        "allgather" — fixed-size windows of the export buffers through one NCCL all-gather (for
+        setups where peer mapping is unavailable)."""
         super().__init__(n_local)
+        if exchange not in ("p2p", "allgather"):
+            raise capi.FbaError(capi.ERR_INVALID, "exchange must be 'p2p' or 'allgather'")
+        self.exchange = exchange
         import torch.distributed as dist
         self.dist, self.group = dist, group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -136,6 +143,26 @@ class ShardedBAImportanceSampling(BAImportanceSampling):
             self._window_cap *= 2
         _check(self.ctx.h, L.fba_belief_reserve_export(h, cap + self._window_cap))
         self._gather_buf = torch.empty(self.world * self._window_cap * rb, dtype=torch.uint8, device="cuda")
+        self._barrier = torch.zeros(1, dtype=torch.float32, device="cuda")
+        if self.exchange == "p2p":
+            # publish / map the import buffers (CUDA IPC): handles travel through one all-gather
+            mine = np.zeros(64, np.uint8)
+            _check(self.ctx.h, L.fba_belief_ipc_handle(h, cap, mine.ctypes.data_as(C.c_void_p)))
+            if self.world > 1:
+                all_h = torch.empty(self.world * 64, dtype=torch.uint8, device="cuda")
+                self.dist.all_gather_into_tensor(all_h, torch.from_numpy(mine).cuda(), group=self.group)
+                handles = all_h.cpu().numpy()
+            else:
+                handles = mine
+            handles = np.ascontiguousarray(handles)
+            _check(self.ctx.h, L.fba_belief_ipc_open(h, handles.ctypes.data_as(C.c_void_p), self.world, self.rank))
+            if self.world > 1:
+                self.dist.all_reduce(self._barrier, group=self.group)
+                self.dist.all_gather_into_tensor(self._totals, torch.zeros(1, dtype=torch.float64, device="cuda"),
+                                                 group=self.group)
+            torch.cuda.synchronize()
+            self._bufs = True
+            return
         if self.world > 1:
             w = 64
             while w <= self._window_cap:  # touch every window size once (NCCL algorithm selection)
@@ -185,7 +212,7 @@ class ShardedBAImportanceSampling(BAImportanceSampling):
         import torch
         if self._bufs:
             torch.cuda.synchronize()
-            self._local = self._totals = self._totals_host = self._stream = self._event = self._gather_buf = None
+            self._local = self._totals = self._totals_host = self._stream = self._event = self._gather_buf = self._barrier = None
             self._bufs = None
         super().free()
 
@@ -215,6 +242,22 @@ class ShardedBAImportanceSampling(BAImportanceSampling):
                 self.dist.all_gather_into_tensor(self._totals, self._local, group=self.group)
             else:
                 self._totals.copy_(self._local)
+            if self.exchange == "p2p":
+                # plan on device, surplus stored into peer memory by the copy kernel; a tiny
+                # all-reduce is the cross-rank barrier between those stores and the imports
+                if trace:
+                    trace[2].record(self._stream)
+                _check(ctx.h, L.fba_belief_shard_resample_p2p(h, self._totals.data_ptr(), u, C.byref(rng)))
+                if trace:
+                    trace[3].record(self._stream)
+                if self.world > 1:
+                    self.dist.all_reduce(self._barrier, group=self.group)
+                _check(ctx.h, L.fba_belief_import_p2p(h))
+                if trace:
+                    trace[4].record(self._stream)
+                    self.trace.append(trace)
+                self.phase_ms = {"enqueue whole update (no host sync)": (time.perf_counter() - t0) * 1e3}
+                return None
             self._totals_host.copy_(self._totals, non_blocking=True)
             self._event.record(self._stream)
             if trace:

@@ -236,6 +236,19 @@ int fba_belief_shard_resample_async(fba_belief* b, const double* totals_device, 
                                     int32_t rank, double u, fba_rng* rng);
 int fba_belief_shard_plan(fba_belief* b, const double* totals_host, int32_t n_ranks, int32_t rank, double u,
                           int64_t* send_plan, double* global_total);
+/* Peer-to-peer exchange over NVLink (one process per GPU, one box): each rank publishes the CUDA IPC
+ * handle of its import buffer, maps its peers', and the resampling kernel stores surplus records
+ * straight into the destination GPU's import buffer. The plan lives on device, so the host never
+ * waits for the GPU during an update. Order per update, all on the context's stream:
+ *   fba_belief_propose(.., NULL) -> all-gather of the shard totals (device) ->
+ *   fba_belief_shard_resample_p2p -> any small collective as a cross-rank barrier ->
+ *   fba_belief_import_p2p. */
+int fba_belief_ipc_handle(fba_belief* b, int64_t cap_records, void* handle64);
+int fba_belief_ipc_open(fba_belief* b, const void* handles, int32_t n_ranks, int32_t rank);
+int fba_belief_shard_resample_p2p(fba_belief* b, const double* totals_device, double u, fba_rng* rng);
+int fba_belief_import_p2p(fba_belief* b);
+/* surplus records that did not fit an export / import buffer since creation (0 in a healthy run) */
+int64_t fba_belief_dropped_records(fba_belief* b);
 int fba_belief_reserve_export(fba_belief* b, int64_t records);
 /* phase 4 from an arbitrary device address (e.g. a segment of an all-gathered export window);
  * successive calls fill successive dead slots. Asynchronous. */
