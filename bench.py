@@ -157,6 +157,61 @@ def run_reference_cpu(n_particles, steps, warmup, replicas):
     return replicas * n_particles * steps / slowest, slowest / steps, res[0][0]
 
 
+def rollouts_leg(ctx, fba, args, torch):
+    """BASELINE.json configs[2]: gridworld BA-POMDP, 10^6 particles, 4096 batched random-policy
+    rollouts per planning step (RBAPOUCT::rollout x 4096 in one launch), plus the saturated rate at
+    2^20 rollouts per launch. Host arrays in, host returns out (that is the call a planner makes)."""
+    import golden_util as G
+    g = G.load("gridworld3")
+    sim = fba.BAPOMDP(ctx, g.desc, g.t_par, g.o_par)
+    n = args.rollout_particles
+    b = fba.BAImportanceSampling(n)
+    rng = fba.Rng.philox(args.seed + 1)
+    b.initiate_sampled(sim, [0], g["is/init_counts"][0][None, :], None, rng)
+    script = [(int(a), int(o)) for a, o, f in zip(g.a, g.o, g.flags) if not (f & 1)]
+    for t in range(2):  # a learned (non-prior) belief
+        b.updateEstimation(script[t][0], script[t][1], rng, want_likelihood=False)
+    rs = np.random.RandomState(5)
+    out = {}
+    for tag, batch, reps in (("batch_4096", 4096, 50), ("batch_1048576", 1 << 20, 5)):
+        pid = rs.randint(0, n, batch).astype(np.int64)
+        start = rs.randint(0, sim.S, batch).astype(np.int32)
+        depth = np.full(batch, g.horizon, np.int32)
+        for _ in range(3):
+            ret = fba.rollouts(b, pid, start, depth, g.discount, rng)
+        ctx.synchronize()
+        ctx.profile_begin()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            ret = fba.rollouts(b, pid, start, depth, g.discount, rng)
+        wall = time.perf_counter() - t0
+        ctx.profile_end()
+        kms, kn = ctx.kernel_time("k_rollouts")
+        out[tag] = {"rollouts_per_s_e2e": batch * reps / wall, "rollouts_per_s_kernel": batch / (kms / kn * 1e-3),
+                    "ms_per_batch_e2e": wall / reps * 1e3, "ms_per_batch_kernel": kms / kn,
+                    "mean_return": float(ret.mean())}
+    out.update(workload="gridworld --size 3 tabular BA-POMDP (S=27, A=4, O=27, 5832 count cells/particle), "
+                        "%d particles, depth %d, discount %.2f" % (n, g.horizon, g.discount),
+               unit="rollouts/s")
+    # the reference's RBAPOUCT::rollout on one host core, bounded sample
+    try:
+        import pyref
+        r = pyref.Ref("gridworld", size=3, horizon=g.horizon, discount=g.discount, seed="42")
+        r.belief_init(pyref.F_IS, 256)
+        m = 4096
+        t0 = time.perf_counter()
+        for i in range(m):
+            r.rollout(pyref.F_IS, int(pid[i] % 256), int(start[i]), g.horizon)
+        out["cpu_baseline"] = {"value": m / (time.perf_counter() - t0), "unit": "rollouts/s", "cores": 1,
+                               "kind": "reference", "sample": "4096 x RBAPOUCT::rollout, depth 20, 1 thread"}
+        r.close()
+    except Exception as e:  # noqa: BLE001
+        out["cpu_baseline"] = {"unavailable": str(e)[:200]}
+    b.free()
+    sim.close()
+    return out
+
+
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -377,6 +432,11 @@ def main_ours(args):
         "full_copy": full,
     }
 
+    b.free()
+    sim.close()
+    if world == 1 and not args.no_rollouts:
+        line["rollouts"] = rollouts_leg(ctx, fba, args, torch)
+
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n = args.ref_particles
         v, s_per_step, kind = run_reference_cpu(n, 6, 1, 1)
@@ -389,8 +449,6 @@ def main_ours(args):
         line["cpu_baseline"] = None
     if rank == 0:
         print(json.dumps(line))
-    b.free()
-    sim.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -407,6 +465,8 @@ def main():
     ap.add_argument("--ref-particles", type=int, default=4096)
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-rollouts", action="store_true", help="skip the POMCP rollouts leg (config 3)")
+    ap.add_argument("--rollout-particles", type=int, default=1_000_000)
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "allgather"],
                     help="how sharded beliefs ship surplus particles between GPUs")
     ap.add_argument("--force-sharded", action="store_true", help="use the sharded code path on 1 GPU")

@@ -96,6 +96,11 @@ struct fba_belief
     long long wave_cap = 0;
     int *att_src = nullptr, *att_state = nullptr, *att_accept = nullptr, *att_pos = nullptr,
         *att_rec = nullptr, *d_total = nullptr;
+    // rollout request / result staging (grow-only)
+    long long roll_cap = 0;
+    long long* roll_p  = nullptr;
+    int *roll_s = nullptr, *roll_d = nullptr;
+    double* roll_r = nullptr;
     // multi-GPU staging
     char* xport = nullptr;
     long long xport_cap = 0, xport_count = 0;
@@ -640,6 +645,7 @@ extern "C" void fba_belief_destroy(fba_belief* b)
     }
     cudaFree(b->w), cudaFree(b->aux), cudaFree(b->tile), cudaFree(b->scal), cudaFree(b->anc);
     cudaFree(b->att_src), cudaFree(b->att_state), cudaFree(b->att_accept), cudaFree(b->att_pos);
+    cudaFree(b->roll_p), cudaFree(b->roll_s), cudaFree(b->roll_d), cudaFree(b->roll_r);
     for (auto p : b->opened) cudaIpcCloseMemHandle(p);
     cudaFree(b->d_plan);
     cudaFree(b->att_rec), cudaFree(b->d_total), cudaFree(b->xport), cudaFree(b->import_buf);
@@ -1402,13 +1408,21 @@ extern "C" int fba_rollouts(fba_belief* b, int64_t n, const int64_t* particle, c
         REQUIRE(ctx, depth[i] >= 0, "rollouts: negative depth");
     }
     CU(ctx, cudaSetDevice(ctx->device));
-    long long* d_p = nullptr;
-    int *d_s = nullptr, *d_d = nullptr;
-    double* d_r = nullptr;
-    CU(ctx, cudaMalloc(&d_p, n * sizeof(long long)));
-    CU(ctx, cudaMalloc(&d_s, n * sizeof(int)));
-    CU(ctx, cudaMalloc(&d_d, n * sizeof(int)));
-    CU(ctx, cudaMalloc(&d_r, n * sizeof(double)));
+    if (n > b->roll_cap)
+    {
+        cudaFree(b->roll_p), cudaFree(b->roll_s), cudaFree(b->roll_d), cudaFree(b->roll_r);
+        b->roll_p = nullptr, b->roll_s = b->roll_d = nullptr, b->roll_r = nullptr;
+        b->roll_cap = 0;
+        long long const cap = n + n / 2 + 1024;
+        CU(ctx, cudaMalloc(&b->roll_p, cap * sizeof(long long)));
+        CU(ctx, cudaMalloc(&b->roll_s, cap * sizeof(int)));
+        CU(ctx, cudaMalloc(&b->roll_d, cap * sizeof(int)));
+        CU(ctx, cudaMalloc(&b->roll_r, cap * sizeof(double)));
+        b->roll_cap = cap;
+    }
+    long long* d_p = b->roll_p;
+    int *d_s = b->roll_s, *d_d = b->roll_d;
+    double* d_r = b->roll_r;
     CU(ctx, cudaMemcpyAsync(d_p, particle, n * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
     CU(ctx, cudaMemcpyAsync(d_s, start_state, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     CU(ctx, cudaMemcpyAsync(d_d, depth, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
@@ -1428,7 +1442,6 @@ extern "C" int fba_rollouts(fba_belief* b, int64_t n, const int64_t* particle, c
                n, d_p, d_s, d_d, discount, philox_args(rng), d_r, ctx->d_flag);
     CU(ctx, cudaMemcpyAsync(returns, d_r, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_p), cudaFree(d_s), cudaFree(d_d), cudaFree(d_r);
     if (rng->mode == FBA_RNG_REPLAY)
     {
         if ((rc = check_flag(ctx))) return rc;
