@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfba_b200.so")
+LIB_PATH = os.environ.get("FBA_B200_LIB") or os.path.join(HERE, "libfba_b200.so")
 
 MAX_FEATURES = 16
 

@@ -186,6 +186,8 @@ extern "C" int fba_ctx_create(int device, fba_ctx** out)
     ctx->device = device;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (const char* g = getenv("FBA_B200_L2_FETCH")) // experiment knob: 32 / 64 / 128 bytes
+        if (e == cudaSuccess) e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_flag, sizeof(int));
     if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_flag, sizeof(int));
