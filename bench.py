@@ -338,14 +338,24 @@ def main_ours(args):
                            "algorithmic_GBps": None if alg is None else round(alg / (per_launch * 1e-3) / 1e9, 1)}
         return ms, table, ctx.launches - launches0, clocks, copies
 
+    try:
+        ncu_ratio = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except (OSError, ValueError):
+        ncu_ratio = {}
+
     def roofline_of(table, name_prefix, note):
         name = next((k for k in table if k.startswith(name_prefix)), None)
         if name is None:
             return None
         row = table[name]
         ach = row["algorithmic_GBps"] or 0.0
+        alg_bytes = ach * 1e9 * row["ms_per_launch"] * 1e-3
+        ratio = ncu_ratio.get(name_prefix, {}).get("traffic_over_algorithmic")
         return {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": row["ms_per_launch"],
+                "frac": ach / peak, "algorithmic_bytes_per_launch": alg_bytes,
+                "traffic": None if ratio is None else alg_bytes * ratio,
+                "traffic_source": ncu_ratio.get(name_prefix, {}).get("source"),
+                "peak_source": peak_src, "kernel_ms": row["ms_per_launch"],
                 "share_of_step": row["share_of_step"], "note": note}
 
     # ---- the default path: in-place systematic resampling (survivors are not moved) ----
@@ -364,7 +374,7 @@ def main_ours(args):
                            "bytes = %d B x copied particles (%.1f%% of the particles per update; survivors "
                            "stay in place)" % (bytes_per_particle, 100 * copied_frac))
     else:
-        roof = roofline_of(table, dominant,
+        roof = roofline_of(table, "k_propose",
                            "k_propose touches %d algorithmic bytes per particle in %d scattered rows; it is "
                            "bound by 32-byte-sector random access, not by streaming bandwidth"
                            % (bytes_propose, FS + FO))
