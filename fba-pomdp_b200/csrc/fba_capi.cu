@@ -24,6 +24,7 @@ struct fba_ctx
     int64_t launches     = 0;
     std::string err;
     // optional per-kernel CUDA-event timing (fba_ctx_profile_*)
+    int rollout_coop = -1; // -1 auto (by batch size and row length), 0 thread per rollout, 1 warp per rollout
     bool inplace_resample = true; // PHILOX mode: survivors keep their slot (fba_ctx_set_option)
     bool profiling       = false;
     struct Timed
@@ -145,6 +146,7 @@ static inline int stream_grid(const fba_ctx* ctx, long long n_particles)
 
 static void profile_mark(fba_ctx* ctx, const char* name, bool begin)
 {
+    if (*name == '(') ++name; // template kernels with a comma are passed parenthesised
     if (begin)
     {
         fba_ctx::Timed t{name, nullptr, nullptr};
@@ -240,6 +242,11 @@ extern "C" int fba_ctx_set_option(fba_ctx* ctx, const char* name, int64_t value)
     if (!strcmp(name, "inplace_resample"))
     {
         ctx->inplace_resample = value != 0;
+        return FBA_OK;
+    }
+    if (!strcmp(name, "rollout_coop"))
+    {
+        ctx->rollout_coop = (int)value;
         return FBA_OK;
     }
     ctx->err = std::string("unknown option ") + name;
@@ -796,6 +803,12 @@ extern "C" int fba_belief_upload(fba_belief* b, int64_t first, int64_t count, co
     {
         CU(ctx, cudaMemcpyAsync(b->w + first, w, count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         b->suffix_valid = b->cdf_valid = false;
+        if (first == 0 && count == b->N)
+        { // WeightedFilter::_total_weight = the sequential sum of the weights as added
+            volatile double acc = 0.0;
+            for (int64_t i = 0; i < count; ++i) acc = acc + w[i];
+            b->total_weight = acc;
+        }
     }
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return FBA_OK;
@@ -1429,6 +1442,12 @@ extern "C" int fba_rollouts(fba_belief* b, int64_t n, const int64_t* particle, c
     CU(ctx, cudaMemcpyAsync(d_s, start_state, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     CU(ctx, cudaMemcpyAsync(d_d, depth, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     int rc = FBA_OK;
+    // warp-per-rollout pays when rows are long and the batch cannot fill the GPU with threads
+    int max_range = 1;
+    for (int f = 0; f < D.FS; ++f) max_range = std::max(max_range, D.feat_s[f]);
+    for (int f = 0; f < D.FO; ++f) max_range = std::max(max_range, D.feat_o[f]);
+    bool const coop = ctx->rollout_coop >= 0 ? ctx->rollout_coop != 0
+                                             : (max_range >= 8 && n <= (long long)ctx->sm_count * 512);
     if (rng->mode == FBA_RNG_REPLAY)
     {
         REQUIRE(ctx, word_offset, "rollouts: REPLAY mode needs word_offset");
@@ -1437,11 +1456,18 @@ extern "C" int fba_rollouts(fba_belief* b, int64_t n, const int64_t* particle, c
         if ((rc = stage_words(ctx, rng, std::max(0ll, avail)))) return rc;
         if ((rc = stage_offsets(ctx, off))) return rc;
         if ((rc = clear_flag(ctx))) return rc;
-        LAUNCH(ctx, k_rollouts<true>, blocks_for(n), kThreads, D, b->counts[b->cur], b->stride, b->sid[b->cur],
-               n, d_p, d_s, d_d, discount, replay_args(ctx, avail, 0, true), d_r, ctx->d_flag);
-    } else
-        LAUNCH(ctx, k_rollouts<false>, blocks_for(n), kThreads, D, b->counts[b->cur], b->stride, b->sid[b->cur],
-               n, d_p, d_s, d_d, discount, philox_args(rng), d_r, ctx->d_flag);
+        if (coop)
+            LAUNCH(ctx, (k_rollouts<true, true>), blocks_for(n * 32), kThreads, D, b->counts[b->cur], b->stride,
+                   b->sid[b->cur], n, d_p, d_s, d_d, discount, replay_args(ctx, avail, 0, true), d_r, ctx->d_flag);
+        else
+            LAUNCH(ctx, (k_rollouts<true, false>), blocks_for(n), kThreads, D, b->counts[b->cur], b->stride,
+                   b->sid[b->cur], n, d_p, d_s, d_d, discount, replay_args(ctx, avail, 0, true), d_r, ctx->d_flag);
+    } else if (coop)
+        LAUNCH(ctx, (k_rollouts<false, true>), blocks_for(n * 32), kThreads, D, b->counts[b->cur], b->stride,
+               b->sid[b->cur], n, d_p, d_s, d_d, discount, philox_args(rng), d_r, ctx->d_flag);
+    else
+        LAUNCH(ctx, (k_rollouts<false, false>), blocks_for(n), kThreads, D, b->counts[b->cur], b->stride,
+               b->sid[b->cur], n, d_p, d_s, d_d, discount, philox_args(rng), d_r, ctx->d_flag);
     CU(ctx, cudaMemcpyAsync(returns, d_r, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     if (rng->mode == FBA_RNG_REPLAY)

@@ -194,6 +194,52 @@ __device__ __forceinline__ int sample_expected_mult(const float* row, int n, dou
     return n - 1;
 }
 
+// The same draw with the row loaded cooperatively by a warp: lane l holds row[base + l] of each
+// 32-element chunk (one coalesced request instead of n dependent ones); every lane then replays the
+// reference's SEQUENTIAL sums through shuffles, so all lanes return the same, bit-identical index.
+// Must be called by all 32 lanes with identical arguments.
+__device__ __forceinline__ int sample_expected_mult_warp(const float* row, int n, double u)
+{
+    int const lane = threadIdx.x & 31;
+    double total   = 0.0;
+    for (int base = 0; base < n; base += 32)
+    {
+        float const v = (base + lane < n) ? row[base + lane] : 0.0f;
+        int const m   = min(32, n - base);
+        for (int k = 0; k < m; ++k)
+        {
+            double const x = (double)__shfl_sync(0xffffffffu, v, k);
+            total          = (base + k == 0) ? x : __dadd_rn(total, x);
+        }
+    }
+    double const p = __dmul_rn(u, total);
+    float sum      = 0.0f;
+    int result     = n - 1;
+    bool found     = false;
+    for (int base = 0; base < n && !found; base += 32)
+    {
+        float const v = (base + lane < n) ? row[base + lane] : 0.0f; // second pass hits L1
+        int const m   = min(32, n - base);
+        for (int k = 0; k < m; ++k)
+        {
+            float const x = __shfl_sync(0xffffffffu, v, k);
+            int const i   = base + k;
+            if (i == 0)
+            {
+                sum = x;
+                continue;
+            }
+            if (!found && p < (double)sum)
+            {
+                result = i - 1;
+                found  = true;
+            }
+            sum = __fadd_rn(sum, x);
+        }
+    }
+    return result;
+}
+
 // expectedMult(dir, n)[k] (random.cpp:257-279): FLOAT sum and FLOAT divide
 __device__ __forceinline__ float expected_mult_at(const float* row, int n, int k)
 {
@@ -364,7 +410,9 @@ enum StepMode {
 
 // nodes: this particle's structure, action a: J entries. counts: the particle's block.
 // Returns s'; o_out = simulated observation. x_new returns the new state's features.
-template<int MODE, class R>
+// COOP: the 32 lanes of a warp run ONE step together (identical arguments and random source in
+// every lane) and load each row cooperatively — for latency-bound small batches of rollouts.
+template<int MODE, class R, bool COOP = false>
 __device__ __forceinline__ int hyper_step(const DevModel& M, const Node* __restrict__ nodes,
                                           float* counts, int s, R& g, int& o_out, Feat& x_new,
                                           int* rec)
@@ -381,7 +429,8 @@ __device__ __forceinline__ int hyper_step(const DevModel& M, const Node* __restr
         Node const nd   = nodes[f];
         int const range = M.feat_s[f];
         int const cell  = nd.off + parent_config(M, nd.par, x) * range;
-        int const v     = sample_expected_mult(counts + cell, range, draw_u(g));
+        int const v     = COOP ? sample_expected_mult_warp(counts + cell, range, draw_u(g))
+                               : sample_expected_mult(counts + cell, range, draw_u(g));
         x2.set(f, v, single_s);
         s2 += v * M.step_s[f];
         if (MODE == STEP_UPDATE) counts[cell + v] = __fadd_rn(counts[cell + v], 1.0f);
@@ -399,7 +448,8 @@ __device__ __forceinline__ int hyper_step(const DevModel& M, const Node* __restr
         Node const nd   = nodes[M.FS + q];
         int const range = M.feat_o[q];
         int const cell  = nd.off + parent_config(M, nd.par, x2) * range;
-        int const v     = sample_expected_mult(counts + cell, range, draw_u(g));
+        int const v     = COOP ? sample_expected_mult_warp(counts + cell, range, draw_u(g))
+                               : sample_expected_mult(counts + cell, range, draw_u(g));
         of.set(q, v, single_o);
         o += v * M.step_o[q];
     }

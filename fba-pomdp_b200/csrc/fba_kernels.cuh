@@ -785,14 +785,18 @@ __global__ void __launch_bounds__(kThreads)
 // ------------------------------------------------------------------------------------------------
 // rollouts: RBAPOUCT::rollout (RBAPOUCT.cpp:295-323), one thread per rollout, counts read-only
 // ------------------------------------------------------------------------------------------------
-template<bool REPLAY>
+// COOP = false: one thread per rollout (large batches: most independent work per SM).
+// COOP = true: one warp per rollout, rows loaded cooperatively (small batches are latency-bound:
+// one coalesced request per row instead of `range` dependent ones).
+template<bool REPLAY, bool COOP>
 __global__ void __launch_bounds__(kThreads)
     k_rollouts(DevModel M, const float* counts, long long stride, const int* __restrict__ sid,
                long long n, const long long* __restrict__ particle, const int* __restrict__ start,
                const int* __restrict__ depth, double discount, RngArgs ra, double* __restrict__ ret_out,
                int* __restrict__ overrun)
 {
-    long long const r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long const t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long const r = COOP ? (t >> 5) : t;
     if (r >= n) return;
     auto g            = RngOf<REPLAY>::make(ra, r);
     long long const p = particle[r];
@@ -807,15 +811,19 @@ __global__ void __launch_bounds__(kThreads)
         int const a = random_action(M, g);
         int o;
         Feat x2;
-        int const s2   = hyper_step<STEP_KEEP>(M, base + (long long)a * M.J, c, s, g, o, x2, nullptr);
+        int const s2 =
+            hyper_step<STEP_KEEP, decltype(g), COOP>(M, base + (long long)a * M.J, c, s, g, o, x2, nullptr);
         double const rew = domain_reward(M, s, a, s2, terminal);
         ret  = __dadd_rn(ret, __dmul_rn(rew, disc)); // Return::add (Return.cpp:6-9)
         disc = __dmul_rn(disc, discount);            // Discount::increment (Discount.cpp:8-11)
         s    = s2;
         --d;
     }
-    ret_out[r] = ret;
-    if (g.overrun) *overrun = 1;
+    if (!COOP || (threadIdx.x & 31) == 0)
+    {
+        ret_out[r] = ret;
+        if (g.overrun) *overrun = 1;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -77,10 +77,13 @@ def test_importance_sampling_replay(ctx, name):
     sim.close()
 
 
+@pytest.mark.parametrize("coop", [0, 1])
 @pytest.mark.parametrize("name", G.NAMES)
-def test_rollouts_replay(ctx, name):
+def test_rollouts_replay(ctx, name, coop):
+    """Both rollout kernels (thread per rollout / warp per rollout with cooperative row loads)."""
     import fba_pomdp_b200 as fba
     g = G.load(name)
+    ctx.set_option("rollout_coop", coop)
     sim = make_sim(ctx, g)
     b = fba.BAImportanceSampling(len(g["is/final_state"]))
     b.initiate(sim, struct_id=g["is/final_struct_id"], counts=g["is/final_counts"], state=g["is/final_state"])
@@ -90,6 +93,7 @@ def test_rollouts_replay(ctx, name):
     np.testing.assert_array_equal(ret, g["roll/ret"])
     # rollouts are KeepCounts: the belief is untouched
     np.testing.assert_array_equal(b.download()["counts"], g["is/final_counts"])
+    ctx.set_option("rollout_coop", -1)
     b.free()
     sim.close()
 
