@@ -50,6 +50,7 @@ struct fba_model
     fba_ctx* ctx = nullptr;
     DevModel dev{};
     int max_structs = 0, n_structs = 0;
+    bool long_rows = false; // some feature has more than 4 values: kernels load rows in chunks
     std::vector<uint32_t> t_par, o_par; // host structure table
     std::vector<int> sizes;
     std::vector<Node> h_nodes;
@@ -172,6 +173,22 @@ static void profile_mark(fba_ctx* ctx, const char* name, bool begin)
         if ((ctx)->profiling) profile_mark(ctx, #kernel, false);                                   \
         ++(ctx)->launches;                                                                         \
         CU(ctx, cudaGetLastError());                                                               \
+    } while (0)
+
+// kernel<REPLAY, LONG> chosen at run time
+#define LAUNCH_RL(ctx, kernel, replay, longrows, grid, block, ...)                                 \
+    do {                                                                                           \
+        if (replay)                                                                                \
+        {                                                                                          \
+            if (longrows) LAUNCH(ctx, (kernel<true, true>), grid, block, __VA_ARGS__);             \
+            else                                                                                   \
+                LAUNCH(ctx, (kernel<true, false>), grid, block, __VA_ARGS__);                      \
+        } else                                                                                     \
+        {                                                                                          \
+            if (longrows) LAUNCH(ctx, (kernel<false, true>), grid, block, __VA_ARGS__);            \
+            else                                                                                   \
+                LAUNCH(ctx, (kernel<false, false>), grid, block, __VA_ARGS__);                     \
+        }                                                                                          \
     } while (0)
 
 // ------------------------------------------------------------------------------------------------
@@ -447,6 +464,8 @@ extern "C" int fba_model_create(fba_ctx* ctx, const fba_model_desc* d, int32_t m
     D.step_o[D.FO - 1] = 1;
     for (int f = D.FO - 2; f >= 0; --f) D.step_o[f] = D.step_o[f + 1] * D.feat_o[f + 1];
     D.tabular = d->tabular, D.domain = d->domain, D.action_draw = d->action_draw;
+    for (int f = 0; f < D.FS; ++f) m->long_rows |= D.feat_s[f] > 4;
+    for (int f = 0; f < D.FO; ++f) m->long_rows |= D.feat_o[f] > 4;
     memcpy(D.dom_ip, d->dom_ip, sizeof(D.dom_ip));
     memcpy(D.dom_dp, d->dom_dp, sizeof(D.dom_dp));
     D.start_kind = d->start_kind;
@@ -874,15 +893,15 @@ static int propose(fba_belief* b, int a, int o, fba_rng* rng, unsigned long long
         long long const per = 2ll * D.J, need = per * b->N;
         if ((rc = stage_words(ctx, rng, need))) return rc;
         if ((rc = clear_flag(ctx))) return rc;
-        LAUNCH(ctx, k_propose<true>, blocks_for(b->N), kThreads, D, b->counts[b->cur], b->stride,
-               b->state[b->cur], b->sid[b->cur], b->w, b->N, a, o, replay_args(ctx, need, per, false),
-               ctx->d_flag);
+        LAUNCH_RL(ctx, k_propose, true, b->m->long_rows, blocks_for(b->N), kThreads, D, b->counts[b->cur],
+                  b->stride, b->state[b->cur], b->sid[b->cur], b->w, b->N, a, o,
+                  replay_args(ctx, need, per, false), ctx->d_flag);
         rng->cursor += need;
     } else
     {
-        LAUNCH(ctx, k_propose<false>, blocks_for(b->N), kThreads, D, b->counts[b->cur], b->stride,
-               b->state[b->cur], b->sid[b->cur], b->w, b->N, a, o, philox_args(rng, stream_base),
-               ctx->d_flag);
+        LAUNCH_RL(ctx, k_propose, false, b->m->long_rows, blocks_for(b->N), kThreads, D, b->counts[b->cur],
+                  b->stride, b->state[b->cur], b->sid[b->cur], b->w, b->N, a, o, philox_args(rng, stream_base),
+                  ctx->d_flag);
     }
     b->suffix_valid = b->cdf_valid = false;
     return FBA_OK;
@@ -1242,14 +1261,9 @@ extern "C" int fba_belief_reject_sample(fba_belief* b, int32_t a, int32_t o, fba
             ra.stream_base = (unsigned long long)attempts;
         }
         if ((rc = clear_flag(ctx))) return rc;
-        if (rng->mode == FBA_RNG_REPLAY)
-            LAUNCH(ctx, k_rs_attempt<true>, blocks_for(wave), kThreads, D, b->counts[b->cur], b->stride,
-                   b->state[b->cur], b->sid[b->cur], b->N, a, o, wave, ra, b->att_src, b->att_state,
-                   b->att_accept, b->att_rec, ctx->d_flag);
-        else
-            LAUNCH(ctx, k_rs_attempt<false>, blocks_for(wave), kThreads, D, b->counts[b->cur], b->stride,
-                   b->state[b->cur], b->sid[b->cur], b->N, a, o, wave, ra, b->att_src, b->att_state,
-                   b->att_accept, b->att_rec, ctx->d_flag);
+        LAUNCH_RL(ctx, k_rs_attempt, rng->mode == FBA_RNG_REPLAY, b->m->long_rows, blocks_for(wave), kThreads, D,
+                  b->counts[b->cur], b->stride, b->state[b->cur], b->sid[b->cur], b->N, a, o, wave, ra,
+                  b->att_src, b->att_state, b->att_accept, b->att_rec, ctx->d_flag);
         LAUNCH(ctx, k_scan_flags, 1, kThreads, b->att_accept, wave, b->att_pos, b->d_total);
         LAUNCH(ctx, k_rs_commit, stream_grid(ctx, wave), kThreads, b->counts[b->cur], b->counts[nx], b->stride,
                b->sid[b->cur], b->sid[nx], b->state[nx], b->m->d_sizes, b->N, D.J, wave, b->att_src,
@@ -1446,8 +1460,13 @@ extern "C" int fba_rollouts(fba_belief* b, int64_t n, const int64_t* particle, c
     int max_range = 1;
     for (int f = 0; f < D.FS; ++f) max_range = std::max(max_range, D.feat_s[f]);
     for (int f = 0; f < D.FO; ++f) max_range = std::max(max_range, D.feat_o[f]);
-    bool const coop = ctx->rollout_coop >= 0 ? ctx->rollout_coop != 0
-                                             : (max_range >= 8 && n <= (long long)ctx->sm_count * 512);
+    // measured (tools/exp_rollouts.py, profiles/r1f_rollouts_*): the cooperative kernel executes 27x more
+    // warp instructions and is issue-bound; it is kept selectable but never chosen automatically
+    bool const coop = ctx->rollout_coop > 0;
+    // thread-per-rollout: spread a small batch over as many SMs as possible (one warp per CTA until
+    // every SM has work), so that its uncoalesced row loads do not queue on a few SMs' LSUs
+    int tpb = kThreads;
+    while (tpb > 32 && (n + tpb - 1) / tpb < 2ll * ctx->sm_count) tpb >>= 1;
     if (rng->mode == FBA_RNG_REPLAY)
     {
         REQUIRE(ctx, word_offset, "rollouts: REPLAY mode needs word_offset");
@@ -1456,18 +1475,27 @@ extern "C" int fba_rollouts(fba_belief* b, int64_t n, const int64_t* particle, c
         if ((rc = stage_words(ctx, rng, std::max(0ll, avail)))) return rc;
         if ((rc = stage_offsets(ctx, off))) return rc;
         if ((rc = clear_flag(ctx))) return rc;
-        if (coop)
-            LAUNCH(ctx, (k_rollouts<true, true>), blocks_for(n * 32), kThreads, D, b->counts[b->cur], b->stride,
-                   b->sid[b->cur], n, d_p, d_s, d_d, discount, replay_args(ctx, avail, 0, true), d_r, ctx->d_flag);
+        RngArgs const ra = replay_args(ctx, avail, 0, true);
+        if (coop) LAUNCH(ctx, (k_rollouts<true, true, false>), blocks_for(n * 32), kThreads, D, b->counts[b->cur],
+                         b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag);
+        else if (b->m->long_rows)
+            LAUNCH(ctx, (k_rollouts<true, false, true>), blocks_for(n, tpb), tpb, D, b->counts[b->cur], b->stride,
+                   b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag);
         else
-            LAUNCH(ctx, (k_rollouts<true, false>), blocks_for(n), kThreads, D, b->counts[b->cur], b->stride,
-                   b->sid[b->cur], n, d_p, d_s, d_d, discount, replay_args(ctx, avail, 0, true), d_r, ctx->d_flag);
-    } else if (coop)
-        LAUNCH(ctx, (k_rollouts<false, true>), blocks_for(n * 32), kThreads, D, b->counts[b->cur], b->stride,
-               b->sid[b->cur], n, d_p, d_s, d_d, discount, philox_args(rng), d_r, ctx->d_flag);
-    else
-        LAUNCH(ctx, (k_rollouts<false, false>), blocks_for(n), kThreads, D, b->counts[b->cur], b->stride,
-               b->sid[b->cur], n, d_p, d_s, d_d, discount, philox_args(rng), d_r, ctx->d_flag);
+            LAUNCH(ctx, (k_rollouts<true, false, false>), blocks_for(n, tpb), tpb, D, b->counts[b->cur], b->stride,
+                   b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag);
+    } else
+    {
+        RngArgs const ra = philox_args(rng);
+        if (coop) LAUNCH(ctx, (k_rollouts<false, true, false>), blocks_for(n * 32), kThreads, D, b->counts[b->cur],
+                         b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag);
+        else if (b->m->long_rows)
+            LAUNCH(ctx, (k_rollouts<false, false, true>), blocks_for(n, tpb), tpb, D, b->counts[b->cur], b->stride,
+                   b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag);
+        else
+            LAUNCH(ctx, (k_rollouts<false, false, false>), blocks_for(n, tpb), tpb, D, b->counts[b->cur], b->stride,
+                   b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag);
+    }
     CU(ctx, cudaMemcpyAsync(returns, d_r, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     if (rng->mode == FBA_RNG_REPLAY)

@@ -180,16 +180,57 @@ __host__ __device__ inline int draw_slow_int(R& g, int max) // rnd::slowRandomIn
 
 // sampleFromExpectedMult (random.cpp:244-255) -> sampleFromMult<float const> (random.hpp:93-115):
 // DOUBLE total of the float counts, FLOAT running prefix compared against a double threshold.
+// LONG = false: plain loop (factored models: feature ranges of 2..5).
+// LONG = true: rows of tabular models (S or O values): 16 independent loads in flight per chunk, so a
+// row costs ceil(n/16) memory latencies instead of n/4; the sums stay strictly sequential. Kernels
+// are instantiated for both so that the short-row variants keep their small register footprint.
+template<bool LONG>
 __device__ __forceinline__ int sample_expected_mult(const float* row, int n, double u)
 {
-    double total = (double)row[0];
-    for (int i = 1; i < n; ++i) total = __dadd_rn(total, (double)row[i]);
-    double const p = __dmul_rn(u, total);
-    float sum      = row[0];
-    for (int i = 1; i < n; ++i)
+    if (!LONG || n <= 4)
     {
-        if (p < (double)sum) return i - 1;
-        sum = __fadd_rn(sum, row[i]);
+        double total = (double)row[0];
+        for (int i = 1; i < n; ++i) total = __dadd_rn(total, (double)row[i]);
+        double const p = __dmul_rn(u, total);
+        float sum      = row[0];
+        for (int i = 1; i < n; ++i)
+        {
+            if (p < (double)sum) return i - 1;
+            sum = __fadd_rn(sum, row[i]);
+        }
+        return n - 1;
+    }
+    constexpr int CH = 16;
+    double total = 0.0;
+    for (int base = 0; base < n; base += CH)
+    {
+        float v[CH];
+#pragma unroll
+        for (int k = 0; k < CH; ++k) v[k] = (base + k < n) ? row[base + k] : 0.0f;
+#pragma unroll
+        for (int k = 0; k < CH; ++k)
+            if (base + k < n) total = (base + k == 0) ? (double)v[k] : __dadd_rn(total, (double)v[k]);
+    }
+    double const p = __dmul_rn(u, total);
+    float sum      = 0.0f;
+    for (int base = 0; base < n; base += CH)
+    {
+        float v[CH];
+#pragma unroll
+        for (int k = 0; k < CH; ++k) v[k] = (base + k < n) ? row[base + k] : 0.0f; // L1 hits
+#pragma unroll
+        for (int k = 0; k < CH; ++k)
+        {
+            int const i = base + k;
+            if (i >= n) break;
+            if (i == 0)
+            {
+                sum = v[k];
+                continue;
+            }
+            if (p < (double)sum) return i - 1;
+            sum = __fadd_rn(sum, v[k]);
+        }
     }
     return n - 1;
 }
@@ -412,7 +453,7 @@ enum StepMode {
 // Returns s'; o_out = simulated observation. x_new returns the new state's features.
 // COOP: the 32 lanes of a warp run ONE step together (identical arguments and random source in
 // every lane) and load each row cooperatively — for latency-bound small batches of rollouts.
-template<int MODE, class R, bool COOP = false>
+template<int MODE, class R, bool COOP = false, bool LONG = false>
 __device__ __forceinline__ int hyper_step(const DevModel& M, const Node* __restrict__ nodes,
                                           float* counts, int s, R& g, int& o_out, Feat& x_new,
                                           int* rec)
@@ -430,7 +471,7 @@ __device__ __forceinline__ int hyper_step(const DevModel& M, const Node* __restr
         int const range = M.feat_s[f];
         int const cell  = nd.off + parent_config(M, nd.par, x) * range;
         int const v     = COOP ? sample_expected_mult_warp(counts + cell, range, draw_u(g))
-                               : sample_expected_mult(counts + cell, range, draw_u(g));
+                               : sample_expected_mult<LONG>(counts + cell, range, draw_u(g));
         x2.set(f, v, single_s);
         s2 += v * M.step_s[f];
         if (MODE == STEP_UPDATE) counts[cell + v] = __fadd_rn(counts[cell + v], 1.0f);
@@ -449,7 +490,7 @@ __device__ __forceinline__ int hyper_step(const DevModel& M, const Node* __restr
         int const range = M.feat_o[q];
         int const cell  = nd.off + parent_config(M, nd.par, x2) * range;
         int const v     = COOP ? sample_expected_mult_warp(counts + cell, range, draw_u(g))
-                               : sample_expected_mult(counts + cell, range, draw_u(g));
+                               : sample_expected_mult<LONG>(counts + cell, range, draw_u(g));
         of.set(q, v, single_o);
         o += v * M.step_o[q];
     }

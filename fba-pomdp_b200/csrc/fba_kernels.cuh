@@ -156,11 +156,11 @@ __global__ void __launch_bounds__(kThreads)
 // importance_sampling::update, per-particle part (ImportanceSampler.hpp:37-54): step in place,
 // weight *= P(o | a, particle). One thread per particle.
 // ------------------------------------------------------------------------------------------------
-template<bool REPLAY>
+template<bool REPLAY, bool LONG>
 #ifndef FBA_PROPOSE_MIN_BLOCKS
 #define FBA_PROPOSE_MIN_BLOCKS 6 // 40 registers, no spills: measured 4 % faster than 48 (tools/exp_propose.py)
 #endif
-__global__ void __launch_bounds__(kThreads, FBA_PROPOSE_MIN_BLOCKS)
+__global__ void __launch_bounds__(kThreads, LONG ? 1 : FBA_PROPOSE_MIN_BLOCKS)
     k_propose(DevModel M, float* counts, long long stride, int* __restrict__ state,
               const int* __restrict__ sid, double* __restrict__ w, long long N, int a, int o, RngArgs ra,
               int* __restrict__ overrun)
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(kThreads, FBA_PROPOSE_MIN_BLOCKS)
     float* c          = counts + i * stride;
     int sim_o;
     Feat x2;
-    int const s2      = hyper_step<STEP_UPDATE>(M, nodes, c, state[i], g, sim_o, x2, nullptr);
+    int const s2 = hyper_step<STEP_UPDATE, decltype(g), false, LONG>(M, nodes, c, state[i], g, sim_o, x2, nullptr);
     double const prob = obs_probability(M, nodes, c, x2, o);
     state[i]          = s2;
     w[i]              = __dmul_rn(w[i], prob);
@@ -788,7 +788,7 @@ __global__ void __launch_bounds__(kThreads)
 // COOP = false: one thread per rollout (large batches: most independent work per SM).
 // COOP = true: one warp per rollout, rows loaded cooperatively (small batches are latency-bound:
 // one coalesced request per row instead of `range` dependent ones).
-template<bool REPLAY, bool COOP>
+template<bool REPLAY, bool COOP, bool LONG>
 __global__ void __launch_bounds__(kThreads)
     k_rollouts(DevModel M, const float* counts, long long stride, const int* __restrict__ sid,
                long long n, const long long* __restrict__ particle, const int* __restrict__ start,
@@ -812,7 +812,7 @@ __global__ void __launch_bounds__(kThreads)
         int o;
         Feat x2;
         int const s2 =
-            hyper_step<STEP_KEEP, decltype(g), COOP>(M, base + (long long)a * M.J, c, s, g, o, x2, nullptr);
+            hyper_step<STEP_KEEP, decltype(g), COOP, LONG>(M, base + (long long)a * M.J, c, s, g, o, x2, nullptr);
         double const rew = domain_reward(M, s, a, s2, terminal);
         ret  = __dadd_rn(ret, __dmul_rn(rew, disc)); // Return::add (Return.cpp:6-9)
         disc = __dmul_rn(disc, discount);            // Discount::increment (Discount.cpp:8-11)
@@ -831,7 +831,7 @@ __global__ void __launch_bounds__(kThreads)
 // attempt t picks a particle uniformly, simulates a step on it WITHOUT touching it and records the
 // outcome; the accepted attempts, in attempt order, become the new particles.
 // ------------------------------------------------------------------------------------------------
-template<bool REPLAY>
+template<bool REPLAY, bool LONG>
 __global__ void __launch_bounds__(kThreads)
     k_rs_attempt(DevModel M, const float* counts, long long stride, const int* __restrict__ state,
                  const int* __restrict__ sid, long long N, int a, int o, long long n_attempts,
@@ -847,7 +847,7 @@ __global__ void __launch_bounds__(kThreads)
     int rec[2 * FBA_MAX_FEATURES];
     int sim_o;
     Feat x2;
-    int const s2 = hyper_step<STEP_RECORD>(M, nodes, c, state[i], g, sim_o, x2, rec);
+    int const s2 = hyper_step<STEP_RECORD, decltype(g), false, LONG>(M, nodes, c, state[i], g, sim_o, x2, rec);
     src_out[t]    = i;
     state_out[t]  = s2;
     accept_out[t] = (sim_o == o) ? 1 : 0;
