@@ -522,8 +522,30 @@ extern "C" void fba_model_destroy(fba_model* m)
     delete m;
 }
 
+static int add_structures(fba_model* m, int32_t n, const uint32_t* t_par, const uint32_t* o_par,
+                          int32_t* ids_out, bool upload);
+
+// uploads the node tables of structures [first_new, n_structs) to the device
+static int upload_structures(fba_model* m, int first_new)
+{
+    fba_ctx* ctx = m->ctx;
+    if (m->n_structs <= first_new) return FBA_OK;
+    size_t const per = (size_t)m->dev.A * m->dev.J;
+    CU(ctx, cudaMemcpy(m->d_nodes + first_new * per, m->h_nodes.data() + first_new * per,
+                       (m->n_structs - first_new) * per * sizeof(Node), cudaMemcpyHostToDevice));
+    CU(ctx, cudaMemcpy(m->d_sizes + first_new, m->sizes.data() + first_new,
+                       (m->n_structs - first_new) * sizeof(int), cudaMemcpyHostToDevice));
+    return FBA_OK;
+}
+
 extern "C" int fba_model_add_structures(fba_model* m, int32_t n, const uint32_t* t_par,
                                         const uint32_t* o_par, int32_t* ids_out)
+{
+    return add_structures(m, n, t_par, o_par, ids_out, true);
+}
+
+static int add_structures(fba_model* m, int32_t n, const uint32_t* t_par, const uint32_t* o_par,
+                          int32_t* ids_out, bool upload)
 {
     if (!m || !t_par || !o_par || n < 0) return FBA_ERR_INVALID;
     fba_ctx* ctx      = m->ctx;
@@ -572,14 +594,7 @@ extern "C" int fba_model_add_structures(fba_model* m, int32_t n, const uint32_t*
         }
         if (ids_out) ids_out[k] = id;
     }
-    if (m->n_structs > first_new)
-    {
-        size_t const per = (size_t)D.A * D.J;
-        CU(ctx, cudaMemcpy(m->d_nodes + first_new * per, m->h_nodes.data() + first_new * per,
-                           (m->n_structs - first_new) * per * sizeof(Node), cudaMemcpyHostToDevice));
-        CU(ctx, cudaMemcpy(m->d_sizes + first_new, m->sizes.data() + first_new,
-                           (m->n_structs - first_new) * sizeof(int), cudaMemcpyHostToDevice));
-    }
+    if (upload) return upload_structures(m, first_new);
     return FBA_OK;
 }
 
@@ -1275,16 +1290,13 @@ extern "C" int fba_belief_reject_sample(fba_belief* b, int32_t a, int32_t o, fba
         long long used = wave; // attempts of this wave that count
         if (accepted + got >= b->N)
         { // the N-th acceptance happened inside this wave: find the attempt that produced it
-            long long const need = b->N - accepted;
-            h_accept.resize((size_t)wave);
-            CU(ctx, cudaMemcpy(h_accept.data(), b->att_accept, wave * sizeof(int), cudaMemcpyDeviceToHost));
-            long long seen = 0;
-            for (long long t = 0; t < wave; ++t)
-                if (h_accept[t] && ++seen == need)
-                {
-                    used = t + 1;
-                    break;
-                }
+            int const need = (int)(b->N - accepted);
+            LAUNCH(ctx, k_find_nth_accept, blocks_for(wave), kThreads, b->att_accept, b->att_pos, wave, need,
+                   b->d_total);
+            int nth = 0;
+            CU(ctx, cudaMemcpyAsync(&nth, b->d_total, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(ctx, cudaStreamSynchronize(ctx->stream));
+            used     = nth;
             accepted = b->N;
         } else
             accepted += got;
@@ -1352,6 +1364,22 @@ extern "C" int fba_belief_reinvigorate(fba_belief* b, fba_belief* fc, int64_t am
     std::vector<uint32_t> tp(nT), op(nO);
     std::map<int, BreedJob> last_writer; // slot -> job; a later breed overwrites an earlier one
     HostDraws g(rng);
+    int const first_new_struct = m->n_structs;
+    struct UploadGuard // whatever the exit path, structures registered on the host reach the device
+    {
+        fba_model* m;
+        int first;
+        bool done = false;
+        int run()
+        {
+            done = true;
+            return upload_structures(m, first);
+        }
+        ~UploadGuard()
+        {
+            if (!done) upload_structures(m, first);
+        }
+    } guard{m, first_new_struct};
     for (int64_t k = 0; k < amount; ++k)
     {
         // ReinvigoratingRejectionSampling.cpp:128: breed(fbapomdp, _belief.sample(),
@@ -1388,7 +1416,7 @@ extern "C" int fba_belief_reinvigorate(fba_belief* b, fba_belief* fc, int64_t am
             default: ctx->err = "reinvigorate: unknown mutate kind"; return FBA_ERR_INVALID;
         }
         int32_t id = -1;
-        int rc     = fba_model_add_structures(m, 1, tp.data(), op.data(), &id);
+        int rc     = add_structures(m, 1, tp.data(), op.data(), &id, false); // uploaded once, below
         if (rc) return rc;
         if (m->sizes[id] > b->stride)
         {
@@ -1404,6 +1432,10 @@ extern "C" int fba_belief_reinvigorate(fba_belief* b, fba_belief* fc, int64_t am
         st[slot]          = job.state;
     }
     g.commit();
+    {
+        int const rc = guard.run();
+        if (rc) return rc;
+    }
 
     std::vector<BreedJob> jobs;
     for (auto const& kv : last_writer) jobs.push_back(kv.second);

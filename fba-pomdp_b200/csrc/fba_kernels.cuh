@@ -899,6 +899,15 @@ __global__ void __launch_bounds__(kThreads)
     if (threadIdx.x == 0) *total = carry;
 }
 
+// the attempt that produced the `need`-th acceptance of this wave: out[0] = its index + 1
+__global__ void __launch_bounds__(kThreads)
+    k_find_nth_accept(const int* __restrict__ accept, const int* __restrict__ pos, long long n, int need,
+                      int* __restrict__ out)
+{
+    long long const t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n && accept[t] && pos[t] == need - 1) out[0] = (int)(t + 1);
+}
+
 // accepted attempt t with slot = already + pos[t] < N: copy its source block and apply the
 // recorded +1 increments (one warp per attempt)
 __global__ void __launch_bounds__(kThreads)
