@@ -5,6 +5,8 @@
 //
 //   CudaBAImportanceSampling : beliefs::BABelief   stands in for beliefs::BAImportanceSampling
 //   CudaBARejectionSampling  : beliefs::BABelief   stands in for beliefs::BARejectionSampling
+//   CudaReinvigoratingRejectionSampling : beliefs::BABelief   stands in for
+//       beliefs::bayes_adaptive::factored::ReinvigoratingRejectionSampling
 //
 // Contract kept (src/beliefs/Belief.hpp:17-41, src/beliefs/bayes-adaptive/BABelief.hpp:22-35):
 // initiate / free / sample / updateEstimation / resetDomainStateDistribution with the same
@@ -24,7 +26,7 @@
 // The heavy per-particle work — step, likelihood, normalisation, resampling, copies — runs on the GPU.
 //
 // This header only uses the reference's PUBLIC API. It is compiled and exercised by
-// oracle/ref_harness.cpp (ref_adapter_selftest) so that it cannot rot.
+// oracle/ref_harness.cpp (ref_adapter_episodes) so that it cannot rot.
 #ifndef FBA_B200_CUDA_BELIEFS_HPP
 #define FBA_B200_CUDA_BELIEFS_HPP
 
@@ -454,6 +456,134 @@ public:
         int64_t attempts = 0;
         check(_cuda->ctx(), fba_belief_reject_sample(_belief, a->index(), o->index(), &_rng, &attempts),
               "fba_belief_reject_sample");
+    }
+};
+
+// beliefs::bayes_adaptive::factored::ReinvigoratingRejectionSampling
+// (src/beliefs/bayes-adaptive/factored/ReinvigoratingRejectionSampling.cpp:37-131): two flat filters —
+// the learned-structure belief and the fully connected one. `mutate_kind` names the domain's
+// FBAPOMDP::mutate (fba_mutate_kind); the factory picks it from the -D string.
+class CudaReinvigoratingRejectionSampling : public beliefs::BABelief
+{
+public:
+    CudaReinvigoratingRejectionSampling(size_t size, size_t reinvigoration_amount, int mutate_kind,
+                                        uint64_t seed = 42, int device = 0) :
+            _size(size), _amount(reinvigoration_amount), _mutate(mutate_kind), _device(device)
+    {
+        if (_size < 1 || _amount < 1) // as ReinvigoratingRejectionSampling.cpp:43-48
+            throw "ReinvigoratingRejectionSampling::cannot initiate belief of size < 1 (" + std::to_string(_size)
+                + "), or resample size of < 1 (" + std::to_string(_amount) + ")";
+        _rng.mode    = FBA_RNG_PHILOX;
+        _rng.words   = nullptr;
+        _rng.n_words = _rng.cursor = 0;
+        _rng.seed    = seed;
+        _rng.offset  = 0;
+    }
+    ~CudaReinvigoratingRejectionSampling() override { release(); }
+
+    void initiate(POMDP const& d) override
+    {
+        auto const& fbapomdp = dynamic_cast<::bayes_adaptive::factored::FBAPOMDP const&>(d);
+        _cuda.reset(new CudaSimulator(fbapomdp, _device, 1 << 16));
+        // :56-75: _size x sampleStartState, then _size x sampleFullyConnectedState (host prior)
+        std::vector<int32_t> state[2], sid[2];
+        std::vector<std::vector<float>> blocks[2];
+        size_t stride = 0;
+        for (int k = 0; k < 2; ++k)
+        {
+            state[k].resize(_size), sid[k].resize(_size), blocks[k].resize(_size);
+            for (size_t i = 0; i < _size; ++i)
+            {
+                BAState const* p = (k == 0) ? static_cast<BAState const*>(d.sampleStartState())
+                                            : static_cast<BAState const*>(fbapomdp.sampleFullyConnectedState());
+                state[k][i] = p->_domain_state->index();
+                sid[k][i]   = _cuda->describe(p, &blocks[k][i]);
+                stride      = std::max(stride, blocks[k][i].size());
+                d.releaseState(p);
+            }
+        }
+        for (int k = 0; k < 2; ++k)
+        {
+            check(_cuda->ctx(),
+                  fba_belief_create(_cuda->ctx(), _cuda->model(), (int64_t)_size, (int64_t)stride, 0, &_b[k]),
+                  "fba_belief_create");
+            size_t const st = (size_t)fba_belief_stride(_b[k]);
+            std::vector<float> flat(_size * st, 0.0f);
+            for (size_t i = 0; i < _size; ++i)
+                std::copy(blocks[k][i].begin(), blocks[k][i].end(), flat.begin() + i * st);
+            check(_cuda->ctx(),
+                  fba_belief_upload(_b[k], 0, (int64_t)_size, state[k].data(), sid[k].data(), flat.data(), nullptr),
+                  "fba_belief_upload");
+        }
+    }
+
+    void free(POMDP const& /*d*/) override { release(); }
+
+    State const* sample() const override
+    {
+        int64_t i = 0;
+        check(_cuda->ctx(), fba_belief_sample(_b[0], &_rng, &i), "fba_belief_sample");
+        std::vector<float> counts((size_t)fba_belief_stride(_b[0]));
+        int32_t state = 0, sid = 0;
+        check(_cuda->ctx(), fba_belief_download(_b[0], i, 1, &state, &sid, counts.data(), nullptr),
+              "fba_belief_download");
+        dropSample();
+        _sample = _cuda->materialise(sid, state, counts);
+        return _sample;
+    }
+
+    void updateEstimation(Action const* a, Observation const* o, POMDP const& /*d*/) override
+    {
+        // :89-106: reinvigorateParticles, then rejectSample on both filters
+        int64_t attempts = 0;
+        check(_cuda->ctx(), fba_belief_reinvigorate(_b[0], _b[1], (int64_t)_amount, _mutate, &_rng),
+              "fba_belief_reinvigorate");
+        for (int k = 0; k < 2; ++k)
+            check(_cuda->ctx(), fba_belief_reject_sample(_b[k], a->index(), o->index(), &_rng, &attempts),
+                  "fba_belief_reject_sample");
+    }
+
+    void resetDomainStateDistribution(BAPOMDP const& bapomdp) override
+    {
+        // :108-119: resetDomainState on every particle of both filters, belief first
+        std::vector<int32_t> state(_size);
+        for (int k = 0; k < 2; ++k)
+        {
+            for (size_t i = 0; i < _size; ++i)
+            {
+                auto s   = bapomdp.sampleDomainState();
+                state[i] = s->index();
+                bapomdp.releaseDomainState(s);
+            }
+            check(_cuda->ctx(),
+                  fba_belief_upload(_b[k], 0, (int64_t)_size, state.data(), nullptr, nullptr, nullptr),
+                  "fba_belief_upload");
+        }
+    }
+
+private:
+    size_t _size, _amount;
+    int _mutate, _device;
+    mutable fba_rng _rng;
+    std::unique_ptr<CudaSimulator> _cuda;
+    fba_belief* _b[2]              = {nullptr, nullptr};
+    mutable BAState const* _sample = nullptr;
+
+    void dropSample() const
+    {
+        if (_sample)
+        {
+            _cuda->sim().releaseState(_sample);
+            _sample = nullptr;
+        }
+    }
+    void release()
+    {
+        if (_cuda) dropSample();
+        fba_belief_destroy(_b[0]);
+        fba_belief_destroy(_b[1]);
+        _b[0] = _b[1] = nullptr;
+        _cuda.reset();
     }
 };
 

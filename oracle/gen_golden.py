@@ -37,6 +37,11 @@ CONFIGS = {
                structure_prior="match-uniform", N=256, steps=20, reinv_N=64, reinv_K=16),
     # configs[4]: linear sysadmin, 10 computers
     "sysadmin": dict(domain="linear-sysadmin", size=10, factored=True, N=96, steps=20, rs_N=48),
+    # extra pins beyond the five configs:
+    # sysadmin's `mutate` (chained subscripts drawn right to left) through reinvigoration
+    "sysadmin3": dict(domain="linear-sysadmin", size=3, factored=True, N=64, steps=12, reinv_N=48, reinv_K=12),
+    # factored gridworld: three OBSERVATION features (likelihood = double product of float factors)
+    "gridworld3_fba": dict(domain="gridworld", size=3, factored=True, N=64, steps=20),
 }
 
 HORIZON = 20

@@ -613,7 +613,9 @@ void ref_env_script(void* hv, int steps, int horizon, int* actions, int* observa
 // initiate once, then per episode resetDomainStateDistribution + episode::run with the reference's
 // planner (--planner string). kind: 0 = the reference's BAImportanceSampling (CPU),
 // 1 = fba_b200::CudaBAImportanceSampling, 2 = the reference's BARejectionSampling,
-// 3 = fba_b200::CudaBARejectionSampling. returns[e] = discounted return of episode e.
+// 3 = fba_b200::CudaBARejectionSampling, 4 = the reference's ReinvigoratingRejectionSampling,
+// 5 = fba_b200::CudaReinvigoratingRejectionSampling (amount = n / 8, mutate kind from the domain).
+// returns[e] = discounted return of episode e.
 // rc: 0 ok, 1 error (see ref_error).
 int ref_adapter_episodes(void* hv, int kind, long n, char const* planner, int sims, int episodes,
                          double* returns)
@@ -633,8 +635,20 @@ int ref_adapter_episodes(void* hv, int kind, long n, char const* planner, int si
             belief.reset(new fba_b200::CudaBAImportanceSampling(n));
         else if (kind == 2)
             belief.reset(new beliefs::BARejectionSampling(n));
-        else
+        else if (kind == 3)
             belief.reset(new fba_b200::CudaBARejectionSampling(n));
+        else
+        {
+            auto const& d  = h->conf.domain_conf.domain;
+            int const mut  = (d.find("factored-tiger") != std::string::npos)       ? FBA_MUT_FACTORED_TIGER
+                             : (d.find("collision-avoidance") != std::string::npos) ? FBA_MUT_COLLISION_AVOIDANCE
+                             : (d.find("sysadmin") != std::string::npos)            ? FBA_MUT_SYSADMIN
+                                                                                    : FBA_MUT_GRIDWORLD;
+            size_t const k = std::max<size_t>(1, n / 8);
+            if (kind == 4) belief.reset(new ReinvRS(n, k));
+            else
+                belief.reset(new fba_b200::CudaReinvigoratingRejectionSampling(n, k, mut));
+        }
 
         belief->initiate(*h->sim);
         for (int e = 0; e < episodes; ++e)

@@ -19,6 +19,11 @@ CASES = [
     ("centered-collision-avoidance", dict(size=1, width=3, height=3, factored=True), (0, 1), 128, 40),
     ("linear-sysadmin", dict(size=3, factored=True), (0, 1), 64, 20),
     ("gridworld", dict(size=3), (0, 1), 16, 10),
+    # reinvigoration: the reference's ReinvigoratingRejectionSampling vs the CUDA adapter
+    ("episodic-factored-tiger", dict(size=3, factored=True, structure_prior="match-uniform"), (4, 5), 128, 40),
+    ("centered-collision-avoidance", dict(size=1, width=3, height=3, factored=True,
+                                          structure_prior="match-uniform"), (4, 5), 128, 40),
+    ("linear-sysadmin", dict(size=3, factored=True), (4, 5), 64, 20),
 ]
 
 
