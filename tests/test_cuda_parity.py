@@ -29,6 +29,13 @@ def count_sums(c):
     return c.astype(np.float64).sum(1)
 
 
+def assert_counts_equal(got, want):
+    """The belief's stride is the largest structure registered in the model, which may exceed the
+    fixture's (e.g. when the structure table also holds the fully connected structures)."""
+    np.testing.assert_array_equal(got[:, :want.shape[1]], want)
+    assert not got[:, want.shape[1]:].any()
+
+
 @pytest.mark.parametrize("name", G.NAMES)
 def test_importance_sampling_replay(ctx, name):
     import fba_pomdp_b200 as fba
@@ -59,7 +66,7 @@ def test_importance_sampling_replay(ctx, name):
         assert d["total_weight"] == float(g["is/%d/total_weight" % t])
         np.testing.assert_array_equal(count_sums(d["counts"]), g["is/%d/count_sums" % t])
         if g.has("is/%d/counts" % t):
-            np.testing.assert_array_equal(d["counts"], g["is/%d/counts" % t])
+            assert_counts_equal(d["counts"], g["is/%d/counts" % t])
         rng = fba.Rng.replay(g["is/%d/resample_words" % t])
         b.resample(rng)
         assert rng.exhausted
@@ -71,7 +78,7 @@ def test_importance_sampling_replay(ctx, name):
         n_upd += 1
     assert n_upd >= 2
     d = b.download()
-    np.testing.assert_array_equal(d["counts"], g["is/final_counts"])
+    assert_counts_equal(d["counts"], g["is/final_counts"])
     np.testing.assert_array_equal(d["state"], g["is/final_state"])
     b.free()
     sim.close()
@@ -92,7 +99,7 @@ def test_rollouts_replay(ctx, name, coop):
                        g["roll/offsets"][:-1])
     np.testing.assert_array_equal(ret, g["roll/ret"])
     # rollouts are KeepCounts: the belief is untouched
-    np.testing.assert_array_equal(b.download()["counts"], g["is/final_counts"])
+    assert_counts_equal(b.download()["counts"], g["is/final_counts"])
     ctx.set_option("rollout_coop", -1)
     b.free()
     sim.close()
@@ -124,7 +131,7 @@ def test_rejection_sampling_replay(ctx, name):
         np.testing.assert_array_equal(count_sums(d["counts"]), g["rs/%d/count_sums" % t])
         done += 1
     assert done >= 1
-    np.testing.assert_array_equal(b.download()["counts"], g["rs/final_counts"])
+    assert_counts_equal(b.download()["counts"], g["rs/final_counts"])
     b.free()
     sim.close()
 
