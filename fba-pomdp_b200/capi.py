@@ -27,7 +27,8 @@ SYMBOLS = [
     "fba_belief_init", "fba_belief_init_sampled", "fba_belief_upload", "fba_belief_download",
     "fba_belief_total_weight", "fba_belief_update", "fba_belief_resample",
     "fba_belief_update_estimation", "fba_belief_reset_domain_states", "fba_belief_sample",
-    "fba_belief_reject_sample", "fba_belief_reinvigorate", "fba_rollouts", "fba_belief_propose",
+    "fba_belief_reject_sample", "fba_belief_reinvigorate", "fba_rollouts",
+    "fba_belief_sample_batch", "fba_belief_gather_states", "fba_step_batch", "fba_belief_propose",
     "fba_belief_normalize", "fba_belief_resample_shard", "fba_belief_resample_stats",
     "fba_belief_shard_resample", "fba_belief_shard_resample_async", "fba_belief_shard_plan",
     "fba_belief_ipc_handle", "fba_belief_ipc_open", "fba_belief_shard_resample_p2p", "fba_belief_import_p2p",
@@ -139,6 +140,9 @@ def lib():
             "fba_belief_reject_sample": (C.c_int, [vp, i32, i32, vp, vp]),
             "fba_belief_reinvigorate": (C.c_int, [vp, vp, i64, i32, vp]),
             "fba_rollouts": (C.c_int, [vp, i64, vp, vp, vp, dbl, vp, vp, vp]),
+            "fba_belief_sample_batch": (C.c_int, [vp, vp, i64, vp]),
+            "fba_belief_gather_states": (C.c_int, [vp, i64, vp, vp]),
+            "fba_step_batch": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp]),
             "fba_belief_propose": (C.c_int, [vp, i32, i32, vp, vp]),
             "fba_belief_normalize": (C.c_int, [vp, dbl]),
             "fba_belief_resample_shard": (C.c_int, [vp, i64, vp]),

@@ -99,7 +99,9 @@ struct fba_belief
     int *att_src = nullptr, *att_state = nullptr, *att_accept = nullptr, *att_pos = nullptr,
         *att_rec = nullptr, *d_total = nullptr;
     // rollout request / result staging (grow-only)
-    long long roll_cap = 0;
+    long long roll_cap = 0, roll_cap_p = 0, step_cap = 0, step_cap_r = 0;
+    int* step_i    = nullptr;
+    double* step_r = nullptr;
     long long* roll_p  = nullptr;
     int *roll_s = nullptr, *roll_d = nullptr;
     double* roll_r = nullptr;
@@ -689,6 +691,7 @@ extern "C" void fba_belief_destroy(fba_belief* b)
     cudaFree(b->w), cudaFree(b->aux), cudaFree(b->tile), cudaFree(b->scal), cudaFree(b->anc);
     cudaFree(b->att_src), cudaFree(b->att_state), cudaFree(b->att_accept), cudaFree(b->att_pos);
     cudaFree(b->roll_p), cudaFree(b->roll_s), cudaFree(b->roll_d), cudaFree(b->roll_r);
+    cudaFree(b->step_i), cudaFree(b->step_r);
     for (auto p : b->opened) cudaIpcCloseMemHandle(p);
     cudaFree(b->d_plan);
     cudaFree(b->att_rec), cudaFree(b->d_total), cudaFree(b->xport), cudaFree(b->import_buf);
@@ -1450,6 +1453,20 @@ extern "C" int fba_belief_reinvigorate(fba_belief* b, fba_belief* fc, int64_t am
     return FBA_OK;
 }
 
+// grow-only device staging of n elements of T
+template<class T>
+static int stage_buf(fba_ctx* ctx, T** buf, long long* cap, long long n)
+{
+    if (n <= *cap) return FBA_OK;
+    cudaFree(*buf);
+    *buf = nullptr;
+    *cap = 0;
+    long long const c = n + n / 2 + 256;
+    CU(ctx, cudaMalloc(buf, (size_t)c * sizeof(T)));
+    *cap = c;
+    return FBA_OK;
+}
+
 // ---- rollouts -----------------------------------------------------------------------------------
 
 extern "C" int fba_rollouts(fba_belief* b, int64_t n, const int64_t* particle, const int32_t* start_state,
@@ -1469,13 +1486,16 @@ extern "C" int fba_rollouts(fba_belief* b, int64_t n, const int64_t* particle, c
         REQUIRE(ctx, depth[i] >= 0, "rollouts: negative depth");
     }
     CU(ctx, cudaSetDevice(ctx->device));
+    {
+        int const rcp = stage_buf(ctx, &b->roll_p, &b->roll_cap_p, (long long)n);
+        if (rcp) return rcp;
+    }
     if (n > b->roll_cap)
     {
-        cudaFree(b->roll_p), cudaFree(b->roll_s), cudaFree(b->roll_d), cudaFree(b->roll_r);
-        b->roll_p = nullptr, b->roll_s = b->roll_d = nullptr, b->roll_r = nullptr;
+        cudaFree(b->roll_s), cudaFree(b->roll_d), cudaFree(b->roll_r);
+        b->roll_s = b->roll_d = nullptr, b->roll_r = nullptr;
         b->roll_cap = 0;
         long long const cap = n + n / 2 + 1024;
-        CU(ctx, cudaMalloc(&b->roll_p, cap * sizeof(long long)));
         CU(ctx, cudaMalloc(&b->roll_s, cap * sizeof(int)));
         CU(ctx, cudaMalloc(&b->roll_d, cap * sizeof(int)));
         CU(ctx, cudaMalloc(&b->roll_r, cap * sizeof(double)));
@@ -1535,6 +1555,85 @@ extern "C" int fba_rollouts(fba_belief* b, int64_t n, const int64_t* particle, c
         if ((rc = check_flag(ctx))) return rc;
         rng->cursor = rng->n_words; // the batch owns the rest of the stream it was handed
     }
+    return FBA_OK;
+}
+
+// ---- planner support ----------------------------------------------------------------------------
+
+extern "C" int fba_belief_sample_batch(fba_belief* b, fba_rng* rng, int64_t n, int64_t* indices)
+{
+    if (!b || !rng || !indices || n < 0) return FBA_ERR_INVALID;
+    fba_ctx* ctx = b->ctx;
+    REQUIRE(ctx, rng->mode == FBA_RNG_PHILOX, "sample_batch: PHILOX mode only (REPLAY: fba_belief_sample)");
+    if (n == 0) return FBA_OK;
+    CU(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = stage_buf(ctx, &b->roll_p, &b->roll_cap_p, n))) return rc;
+    if (b->weighted && !b->cdf_valid)
+        if ((rc = native_normalize(b, false, 1.0))) return rc;
+    LAUNCH(ctx, k_sample_batch, blocks_for(n), kThreads, b->weighted ? b->aux : (const double*)nullptr, b->N,
+           (long long)n, philox_args(rng), b->roll_p);
+    CU(ctx, cudaMemcpyAsync(indices, b->roll_p, n * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return FBA_OK;
+}
+
+// domain states of the given particles (host indices in, host states out)
+extern "C" int fba_belief_gather_states(fba_belief* b, int64_t n, const int64_t* indices, int32_t* states)
+{
+    if (!b || n < 0 || (n && (!indices || !states))) return FBA_ERR_INVALID;
+    fba_ctx* ctx = b->ctx;
+    if (n == 0) return FBA_OK;
+    for (int64_t i = 0; i < n; ++i)
+        REQUIRE(ctx, indices[i] >= 0 && indices[i] < b->N, "gather_states: particle index out of range");
+    CU(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = stage_buf(ctx, &b->roll_p, &b->roll_cap_p, n))) return rc;
+    if ((rc = stage_buf(ctx, &b->step_i, &b->step_cap, n))) return rc;
+    CU(ctx, cudaMemcpyAsync(b->roll_p, indices, n * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, k_gather_states, blocks_for(n), kThreads, b->state[b->cur], b->roll_p, (long long)n, b->step_i);
+    CU(ctx, cudaMemcpyAsync(states, b->step_i, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return FBA_OK;
+}
+
+extern "C" int fba_step_batch(fba_belief* b, int64_t n, const int64_t* particle, const int32_t* state,
+                              const int32_t* action, fba_rng* rng, int32_t* new_state, int32_t* observation,
+                              double* reward, int32_t* terminal)
+{
+    if (!b || !rng) return FBA_ERR_INVALID;
+    fba_ctx* ctx      = b->ctx;
+    DevModel const& D = b->m->dev;
+    REQUIRE(ctx, n >= 0 && particle && state && action && new_state && observation && reward && terminal,
+            "step_batch: null argument");
+    REQUIRE(ctx, rng->mode == FBA_RNG_PHILOX, "step_batch: PHILOX mode only");
+    if (n == 0) return FBA_OK;
+    for (int64_t i = 0; i < n; ++i)
+    {
+        REQUIRE(ctx, particle[i] >= 0 && particle[i] < b->N, "step_batch: particle index out of range");
+        REQUIRE(ctx, state[i] >= 0 && state[i] < D.S, "step_batch: state out of range");
+        REQUIRE(ctx, action[i] >= 0 && action[i] < D.A, "step_batch: action out of range");
+    }
+    CU(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = stage_buf(ctx, &b->roll_p, &b->roll_cap_p, n))) return rc;
+    if ((rc = stage_buf(ctx, &b->step_i, &b->step_cap, 5 * n))) return rc; // state, action, s', o, terminal
+    if ((rc = stage_buf(ctx, &b->step_r, &b->step_cap_r, n))) return rc;
+    int *d_s = b->step_i, *d_a = b->step_i + n, *d_s2 = b->step_i + 2 * n, *d_o = b->step_i + 3 * n,
+        *d_t = b->step_i + 4 * n;
+    CU(ctx, cudaMemcpyAsync(b->roll_p, particle, n * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(d_s, state, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(d_a, action, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    int tpb = kThreads;
+    while (tpb > 32 && (n + tpb - 1) / tpb < 2ll * ctx->sm_count) tpb >>= 1;
+    LAUNCH_RL(ctx, k_step_batch, false, b->m->long_rows, blocks_for(n, tpb), tpb, D, b->counts[b->cur], b->stride,
+              b->sid[b->cur], (long long)n, b->roll_p, d_s, d_a, philox_args(rng), d_s2, d_o, b->step_r, d_t,
+              ctx->d_flag);
+    CU(ctx, cudaMemcpyAsync(new_state, d_s2, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(observation, d_o, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(terminal, d_t, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(reward, b->step_r, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
     return FBA_OK;
 }
 

@@ -827,6 +827,72 @@ __global__ void __launch_bounds__(kThreads)
 }
 
 // ------------------------------------------------------------------------------------------------
+// planner support: n independent single steps (BAPOMDP::step in KeepCounts mode, BAPOMDP.cpp:111-143)
+// from given (particle, domain state, action) triples — the in-tree steps of a wave of POMCP
+// simulations (RBAPOUCT::traverseChanceNode, RBAPOUCT.cpp:249). One thread per request.
+// ------------------------------------------------------------------------------------------------
+template<bool REPLAY, bool LONG>
+__global__ void __launch_bounds__(kThreads)
+    k_step_batch(DevModel M, const float* counts, long long stride, const int* __restrict__ sid, long long n,
+                 const long long* __restrict__ particle, const int* __restrict__ state,
+                 const int* __restrict__ action, RngArgs ra, int* __restrict__ new_state,
+                 int* __restrict__ obs, double* __restrict__ reward, int* __restrict__ terminal,
+                 int* __restrict__ overrun)
+{
+    long long const r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    auto g            = RngOf<REPLAY>::make(ra, r);
+    long long const p = particle[r];
+    float* c          = const_cast<float*>(counts) + p * stride; // STEP_KEEP never writes
+    int const a       = action[r];
+    const Node* nodes = M.nodes + ((long long)sid[p] * M.A + a) * M.J;
+    int o;
+    Feat x2;
+    int const s  = state[r];
+    int const s2 = hyper_step<STEP_KEEP, decltype(g), false, LONG>(M, nodes, c, s, g, o, x2, nullptr);
+    bool term;
+    reward[r]    = domain_reward(M, s, a, s2, term);
+    new_state[r] = s2;
+    obs[r]       = o;
+    terminal[r]  = term ? 1 : 0;
+    if (g.overrun) *overrun = 1;
+}
+
+__global__ void __launch_bounds__(kThreads)
+    k_gather_states(const int* __restrict__ state, const long long* __restrict__ idx, long long n,
+                    int* __restrict__ out)
+{
+    long long const j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) out[j] = state[idx[j]];
+}
+
+// Belief::sample x n in one launch (native mode): weighted beliefs draw from the cdf, flat ones
+// uniformly
+__global__ void __launch_bounds__(kThreads)
+    k_sample_batch(const double* __restrict__ cdf, long long N, long long n, RngArgs ra,
+                   long long* __restrict__ out)
+{
+    long long const j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    auto g = RngOf<false>::make(ra, j);
+    if (!cdf)
+    {
+        out[j] = draw_k(g, (uint32_t)N);
+        return;
+    }
+    double const thr = draw_u(g) * cdf[N - 1];
+    long long lo = 0, hi = N - 1;
+    while (lo < hi)
+    {
+        long long const mid = (lo + hi) >> 1;
+        if (cdf[mid] > thr) hi = mid;
+        else
+            lo = mid + 1;
+    }
+    out[j] = lo;
+}
+
+// ------------------------------------------------------------------------------------------------
 // rejection sampling (RejectionSampling.hpp:26-72) as waves of independent attempts:
 // attempt t picks a particle uniformly, simulates a step on it WITHOUT touching it and records the
 // outcome; the accepted attempts, in attempt order, become the new particles.

@@ -561,6 +561,9 @@ public:
         }
     }
 
+    fba_belief* handle() const { return _b[0]; }
+    CudaSimulator const& cuda() const { return *_cuda; }
+
 private:
     size_t _size, _amount;
     int _mutate, _device;

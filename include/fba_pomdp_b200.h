@@ -211,6 +211,19 @@ int fba_rollouts(fba_belief* b, int64_t n, const int64_t* particle, const int32_
                  const int32_t* depth, double discount, fba_rng* rng, const int64_t* word_offset,
                  double* returns);
 
+/* ---- planner support (wave-parallel POMCP on the host, its simulator calls batched on the GPU) ---- */
+/* n x Belief::sample (Belief.hpp:34) in one launch: the root particles of n simulations
+ * (RBAPOUCT.cpp:92). PHILOX mode. indices: n host int64. */
+int fba_belief_sample_batch(fba_belief* b, fba_rng* rng, int64_t n, int64_t* indices);
+/* the domain states of n particles (BAState::_domain_state, src/bayes-adaptive/states/BAState.hpp:20) */
+int fba_belief_gather_states(fba_belief* b, int64_t n, const int64_t* indices, int32_t* states);
+/* n x BAPOMDP::step in KeepCounts mode (BAPOMDP.cpp:111-143) from (particle, domain state, action):
+ * the in-tree steps of a wave of simulations (RBAPOUCT::traverseChanceNode, RBAPOUCT.cpp:249).
+ * Outputs (host, n each): new domain state, observation, reward, terminal flag. PHILOX mode. */
+int fba_step_batch(fba_belief* b, int64_t n, const int64_t* particle, const int32_t* state,
+                   const int32_t* action, fba_rng* rng, int32_t* new_state, int32_t* observation,
+                   double* reward, int32_t* terminal);
+
 /* ---- multi-GPU phases (one process per GPU; the host runs the collective between them) ---- */
 /* phase 1: step + weight, no normalisation; *local_total = this shard's weight sum. With
  * local_total == NULL the call only enqueues work: the total is then the first double at

@@ -60,6 +60,7 @@
 // the C++ host adapters of this repo (the drop-in beliefs), compiled against the reference here
 #define FBA_B200_PRIVATE_ACCESS
 #include "CudaBeliefs.hpp"
+#include "CudaPlanner.hpp"
 #include "environment/Discount.hpp"
 #include "environment/Horizon.hpp"
 #include "environment/Return.hpp"
@@ -627,7 +628,16 @@ int ref_adapter_episodes(void* hv, int kind, long n, char const* planner, int si
         conf.planner                             = planner;
         conf.planner_conf.mcts_simulation_amount = sims;
         conf.planner_conf.mcts_max_depth         = conf.horizon;
-        auto plan = factory::makeBAPlanner(conf);
+        // planner "cuda-po-uct[:wave]" = this repo's wave-parallel POMCP over the C ABI
+        std::unique_ptr<Planner> plan;
+        if (conf.planner.rfind("cuda-po-uct", 0) == 0)
+        {
+            int wave = 64;
+            auto pos = conf.planner.find(':');
+            if (pos != std::string::npos) wave = std::stoi(conf.planner.substr(pos + 1));
+            plan.reset(new fba_b200::CudaBatchedPOUCT(conf, wave));
+        } else
+            plan = factory::makeBAPlanner(conf);
 
         std::unique_ptr<beliefs::BABelief> belief;
         if (kind == 0) belief.reset(new beliefs::BAImportanceSampling(n));

@@ -39,3 +39,34 @@ def test_reference_episode_loop_with_cuda_belief(domain, kw, kinds, n, episodes)
     assert np.all(np.isfinite(ours))
     se = np.sqrt(ref.var(ddof=1) / len(ref) + ours.var(ddof=1) / len(ours)) + 1e-9
     assert abs(ref.mean() - ours.mean()) <= 4.0 * se + 1e-6, (ref.mean(), ours.mean(), se)
+
+
+PLANNER_CASES = [
+    # domain, kwargs, particles, episodes, simulations, wave
+    ("episodic-tiger", dict(), 512, 150, 128, 8),
+    ("gridworld", dict(size=3), 64, 40, 128, 16),
+    ("centered-collision-avoidance", dict(size=1, width=3, height=3, factored=True), 128, 60, 128, 16),
+    ("linear-sysadmin", dict(size=3, factored=True), 64, 30, 128, 16),
+]
+
+
+@pytest.mark.parametrize("domain,kw,n,episodes,sims,wave", PLANNER_CASES)
+def test_reference_episode_loop_with_cuda_planner(domain, kw, n, episodes, sims, wave):
+    """fba_b200::CudaBatchedPOUCT (wave-parallel POMCP, simulator steps and leaf rollouts batched on
+    the GPU) + the CUDA belief, inside the reference's own episode::run, against the reference's
+    RBAPOUCT + BAImportanceSampling: mean episode returns agree within 4 standard errors, and the
+    planner is clearly better than acting at random."""
+    horizon = 8
+    r = pyref.Ref(domain, horizon=horizon, seed="11", **kw)
+    try:
+        ref = r.adapter_episodes(0, n, "po-uct", sims, episodes)
+        ours = r.adapter_episodes(1, n, "cuda-po-uct:%d" % wave, sims, episodes)
+        rand = r.adapter_episodes(0, n, "random", sims, episodes)
+    finally:
+        r.close()
+    assert np.all(np.isfinite(ours))
+    se = np.sqrt(ref.var(ddof=1) / len(ref) + ours.var(ddof=1) / len(ours)) + 1e-9
+    assert abs(ref.mean() - ours.mean()) <= 4.0 * se + 1e-6, (ref.mean(), ours.mean(), se)
+    if domain in ("episodic-tiger", "centered-collision-avoidance"):
+        # planning matters in these two at this horizon: both planners beat the random policy
+        assert ours.mean() > rand.mean() and ref.mean() > rand.mean(), (ours.mean(), ref.mean(), rand.mean())
