@@ -65,6 +65,8 @@ def lib():
         L.ref_adapter_episodes.restype = C.c_int
         L.ref_adapter_episodes.argtypes = [C.c_void_p, C.c_int, C.c_long, C.c_char_p, C.c_int, C.c_int,
                                            C.c_void_p]
+        L.ref_plan_seconds.restype = C.c_double
+        L.ref_plan_seconds.argtypes = [C.c_void_p, C.c_int, C.c_long, C.c_char_p, C.c_int, C.c_int]
         _lib = L
     return _lib
 
@@ -195,3 +197,10 @@ class Ref:
         if self.L.ref_adapter_episodes(self.h, kind, n, planner.encode(), sims, episodes, _p(out)):
             raise RuntimeError("reference/adapter: " + self.L.ref_error(self.h).decode())
         return out
+
+    def plan_seconds(self, kind, n, planner, sims, reps=3):
+        """Seconds per Planner::selectAction with `sims` simulations (empty history)."""
+        v = self.L.ref_plan_seconds(self.h, kind, n, planner.encode(), sims, reps)
+        if v < 0:
+            raise RuntimeError("reference/adapter: " + self.L.ref_error(self.h).decode())
+        return v

@@ -24,6 +24,7 @@
 //
 // Built with -fno-access-control (this TU only) so private filters can be dumped.
 
+#include <chrono>
 #include <cstdint>
 #include <cstring>
 #include <memory>
@@ -679,6 +680,55 @@ int ref_adapter_episodes(void* hv, int kind, long n, char const* planner, int si
         return 1;
     }
     return 0;
+}
+
+
+// seconds per Planner::selectAction (empty history) with `sims` simulations, belief kind as in
+// ref_adapter_episodes, planner "po-uct" (the reference's RBAPOUCT) or "cuda-po-uct[:wave]".
+double ref_plan_seconds(void* hv, int kind, long n, char const* planner, int sims, int reps)
+{
+    auto h = static_cast<Handle*>(hv);
+    try
+    {
+        auto conf                                = h->conf;
+        conf.planner                             = planner;
+        conf.planner_conf.mcts_simulation_amount = sims;
+        conf.planner_conf.mcts_max_depth         = conf.horizon;
+        std::unique_ptr<Planner> plan;
+        if (conf.planner.rfind("cuda-po-uct", 0) == 0)
+        {
+            int wave = 64;
+            auto pos = conf.planner.find(':');
+            if (pos != std::string::npos) wave = std::stoi(conf.planner.substr(pos + 1));
+            plan.reset(new fba_b200::CudaBatchedPOUCT(conf, wave));
+        } else
+            plan = factory::makeBAPlanner(conf);
+        std::unique_ptr<beliefs::BABelief> belief;
+        if (kind == 0) belief.reset(new beliefs::BAImportanceSampling(n));
+        else
+            belief.reset(new fba_b200::CudaBAImportanceSampling(n));
+        belief->initiate(*h->sim);
+        History hist;
+        auto warm = plan->selectAction(*h->sim, *belief, hist);
+        h->sim->releaseAction(warm);
+        auto t0 = std::chrono::steady_clock::now();
+        for (int r = 0; r < reps; ++r)
+        {
+            auto a = plan->selectAction(*h->sim, *belief, hist);
+            h->sim->releaseAction(a);
+        }
+        double const dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        belief->free(*h->sim);
+        return dt / reps;
+    } catch (std::string const& e)
+    {
+        h->err = e;
+        return -1;
+    } catch (char const* e)
+    {
+        h->err = e;
+        return -1;
+    }
 }
 
 } // extern "C"
