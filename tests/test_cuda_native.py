@@ -220,3 +220,48 @@ def test_shard_plan_matches_python(ctx):
         assert rc == 0
     b.free()
     sim.close()
+
+
+@pytest.mark.parametrize("name,n", [("ftiger_mu", 100_000), ("gridworld3", 1_000_000), ("ca", 1_000_000)])
+def test_full_size_properties_other_configs(ctx, name, n):
+    """BASELINE sizes of configs 2-4 (heterogeneous structures included): after every update the
+    weights are a distribution, states are in range, probed count blocks grew by exactly FS+FO per
+    update; after the in-place resample the weights are uniform and each structure's share of the
+    belief only moved by what resampling can do (no particle lost or invented: structure ids stay
+    within the prior's set)."""
+    import fba_pomdp_b200 as fba
+    g = G.load(name)
+    sim = fba.BAPOMDP(ctx, g.desc, g.t_par, g.o_par)
+    sid, counts = g["is/init_struct_id"], g["is/init_counts"]
+    keys, psid, pc = {}, [], []
+    for i in range(len(sid)):
+        k = (int(sid[i]), counts[i].tobytes())
+        if k not in keys:
+            keys[k] = len(psid)
+            psid.append(int(sid[i]))
+            pc.append(counts[i])
+    pc = np.stack(pc)
+    base = {s: float(c.astype(np.float64).sum()) for s, c in zip(psid, pc)}
+    assert len(set(psid)) == len(psid)  # one prototype per structure in these priors
+    b = fba.BAImportanceSampling(n)
+    rng = fba.Rng.philox(9)
+    b.initiate_sampled(sim, np.array(psid, np.int32), pc, np.ones(len(psid)), rng, stride=pc.shape[1])
+    J = sim.FS + sim.FO
+    script = [(int(a), int(o)) for a, o, f in zip(g.a, g.o, g.flags) if not (f & 1)]
+    probe = np.unique(np.random.RandomState(1).randint(0, n, 24))
+    for t in range(3):
+        a, o = script[t % len(script)]
+        lik = b.update(a, o, rng)
+        assert 0.0 < lik <= 1.0
+        d = b.download(counts=False)
+        assert abs(d["w"].sum() - 1.0) < 1e-9 and d["w"].min() >= 0.0
+        assert d["state"].min() >= 0 and d["state"].max() < sim.S
+        b.resample(rng)
+        d = b.download(counts=False)
+        np.testing.assert_array_equal(d["w"], np.full(n, 1.0 / n))
+        assert set(np.unique(d["struct_id"])) <= set(psid)
+        for i in probe:
+            p = b.download(int(i), 1)
+            assert p["counts"][0].astype(np.float64).sum() == base[int(p["struct_id"][0])] + J * (t + 1)
+    b.free()
+    sim.close()

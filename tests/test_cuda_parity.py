@@ -201,3 +201,55 @@ def test_reinvigoration_replay(ctx, name):
 def test_smoke_entry():
     import __graft_entry__ as ge
     ge.smoke()
+
+
+@pytest.mark.parametrize("name,n", [("tiger", 5000), ("tiger", 20000), ("sysadmin", 6000), ("ca", 4100),
+                                    ("gridworld3", 3000)])
+def test_replay_vs_oracle_beyond_fixture_sizes(ctx, name, n):
+    """CUDA vs the CPU oracle on seeded streams at particle counts the fixtures do not reach — in
+    particular several chunks of the sequential weight chains (k_seq_normalize stages 2048 weights at
+    a time) and heterogeneous structures. Three update+resample rounds: bit-identical states,
+    weights, likelihood, _total_weight and count blocks."""
+    import fba_pomdp_b200 as fba
+    import pyoracle as O
+    g = G.load(name)
+    m = O.Model(g.desc)
+    st = O.Structs(m, g.t_par, g.o_par)
+    rs = np.random.RandomState(n)
+    idx = rs.randint(0, len(g["is/init_state"]), n)
+    counts0 = g["is/init_counts"][idx]
+    sid0 = g["is/init_struct_id"][idx]
+    state0 = rs.randint(0, m.S, n).astype(np.int32)
+
+    ob = O.Belief(n, counts0.shape[1])
+    ob.counts[:], ob.state[:], ob.struct_id[:] = counts0, state0, sid0
+    ob.total_weight = O.sequential_uniform_total(n)
+
+    sim = make_sim(ctx, g)
+    b = fba.BAImportanceSampling(n)
+    b.initiate(sim, struct_id=sid0, counts=counts0, state=state0, stride=counts0.shape[1])
+    J = m.FS + m.FO
+    script = [(int(a), int(o)) for a, o, f in zip(g.a, g.o, g.flags) if not (f & 1)]
+    for t in range(3):
+        a, o = script[t % len(script)]
+        words = rs.randint(0, 2**32, size=2 * J * n + 2 * n, dtype=np.uint64).astype(np.uint32)
+        orng = O.Rng(words)
+        lik_ref = O.is_update(m, st, ob, a, o, orng)
+        rng = fba.Rng.replay(words)
+        lik = b.update(a, o, rng)
+        assert rng.cursor == orng.cur
+        d = b.download()
+        assert lik == lik_ref and d["total_weight"] == ob.total_weight
+        np.testing.assert_array_equal(d["state"], ob.state)
+        np.testing.assert_array_equal(d["w"], ob.w)
+        assert_counts_equal(d["counts"], ob.counts)
+        ob, anc = O.is_resample(ob, orng)
+        b.resample(rng)
+        assert rng.cursor == orng.cur and rng.exhausted
+        d = b.download()
+        np.testing.assert_array_equal(d["state"], ob.state)
+        np.testing.assert_array_equal(d["struct_id"], ob.struct_id)
+        assert_counts_equal(d["counts"], ob.counts)
+        assert d["total_weight"] == ob.total_weight
+    b.free()
+    sim.close()
