@@ -120,6 +120,7 @@ class BAPOMDP:
         for i, v in enumerate(np.asarray(d.get("start_ip", []), np.int32).reshape(-1)[:4]):
             md.start_ip[i] = int(v)
         md.start_total = float(d.get("start_total", 0.0))
+        md.delta_capacity = int(d.get("delta_capacity", 0))
         self.S, self.A, self.O, self.FS, self.FO = md.S, md.A, md.O, len(fs), len(fo)
         t_par = np.ascontiguousarray(t_par, np.uint32).reshape(-1, self.A * self.FS)
         o_par = np.ascontiguousarray(o_par, np.uint32).reshape(-1, self.A * self.FO)

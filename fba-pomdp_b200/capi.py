@@ -51,6 +51,7 @@ class ModelDesc(C.Structure):
         ("term_as2", C.c_void_p),
         ("action_draw", C.c_int32), ("start_kind", C.c_int32), ("start_ip", C.c_int32 * 4),
         ("start_values", C.c_void_p), ("start_total", C.c_double), ("start_table", C.c_void_p),
+        ("delta_capacity", C.c_int32),
     ]
 
 

@@ -51,6 +51,7 @@ struct fba_model
     DevModel dev{};
     int max_structs = 0, n_structs = 0;
     bool long_rows = false; // some feature has more than 4 values: kernels load rows in chunks
+    int delta_cap  = 0;     // > 0: tabular base+delta storage with this many increments per particle
     std::vector<uint32_t> t_par, o_par; // host structure table
     std::vector<int> sizes;
     std::vector<Node> h_nodes;
@@ -64,8 +65,14 @@ struct fba_belief
 {
     fba_ctx* ctx   = nullptr;
     fba_model* m   = nullptr;
-    long long N    = 0, stride = 0;
+    long long N    = 0, stride = 0; // stride: PHYSICAL floats per particle block
+    long long lstride = 0;          // logical (dense) cells per particle, what the API calls "stride"
     bool weighted  = true;
+    // base+delta storage: the dense tables of the prior prototypes, shared by all particles
+    int delta_cap     = 0;
+    float* base       = nullptr;
+    int n_bases       = 0;
+    std::vector<float> h_base;
     float* counts[2] = {nullptr, nullptr};
     int* state[2]    = {nullptr, nullptr};
     int* sid[2]      = {nullptr, nullptr};
@@ -380,6 +387,11 @@ static int check_flag(fba_ctx* ctx)
 {
     CU(ctx, cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (*ctx->h_flag == 2)
+    {
+        ctx->err = "base+delta particle ran out of increment slots (raise fba_model_desc.delta_capacity)";
+        return FBA_ERR_CAPACITY;
+    }
     if (*ctx->h_flag)
     {
         ctx->err = "replay stream underrun on device";
@@ -452,10 +464,15 @@ extern "C" int fba_model_create(fba_ctx* ctx, const fba_model_desc* d, int32_t m
     REQUIRE(ctx, ps == d->S && po == d->O, "model: feature sizes do not multiply to S / O");
     REQUIRE(ctx, !d->tabular || (d->n_state_features == 1 && d->n_obs_features == 1),
             "model: tabular models have exactly one state and one observation feature");
+    REQUIRE(ctx, d->delta_capacity >= 0, "model: negative delta_capacity");
+    REQUIRE(ctx, d->delta_capacity == 0 || d->tabular, "model: base+delta storage is for tabular models");
+    REQUIRE(ctx, d->delta_capacity == 0 || (d->S <= kMaxDeltaRow && d->O <= kMaxDeltaRow),
+            "model: base+delta storage supports rows of at most " + std::to_string(kMaxDeltaRow) + " cells");
 
     auto m         = new fba_model();
     m->ctx         = ctx;
     m->max_structs = max_structures;
+    m->delta_cap   = d->delta_capacity;
     DevModel& D    = m->dev;
     D.S = d->S, D.A = d->A, D.O = d->O;
     D.FS = d->n_state_features, D.FO = d->n_obs_features, D.J = D.FS + D.FO;
@@ -634,13 +651,21 @@ extern "C" int fba_belief_create(fba_ctx* ctx, fba_model* m, int64_t N, int64_t 
     if (stride <= 0) stride = need;
     stride = (stride + 3) & ~3ll;
     REQUIRE(ctx, stride >= need, "belief: stride smaller than the largest registered structure");
+    long long const lstride = stride;
+    if (m->delta_cap > 0)
+    {
+        REQUIRE(ctx, m->n_structs == 1, "belief: base+delta storage needs exactly one (tabular) structure");
+        stride = ((long long)m->delta_cap + 1 + 3) & ~3ll; // header + increments, in 4-byte words
+    }
     CU(ctx, cudaSetDevice(ctx->device));
 
-    auto b      = new fba_belief();
-    b->ctx      = ctx;
-    b->m        = m;
-    b->N        = N;
-    b->stride   = stride;
+    auto b       = new fba_belief();
+    b->ctx       = ctx;
+    b->m         = m;
+    b->N         = N;
+    b->stride    = stride;
+    b->lstride   = lstride;
+    b->delta_cap = m->delta_cap;
     b->weighted = weighted != 0;
     cudaError_t e = cudaSuccess;
     for (int k = 0; k < 2 && e == cudaSuccess; ++k)
@@ -688,6 +713,7 @@ extern "C" void fba_belief_destroy(fba_belief* b)
         cudaFree(b->state[k]);
         cudaFree(b->sid[k]);
     }
+    cudaFree(b->base);
     cudaFree(b->w), cudaFree(b->aux), cudaFree(b->tile), cudaFree(b->scal), cudaFree(b->anc);
     cudaFree(b->att_src), cudaFree(b->att_state), cudaFree(b->att_accept), cudaFree(b->att_pos);
     cudaFree(b->roll_p), cudaFree(b->roll_s), cudaFree(b->roll_d), cudaFree(b->roll_r);
@@ -705,7 +731,7 @@ extern "C" int64_t fba_belief_size(const fba_belief* b)
 }
 extern "C" int64_t fba_belief_stride(const fba_belief* b)
 {
-    return b ? b->stride : 0;
+    return b ? b->lstride : 0;
 }
 extern "C" void* fba_belief_counts_ptr(fba_belief* b)
 {
@@ -744,6 +770,20 @@ static void weights_became_uniform(fba_belief* b)
     b->cdf_valid    = false;
 }
 
+// base+delta storage: the prior prototypes become the shared base tables
+static int install_base_tables(fba_belief* b, int n_protos, const float* proto_counts)
+{
+    fba_ctx* ctx = b->ctx;
+    size_t const n = (size_t)n_protos * b->lstride;
+    cudaFree(b->base);
+    b->base = nullptr;
+    CU(ctx, cudaMalloc(&b->base, n * sizeof(float)));
+    CU(ctx, cudaMemcpyAsync(b->base, proto_counts, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    b->h_base.assign(proto_counts, proto_counts + n);
+    b->n_bases = n_protos;
+    return FBA_OK;
+}
+
 extern "C" int fba_belief_init(fba_belief* b, int32_t n_protos, const int32_t* proto_struct_id,
                                const float* proto_counts, const int32_t* particle_proto,
                                const int32_t* particle_state)
@@ -756,20 +796,34 @@ extern "C" int fba_belief_init(fba_belief* b, int32_t n_protos, const int32_t* p
         REQUIRE(ctx, proto_struct_id[p] >= 0 && proto_struct_id[p] < b->m->n_structs,
                 "belief_init: unknown structure id");
     CU(ctx, cudaSetDevice(ctx->device));
+    if (particle_proto)
+        for (long long i = 0; i < b->N; ++i)
+            REQUIRE(ctx, particle_proto[i] >= 0 && particle_proto[i] < n_protos, "belief_init: bad prototype index");
     float* d_protos = nullptr;
     int *d_psid = nullptr, *d_pp = nullptr, *d_ps = nullptr;
-    size_t const pc = (size_t)n_protos * b->stride;
-    CU(ctx, cudaMalloc(&d_protos, pc * sizeof(float)));
-    CU(ctx, cudaMalloc(&d_psid, n_protos * sizeof(int)));
+    size_t const pc = (size_t)n_protos * b->lstride;
     CU(ctx, cudaMalloc(&d_ps, (size_t)b->N * sizeof(int)));
-    CU(ctx, cudaMemcpyAsync(d_protos, proto_counts, pc * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    CU(ctx, cudaMemcpyAsync(d_psid, proto_struct_id, n_protos * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     CU(ctx, cudaMemcpyAsync(d_ps, particle_state, (size_t)b->N * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     if (particle_proto)
     {
         CU(ctx, cudaMalloc(&d_pp, (size_t)b->N * sizeof(int)));
         CU(ctx, cudaMemcpyAsync(d_pp, particle_proto, (size_t)b->N * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     }
+    if (b->delta_cap > 0)
+    {
+        int const rc = install_base_tables(b, n_protos, proto_counts);
+        if (rc) return rc;
+        LAUNCH(ctx, k_init_delta, blocks_for(b->N), kThreads, b->counts[b->cur], b->stride, b->state[b->cur],
+               b->sid[b->cur], b->weighted ? b->w : nullptr, b->N, d_pp, d_ps);
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(d_pp), cudaFree(d_ps);
+        weights_became_uniform(b);
+        return FBA_OK;
+    }
+    CU(ctx, cudaMalloc(&d_protos, pc * sizeof(float)));
+    CU(ctx, cudaMalloc(&d_psid, n_protos * sizeof(int)));
+    CU(ctx, cudaMemcpyAsync(d_protos, proto_counts, pc * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(d_psid, proto_struct_id, n_protos * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     LAUNCH(ctx, k_init_from_protos, stream_grid(ctx, b->N), kThreads, b->counts[b->cur], b->stride,
            b->state[b->cur], b->sid[b->cur], b->weighted ? b->w : nullptr, b->N, d_protos, d_psid, d_pp,
            d_ps);
@@ -790,7 +844,7 @@ extern "C" int fba_belief_init_sampled(fba_belief* b, int32_t n_protos, const in
     float* d_protos = nullptr;
     int *d_psid = nullptr, *d_pp = nullptr, *d_ps = nullptr;
     double* d_cdf   = nullptr;
-    size_t const pc = (size_t)n_protos * b->stride;
+    size_t const pc = (size_t)n_protos * b->lstride;
     CU(ctx, cudaMalloc(&d_protos, pc * sizeof(float)));
     CU(ctx, cudaMalloc(&d_psid, n_protos * sizeof(int)));
     CU(ctx, cudaMalloc(&d_pp, (size_t)b->N * sizeof(int)));
@@ -808,6 +862,18 @@ extern "C" int fba_belief_init_sampled(fba_belief* b, int32_t n_protos, const in
     }
     LAUNCH(ctx, k_draw_init<false>, blocks_for(b->N), kThreads, b->m->dev, b->N, n_protos, d_cdf, d_pp,
            d_ps, philox_args(rng));
+    if (b->delta_cap > 0)
+    {
+        int const rc = install_base_tables(b, n_protos, proto_counts);
+        if (rc) return rc;
+        LAUNCH(ctx, k_init_delta, blocks_for(b->N), kThreads, b->counts[b->cur], b->stride, b->state[b->cur],
+               b->sid[b->cur], b->weighted ? b->w : nullptr, b->N, d_pp, d_ps);
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(d_protos), cudaFree(d_psid), cudaFree(d_pp), cudaFree(d_ps), cudaFree(d_cdf);
+        b->total_weight = 1.0;
+        b->suffix_valid = b->cdf_valid = false;
+        return FBA_OK;
+    }
     LAUNCH(ctx, k_init_from_protos, stream_grid(ctx, b->N), kThreads, b->counts[b->cur], b->stride,
            b->state[b->cur], b->sid[b->cur], b->weighted ? b->w : nullptr, b->N, d_protos, d_psid, d_pp,
            d_ps);
@@ -827,6 +893,8 @@ extern "C" int fba_belief_upload(fba_belief* b, int64_t first, int64_t count, co
     CU(ctx, cudaSetDevice(ctx->device));
     if (state)
         CU(ctx, cudaMemcpyAsync(b->state[b->cur] + first, state, count * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    REQUIRE(ctx, !(b->delta_cap > 0 && (counts || struct_id)),
+            "belief_upload: base+delta beliefs take their counts from fba_belief_init prototypes");
     if (struct_id)
     {
         for (int64_t i = 0; i < count; ++i)
@@ -869,12 +937,35 @@ extern "C" int fba_belief_download(fba_belief* b, int64_t first, int64_t count, 
         CU(ctx, cudaMemcpyAsync(state, b->state[b->cur] + first, count * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     if (sid_host)
         CU(ctx, cudaMemcpyAsync(sid_host, b->sid[b->cur] + first, count * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    if (counts)
+    std::vector<int> blocks;
+    if (counts && b->delta_cap > 0)
+    {
+        blocks.resize((size_t)count * b->stride);
+        CU(ctx, cudaMemcpyAsync(blocks.data(), b->counts[b->cur] + first * b->stride,
+                                (size_t)count * b->stride * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    } else if (counts)
         CU(ctx, cudaMemcpyAsync(counts, b->counts[b->cur] + first * b->stride,
                                 (size_t)count * b->stride * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     if (w && b->weighted)
         CU(ctx, cudaMemcpyAsync(w, b->w + first, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (counts && b->delta_cap > 0)
+    { // dense view = the particle's base table + its increments, each exactly +1.0f in time order
+        for (int64_t i = 0; i < count; ++i)
+        {
+            float* out = counts + i * b->lstride;
+            memcpy(out, b->h_base.data() + (size_t)sid_host[i] * b->lstride, (size_t)b->lstride * sizeof(float));
+            const int* blk = blocks.data() + (size_t)i * b->stride;
+            for (int e = 1; e <= blk[0]; ++e)
+            {
+                volatile float v = out[blk[e]];
+                v                = v + 1.0f;
+                out[blk[e]]      = v;
+            }
+            if (struct_id) struct_id[i] = 0; // the only (tabular) structure; sid holds the base table id
+        }
+        return FBA_OK;
+    }
     if (counts)
     { // cells past a particle's own structure are padding: report zeros (copies skip them)
         for (int64_t i = 0; i < count; ++i)
@@ -905,6 +996,24 @@ static int propose(fba_belief* b, int a, int o, fba_rng* rng, unsigned long long
     REQUIRE(ctx, o >= 0 && o < D.O, "observation out of range");
     CU(ctx, cudaSetDevice(ctx->device));
     int rc;
+    if (b->delta_cap > 0)
+    {
+        if (rng->mode == FBA_RNG_REPLAY)
+        {
+            long long const per = 2ll * D.J, need = per * b->N;
+            if ((rc = stage_words(ctx, rng, need))) return rc;
+            if ((rc = clear_flag(ctx))) return rc;
+            LAUNCH(ctx, k_propose_delta<true>, blocks_for(b->N), kThreads, D, b->base, b->lstride, b->counts[b->cur],
+                   b->stride, b->delta_cap, b->state[b->cur], b->sid[b->cur], b->w, b->N, a, o,
+                   replay_args(ctx, need, per, false), ctx->d_flag);
+            rng->cursor += need;
+        } else
+            LAUNCH(ctx, k_propose_delta<false>, blocks_for(b->N), kThreads, D, b->base, b->lstride,
+                   b->counts[b->cur], b->stride, b->delta_cap, b->state[b->cur], b->sid[b->cur], b->w, b->N, a, o,
+                   philox_args(rng, stream_base), ctx->d_flag);
+        b->suffix_valid = b->cdf_valid = false;
+        return FBA_OK;
+    }
     if (rng->mode == FBA_RNG_REPLAY)
     {
         // particle-major: particle i consumes J uniforms = 2J words (SURVEY.md §8 a')
@@ -1014,7 +1123,8 @@ static int gather_into_next(fba_belief* b, long long n_out, bool copy_state)
     int const nx = b->cur ^ 1;
     LAUNCH(ctx, k_gather, stream_grid(ctx, n_out), kThreads, b->counts[b->cur], b->counts[nx], b->stride,
            b->state[b->cur], copy_state ? b->state[nx] : nullptr, b->sid[b->cur], b->sid[nx],
-           b->m->d_sizes, b->weighted ? b->w : nullptr, 1.0 / (double)b->N, b->anc, n_out);
+           b->m->d_sizes, b->weighted ? b->w : nullptr, 1.0 / (double)b->N, b->anc, n_out,
+           b->delta_cap > 0 ? 1 : 0);
     return FBA_OK;
 }
 
@@ -1054,7 +1164,7 @@ static int resample_inplace(fba_belief* b, fba_rng* rng, long long n_out, const 
     LAUNCH(ctx, k_copy_inplace, stream_grid(ctx, b->N), kThreads, b->counts[b->cur], b->stride,
            b->state[b->cur], b->sid[b->cur], b->m->d_sizes, b->escan, b->src_of, b->N, b->dead, b->totals,
            b->xport, rb, b->xport_cap, b->stats, b->src_cap, p2p ? b->d_plan : (const long long*)nullptr,
-           b->p2p_ranks, b->p2p_rank, b->peers);
+           b->p2p_ranks, b->p2p_rank, b->peers, b->delta_cap > 0 ? 1 : 0);
     LAUNCH(ctx, k_fill, blocks_for(b->N), kThreads, b->w, b->N, 1.0 / (double)b->N);
     b->total_weight = 1.0;
     b->suffix_valid = b->cdf_valid = false;
@@ -1279,13 +1389,25 @@ extern "C" int fba_belief_reject_sample(fba_belief* b, int32_t a, int32_t o, fba
             ra.stream_base = (unsigned long long)attempts;
         }
         if ((rc = clear_flag(ctx))) return rc;
-        LAUNCH_RL(ctx, k_rs_attempt, rng->mode == FBA_RNG_REPLAY, b->m->long_rows, blocks_for(wave), kThreads, D,
-                  b->counts[b->cur], b->stride, b->state[b->cur], b->sid[b->cur], b->N, a, o, wave, ra,
-                  b->att_src, b->att_state, b->att_accept, b->att_rec, ctx->d_flag);
+        if (b->delta_cap > 0)
+        {
+            if (rng->mode == FBA_RNG_REPLAY)
+                LAUNCH(ctx, k_rs_attempt_delta<true>, blocks_for(wave), kThreads, D, b->base, b->lstride,
+                       b->counts[b->cur], b->stride, b->state[b->cur], b->sid[b->cur], b->N, a, o, wave, ra,
+                       b->att_src, b->att_state, b->att_accept, b->att_rec, ctx->d_flag);
+            else
+                LAUNCH(ctx, k_rs_attempt_delta<false>, blocks_for(wave), kThreads, D, b->base, b->lstride,
+                       b->counts[b->cur], b->stride, b->state[b->cur], b->sid[b->cur], b->N, a, o, wave, ra,
+                       b->att_src, b->att_state, b->att_accept, b->att_rec, ctx->d_flag);
+        } else
+            LAUNCH_RL(ctx, k_rs_attempt, rng->mode == FBA_RNG_REPLAY, b->m->long_rows, blocks_for(wave), kThreads,
+                      D, b->counts[b->cur], b->stride, b->state[b->cur], b->sid[b->cur], b->N, a, o, wave, ra,
+                      b->att_src, b->att_state, b->att_accept, b->att_rec, ctx->d_flag);
         LAUNCH(ctx, k_scan_flags, 1, kThreads, b->att_accept, wave, b->att_pos, b->d_total);
         LAUNCH(ctx, k_rs_commit, stream_grid(ctx, wave), kThreads, b->counts[b->cur], b->counts[nx], b->stride,
                b->sid[b->cur], b->sid[nx], b->state[nx], b->m->d_sizes, b->N, D.J, wave, b->att_src,
-               b->att_state, b->att_accept, b->att_pos, b->att_rec, accepted);
+               b->att_state, b->att_accept, b->att_pos, b->att_rec, accepted, b->delta_cap > 0 ? 1 : 0,
+               b->delta_cap, ctx->d_flag);
         int got = 0;
         CU(ctx, cudaMemcpyAsync(&got, b->d_total, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         if ((rc = check_flag(ctx))) return rc; // synchronises
@@ -1353,7 +1475,7 @@ extern "C" int fba_belief_reinvigorate(fba_belief* b, fba_belief* fc, int64_t am
     DevModel const& D = m->dev;
     REQUIRE(ctx, fc->m == m, "reinvigorate: both beliefs must share one model");
     REQUIRE(ctx, amount >= 1, "reinvigorate: resample size of < 1 (" + std::to_string(amount) + ")");
-    REQUIRE(ctx, !D.tabular, "reinvigorate: factored models only");
+    REQUIRE(ctx, !D.tabular && b->delta_cap == 0, "reinvigorate: factored models only");
     CU(ctx, cudaSetDevice(ctx->device));
 
     // host mirrors of the small per-particle arrays the sequential part reads
@@ -1528,7 +1650,10 @@ extern "C" int fba_rollouts(fba_belief* b, int64_t n, const int64_t* particle, c
         if ((rc = stage_offsets(ctx, off))) return rc;
         if ((rc = clear_flag(ctx))) return rc;
         RngArgs const ra = replay_args(ctx, avail, 0, true);
-        if (coop) LAUNCH(ctx, (k_rollouts<true, true, false>), blocks_for(n * 32), kThreads, D, b->counts[b->cur],
+        if (b->delta_cap > 0)
+            LAUNCH(ctx, k_rollouts_delta<true>, blocks_for(n, tpb), tpb, D, b->base, b->lstride, b->counts[b->cur],
+                   b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag);
+        else if (coop) LAUNCH(ctx, (k_rollouts<true, true, false>), blocks_for(n * 32), kThreads, D, b->counts[b->cur],
                          b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag);
         else if (b->m->long_rows)
             LAUNCH(ctx, (k_rollouts<true, false, true>), blocks_for(n, tpb), tpb, D, b->counts[b->cur], b->stride,
@@ -1539,7 +1664,10 @@ extern "C" int fba_rollouts(fba_belief* b, int64_t n, const int64_t* particle, c
     } else
     {
         RngArgs const ra = philox_args(rng);
-        if (coop) LAUNCH(ctx, (k_rollouts<false, true, false>), blocks_for(n * 32), kThreads, D, b->counts[b->cur],
+        if (b->delta_cap > 0)
+            LAUNCH(ctx, k_rollouts_delta<false>, blocks_for(n, tpb), tpb, D, b->base, b->lstride, b->counts[b->cur],
+                   b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag);
+        else if (coop) LAUNCH(ctx, (k_rollouts<false, true, false>), blocks_for(n * 32), kThreads, D, b->counts[b->cur],
                          b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag);
         else if (b->m->long_rows)
             LAUNCH(ctx, (k_rollouts<false, false, true>), blocks_for(n, tpb), tpb, D, b->counts[b->cur], b->stride,
@@ -1626,9 +1754,14 @@ extern "C" int fba_step_batch(fba_belief* b, int64_t n, const int64_t* particle,
     CU(ctx, cudaMemcpyAsync(d_a, action, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     int tpb = kThreads;
     while (tpb > 32 && (n + tpb - 1) / tpb < 2ll * ctx->sm_count) tpb >>= 1;
-    LAUNCH_RL(ctx, k_step_batch, false, b->m->long_rows, blocks_for(n, tpb), tpb, D, b->counts[b->cur], b->stride,
-              b->sid[b->cur], (long long)n, b->roll_p, d_s, d_a, philox_args(rng), d_s2, d_o, b->step_r, d_t,
-              ctx->d_flag);
+    if (b->delta_cap > 0)
+        LAUNCH(ctx, k_step_batch_delta<false>, blocks_for(n, tpb), tpb, D, b->base, b->lstride, b->counts[b->cur],
+               b->stride, b->sid[b->cur], (long long)n, b->roll_p, d_s, d_a, philox_args(rng), d_s2, d_o, b->step_r,
+               d_t, ctx->d_flag);
+    else
+        LAUNCH_RL(ctx, k_step_batch, false, b->m->long_rows, blocks_for(n, tpb), tpb, D, b->counts[b->cur],
+                  b->stride, b->sid[b->cur], (long long)n, b->roll_p, d_s, d_a, philox_args(rng), d_s2, d_o,
+                  b->step_r, d_t, ctx->d_flag);
     CU(ctx, cudaMemcpyAsync(new_state, d_s2, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaMemcpyAsync(observation, d_o, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaMemcpyAsync(terminal, d_t, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1990,7 +2123,7 @@ extern "C" int fba_belief_resample_shard(fba_belief* b, int64_t n_offspring, fba
     int const nx = b->cur ^ 1;
     LAUNCH(ctx, k_gather, stream_grid(ctx, kept), kThreads, b->counts[b->cur], b->counts[nx], b->stride,
            b->state[b->cur], b->state[nx], b->sid[b->cur], b->sid[nx], b->m->d_sizes, b->w,
-           1.0 / (double)b->N, anc, kept);
+           1.0 / (double)b->N, anc, kept, b->delta_cap > 0 ? 1 : 0);
     if (surplus > 0)
     {
         long long const rb = fba_belief_record_bytes(b);

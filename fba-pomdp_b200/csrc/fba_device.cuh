@@ -539,6 +539,73 @@ __device__ __forceinline__ double obs_probability(const DevModel& M, const Node*
     }
     return prob;
 }
+// ------------------------------------------------------------------------------------------------
+// Tabular particles stored as SHARED BASE + PRIVATE DELTA (SURVEY.md §7 hard part 4): the dense
+// phi/psi tables of a large tabular model (gridworld 5: 720 KB, gridworld 7: 7.7 MB per particle)
+// cannot be replicated per particle. The reference survives through copy-on-write rows
+// (BAFlatModel.cpp:185-252,284-354); here a particle owns only the list of cells it has incremented:
+//   block[0] = n, block[1..n] = cell index of each +1, in time order
+// and reads a row as base row + its own increments. Every increment is exactly +1.0f
+// (BAFlatModel.cpp:126-141), so applying them one by one reproduces the reference's float adds
+// bit for bit whatever the order.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxDeltaRow = 512; // longest row (S or O) a delta model may have
+
+__device__ __forceinline__ void delta_row(const float* __restrict__ base, const int* block, int cell0, int n,
+                                          float* buf)
+{
+    for (int i = 0; i < n; ++i) buf[i] = base[cell0 + i];
+    int const ne = block[0];
+    for (int e = 1; e <= ne; ++e)
+    {
+        unsigned const c = (unsigned)(block[e] - cell0);
+        if (c < (unsigned)n) buf[c] = __fadd_rn(buf[c], 1.0f);
+    }
+}
+
+// BAPOMDP::step on a delta particle (tabular: one transition node and one observation node per
+// action). overflow is set when the increment list is full (the increments are then dropped).
+template<int MODE, class R>
+__device__ __forceinline__ int hyper_step_delta(const DevModel& M, const Node* __restrict__ nodes,
+                                                const float* __restrict__ base, int* block, int cap, int s,
+                                                R& g, int& o_out, int* rec, int* overflow)
+{
+    float buf[kMaxDeltaRow];
+    int const cell_t = nodes[0].off + s * M.S; // phi[s][a][.]
+    delta_row(base, block, cell_t, M.S, buf);
+    int const s2     = sample_expected_mult<true>(buf, M.S, draw_u(g));
+    int const cell_o = nodes[1].off + s2 * M.O; // psi[a][s'][.]
+    delta_row(base, block, cell_o, M.O, buf);
+    int const o = sample_expected_mult<true>(buf, M.O, draw_u(g));
+    if (MODE == STEP_UPDATE)
+    { // incrementCountsOf(s, a, o, s') (BAFlatModel.cpp:126-141)
+        int const ne = block[0];
+        if (ne + 2 <= cap)
+        {
+            block[1 + ne] = cell_t + s2;
+            block[2 + ne] = cell_o + o;
+            block[0]      = ne + 2;
+        } else
+            *overflow = 2;
+    }
+    if (MODE == STEP_RECORD)
+    {
+        rec[0] = cell_t + s2;
+        rec[1] = cell_o + o;
+    }
+    o_out = o;
+    return s2;
+}
+
+__device__ __forceinline__ double obs_probability_delta(const DevModel& M, const Node* __restrict__ nodes,
+                                                        const float* __restrict__ base, const int* block,
+                                                        int s2, int o)
+{
+    if (M.O == 1) return 1.0; // BAFlatModel.cpp:117-120
+    float buf[kMaxDeltaRow];
+    delta_row(base, block, nodes[1].off + s2 * M.O, M.O, buf);
+    return (double)expected_mult_at(buf, M.O, o);
+}
 #endif // __CUDACC__
 
 } // namespace fba

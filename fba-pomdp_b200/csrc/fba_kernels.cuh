@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(kThreads)
              const int* __restrict__ src_state, int* __restrict__ dst_state,
              const int* __restrict__ src_sid, int* __restrict__ dst_sid,
              const int* __restrict__ struct_size, double* __restrict__ w, double w_new,
-             const int* __restrict__ anc, long long n_out)
+             const int* __restrict__ anc, long long n_out, int delta)
 {
     int const lane        = threadIdx.x & 31;
     long long const warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -140,8 +140,10 @@ __global__ void __launch_bounds__(kThreads)
     {
         long long const i = anc[j];
         int const id      = src_sid[i];
-        // copy only the cells this particle's structure owns (rounded to 16 bytes)
-        int const n_vec = (struct_size[id] + 3) >> 2;
+        // copy only the cells this particle owns (rounded to 16 bytes): its structure's CPTs, or —
+        // base+delta storage — the header and the increments recorded so far
+        int const n_vec = delta ? (reinterpret_cast<const int*>(src + i * stride)[0] + 1 + 3) >> 2
+                                : (struct_size[id] + 3) >> 2;
         warp_copy_block(src + i * stride, dst + j * stride, n_vec, lane);
         if (lane == 0)
         {
@@ -694,7 +696,7 @@ __global__ void __launch_bounds__(kThreads)
                    const int* __restrict__ extra_scan, const int* __restrict__ src_of, long long N,
                    const int* __restrict__ dead_slot, const int* __restrict__ totals, char* __restrict__ xport,
                    long long rec_bytes, long long xport_cap, long long* __restrict__ stats, long long src_cap,
-                   const long long* __restrict__ plan, int n_ranks, int rank, PeerTable peers)
+                   const long long* __restrict__ plan, int n_ranks, int rank, PeerTable peers, int delta)
 {
     long long const n_dead = totals[0];
     long long const n_fill = min(n_dead, (long long)totals[1]); // the rest (if any) is this shard's surplus
@@ -726,7 +728,9 @@ __global__ void __launch_bounds__(kThreads)
         if (k < n_fill)
         {
             long long const j = dead_slot[k];
-            warp_copy_block(counts + i * stride, counts + j * stride, (struct_size[id] + 3) >> 2, lane);
+            int const n_vec   = delta ? (reinterpret_cast<const int*>(counts + i * stride)[0] + 1 + 3) >> 2
+                                      : (struct_size[id] + 3) >> 2;
+            warp_copy_block(counts + i * stride, counts + j * stride, n_vec, lane);
             if (lane == 0)
             {
                 sid[j]   = id;
@@ -982,7 +986,7 @@ __global__ void __launch_bounds__(kThreads)
                 const int* __restrict__ struct_size, long long N, int J, long long n_attempts,
                 const int* __restrict__ att_src, const int* __restrict__ att_state,
                 const int* __restrict__ accept, const int* __restrict__ pos, const int* __restrict__ rec,
-                long long already)
+                long long already, int delta, int delta_cap, int* __restrict__ overflow)
 {
     int const lane        = threadIdx.x & 31;
     long long const warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -995,6 +999,26 @@ __global__ void __launch_bounds__(kThreads)
         long long const i = att_src[t];
         int const id      = src_sid[i];
         float* d          = dst + slot * stride;
+        if (delta)
+        { // base+delta: copy the increment list, append the two recorded cells
+            const int* sb = reinterpret_cast<const int*>(src + i * stride);
+            int* db       = reinterpret_cast<int*>(d);
+            int const ne  = sb[0];
+            warp_copy_block(src + i * stride, d, (ne + 1 + 3) >> 2, lane);
+            __syncwarp();
+            if (lane == 0)
+            {
+                if (ne + 2 <= delta_cap)
+                {
+                    db[1 + ne] = rec[t * J], db[2 + ne] = rec[t * J + 1];
+                    db[0] = ne + 2;
+                } else
+                    *overflow = 2;
+                dst_sid[slot]   = id;
+                dst_state[slot] = att_state[t];
+            }
+            continue;
+        }
         warp_copy_block(src + i * stride, d, (struct_size[id] + 3) >> 2, lane);
         __syncwarp();
         if (lane < J) d[rec[t * J + lane]] = __fadd_rn(src[i * stride + rec[t * J + lane]], 1.0f);
@@ -1080,6 +1104,130 @@ __global__ void __launch_bounds__(kThreads)
         dst_state[job.slot] = job.state;
         dst_sid[job.slot]   = job.new_struct;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// base+delta storage (tabular models too large for dense private blocks): the per-particle kernels
+// ------------------------------------------------------------------------------------------------
+
+// Belief::initiate: empty increment lists; sid[i] = which base table (prior prototype) particle i uses
+__global__ void __launch_bounds__(kThreads)
+    k_init_delta(float* __restrict__ blocks, long long stride, int* __restrict__ state, int* __restrict__ sid,
+                 double* __restrict__ w, long long N, const int* __restrict__ particle_proto,
+                 const int* __restrict__ particle_state)
+{
+    long long const i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    reinterpret_cast<int*>(blocks + i * stride)[0] = 0;
+    sid[i] = particle_proto ? particle_proto[i] : 0;
+    if (particle_state) state[i] = particle_state[i];
+    if (w) w[i] = 1.0 / (double)N;
+}
+
+template<bool REPLAY>
+__global__ void __launch_bounds__(kThreads)
+    k_propose_delta(DevModel M, const float* __restrict__ base, long long base_stride, float* blocks,
+                    long long stride, int cap, int* __restrict__ state, const int* __restrict__ sid,
+                    double* __restrict__ w, long long N, int a, int o, RngArgs ra, int* __restrict__ overrun)
+{
+    long long const i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    auto g            = RngOf<REPLAY>::make(ra, i);
+    const Node* nodes = M.nodes + (long long)a * M.J; // tabular: one structure
+    const float* tb   = base + (long long)sid[i] * base_stride;
+    int* block        = reinterpret_cast<int*>(blocks + i * stride);
+    int sim_o;
+    int const s2 = hyper_step_delta<STEP_UPDATE>(M, nodes, tb, block, cap, state[i], g, sim_o, nullptr, overrun);
+    double const prob = obs_probability_delta(M, nodes, tb, block, s2, o);
+    state[i]          = s2;
+    w[i]              = __dmul_rn(w[i], prob);
+    if (g.overrun) *overrun = 1;
+}
+
+template<bool REPLAY>
+__global__ void __launch_bounds__(kThreads)
+    k_rollouts_delta(DevModel M, const float* __restrict__ base, long long base_stride, const float* blocks,
+                     long long stride, const int* __restrict__ sid, long long n,
+                     const long long* __restrict__ particle, const int* __restrict__ start,
+                     const int* __restrict__ depth, double discount, RngArgs ra, double* __restrict__ ret_out,
+                     int* __restrict__ overrun)
+{
+    long long const r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    auto g            = RngOf<REPLAY>::make(ra, r);
+    long long const p = particle[r];
+    const float* tb   = base + (long long)sid[p] * base_stride;
+    int* block        = reinterpret_cast<int*>(const_cast<float*>(blocks) + p * stride); // read-only here
+    double ret = 0.0, disc = 1.0;
+    int s = start[r], d = depth[r];
+    bool terminal = false;
+    while (d > 0 && !terminal)
+    {
+        int const a = random_action(M, g);
+        int o;
+        int const s2 = hyper_step_delta<STEP_KEEP>(M, M.nodes + (long long)a * M.J, tb, block, 0, s, g, o,
+                                                   nullptr, nullptr);
+        double const rew = domain_reward(M, s, a, s2, terminal);
+        ret  = __dadd_rn(ret, __dmul_rn(rew, disc));
+        disc = __dmul_rn(disc, discount);
+        s    = s2;
+        --d;
+    }
+    ret_out[r] = ret;
+    if (g.overrun) *overrun = 1;
+}
+
+template<bool REPLAY>
+__global__ void __launch_bounds__(kThreads)
+    k_step_batch_delta(DevModel M, const float* __restrict__ base, long long base_stride, const float* blocks,
+                       long long stride, const int* __restrict__ sid, long long n,
+                       const long long* __restrict__ particle, const int* __restrict__ state,
+                       const int* __restrict__ action, RngArgs ra, int* __restrict__ new_state,
+                       int* __restrict__ obs, double* __restrict__ reward, int* __restrict__ terminal,
+                       int* __restrict__ overrun)
+{
+    long long const r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    auto g            = RngOf<REPLAY>::make(ra, r);
+    long long const p = particle[r];
+    int const a       = action[r];
+    int o;
+    int const s  = state[r];
+    int const s2 = hyper_step_delta<STEP_KEEP>(
+        M, M.nodes + (long long)a * M.J, base + (long long)sid[p] * base_stride,
+        reinterpret_cast<int*>(const_cast<float*>(blocks) + p * stride), 0, s, g, o, nullptr, nullptr);
+    bool term;
+    reward[r]    = domain_reward(M, s, a, s2, term);
+    new_state[r] = s2;
+    obs[r]       = o;
+    terminal[r]  = term ? 1 : 0;
+    if (g.overrun) *overrun = 1;
+}
+
+template<bool REPLAY>
+__global__ void __launch_bounds__(kThreads)
+    k_rs_attempt_delta(DevModel M, const float* __restrict__ base, long long base_stride, const float* blocks,
+                       long long stride, const int* __restrict__ state, const int* __restrict__ sid, long long N,
+                       int a, int o, long long n_attempts, RngArgs ra, int* __restrict__ src_out,
+                       int* __restrict__ state_out, int* __restrict__ accept_out, int* __restrict__ rec_out,
+                       int* __restrict__ overrun)
+{
+    long long const t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_attempts) return;
+    auto g      = RngOf<REPLAY>::make(ra, t);
+    int const i = draw_k(g, (uint32_t)N);
+    int rec[2];
+    int sim_o;
+    int const s2 = hyper_step_delta<STEP_RECORD>(
+        M, M.nodes + (long long)a * M.J, base + (long long)sid[i] * base_stride,
+        reinterpret_cast<int*>(const_cast<float*>(blocks) + (long long)i * stride), 0, state[i], g, sim_o, rec,
+        nullptr);
+    src_out[t]         = i;
+    state_out[t]       = s2;
+    accept_out[t]      = (sim_o == o) ? 1 : 0;
+    rec_out[t * 2]     = rec[0];
+    rec_out[t * 2 + 1] = rec[1];
+    if (g.overrun) *overrun = 1;
 }
 
 } // namespace fba

@@ -102,6 +102,12 @@ typedef struct fba_model_desc {
     const float* start_values; /* host pointers */
     double start_total;
     const int32_t* start_table;
+    /* 0: every particle owns a dense count block. > 0 (tabular models only): base+delta storage —
+     * particles share the prior's dense tables and own only a list of at most delta_capacity
+     * increments (2 per update). For tabular models whose dense block is too large to replicate
+     * (gridworld --size 5: 720 KB per particle); stands in for BAFlatModel's copy-on-write rows
+     * (src/bayes-adaptive/states/table/BAFlatModel.cpp:185-252,284-354). */
+    int32_t delta_capacity;
 } fba_model_desc;
 
 enum fba_rng_mode { FBA_RNG_REPLAY = 0, FBA_RNG_PHILOX = 1 };

@@ -40,6 +40,9 @@ CONFIGS = {
     # extra pins beyond the five configs:
     # sysadmin's `mutate` (chained subscripts drawn right to left) through reinvigoration
     "sysadmin3": dict(domain="linear-sysadmin", size=3, factored=True, N=64, steps=12, reinv_N=48, reinv_K=12),
+    # gridworld size 5 (S = O = 150, 180 000 count cells = 720 KB per particle): the case that needs
+    # base+delta storage on the GPU (SURVEY.md §7 hard part 4); the reference runs it with COW rows
+    "gridworld5": dict(domain="gridworld", size=5, factored=False, N=24, steps=20, rs_N=16),
     # factored gridworld: three OBSERVATION features (likelihood = double product of float factors)
     "gridworld3_fba": dict(domain="gridworld", size=3, factored=True, N=64, steps=20),
 }

@@ -4,7 +4,9 @@ import os
 import numpy as np
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-NAMES = ["tiger", "ftiger", "ftiger_mu", "gridworld3", "ca", "sysadmin", "sysadmin3", "gridworld3_fba"]
+NAMES = ["tiger", "ftiger", "ftiger_mu", "gridworld3", "ca", "sysadmin", "sysadmin3", "gridworld3_fba",
+         "gridworld5"]
+TABULAR = ["tiger", "gridworld3", "gridworld5"]
 MUTATE_KIND = {"ftiger_mu": 0, "ca": 1, "sysadmin3": 2}
 
 
