@@ -18,8 +18,10 @@ MUT_FACTORED_TIGER, MUT_COLLISION_AVOIDANCE, MUT_SYSADMIN, MUT_GRIDWORLD = range
 RNG_REPLAY, RNG_PHILOX = 0, 1
 
 # every symbol include/fba_pomdp_b200.h declares (tests check the library exports all of them)
+ABI_VERSION = 4  # must equal FBA_ABI_VERSION in include/fba_pomdp_b200.h
+
 SYMBOLS = [
-    "fba_ctx_create", "fba_ctx_destroy", "fba_last_error", "fba_ctx_stream", "fba_ctx_synchronize",
+    "fba_abi_version", "fba_ctx_create", "fba_ctx_destroy", "fba_last_error", "fba_ctx_stream", "fba_ctx_synchronize",
     "fba_ctx_launch_count", "fba_ctx_set_option", "fba_ctx_profile_begin", "fba_ctx_profile_end", "fba_ctx_profile_get", "fba_ctx_profile_list",
     "fba_model_create", "fba_model_destroy", "fba_model_add_structures",
     "fba_model_num_structures", "fba_model_structure_size", "fba_model_get_structure",
@@ -96,6 +98,7 @@ def lib():
         vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
         pp = C.POINTER(vp)
         sig = {
+            "fba_abi_version": (C.c_int, []),
             "fba_ctx_create": (C.c_int, [C.c_int, pp]),
             "fba_ctx_destroy": (None, [vp]),
             "fba_last_error": (C.c_char_p, [vp]),
@@ -161,6 +164,9 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
+        if L.fba_abi_version() != ABI_VERSION:
+            raise FbaError(ERR_INVALID, "libfba_b200.so has ABI version %d, this binding expects %d: rebuild"
+                           % (L.fba_abi_version(), ABI_VERSION))
         _lib = L
     return _lib
 

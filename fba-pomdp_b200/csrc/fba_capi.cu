@@ -203,6 +203,11 @@ static void profile_mark(fba_ctx* ctx, const char* name, bool begin)
 // ------------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------------
+extern "C" int fba_abi_version(void)
+{
+    return FBA_ABI_VERSION;
+}
+
 extern "C" int fba_ctx_create(int device, fba_ctx** out)
 {
     if (!out) return FBA_ERR_INVALID;

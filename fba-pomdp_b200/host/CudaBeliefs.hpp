@@ -62,8 +62,13 @@ inline void check(fba_ctx* ctx, int rc, char const* what)
 class CudaSimulator
 {
 public:
-    CudaSimulator(BAPOMDP const& sim, int device = 0, int max_structures = 4096) : _sim(sim)
+    // delta_capacity: -1 = choose automatically (base+delta storage for tabular models whose dense
+    // count block exceeds 256 KB, with room for 2048 increments = 1024 updates per particle)
+    CudaSimulator(BAPOMDP const& sim, int device = 0, int max_structures = 4096, int delta_capacity = -1) :
+            _sim(sim)
     {
+        if (fba_abi_version() != FBA_ABI_VERSION)
+            throw std::string("fba_b200: libfba_b200.so was built with another ABI version than this header");
         int rc = fba_ctx_create(device, &_ctx);
         if (rc == FBA_ERR_NO_DEVICE) throw std::string("fba_b200: no CUDA device (there is no CPU fallback)");
         check(nullptr, rc, "fba_ctx_create");
@@ -90,6 +95,9 @@ public:
 
         probeRewards(d);
         d.domain      = FBA_DOM_TABLE;
+        long long const dense_cells = (long long)d.A * d.S * d.S + (long long)d.A * d.S * d.O;
+        if (delta_capacity < 0) delta_capacity = (d.tabular && dense_cells * 4 > (256 << 10)) ? 2048 : 0;
+        d.delta_capacity = d.tabular ? delta_capacity : 0;
         d.action_draw = FBA_ACT_UNIFORM_INT; // rollouts only; all reference domains draw uniformly
         d.start_kind  = FBA_START_CONST;     // unused: start states come from the host domain
 
@@ -342,29 +350,42 @@ public:
         auto const& sim = dynamic_cast<BAPOMDP const&>(d);
         _cuda.reset(new CudaSimulator(sim, _device));
         // Belief::initiate = N x sampleStartState (BAImportanceSampling.cpp:49-60): the reference's
-        // prior and domain run on the host, the particles are uploaded
-        std::vector<int32_t> state(_n), sid(_n);
-        std::vector<std::vector<float>> blocks(_n);
+        // prior and domain run on the host; distinct (structure, count block) pairs become prototypes
+        // that are uploaded once, each particle names its prototype and its domain start state
+        std::vector<int32_t> state(_n), proto(_n), proto_sid;
+        std::vector<std::vector<float>> proto_blocks;
+        std::map<std::string, int32_t> known;
+        std::vector<float> block;
         size_t stride = 0;
         for (size_t i = 0; i < _n; ++i)
         {
-            auto p   = static_cast<BAState const*>(d.sampleStartState());
-            state[i] = p->_domain_state->index();
-            sid[i]   = _cuda->describe(p, &blocks[i]);
-            stride   = std::max(stride, blocks[i].size());
+            auto p            = static_cast<BAState const*>(d.sampleStartState());
+            state[i]          = p->_domain_state->index();
+            int32_t const sid = _cuda->describe(p, &block);
+            std::string key((char const*)&sid, sizeof(sid));
+            key.append((char const*)block.data(), block.size() * sizeof(float));
+            auto it = known.find(key);
+            if (it == known.end())
+            {
+                it = known.emplace(std::move(key), (int32_t)proto_sid.size()).first;
+                proto_sid.push_back(sid);
+                proto_blocks.push_back(block);
+                stride = std::max(stride, block.size());
+            }
+            proto[i] = it->second;
             d.releaseState(p);
         }
         check(_cuda->ctx(), fba_belief_create(_cuda->ctx(), _cuda->model(), (int64_t)_n, (int64_t)stride,
                                                _weighted ? 1 : 0, &_belief),
               "fba_belief_create");
         stride = (size_t)fba_belief_stride(_belief);
-        std::vector<float> flat(_n * stride, 0.0f);
-        for (size_t i = 0; i < _n; ++i) std::copy(blocks[i].begin(), blocks[i].end(), flat.begin() + i * stride);
-        std::vector<double> w(_n, 1.0 / (double)_n);
+        std::vector<float> flat(proto_sid.size() * stride, 0.0f);
+        for (size_t k = 0; k < proto_sid.size(); ++k)
+            std::copy(proto_blocks[k].begin(), proto_blocks[k].end(), flat.begin() + k * stride);
         check(_cuda->ctx(),
-              fba_belief_upload(_belief, 0, (int64_t)_n, state.data(), sid.data(), flat.data(),
-                                _weighted ? w.data() : nullptr),
-              "fba_belief_upload");
+              fba_belief_init(_belief, (int32_t)proto_sid.size(), proto_sid.data(), flat.data(), proto.data(),
+                              state.data()),
+              "fba_belief_init");
     }
 
     void free(POMDP const& /*d*/) override { release(); }

@@ -30,6 +30,8 @@ extern "C" {
 #endif
 
 #define FBA_MAX_FEATURES 16
+/* bumped whenever a struct below changes layout; compare with fba_abi_version() after loading */
+#define FBA_ABI_VERSION 4
 
 typedef struct fba_ctx fba_ctx;
 typedef struct fba_model fba_model;
@@ -125,6 +127,7 @@ typedef struct fba_rng {
 } fba_rng;
 
 /* ---- context ---- */
+int fba_abi_version(void); /* FBA_ABI_VERSION the library was built with */
 int fba_ctx_create(int device, fba_ctx** out);
 void fba_ctx_destroy(fba_ctx* ctx);
 const char* fba_last_error(const fba_ctx* ctx);

@@ -19,6 +19,9 @@ CASES = [
     ("centered-collision-avoidance", dict(size=1, width=3, height=3, factored=True), (0, 1), 128, 40),
     ("linear-sysadmin", dict(size=3, factored=True), (0, 1), 64, 20),
     ("gridworld", dict(size=3), (0, 1), 16, 10),
+    # gridworld size 5: the adapter switches to base+delta storage by itself (dense block = 720 KB)
+    ("gridworld", dict(size=5), (0, 1), 16, 6),
+    ("gridworld", dict(size=5), (2, 3), 16, 6),
     # reinvigoration: the reference's ReinvigoratingRejectionSampling vs the CUDA adapter
     ("episodic-factored-tiger", dict(size=3, factored=True, structure_prior="match-uniform"), (4, 5), 128, 40),
     ("centered-collision-avoidance", dict(size=1, width=3, height=3, factored=True,
@@ -45,6 +48,7 @@ PLANNER_CASES = [
     # domain, kwargs, particles, episodes, simulations, wave
     ("episodic-tiger", dict(), 512, 150, 128, 8),
     ("gridworld", dict(size=3), 64, 40, 128, 16),
+    ("gridworld", dict(size=5), 16, 8, 64, 16),
     ("centered-collision-avoidance", dict(size=1, width=3, height=3, factored=True), 128, 60, 128, 16),
     ("linear-sysadmin", dict(size=3, factored=True), 64, 30, 128, 16),
 ]

@@ -45,9 +45,9 @@ def time_updates(ctx, fn, steps, warmup=3):
     return (time.perf_counter() - t0) / steps
 
 
-def is_config(ctx, name, n, steps=20):
+def is_config(ctx, name, n, steps=20, delta_capacity=0):
     g = G.load(name)
-    sim = fba.BAPOMDP(ctx, g.desc, g.t_par, g.o_par)
+    sim = fba.BAPOMDP(ctx, dict(g.desc, delta_capacity=delta_capacity), g.t_par, g.o_par)
     psid, pc = prototypes(g)
     b = fba.BAImportanceSampling(n)
     rng = fba.Rng.philox(1)
@@ -97,6 +97,10 @@ def main():
     out["3 gridworld-3 BA-POMDP IS N=1e6"] = dict(
         is_config(ctx, "gridworld3", 1_000_000, 10),
         reference_cpu="size 5 at N=4096: 2.5e5 / 3.9e4 particles/s (BASELINE.md §2)")
+    # the same at --size 5 (720 KB dense per particle): base+delta storage, 256 increments per particle
+    out["3b gridworld-5 BA-POMDP IS N=1e6, base+delta storage"] = dict(
+        is_config(ctx, "gridworld5", 1_000_000, 10, delta_capacity=256),
+        reference_cpu="N=4096: 2.5e5 / 3.9e4 particles/s (BASELINE.md §2)")
     # configs[3]: collision avoidance 5x5x1, heterogeneous structures, 1e6 particles
     out["4 collision-avoidance 5x5x1 FBA-POMDP IS N=1e6 (match-uniform structures)"] = dict(
         is_config(ctx, "ca", 1_000_000),
