@@ -91,21 +91,46 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def workload():
+WORKLOADS = {
+    # BASELINE.json configs[4] (the headline): one shared structure
+    "sysadmin": dict(fixture="sysadmin", particles=PER_GPU_PARTICLES, text=WORKLOAD,
+                     ref=dict(domain="linear-sysadmin", size=10, factored=True)),
+    # configs[3]: collision avoidance 5x5, 1 obstacle, --structure-prior match-uniform
+    # (heterogeneous DBN structures), 10^6 particles per GPU
+    "ca": dict(fixture="ca", particles=1_000_000,
+               text="centered-collision-avoidance 5x5x1 FBA-POMDP (match-uniform structure prior), "
+                    "importance-sampling belief update (update+resample)",
+               ref=dict(domain="centered-collision-avoidance", size=1, width=5, height=5, factored=True,
+                        structure_prior="match-uniform")),
+}
+
+
+def workload(name="sysadmin"):
+    """(fixture, prototype structure ids, prototype count blocks, (a,o) script): the distinct
+    (structure, counts) pairs the reference's prior produced become equally likely prototypes."""
     import golden_util as G
-    g = G.load("sysadmin")
+    g = G.load(WORKLOADS[name]["fixture"])
+    sid, counts = g["is/init_struct_id"], g["is/init_counts"]
+    seen, psid, pc = {}, [], []
+    for i in range(len(sid)):
+        k = (int(sid[i]), counts[i].tobytes())
+        if k not in seen:
+            seen[k] = len(psid)
+            psid.append(int(sid[i]))
+            pc.append(counts[i])
     steps = [(int(a), int(o)) for a, o, f in zip(g.a, g.o, g.flags) if not (f & 1)]
-    return g, g["is/init_counts"][0].copy(), steps
+    return g, np.array(psid, np.int32), np.stack(pc), steps
 
 
 # ------------------------------------------------------------------------------------------------
 # the reference's own CPU implementation (cpu_baseline and --impl reference)
 # ------------------------------------------------------------------------------------------------
-def _ref_worker(n, steps, warmup, seed, script, q):
+def _ref_worker(n, steps, warmup, seed, script, q, wl="sysadmin"):
     try:
         import pyref
         kind = "reference"
-        r = pyref.Ref("linear-sysadmin", size=10, factored=True, seed=seed)
+        kw = dict(WORKLOADS[wl]["ref"])
+        r = pyref.Ref(kw.pop("domain"), seed=seed, **kw)
         r.belief_init(pyref.F_IS, n)
 
         def one(t):
@@ -115,7 +140,7 @@ def _ref_worker(n, steps, warmup, seed, script, q):
         kind = "port"
         import golden_util as G
         import pyoracle as O
-        g = G.load("sysadmin")
+        g = G.load(WORKLOADS[wl]["fixture"])
         m = O.Model(g.desc)
         st = O.Structs(m, g.t_par, g.o_par)
         state = {"b": O.Belief(n, g["is/init_counts"].shape[1])}
@@ -139,14 +164,14 @@ def _ref_worker(n, steps, warmup, seed, script, q):
     q.put((kind, time.perf_counter() - t0))
 
 
-def run_reference_cpu(n_particles, steps, warmup, replicas):
+def run_reference_cpu(n_particles, steps, warmup, replicas, wl="sysadmin"):
     """`replicas` independent single-threaded reference beliefs (the reference has no threads),
     one per host core; returns (particles/s aggregate, seconds per step, kind)."""
     import multiprocessing as mp
-    _, _, script = workload()
+    script = workload(wl)[3]
     ctxmp = mp.get_context("fork")
     q = ctxmp.Queue()
-    procs = [ctxmp.Process(target=_ref_worker, args=(n_particles, steps, warmup, str(42 + i), script, q))
+    procs = [ctxmp.Process(target=_ref_worker, args=(n_particles, steps, warmup, str(42 + i), script, q, wl))
              for i in range(replicas)]
     for p in procs:
         p.start()
@@ -218,7 +243,7 @@ def main_reference(args):
         return 0  # the CPU arm runs once per box
     cores = os.cpu_count() or 1
     n = args.ref_particles
-    value, s_per_step, kind = run_reference_cpu(n, args.steps, args.warmup, cores)
+    value, s_per_step, kind = run_reference_cpu(n, args.steps, args.warmup, cores, args.workload)
     sample = ("%d independent single-threaded replicas (one per host core), each a BAImportanceSampling "
               "belief of %d particles (the reference's resample is O(N^2); BASELINE.md quotes it at "
               "N=4096), %d updateEstimation steps" % (cores, n, args.steps))
@@ -226,7 +251,7 @@ def main_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 counts / f64 weights",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "particles_per_replica": n,
+        "data": "synthetic", "config": {"workload": WORKLOADS[args.workload]["text"], "particles_per_replica": n,
                                         "replicas": cores, "l2": "n/a (CPU)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -254,11 +279,12 @@ def main_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    g, proto, script = workload()
-    n_local = args.particles
+    g, psid, protos, script = workload(args.workload)
+    n_local = args.particles or WORKLOADS[args.workload]["particles"]
     ctx = fba.Context(local_rank)
     sim = fba.BAPOMDP(ctx, g.desc, g.t_par, g.o_par)
-    C = int(sim.structure_size(0))
+    # count cells a particle owns (mean over the prior's structures when they differ)
+    C = int(round(np.mean([sim.structure_size(int(i)) for i in psid])))
     bytes_per_particle = 2 * (4 * C + 4 + 8)  # counts + state + weight, read + written
 
     if world > 1 or args.force_sharded:
@@ -267,7 +293,8 @@ def main_ours(args):
     else:
         b = fba.BAImportanceSampling(n_local)
         rng = fba.Rng.philox(args.seed)
-    b.initiate_sampled(sim, [0], proto[None, :], None, rng)
+    b.initiate_sampled(sim, psid, protos, None if len(psid) == 1 else np.ones(len(psid)), rng,
+                       stride=protos.shape[1])
     shared = np.random.RandomState(args.seed)  # same on every rank: quota offsets
 
     def step(t, want_likelihood=False):
@@ -299,22 +326,25 @@ def main_ours(args):
     peak, peak_src = load_peaks()
     stream = torch.cuda.ExternalStream(ctx.stream)
 
-    def timed_region(n_steps, t_first):
+    def timed_region(n_steps, t_first, profile=True):
         """K steps bracketed by barrier + synchronize, CUDA events on the launching stream, per-kernel
-        events inside; returns (ms max over ranks, per-kernel table, launches, clocks, copies)."""
+        events inside (profile=True); returns (ms max over ranks, per-kernel table, launches, clocks,
+        copies)."""
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sampler = ClockSampler(local_rank)
         sampler.start()
         launches0 = ctx.launches
         copies0 = b.resample_stats()[0]
-        ctx.profile_begin()
+        if profile:
+            ctx.profile_begin()
         ev0.record(stream)
         for t in range(n_steps):
             step(t_first + t)
         ev1.record(stream)
         barrier()
-        ctx.profile_end()
+        if profile:
+            ctx.profile_end()
         clocks = sampler.stop()
         ms = ev0.elapsed_time(ev1)
         if world > 1:
@@ -323,7 +353,7 @@ def main_ours(args):
             ms = float(tt.item())
         copies = b.resample_stats()[0] - copies0
         table = {}
-        for name, (kms, cnt) in ctx.kernel_times().items():
+        for name, (kms, cnt) in (ctx.kernel_times().items() if profile else ()):
             per_launch = kms / max(cnt, 1)
             if name.startswith("k_gather"):
                 alg = bytes_per_particle * n_local
@@ -359,7 +389,14 @@ def main_ours(args):
                 "share_of_step": row["share_of_step"], "note": note}
 
     # ---- the default path: in-place systematic resampling (survivors are not moved) ----
-    ms, table, launches, clocks, copies = timed_region(args.steps, args.warmup + 2)
+    if world == 1:
+        ms, table, launches, clocks, copies = timed_region(args.steps, args.warmup + 2)
+    else:
+        # multi-GPU: the K timed steps run without the per-kernel event pairs (two extra event records
+        # per launch on every rank); the per-kernel table comes from a second, separate pass
+        ms, _, launches, clocks, copies = timed_region(args.steps, args.warmup + 2, profile=False)
+        _, table, _, _, pcopies = timed_region(min(args.steps, 10), 500)
+        table = {k: dict(v, share_of_step=None) for k, v in table.items()}
     if world > 1 and args.trace:
         b.trace = []
         for t in range(10):
@@ -367,7 +404,7 @@ def main_ours(args):
         print("trace rank %d: %s" % (rank, b.trace_summary()), file=sys.stderr)
         b.trace = None
     value = n_local * world * args.steps / (ms * 1e-3)
-    dominant = max(table, key=lambda k: table[k]["share_of_step"])
+    dominant = max(table, key=lambda k: table[k]["ms_per_launch"] * table[k]["launches"])
     copied_frac = copies / float(n_local * args.steps)
     if dominant.startswith("k_copy_inplace"):
         roof = roofline_of(table, "k_copy_inplace",
@@ -421,7 +458,8 @@ def main_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32 counts / f64 weights", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "particles_per_gpu": n_local, "particles_total": n_local * world,
+        "config": {"workload": WORKLOADS[args.workload]["text"], "structures": int(len(psid)),
+                   "particles_per_gpu": n_local, "particles_total": n_local * world,
                    "count_cells_per_particle": C, "rng": "philox4x32-10",
                    "resampling": "systematic, in place (survivors keep their slot; duplicates fill dead slots)",
                    "algorithmic_bytes_per_particle_copy": bytes_per_particle,
@@ -449,7 +487,7 @@ def main_ours(args):
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n = args.ref_particles
-        v, s_per_step, kind = run_reference_cpu(n, 6, 1, 1)
+        v, s_per_step, kind = run_reference_cpu(n, 6, 1, 1, args.workload)
         line["cpu_baseline"] = {
             "value": v, "unit": UNIT, "cores": 1, "kind": kind,
             "sample": "the reference's BAImportanceSampling::updateEstimation, 1 thread (it has no "
@@ -471,7 +509,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--particles", type=int, default=PER_GPU_PARTICLES, help="particles per GPU")
+    ap.add_argument("--workload", default="sysadmin", choices=sorted(WORKLOADS),
+                    help="sysadmin = BASELINE configs[4] (default, the headline); ca = configs[3]")
+    ap.add_argument("--particles", type=int, default=0, help="particles per GPU (0: the workload's own)")
     ap.add_argument("--ref-particles", type=int, default=4096)
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--no-cpu-baseline", action="store_true")
