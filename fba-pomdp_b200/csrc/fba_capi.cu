@@ -24,6 +24,7 @@ struct fba_ctx
     int64_t launches     = 0;
     std::string err;
     // optional per-kernel CUDA-event timing (fba_ctx_profile_*)
+    int bulk_copy    = 0;  // 1: full-copy gathers go through the TMA engine (k_gather_bulk)
     int rollout_coop = -1; // -1 auto (by batch size and row length), 0 thread per rollout, 1 warp per rollout
     bool inplace_resample = true; // PHILOX mode: survivors keep their slot (fba_ctx_set_option)
     bool profiling       = false;
@@ -273,6 +274,11 @@ extern "C" int fba_ctx_set_option(fba_ctx* ctx, const char* name, int64_t value)
     if (!strcmp(name, "inplace_resample"))
     {
         ctx->inplace_resample = value != 0;
+        return FBA_OK;
+    }
+    if (!strcmp(name, "bulk_copy"))
+    {
+        ctx->bulk_copy = value != 0;
         return FBA_OK;
     }
     if (!strcmp(name, "rollout_coop"))
@@ -1126,6 +1132,23 @@ static int gather_into_next(fba_belief* b, long long n_out, bool copy_state)
 {
     fba_ctx* ctx = b->ctx;
     int const nx = b->cur ^ 1;
+    long long const stage_bytes = b->stride * (long long)sizeof(float);
+    if (ctx->bulk_copy && b->delta_cap == 0 && stage_bytes >= 1024
+        && kBulkStages * stage_bytes + kBulkStages * 8 <= 200 * 1024)
+    {
+        size_t const shmem = (size_t)kBulkStages * stage_bytes + kBulkStages * sizeof(unsigned long long);
+        CU(ctx, cudaFuncSetAttribute(k_gather_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+        int const grid = (int)std::min<long long>(n_out, (long long)ctx->sm_count * 2);
+        if (ctx->profiling) profile_mark(ctx, "k_gather_bulk", true);
+        k_gather_bulk<<<grid, 32, shmem, ctx->stream>>>(
+            b->counts[b->cur], b->counts[nx], b->stride, b->state[b->cur], copy_state ? b->state[nx] : nullptr,
+            b->sid[b->cur], b->sid[nx], b->m->d_sizes, b->weighted ? b->w : nullptr, 1.0 / (double)b->N, b->anc,
+            n_out, (int)stage_bytes);
+        if (ctx->profiling) profile_mark(ctx, "k_gather_bulk", false);
+        ++ctx->launches;
+        CU(ctx, cudaGetLastError());
+        return FBA_OK;
+    }
     LAUNCH(ctx, k_gather, stream_grid(ctx, n_out), kThreads, b->counts[b->cur], b->counts[nx], b->stride,
            b->state[b->cur], copy_state ? b->state[nx] : nullptr, b->sid[b->cur], b->sid[nx],
            b->m->d_sizes, b->weighted ? b->w : nullptr, 1.0 / (double)b->N, b->anc, n_out,

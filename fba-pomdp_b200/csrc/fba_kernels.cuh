@@ -155,6 +155,121 @@ __global__ void __launch_bounds__(kThreads)
 }
 
 // ------------------------------------------------------------------------------------------------
+// The same gather through the TMA engine (cp.async.bulk, SASS: UBLKCP): one CTA per SM; its thread 0
+// drives a ring of shared-memory stages — bulk load global -> shared (completion on an mbarrier),
+// bulk store shared -> global (bulk async-group) — so whole count blocks move as single DMA
+// transfers and no register or LSU bandwidth is spent on the payload. The other lanes write the
+// per-particle scalars (state, structure id, weight). Loads run STAGES-1 blocks ahead of the stores.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p)
+{
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, unsigned bytes,
+                                          unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gmem_dst, const void* smem_src, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst),
+                 "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+constexpr int kBulkStages = 8;
+
+// dynamic shared memory: kBulkStages * stage_bytes, then kBulkStages mbarriers
+__global__ void __launch_bounds__(32)
+    k_gather_bulk(const float* __restrict__ src, float* __restrict__ dst, long long stride,
+                  const int* __restrict__ src_state, int* __restrict__ dst_state,
+                  const int* __restrict__ src_sid, int* __restrict__ dst_sid,
+                  const int* __restrict__ struct_size, double* __restrict__ w, double w_new,
+                  const int* __restrict__ anc, long long n_out, int stage_bytes)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + (size_t)kBulkStages * stage_bytes);
+    int const tid            = threadIdx.x;
+    long long const first = blockIdx.x, step = gridDim.x;
+    long long const L     = (n_out > first) ? (n_out - first + step - 1) / step : 0; // this CTA's jobs
+
+    if (tid == 0)
+    {
+        for (int s = 0; s < kBulkStages; ++s) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (tid == 0)
+    {
+        auto issue_load = [&](long long n) {
+            long long const j  = first + n * step;
+            long long const i  = anc[j];
+            unsigned const bytes = (unsigned)(((struct_size[src_sid[i]] + 3) >> 2) << 4);
+            int const st       = (int)(n % kBulkStages);
+            mbar_expect_tx(&bars[st], bytes);
+            bulk_load(smem + (size_t)st * stage_bytes, src + i * stride, bytes, &bars[st]);
+        };
+        long long const ahead = kBulkStages - 1;
+        for (long long n = 0; n < L && n < ahead; ++n) issue_load(n);
+        for (long long n = 0; n < L; ++n)
+        {
+            int const st = (int)(n % kBulkStages);
+            mbar_wait(&bars[st], (unsigned)((n / kBulkStages) & 1));
+            long long const j    = first + n * step;
+            long long const i    = anc[j];
+            unsigned const bytes = (unsigned)(((struct_size[src_sid[i]] + 3) >> 2) << 4);
+            bulk_store(dst + j * stride, smem + (size_t)st * stage_bytes, bytes);
+            // the stage the next load wants was last used by job n + ahead - kBulkStages = n - 1:
+            // its store must have finished reading shared memory (at most this iteration's may pend)
+            if (n + ahead < L)
+            {
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                issue_load(n + ahead);
+            }
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    } else
+    {
+        for (long long n = tid - 1; n < L; n += 31)
+        {
+            long long const j = first + n * step;
+            long long const i = anc[j];
+            dst_sid[j]        = src_sid[i];
+            if (dst_state) dst_state[j] = src_state[i];
+            if (w) w[j] = w_new;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // importance_sampling::update, per-particle part (ImportanceSampler.hpp:37-54): step in place,
 // weight *= P(o | a, particle). One thread per particle.
 // ------------------------------------------------------------------------------------------------
