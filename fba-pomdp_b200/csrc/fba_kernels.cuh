@@ -46,36 +46,59 @@ struct RngOf<false>
 // particle block copies: one warp per destination particle, 16-byte vectors, streaming hints
 // (every byte is touched once per update, so nothing should be kept in L1)
 // ------------------------------------------------------------------------------------------------
+// Cache hint of the block copies. Measured on B200 (tools/exp_bulk.py, sysadmin, 1.25e6 particles,
+// k_gather): .nc.L1::no_allocate 5.73 TB/s, plain 5.84 TB/s, .cs (evict-first streaming) 5.99 TB/s
+// with 4 and 6.15 TB/s with 8 loads in flight per lane; the TMA bulk-copy version (k_gather_bulk)
+// 5.37 TB/s. The in-place copy (scattered sources and destinations) is best with .cs and 4.
+#ifndef FBA_COPY_HINT
+#define FBA_COPY_HINT 1 // 0: .nc.L1::no_allocate / .L1::no_allocate, 1: .cs (streaming), 2: plain
+#endif
+
 __device__ __forceinline__ float4 ld_stream(const float4* p)
 {
     float4 v;
+#if FBA_COPY_HINT == 0
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                  : "l"(p));
+#elif FBA_COPY_HINT == 1
+    asm volatile("ld.global.cs.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+#else
+    v = *p;
+#endif
     return v;
 }
 __device__ __forceinline__ void st_stream(float4* p, float4 v)
 {
+#if FBA_COPY_HINT == 0
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
                  "f"(v.z), "f"(v.w)
                  : "memory");
+#elif FBA_COPY_HINT == 1
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+#else
+    *p = v;
+#endif
 }
 
+// U independent 16-byte loads in flight per lane before the first store
+template<int U = 4>
 __device__ __forceinline__ void warp_copy_block(const float* __restrict__ src, float* __restrict__ dst,
                                                 int n_vec, int lane)
 {
     const float4* s = reinterpret_cast<const float4*>(src);
     float4* d       = reinterpret_cast<float4*>(dst);
     int i           = lane;
-    // 4 independent 16-byte loads in flight per lane before the first store
-    for (; i + 96 < n_vec; i += 128)
+    for (; i + 32 * (U - 1) < n_vec; i += 32 * U)
     {
-        float4 a = ld_stream(s + i), b = ld_stream(s + i + 32), c = ld_stream(s + i + 64),
-               e = ld_stream(s + i + 96);
-        st_stream(d + i, a);
-        st_stream(d + i + 32, b);
-        st_stream(d + i + 64, c);
-        st_stream(d + i + 96, e);
+        float4 v[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) v[k] = ld_stream(s + i + 32 * k);
+#pragma unroll
+        for (int k = 0; k < U; ++k) st_stream(d + i + 32 * k, v[k]);
     }
     for (; i < n_vec; i += 32) st_stream(d + i, ld_stream(s + i));
 }
@@ -144,7 +167,7 @@ __global__ void __launch_bounds__(kThreads)
         // base+delta storage — the header and the increments recorded so far
         int const n_vec = delta ? (reinterpret_cast<const int*>(src + i * stride)[0] + 1 + 3) >> 2
                                 : (struct_size[id] + 3) >> 2;
-        warp_copy_block(src + i * stride, dst + j * stride, n_vec, lane);
+        warp_copy_block<8>(src + i * stride, dst + j * stride, n_vec, lane);
         if (lane == 0)
         {
             dst_sid[j] = id;

@@ -12,7 +12,7 @@ n = 1_250_000
 ctx = fba.Context(0)
 ctx.set_option("inplace_resample", 0)
 sim = fba.BAPOMDP(ctx, g.desc, g.t_par, g.o_par)
-for bulk in (0, 1, 0, 1):
+for bulk in (0, 1):
     ctx.set_option("bulk_copy", bulk)
     b = fba.BAImportanceSampling(n)
     rng = fba.Rng.philox(42)
