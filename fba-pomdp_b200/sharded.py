@@ -145,9 +145,15 @@ class ShardedBAImportanceSampling(BAImportanceSampling):
         self._gather_buf = torch.empty(self.world * self._window_cap * rb, dtype=torch.uint8, device="cuda")
         self._barrier = torch.zeros(1, dtype=torch.float32, device="cuda")
         if self.exchange == "p2p":
-            # publish / map the import buffers (CUDA IPC): handles travel through one all-gather
-            mine = np.zeros(64, np.uint8)
-            _check(self.ctx.h, L.fba_belief_ipc_handle(h, cap, mine.ctypes.data_as(C.c_void_p)))
+            # publish / map the import buffers (CUDA IPC): handles travel through one all-gather.
+            # If any rank cannot map its peers (no peer access / IPC in this container), every rank
+            # falls back to the all-gather exchange — the decision is made collectively.
+            ok = 1.0
+            try:
+                mine = np.zeros(64, np.uint8)
+                _check(self.ctx.h, L.fba_belief_ipc_handle(h, cap, mine.ctypes.data_as(C.c_void_p)))
+            except capi.FbaError:
+                ok = 0.0
             if self.world > 1:
                 all_h = torch.empty(self.world * 64, dtype=torch.uint8, device="cuda")
                 self.dist.all_gather_into_tensor(all_h, torch.from_numpy(mine).cuda(), group=self.group)
@@ -155,14 +161,25 @@ class ShardedBAImportanceSampling(BAImportanceSampling):
             else:
                 handles = mine
             handles = np.ascontiguousarray(handles)
-            _check(self.ctx.h, L.fba_belief_ipc_open(h, handles.ctypes.data_as(C.c_void_p), self.world, self.rank))
+            if ok:
+                try:
+                    _check(self.ctx.h,
+                           L.fba_belief_ipc_open(h, handles.ctypes.data_as(C.c_void_p), self.world, self.rank))
+                except capi.FbaError:
+                    ok = 0.0
             if self.world > 1:
-                self.dist.all_reduce(self._barrier, group=self.group)
-                self.dist.all_gather_into_tensor(self._totals, torch.zeros(1, dtype=torch.float64, device="cuda"),
-                                                 group=self.group)
-            torch.cuda.synchronize()
-            self._bufs = True
-            return
+                flag = torch.tensor([ok], dtype=torch.float32, device="cuda")
+                self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN, group=self.group)
+                ok = float(flag.item())
+            if ok:
+                if self.world > 1:
+                    self.dist.all_reduce(self._barrier, group=self.group)
+                    self.dist.all_gather_into_tensor(
+                        self._totals, torch.zeros(1, dtype=torch.float64, device="cuda"), group=self.group)
+                torch.cuda.synchronize()
+                self._bufs = True
+                return
+            self.exchange = "allgather"
         if self.world > 1:
             w = 64
             while w <= self._window_cap:  # touch every window size once (NCCL algorithm selection)
