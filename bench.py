@@ -465,7 +465,7 @@ def main_ours(args):
                    "algorithmic_bytes_per_particle_copy": bytes_per_particle,
                    "algorithmic_bytes_per_particle_propose": bytes_propose,
                    "parallelism": "particles sharded, %d rank(s)%s" % (
-                       world, ", exchange=%s" % args.exchange if world > 1 else ""),
+                       world, ", exchange=%s" % getattr(b, "exchange", args.exchange) if world > 1 else ""),
                    "last_step_phases_ms_rank0": phases,
                    "l2": "inputs (%.1f GB of counts per GPU) exceed the 126 MB L2; no flush needed"
                          % (n_local * C * 4 / 1e9),
