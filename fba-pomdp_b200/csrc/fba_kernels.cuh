@@ -1183,11 +1183,14 @@ struct BreedJob
     int state;      // domain state of the structure donor
 };
 
+constexpr int kBreedCache = 8192; // source configurations whose projection is cached per node
+
 __global__ void __launch_bounds__(kThreads)
     k_breed(DevModel M, const float* __restrict__ fc_counts, long long fc_stride, float* dst_counts,
             long long dst_stride, int* __restrict__ dst_state, int* __restrict__ dst_sid,
             const BreedJob* __restrict__ jobs)
 {
+    __shared__ short proj_of[kBreedCache];
     BreedJob const job = jobs[blockIdx.x];
     const float* src   = fc_counts + (long long)job.fc_index * fc_stride;
     float* dst         = dst_counts + (long long)job.slot * dst_stride;
@@ -1210,25 +1213,35 @@ __global__ void __launch_bounds__(kThreads)
             for (int k = threadIdx.x; k < n_src * range; k += blockDim.x) dst[d.off + k] = src[s.off + k];
             continue;
         }
+        // projection of every source configuration onto the destination parents, once per node
+        // (shared memory when it fits, recomputed per use otherwise)
+        auto project = [&](int cfg) {
+            int rem = cfg, proj = 0, mult = 1;
+            for (int f = M.FS - 1; f >= 0; --f)
+            {
+                if (!(s.par & (1u << f))) continue;
+                int const xv = rem % M.feat_s[f];
+                rem /= M.feat_s[f];
+                if (d.par & (1u << f))
+                {
+                    proj += xv * mult;
+                    mult *= M.feat_s[f];
+                }
+            }
+            return proj;
+        };
+        bool const cached = n_src <= kBreedCache;
+        __syncthreads();
+        if (cached)
+            for (int cfg = threadIdx.x; cfg < n_src; cfg += blockDim.x) proj_of[cfg] = (short)project(cfg);
+        __syncthreads();
         for (int cell = threadIdx.x; cell < n_dst * range; cell += blockDim.x)
         {
             int const dcfg = cell / range, v = cell - dcfg * range;
             float acc = 0.0f;
             for (int cfg = 0; cfg < n_src; ++cfg)
             {
-                // decode cfg over the source parents and project onto the destination parents
-                int rem = cfg, proj = 0, mult = 1;
-                for (int f = M.FS - 1; f >= 0; --f)
-                {
-                    if (!(s.par & (1u << f))) continue;
-                    int const xv = rem % M.feat_s[f];
-                    rem /= M.feat_s[f];
-                    if (d.par & (1u << f))
-                    {
-                        proj += xv * mult;
-                        mult *= M.feat_s[f];
-                    }
-                }
+                int const proj = cached ? (int)proj_of[cfg] : project(cfg);
                 if (proj == dcfg) acc = __fadd_rn(acc, src[s.off + cfg * range + v]);
             }
             dst[d.off + cell] = acc;
