@@ -105,7 +105,7 @@ struct fba_belief
     // rejection sampling wave buffers
     long long wave_cap = 0;
     int *att_src = nullptr, *att_state = nullptr, *att_accept = nullptr, *att_pos = nullptr,
-        *att_rec = nullptr, *d_total = nullptr;
+        *att_rec = nullptr, *d_total = nullptr, *att_tiles = nullptr;
     // rollout request / result staging (grow-only)
     long long roll_cap = 0, roll_cap_p = 0, step_cap = 0, step_cap_r = 0;
     int* step_i    = nullptr;
@@ -731,6 +731,7 @@ extern "C" void fba_belief_destroy(fba_belief* b)
     cudaFree(b->step_i), cudaFree(b->step_r);
     for (auto p : b->opened) cudaIpcCloseMemHandle(p);
     cudaFree(b->d_plan);
+    cudaFree(b->att_tiles);
     cudaFree(b->att_rec), cudaFree(b->d_total), cudaFree(b->xport), cudaFree(b->import_buf);
     cudaFree(b->src_of), cudaFree(b->d_quota), cudaFree(b->stats), cudaFree(b->noff), cudaFree(b->escan), cudaFree(b->dead), cudaFree(b->totals), cudaFree(b->tile_pairs);
     delete b;
@@ -1352,8 +1353,10 @@ static int ensure_wave(fba_belief* b, long long cap)
     fba_ctx* ctx = b->ctx;
     if (cap <= b->wave_cap) return FBA_OK;
     cudaFree(b->att_src), cudaFree(b->att_state), cudaFree(b->att_accept), cudaFree(b->att_pos), cudaFree(b->att_rec);
-    b->att_src = b->att_state = b->att_accept = b->att_pos = b->att_rec = nullptr;
+    cudaFree(b->att_tiles);
+    b->att_src = b->att_state = b->att_accept = b->att_pos = b->att_rec = b->att_tiles = nullptr;
     b->wave_cap = 0;
+    CU(ctx, cudaMalloc(&b->att_tiles, ((cap + kFlagTile - 1) / kFlagTile + 1) * sizeof(int)));
     CU(ctx, cudaMalloc(&b->att_src, cap * sizeof(int)));
     CU(ctx, cudaMalloc(&b->att_state, cap * sizeof(int)));
     CU(ctx, cudaMalloc(&b->att_accept, cap * sizeof(int)));
@@ -1431,7 +1434,12 @@ extern "C" int fba_belief_reject_sample(fba_belief* b, int32_t a, int32_t o, fba
             LAUNCH_RL(ctx, k_rs_attempt, rng->mode == FBA_RNG_REPLAY, b->m->long_rows, blocks_for(wave), kThreads,
                       D, b->counts[b->cur], b->stride, b->state[b->cur], b->sid[b->cur], b->N, a, o, wave, ra,
                       b->att_src, b->att_state, b->att_accept, b->att_rec, ctx->d_flag);
-        LAUNCH(ctx, k_scan_flags, 1, kThreads, b->att_accept, wave, b->att_pos, b->d_total);
+        {
+            int const n_ft = (int)((wave + kFlagTile - 1) / kFlagTile);
+            LAUNCH(ctx, k_flag_tile_counts, n_ft, kThreads, b->att_accept, wave, b->att_tiles);
+            LAUNCH(ctx, k_flag_scan_tiles, 1, kThreads, b->att_tiles, n_ft, b->d_total);
+            LAUNCH(ctx, k_flag_scan_apply, n_ft, kThreads, b->att_accept, wave, b->att_tiles, b->att_pos);
+        }
         LAUNCH(ctx, k_rs_commit, stream_grid(ctx, wave), kThreads, b->counts[b->cur], b->counts[nx], b->stride,
                b->sid[b->cur], b->sid[nx], b->state[nx], b->m->d_sizes, b->N, D.J, wave, b->att_src,
                b->att_state, b->att_accept, b->att_pos, b->att_rec, accepted, b->delta_cap > 0 ? 1 : 0,

@@ -1063,27 +1063,45 @@ __global__ void __launch_bounds__(kThreads)
     if (g.overrun) *overrun = 1;
 }
 
-// exclusive scan of 0/1 flags in one block (waves are at most a few million attempts)
+// exclusive scan of the 0/1 accept flags over a wave (up to a few million attempts), three phases:
+// per-tile counts, one-block scan of the tile counts (+ the total), per-tile scan with offset
+constexpr int kFlagTile = 2048; // flags per CTA (8 per thread)
+
 __global__ void __launch_bounds__(kThreads)
-    k_scan_flags(const int* __restrict__ flags, long long n, int* __restrict__ pos, int* __restrict__ total)
+    k_flag_tile_counts(const int* __restrict__ flags, long long n, int* __restrict__ tile_count)
+{
+    __shared__ int sh[kThreads / 32];
+    long long const base = (long long)blockIdx.x * kFlagTile;
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < kFlagTile / kThreads; ++k)
+    {
+        long long const i = base + threadIdx.x + k * kThreads;
+        if (i < n) c += flags[i];
+    }
+    for (int o = 16; o; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        int t = 0;
+        for (int k = 0; k < kThreads / 32; ++k) t += sh[k];
+        tile_count[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+    k_flag_scan_tiles(int* __restrict__ tile_count, int n_tiles, int* __restrict__ total)
 {
     __shared__ int sh[kThreads];
     __shared__ int carry;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    constexpr int PER = 8;
-    for (long long base = 0; base < n; base += (long long)kThreads * PER)
+    for (int base = 0; base < n_tiles; base += kThreads)
     {
-        int v[PER];
-        int run = 0;
-#pragma unroll
-        for (int k = 0; k < PER; ++k)
-        {
-            long long const i = base + (long long)threadIdx.x * PER + k;
-            v[k]              = (i < n) ? flags[i] : 0;
-            run += v[k];
-        }
-        sh[threadIdx.x] = run;
+        int const i = base + threadIdx.x;
+        int const v = (i < n_tiles) ? tile_count[i] : 0;
+        sh[threadIdx.x] = v;
         __syncthreads();
         for (int o = 1; o < kThreads; o <<= 1)
         {
@@ -1092,19 +1110,47 @@ __global__ void __launch_bounds__(kThreads)
             sh[threadIdx.x] += t;
             __syncthreads();
         }
-        int off = carry + sh[threadIdx.x] - run;
-#pragma unroll
-        for (int k = 0; k < PER; ++k)
-        {
-            long long const i = base + (long long)threadIdx.x * PER + k;
-            if (i < n) pos[i] = off;
-            off += v[k];
-        }
+        if (i < n_tiles) tile_count[i] = carry + sh[threadIdx.x] - v;
         __syncthreads();
         if (threadIdx.x == kThreads - 1) carry += sh[kThreads - 1];
         __syncthreads();
     }
     if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void __launch_bounds__(kThreads)
+    k_flag_scan_apply(const int* __restrict__ flags, long long n, const int* __restrict__ tile_off,
+                      int* __restrict__ pos)
+{
+    __shared__ int sh[kThreads];
+    constexpr int PER    = kFlagTile / kThreads;
+    long long const base = (long long)blockIdx.x * kFlagTile + (long long)threadIdx.x * PER;
+    int v[PER];
+    int run = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k)
+    {
+        long long const i = base + k;
+        v[k]              = (i < n) ? flags[i] : 0;
+        run += v[k];
+    }
+    sh[threadIdx.x] = run;
+    __syncthreads();
+    for (int o = 1; o < kThreads; o <<= 1)
+    {
+        int const t = (threadIdx.x >= o) ? sh[threadIdx.x - o] : 0;
+        __syncthreads();
+        sh[threadIdx.x] += t;
+        __syncthreads();
+    }
+    int off = tile_off[blockIdx.x] + sh[threadIdx.x] - run;
+#pragma unroll
+    for (int k = 0; k < PER; ++k)
+    {
+        long long const i = base + k;
+        if (i < n) pos[i] = off;
+        off += v[k];
+    }
 }
 
 // the attempt that produced the `need`-th acceptance of this wave: out[0] = its index + 1
