@@ -121,6 +121,7 @@ class BAPOMDP:
             md.start_ip[i] = int(v)
         md.start_total = float(d.get("start_total", 0.0))
         md.delta_capacity = int(d.get("delta_capacity", 0))
+        md.dirichlet_sampling = int(d.get("dirichlet_sampling", 0))
         self.S, self.A, self.O, self.FS, self.FO = md.S, md.A, md.O, len(fs), len(fo)
         t_par = np.ascontiguousarray(t_par, np.uint32).reshape(-1, self.A * self.FS)
         o_par = np.ascontiguousarray(o_par, np.uint32).reshape(-1, self.A * self.FO)

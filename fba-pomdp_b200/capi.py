@@ -18,7 +18,7 @@ MUT_FACTORED_TIGER, MUT_COLLISION_AVOIDANCE, MUT_SYSADMIN, MUT_GRIDWORLD = range
 RNG_REPLAY, RNG_PHILOX = 0, 1
 
 # every symbol include/fba_pomdp_b200.h declares (tests check the library exports all of them)
-ABI_VERSION = 4  # must equal FBA_ABI_VERSION in include/fba_pomdp_b200.h
+ABI_VERSION = 5  # must equal FBA_ABI_VERSION in include/fba_pomdp_b200.h
 
 SYMBOLS = [
     "fba_abi_version", "fba_ctx_create", "fba_ctx_destroy", "fba_last_error", "fba_ctx_stream", "fba_ctx_synchronize",
@@ -53,7 +53,7 @@ class ModelDesc(C.Structure):
         ("term_as2", C.c_void_p),
         ("action_draw", C.c_int32), ("start_kind", C.c_int32), ("start_ip", C.c_int32 * 4),
         ("start_values", C.c_void_p), ("start_total", C.c_double), ("start_table", C.c_void_p),
-        ("delta_capacity", C.c_int32),
+        ("delta_capacity", C.c_int32), ("dirichlet_sampling", C.c_int32),
     ]
 
 

@@ -185,20 +185,36 @@ static void profile_mark(fba_ctx* ctx, const char* name, bool begin)
         CU(ctx, cudaGetLastError());                                                               \
     } while (0)
 
-// kernel<REPLAY, LONG> chosen at run time
+// kernel<REPLAY, LONG, SAMPLED> chosen at run time (sampled-Dirichlet models never replay)
 #define LAUNCH_RL(ctx, kernel, replay, longrows, grid, block, ...)                                 \
     do {                                                                                           \
+        bool const smp_ = D.sampled != 0;                                                          \
         if (replay)                                                                                \
         {                                                                                          \
-            if (longrows) LAUNCH(ctx, (kernel<true, true>), grid, block, __VA_ARGS__);             \
+            if (longrows) LAUNCH(ctx, (kernel<true, true, false>), grid, block, __VA_ARGS__);      \
             else                                                                                   \
-                LAUNCH(ctx, (kernel<true, false>), grid, block, __VA_ARGS__);                      \
+                LAUNCH(ctx, (kernel<true, false, false>), grid, block, __VA_ARGS__);               \
+        } else if (smp_)                                                                           \
+        {                                                                                          \
+            if (longrows) LAUNCH(ctx, (kernel<false, true, true>), grid, block, __VA_ARGS__);      \
+            else                                                                                   \
+                LAUNCH(ctx, (kernel<false, false, true>), grid, block, __VA_ARGS__);               \
         } else                                                                                     \
         {                                                                                          \
-            if (longrows) LAUNCH(ctx, (kernel<false, true>), grid, block, __VA_ARGS__);            \
+            if (longrows) LAUNCH(ctx, (kernel<false, true, false>), grid, block, __VA_ARGS__);     \
             else                                                                                   \
-                LAUNCH(ctx, (kernel<false, false>), grid, block, __VA_ARGS__);                     \
+                LAUNCH(ctx, (kernel<false, false, false>), grid, block, __VA_ARGS__);              \
         }                                                                                          \
+    } while (0)
+
+// delta kernel<REPLAY, SAMPLED>
+#define LAUNCH_DELTA(ctx, kernel, replay, grid, block, ...)                                        \
+    do {                                                                                           \
+        if (replay) LAUNCH(ctx, (kernel<true, false>), grid, block, __VA_ARGS__);                  \
+        else if (D.sampled)                                                                        \
+            LAUNCH(ctx, (kernel<false, true>), grid, block, __VA_ARGS__);                          \
+        else                                                                                       \
+            LAUNCH(ctx, (kernel<false, false>), grid, block, __VA_ARGS__);                         \
     } while (0)
 
 // ------------------------------------------------------------------------------------------------
@@ -494,6 +510,7 @@ extern "C" int fba_model_create(fba_ctx* ctx, const fba_model_desc* d, int32_t m
     D.step_o[D.FO - 1] = 1;
     for (int f = D.FO - 2; f >= 0; --f) D.step_o[f] = D.step_o[f + 1] * D.feat_o[f + 1];
     D.tabular = d->tabular, D.domain = d->domain, D.action_draw = d->action_draw;
+    D.sampled = d->dirichlet_sampling != 0;
     for (int f = 0; f < D.FS; ++f) m->long_rows |= D.feat_s[f] > 4;
     for (int f = 0; f < D.FO; ++f) m->long_rows |= D.feat_o[f] > 4;
     memcpy(D.dom_ip, d->dom_ip, sizeof(D.dom_ip));
@@ -1004,6 +1021,8 @@ static int propose(fba_belief* b, int a, int o, fba_rng* rng, unsigned long long
     fba_ctx* ctx      = b->ctx;
     DevModel const& D = b->m->dev;
     REQUIRE(ctx, b->weighted, "importance sampling needs a weighted belief");
+    REQUIRE(ctx, !(D.sampled && rng->mode == FBA_RNG_REPLAY),
+            "sampled-Dirichlet models run in PHILOX mode (their gamma draws cannot replay libm bit for bit)");
     REQUIRE(ctx, a >= 0 && a < D.A, "action out of range");
     REQUIRE(ctx, o >= 0 && o < D.O, "observation out of range");
     CU(ctx, cudaSetDevice(ctx->device));
@@ -1015,14 +1034,14 @@ static int propose(fba_belief* b, int a, int o, fba_rng* rng, unsigned long long
             long long const per = 2ll * D.J, need = per * b->N;
             if ((rc = stage_words(ctx, rng, need))) return rc;
             if ((rc = clear_flag(ctx))) return rc;
-            LAUNCH(ctx, k_propose_delta<true>, blocks_for(b->N), kThreads, D, b->base, b->lstride, b->counts[b->cur],
-                   b->stride, b->delta_cap, b->state[b->cur], b->sid[b->cur], b->w, b->N, a, o,
-                   replay_args(ctx, need, per, false), ctx->d_flag);
+            LAUNCH_DELTA(ctx, k_propose_delta, true, blocks_for(b->N), kThreads, D, b->base, b->lstride,
+                         b->counts[b->cur], b->stride, b->delta_cap, b->state[b->cur], b->sid[b->cur], b->w, b->N,
+                         a, o, replay_args(ctx, need, per, false), ctx->d_flag);
             rng->cursor += need;
         } else
-            LAUNCH(ctx, k_propose_delta<false>, blocks_for(b->N), kThreads, D, b->base, b->lstride,
-                   b->counts[b->cur], b->stride, b->delta_cap, b->state[b->cur], b->sid[b->cur], b->w, b->N, a, o,
-                   philox_args(rng, stream_base), ctx->d_flag);
+            LAUNCH_DELTA(ctx, k_propose_delta, false, blocks_for(b->N), kThreads, D, b->base, b->lstride,
+                         b->counts[b->cur], b->stride, b->delta_cap, b->state[b->cur], b->sid[b->cur], b->w, b->N,
+                         a, o, philox_args(rng, stream_base), ctx->d_flag);
         b->suffix_valid = b->cdf_valid = false;
         return FBA_OK;
     }
@@ -1422,14 +1441,9 @@ extern "C" int fba_belief_reject_sample(fba_belief* b, int32_t a, int32_t o, fba
         if ((rc = clear_flag(ctx))) return rc;
         if (b->delta_cap > 0)
         {
-            if (rng->mode == FBA_RNG_REPLAY)
-                LAUNCH(ctx, k_rs_attempt_delta<true>, blocks_for(wave), kThreads, D, b->base, b->lstride,
-                       b->counts[b->cur], b->stride, b->state[b->cur], b->sid[b->cur], b->N, a, o, wave, ra,
-                       b->att_src, b->att_state, b->att_accept, b->att_rec, ctx->d_flag);
-            else
-                LAUNCH(ctx, k_rs_attempt_delta<false>, blocks_for(wave), kThreads, D, b->base, b->lstride,
-                       b->counts[b->cur], b->stride, b->state[b->cur], b->sid[b->cur], b->N, a, o, wave, ra,
-                       b->att_src, b->att_state, b->att_accept, b->att_rec, ctx->d_flag);
+            LAUNCH_DELTA(ctx, k_rs_attempt_delta, rng->mode == FBA_RNG_REPLAY, blocks_for(wave), kThreads, D, b->base,
+                         b->lstride, b->counts[b->cur], b->stride, b->state[b->cur], b->sid[b->cur], b->N, a, o,
+                         wave, ra, b->att_src, b->att_state, b->att_accept, b->att_rec, ctx->d_flag);
         } else
             LAUNCH_RL(ctx, k_rs_attempt, rng->mode == FBA_RNG_REPLAY, b->m->long_rows, blocks_for(wave), kThreads,
                       D, b->counts[b->cur], b->stride, b->state[b->cur], b->sid[b->cur], b->N, a, o, wave, ra,
@@ -1687,30 +1701,41 @@ extern "C" int fba_rollouts(fba_belief* b, int64_t n, const int64_t* particle, c
         if ((rc = clear_flag(ctx))) return rc;
         RngArgs const ra = replay_args(ctx, avail, 0, true);
         if (b->delta_cap > 0)
-            LAUNCH(ctx, k_rollouts_delta<true>, blocks_for(n, tpb), tpb, D, b->base, b->lstride, b->counts[b->cur],
+            LAUNCH_DELTA(ctx, k_rollouts_delta, true, blocks_for(n, tpb), tpb, D, b->base, b->lstride,
+                         b->counts[b->cur], b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r,
+                         ctx->d_flag);
+        else if (coop)
+            LAUNCH(ctx, (k_rollouts<true, true, false, false>), blocks_for(n * 32), kThreads, D, b->counts[b->cur],
                    b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag);
-        else if (coop) LAUNCH(ctx, (k_rollouts<true, true, false>), blocks_for(n * 32), kThreads, D, b->counts[b->cur],
-                         b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag);
         else if (b->m->long_rows)
-            LAUNCH(ctx, (k_rollouts<true, false, true>), blocks_for(n, tpb), tpb, D, b->counts[b->cur], b->stride,
-                   b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag);
+            LAUNCH(ctx, (k_rollouts<true, false, true, false>), blocks_for(n, tpb), tpb, D, b->counts[b->cur],
+                   b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag);
         else
-            LAUNCH(ctx, (k_rollouts<true, false, false>), blocks_for(n, tpb), tpb, D, b->counts[b->cur], b->stride,
-                   b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag);
+            LAUNCH(ctx, (k_rollouts<true, false, false, false>), blocks_for(n, tpb), tpb, D, b->counts[b->cur],
+                   b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag);
     } else
     {
         RngArgs const ra = philox_args(rng);
+        bool const lr = b->m->long_rows;
         if (b->delta_cap > 0)
-            LAUNCH(ctx, k_rollouts_delta<false>, blocks_for(n, tpb), tpb, D, b->base, b->lstride, b->counts[b->cur],
+            LAUNCH_DELTA(ctx, k_rollouts_delta, false, blocks_for(n, tpb), tpb, D, b->base, b->lstride,
+                         b->counts[b->cur], b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r,
+                         ctx->d_flag);
+        else if (coop && !D.sampled)
+            LAUNCH(ctx, (k_rollouts<false, true, false, false>), blocks_for(n * 32), kThreads, D, b->counts[b->cur],
                    b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag);
-        else if (coop) LAUNCH(ctx, (k_rollouts<false, true, false>), blocks_for(n * 32), kThreads, D, b->counts[b->cur],
-                         b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag);
-        else if (b->m->long_rows)
-            LAUNCH(ctx, (k_rollouts<false, false, true>), blocks_for(n, tpb), tpb, D, b->counts[b->cur], b->stride,
-                   b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag);
+        else if (D.sampled && lr)
+            LAUNCH(ctx, (k_rollouts<false, false, true, true>), blocks_for(n, tpb), tpb, D, b->counts[b->cur],
+                   b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag);
+        else if (D.sampled)
+            LAUNCH(ctx, (k_rollouts<false, false, false, true>), blocks_for(n, tpb), tpb, D, b->counts[b->cur],
+                   b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag);
+        else if (lr)
+            LAUNCH(ctx, (k_rollouts<false, false, true, false>), blocks_for(n, tpb), tpb, D, b->counts[b->cur],
+                   b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag);
         else
-            LAUNCH(ctx, (k_rollouts<false, false, false>), blocks_for(n, tpb), tpb, D, b->counts[b->cur], b->stride,
-                   b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag);
+            LAUNCH(ctx, (k_rollouts<false, false, false, false>), blocks_for(n, tpb), tpb, D, b->counts[b->cur],
+                   b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag);
     }
     CU(ctx, cudaMemcpyAsync(returns, d_r, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1791,9 +1816,9 @@ extern "C" int fba_step_batch(fba_belief* b, int64_t n, const int64_t* particle,
     int tpb = kThreads;
     while (tpb > 32 && (n + tpb - 1) / tpb < 2ll * ctx->sm_count) tpb >>= 1;
     if (b->delta_cap > 0)
-        LAUNCH(ctx, k_step_batch_delta<false>, blocks_for(n, tpb), tpb, D, b->base, b->lstride, b->counts[b->cur],
-               b->stride, b->sid[b->cur], (long long)n, b->roll_p, d_s, d_a, philox_args(rng), d_s2, d_o, b->step_r,
-               d_t, ctx->d_flag);
+        LAUNCH_DELTA(ctx, k_step_batch_delta, false, blocks_for(n, tpb), tpb, D, b->base, b->lstride,
+                     b->counts[b->cur], b->stride, b->sid[b->cur], (long long)n, b->roll_p, d_s, d_a, philox_args(rng),
+                     d_s2, d_o, b->step_r, d_t, ctx->d_flag);
     else
         LAUNCH_RL(ctx, k_step_batch, false, b->m->long_rows, blocks_for(n, tpb), tpb, D, b->counts[b->cur],
                   b->stride, b->sid[b->cur], (long long)n, b->roll_p, d_s, d_a, philox_args(rng), d_s2, d_o,

@@ -26,6 +26,7 @@ struct DevModel
     int feat_s[FBA_MAX_FEATURES], feat_o[FBA_MAX_FEATURES];
     int step_s[FBA_MAX_FEATURES], step_o[FBA_MAX_FEATURES]; // indexing::stepSize (index.cpp:18-49)
     int tabular, domain, action_draw;
+    int sampled; // 1: --dirichlet_sampling_method regular (sample the multinomial from the Dirichlet)
     int dom_ip[32];
     double dom_dp[8];
     const double* rew_sa;
@@ -291,6 +292,94 @@ __device__ __forceinline__ float expected_mult_at(const float* row, int n, int k
 }
 
 // ------------------------------------------------------------------------------------------------
+// Dirichlet rows, SAMPLED mode (--dirichlet_sampling_method regular):
+// the multinomial is itself drawn from the Dirichlet — p ~ Dir(counts), via one Gamma(count_i, 1)
+// per cell — before the categorical draw (sampleFromSampledMult, random.cpp:217-242) or before the
+// likelihood is read off (sampleMult, random.cpp:281-304). The reference's gamma sampler is
+// Marsaglia–Tsang fed by a 128-strip ziggurat normal (random.cpp:146-213) on libm's log/exp/pow;
+// device libm differs in the last bits, so this mode has STATISTICAL parity only (PHILOX mode):
+// the same Marsaglia–Tsang construction with a Box–Muller normal.
+// ------------------------------------------------------------------------------------------------
+template<class R>
+__device__ __forceinline__ double draw_normal(R& g)
+{
+    double const u1 = fmax(draw_u(g), 1e-300), u2 = draw_u(g);
+    return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}
+
+template<class R>
+__device__ double draw_gamma(R& g, double shape) // rnd::sample::gamma, random.cpp:189-213
+{
+    if (shape <= 0.0) return 0.0; // gamma(shape + 1) * pow(u, 1 / 0) = 0
+    double boost = 1.0;
+    if (shape < 1.0)
+    {
+        boost = pow(draw_u(g), 1.0 / shape);
+        shape += 1.0;
+    }
+    double const d = shape - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+    for (int guard = 0; guard < 1000; ++guard)
+    {
+        double x, v;
+        do {
+            x = draw_normal(g);
+            v = 1.0 + c * x;
+        } while (v <= 0.0);
+        v               = v * v * v;
+        double const u  = draw_u(g), x2 = x * x;
+        if (u < 1.0 - 0.0331 * x2 * x2) return boost * d * v;
+        if (log(u) < 0.5 * x2 + d * (1.0 - v + log(v))) return boost * d * v;
+    }
+    return boost * d;
+}
+
+// category ~ Gamma(row_i) / sum: one pass, no storage (weighted reservoir: cell i replaces the
+// current pick with probability g_i / (g_0 + … + g_i))
+template<class R>
+__device__ int sample_sampled_mult(const float* row, int n, R& g)
+{
+    double sum = 0.0;
+    int pick   = n - 1;
+    for (int i = 0; i < n; ++i)
+    {
+        double const gi = draw_gamma(g, (double)row[i]);
+        sum += gi;
+        if (gi > 0.0 && draw_u(g) * sum < gi) pick = i;
+    }
+    return pick;
+}
+
+// sampleMult(row, n)[k] (random.cpp:281-304): float gammas, float sum, float divide
+template<class R>
+__device__ float sampled_mult_at(const float* row, int n, int k, R& g)
+{
+    float sum = 0.0f, gk = 0.0f;
+    for (int i = 0; i < n; ++i)
+    {
+        float const gi = (float)draw_gamma(g, (double)row[i]);
+        sum += gi;
+        if (i == k) gk = gi;
+    }
+    return (sum > 0.0f) ? gk / sum : 0.0f;
+}
+
+// the categorical draw / the likelihood factor in whichever mode the model is in
+// (SAMPLED is a template parameter, not a run-time branch: the expected-mode kernels keep their
+// register footprint — k_propose stays at 40 registers without spills)
+template<bool LONG, bool SAMPLED, class R>
+__device__ __forceinline__ int sample_row(const float* row, int n, R& g)
+{
+    if (SAMPLED) return sample_sampled_mult(row, n, g);
+    return sample_expected_mult<LONG>(row, n, draw_u(g));
+}
+template<bool SAMPLED, class R>
+__device__ __forceinline__ float likelihood_at(const float* row, int n, int k, R& g)
+{
+    if (SAMPLED) return sampled_mult_at(row, n, k, g);
+    return expected_mult_at(row, n, k);
+}
+
+// ------------------------------------------------------------------------------------------------
 // feature vectors: up to 16 features of <= 256 values packed in two 64-bit words, so that no
 // per-thread array (and no local memory) is needed. A single feature (tabular) keeps its full value.
 // ------------------------------------------------------------------------------------------------
@@ -453,7 +542,7 @@ enum StepMode {
 // Returns s'; o_out = simulated observation. x_new returns the new state's features.
 // COOP: the 32 lanes of a warp run ONE step together (identical arguments and random source in
 // every lane) and load each row cooperatively — for latency-bound small batches of rollouts.
-template<int MODE, class R, bool COOP = false, bool LONG = false>
+template<int MODE, class R, bool COOP = false, bool LONG = false, bool SAMPLED = false>
 __device__ __forceinline__ int hyper_step(const DevModel& M, const Node* __restrict__ nodes,
                                           float* counts, int s, R& g, int& o_out, Feat& x_new,
                                           int* rec)
@@ -471,7 +560,7 @@ __device__ __forceinline__ int hyper_step(const DevModel& M, const Node* __restr
         int const range = M.feat_s[f];
         int const cell  = nd.off + parent_config(M, nd.par, x) * range;
         int const v     = COOP ? sample_expected_mult_warp(counts + cell, range, draw_u(g))
-                               : sample_expected_mult<LONG>(counts + cell, range, draw_u(g));
+                               : sample_row<LONG, SAMPLED>(counts + cell, range, g);
         x2.set(f, v, single_s);
         s2 += v * M.step_s[f];
         if (MODE == STEP_UPDATE) counts[cell + v] = __fadd_rn(counts[cell + v], 1.0f);
@@ -490,7 +579,7 @@ __device__ __forceinline__ int hyper_step(const DevModel& M, const Node* __restr
         int const range = M.feat_o[q];
         int const cell  = nd.off + parent_config(M, nd.par, x2) * range;
         int const v     = COOP ? sample_expected_mult_warp(counts + cell, range, draw_u(g))
-                               : sample_expected_mult<LONG>(counts + cell, range, draw_u(g));
+                               : sample_row<LONG, SAMPLED>(counts + cell, range, g);
         of.set(q, v, single_o);
         o += v * M.step_o[q];
     }
@@ -518,14 +607,15 @@ __device__ __forceinline__ int hyper_step(const DevModel& M, const Node* __restr
 
 // BA{Flat,BN}Model::computeObservationProbability, expected mode
 // (BAFlatModel.cpp:105-124, BABNModel.cpp:328-352), for the state whose features are x
+template<bool SAMPLED, class R>
 __device__ __forceinline__ double obs_probability(const DevModel& M, const Node* __restrict__ nodes,
-                                                  const float* counts, const Feat& x, int o)
+                                                  const float* counts, const Feat& x, int o, R& g)
 {
     if (M.tabular)
     {
         if (M.O == 1) return 1.0;
         Node const nd = nodes[M.FS];
-        return (double)expected_mult_at(counts + nd.off + (int)x.lo * M.O, M.O, o);
+        return (double)likelihood_at<SAMPLED>(counts + nd.off + (int)x.lo * M.O, M.O, o, g);
     }
     Feat const of       = decode(o, M.step_o, M.FO);
     bool const single_o = (M.FO == 1);
@@ -535,7 +625,7 @@ __device__ __forceinline__ double obs_probability(const DevModel& M, const Node*
         Node const nd   = nodes[M.FS + q];
         int const range = M.feat_o[q];
         int const cell  = nd.off + parent_config(M, nd.par, x) * range;
-        prob = __dmul_rn(prob, (double)expected_mult_at(counts + cell, range, of.get(q, single_o)));
+        prob = __dmul_rn(prob, (double)likelihood_at<SAMPLED>(counts + cell, range, of.get(q, single_o), g));
     }
     return prob;
 }
@@ -565,7 +655,7 @@ __device__ __forceinline__ void delta_row(const float* __restrict__ base, const 
 
 // BAPOMDP::step on a delta particle (tabular: one transition node and one observation node per
 // action). overflow is set when the increment list is full (the increments are then dropped).
-template<int MODE, class R>
+template<int MODE, bool SAMPLED, class R>
 __device__ __forceinline__ int hyper_step_delta(const DevModel& M, const Node* __restrict__ nodes,
                                                 const float* __restrict__ base, int* block, int cap, int s,
                                                 R& g, int& o_out, int* rec, int* overflow)
@@ -573,10 +663,10 @@ __device__ __forceinline__ int hyper_step_delta(const DevModel& M, const Node* _
     float buf[kMaxDeltaRow];
     int const cell_t = nodes[0].off + s * M.S; // phi[s][a][.]
     delta_row(base, block, cell_t, M.S, buf);
-    int const s2     = sample_expected_mult<true>(buf, M.S, draw_u(g));
+    int const s2     = sample_row<true, SAMPLED>(buf, M.S, g);
     int const cell_o = nodes[1].off + s2 * M.O; // psi[a][s'][.]
     delta_row(base, block, cell_o, M.O, buf);
-    int const o = sample_expected_mult<true>(buf, M.O, draw_u(g));
+    int const o = sample_row<true, SAMPLED>(buf, M.O, g);
     if (MODE == STEP_UPDATE)
     { // incrementCountsOf(s, a, o, s') (BAFlatModel.cpp:126-141)
         int const ne = block[0];
@@ -597,14 +687,15 @@ __device__ __forceinline__ int hyper_step_delta(const DevModel& M, const Node* _
     return s2;
 }
 
+template<bool SAMPLED, class R>
 __device__ __forceinline__ double obs_probability_delta(const DevModel& M, const Node* __restrict__ nodes,
                                                         const float* __restrict__ base, const int* block,
-                                                        int s2, int o)
+                                                        int s2, int o, R& g)
 {
     if (M.O == 1) return 1.0; // BAFlatModel.cpp:117-120
     float buf[kMaxDeltaRow];
     delta_row(base, block, nodes[1].off + s2 * M.O, M.O, buf);
-    return (double)expected_mult_at(buf, M.O, o);
+    return (double)likelihood_at<SAMPLED>(buf, M.O, o, g);
 }
 #endif // __CUDACC__
 

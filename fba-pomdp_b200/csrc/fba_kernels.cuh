@@ -296,11 +296,11 @@ __global__ void __launch_bounds__(32)
 // importance_sampling::update, per-particle part (ImportanceSampler.hpp:37-54): step in place,
 // weight *= P(o | a, particle). One thread per particle.
 // ------------------------------------------------------------------------------------------------
-template<bool REPLAY, bool LONG>
+template<bool REPLAY, bool LONG, bool SAMPLED>
 #ifndef FBA_PROPOSE_MIN_BLOCKS
 #define FBA_PROPOSE_MIN_BLOCKS 6 // 40 registers, no spills: measured 4 % faster than 48 (tools/exp_propose.py)
 #endif
-__global__ void __launch_bounds__(kThreads, LONG ? 1 : FBA_PROPOSE_MIN_BLOCKS)
+__global__ void __launch_bounds__(kThreads, (LONG || SAMPLED) ? 1 : FBA_PROPOSE_MIN_BLOCKS)
     k_propose(DevModel M, float* counts, long long stride, int* __restrict__ state,
               const int* __restrict__ sid, double* __restrict__ w, long long N, int a, int o, RngArgs ra,
               int* __restrict__ overrun)
@@ -312,8 +312,8 @@ __global__ void __launch_bounds__(kThreads, LONG ? 1 : FBA_PROPOSE_MIN_BLOCKS)
     float* c          = counts + i * stride;
     int sim_o;
     Feat x2;
-    int const s2 = hyper_step<STEP_UPDATE, decltype(g), false, LONG>(M, nodes, c, state[i], g, sim_o, x2, nullptr);
-    double const prob = obs_probability(M, nodes, c, x2, o);
+    int const s2 = hyper_step<STEP_UPDATE, decltype(g), false, LONG, SAMPLED>(M, nodes, c, state[i], g, sim_o, x2, nullptr);
+    double const prob = obs_probability<SAMPLED>(M, nodes, c, x2, o, g);
     state[i]          = s2;
     w[i]              = __dmul_rn(w[i], prob);
     if (g.overrun) *overrun = 1;
@@ -930,7 +930,7 @@ __global__ void __launch_bounds__(kThreads)
 // COOP = false: one thread per rollout (large batches: most independent work per SM).
 // COOP = true: one warp per rollout, rows loaded cooperatively (small batches are latency-bound:
 // one coalesced request per row instead of `range` dependent ones).
-template<bool REPLAY, bool COOP, bool LONG>
+template<bool REPLAY, bool COOP, bool LONG, bool SAMPLED>
 __global__ void __launch_bounds__(kThreads)
     k_rollouts(DevModel M, const float* counts, long long stride, const int* __restrict__ sid,
                long long n, const long long* __restrict__ particle, const int* __restrict__ start,
@@ -954,7 +954,7 @@ __global__ void __launch_bounds__(kThreads)
         int o;
         Feat x2;
         int const s2 =
-            hyper_step<STEP_KEEP, decltype(g), COOP, LONG>(M, base + (long long)a * M.J, c, s, g, o, x2, nullptr);
+            hyper_step<STEP_KEEP, decltype(g), COOP, LONG, SAMPLED>(M, base + (long long)a * M.J, c, s, g, o, x2, nullptr);
         double const rew = domain_reward(M, s, a, s2, terminal);
         ret  = __dadd_rn(ret, __dmul_rn(rew, disc)); // Return::add (Return.cpp:6-9)
         disc = __dmul_rn(disc, discount);            // Discount::increment (Discount.cpp:8-11)
@@ -973,7 +973,7 @@ __global__ void __launch_bounds__(kThreads)
 // from given (particle, domain state, action) triples — the in-tree steps of a wave of POMCP
 // simulations (RBAPOUCT::traverseChanceNode, RBAPOUCT.cpp:249). One thread per request.
 // ------------------------------------------------------------------------------------------------
-template<bool REPLAY, bool LONG>
+template<bool REPLAY, bool LONG, bool SAMPLED>
 __global__ void __launch_bounds__(kThreads)
     k_step_batch(DevModel M, const float* counts, long long stride, const int* __restrict__ sid, long long n,
                  const long long* __restrict__ particle, const int* __restrict__ state,
@@ -991,7 +991,7 @@ __global__ void __launch_bounds__(kThreads)
     int o;
     Feat x2;
     int const s  = state[r];
-    int const s2 = hyper_step<STEP_KEEP, decltype(g), false, LONG>(M, nodes, c, s, g, o, x2, nullptr);
+    int const s2 = hyper_step<STEP_KEEP, decltype(g), false, LONG, SAMPLED>(M, nodes, c, s, g, o, x2, nullptr);
     bool term;
     reward[r]    = domain_reward(M, s, a, s2, term);
     new_state[r] = s2;
@@ -1039,7 +1039,7 @@ __global__ void __launch_bounds__(kThreads)
 // attempt t picks a particle uniformly, simulates a step on it WITHOUT touching it and records the
 // outcome; the accepted attempts, in attempt order, become the new particles.
 // ------------------------------------------------------------------------------------------------
-template<bool REPLAY, bool LONG>
+template<bool REPLAY, bool LONG, bool SAMPLED>
 __global__ void __launch_bounds__(kThreads)
     k_rs_attempt(DevModel M, const float* counts, long long stride, const int* __restrict__ state,
                  const int* __restrict__ sid, long long N, int a, int o, long long n_attempts,
@@ -1055,7 +1055,7 @@ __global__ void __launch_bounds__(kThreads)
     int rec[2 * FBA_MAX_FEATURES];
     int sim_o;
     Feat x2;
-    int const s2 = hyper_step<STEP_RECORD, decltype(g), false, LONG>(M, nodes, c, state[i], g, sim_o, x2, rec);
+    int const s2 = hyper_step<STEP_RECORD, decltype(g), false, LONG, SAMPLED>(M, nodes, c, state[i], g, sim_o, x2, rec);
     src_out[t]    = i;
     state_out[t]  = s2;
     accept_out[t] = (sim_o == o) ? 1 : 0;
@@ -1321,7 +1321,7 @@ __global__ void __launch_bounds__(kThreads)
     if (w) w[i] = 1.0 / (double)N;
 }
 
-template<bool REPLAY>
+template<bool REPLAY, bool SAMPLED>
 __global__ void __launch_bounds__(kThreads)
     k_propose_delta(DevModel M, const float* __restrict__ base, long long base_stride, float* blocks,
                     long long stride, int cap, int* __restrict__ state, const int* __restrict__ sid,
@@ -1334,14 +1334,14 @@ __global__ void __launch_bounds__(kThreads)
     const float* tb   = base + (long long)sid[i] * base_stride;
     int* block        = reinterpret_cast<int*>(blocks + i * stride);
     int sim_o;
-    int const s2 = hyper_step_delta<STEP_UPDATE>(M, nodes, tb, block, cap, state[i], g, sim_o, nullptr, overrun);
-    double const prob = obs_probability_delta(M, nodes, tb, block, s2, o);
+    int const s2 = hyper_step_delta<STEP_UPDATE, SAMPLED>(M, nodes, tb, block, cap, state[i], g, sim_o, nullptr, overrun);
+    double const prob = obs_probability_delta<SAMPLED>(M, nodes, tb, block, s2, o, g);
     state[i]          = s2;
     w[i]              = __dmul_rn(w[i], prob);
     if (g.overrun) *overrun = 1;
 }
 
-template<bool REPLAY>
+template<bool REPLAY, bool SAMPLED>
 __global__ void __launch_bounds__(kThreads)
     k_rollouts_delta(DevModel M, const float* __restrict__ base, long long base_stride, const float* blocks,
                      long long stride, const int* __restrict__ sid, long long n,
@@ -1362,7 +1362,7 @@ __global__ void __launch_bounds__(kThreads)
     {
         int const a = random_action(M, g);
         int o;
-        int const s2 = hyper_step_delta<STEP_KEEP>(M, M.nodes + (long long)a * M.J, tb, block, 0, s, g, o,
+        int const s2 = hyper_step_delta<STEP_KEEP, SAMPLED>(M, M.nodes + (long long)a * M.J, tb, block, 0, s, g, o,
                                                    nullptr, nullptr);
         double const rew = domain_reward(M, s, a, s2, terminal);
         ret  = __dadd_rn(ret, __dmul_rn(rew, disc));
@@ -1374,7 +1374,7 @@ __global__ void __launch_bounds__(kThreads)
     if (g.overrun) *overrun = 1;
 }
 
-template<bool REPLAY>
+template<bool REPLAY, bool SAMPLED>
 __global__ void __launch_bounds__(kThreads)
     k_step_batch_delta(DevModel M, const float* __restrict__ base, long long base_stride, const float* blocks,
                        long long stride, const int* __restrict__ sid, long long n,
@@ -1390,7 +1390,7 @@ __global__ void __launch_bounds__(kThreads)
     int const a       = action[r];
     int o;
     int const s  = state[r];
-    int const s2 = hyper_step_delta<STEP_KEEP>(
+    int const s2 = hyper_step_delta<STEP_KEEP, SAMPLED>(
         M, M.nodes + (long long)a * M.J, base + (long long)sid[p] * base_stride,
         reinterpret_cast<int*>(const_cast<float*>(blocks) + p * stride), 0, s, g, o, nullptr, nullptr);
     bool term;
@@ -1401,7 +1401,7 @@ __global__ void __launch_bounds__(kThreads)
     if (g.overrun) *overrun = 1;
 }
 
-template<bool REPLAY>
+template<bool REPLAY, bool SAMPLED>
 __global__ void __launch_bounds__(kThreads)
     k_rs_attempt_delta(DevModel M, const float* __restrict__ base, long long base_stride, const float* blocks,
                        long long stride, const int* __restrict__ state, const int* __restrict__ sid, long long N,
@@ -1415,7 +1415,7 @@ __global__ void __launch_bounds__(kThreads)
     int const i = draw_k(g, (uint32_t)N);
     int rec[2];
     int sim_o;
-    int const s2 = hyper_step_delta<STEP_RECORD>(
+    int const s2 = hyper_step_delta<STEP_RECORD, SAMPLED>(
         M, M.nodes + (long long)a * M.J, base + (long long)sid[i] * base_stride,
         reinterpret_cast<int*>(const_cast<float*>(blocks) + (long long)i * stride), 0, state[i], g, sim_o, rec,
         nullptr);

@@ -98,6 +98,9 @@ public:
         long long const dense_cells = (long long)d.A * d.S * d.S + (long long)d.A * d.S * d.O;
         if (delta_capacity < 0) delta_capacity = (d.tabular && dense_cells * 4 > (256 << 10)) ? 2048 : 0;
         d.delta_capacity = d.tabular ? delta_capacity : 0;
+        // --dirichlet_sampling_method regular (BAPOMDP.cpp:197-201): every draw first samples the
+        // multinomial from the particle's Dirichlets instead of using their expectation
+        d.dirichlet_sampling = sampledDirichlets() ? 1 : 0;
         d.action_draw = FBA_ACT_UNIFORM_INT; // rollouts only; all reference domains draw uniformly
         d.start_kind  = FBA_START_CONST;     // unused: start states come from the host domain
 
@@ -304,6 +307,8 @@ private:
     // by stepping a scratch particle whose counts force the transition s -> s2 … too slow; instead
     // the extension is reached through the friend-free public hook below.
     double rewardOf(int s, Action const* a, int s2, uint8_t* terminal) const;
+    // whether the simulator was built with rnd::sample::Dir::Regular (BAConf.hpp:22)
+    bool sampledDirichlets() const;
 };
 
 // Specialisation point: how to reach BADomainExtension from a BAPOMDP. In the reference the
@@ -319,6 +324,10 @@ inline double CudaSimulator::rewardOf(int s, Action const* a, int s2, uint8_t* t
     *terminal = ext->terminal(st, a, st2).terminated();
     return ext->reward(st, a, st2).toDouble();
 }
+inline bool CudaSimulator::sampledDirichlets() const
+{
+    return _sim._sample_method == &rnd::sample::Dir::sampleFromSampledMult;
+}
 #else
 inline double CudaSimulator::rewardOf(int s, Action const* a, int s2, uint8_t* terminal) const
 {
@@ -327,6 +336,10 @@ inline double CudaSimulator::rewardOf(int s, Action const* a, int s2, uint8_t* t
     auto st2  = ext->getState(s2);
     *terminal = ext->terminal(st, a, st2).terminated();
     return ext->reward(st, a, st2).toDouble();
+}
+inline bool CudaSimulator::sampledDirichlets() const
+{
+    return _sim.samplesDirichlets(); // accessor added per INTEGRATION.md
 }
 #endif
 

@@ -31,7 +31,7 @@ extern "C" {
 
 #define FBA_MAX_FEATURES 16
 /* bumped whenever a struct below changes layout; compare with fba_abi_version() after loading */
-#define FBA_ABI_VERSION 4
+#define FBA_ABI_VERSION 5
 
 typedef struct fba_ctx fba_ctx;
 typedef struct fba_model fba_model;
@@ -110,6 +110,12 @@ typedef struct fba_model_desc {
      * (gridworld --size 5: 720 KB per particle); stands in for BAFlatModel's copy-on-write rows
      * (src/bayes-adaptive/states/table/BAFlatModel.cpp:185-252,284-354). */
     int32_t delta_capacity;
+    /* 0: expected-Dirichlet mode, the reference default (--dirichlet_sampling_method expected,
+     * BAConf.hpp:22; sampleFromExpectedMult / expectedMult). 1: sampled mode (regular): the
+     * multinomial is drawn from the Dirichlet for every step and every likelihood
+     * (sampleFromSampledMult / sampleMult, src/utils/random.cpp:217-242,281-304). PHILOX mode only;
+     * statistical parity (device libm differs from glibc in the last bits of log / pow). */
+    int32_t dirichlet_sampling;
 } fba_model_desc;
 
 enum fba_rng_mode { FBA_RNG_REPLAY = 0, FBA_RNG_PHILOX = 1 };

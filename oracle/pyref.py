@@ -23,9 +23,9 @@ def lib():
     global _lib
     if _lib is None:
         L = C.CDLL(LIB_PATH)
-        L.ref_open.restype = C.c_void_p
-        L.ref_open.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p,
-                               C.c_double, C.c_int, C.c_char_p]
+        L.ref_open_ex.restype = C.c_void_p
+        L.ref_open_ex.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p,
+                                  C.c_double, C.c_int, C.c_char_p, C.c_int]
         L.ref_error.restype = C.c_char_p
         L.ref_error.argtypes = [C.c_void_p]
         L.ref_close.argtypes = [C.c_void_p]
@@ -80,10 +80,10 @@ class Ref:
     global RNG, so only one Ref should be active at a time."""
 
     def __init__(self, domain, size=0, width=0, height=0, factored=False, structure_prior="",
-                 discount=0.95, horizon=20, seed="42"):
+                 discount=0.95, horizon=20, seed="42", sampled=False):
         self.L = lib()
-        self.h = self.L.ref_open(domain.encode(), size, width, height, int(factored),
-                                 structure_prior.encode(), discount, horizon, seed.encode())
+        self.h = self.L.ref_open_ex(domain.encode(), size, width, height, int(factored),
+                                    structure_prior.encode(), discount, horizon, seed.encode(), int(sampled))
         err = self.L.ref_error(self.h).decode()
         if err:
             raise RuntimeError("reference: " + err)

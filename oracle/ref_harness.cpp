@@ -135,7 +135,8 @@ uint32_t maskOf(std::vector<int> const& parents)
 extern "C" {
 
 // domain: reference -D string. factored: 0 = tabular BA-POMDP (makeTBAPOMDP), 1 = FBA-POMDP.
-void* ref_open(
+// sampled: 0 = expected Dirichlets (the reference default), 1 = --dirichlet_sampling_method regular
+void* ref_open_ex(
     char const* domain,
     int size,
     int width,
@@ -144,7 +145,8 @@ void* ref_open(
     char const* structure_prior,
     double discount,
     int horizon,
-    char const* seed)
+    char const* seed,
+    int sampled)
 {
     auto h = new Handle();
     try
@@ -165,7 +167,8 @@ void* ref_open(
         c.structure_prior       = structure_prior;
         c.discount              = discount;
         c.horizon               = horizon;
-        c.bayes_sample_method   = rnd::sample::Dir::Expected; // the reference default (BAConf.hpp:22)
+        c.bayes_sample_method   = sampled ? rnd::sample::Dir::Regular
+                                          : rnd::sample::Dir::Expected; // the default (BAConf.hpp:22)
         c.planner_conf.mcts_max_depth         = horizon;
         c.planner_conf.mcts_simulation_amount = 16;
 
@@ -195,6 +198,20 @@ void* ref_open(
         h->err = e.what();
     }
     return h;
+}
+
+void* ref_open(
+    char const* domain,
+    int size,
+    int width,
+    int height,
+    int factored,
+    char const* structure_prior,
+    double discount,
+    int horizon,
+    char const* seed)
+{
+    return ref_open_ex(domain, size, width, height, factored, structure_prior, discount, horizon, seed, 0);
 }
 
 char const* ref_error(void* hv)
