@@ -89,7 +89,7 @@ struct PhiloxRng
 {
     uint32_t k0, k1;
     uint32_t c0, c1, c2, c3;
-    uint32_t buf[4];
+    uint32_t b0, b1, b2, b3; // buffered words, handed out b0 first (registers: no indexed array)
     int have;
     int overrun; // never set; keeps the two sources interchangeable
 
@@ -119,14 +119,17 @@ struct PhiloxRng
             a += 0x9E3779B9u;
             b += 0xBB67AE85u;
         }
-        buf[0] = x0, buf[1] = x1, buf[2] = x2, buf[3] = x3;
+        b0 = x3, b1 = x2, b2 = x1, b3 = x0;
         ++c0;
         have = 4;
     }
     __host__ __device__ uint32_t next()
     {
         if (!have) refill();
-        return buf[--have];
+        uint32_t const r = b0;
+        b0 = b1, b1 = b2, b2 = b3;
+        --have;
+        return r;
     }
 };
 

@@ -21,5 +21,5 @@ for t in range(12):
     b.updateEstimation(*script[(5 + t) % len(script)], rng, want_likelihood=False)
 ctx.profile_end()
 kt = ctx.kernel_times()
-print(os.environ.get("FBA_B200_LIB", "default").split("/")[-1], "L2fetch", os.environ.get("FBA_B200_L2_FETCH", "-"),
+print(os.environ.get("FBA_B200_LIB", "default").split("/")[-1], 
       {k: round(v[0] / v[1], 4) for k, v in kt.items() if k.startswith(("k_copy", "k_propose"))})
