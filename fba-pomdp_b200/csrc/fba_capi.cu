@@ -225,6 +225,8 @@ extern "C" int fba_abi_version(void)
     return FBA_ABI_VERSION;
 }
 
+extern "C" void fba_ctx_destroy(fba_ctx* ctx);
+
 extern "C" int fba_ctx_create(int device, fba_ctx** out)
 {
     if (!out) return FBA_ERR_INVALID;
@@ -244,7 +246,7 @@ extern "C" int fba_ctx_create(int device, fba_ctx** out)
     if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_scal, 4 * sizeof(double));
     if (e != cudaSuccess)
     {
-        delete ctx;
+        fba_ctx_destroy(ctx);
         return FBA_ERR_CUDA;
     }
     *out = ctx;
@@ -255,14 +257,14 @@ extern "C" void fba_ctx_destroy(fba_ctx* ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
     cudaFree(ctx->d_words);
     cudaFree(ctx->d_offsets);
     cudaFree(ctx->d_flag);
     cudaFreeHost(ctx->h_flag);
     cudaFreeHost(ctx->h_scal);
-    cudaStreamDestroy(ctx->stream);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
@@ -272,16 +274,17 @@ extern "C" const char* fba_last_error(const fba_ctx* ctx)
 }
 extern "C" void* fba_ctx_stream(const fba_ctx* ctx)
 {
-    return (void*)ctx->stream;
+    return ctx ? (void*)ctx->stream : nullptr;
 }
 extern "C" int fba_ctx_synchronize(fba_ctx* ctx)
 {
+    if (!ctx) return FBA_ERR_INVALID;
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return FBA_OK;
 }
 extern "C" int64_t fba_ctx_launch_count(const fba_ctx* ctx)
 {
-    return ctx->launches;
+    return ctx ? ctx->launches : -1;
 }
 
 extern "C" int fba_ctx_set_option(fba_ctx* ctx, const char* name, int64_t value)
@@ -380,9 +383,12 @@ static int stage_words(fba_ctx* ctx, const fba_rng* rng, long long n)
     }
     if ((size_t)n > ctx->words_cap)
     {
-        cudaFree(ctx->d_words);
-        ctx->words_cap = (size_t)n + (size_t)n / 2 + 1024;
-        CU(ctx, cudaMalloc(&ctx->d_words, ctx->words_cap * sizeof(uint32_t)));
+        cudaFree(ctx->d_words); // (synchronises: no kernel still reads the old buffer)
+        ctx->d_words     = nullptr;
+        ctx->words_cap   = 0;
+        size_t const cap = (size_t)n + (size_t)n / 2 + 1024;
+        CU(ctx, cudaMalloc(&ctx->d_words, cap * sizeof(uint32_t)));
+        ctx->words_cap = cap;
     }
     if (n)
         CU(ctx, cudaMemcpyAsync(ctx->d_words, rng->words + rng->cursor, (size_t)n * sizeof(uint32_t),
@@ -395,8 +401,11 @@ static int stage_offsets(fba_ctx* ctx, const std::vector<long long>& off)
     if (off.size() > ctx->offsets_cap)
     {
         cudaFree(ctx->d_offsets);
-        ctx->offsets_cap = off.size() + off.size() / 2 + 1024;
-        CU(ctx, cudaMalloc(&ctx->d_offsets, ctx->offsets_cap * sizeof(long long)));
+        ctx->d_offsets   = nullptr;
+        ctx->offsets_cap = 0;
+        size_t const cap = off.size() + off.size() / 2 + 1024;
+        CU(ctx, cudaMalloc(&ctx->d_offsets, cap * sizeof(long long)));
+        ctx->offsets_cap = cap;
     }
     // pageable source: the copy is staged before the call returns, so `off` may die afterwards
     CU(ctx, cudaMemcpyAsync(ctx->d_offsets, off.data(), off.size() * sizeof(long long),
@@ -456,8 +465,8 @@ static int to_device(fba_model* m, const T* host, size_t n, const T** out)
     if (!host || !n) return FBA_OK;
     T* d = nullptr;
     CU(m->ctx, cudaMalloc(&d, n * sizeof(T)));
+    m->owned.push_back(d); // owned from here on: freed by fba_model_destroy even if the copy fails
     CU(m->ctx, cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice));
-    m->owned.push_back(d);
     *out = d;
     return FBA_OK;
 }
@@ -601,7 +610,9 @@ static int add_structures(fba_model* m, int32_t n, const uint32_t* t_par, const 
     int const nT = D.A * D.FS, nO = D.A * D.FO;
     int const first_new = m->n_structs;
     uint32_t const full = (D.FS >= 32) ? 0xffffffffu : ((1u << D.FS) - 1u);
-    for (int k = 0; k < n; ++k)
+    int rc = FBA_OK;
+    std::vector<Node> fresh((size_t)D.A * D.J);
+    for (int k = 0; k < n && rc == FBA_OK; ++k)
     {
         const uint32_t* tp = t_par + (size_t)k * nT;
         const uint32_t* op = o_par + (size_t)k * nO;
@@ -612,37 +623,51 @@ static int add_structures(fba_model* m, int32_t n, const uint32_t* t_par, const 
         if (it != m->index.end()) id = it->second;
         else
         {
-            if (m->n_structs >= m->max_structs)
-            {
-                ctx->err = "structure table full (" + std::to_string(m->max_structs) + ")";
-                return FBA_ERR_CAPACITY;
-            }
-            id = m->n_structs++;
-            m->index[key] = id;
-            m->t_par.insert(m->t_par.end(), tp, tp + nT);
-            m->o_par.insert(m->o_par.end(), op, op + nO);
+            // lay the structure out first; it is registered only once it is known to be valid
             long long off = 0;
-            Node* nodes   = m->h_nodes.data() + (size_t)id * D.A * D.J;
-            for (int a = 0; a < D.A; ++a)
+            for (int a = 0; a < D.A && rc == FBA_OK; ++a)
                 for (int j = 0; j < D.J; ++j)
                 {
                     uint32_t const par = (j < D.FS) ? tp[a * D.FS + j] : op[a * D.FO + (j - D.FS)];
-                    REQUIRE(ctx, (par & ~full) == 0, "structure: parent mask names a missing feature");
-                    long long cfgs = 1;
+                    long long cfgs     = 1;
                     for (int f = 0; f < D.FS; ++f)
                         if (par & (1u << f)) cfgs *= D.feat_s[f];
-                    int const range       = (j < D.FS) ? D.feat_s[j] : D.feat_o[j - D.FS];
-                    nodes[a * D.J + j].par = par;
-                    nodes[a * D.J + j].off = (int32_t)off;
+                    int const range        = (j < D.FS) ? D.feat_s[j] : D.feat_o[j - D.FS];
+                    fresh[a * D.J + j].par = par;
+                    fresh[a * D.J + j].off = (int32_t)off;
                     off += cfgs * range;
-                    REQUIRE(ctx, off < (1ll << 31), "structure: count block exceeds 2^31 cells");
+                    if ((par & ~full) != 0) ctx->err = "structure: parent mask names a missing feature", rc = FBA_ERR_INVALID;
+                    else if (off >= (1ll << 31))
+                        ctx->err = "structure: count block exceeds 2^31 cells", rc = FBA_ERR_INVALID;
+                    if (rc != FBA_OK) break;
                 }
+            if (rc == FBA_OK && m->n_structs >= m->max_structs)
+            {
+                ctx->err = "structure table full (" + std::to_string(m->max_structs) + ")";
+                rc       = FBA_ERR_CAPACITY;
+            }
+            if (rc != FBA_OK) break;
+            id            = m->n_structs++;
+            m->index[key] = id;
+            m->t_par.insert(m->t_par.end(), tp, tp + nT);
+            m->o_par.insert(m->o_par.end(), op, op + nO);
+            std::copy(fresh.begin(), fresh.end(), m->h_nodes.begin() + (size_t)id * D.A * D.J);
             m->sizes.push_back((int)off);
         }
         if (ids_out) ids_out[k] = id;
     }
-    if (upload) return upload_structures(m, first_new);
-    return FBA_OK;
+    // structures registered before a failing one stay registered, so they are uploaded either way
+    // (only entries [first_new, n_structs) are written: no particle names them yet, so kernels in
+    // flight on the context's stream never read what this copy writes)
+    if (upload)
+    {
+        std::string const keep = ctx->err;
+        int const up           = upload_structures(m, first_new);
+        if (rc != FBA_OK) ctx->err = keep;
+        else
+            rc = up;
+    }
+    return rc;
 }
 
 extern "C" int32_t fba_model_num_structures(const fba_model* m)
@@ -695,13 +720,11 @@ extern "C" int fba_belief_create(fba_ctx* ctx, fba_model* m, int64_t N, int64_t 
     b->lstride   = lstride;
     b->delta_cap = m->delta_cap;
     b->weighted = weighted != 0;
-    cudaError_t e = cudaSuccess;
-    for (int k = 0; k < 2 && e == cudaSuccess; ++k)
-    {
-        e = cudaMalloc(&b->counts[k], (size_t)N * stride * sizeof(float));
-        if (e == cudaSuccess) e = cudaMalloc(&b->state[k], (size_t)N * sizeof(int));
-        if (e == cudaSuccess) e = cudaMalloc(&b->sid[k], (size_t)N * sizeof(int));
-    }
+    // only the front buffer: the back buffer (full-copy resampling, rejection sampling) is allocated
+    // on first use (ensure_next), so a production belief that resamples in place can fill the HBM
+    cudaError_t e = cudaMalloc(&b->counts[0], (size_t)N * stride * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&b->state[0], (size_t)N * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&b->sid[0], (size_t)N * sizeof(int));
     long long const n_tiles = (N + kTile - 1) / kTile;
     if (e == cudaSuccess) e = cudaMalloc(&b->w, (size_t)N * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&b->aux, (size_t)N * sizeof(double));
@@ -764,19 +787,19 @@ extern "C" int64_t fba_belief_stride(const fba_belief* b)
 }
 extern "C" void* fba_belief_counts_ptr(fba_belief* b)
 {
-    return b->counts[b->cur];
+    return b ? b->counts[b->cur] : nullptr;
 }
 extern "C" void* fba_belief_state_ptr(fba_belief* b)
 {
-    return b->state[b->cur];
+    return b ? b->state[b->cur] : nullptr;
 }
 extern "C" void* fba_belief_weight_ptr(fba_belief* b)
 {
-    return b->w;
+    return b ? b->w : nullptr;
 }
 extern "C" void* fba_belief_scalars_ptr(fba_belief* b)
 {
-    return b->scal;
+    return b ? b->scal : nullptr;
 }
 
 // WeightedFilter::_total_weight after N x add(s, 1/N) (WeightedFilter.cpp:60-66): data independent
@@ -798,6 +821,19 @@ static void weights_became_uniform(fba_belief* b)
     b->suffix_valid = false;
     b->cdf_valid    = false;
 }
+
+// device scratch that dies with the call, whichever way the call returns
+template<class T>
+struct DevTmp
+{
+    T* p = nullptr;
+    ~DevTmp() { cudaFree(p); }
+    operator T*() const { return p; }
+    T** operator&() { return &p; }
+    DevTmp()              = default;
+    DevTmp(DevTmp const&) = delete;
+    DevTmp& operator=(DevTmp const&) = delete;
+};
 
 // base+delta storage: the prior prototypes become the shared base tables
 static int install_base_tables(fba_belief* b, int n_protos, const float* proto_counts)
@@ -828,8 +864,10 @@ extern "C" int fba_belief_init(fba_belief* b, int32_t n_protos, const int32_t* p
     if (particle_proto)
         for (long long i = 0; i < b->N; ++i)
             REQUIRE(ctx, particle_proto[i] >= 0 && particle_proto[i] < n_protos, "belief_init: bad prototype index");
-    float* d_protos = nullptr;
-    int *d_psid = nullptr, *d_pp = nullptr, *d_ps = nullptr;
+    for (long long i = 0; i < b->N; ++i)
+        REQUIRE(ctx, particle_state[i] >= 0 && particle_state[i] < b->m->dev.S, "belief_init: state out of range");
+    DevTmp<float> d_protos;
+    DevTmp<int> d_psid, d_pp, d_ps;
     size_t const pc = (size_t)n_protos * b->lstride;
     CU(ctx, cudaMalloc(&d_ps, (size_t)b->N * sizeof(int)));
     CU(ctx, cudaMemcpyAsync(d_ps, particle_state, (size_t)b->N * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
@@ -845,7 +883,6 @@ extern "C" int fba_belief_init(fba_belief* b, int32_t n_protos, const int32_t* p
         LAUNCH(ctx, k_init_delta, blocks_for(b->N), kThreads, b->counts[b->cur], b->stride, b->state[b->cur],
                b->sid[b->cur], b->weighted ? b->w : nullptr, b->N, d_pp, d_ps);
         CU(ctx, cudaStreamSynchronize(ctx->stream));
-        cudaFree(d_pp), cudaFree(d_ps);
         weights_became_uniform(b);
         return FBA_OK;
     }
@@ -857,7 +894,6 @@ extern "C" int fba_belief_init(fba_belief* b, int32_t n_protos, const int32_t* p
            b->state[b->cur], b->sid[b->cur], b->weighted ? b->w : nullptr, b->N, d_protos, d_psid, d_pp,
            d_ps);
     CU(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_protos), cudaFree(d_psid), cudaFree(d_pp), cudaFree(d_ps);
     weights_became_uniform(b);
     return FBA_OK;
 }
@@ -869,10 +905,13 @@ extern "C" int fba_belief_init_sampled(fba_belief* b, int32_t n_protos, const in
     fba_ctx* ctx = b->ctx;
     REQUIRE(ctx, rng->mode == FBA_RNG_PHILOX, "belief_init_sampled: PHILOX mode only");
     REQUIRE(ctx, n_protos >= 1 && proto_struct_id && proto_counts, "belief_init_sampled: prototypes required");
+    for (int p = 0; p < n_protos; ++p)
+        REQUIRE(ctx, proto_struct_id[p] >= 0 && proto_struct_id[p] < b->m->n_structs,
+                "belief_init_sampled: unknown structure id");
     CU(ctx, cudaSetDevice(ctx->device));
-    float* d_protos = nullptr;
-    int *d_psid = nullptr, *d_pp = nullptr, *d_ps = nullptr;
-    double* d_cdf   = nullptr;
+    DevTmp<float> d_protos;
+    DevTmp<int> d_psid, d_pp, d_ps;
+    DevTmp<double> d_cdf;
     size_t const pc = (size_t)n_protos * b->lstride;
     CU(ctx, cudaMalloc(&d_protos, pc * sizeof(float)));
     CU(ctx, cudaMalloc(&d_psid, n_protos * sizeof(int)));
@@ -898,7 +937,6 @@ extern "C" int fba_belief_init_sampled(fba_belief* b, int32_t n_protos, const in
         LAUNCH(ctx, k_init_delta, blocks_for(b->N), kThreads, b->counts[b->cur], b->stride, b->state[b->cur],
                b->sid[b->cur], b->weighted ? b->w : nullptr, b->N, d_pp, d_ps);
         CU(ctx, cudaStreamSynchronize(ctx->stream));
-        cudaFree(d_protos), cudaFree(d_psid), cudaFree(d_pp), cudaFree(d_ps), cudaFree(d_cdf);
         b->total_weight = 1.0;
         b->suffix_valid = b->cdf_valid = false;
         return FBA_OK;
@@ -907,7 +945,6 @@ extern "C" int fba_belief_init_sampled(fba_belief* b, int32_t n_protos, const in
            b->state[b->cur], b->sid[b->cur], b->weighted ? b->w : nullptr, b->N, d_protos, d_psid, d_pp,
            d_ps);
     CU(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_protos), cudaFree(d_psid), cudaFree(d_pp), cudaFree(d_ps), cudaFree(d_cdf);
     b->total_weight = 1.0;
     b->suffix_valid = b->cdf_valid = false;
     return FBA_OK;
@@ -921,7 +958,11 @@ extern "C" int fba_belief_upload(fba_belief* b, int64_t first, int64_t count, co
     REQUIRE(ctx, first >= 0 && count >= 0 && first + count <= b->N, "belief_upload: range out of bounds");
     CU(ctx, cudaSetDevice(ctx->device));
     if (state)
+    {
+        for (int64_t i = 0; i < count; ++i)
+            REQUIRE(ctx, state[i] >= 0 && state[i] < b->m->dev.S, "belief_upload: state out of range");
         CU(ctx, cudaMemcpyAsync(b->state[b->cur] + first, state, count * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    }
     REQUIRE(ctx, !(b->delta_cap > 0 && (counts || struct_id)),
             "belief_upload: base+delta beliefs take their counts from fba_belief_init prototypes");
     if (struct_id)
@@ -1119,6 +1160,25 @@ static void flip(fba_belief* b)
     b->cur ^= 1;
 }
 
+// the back buffer of the double-buffered operations, allocated on first use
+static int ensure_next(fba_belief* b)
+{
+    fba_ctx* ctx = b->ctx;
+    int const nx = b->cur ^ 1;
+    if (b->counts[nx]) return FBA_OK;
+    cudaError_t e = cudaMalloc(&b->counts[nx], (size_t)b->N * b->stride * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&b->state[nx], (size_t)b->N * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&b->sid[nx], (size_t)b->N * sizeof(int));
+    if (e != cudaSuccess)
+    {
+        cudaFree(b->counts[nx]), cudaFree(b->state[nx]), cudaFree(b->sid[nx]);
+        b->counts[nx] = nullptr, b->state[nx] = nullptr, b->sid[nx] = nullptr;
+        ctx->err = std::string("belief back buffer: ") + cudaGetErrorString(e);
+        return FBA_ERR_CUDA;
+    }
+    return FBA_OK;
+}
+
 // pick N ancestors from the current weights into b->anc
 static int pick_ancestors(fba_belief* b, fba_rng* rng, long long n_out, long long words_per_item,
                           bool use_offsets, long long n_words)
@@ -1152,6 +1212,7 @@ static int gather_into_next(fba_belief* b, long long n_out, bool copy_state)
 {
     fba_ctx* ctx = b->ctx;
     int const nx = b->cur ^ 1;
+    if (int const rc = ensure_next(b)) return rc;
     long long const stage_bytes = b->stride * (long long)sizeof(float);
     if (ctx->bulk_copy && b->delta_cap == 0 && stage_bytes >= 1024
         && kBulkStages * stage_bytes + kBulkStages * 8 <= 200 * 1024)
@@ -1311,7 +1372,10 @@ extern "C" int fba_belief_reset_domain_states(fba_belief* b, fba_rng* rng)
         if (b->weighted) weights_became_uniform(b);
     } else
     {
-        if (b->weighted)
+        if (b->weighted && ctx->inplace_resample)
+        { // survivors keep their slot (and the back buffer stays unallocated); states are redrawn below
+            if ((rc = resample_inplace(b, rng, b->N))) return rc;
+        } else if (b->weighted)
         {
             if ((rc = pick_ancestors(b, rng, b->N, 0, false, 0))) return rc;
             if ((rc = gather_into_next(b, b->N, false))) return rc;
@@ -1395,6 +1459,7 @@ extern "C" int fba_belief_reject_sample(fba_belief* b, int32_t a, int32_t o, fba
     CU(ctx, cudaSetDevice(ctx->device));
     int rc;
     int const nx        = b->cur ^ 1;
+    if ((rc = ensure_next(b))) return rc;
     long long accepted = 0, attempts = 0;
     long long const cap = 1ll << 22;
     double rate         = 0.5; // running estimate of the acceptance rate
@@ -1523,7 +1588,7 @@ extern "C" int fba_belief_reinvigorate(fba_belief* b, fba_belief* fc, int64_t am
     fba_ctx* ctx      = b->ctx;
     fba_model* m      = b->m;
     DevModel const& D = m->dev;
-    REQUIRE(ctx, fc->m == m, "reinvigorate: both beliefs must share one model");
+    REQUIRE(ctx, fc->m == m && fc->ctx == ctx, "reinvigorate: both beliefs must share one model and context");
     REQUIRE(ctx, amount >= 1, "reinvigorate: resample size of < 1 (" + std::to_string(amount) + ")");
     REQUIRE(ctx, !D.tabular && b->delta_cap == 0, "reinvigorate: factored models only");
     CU(ctx, cudaSetDevice(ctx->device));
@@ -1614,14 +1679,13 @@ extern "C" int fba_belief_reinvigorate(fba_belief* b, fba_belief* fc, int64_t am
 
     std::vector<BreedJob> jobs;
     for (auto const& kv : last_writer) jobs.push_back(kv.second);
-    BreedJob* d_jobs = nullptr;
+    DevTmp<BreedJob> d_jobs;
     CU(ctx, cudaMalloc(&d_jobs, jobs.size() * sizeof(BreedJob)));
     CU(ctx, cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(BreedJob), cudaMemcpyHostToDevice, ctx->stream));
     // structures may have been added: the node table pointer is unchanged, its contents were copied
     LAUNCH(ctx, k_breed, (int)jobs.size(), kThreads, D, fc->counts[fc->cur], fc->stride, b->counts[b->cur],
-           b->stride, b->state[b->cur], b->sid[b->cur], d_jobs);
+           b->stride, b->state[b->cur], b->sid[b->cur], (const BreedJob*)d_jobs);
     CU(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_jobs);
     return FBA_OK;
 }
 
@@ -1695,6 +1759,9 @@ extern "C" int fba_rollouts(fba_belief* b, int64_t n, const int64_t* particle, c
     {
         REQUIRE(ctx, word_offset, "rollouts: REPLAY mode needs word_offset");
         long long const avail = rng->n_words - rng->cursor;
+        for (int64_t i = 0; i < n; ++i)
+            REQUIRE(ctx, word_offset[i] >= 0 && word_offset[i] <= std::max(0ll, avail),
+                    "rollouts: word_offset outside the replay stream");
         std::vector<long long> off(word_offset, word_offset + n);
         if ((rc = stage_words(ctx, rng, std::max(0ll, avail)))) return rc;
         if ((rc = stage_offsets(ctx, off))) return rc;
@@ -2030,6 +2097,9 @@ extern "C" int fba_belief_ipc_open(fba_belief* b, const void* handles, int32_t n
     REQUIRE(ctx, n_ranks >= 1 && n_ranks <= kMaxRanks && rank >= 0 && rank < n_ranks, "ipc_open: bad rank");
     REQUIRE(ctx, b->import_buf, "ipc_open: call fba_belief_ipc_handle first");
     CU(ctx, cudaSetDevice(ctx->device));
+    for (auto p : b->opened) cudaIpcCloseMemHandle(p); // a second call re-maps: drop the old mappings
+    b->opened.clear();
+    b->peers_open = false;
     for (int g = 0; g < n_ranks; ++g)
     {
         if (g == rank)
@@ -2097,6 +2167,7 @@ extern "C" int fba_belief_reserve_export(fba_belief* b, int64_t records)
 
 extern "C" int64_t fba_belief_record_bytes(const fba_belief* b)
 {
+    if (!b) return -1;
     return b->stride * (int64_t)sizeof(float) + 16;
 }
 
@@ -2182,6 +2253,7 @@ extern "C" int fba_belief_resample_shard(fba_belief* b, int64_t n_offspring, fba
     LAUNCH(ctx, k_pick_native, blocks_for(n_offspring), kThreads, b->aux, b->N, (long long)n_offspring, 1,
            philox_args(rng), anc);
     int const nx = b->cur ^ 1;
+    if (int const rc = ensure_next(b)) return rc;
     LAUNCH(ctx, k_gather, stream_grid(ctx, kept), kThreads, b->counts[b->cur], b->counts[nx], b->stride,
            b->state[b->cur], b->state[nx], b->sid[b->cur], b->sid[nx], b->m->d_sizes, b->w,
            1.0 / (double)b->N, anc, kept, b->delta_cap > 0 ? 1 : 0);

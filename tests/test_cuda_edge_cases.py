@@ -152,3 +152,81 @@ def test_zero_weight_particles_never_resampled_replay(ctx):
     assert set(ids) <= {3, 17, 40} and rng.exhausted
     b.free()
     sim.close()
+
+
+def test_impossible_observation_keeps_the_belief_intact(ctx):
+    """Every particle gives the real observation probability 0 (its count row is all zeros): the
+    step likelihood is 0 and the normalised weights are 0/0. The reference's behaviour is undefined
+    there (NaN weights, WeightedFilter.cpp:130-143); the CUDA path must stay memory-safe and
+    deterministic: no offspring are assigned, so every particle stays where it is, the weights go
+    back to uniform and the next update works."""
+    import fba_pomdp_b200 as fba
+    S, A, O = 2, 1, 2
+    d = tiny_desc(S=S, A=A, O=O)
+    sim = fba.BAPOMDP(ctx, d, np.ones((1, A), np.uint32), np.ones((1, A), np.uint32))
+    n = 5000
+    stride = sim.structure_size(0)          # T[a][s][s'] (4 cells) then O[a][s'][o] (4 cells)
+    counts = np.ones((n, stride), np.float32)
+    counts[:, 4 + 1] = 0.0                  # P(o = 1 | s' = 0) = 0
+    counts[:, 4 + 3] = 0.0                  # P(o = 1 | s' = 1) = 0
+    b = fba.BAImportanceSampling(n)
+    b.initiate(sim, struct_id=np.zeros(n, np.int32), counts=counts, state=np.zeros(n, np.int32))
+    rng = fba.Rng.philox(3)
+    lik = b.update(0, 1, rng)
+    assert lik == 0.0
+    b.resample(rng)
+    got = b.download()
+    np.testing.assert_array_equal(got["w"], np.full(n, 1.0 / n))
+    assert set(np.unique(got["state"])) <= {0, 1}
+    # the update itself ran (one transition count and one observation count per particle) ...
+    np.testing.assert_array_equal(got["counts"].astype(np.float64).sum(1), np.full(n, 6.0 + 2.0))
+    # ... and the belief is usable afterwards
+    lik2 = b.updateEstimation(0, 0, rng)
+    assert 0.99 < lik2 <= 1.0
+    b.free()
+    sim.close()
+
+
+def test_states_out_of_range_are_rejected(ctx):
+    import fba_pomdp_b200 as fba
+    d = tiny_desc()
+    sim = fba.BAPOMDP(ctx, d, np.ones((1, 2), np.uint32), np.ones((1, 2), np.uint32))
+    b = fba.BAImportanceSampling(4)
+    counts = np.ones((4, sim.structure_size(0)), np.float32)
+    with pytest.raises(fba.capi.FbaError):
+        b.initiate(sim, struct_id=np.zeros(4, np.int32), counts=counts, state=np.array([0, 1, 3, 0], np.int32))
+    b.free()
+    b = fba.BAImportanceSampling(4)
+    with pytest.raises(fba.capi.FbaError):
+        b.initiate(sim, proto_struct_id=[0], proto_counts=counts[:1], particle_proto=None,
+                   state=np.array([0, -1, 0, 0], np.int32))
+    b.free()
+    sim.close()
+
+
+def test_back_buffer_is_allocated_on_first_use(ctx):
+    """In-place (PHILOX) importance sampling never touches the second particle buffer; a full-copy
+    resample (REPLAY) allocates it on the spot and gives the same belief as before the change."""
+    import torch
+    import fba_pomdp_b200 as fba
+    g = G.load("sysadmin")
+    n = 20000
+    sim = fba.BAPOMDP(ctx, g.desc, g.t_par, g.o_par)
+    free0 = torch.cuda.mem_get_info(0)[0]
+    b = fba.BAImportanceSampling(n)
+    b.initiate(sim, proto_struct_id=[0], proto_counts=g["is/init_counts"][:1], particle_proto=None,
+               state=np.zeros(n, np.int32))
+    rng = fba.Rng.philox(1)
+    b.updateEstimation(int(g.a[0]), int(g.o[0]), rng)
+    ctx.synchronize()
+    used_inplace = free0 - torch.cuda.mem_get_info(0)[0]
+    block = n * sim.max_structure_size() * 4
+    assert used_inplace < 1.6 * block, (used_inplace, block)     # one count buffer, not two
+    words = np.random.RandomState(0).randint(0, 2**32, 64 * n, dtype=np.uint64).astype(np.uint32)
+    b.updateEstimation(int(g.a[1]), int(g.o[1]), fba.Rng.replay(words))   # full copy: needs the back buffer
+    ctx.synchronize()
+    assert free0 - torch.cuda.mem_get_info(0)[0] >= 2 * block
+    d = b.download(counts=False)
+    assert abs(d["w"].sum() - 1.0) < 1e-9
+    b.free()
+    sim.close()
