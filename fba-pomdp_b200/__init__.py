@@ -4,11 +4,11 @@ The product is libfba_b200.so (hand-written CUDA kernels behind the C ABI in
 include/fba_pomdp_b200.h). This package is the thin host-side mirror of the reference's
 Belief / BABelief / rollout interfaces used by the tests and the benchmark."""
 from . import capi  # noqa: F401
-from .beliefs import (BAImportanceSampling, BAPOMDP, BARejectionSampling, Context,  # noqa: F401
-                      ReinvigoratingRejectionSampling, rollouts)
+from .beliefs import (BAImportanceSampling, BAPOMDP, BARejectionSampling, BatchedBAImportanceSampling,  # noqa: F401
+                      Context, ReinvigoratingRejectionSampling, rollouts)
 from .capi import FbaError, Rng  # noqa: F401
 
-__all__ = ["capi", "Context", "BAPOMDP", "BAImportanceSampling", "BARejectionSampling",
+__all__ = ["capi", "Context", "BAPOMDP", "BAImportanceSampling", "BARejectionSampling", "BatchedBAImportanceSampling",
            "ReinvigoratingRejectionSampling", "rollouts", "Rng", "FbaError"]
 from .sharded import ShardedBAImportanceSampling, exchange_plan, offspring_quotas  # noqa: F401,E402
 from .sharded import exchange_records  # noqa: F401,E402

@@ -366,6 +366,73 @@ class ReinvigoratingRejectionSampling(_ParticleBelief):
             self.fc = None
 
 
+class BatchedBAImportanceSampling:
+    """The importance-sampling beliefs of `n_runs` INDEPENDENT runs (the reference's `--runs`,
+    src/experiments/BAPOMDPExperiment.cpp:32-78), `n` particles each, advanced together: every call
+    is one kernel launch with one CTA per run, each run with its own action and observation. Run r is
+    bit-identical to a stand-alone BAImportanceSampling(n) driven by Rng.philox(seed + r) through the
+    same calls. `active`: optional boolean mask; runs with False are left untouched."""
+
+    def __init__(self, n_runs, n):
+        if n_runs < 1 or n < 1:
+            raise FbaError(capi.ERR_INVALID, "cannot initiate %d runs of %d particles" % (n_runs, n))
+        self.n_runs, self.n = int(n_runs), int(n)
+        self.h = self.L = self.ctx = self.sim = None
+
+    def initiate_sampled(self, simulator, proto_struct_id, proto_counts, proto_probs, rng, stride=0):
+        self.sim, self.ctx, self.L = simulator, simulator.ctx, simulator.L
+        if stride <= 0:
+            stride = simulator.max_structure_size()
+        h = C.c_void_p()
+        _check(self.ctx.h, self.L.fba_runs_create(self.ctx.h, simulator.h, self.n_runs, self.n, stride, C.byref(h)))
+        self.h = h
+        self.storage = self.L.fba_runs_belief(self.h)
+        s = self.L.fba_belief_stride(self.storage)
+        psid = np.ascontiguousarray(proto_struct_id, np.int32).reshape(-1)
+        pc = np.zeros((len(psid), s), np.float32)
+        src = np.asarray(proto_counts, np.float32).reshape(len(psid), -1)
+        pc[:, :src.shape[1]] = src
+        pr = None if proto_probs is None else np.ascontiguousarray(proto_probs, np.float64)
+        _check(self.ctx.h, self.L.fba_runs_init_sampled(self.h, len(psid), ptr(psid), ptr(pc), ptr(pr), C.byref(rng)))
+
+    def _mask(self, active):
+        if active is None:
+            return None
+        m = np.ascontiguousarray(active, np.uint8).reshape(-1)
+        assert len(m) == self.n_runs
+        return m
+
+    def updateEstimation(self, a, o, rng, active=None, want_likelihood=True):
+        a = np.ascontiguousarray(a, np.int32).reshape(-1)
+        o = np.ascontiguousarray(o, np.int32).reshape(-1)
+        assert len(a) == self.n_runs and len(o) == self.n_runs
+        m = self._mask(active)
+        lik = np.full(self.n_runs, np.nan) if want_likelihood else None
+        _check(self.ctx.h, self.L.fba_runs_update_estimation(self.h, ptr(a), ptr(o), ptr(m), C.byref(rng), ptr(lik)))
+        return lik
+
+    def resetDomainStateDistribution(self, rng, active=None):
+        _check(self.ctx.h, self.L.fba_runs_reset_domain_states(self.h, ptr(self._mask(active)), C.byref(rng)))
+
+    def sample(self, rng, active=None):
+        """one particle index per run (inside the run); -1 for inactive runs"""
+        idx = np.full(self.n_runs, -1, np.int64)
+        _check(self.ctx.h, self.L.fba_runs_sample(self.h, ptr(self._mask(active)), C.byref(rng), ptr(idx)))
+        return idx
+
+    def download(self, run, counts=True):
+        """the particles of one run, as _ParticleBelief.download"""
+        return _ParticleBelief._download(self.L, self.ctx, self.storage, True, run * self.n, self.n, counts)
+
+    def copies(self):
+        return int(self.L.fba_runs_copies(self.h))
+
+    def free(self, _simulator=None):
+        if self.h:
+            self.L.fba_runs_destroy(self.h)
+            self.h = None
+
+
 def rollouts(belief, particle, start_state, depth, discount, rng, word_offset=None):
     """n x RBAPOUCT::rollout (RBAPOUCT.cpp:295-323) in one launch; returns the n returns."""
     p = np.ascontiguousarray(particle, np.int64)

@@ -1898,6 +1898,253 @@ extern "C" int fba_step_batch(fba_belief* b, int64_t n, const int64_t* particle,
     return FBA_OK;
 }
 
+// ---- many independent runs ------------------------------------------------------------------------
+
+struct fba_runs
+{
+    fba_belief* b = nullptr;
+    int R         = 0;
+    long long n   = 0;
+    int n_tiles   = 0;
+    double* tile  = nullptr;
+    int2* pairs   = nullptr;
+    int* totals   = nullptr;
+    double* scal  = nullptr;
+    long long* picked = nullptr;
+    int *d_a = nullptr, *d_o = nullptr;
+    unsigned char* d_active       = nullptr;
+    unsigned long long* d_copies = nullptr;
+};
+
+extern "C" void fba_runs_destroy(fba_runs* r)
+{
+    if (!r) return;
+    if (r->b)
+    {
+        cudaSetDevice(r->b->ctx->device);
+        cudaStreamSynchronize(r->b->ctx->stream);
+    }
+    cudaFree(r->tile), cudaFree(r->pairs), cudaFree(r->totals), cudaFree(r->scal), cudaFree(r->picked);
+    cudaFree(r->d_a), cudaFree(r->d_o), cudaFree(r->d_active), cudaFree(r->d_copies);
+    fba_belief_destroy(r->b);
+    delete r;
+}
+
+extern "C" int fba_runs_create(fba_ctx* ctx, fba_model* m, int32_t n_runs, int64_t particles_per_run,
+                               int64_t stride, fba_runs** out)
+{
+    if (!ctx || !m || !out) return FBA_ERR_INVALID;
+    *out = nullptr;
+    REQUIRE(ctx, n_runs >= 1 && particles_per_run >= 1, "runs: n_runs and particles_per_run must be >= 1");
+    REQUIRE(ctx, m->delta_cap == 0, "runs: dense storage only (small beliefs are what gets batched)");
+    REQUIRE(ctx, (long long)n_runs * particles_per_run < (1ll << 31), "runs: at most 2^31-1 particles in total");
+    auto r = new fba_runs();
+    int rc = fba_belief_create(ctx, m, (long long)n_runs * particles_per_run, stride, 1, &r->b);
+    if (rc)
+    {
+        delete r;
+        return rc;
+    }
+    r->R       = n_runs;
+    r->n       = particles_per_run;
+    r->n_tiles = (int)((particles_per_run + kTile - 1) / kTile);
+    size_t const nt = (size_t)n_runs * r->n_tiles;
+    cudaError_t e   = cudaMalloc(&r->tile, nt * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&r->pairs, nt * sizeof(int2));
+    if (e == cudaSuccess) e = cudaMalloc(&r->totals, (size_t)n_runs * 2 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&r->scal, (size_t)n_runs * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&r->picked, (size_t)n_runs * sizeof(long long));
+    if (e == cudaSuccess) e = cudaMalloc(&r->d_a, (size_t)n_runs * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&r->d_o, (size_t)n_runs * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&r->d_active, (size_t)n_runs);
+    if (e == cudaSuccess) e = cudaMalloc(&r->d_copies, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(r->d_copies, 0, sizeof(unsigned long long));
+    if (e != cudaSuccess)
+    {
+        ctx->err = std::string("runs alloc: ") + cudaGetErrorString(e);
+        fba_runs_destroy(r);
+        return FBA_ERR_CUDA;
+    }
+    *out = r;
+    return FBA_OK;
+}
+
+extern "C" fba_belief* fba_runs_belief(fba_runs* r)
+{
+    return r ? r->b : nullptr;
+}
+
+extern "C" int fba_runs_init_sampled(fba_runs* r, int32_t n_protos, const int32_t* proto_struct_id,
+                                     const float* proto_counts, const double* proto_probs, fba_rng* rng)
+{
+    if (!r || !rng) return FBA_ERR_INVALID;
+    fba_belief* b = r->b;
+    fba_ctx* ctx  = b->ctx;
+    REQUIRE(ctx, rng->mode == FBA_RNG_PHILOX, "runs: PHILOX mode only");
+    REQUIRE(ctx, n_protos >= 1 && proto_struct_id && proto_counts, "runs_init_sampled: prototypes required");
+    for (int p = 0; p < n_protos; ++p)
+        REQUIRE(ctx, proto_struct_id[p] >= 0 && proto_struct_id[p] < b->m->n_structs,
+                "runs_init_sampled: unknown structure id");
+    CU(ctx, cudaSetDevice(ctx->device));
+    DevTmp<float> d_protos;
+    DevTmp<int> d_psid, d_pp, d_ps;
+    DevTmp<double> d_cdf;
+    size_t const pc = (size_t)n_protos * b->lstride;
+    CU(ctx, cudaMalloc(&d_protos, pc * sizeof(float)));
+    CU(ctx, cudaMalloc(&d_psid, n_protos * sizeof(int)));
+    CU(ctx, cudaMalloc(&d_pp, (size_t)b->N * sizeof(int)));
+    CU(ctx, cudaMalloc(&d_ps, (size_t)b->N * sizeof(int)));
+    CU(ctx, cudaMemcpyAsync(d_protos, proto_counts, pc * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(d_psid, proto_struct_id, n_protos * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<double> cdf;
+    if (proto_probs)
+    { // the same host arithmetic as fba_belief_init_sampled
+        double acc = 0, tot = 0;
+        for (int p = 0; p < n_protos; ++p) tot += proto_probs[p];
+        for (int p = 0; p < n_protos; ++p) cdf.push_back((acc += proto_probs[p]) / tot);
+        CU(ctx, cudaMalloc(&d_cdf, n_protos * sizeof(double)));
+        CU(ctx, cudaMemcpyAsync(d_cdf, cdf.data(), n_protos * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    LAUNCH(ctx, k_runs_draw_init, blocks_for(b->N), kThreads, b->m->dev, r->n, b->N, n_protos,
+           (const double*)d_cdf, (int*)d_pp, (int*)d_ps, philox_args(rng));
+    LAUNCH(ctx, k_init_from_protos, stream_grid(ctx, b->N), kThreads, b->counts[b->cur], b->stride,
+           b->state[b->cur], b->sid[b->cur], b->w, b->N, (const float*)d_protos, (const int*)d_psid,
+           (const int*)d_pp, (const int*)d_ps);
+    LAUNCH(ctx, k_fill, blocks_for(b->N), kThreads, b->w, b->N, 1.0 / (double)r->n);
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    b->suffix_valid = b->cdf_valid = false;
+    return FBA_OK;
+}
+
+static RunsArgs runs_args(fba_runs* r)
+{
+    fba_belief* b = r->b;
+    RunsArgs A{};
+    A.counts = b->counts[b->cur], A.stride = b->stride, A.state = b->state[b->cur], A.sid = b->sid[b->cur];
+    A.w = b->w, A.cdf = b->aux, A.noff = b->noff, A.escan = b->escan, A.dead = b->dead, A.src_of = b->src_of;
+    A.tile = r->tile, A.tile_pairs = r->pairs, A.totals = r->totals, A.scal = r->scal, A.picked = r->picked;
+    A.n = r->n, A.n_tiles = r->n_tiles;
+    A.action = r->d_a, A.observation = r->d_o, A.active = nullptr;
+    A.struct_size = b->m->d_sizes;
+    A.copies      = r->d_copies;
+    return A;
+}
+
+static int runs_stage_active(fba_runs* r, const uint8_t* active, RunsArgs& A)
+{
+    fba_ctx* ctx = r->b->ctx;
+    if (!active) return FBA_OK;
+    CU(ctx, cudaMemcpyAsync(r->d_active, active, (size_t)r->R, cudaMemcpyHostToDevice, ctx->stream));
+    A.active = r->d_active;
+    return FBA_OK;
+}
+
+// k_runs_step<LONG, SAMPLED, MODE> chosen at run time
+#define LAUNCH_RUNS(ctx, mode, longrows, sampled, grid, ...)                                       \
+    do {                                                                                           \
+        if (sampled)                                                                               \
+        {                                                                                          \
+            if (longrows) LAUNCH(ctx, (k_runs_step<true, true, mode>), grid, kThreads, __VA_ARGS__);   \
+            else                                                                                   \
+                LAUNCH(ctx, (k_runs_step<false, true, mode>), grid, kThreads, __VA_ARGS__);        \
+        } else                                                                                     \
+        {                                                                                          \
+            if (longrows) LAUNCH(ctx, (k_runs_step<true, false, mode>), grid, kThreads, __VA_ARGS__);  \
+            else                                                                                   \
+                LAUNCH(ctx, (k_runs_step<false, false, mode>), grid, kThreads, __VA_ARGS__);       \
+        }                                                                                          \
+    } while (0)
+
+extern "C" int fba_runs_update_estimation(fba_runs* r, const int32_t* action, const int32_t* observation,
+                                          const uint8_t* active, fba_rng* rng, double* likelihood)
+{
+    if (!r || !rng) return FBA_ERR_INVALID;
+    fba_belief* b     = r->b;
+    fba_ctx* ctx      = b->ctx;
+    DevModel const& D = b->m->dev;
+    REQUIRE(ctx, rng->mode == FBA_RNG_PHILOX, "runs: PHILOX mode only");
+    REQUIRE(ctx, action && observation, "runs_update_estimation: action and observation are required");
+    for (int k = 0; k < r->R; ++k)
+    {
+        if (active && !active[k]) continue;
+        REQUIRE(ctx, action[k] >= 0 && action[k] < D.A, "runs_update_estimation: action out of range");
+        REQUIRE(ctx, observation[k] >= 0 && observation[k] < D.O, "runs_update_estimation: observation out of range");
+    }
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpyAsync(r->d_a, action, (size_t)r->R * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(r->d_o, observation, (size_t)r->R * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    RunsArgs A = runs_args(r);
+    int rc     = runs_stage_active(r, active, A);
+    if (rc) return rc;
+    RngArgs ra{};
+    ra.seed   = rng->seed;
+    ra.offset = rng->offset;
+    rng->offset += 2; // update + resample, as fba_belief_update_estimation
+    LAUNCH_RUNS(ctx, 0, b->m->long_rows, D.sampled != 0, r->R, D, A, ra);
+    if (likelihood)
+    {
+        std::vector<double> tmp((size_t)r->R);
+        CU(ctx, cudaMemcpyAsync(tmp.data(), r->scal, (size_t)r->R * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int k = 0; k < r->R; ++k)
+            if (!active || active[k]) likelihood[k] = tmp[k];
+    }
+    return FBA_OK;
+}
+
+extern "C" int fba_runs_reset_domain_states(fba_runs* r, const uint8_t* active, fba_rng* rng)
+{
+    if (!r || !rng) return FBA_ERR_INVALID;
+    fba_belief* b     = r->b;
+    fba_ctx* ctx      = b->ctx;
+    DevModel const& D = b->m->dev;
+    REQUIRE(ctx, rng->mode == FBA_RNG_PHILOX, "runs: PHILOX mode only");
+    CU(ctx, cudaSetDevice(ctx->device));
+    RunsArgs A = runs_args(r);
+    int rc     = runs_stage_active(r, active, A);
+    if (rc) return rc;
+    RngArgs ra{};
+    ra.seed   = rng->seed;
+    ra.offset = rng->offset;
+    rng->offset += 2; // resample + start states, as fba_belief_reset_domain_states
+    LAUNCH(ctx, (k_runs_step<false, false, 1>), r->R, kThreads, D, A, ra); // no categorical draws: one variant
+    return FBA_OK;
+}
+
+extern "C" int fba_runs_sample(fba_runs* r, const uint8_t* active, fba_rng* rng, int64_t* index)
+{
+    if (!r || !rng || !index) return FBA_ERR_INVALID;
+    fba_belief* b     = r->b;
+    fba_ctx* ctx      = b->ctx;
+    DevModel const& D = b->m->dev;
+    REQUIRE(ctx, rng->mode == FBA_RNG_PHILOX, "runs: PHILOX mode only");
+    CU(ctx, cudaSetDevice(ctx->device));
+    RunsArgs A = runs_args(r);
+    int rc     = runs_stage_active(r, active, A);
+    if (rc) return rc;
+    RngArgs ra{};
+    ra.seed   = rng->seed;
+    ra.offset = rng->offset;
+    rng->offset += 1; // as fba_belief_sample
+    LAUNCH(ctx, (k_runs_step<false, false, 2>), r->R, kThreads, D, A, ra);
+    std::vector<long long> tmp((size_t)r->R);
+    CU(ctx, cudaMemcpyAsync(tmp.data(), r->picked, (size_t)r->R * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < r->R; ++k)
+        if (!active || active[k]) index[k] = tmp[k];
+    return FBA_OK;
+}
+
+extern "C" int64_t fba_runs_copies(fba_runs* r)
+{
+    if (!r) return -1;
+    unsigned long long h = 0;
+    cudaSetDevice(r->b->ctx->device);
+    if (cudaMemcpyAsync(&h, r->d_copies, sizeof(h), cudaMemcpyDeviceToHost, r->b->ctx->stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(r->b->ctx->stream) != cudaSuccess) return -1;
+    return (int64_t)h;
+}
+
 // ---- multi-GPU phases ---------------------------------------------------------------------------
 
 extern "C" int fba_belief_propose(fba_belief* b, int32_t a, int32_t o, fba_rng* rng, double* local_total)

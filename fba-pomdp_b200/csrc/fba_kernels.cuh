@@ -444,11 +444,14 @@ __device__ __forceinline__ double block_reduce_sum(double v, double* sh)
     return v; // valid in thread 0
 }
 
-__global__ void __launch_bounds__(kThreads)
-    k_tile_sums(const double* __restrict__ w, long long N, double* __restrict__ tile_sum)
+// The native reductions / scans below are written as *_body device functions over one tile (or one
+// block-wide pass) so that the one-launch-per-phase kernels and the fused one-CTA-per-run kernel
+// (k_runs_update) execute literally the same arithmetic in the same order: a batched run is bit-identical
+// to a stand-alone belief.
+__device__ __forceinline__ void tile_sums_body(int tile, const double* __restrict__ w, long long N,
+                                               double* __restrict__ tile_sum, double* sh)
 {
-    __shared__ double sh[kThreads / 32];
-    long long const base = (long long)blockIdx.x * kTile;
+    long long const base = (long long)tile * kTile;
     double v             = 0.0;
 #pragma unroll
     for (int k = 0; k < kTile / kThreads; ++k)
@@ -457,16 +460,21 @@ __global__ void __launch_bounds__(kThreads)
         if (i < N) v += w[i];
     }
     v = block_reduce_sum(v, sh);
-    if (threadIdx.x == 0) tile_sum[blockIdx.x] = v;
+    if (threadIdx.x == 0) tile_sum[tile] = v;
+}
+
+__global__ void __launch_bounds__(kThreads)
+    k_tile_sums(const double* __restrict__ w, long long N, double* __restrict__ tile_sum)
+{
+    __shared__ double sh[kThreads / 32];
+    tile_sums_body(blockIdx.x, w, N, tile_sum, sh);
 }
 
 // exclusive scan of the tile sums in one block; scal[0] = grand total
-__global__ void __launch_bounds__(kThreads)
-    k_scan_tile_sums(double* __restrict__ tile_sum, int n_tiles, double* __restrict__ scal)
+__device__ __forceinline__ void scan_tile_sums_body(double* __restrict__ tile_sum, int n_tiles,
+                                                    double* __restrict__ scal, double* sh, double* carry)
 {
-    __shared__ double sh[kThreads];
-    __shared__ double carry;
-    if (threadIdx.x == 0) carry = 0.0;
+    if (threadIdx.x == 0) *carry = 0.0;
     __syncthreads();
     for (int base = 0; base < n_tiles; base += kThreads)
     {
@@ -482,22 +490,28 @@ __global__ void __launch_bounds__(kThreads)
             __syncthreads();
         }
         double const incl = sh[threadIdx.x];
-        if (i < n_tiles) tile_sum[i] = carry + incl - v;
+        if (i < n_tiles) tile_sum[i] = *carry + incl - v;
         __syncthreads();
-        if (threadIdx.x == kThreads - 1) carry += incl;
+        if (threadIdx.x == kThreads - 1) *carry += incl;
         __syncthreads();
     }
-    if (threadIdx.x == 0) scal[0] = carry;
+    if (threadIdx.x == 0) scal[0] = *carry;
+}
+
+__global__ void __launch_bounds__(kThreads)
+    k_scan_tile_sums(double* __restrict__ tile_sum, int n_tiles, double* __restrict__ scal)
+{
+    __shared__ double sh[kThreads];
+    __shared__ double carry;
+    scan_tile_sums_body(tile_sum, n_tiles, scal, sh, &carry);
 }
 
 // w_i /= scal[0] (optionally), inclusive prefix sums into cdf
-__global__ void __launch_bounds__(kThreads)
-    k_scale_and_scan(double* __restrict__ w, long long N, const double* __restrict__ tile_off,
-                     const double* __restrict__ total_ptr, double divide_by, double* __restrict__ cdf)
+__device__ __forceinline__ void scale_and_scan_body(int tile, double* __restrict__ w, long long N,
+                                                    const double* __restrict__ tile_off, double total,
+                                                    double* __restrict__ cdf, double* sh)
 {
-    __shared__ double sh[kThreads];
-    long long const base = (long long)blockIdx.x * kTile + (long long)threadIdx.x * (kTile / kThreads);
-    double const total   = total_ptr ? *total_ptr : divide_by;
+    long long const base = (long long)tile * kTile + (long long)threadIdx.x * (kTile / kThreads);
     double v[kTile / kThreads];
     double run = 0.0;
 #pragma unroll
@@ -518,13 +532,21 @@ __global__ void __launch_bounds__(kThreads)
         sh[threadIdx.x] += t;
         __syncthreads();
     }
-    double const off = tile_off[blockIdx.x] / total + sh[threadIdx.x] - run;
+    double const off = tile_off[tile] / total + sh[threadIdx.x] - run;
 #pragma unroll
     for (int k = 0; k < kTile / kThreads; ++k)
     {
         long long const i = base + k;
         if (i < N) cdf[i] = off + v[k];
     }
+}
+
+__global__ void __launch_bounds__(kThreads)
+    k_scale_and_scan(double* __restrict__ w, long long N, const double* __restrict__ tile_off,
+                     const double* __restrict__ total_ptr, double divide_by, double* __restrict__ cdf)
+{
+    __shared__ double sh[kThreads];
+    scale_and_scan_body(blockIdx.x, w, N, tile_off, total_ptr ? *total_ptr : divide_by, cdf, sh);
 }
 
 // NATIVE ancestor selection over the inclusive cdf (cdf[N-1] ~ 1).
@@ -665,20 +687,16 @@ struct PeerTable
     long long cap;               // records each holds
 };
 
-// per tile: offspring counts -> (dead, extra) tile sums
-__global__ void __launch_bounds__(kThreads)
-    k_offspring(const double* __restrict__ cdf, long long N, long long n_out,
-                const long long* __restrict__ n_out_ptr, RngArgs ra, int* __restrict__ noff,
-                int2* __restrict__ tile_sum)
+__device__ __forceinline__ void offspring_body(int tile, const double* __restrict__ cdf, long long N,
+                                               long long n_out, const RngArgs& ra, int* __restrict__ noff,
+                                               int2* __restrict__ tile_sum, int* shd, int* she)
 {
-    __shared__ int shd[kThreads / 32], she[kThreads / 32];
-    if (n_out_ptr) n_out = *n_out_ptr;
     auto g             = RngOf<false>::make(ra, 0);
     double const u     = draw_u(g);
     // a shard whose weights all collapsed gets no offspring: every slot is dead
     double const inv_s = (n_out > 0 && cdf[N - 1] > 0.0) ? (double)n_out / cdf[N - 1] : 0.0;
     if (inv_s == 0.0) n_out = 0;
-    long long const base = (long long)blockIdx.x * kTile;
+    long long const base = (long long)tile * kTile;
     int d = 0, e = 0;
 #pragma unroll
     for (int k = 0; k < kTile / kThreads; ++k)
@@ -706,18 +724,27 @@ __global__ void __launch_bounds__(kThreads)
     {
         int td = 0, te = 0;
         for (int k = 0; k < kThreads / 32; ++k) td += shd[k], te += she[k];
-        tile_sum[blockIdx.x] = make_int2(td, te);
+        tile_sum[tile] = make_int2(td, te);
     }
 }
 
-// exclusive scan of the (dead, extra) tile sums in one block; totals[0] = #dead, totals[1] = #extra
+// per tile: offspring counts -> (dead, extra) tile sums
 __global__ void __launch_bounds__(kThreads)
-    k_scan_tile_pairs(int2* __restrict__ tile_sum, int n_tiles, int* __restrict__ totals,
-                      long long* __restrict__ stats)
+    k_offspring(const double* __restrict__ cdf, long long N, long long n_out,
+                const long long* __restrict__ n_out_ptr, RngArgs ra, int* __restrict__ noff,
+                int2* __restrict__ tile_sum)
 {
-    __shared__ int shd[kThreads], she[kThreads];
-    __shared__ int cd, ce;
-    if (threadIdx.x == 0) cd = 0, ce = 0;
+    __shared__ int shd[kThreads / 32], she[kThreads / 32];
+    if (n_out_ptr) n_out = *n_out_ptr;
+    offspring_body(blockIdx.x, cdf, N, n_out, ra, noff, tile_sum, shd, she);
+}
+
+// exclusive scan of the (dead, extra) tile sums in one block; totals[0] = #dead, totals[1] = #extra
+__device__ __forceinline__ void scan_tile_pairs_body(int2* __restrict__ tile_sum, int n_tiles,
+                                                     int* __restrict__ totals, long long* __restrict__ stats,
+                                                     int* shd, int* she, int* cd, int* ce)
+{
+    if (threadIdx.x == 0) *cd = 0, *ce = 0;
     __syncthreads();
     for (int base = 0; base < n_tiles; base += kThreads)
     {
@@ -733,28 +760,39 @@ __global__ void __launch_bounds__(kThreads)
             shd[threadIdx.x] += a, she[threadIdx.x] += b;
             __syncthreads();
         }
-        if (i < n_tiles) tile_sum[i] = make_int2(cd + shd[threadIdx.x] - v.x, ce + she[threadIdx.x] - v.y);
+        if (i < n_tiles) tile_sum[i] = make_int2(*cd + shd[threadIdx.x] - v.x, *ce + she[threadIdx.x] - v.y);
         __syncthreads();
-        if (threadIdx.x == kThreads - 1) cd += shd[kThreads - 1], ce += she[kThreads - 1];
+        if (threadIdx.x == kThreads - 1) *cd += shd[kThreads - 1], *ce += she[kThreads - 1];
         __syncthreads();
     }
     if (threadIdx.x == 0)
     {
-        totals[0] = cd, totals[1] = ce;
-        stats[0] += ce; // block copies this resample performs
-        stats[1] += 1;
+        totals[0] = *cd, totals[1] = *ce;
+        if (stats)
+        {
+            stats[0] += *ce; // block copies this resample performs
+            stats[1] += 1;
+        }
     }
 }
 
-// per tile: dead_slot[k] = index of the k-th dead particle; extra_scan[i] = exclusive scan of extra
 __global__ void __launch_bounds__(kThreads)
-    k_offspring_apply(const int* __restrict__ noff, long long N, const int2* __restrict__ tile_off,
-                      int* __restrict__ dead_slot, int* __restrict__ extra_scan, int* __restrict__ src_of,
-                      long long src_cap)
+    k_scan_tile_pairs(int2* __restrict__ tile_sum, int n_tiles, int* __restrict__ totals,
+                      long long* __restrict__ stats)
 {
     __shared__ int shd[kThreads], she[kThreads];
+    __shared__ int cd, ce;
+    scan_tile_pairs_body(tile_sum, n_tiles, totals, stats, shd, she, &cd, &ce);
+}
+
+// per tile: dead_slot[k] = index of the k-th dead particle; extra_scan[i] = exclusive scan of extra
+__device__ __forceinline__ void offspring_apply_body(int tile, const int* __restrict__ noff, long long N,
+                                                     const int2* __restrict__ tile_off,
+                                                     int* __restrict__ dead_slot, int* __restrict__ extra_scan,
+                                                     int* __restrict__ src_of, long long src_cap, int* shd, int* she)
+{
     constexpr int PER    = kTile / kThreads;
-    long long const base = (long long)blockIdx.x * kTile + (long long)threadIdx.x * PER;
+    long long const base = (long long)tile * kTile + (long long)threadIdx.x * PER;
     int n[PER];
     int d = 0, e = 0;
 #pragma unroll
@@ -775,7 +813,7 @@ __global__ void __launch_bounds__(kThreads)
         shd[threadIdx.x] += a, she[threadIdx.x] += b;
         __syncthreads();
     }
-    int2 const off = tile_off[blockIdx.x];
+    int2 const off = tile_off[tile];
     int pd = off.x + shd[threadIdx.x] - d, pe = off.y + she[threadIdx.x] - e;
 #pragma unroll
     for (int k = 0; k < PER; ++k)
@@ -792,6 +830,15 @@ __global__ void __launch_bounds__(kThreads)
             pe += (n[k] > 1) ? n[k] - 1 : 0;
         }
     }
+}
+
+__global__ void __launch_bounds__(kThreads)
+    k_offspring_apply(const int* __restrict__ noff, long long N, const int2* __restrict__ tile_off,
+                      int* __restrict__ dead_slot, int* __restrict__ extra_scan, int* __restrict__ src_of,
+                      long long src_cap)
+{
+    __shared__ int shd[kThreads], she[kThreads];
+    offspring_apply_body(blockIdx.x, noff, N, tile_off, dead_slot, extra_scan, src_of, src_cap, shd, she);
 }
 
 // multi-GPU: imported record r fills the (n_extra + r)-th dead slot (those the local extras left)
@@ -898,6 +945,198 @@ __global__ void __launch_bounds__(kThreads)
             }
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// MANY INDEPENDENT RUNS on one GPU. The reference's real workloads are hundreds
+// to thousands of independent runs of a SMALL belief (episodic tiger: 1024 particles), each of which
+// is launch-latency-bound on its own (nine launches, ~40 us per update). Here the beliefs of R runs
+// lie back to back in ONE particle array (run r owns particles [r n, (r+1) n)), and ONE launch with
+// ONE CTA PER RUN performs the whole update of every run — propose with the run's own (action,
+// observation), normalise, systematic in-place resample — by calling the same *_body functions as the
+// one-launch-per-phase kernels, phase after phase, with __syncthreads() in between. Run r draws from
+// Philox streams keyed (seed + r, local particle index), i.e. exactly what a stand-alone belief of n
+// particles seeded with seed + r draws: a batched run is bit-identical to that belief
+// (tests/test_cuda_runs.py).
+//   MODE 0: updateEstimation (update + resample); 1: resetDomainStateDistribution (resample + start
+//   states); 2: sample (one particle index per run)
+// ------------------------------------------------------------------------------------------------
+struct RunsArgs
+{
+    float* counts;
+    long long stride;
+    int *state, *sid;
+    double *w, *cdf;
+    int *noff, *escan, *dead, *src_of; // per particle (src_of: n per run)
+    double* tile;                      // [R][n_tiles]
+    int2* tile_pairs;                  // [R][n_tiles]
+    int* totals;                       // [R][2]
+    double* scal;                      // [R]: the run's total weight before normalisation (step likelihood)
+    long long* picked;                 // [R]: MODE 2 result (local particle index)
+    long long n;                       // particles per run
+    int n_tiles;
+    const int *action, *observation;   // [R] (MODE 0)
+    const unsigned char* active;       // [R] or NULL: runs with 0 are left untouched
+    const int* struct_size;
+    unsigned long long* copies;        // [1]: block copies made, all runs
+};
+
+template<bool LONG, bool SAMPLED, int MODE>
+__global__ void __launch_bounds__(kThreads)
+    k_runs_step(DevModel M, RunsArgs A, RngArgs ra)
+{
+    __shared__ double sh_d[kThreads];
+    __shared__ int sh_a[kThreads], sh_b[kThreads];
+    __shared__ double carry;
+    __shared__ int cd, ce;
+    int const r = blockIdx.x;
+    if (A.active && !A.active[r]) return;
+    long long const n  = A.n;
+    long long const p0 = (long long)r * n; // first particle of the run
+    float* const counts = A.counts + p0 * A.stride;
+    int* const state    = A.state + p0;
+    int* const sid      = A.sid + p0;
+    double* const w     = A.w + p0;
+    double* const cdf   = A.cdf + p0;
+    int* const noff     = A.noff + p0;
+    int* const escan    = A.escan + p0;
+    int* const dead     = A.dead + p0;
+    int* const src_of   = A.src_of + p0;
+    double* const tile  = A.tile + (long long)r * A.n_tiles;
+    int2* const pairs   = A.tile_pairs + (long long)r * A.n_tiles;
+    int* const totals   = A.totals + 2 * r;
+    RngArgs rr          = ra; // the run's own random source: a stand-alone belief seeded seed + r
+    rr.seed             = ra.seed + (unsigned long long)r;
+
+    if (MODE == 0)
+    { // importance_sampling::update, per-particle part (k_propose)
+        int const a = A.action[r], o = A.observation[r];
+        for (long long i = threadIdx.x; i < n; i += kThreads)
+        {
+            auto g            = RngOf<false>::make(rr, i);
+            const Node* nodes = M.nodes + ((long long)sid[i] * M.A + a) * M.J;
+            float* c          = counts + i * A.stride;
+            int sim_o;
+            Feat x2;
+            int const s2 = hyper_step<STEP_UPDATE, decltype(g), false, LONG, SAMPLED>(M, nodes, c, state[i], g, sim_o,
+                                                                                      x2, nullptr);
+            double const prob = obs_probability<SAMPLED>(M, nodes, c, x2, o, g);
+            state[i]          = s2;
+            w[i]              = __dmul_rn(w[i], prob);
+        }
+        ++rr.offset;
+        __syncthreads();
+    }
+    // native_normalize: tile sums -> scan -> divide (MODE 0: by the total; otherwise by 1) + cdf
+    for (int t = 0; t < A.n_tiles; ++t)
+    {
+        tile_sums_body(t, w, n, tile, sh_d);
+        __syncthreads();
+    }
+    scan_tile_sums_body(tile, A.n_tiles, A.scal + r, sh_d, &carry);
+    __syncthreads();
+    double const total = (MODE == 0) ? A.scal[r] : 1.0;
+    for (int t = 0; t < A.n_tiles; ++t)
+    {
+        scale_and_scan_body(t, w, n, tile, total, cdf, sh_d);
+        __syncthreads();
+    }
+    if (MODE == 2)
+    { // WeightedFilter::sample on the native cdf (k_pick_native, multinomial, one draw)
+        if (threadIdx.x == 0)
+        {
+            auto g     = RngOf<false>::make(rr, 0);
+            double thr = draw_u(g);
+            thr *= cdf[n - 1];
+            long long lo = 0, hi = n - 1;
+            while (lo < hi)
+            {
+                long long const mid = (lo + hi) >> 1;
+                if (cdf[mid] > thr) hi = mid;
+                else
+                    lo = mid + 1;
+            }
+            A.picked[r] = lo;
+        }
+        return;
+    }
+    // resample_inplace
+    for (int t = 0; t < A.n_tiles; ++t)
+    {
+        offspring_body(t, cdf, n, n, rr, noff, pairs, sh_a, sh_b);
+        __syncthreads();
+    }
+    ++rr.offset;
+    scan_tile_pairs_body(pairs, A.n_tiles, totals, nullptr, sh_a, sh_b, &cd, &ce);
+    for (long long k = threadIdx.x; k < n; k += kThreads) src_of[k] = -1;
+    __syncthreads();
+    for (int t = 0; t < A.n_tiles; ++t)
+    {
+        offspring_apply_body(t, noff, n, pairs, dead, escan, src_of, n, sh_a, sh_b);
+        __syncthreads();
+    }
+    { // k_copy_inplace, the run's own warps: the k-th extra copy fills the k-th dead slot
+        long long const n_fill = min((long long)totals[0], (long long)totals[1]);
+        if (threadIdx.x == 0 && A.copies) atomicAdd(A.copies, (unsigned long long)n_fill);
+        int const lane = threadIdx.x & 31;
+        for (long long k = threadIdx.x >> 5; k < n_fill; k += kThreads / 32)
+        {
+            long long i = src_of[k];
+            if (i < 0)
+            {
+                long long lo = 0, hi = n;
+                while (lo < hi)
+                {
+                    long long const mid = (lo + hi) >> 1;
+                    if (escan[mid] > (int)k) hi = mid;
+                    else
+                        lo = mid + 1;
+                }
+                i = lo - 1;
+            }
+            int const id      = sid[i];
+            long long const j = dead[k];
+            warp_copy_block(counts + i * A.stride, counts + j * A.stride, (A.struct_size[id] + 3) >> 2, lane);
+            if (lane == 0)
+            {
+                sid[j]   = id;
+                state[j] = state[i];
+            }
+        }
+    }
+    double const uniform = 1.0 / (double)n;
+    for (long long i = threadIdx.x; i < n; i += kThreads) w[i] = uniform;
+    if (MODE == 1)
+    { // BABelief::resetDomainStateDistribution: fresh start states (k_reset_states)
+        __syncthreads();
+        for (long long i = threadIdx.x; i < n; i += kThreads)
+        {
+            auto g   = RngOf<false>::make(rr, i);
+            state[i] = sample_start_state(M, g);
+        }
+    }
+}
+
+// fba_runs_init: prototype + start state per particle, run r drawing like a stand-alone
+// fba_belief_init_sampled with seed + r (k_draw_init)
+__global__ void __launch_bounds__(kThreads)
+    k_runs_draw_init(DevModel M, long long n, long long n_total, int n_protos,
+                     const double* __restrict__ proto_cdf, int* __restrict__ particle_proto,
+                     int* __restrict__ particle_state, RngArgs ra)
+{
+    long long const i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_total) return;
+    RngArgs rr = ra;
+    rr.seed    = ra.seed + (unsigned long long)(i / n);
+    auto g     = RngOf<false>::make(rr, i % n);
+    int p      = 0;
+    if (proto_cdf)
+    {
+        double const u = draw_u(g);
+        while (p < n_protos - 1 && u >= proto_cdf[p]) ++p;
+    }
+    particle_proto[i] = p;
+    particle_state[i] = sample_start_state(M, g);
 }
 
 __global__ void __launch_bounds__(kThreads) k_fill(double* __restrict__ w, long long N, double v)

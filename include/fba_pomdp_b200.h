@@ -31,7 +31,7 @@ extern "C" {
 
 #define FBA_MAX_FEATURES 16
 /* bumped whenever a struct below changes layout; compare with fba_abi_version() after loading */
-#define FBA_ABI_VERSION 5
+#define FBA_ABI_VERSION 6
 
 typedef struct fba_ctx fba_ctx;
 typedef struct fba_model fba_model;
@@ -291,6 +291,40 @@ void* fba_belief_import_ptr(fba_belief* b, int64_t n_records);
 int64_t fba_belief_record_bytes(const fba_belief* b);
 /* phase 4: place n_records imported records into the slots the local resample left empty */
 int fba_belief_import(fba_belief* b, int64_t n_records);
+
+/* ---- many independent runs on one GPU ---------------------------------------
+ * The reference runs its `--runs` one after the other (src/experiments/BAPOMDPExperiment.cpp:32-78),
+ * each with its own small belief (episodic tiger: 1024 particles), which on its own leaves a GPU
+ * idle. An fba_runs object holds the importance-sampling beliefs of n_runs runs of
+ * particles_per_run particles back to back (run r owns particles [r n, (r+1) n) of
+ * fba_runs_belief()), and each call below advances EVERY run with one kernel launch, one CTA per
+ * run, each run with its own action / observation. PHILOX mode, dense storage. Run r is
+ * bit-identical to a stand-alone weighted fba_belief of particles_per_run particles driven by an
+ * fba_rng with seed + r through the same sequence of calls (each call here advances rng->offset
+ * exactly as its single-belief counterpart does).
+ * active (n_runs bytes, may be NULL = all): runs with 0 are left untouched (e.g. finished episodes). */
+typedef struct fba_runs fba_runs;
+int fba_runs_create(fba_ctx* ctx, fba_model* model, int32_t n_runs, int64_t particles_per_run, int64_t stride,
+                    fba_runs** out);
+void fba_runs_destroy(fba_runs* runs);
+/* the underlying particle storage, for fba_belief_download / fba_belief_upload (NOT a belief to
+ * update on its own: its weights are normalised per run) */
+fba_belief* fba_runs_belief(fba_runs* runs);
+/* Belief::initiate of every run: as fba_belief_init_sampled */
+int fba_runs_init_sampled(fba_runs* runs, int32_t n_protos, const int32_t* proto_struct_id,
+                          const float* proto_counts, const double* proto_probs, fba_rng* rng);
+/* Belief::updateEstimation of every run (BAImportanceSampling.cpp:74-88): action / observation are
+ * n_runs entries on the host; likelihood (n_runs doubles, may be NULL) receives each run's step
+ * likelihood */
+int fba_runs_update_estimation(fba_runs* runs, const int32_t* action, const int32_t* observation,
+                               const uint8_t* active, fba_rng* rng, double* likelihood);
+/* BABelief::resetDomainStateDistribution of every (active) run */
+int fba_runs_reset_domain_states(fba_runs* runs, const uint8_t* active, fba_rng* rng);
+/* Belief::sample of every (active) run: index[r] = particle index inside run r (storage index
+ * r * particles_per_run + index[r]); entries of inactive runs are left untouched */
+int fba_runs_sample(fba_runs* runs, const uint8_t* active, fba_rng* rng, int64_t* index);
+/* count blocks copied by the in-place resamples of all runs since creation */
+int64_t fba_runs_copies(fba_runs* runs);
 
 /* device pointers of the current particle arrays, for zero-copy views by the host language */
 void* fba_belief_counts_ptr(fba_belief* b);

@@ -1,0 +1,155 @@
+"""GPU: many independent runs batched on one GPU (fba_runs_*). One kernel launch
+advances the belief of every run (one CTA per run). The parity contract is exact: run r of the batch
+is BIT-IDENTICAL — states, structure ids, counts, weights, step likelihood, sampled index — to a
+stand-alone BAImportanceSampling of the same size driven by Rng.philox(seed + r) through the same
+sequence of calls (that stand-alone path is the one checked against the oracle and the reference
+elsewhere in this suite)."""
+import numpy as np
+import pytest
+
+import golden_util as G
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import fba_pomdp_b200 as fba
+    c = fba.Context(0)
+    yield c
+    c.close()
+
+
+def _protos(g):
+    sid0, counts0 = g["is/init_struct_id"], g["is/init_counts"]
+    used, sid0 = np.unique(sid0, return_inverse=True)
+    keys, psid, pc = {}, [], []
+    for i in range(len(sid0)):
+        k = (int(sid0[i]), counts0[i].tobytes())
+        if k not in keys:
+            keys[k] = len(psid)
+            psid.append(int(sid0[i]))
+            pc.append(counts0[i])
+    freq = np.bincount([keys[(int(sid0[i]), counts0[i].tobytes())] for i in range(len(sid0))],
+                       minlength=len(psid)).astype(np.float64)
+    return used, np.array(psid, np.int32), np.stack(pc), freq
+
+
+# name, runs, particles per run (1024 = one scan tile; 300 / 2500: ragged and multi-tile runs)
+CASES = [("tiger", 7, 1024), ("tiger", 3, 2500), ("ftiger", 4, 300), ("sysadmin3", 5, 700), ("ca", 3, 1500),
+         ("gridworld3", 3, 640)]
+
+
+@pytest.mark.parametrize("name,R,n", CASES)
+def test_batched_runs_equal_stand_alone_beliefs(ctx, name, R, n):
+    import fba_pomdp_b200 as fba
+    g = G.load(name)
+    used, psid, pc, freq = _protos(g)
+    sim = fba.BAPOMDP(ctx, g.desc, g.t_par[used], g.o_par[used])
+    seed = 1234
+    A, O = int(g.desc["A"]), int(g.desc["O"])
+    rs = np.random.RandomState(5)
+    T = 5
+    acts = rs.randint(0, A, (T, R)).astype(np.int32)
+    # observations the particles can actually produce: the golden script's (a, o) pairs
+    pairs = {}
+    for a, o in zip(g.a, g.o):
+        pairs.setdefault(int(a), []).append(int(o))
+    for t in range(T):
+        for r in range(R):
+            if int(acts[t, r]) not in pairs:
+                acts[t, r] = int(g.a[0])
+    obs = np.array([[pairs[int(acts[t, r])][rs.randint(len(pairs[int(acts[t, r])]))] for r in range(R)]
+                    for t in range(T)], np.int32)
+    active = np.ones((T, R), np.uint8)
+    active[2, 1] = 0      # run 1 sits out step 2
+    active[3, 0] = 0
+
+    # --- the batch
+    batch = fba.BatchedBAImportanceSampling(R, n)
+    rng = fba.Rng.philox(seed)
+    batch.initiate_sampled(sim, psid, pc, freq, rng, stride=pc.shape[1])
+    b_lik, b_idx = [], []
+    for t in range(T):
+        if t == 3:
+            batch.resetDomainStateDistribution(rng, active=active[t])
+        b_lik.append(batch.updateEstimation(acts[t], obs[t], rng, active=active[t]))
+        b_idx.append(batch.sample(rng, active=active[t]))
+    got = [batch.download(r) for r in range(R)]
+    copies = batch.copies()
+    batch.free()
+
+    # --- R stand-alone beliefs
+    total_copies = 0
+    for r in range(R):
+        b = fba.BAImportanceSampling(n)
+        rr = fba.Rng.philox(seed + r)
+        b.initiate_sampled(sim, psid, pc, freq, rr, stride=pc.shape[1])
+        for t in range(T):
+            if not active[t, r]:
+                rr.offset += (2 if t == 3 else 0) + 2 + 1    # the batch's calls advanced the offset anyway
+                continue
+            if t == 3:
+                b.resetDomainStateDistribution(rr)
+            lik = b.updateEstimation(int(acts[t, r]), int(obs[t, r]), rr)
+            assert lik == b_lik[t][r], (name, r, t)
+            assert b.sample(rr) == b_idx[t][r], (name, r, t)
+        want = b.download()
+        for k in ("state", "struct_id", "w"):
+            np.testing.assert_array_equal(got[r][k], want[k], err_msg="%s run %d %s" % (name, r, k))
+        np.testing.assert_array_equal(got[r]["counts"], want["counts"])
+        total_copies += b.resample_stats()[0]
+        b.free()
+    assert copies == total_copies
+    # inactive steps really were skipped
+    assert np.isnan(b_lik[2][1]) and b_idx[2][1] == -1 and np.isnan(b_lik[3][0])
+    sim.close()
+
+
+def test_runs_do_not_mix(ctx):
+    """Particles never cross a run boundary: every run is tagged through an otherwise unused count
+    cell and keeps its tag through ten updates with different actions and observations per run."""
+    import fba_pomdp_b200 as fba
+    g = G.load("tiger")
+    R, n = 64, 1024
+    sim = fba.BAPOMDP(ctx, g.desc, g.t_par, g.o_par)
+    batch = fba.BatchedBAImportanceSampling(R, n)
+    rng = fba.Rng.philox(9)
+    proto = g["is/init_counts"][:1]
+    batch.initiate_sampled(sim, [0], proto, None, rng)
+    L, h = batch.L, batch.storage
+    # tag: T[open-left][s=0][s'] is never touched by listen-only scripts
+    full = fba.beliefs._ParticleBelief._download(L, ctx, h, True)
+    full["counts"][:, 0] = 1000.0 + np.repeat(np.arange(R), n)
+    assert L.fba_belief_upload(h, 0, R * n, None, None, fba.capi.ptr(full["counts"]), None) == 0
+    rs = np.random.RandomState(0)
+    for t in range(10):
+        lik = batch.updateEstimation(np.full(R, 2), rs.randint(0, 2, R), rng)
+        assert np.all((lik > 0) & (lik <= 1))
+    after = fba.beliefs._ParticleBelief._download(L, ctx, h, True)
+    np.testing.assert_array_equal(after["counts"][:, 0], 1000.0 + np.repeat(np.arange(R), n))
+    np.testing.assert_array_equal(after["w"], np.full(R * n, 1.0 / n))
+    base = proto[0].astype(np.float64).sum() + 1000.0 - proto[0][0]
+    sums = after["counts"].astype(np.float64).sum(1) - np.repeat(np.arange(R), n)
+    np.testing.assert_array_equal(sums, np.full(R * n, base + 2 * 10))
+    batch.free()
+    sim.close()
+
+
+def test_runs_argument_checks(ctx):
+    import fba_pomdp_b200 as fba
+    g = G.load("tiger")
+    sim = fba.BAPOMDP(ctx, g.desc, g.t_par, g.o_par)
+    batch = fba.BatchedBAImportanceSampling(2, 64)
+    rng = fba.Rng.philox(1)
+    batch.initiate_sampled(sim, [0], g["is/init_counts"][:1], None, rng)
+    with pytest.raises(fba.FbaError):
+        batch.updateEstimation([2, 9], [0, 0], rng)
+    with pytest.raises(fba.FbaError):
+        batch.updateEstimation([2, 2], [0, 0], fba.Rng.replay(np.zeros(64, np.uint32)))
+    # an out-of-range action of an INACTIVE run is ignored
+    batch.updateEstimation([2, 9], [0, 0], rng, active=[1, 0])
+    batch.free()
+    with pytest.raises(fba.FbaError):
+        fba.BatchedBAImportanceSampling(0, 64)
+    sim.close()
