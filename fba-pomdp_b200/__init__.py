@@ -5,10 +5,10 @@ include/fba_pomdp_b200.h). This package is the thin host-side mirror of the refe
 Belief / BABelief / rollout interfaces used by the tests and the benchmark."""
 from . import capi  # noqa: F401
 from .beliefs import (BAImportanceSampling, BAPOMDP, BARejectionSampling, BatchedBAImportanceSampling,  # noqa: F401
-                      Context, ReinvigoratingRejectionSampling, rollouts)
+                      Context, ReinvigoratingRejectionSampling, SearchTree, rollouts)
 from .capi import FbaError, Rng  # noqa: F401
 
-__all__ = ["capi", "Context", "BAPOMDP", "BAImportanceSampling", "BARejectionSampling", "BatchedBAImportanceSampling",
+__all__ = ["capi", "Context", "BAPOMDP", "BAImportanceSampling", "BARejectionSampling", "BatchedBAImportanceSampling", "SearchTree",
            "ReinvigoratingRejectionSampling", "rollouts", "Rng", "FbaError"]
 from .sharded import ShardedBAImportanceSampling, exchange_plan, offspring_quotas  # noqa: F401,E402
 from .sharded import exchange_records  # noqa: F401,E402

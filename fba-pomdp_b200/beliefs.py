@@ -366,6 +366,33 @@ class ReinvigoratingRejectionSampling(_ParticleBelief):
             self.fc = None
 
 
+class SearchTree:
+    """Device-resident POMCP search tree (fba_tree_*): planners::RBAPOUCT::selectAction
+    (RBAPOUCT.cpp:67-153) with whole simulations inside one kernel, `wave` at a time."""
+
+    def __init__(self, simulator, max_simulations, max_depth):
+        self.sim, self.ctx, self.L = simulator, simulator.ctx, simulator.L
+        h = C.c_void_p()
+        _check(self.ctx.h, self.L.fba_tree_create(self.ctx.h, simulator.h, int(max_simulations), int(max_depth),
+                                                  C.byref(h)))
+        self.h = h
+
+    def selectAction(self, belief, n_simulations, depth, u, discount, wave, rng):
+        """-> (action, q[A], visits[A])"""
+        act = C.c_int32(-1)
+        q = np.zeros(self.sim.A, np.float64)
+        n = np.zeros(self.sim.A, np.int64)
+        _check(self.ctx.h, self.L.fba_tree_search(self.h, belief.h, int(n_simulations), int(depth), float(u),
+                                                  float(discount), int(wave), C.byref(rng), C.byref(act), ptr(q),
+                                                  ptr(n)))
+        return int(act.value), q, n
+
+    def free(self):
+        if self.h:
+            self.L.fba_tree_destroy(self.h)
+            self.h = None
+
+
 class BatchedBAImportanceSampling:
     """The importance-sampling beliefs of `n_runs` INDEPENDENT runs (the reference's `--runs`,
     src/experiments/BAPOMDPExperiment.cpp:32-78), `n` particles each, advanced together: every call

@@ -1898,6 +1898,161 @@ extern "C" int fba_step_batch(fba_belief* b, int64_t n, const int64_t* particle,
     return FBA_OK;
 }
 
+// ---- POMCP, tree on the device -------------------------------------------------------------------
+
+struct fba_tree
+{
+    fba_ctx* ctx   = nullptr;
+    fba_model* m   = nullptr;
+    long long max_sims = 0;
+    int max_depth  = 0;
+    unsigned table = 0; // slots (power of two); node `table` is the root
+    unsigned long long* keys = nullptr;
+    int *visits = nullptr, *n_sel = nullptr, *n_done = nullptr;
+    double* q_sum = nullptr;
+    long long path_cap = 0; // simulations per wave the path scratch holds
+    int *path_node = nullptr, *path_action = nullptr;
+    double* path_reward = nullptr;
+    int* d_overflow = nullptr;
+};
+
+extern "C" void fba_tree_destroy(fba_tree* t)
+{
+    if (!t) return;
+    cudaSetDevice(t->ctx->device);
+    cudaStreamSynchronize(t->ctx->stream);
+    cudaFree(t->keys), cudaFree(t->visits), cudaFree(t->n_sel), cudaFree(t->n_done), cudaFree(t->q_sum);
+    cudaFree(t->path_node), cudaFree(t->path_action), cudaFree(t->path_reward), cudaFree(t->d_overflow);
+    delete t;
+}
+
+extern "C" int fba_tree_create(fba_ctx* ctx, fba_model* m, int64_t max_simulations, int32_t max_depth,
+                               fba_tree** out)
+{
+    if (!ctx || !m || !out) return FBA_ERR_INVALID;
+    *out = nullptr;
+    REQUIRE(ctx, max_simulations >= 1 && max_simulations <= (1ll << 26), "tree: max_simulations must be in [1, 2^26]");
+    REQUIRE(ctx, max_depth >= 1 && max_depth <= 4096, "tree: max_depth must be in [1, 4096]");
+    CU(ctx, cudaSetDevice(ctx->device));
+    auto t       = new fba_tree();
+    t->ctx       = ctx;
+    t->m         = m;
+    t->max_sims  = max_simulations;
+    t->max_depth = max_depth;
+    t->table     = 1024;
+    while ((long long)t->table < 2 * max_simulations) t->table <<= 1; // load factor <= 1/2
+    size_t const nodes = (size_t)t->table + 1, A = (size_t)m->dev.A;
+    cudaError_t e = cudaMalloc(&t->keys, (size_t)t->table * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&t->visits, nodes * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&t->n_sel, nodes * A * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&t->n_done, nodes * A * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&t->q_sum, nodes * A * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&t->d_overflow, sizeof(int));
+    if (e != cudaSuccess)
+    {
+        ctx->err = std::string("tree alloc: ") + cudaGetErrorString(e);
+        fba_tree_destroy(t);
+        return FBA_ERR_CUDA;
+    }
+    *out = t;
+    return FBA_OK;
+}
+
+extern "C" int fba_tree_search(fba_tree* t, fba_belief* b, int64_t n_sims, int32_t depth, double u, double discount,
+                               int32_t wave, fba_rng* rng, int32_t* action, double* q_out, int64_t* visits_out)
+{
+    if (!t || !b || !rng || !action) return FBA_ERR_INVALID;
+    fba_ctx* ctx      = t->ctx;
+    DevModel const& D = t->m->dev;
+    REQUIRE(ctx, b->m == t->m && b->ctx == ctx, "tree_search: the belief must use the tree's model and context");
+    REQUIRE(ctx, rng->mode == FBA_RNG_PHILOX, "tree_search: PHILOX mode only");
+    REQUIRE(ctx, n_sims >= 1 && n_sims <= t->max_sims, "tree_search: n_simulations must be in [1, max_simulations]");
+    REQUIRE(ctx, depth >= 0 && depth <= t->max_depth, "tree_search: depth must be in [0, max_depth]");
+    REQUIRE(ctx, wave >= 1, "tree_search: wave must be at least 1");
+    REQUIRE(ctx, discount > 0 && discount <= 1 && u >= 0, "tree_search: discount in (0, 1], u >= 0");
+    CU(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    long long const W = std::min<long long>(wave, n_sims);
+    if (W > t->path_cap)
+    {
+        cudaFree(t->path_node), cudaFree(t->path_action), cudaFree(t->path_reward);
+        t->path_node = t->path_action = nullptr, t->path_reward = nullptr;
+        t->path_cap = 0;
+        size_t const cells = (size_t)W * t->max_depth;
+        CU(ctx, cudaMalloc(&t->path_node, cells * sizeof(int)));
+        CU(ctx, cudaMalloc(&t->path_action, cells * sizeof(int)));
+        CU(ctx, cudaMalloc(&t->path_reward, cells * sizeof(double)));
+        t->path_cap = W;
+    }
+    size_t const nodes = (size_t)t->table + 1, A = (size_t)D.A;
+    CU(ctx, cudaMemsetAsync(t->keys, 0xFF, (size_t)t->table * sizeof(unsigned long long), ctx->stream));
+    CU(ctx, cudaMemsetAsync(t->visits, 0, nodes * sizeof(int), ctx->stream));
+    CU(ctx, cudaMemsetAsync(t->n_sel, 0, nodes * A * sizeof(int), ctx->stream));
+    CU(ctx, cudaMemsetAsync(t->n_done, 0, nodes * A * sizeof(int), ctx->stream));
+    CU(ctx, cudaMemsetAsync(t->q_sum, 0, nodes * A * sizeof(double), ctx->stream));
+    CU(ctx, cudaMemsetAsync(t->d_overflow, 0, sizeof(int), ctx->stream));
+    if (b->weighted && !b->cdf_valid)
+        if ((rc = native_normalize(b, false, 1.0))) return rc;
+
+    TreeArgs T{};
+    T.keys = t->keys, T.visits = t->visits, T.n_sel = t->n_sel, T.n_done = t->n_done, T.q_sum = t->q_sum;
+    T.mask = t->table - 1, T.root = (int)t->table;
+    T.counts = b->counts[b->cur], T.stride = b->stride, T.sid = b->sid[b->cur], T.state = b->state[b->cur];
+    T.cdf = b->weighted ? b->aux : nullptr, T.N = b->N;
+    T.base = b->base, T.base_stride = b->lstride;
+    T.depth = depth, T.u = u, T.discount = discount;
+    T.path_node = t->path_node, T.path_action = t->path_action, T.path_reward = t->path_reward;
+    T.overflow = t->d_overflow;
+    RngArgs ra{};
+    ra.seed   = rng->seed;
+    ra.offset = rng->offset++;
+    for (long long first = 0; first < n_sims; first += W)
+    {
+        T.first_sim = first;
+        T.n_wave    = std::min(W, n_sims - first);
+        // spread a small wave over as many SMs as possible (latency-bound: see fba_rollouts)
+        int tpb = kThreads;
+        while (tpb > 32 && (T.n_wave + tpb - 1) / tpb < 2ll * ctx->sm_count) tpb >>= 1;
+        int const grid = blocks_for(T.n_wave, tpb);
+        if (b->delta_cap > 0)
+        {
+            if (D.sampled) LAUNCH(ctx, (k_pomcp_wave<true, true, true>), grid, tpb, D, T, ra);
+            else
+                LAUNCH(ctx, (k_pomcp_wave<true, true, false>), grid, tpb, D, T, ra);
+        } else if (D.sampled)
+        {
+            if (b->m->long_rows) LAUNCH(ctx, (k_pomcp_wave<false, true, true>), grid, tpb, D, T, ra);
+            else
+                LAUNCH(ctx, (k_pomcp_wave<false, false, true>), grid, tpb, D, T, ra);
+        } else
+        {
+            if (b->m->long_rows) LAUNCH(ctx, (k_pomcp_wave<false, true, false>), grid, tpb, D, T, ra);
+            else
+                LAUNCH(ctx, (k_pomcp_wave<false, false, false>), grid, tpb, D, T, ra);
+        }
+    }
+    std::vector<int> nd(A);
+    std::vector<double> qs(A);
+    CU(ctx, cudaMemcpyAsync(nd.data(), t->n_done + (size_t)t->table * A, A * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(qs.data(), t->q_sum + (size_t)t->table * A, A * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    // the final choice: best mean return, no exploration term, random among ties (RBAPOUCT.cpp:204)
+    PhiloxRng g(rng->seed, 0, rng->offset++);
+    double best = -1.7976931348623157e308;
+    int pick = 0, ties = 0;
+    for (int a = 0; a < D.A; ++a)
+    {
+        double const v = nd[a] > 0 ? qs[a] / (double)nd[a] : 0.0;
+        if (q_out) q_out[a] = v;
+        if (visits_out) visits_out[a] = nd[a];
+        if (v > best) best = v, pick = a, ties = 1;
+        else if (v == best && draw_k(g, (uint32_t)++ties) == 0)
+            pick = a;
+    }
+    *action = pick;
+    return FBA_OK;
+}
+
 // ---- many independent runs ------------------------------------------------------------------------
 
 struct fba_runs

@@ -1274,6 +1274,194 @@ __global__ void __launch_bounds__(kThreads)
 }
 
 // ------------------------------------------------------------------------------------------------
+// POMCP with the SEARCH TREE ON THE DEVICE: planners::RBAPOUCT::selectAction
+// (RBAPOUCT.cpp:67-153) as waves of simulations, one thread per simulation, the whole simulation —
+// root particle, UCB descent (traverseActionNode / traverseChanceNode, RBAPOUCT.cpp:197-277), leaf
+// expansion, random-policy rollout (RBAPOUCT.cpp:295-323) and back-up — inside one kernel. The
+// simulations of a wave share the tree through atomics:
+//   * a tree node IS a slot of an open-addressing hash table keyed (parent node, action, observation);
+//     claiming the slot with one atomicCAS creates the node, so there is no allocator and no waiting;
+//   * UCB reads q = q_sum / n_done and the selection counts n_sel, which are incremented when an action
+//     is CHOSEN (virtual visits): concurrent simulations spread over the actions instead of all taking
+//     the same path; returns are added to q_sum / n_done when the simulation has finished
+//     (ChanceNode::addVisit, MCTSTreeNodes.cpp:8-12: the mean of the returns).
+// Root sampling (RBAPOUCT.cpp:86-106): the particle keeps its counts for the whole simulation
+// (KeepCounts), only the domain state evolves. The tree differs from the sequential planner's only
+// in the order in which simulations see each other's statistics.
+// ------------------------------------------------------------------------------------------------
+struct TreeArgs
+{
+    unsigned long long* keys; // [table]: (parent + 1) << 32 | (action * O + observation); EMPTY = ~0
+    int* visits;              // [table + 1] selections through the node; node `table` is the root
+    int* n_sel;               // [table + 1][A] times the action was chosen (incl. simulations in flight)
+    int* n_done;              // [table + 1][A] returns backed up
+    double* q_sum;            // [table + 1][A] sum of those returns
+    unsigned int mask;        // table - 1 (table is a power of two)
+    int root;                 // = table
+    // belief
+    const float* counts;
+    long long stride;
+    const int *sid, *state;
+    const double* cdf; // weighted beliefs: inclusive cdf; NULL: flat filter, uniform pick
+    long long N;
+    const float* base; // base+delta storage
+    long long base_stride;
+    // search
+    int depth;
+    double u, discount;
+    long long first_sim, n_wave;
+    int* path_node;   // [depth][wave]
+    int* path_action; // [depth][wave]
+    double* path_reward;
+    int* overflow;    // set when the table was full (the simulation then ends in a rollout)
+};
+
+__device__ __forceinline__ unsigned int tree_hash(unsigned long long k)
+{
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdull;
+    k ^= k >> 33;
+    k *= 0xc4ceb9fe1a85ec53ull;
+    k ^= k >> 33;
+    return (unsigned int)k;
+}
+
+// argmax_a q(a) + u sqrt(log(visits + 1) / n_sel(a)), +inf for n_sel = 0 (RBAPOUCT.cpp:349-357);
+// ties broken uniformly (RBAPOUCT.cpp:204) with one draw per tie
+template<class R>
+__device__ __forceinline__ int tree_ucb(const TreeArgs& T, int node, int A, R& g)
+{
+    double const lg = log1p((double)T.visits[node]);
+    double best     = -1.7976931348623157e308;
+    int pick = 0, ties = 0;
+    for (int a = 0; a < A; ++a)
+    {
+        int const ns = T.n_sel[(long long)node * A + a], nd = T.n_done[(long long)node * A + a];
+        double v;
+        if (ns == 0) v = 1.7976931348623157e308;
+        else
+            v = ((nd > 0) ? T.q_sum[(long long)node * A + a] / (double)nd : 0.0) + T.u * sqrt(lg / (double)ns);
+        if (v > best) best = v, pick = a, ties = 1;
+        else if (v == best && draw_k(g, (uint32_t)++ties) == 0)
+            pick = a;
+    }
+    return pick;
+}
+
+template<bool DELTA, bool LONG, bool SAMPLED>
+__global__ void __launch_bounds__(kThreads)
+    k_pomcp_wave(DevModel M, TreeArgs T, RngArgs ra)
+{
+    long long const t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T.n_wave) return;
+    auto g = RngOf<false>::make(ra, T.first_sim + t);
+    // root particle: Belief::sample()
+    long long p;
+    if (T.cdf)
+    {
+        double const thr = draw_u(g) * T.cdf[T.N - 1];
+        long long lo = 0, hi = T.N - 1;
+        while (lo < hi)
+        {
+            long long const mid = (lo + hi) >> 1;
+            if (T.cdf[mid] > thr) hi = mid;
+            else
+                lo = mid + 1;
+        }
+        p = lo;
+    } else
+        p = draw_k(g, (uint32_t)T.N);
+    float* c         = const_cast<float*>(T.counts) + p * T.stride; // KeepCounts: never written
+    const Node* base = DELTA ? M.nodes : M.nodes + (long long)T.sid[p] * M.A * M.J;
+    const float* tb  = DELTA ? T.base + (long long)T.sid[p] * T.base_stride : nullptr;
+    int s    = T.state[p];
+    int node = T.root, len = 0, d = T.depth;
+    double leaf = 0.0;
+    while (d > 0)
+    {
+        int const a = tree_ucb(T, node, M.A, g);
+        atomicAdd(&T.visits[node], 1);
+        atomicAdd(&T.n_sel[(long long)node * M.A + a], 1);
+        int o, s2;
+        if (DELTA)
+            s2 = hyper_step_delta<STEP_KEEP, SAMPLED>(M, base + (long long)a * M.J, tb, reinterpret_cast<int*>(c), 0, s,
+                                                      g, o, nullptr, nullptr);
+        else
+        {
+            Feat x2;
+            s2 = hyper_step<STEP_KEEP, decltype(g), false, LONG, SAMPLED>(M, base + (long long)a * M.J, c, s, g, o, x2,
+                                                                          nullptr);
+        }
+        bool terminal;
+        double const rew                      = domain_reward(M, s, a, s2, terminal);
+        T.path_node[len * T.n_wave + t]   = node;
+        T.path_action[len * T.n_wave + t] = a;
+        T.path_reward[len * T.n_wave + t] = rew;
+        ++len;
+        s = s2;
+        --d;
+        if (terminal) break; // delayed return 0 (RBAPOUCT.cpp:252)
+        // the child for (node, a, o): find it, or create it by claiming a slot
+        unsigned long long const key =
+            ((unsigned long long)(node + 1) << 32) | (unsigned long long)((long long)a * M.O + o);
+        unsigned int h = tree_hash(key) & T.mask;
+        int child = -1;
+        bool created = false;
+        for (unsigned int probe = 0; probe <= T.mask; ++probe, h = (h + 1) & T.mask)
+        {
+            unsigned long long const seen = atomicCAS(&T.keys[h], ~0ull, key);
+            if (seen == ~0ull)
+            {
+                child   = (int)h;
+                created = true;
+                break;
+            }
+            if (seen == key)
+            {
+                child = (int)h;
+                break;
+            }
+        }
+        if (child < 0) *T.overflow = 1;
+        if (created || child < 0)
+        { // new leaf: evaluate by a random-policy rollout (RBAPOUCT.cpp:258-266, 295-323)
+            double disc = 1.0;
+            bool term   = false;
+            while (d > 0 && !term)
+            {
+                int const ra_ = random_action(M, g);
+                int o2, s3;
+                if (DELTA)
+                    s3 = hyper_step_delta<STEP_KEEP, SAMPLED>(M, base + (long long)ra_ * M.J, tb,
+                                                              reinterpret_cast<int*>(c), 0, s, g, o2, nullptr, nullptr);
+                else
+                {
+                    Feat x3;
+                    s3 = hyper_step<STEP_KEEP, decltype(g), false, LONG, SAMPLED>(M, base + (long long)ra_ * M.J, c, s,
+                                                                                  g, o2, x3, nullptr);
+                }
+                double const r2 = domain_reward(M, s, ra_, s3, term);
+                leaf            = __dadd_rn(leaf, __dmul_rn(r2, disc));
+                disc            = __dmul_rn(disc, T.discount);
+                s               = s3;
+                --d;
+            }
+            break;
+        }
+        node = child;
+    }
+    // back up: ret = r + discount * delayed (RBAPOUCT.cpp:271-272)
+    double ret = leaf;
+    for (int k = len - 1; k >= 0; --k)
+    {
+        ret = T.path_reward[k * T.n_wave + t] + T.discount * ret;
+        long long const cell = (long long)T.path_node[k * T.n_wave + t] * M.A + T.path_action[k * T.n_wave + t];
+        atomicAdd(&T.q_sum[cell], ret);
+        atomicAdd(&T.n_done[cell], 1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // rejection sampling (RejectionSampling.hpp:26-72) as waves of independent attempts:
 // attempt t picks a particle uniformly, simulates a step on it WITHOUT touching it and records the
 // outcome; the accepted attempts, in attempt order, become the new particles.

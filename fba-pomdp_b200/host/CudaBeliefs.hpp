@@ -111,6 +111,7 @@ public:
 
     ~CudaSimulator()
     {
+        fba_tree_destroy(_tree);
         fba_model_destroy(_model);
         fba_ctx_destroy(_ctx);
     }
@@ -119,6 +120,23 @@ public:
 
     fba_ctx* ctx() const { return _ctx; }
     fba_model* model() const { return _model; }
+    // the device-resident POMCP tree for this simulator (CudaTreePOUCT); it lives and dies with the
+    // context, so a planner that outlives the belief never holds a dangling handle
+    fba_tree* tree(int64_t simulations, int depth) const
+    {
+        if (_tree && (simulations > _tree_sims || depth > _tree_depth))
+        {
+            fba_tree_destroy(_tree);
+            _tree = nullptr;
+        }
+        if (!_tree)
+        {
+            check(_ctx, fba_tree_create(_ctx, _model, simulations, depth, &_tree), "fba_tree_create");
+            _tree_sims  = simulations;
+            _tree_depth = depth;
+        }
+        return _tree;
+    }
     BAPOMDP const& sim() const { return _sim; }
     bool factored() const { return _fbapomdp != nullptr; }
     int A() const { return _sim.domainSize()->_A; }
@@ -214,6 +232,9 @@ private:
     ::bayes_adaptive::factored::FBAPOMDP const* _fbapomdp = nullptr;
     fba_ctx* _ctx     = nullptr;
     fba_model* _model = nullptr;
+    mutable fba_tree* _tree     = nullptr;
+    mutable int64_t _tree_sims  = 0;
+    mutable int _tree_depth     = 0;
     std::vector<int> _feat_s, _feat_o;
     std::vector<double> _rew_sa, _rew_as2;
     std::vector<uint8_t> _term_sa, _term_as2;

@@ -29,6 +29,7 @@
 #ifndef FBA_B200_CUDA_PLANNER_HPP
 #define FBA_B200_CUDA_PLANNER_HPP
 
+#include <algorithm>
 #include <cmath>
 #include <limits>
 #include <memory>
@@ -271,6 +272,68 @@ private:
         check(ctx, fba_belief_gather_states(b, (int64_t)particle.size(), particle.data(), state->data()),
               "fba_belief_gather_states");
     }
+};
+
+// POMCP with the search tree itself on the device (fba_tree_*): every simulation — root particle,
+// UCB descent, leaf expansion, rollout, back-up — runs inside one kernel, `wave` simulations at a
+// time sharing the tree through atomics. The host only sees the root's action values. Stands in for
+// planners::RBAPOUCT like CudaBatchedPOUCT, with no per-level round trip between host and device.
+class CudaTreePOUCT : public planners::BAPlanner
+{
+public:
+    explicit CudaTreePOUCT(configurations::Conf const& c, int wave = 256, uint64_t seed = 777) :
+            _n(c.planner_conf.mcts_simulation_amount),
+            _max_depth(c.planner_conf.mcts_max_depth == -1 ? c.horizon : c.planner_conf.mcts_max_depth),
+            _h(c.horizon),
+            _u(c.planner_conf.mcts_exploration_const),
+            _discount(c.discount),
+            _wave(wave)
+    {
+        // the reference's argument checks (RBAPOUCT.cpp:38-55)
+        if (_n < 1) throw "cannot initiate RBAPOUCT with " + std::to_string(_n) + " simulations, must be greater than 0";
+        if (_max_depth < 0)
+            throw "cannot initiate RBAPOUCT with " + std::to_string(_max_depth) + " max depth, must be greater or equal to 0";
+        if (_h <= 0) throw "cannot initiate RBAPOUCT with " + std::to_string(_h) + " horizon, must be greater than 0";
+        if (_wave < 1) throw std::string("CudaTreePOUCT: wave must be at least 1");
+        _rng.mode    = FBA_RNG_PHILOX;
+        _rng.words   = nullptr;
+        _rng.n_words = _rng.cursor = 0;
+        _rng.seed    = seed;
+        _rng.offset  = 0;
+    }
+
+    Action const* selectAction(BAPOMDP const& simulator, beliefs::BABelief const& belief, History const& history)
+        const override
+    {
+        fba_belief* b               = nullptr;
+        CudaSimulator const* cuda = nullptr;
+        if (auto p = dynamic_cast<CudaParticleBelief const*>(&belief)) b = p->handle(), cuda = &p->cuda();
+        else if (auto r = dynamic_cast<CudaReinvigoratingRejectionSampling const*>(&belief))
+            b = r->handle(), cuda = &r->cuda();
+        else
+            throw std::string("CudaTreePOUCT needs one of the fba_b200 CUDA beliefs");
+        fba_ctx* ctx   = cuda->ctx();
+        fba_tree* tree = cuda->tree(_n, std::max(1, std::max(_max_depth, _h)));
+        int const depth = std::min(_h - (int)history.length(), _max_depth);
+        int32_t best    = 0;
+        check(ctx, fba_tree_search(tree, b, _n, depth, _u, _discount, _wave, &_rng, &best, nullptr, nullptr),
+              "fba_tree_search");
+        // the domain's own action object for that index (RBAPOUCT.cpp:74)
+        std::vector<Action const*> actions;
+        simulator.addLegalActions(belief.sample(), &actions);
+        Action const* chosen = nullptr;
+        for (auto a : actions)
+            if (a->index() == best) chosen = simulator.copyAction(a);
+        for (auto a : actions) simulator.releaseAction(a);
+        if (!chosen) throw std::string("CudaTreePOUCT: state-dependent action sets are not supported");
+        return chosen;
+    }
+
+private:
+    int _n, _max_depth, _h;
+    double _u, _discount;
+    int _wave;
+    mutable fba_rng _rng;
 };
 
 } // namespace fba_b200

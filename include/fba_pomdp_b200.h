@@ -31,7 +31,7 @@ extern "C" {
 
 #define FBA_MAX_FEATURES 16
 /* bumped whenever a struct below changes layout; compare with fba_abi_version() after loading */
-#define FBA_ABI_VERSION 6
+#define FBA_ABI_VERSION 7
 
 typedef struct fba_ctx fba_ctx;
 typedef struct fba_model fba_model;
@@ -291,6 +291,22 @@ void* fba_belief_import_ptr(fba_belief* b, int64_t n_records);
 int64_t fba_belief_record_bytes(const fba_belief* b);
 /* phase 4: place n_records imported records into the slots the local resample left empty */
 int fba_belief_import(fba_belief* b, int64_t n_records);
+
+/* ---- POMCP with the search tree on the device --------------------------------
+ * planners::RBAPOUCT::selectAction (src/planners/bayes-adaptive/RBAPOUCT.cpp:67-153) as waves of
+ * `wave` concurrent simulations, each one entirely on the device: root particle from the belief
+ * (weighted or flat), UCB descent with BAPOMDP::step in KeepCounts mode (RBAPOUCT.cpp:197-277), one
+ * new leaf, random-policy rollout (RBAPOUCT.cpp:295-323), back-up. Simulations of one wave see each
+ * other through atomic statistics (selection counts are raised when an action is chosen). PHILOX
+ * mode. max_simulations bounds the tree (one node per simulation), max_depth the search depth. */
+typedef struct fba_tree fba_tree;
+int fba_tree_create(fba_ctx* ctx, fba_model* model, int64_t max_simulations, int32_t max_depth, fba_tree** out);
+void fba_tree_destroy(fba_tree* tree);
+/* depth = min(horizon - history length, max depth) as RBAPOUCT.cpp:80; u = UCB exploration constant;
+ * *action = argmax_a Q(root, a), ties broken uniformly; q / visits (n_actions entries, may be NULL)
+ * receive the root's mean returns and completed visit counts */
+int fba_tree_search(fba_tree* tree, fba_belief* b, int64_t n_simulations, int32_t depth, double u,
+                    double discount, int32_t wave, fba_rng* rng, int32_t* action, double* q, int64_t* visits);
 
 /* ---- many independent runs on one GPU ---------------------------------------
  * The reference runs its `--runs` one after the other (src/experiments/BAPOMDPExperiment.cpp:32-78),

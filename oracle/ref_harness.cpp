@@ -646,14 +646,17 @@ int ref_adapter_episodes(void* hv, int kind, long n, char const* planner, int si
         conf.planner                             = planner;
         conf.planner_conf.mcts_simulation_amount = sims;
         conf.planner_conf.mcts_max_depth         = conf.horizon;
-        // planner "cuda-po-uct[:wave]" = this repo's wave-parallel POMCP over the C ABI
+        // planner "cuda-po-uct[:wave]" = this repo's wave-parallel POMCP over the C ABI (tree on the host),
+        // "cuda-tree-po-uct[:wave]" = the same with the tree on the device
         std::unique_ptr<Planner> plan;
-        if (conf.planner.rfind("cuda-po-uct", 0) == 0)
+        if (conf.planner.rfind("cuda-po-uct", 0) == 0 || conf.planner.rfind("cuda-tree-po-uct", 0) == 0)
         {
             int wave = 64;
             auto pos = conf.planner.find(':');
             if (pos != std::string::npos) wave = std::stoi(conf.planner.substr(pos + 1));
-            plan.reset(new fba_b200::CudaBatchedPOUCT(conf, wave));
+            if (conf.planner.rfind("cuda-tree", 0) == 0) plan.reset(new fba_b200::CudaTreePOUCT(conf, wave));
+            else
+                plan.reset(new fba_b200::CudaBatchedPOUCT(conf, wave));
         } else
             plan = factory::makeBAPlanner(conf);
 
@@ -712,12 +715,14 @@ double ref_plan_seconds(void* hv, int kind, long n, char const* planner, int sim
         conf.planner_conf.mcts_simulation_amount = sims;
         conf.planner_conf.mcts_max_depth         = conf.horizon;
         std::unique_ptr<Planner> plan;
-        if (conf.planner.rfind("cuda-po-uct", 0) == 0)
+        if (conf.planner.rfind("cuda-po-uct", 0) == 0 || conf.planner.rfind("cuda-tree-po-uct", 0) == 0)
         {
             int wave = 64;
             auto pos = conf.planner.find(':');
             if (pos != std::string::npos) wave = std::stoi(conf.planner.substr(pos + 1));
-            plan.reset(new fba_b200::CudaBatchedPOUCT(conf, wave));
+            if (conf.planner.rfind("cuda-tree", 0) == 0) plan.reset(new fba_b200::CudaTreePOUCT(conf, wave));
+            else
+                plan.reset(new fba_b200::CudaBatchedPOUCT(conf, wave));
         } else
             plan = factory::makeBAPlanner(conf);
         std::unique_ptr<beliefs::BABelief> belief;
