@@ -447,6 +447,17 @@ class BatchedBAImportanceSampling:
         _check(self.ctx.h, self.L.fba_runs_sample(self.h, ptr(self._mask(active)), C.byref(rng), ptr(idx)))
         return idx
 
+    def selectAction(self, n_simulations, depth, u, discount, rng, sims_per_wave=1, active=None):
+        """Planner::selectAction of every run (one device tree per run) -> (action[R], q[R, A], visits[R, A])"""
+        depth = np.ascontiguousarray(np.broadcast_to(np.asarray(depth, np.int32), (self.n_runs,)))
+        act = np.full(self.n_runs, -1, np.int32)
+        q = np.zeros((self.n_runs, self.sim.A), np.float64)
+        n = np.zeros((self.n_runs, self.sim.A), np.int64)
+        _check(self.ctx.h, self.L.fba_runs_plan(self.h, int(n_simulations), ptr(depth), float(u), float(discount),
+                                                int(sims_per_wave), ptr(self._mask(active)), C.byref(rng), ptr(act),
+                                                ptr(q), ptr(n)))
+        return act, q, n
+
     def download(self, run, counts=True):
         """the particles of one run, as _ParticleBelief.download"""
         return _ParticleBelief._download(self.L, self.ctx, self.storage, True, run * self.n, self.n, counts)

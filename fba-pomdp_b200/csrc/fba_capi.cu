@@ -2069,6 +2069,14 @@ struct fba_runs
     int *d_a = nullptr, *d_o = nullptr;
     unsigned char* d_active       = nullptr;
     unsigned long long* d_copies = nullptr;
+    // fba_runs_plan: one search tree per run in one hash table (allocated on first use)
+    unsigned long long table = 0; // slots; node table + r is the root of run r
+    unsigned long long* keys = nullptr;
+    int *visits = nullptr, *n_sel = nullptr, *n_done = nullptr;
+    double* q_sum = nullptr;
+    long long path_cells = 0;
+    int *path_node = nullptr, *path_action = nullptr, *d_depth = nullptr, *d_overflow = nullptr;
+    double* path_reward = nullptr;
 };
 
 extern "C" void fba_runs_destroy(fba_runs* r)
@@ -2081,6 +2089,9 @@ extern "C" void fba_runs_destroy(fba_runs* r)
     }
     cudaFree(r->tile), cudaFree(r->pairs), cudaFree(r->totals), cudaFree(r->scal), cudaFree(r->picked);
     cudaFree(r->d_a), cudaFree(r->d_o), cudaFree(r->d_active), cudaFree(r->d_copies);
+    cudaFree(r->keys), cudaFree(r->visits), cudaFree(r->n_sel), cudaFree(r->n_done), cudaFree(r->q_sum);
+    cudaFree(r->path_node), cudaFree(r->path_action), cudaFree(r->path_reward), cudaFree(r->d_depth);
+    cudaFree(r->d_overflow);
     fba_belief_destroy(r->b);
     delete r;
 }
@@ -2287,6 +2298,138 @@ extern "C" int fba_runs_sample(fba_runs* r, const uint8_t* active, fba_rng* rng,
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     for (int k = 0; k < r->R; ++k)
         if (!active || active[k]) index[k] = tmp[k];
+    return FBA_OK;
+}
+
+extern "C" int fba_runs_plan(fba_runs* r, int64_t n_sims, const int32_t* depth, double u, double discount,
+                             int32_t sims_per_wave, const uint8_t* active, fba_rng* rng, int32_t* action,
+                             double* q_out, int64_t* visits_out)
+{
+    if (!r || !rng || !depth || !action) return FBA_ERR_INVALID;
+    fba_belief* b     = r->b;
+    fba_ctx* ctx      = b->ctx;
+    DevModel const& D = b->m->dev;
+    REQUIRE(ctx, rng->mode == FBA_RNG_PHILOX, "runs: PHILOX mode only");
+    REQUIRE(ctx, n_sims >= 1 && sims_per_wave >= 1, "runs_plan: n_simulations and sims_per_wave must be >= 1");
+    REQUIRE(ctx, discount > 0 && discount <= 1 && u >= 0, "runs_plan: discount in (0, 1], u >= 0");
+    int max_depth = 1;
+    for (int k = 0; k < r->R; ++k)
+    {
+        if (active && !active[k]) continue;
+        REQUIRE(ctx, depth[k] >= 0 && depth[k] <= 4096, "runs_plan: depth must be in [0, 4096]");
+        max_depth = std::max(max_depth, (int)depth[k]);
+    }
+    CU(ctx, cudaSetDevice(ctx->device));
+    size_t const A = (size_t)D.A;
+    // one node per simulation per run, load factor <= 1/2
+    unsigned long long table = 1024;
+    while (table < 2ull * (unsigned long long)r->R * (unsigned long long)n_sims) table <<= 1;
+    REQUIRE(ctx, table <= (1ull << 31), "runs_plan: n_runs x n_simulations exceeds 2^30 tree nodes");
+    if (table > r->table)
+    {
+        cudaFree(r->keys), cudaFree(r->visits), cudaFree(r->n_sel), cudaFree(r->n_done), cudaFree(r->q_sum);
+        r->keys = nullptr, r->visits = r->n_sel = r->n_done = nullptr, r->q_sum = nullptr;
+        r->table = 0;
+        size_t const nodes = (size_t)table + (size_t)r->R;
+        cudaError_t e = cudaMalloc(&r->keys, (size_t)table * sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaMalloc(&r->visits, nodes * sizeof(int));
+        if (e == cudaSuccess) e = cudaMalloc(&r->n_sel, nodes * A * sizeof(int));
+        if (e == cudaSuccess) e = cudaMalloc(&r->n_done, nodes * A * sizeof(int));
+        if (e == cudaSuccess) e = cudaMalloc(&r->q_sum, nodes * A * sizeof(double));
+        if (e != cudaSuccess)
+        {
+            cudaFree(r->keys), cudaFree(r->visits), cudaFree(r->n_sel), cudaFree(r->n_done), cudaFree(r->q_sum);
+            r->keys = nullptr, r->visits = r->n_sel = r->n_done = nullptr, r->q_sum = nullptr;
+            ctx->err = std::string("runs_plan: tree tables: ") + cudaGetErrorString(e);
+            return FBA_ERR_CUDA;
+        }
+        r->table = table;
+    }
+    table = r->table;
+    long long const W     = std::min<long long>(sims_per_wave, n_sims);
+    long long const cells = (long long)r->R * W * max_depth;
+    if (cells > r->path_cells)
+    {
+        cudaFree(r->path_node), cudaFree(r->path_action), cudaFree(r->path_reward);
+        r->path_node = r->path_action = nullptr, r->path_reward = nullptr;
+        r->path_cells = 0;
+        CU(ctx, cudaMalloc(&r->path_node, (size_t)cells * sizeof(int)));
+        CU(ctx, cudaMalloc(&r->path_action, (size_t)cells * sizeof(int)));
+        CU(ctx, cudaMalloc(&r->path_reward, (size_t)cells * sizeof(double)));
+        r->path_cells = cells;
+    }
+    if (!r->d_depth) CU(ctx, cudaMalloc(&r->d_depth, (size_t)r->R * sizeof(int)));
+    if (!r->d_overflow) CU(ctx, cudaMalloc(&r->d_overflow, sizeof(int)));
+    size_t const nodes = (size_t)table + (size_t)r->R;
+    CU(ctx, cudaMemsetAsync(r->keys, 0xFF, (size_t)table * sizeof(unsigned long long), ctx->stream));
+    CU(ctx, cudaMemsetAsync(r->visits, 0, nodes * sizeof(int), ctx->stream));
+    CU(ctx, cudaMemsetAsync(r->n_sel, 0, nodes * A * sizeof(int), ctx->stream));
+    CU(ctx, cudaMemsetAsync(r->n_done, 0, nodes * A * sizeof(int), ctx->stream));
+    CU(ctx, cudaMemsetAsync(r->q_sum, 0, nodes * A * sizeof(double), ctx->stream));
+    CU(ctx, cudaMemsetAsync(r->d_overflow, 0, sizeof(int), ctx->stream));
+    CU(ctx, cudaMemcpyAsync(r->d_depth, depth, (size_t)r->R * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    RunsArgs RA = runs_args(r);
+    int rc      = runs_stage_active(r, active, RA);
+    if (rc) return rc;
+    // the cdf of each run's (uniform) weights, as fba_tree_search's native_normalize on a stand-alone belief
+    LAUNCH(ctx, (k_runs_step<false, false, 3>), r->R, kThreads, D, RA, RngArgs{});
+
+    TreeArgs T{};
+    T.keys = r->keys, T.visits = r->visits, T.n_sel = r->n_sel, T.n_done = r->n_done, T.q_sum = r->q_sum;
+    T.mask = (unsigned int)(table - 1), T.root = (int)table;
+    T.counts = b->counts[b->cur], T.stride = b->stride, T.sid = b->sid[b->cur], T.state = b->state[b->cur];
+    T.cdf = b->aux, T.N = b->N;
+    T.depth = 0, T.u = u, T.discount = discount;
+    T.path_node = r->path_node, T.path_action = r->path_action, T.path_reward = r->path_reward;
+    T.overflow = r->d_overflow;
+    T.R = r->R, T.w = (int)W, T.run_n = r->n, T.n_sims = n_sims;
+    T.depth_r = r->d_depth, T.active = RA.active;
+    T.n_wave  = (long long)r->R * W;
+    RngArgs ra{};
+    ra.seed   = rng->seed;
+    ra.offset = rng->offset++;
+    int tpb = kThreads;
+    while (tpb > 32 && (T.n_wave + tpb - 1) / tpb < 2ll * ctx->sm_count) tpb >>= 1;
+    int const grid = blocks_for(T.n_wave, tpb);
+    for (long long first = 0; first < n_sims; first += W)
+    {
+        T.first_sim = first;
+        if (D.sampled)
+        {
+            if (b->m->long_rows) LAUNCH(ctx, (k_pomcp_wave<false, true, true>), grid, tpb, D, T, ra);
+            else
+                LAUNCH(ctx, (k_pomcp_wave<false, false, true>), grid, tpb, D, T, ra);
+        } else
+        {
+            if (b->m->long_rows) LAUNCH(ctx, (k_pomcp_wave<false, true, false>), grid, tpb, D, T, ra);
+            else
+                LAUNCH(ctx, (k_pomcp_wave<false, false, false>), grid, tpb, D, T, ra);
+        }
+    }
+    std::vector<int> nd((size_t)r->R * A);
+    std::vector<double> qs((size_t)r->R * A);
+    CU(ctx, cudaMemcpyAsync(nd.data(), r->n_done + (size_t)table * A, nd.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(qs.data(), r->q_sum + (size_t)table * A, qs.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    unsigned long long const pick_offset = rng->offset++;
+    for (int k = 0; k < r->R; ++k)
+    {
+        if (active && !active[k]) continue;
+        PhiloxRng g(rng->seed + (unsigned long long)k, 0, pick_offset);
+        double best = -1.7976931348623157e308;
+        int pick = 0, ties = 0;
+        for (int a = 0; a < D.A; ++a)
+        {
+            int const n    = nd[(size_t)k * A + a];
+            double const v = n > 0 ? qs[(size_t)k * A + a] / (double)n : 0.0;
+            if (q_out) q_out[(size_t)k * A + a] = v;
+            if (visits_out) visits_out[(size_t)k * A + a] = n;
+            if (v > best) best = v, pick = a, ties = 1;
+            else if (v == best && draw_k(g, (uint32_t)++ties) == 0)
+                pick = a;
+        }
+        action[k] = pick;
+    }
     return FBA_OK;
 }
 

@@ -959,7 +959,7 @@ __global__ void __launch_bounds__(kThreads)
 // particles seeded with seed + r draws: a batched run is bit-identical to that belief
 // (tests/test_cuda_runs.py).
 //   MODE 0: updateEstimation (update + resample); 1: resetDomainStateDistribution (resample + start
-//   states); 2: sample (one particle index per run)
+//   states); 2: sample (one particle index per run); 3: normalise only (cdf for fba_runs_plan)
 // ------------------------------------------------------------------------------------------------
 struct RunsArgs
 {
@@ -1041,6 +1041,7 @@ __global__ void __launch_bounds__(kThreads)
         scale_and_scan_body(t, w, n, tile, total, cdf, sh_d);
         __syncthreads();
     }
+    if (MODE == 3) return; // normalise only: the cdf a planner's root sampling reads
     if (MODE == 2)
     { // WeightedFilter::sample on the native cdf (k_pick_native, multinomial, one draw)
         if (threadIdx.x == 0)
@@ -1314,6 +1315,14 @@ struct TreeArgs
     int* path_action; // [depth][wave]
     double* path_reward;
     int* overflow;    // set when the table was full (the simulation then ends in a rollout)
+    // many runs at once (fba_runs_plan): R > 0. Thread t serves run t / w, its simulation
+    // first_sim + t % w; run r owns particles [r run_n, (r+1) run_n), its root is node root + r, it
+    // draws from Philox streams keyed seed + r — with w = 1 exactly what fba_tree_search(wave = 1)
+    // does on a stand-alone belief seeded seed + r.
+    int R, w;
+    long long run_n, n_sims;
+    const int* depth_r;          // [R] search depth per run (episodes are at different steps)
+    const unsigned char* active; // [R] or NULL
 };
 
 __device__ __forceinline__ unsigned int tree_hash(unsigned long long k)
@@ -1354,34 +1363,57 @@ __global__ void __launch_bounds__(kThreads)
 {
     long long const t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T.n_wave) return;
-    auto g = RngOf<false>::make(ra, T.first_sim + t);
+    long long sim = T.first_sim + t, p0 = 0, np = T.N;
+    int root = T.root, depth = T.depth;
+    if (T.R > 0)
+    {
+        int const r = (int)(t / T.w);
+        sim         = T.first_sim + t % T.w;
+        if (sim >= T.n_sims || (T.active && !T.active[r])) return;
+        ra.seed += (unsigned long long)r;
+        p0 = (long long)r * T.run_n, np = T.run_n;
+        root += r;
+        if (T.depth_r) depth = T.depth_r[r];
+    }
+    auto g = RngOf<false>::make(ra, sim);
     // root particle: Belief::sample()
     long long p;
     if (T.cdf)
     {
-        double const thr = draw_u(g) * T.cdf[T.N - 1];
-        long long lo = 0, hi = T.N - 1;
+        const double* cdf = T.cdf + p0;
+        double const thr  = draw_u(g) * cdf[np - 1];
+        long long lo = 0, hi = np - 1;
         while (lo < hi)
         {
             long long const mid = (lo + hi) >> 1;
-            if (T.cdf[mid] > thr) hi = mid;
+            if (cdf[mid] > thr) hi = mid;
             else
                 lo = mid + 1;
         }
-        p = lo;
+        p = p0 + lo;
     } else
-        p = draw_k(g, (uint32_t)T.N);
+        p = p0 + draw_k(g, (uint32_t)np);
     float* c         = const_cast<float*>(T.counts) + p * T.stride; // KeepCounts: never written
     const Node* base = DELTA ? M.nodes : M.nodes + (long long)T.sid[p] * M.A * M.J;
     const float* tb  = DELTA ? T.base + (long long)T.sid[p] * T.base_stride : nullptr;
     int s    = T.state[p];
-    int node = T.root, len = 0, d = T.depth;
-    double leaf = 0.0;
+    int node = root, len = 0, d = depth;
+    // ONE loop over simulated steps for both phases (in the tree: UCB action, path record, child
+    // lookup; below the new leaf: random action, discounted return — RBAPOUCT::rollout), so that
+    // the lanes of a warp, which are at different depths and phases of different simulations, still
+    // run the expensive part — BAPOMDP::step — together instead of serialising on divergent code.
+    bool in_tree = true;
+    double leaf = 0.0, disc = 1.0;
     while (d > 0)
     {
-        int const a = tree_ucb(T, node, M.A, g);
-        atomicAdd(&T.visits[node], 1);
-        atomicAdd(&T.n_sel[(long long)node * M.A + a], 1);
+        int a;
+        if (in_tree)
+        {
+            a = tree_ucb(T, node, M.A, g);
+            atomicAdd(&T.visits[node], 1);
+            atomicAdd(&T.n_sel[(long long)node * M.A + a], 1);
+        } else
+            a = random_action(M, g);
         int o, s2;
         if (DELTA)
             s2 = hyper_step_delta<STEP_KEEP, SAMPLED>(M, base + (long long)a * M.J, tb, reinterpret_cast<int*>(c), 0, s,
@@ -1393,62 +1425,50 @@ __global__ void __launch_bounds__(kThreads)
                                                                           nullptr);
         }
         bool terminal;
-        double const rew                      = domain_reward(M, s, a, s2, terminal);
-        T.path_node[len * T.n_wave + t]   = node;
-        T.path_action[len * T.n_wave + t] = a;
-        T.path_reward[len * T.n_wave + t] = rew;
-        ++len;
+        double const rew = domain_reward(M, s, a, s2, terminal);
+        if (in_tree)
+        {
+            T.path_node[len * T.n_wave + t]   = node;
+            T.path_action[len * T.n_wave + t] = a;
+            T.path_reward[len * T.n_wave + t] = rew;
+            ++len;
+        } else
+        { // Return::add / Discount::increment (Return.cpp:6-9, Discount.cpp:8-11)
+            leaf = __dadd_rn(leaf, __dmul_rn(rew, disc));
+            disc = __dmul_rn(disc, T.discount);
+        }
         s = s2;
         --d;
         if (terminal) break; // delayed return 0 (RBAPOUCT.cpp:252)
-        // the child for (node, a, o): find it, or create it by claiming a slot
-        unsigned long long const key =
-            ((unsigned long long)(node + 1) << 32) | (unsigned long long)((long long)a * M.O + o);
-        unsigned int h = tree_hash(key) & T.mask;
-        int child = -1;
-        bool created = false;
-        for (unsigned int probe = 0; probe <= T.mask; ++probe, h = (h + 1) & T.mask)
-        {
-            unsigned long long const seen = atomicCAS(&T.keys[h], ~0ull, key);
-            if (seen == ~0ull)
+        if (in_tree)
+        { // the child for (node, a, o): find it, or create it by claiming a slot
+            unsigned long long const key =
+                ((unsigned long long)(node + 1) << 32) | (unsigned long long)((long long)a * M.O + o);
+            unsigned int h = tree_hash(key) & T.mask;
+            int child = -1;
+            bool created = false;
+            for (unsigned int probe = 0; probe <= T.mask; ++probe, h = (h + 1) & T.mask)
             {
-                child   = (int)h;
-                created = true;
-                break;
-            }
-            if (seen == key)
-            {
-                child = (int)h;
-                break;
-            }
-        }
-        if (child < 0) *T.overflow = 1;
-        if (created || child < 0)
-        { // new leaf: evaluate by a random-policy rollout (RBAPOUCT.cpp:258-266, 295-323)
-            double disc = 1.0;
-            bool term   = false;
-            while (d > 0 && !term)
-            {
-                int const ra_ = random_action(M, g);
-                int o2, s3;
-                if (DELTA)
-                    s3 = hyper_step_delta<STEP_KEEP, SAMPLED>(M, base + (long long)ra_ * M.J, tb,
-                                                              reinterpret_cast<int*>(c), 0, s, g, o2, nullptr, nullptr);
-                else
+                unsigned long long const seen = atomicCAS(&T.keys[h], ~0ull, key);
+                if (seen == ~0ull)
                 {
-                    Feat x3;
-                    s3 = hyper_step<STEP_KEEP, decltype(g), false, LONG, SAMPLED>(M, base + (long long)ra_ * M.J, c, s,
-                                                                                  g, o2, x3, nullptr);
+                    child   = (int)h;
+                    created = true;
+                    break;
                 }
-                double const r2 = domain_reward(M, s, ra_, s3, term);
-                leaf            = __dadd_rn(leaf, __dmul_rn(r2, disc));
-                disc            = __dmul_rn(disc, T.discount);
-                s               = s3;
-                --d;
+                if (seen == key)
+                {
+                    child = (int)h;
+                    break;
+                }
             }
-            break;
+            if (child < 0) *T.overflow = 1;
+            // a new leaf is evaluated by a random-policy rollout (RBAPOUCT.cpp:258-266, 295-323):
+            // the remaining steps of this loop
+            if (created || child < 0) in_tree = false;
+            else
+                node = child;
         }
-        node = child;
     }
     // back up: ret = r + discount * delayed (RBAPOUCT.cpp:271-272)
     double ret = leaf;

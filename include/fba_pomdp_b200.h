@@ -31,7 +31,7 @@ extern "C" {
 
 #define FBA_MAX_FEATURES 16
 /* bumped whenever a struct below changes layout; compare with fba_abi_version() after loading */
-#define FBA_ABI_VERSION 7
+#define FBA_ABI_VERSION 8
 
 typedef struct fba_ctx fba_ctx;
 typedef struct fba_model fba_model;
@@ -339,6 +339,17 @@ int fba_runs_reset_domain_states(fba_runs* runs, const uint8_t* active, fba_rng*
 /* Belief::sample of every (active) run: index[r] = particle index inside run r (storage index
  * r * particles_per_run + index[r]); entries of inactive runs are left untouched */
 int fba_runs_sample(fba_runs* runs, const uint8_t* active, fba_rng* rng, int64_t* index);
+/* Planner::selectAction of every (active) run at once (RBAPOUCT.cpp:67-153, as fba_tree_search): each
+ * run has its own search tree on the device; a wave advances sims_per_wave simulations of EVERY run,
+ * so with sims_per_wave = 1 each run's search is the reference's sequential algorithm while the GPU
+ * is kept busy by the number of runs. depth: n_runs entries (episodes may be at different steps).
+ * action: n_runs entries; q / visits (n_runs x n_actions, may be NULL): the roots' mean returns and
+ * visit counts. With sims_per_wave = 1, run r is bit-identical to fba_tree_search(wave = 1) on a
+ * stand-alone belief with an fba_rng seeded seed + r. Call after init / update_estimation / reset
+ * (uniform weights). */
+int fba_runs_plan(fba_runs* runs, int64_t n_simulations, const int32_t* depth, double u, double discount,
+                  int32_t sims_per_wave, const uint8_t* active, fba_rng* rng, int32_t* action, double* q,
+                  int64_t* visits);
 /* count blocks copied by the in-place resamples of all runs since creation */
 int64_t fba_runs_copies(fba_runs* runs);
 

@@ -153,3 +153,65 @@ def test_runs_argument_checks(ctx):
     with pytest.raises(fba.FbaError):
         fba.BatchedBAImportanceSampling(0, 64)
     sim.close()
+
+
+@pytest.mark.parametrize("name,R,n", [("tiger", 6, 512), ("sysadmin3", 4, 300), ("gridworld3", 3, 256)])
+def test_batched_planning_equals_stand_alone_search(ctx, name, R, n):
+    """fba_runs_plan with one simulation per run per wave: every run's POMCP search is the sequential
+    algorithm, and bit-identical — chosen action, root values, visit counts — to fba_tree_search
+    (wave = 1) on a stand-alone belief seeded seed + r that went through the same calls."""
+    import fba_pomdp_b200 as fba
+    g = G.load(name)
+    used, psid, pc, freq = _protos(g)
+    sim = fba.BAPOMDP(ctx, g.desc, g.t_par[used], g.o_par[used])
+    seed, sims, u, disc = 77, 200, 5.0, 0.95
+    a0, o0 = int(g.a[0]), int(g.o[0])
+    depth = np.array([2 + (r % 3) for r in range(R)], np.int32)
+    batch = fba.BatchedBAImportanceSampling(R, n)
+    rng = fba.Rng.philox(seed)
+    batch.initiate_sampled(sim, psid, pc, freq, rng, stride=pc.shape[1])
+    batch.updateEstimation(np.full(R, a0), np.full(R, o0), rng)
+    act, q, visits = batch.selectAction(sims, depth, u, disc, rng, sims_per_wave=1)
+    act2, q2, visits2 = batch.selectAction(sims, depth, u, disc, rng, sims_per_wave=1)   # a second search: fresh trees
+    batch.free()
+    assert np.all(visits.sum(1) == sims) and np.all(visits2.sum(1) == sims)
+    for r in range(R):
+        b = fba.BAImportanceSampling(n)
+        rr = fba.Rng.philox(seed + r)
+        b.initiate_sampled(sim, psid, pc, freq, rr, stride=pc.shape[1])
+        b.updateEstimation(a0, o0, rr)
+        tree = fba.SearchTree(sim, sims, 8)
+        for want_a, want_q, want_v in ((act, q, visits), (act2, q2, visits2)):
+            a, qq, vv = tree.selectAction(b, sims, int(depth[r]), u, disc, 1, rr)
+            np.testing.assert_array_equal(vv, want_v[r], err_msg="%s run %d visits" % (name, r))
+            np.testing.assert_array_equal(qq, want_q[r], err_msg="%s run %d q" % (name, r))
+            assert a == want_a[r]
+        tree.free()
+        b.free()
+    sim.close()
+
+
+def test_batched_planning_wide_waves_and_masks(ctx):
+    """Several simulations per run per wave (atomics inside a run's tree) and an active mask: visit
+    counts add up, parked runs are untouched, informed runs pick the right door."""
+    import fba_pomdp_b200 as fba
+    g = G.load("tiger")
+    R, n = 32, 256
+    sim = fba.BAPOMDP(ctx, g.desc, g.t_par, g.o_par)
+    batch = fba.BatchedBAImportanceSampling(R, n)
+    rng = fba.Rng.philox(3)
+    batch.initiate_sampled(sim, [0], g["is/init_counts"][:1], None, rng)
+    # put the tiger behind door r % 2 in every particle of run r
+    st = np.repeat(np.arange(R) % 2, n).astype(np.int32)
+    assert batch.L.fba_belief_upload(batch.storage, 0, R * n, fba.capi.ptr(st), None, None, None) == 0
+    active = np.ones(R, np.uint8)
+    active[5] = 0
+    act, q, visits = batch.selectAction(512, 3, 20.0, 0.95, rng, sims_per_wave=16, active=active)
+    assert act[5] == -1 and visits[5].sum() == 0
+    for r in range(R):
+        if r == 5:
+            continue
+        assert visits[r].sum() == 512
+        assert act[r] == r % 2 and q[r, r % 2] == 10.0 and q[r, 1 - r % 2] == -100.0
+    batch.free()
+    sim.close()

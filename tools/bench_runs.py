@@ -26,6 +26,10 @@ def main():
     ap.add_argument("--particles", type=int, default=1024)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--runs", type=int, nargs="*", default=[1, 16, 148, 1024, 4096, 16384])
+    ap.add_argument("--plan-runs", type=int, nargs="*", default=[1, 148, 1024, 4096])
+    ap.add_argument("--sims", type=int, default=1024)
+    ap.add_argument("--depth", type=int, default=20)
+    ap.add_argument("--sims-per-wave", type=int, nargs="*", default=[1, 4])
     args = ap.parse_args()
     g = G.load(args.name)
     script = [(int(a), int(o)) for a, o, f in zip(g.a, g.o, g.flags) if not (f & 1)]
@@ -78,6 +82,25 @@ def main():
                                 speedup_vs_one_after_the_other=single_us * 1e-6 * R / dt))
         batch.free()
     out["reference_cpu_ms_per_run_update"] = 1.57 if (args.name == "tiger" and n == 1024) else None
+
+    # planning: Planner::selectAction of every run at once, one device tree per run (fba_runs_plan)
+    out["planning"] = dict(simulations=args.sims, depth=args.depth, rows=[])
+    for R in args.plan_runs:
+        batch = fba.BatchedBAImportanceSampling(R, n)
+        rng = fba.Rng.philox(3)
+        batch.initiate_sampled(sim, [0], proto, None, rng)
+        for w in args.sims_per_wave:
+            batch.selectAction(min(args.sims, 64), args.depth, 5.0, 0.95, rng, sims_per_wave=w)   # warm-up, allocations
+            ctx.synchronize()
+            t0 = time.perf_counter()
+            reps = 3
+            for _ in range(reps):
+                act, q, visits = batch.selectAction(args.sims, args.depth, 5.0, 0.95, rng, sims_per_wave=w)
+            dt = (time.perf_counter() - t0) / reps
+            out["planning"]["rows"].append(dict(runs=R, sims_per_wave=w, s_per_batched_selectAction=dt,
+                                                ms_per_run_selectAction=dt / R * 1e3,
+                                                simulations_per_s=R * args.sims / dt))
+        batch.free()
     print(json.dumps(out))
 
 
