@@ -1908,8 +1908,8 @@ struct fba_tree
     int max_depth  = 0;
     unsigned table = 0; // slots (power of two); node `table` is the root
     unsigned long long* keys = nullptr;
-    int *visits = nullptr, *n_sel = nullptr, *n_done = nullptr;
-    double* q_sum = nullptr;
+    int* visits    = nullptr;
+    TreeStat* stat = nullptr;
     long long path_cap = 0; // simulations per wave the path scratch holds
     int *path_node = nullptr, *path_action = nullptr;
     double* path_reward = nullptr;
@@ -1921,7 +1921,7 @@ extern "C" void fba_tree_destroy(fba_tree* t)
     if (!t) return;
     cudaSetDevice(t->ctx->device);
     cudaStreamSynchronize(t->ctx->stream);
-    cudaFree(t->keys), cudaFree(t->visits), cudaFree(t->n_sel), cudaFree(t->n_done), cudaFree(t->q_sum);
+    cudaFree(t->keys), cudaFree(t->visits), cudaFree(t->stat);
     cudaFree(t->path_node), cudaFree(t->path_action), cudaFree(t->path_reward), cudaFree(t->d_overflow);
     delete t;
 }
@@ -1944,9 +1944,7 @@ extern "C" int fba_tree_create(fba_ctx* ctx, fba_model* m, int64_t max_simulatio
     size_t const nodes = (size_t)t->table + 1, A = (size_t)m->dev.A;
     cudaError_t e = cudaMalloc(&t->keys, (size_t)t->table * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(&t->visits, nodes * sizeof(int));
-    if (e == cudaSuccess) e = cudaMalloc(&t->n_sel, nodes * A * sizeof(int));
-    if (e == cudaSuccess) e = cudaMalloc(&t->n_done, nodes * A * sizeof(int));
-    if (e == cudaSuccess) e = cudaMalloc(&t->q_sum, nodes * A * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&t->stat, nodes * A * sizeof(TreeStat));
     if (e == cudaSuccess) e = cudaMalloc(&t->d_overflow, sizeof(int));
     if (e != cudaSuccess)
     {
@@ -1987,15 +1985,13 @@ extern "C" int fba_tree_search(fba_tree* t, fba_belief* b, int64_t n_sims, int32
     size_t const nodes = (size_t)t->table + 1, A = (size_t)D.A;
     CU(ctx, cudaMemsetAsync(t->keys, 0xFF, (size_t)t->table * sizeof(unsigned long long), ctx->stream));
     CU(ctx, cudaMemsetAsync(t->visits, 0, nodes * sizeof(int), ctx->stream));
-    CU(ctx, cudaMemsetAsync(t->n_sel, 0, nodes * A * sizeof(int), ctx->stream));
-    CU(ctx, cudaMemsetAsync(t->n_done, 0, nodes * A * sizeof(int), ctx->stream));
-    CU(ctx, cudaMemsetAsync(t->q_sum, 0, nodes * A * sizeof(double), ctx->stream));
+    CU(ctx, cudaMemsetAsync(t->stat, 0, nodes * A * sizeof(TreeStat), ctx->stream));
     CU(ctx, cudaMemsetAsync(t->d_overflow, 0, sizeof(int), ctx->stream));
     if (b->weighted && !b->cdf_valid)
         if ((rc = native_normalize(b, false, 1.0))) return rc;
 
     TreeArgs T{};
-    T.keys = t->keys, T.visits = t->visits, T.n_sel = t->n_sel, T.n_done = t->n_done, T.q_sum = t->q_sum;
+    T.keys = t->keys, T.visits = t->visits, T.stat = t->stat;
     T.mask = t->table - 1, T.root = (int)t->table;
     T.counts = b->counts[b->cur], T.stride = b->stride, T.sid = b->sid[b->cur], T.state = b->state[b->cur];
     T.cdf = b->weighted ? b->aux : nullptr, T.N = b->N;
@@ -2031,10 +2027,9 @@ extern "C" int fba_tree_search(fba_tree* t, fba_belief* b, int64_t n_sims, int32
                 LAUNCH(ctx, (k_pomcp_wave<false, false, false>), grid, tpb, D, T, ra);
         }
     }
-    std::vector<int> nd(A);
-    std::vector<double> qs(A);
-    CU(ctx, cudaMemcpyAsync(nd.data(), t->n_done + (size_t)t->table * A, A * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaMemcpyAsync(qs.data(), t->q_sum + (size_t)t->table * A, A * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<TreeStat> root(A);
+    CU(ctx, cudaMemcpyAsync(root.data(), t->stat + (size_t)t->table * A, A * sizeof(TreeStat), cudaMemcpyDeviceToHost,
+                            ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     // the final choice: best mean return, no exploration term, random among ties (RBAPOUCT.cpp:204)
     PhiloxRng g(rng->seed, 0, rng->offset++);
@@ -2042,9 +2037,9 @@ extern "C" int fba_tree_search(fba_tree* t, fba_belief* b, int64_t n_sims, int32
     int pick = 0, ties = 0;
     for (int a = 0; a < D.A; ++a)
     {
-        double const v = nd[a] > 0 ? qs[a] / (double)nd[a] : 0.0;
+        double const v = root[a].n_done > 0 ? root[a].q_sum / (double)root[a].n_done : 0.0;
         if (q_out) q_out[a] = v;
-        if (visits_out) visits_out[a] = nd[a];
+        if (visits_out) visits_out[a] = root[a].n_done;
         if (v > best) best = v, pick = a, ties = 1;
         else if (v == best && draw_k(g, (uint32_t)++ties) == 0)
             pick = a;
@@ -2072,8 +2067,8 @@ struct fba_runs
     // fba_runs_plan: one search tree per run in one hash table (allocated on first use)
     unsigned long long table = 0; // slots; node table + r is the root of run r
     unsigned long long* keys = nullptr;
-    int *visits = nullptr, *n_sel = nullptr, *n_done = nullptr;
-    double* q_sum = nullptr;
+    int* visits    = nullptr;
+    TreeStat* stat = nullptr;
     long long path_cells = 0;
     int *path_node = nullptr, *path_action = nullptr, *d_depth = nullptr, *d_overflow = nullptr;
     double* path_reward = nullptr;
@@ -2089,7 +2084,7 @@ extern "C" void fba_runs_destroy(fba_runs* r)
     }
     cudaFree(r->tile), cudaFree(r->pairs), cudaFree(r->totals), cudaFree(r->scal), cudaFree(r->picked);
     cudaFree(r->d_a), cudaFree(r->d_o), cudaFree(r->d_active), cudaFree(r->d_copies);
-    cudaFree(r->keys), cudaFree(r->visits), cudaFree(r->n_sel), cudaFree(r->n_done), cudaFree(r->q_sum);
+    cudaFree(r->keys), cudaFree(r->visits), cudaFree(r->stat);
     cudaFree(r->path_node), cudaFree(r->path_action), cudaFree(r->path_reward), cudaFree(r->d_depth);
     cudaFree(r->d_overflow);
     fba_belief_destroy(r->b);
@@ -2327,19 +2322,17 @@ extern "C" int fba_runs_plan(fba_runs* r, int64_t n_sims, const int32_t* depth, 
     REQUIRE(ctx, table <= (1ull << 31), "runs_plan: n_runs x n_simulations exceeds 2^30 tree nodes");
     if (table > r->table)
     {
-        cudaFree(r->keys), cudaFree(r->visits), cudaFree(r->n_sel), cudaFree(r->n_done), cudaFree(r->q_sum);
-        r->keys = nullptr, r->visits = r->n_sel = r->n_done = nullptr, r->q_sum = nullptr;
+        cudaFree(r->keys), cudaFree(r->visits), cudaFree(r->stat);
+        r->keys = nullptr, r->visits = nullptr, r->stat = nullptr;
         r->table = 0;
         size_t const nodes = (size_t)table + (size_t)r->R;
         cudaError_t e = cudaMalloc(&r->keys, (size_t)table * sizeof(unsigned long long));
         if (e == cudaSuccess) e = cudaMalloc(&r->visits, nodes * sizeof(int));
-        if (e == cudaSuccess) e = cudaMalloc(&r->n_sel, nodes * A * sizeof(int));
-        if (e == cudaSuccess) e = cudaMalloc(&r->n_done, nodes * A * sizeof(int));
-        if (e == cudaSuccess) e = cudaMalloc(&r->q_sum, nodes * A * sizeof(double));
+        if (e == cudaSuccess) e = cudaMalloc(&r->stat, nodes * A * sizeof(TreeStat));
         if (e != cudaSuccess)
         {
-            cudaFree(r->keys), cudaFree(r->visits), cudaFree(r->n_sel), cudaFree(r->n_done), cudaFree(r->q_sum);
-            r->keys = nullptr, r->visits = r->n_sel = r->n_done = nullptr, r->q_sum = nullptr;
+            cudaFree(r->keys), cudaFree(r->visits), cudaFree(r->stat);
+            r->keys = nullptr, r->visits = nullptr, r->stat = nullptr;
             ctx->err = std::string("runs_plan: tree tables: ") + cudaGetErrorString(e);
             return FBA_ERR_CUDA;
         }
@@ -2363,9 +2356,7 @@ extern "C" int fba_runs_plan(fba_runs* r, int64_t n_sims, const int32_t* depth, 
     size_t const nodes = (size_t)table + (size_t)r->R;
     CU(ctx, cudaMemsetAsync(r->keys, 0xFF, (size_t)table * sizeof(unsigned long long), ctx->stream));
     CU(ctx, cudaMemsetAsync(r->visits, 0, nodes * sizeof(int), ctx->stream));
-    CU(ctx, cudaMemsetAsync(r->n_sel, 0, nodes * A * sizeof(int), ctx->stream));
-    CU(ctx, cudaMemsetAsync(r->n_done, 0, nodes * A * sizeof(int), ctx->stream));
-    CU(ctx, cudaMemsetAsync(r->q_sum, 0, nodes * A * sizeof(double), ctx->stream));
+    CU(ctx, cudaMemsetAsync(r->stat, 0, nodes * A * sizeof(TreeStat), ctx->stream));
     CU(ctx, cudaMemsetAsync(r->d_overflow, 0, sizeof(int), ctx->stream));
     CU(ctx, cudaMemcpyAsync(r->d_depth, depth, (size_t)r->R * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     RunsArgs RA = runs_args(r);
@@ -2375,7 +2366,7 @@ extern "C" int fba_runs_plan(fba_runs* r, int64_t n_sims, const int32_t* depth, 
     LAUNCH(ctx, (k_runs_step<false, false, 3>), r->R, kThreads, D, RA, RngArgs{});
 
     TreeArgs T{};
-    T.keys = r->keys, T.visits = r->visits, T.n_sel = r->n_sel, T.n_done = r->n_done, T.q_sum = r->q_sum;
+    T.keys = r->keys, T.visits = r->visits, T.stat = r->stat;
     T.mask = (unsigned int)(table - 1), T.root = (int)table;
     T.counts = b->counts[b->cur], T.stride = b->stride, T.sid = b->sid[b->cur], T.state = b->state[b->cur];
     T.cdf = b->aux, T.N = b->N;
@@ -2406,10 +2397,9 @@ extern "C" int fba_runs_plan(fba_runs* r, int64_t n_sims, const int32_t* depth, 
                 LAUNCH(ctx, (k_pomcp_wave<false, false, false>), grid, tpb, D, T, ra);
         }
     }
-    std::vector<int> nd((size_t)r->R * A);
-    std::vector<double> qs((size_t)r->R * A);
-    CU(ctx, cudaMemcpyAsync(nd.data(), r->n_done + (size_t)table * A, nd.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaMemcpyAsync(qs.data(), r->q_sum + (size_t)table * A, qs.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<TreeStat> roots((size_t)r->R * A);
+    CU(ctx, cudaMemcpyAsync(roots.data(), r->stat + (size_t)table * A, roots.size() * sizeof(TreeStat),
+                            cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     unsigned long long const pick_offset = rng->offset++;
     for (int k = 0; k < r->R; ++k)
@@ -2420,8 +2410,8 @@ extern "C" int fba_runs_plan(fba_runs* r, int64_t n_sims, const int32_t* depth, 
         int pick = 0, ties = 0;
         for (int a = 0; a < D.A; ++a)
         {
-            int const n    = nd[(size_t)k * A + a];
-            double const v = n > 0 ? qs[(size_t)k * A + a] / (double)n : 0.0;
+            int const n    = roots[(size_t)k * A + a].n_done;
+            double const v = n > 0 ? roots[(size_t)k * A + a].q_sum / (double)n : 0.0;
             if (q_out) q_out[(size_t)k * A + a] = v;
             if (visits_out) visits_out[(size_t)k * A + a] = n;
             if (v > best) best = v, pick = a, ties = 1;

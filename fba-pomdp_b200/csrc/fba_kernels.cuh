@@ -1290,13 +1290,18 @@ __global__ void __launch_bounds__(kThreads)
 // (KeepCounts), only the domain state evolves. The tree differs from the sequential planner's only
 // in the order in which simulations see each other's statistics.
 // ------------------------------------------------------------------------------------------------
+struct __align__(16) TreeStat // one 16-byte load per action in the UCB scan
+{
+    int n_sel;    // times the action was chosen (incl. simulations in flight)
+    int n_done;   // returns backed up
+    double q_sum; // sum of those returns
+};
+
 struct TreeArgs
 {
     unsigned long long* keys; // [table]: (parent + 1) << 32 | (action * O + observation); EMPTY = ~0
     int* visits;              // [table + 1] selections through the node; node `table` is the root
-    int* n_sel;               // [table + 1][A] times the action was chosen (incl. simulations in flight)
-    int* n_done;              // [table + 1][A] returns backed up
-    double* q_sum;            // [table + 1][A] sum of those returns
+    TreeStat* stat;           // [table + 1][A] per (node, action)
     unsigned int mask;        // table - 1 (table is a power of two)
     int root;                 // = table
     // belief
@@ -1343,16 +1348,31 @@ __device__ __forceinline__ int tree_ucb(const TreeArgs& T, int node, int A, R& g
     double const lg = log1p((double)T.visits[node]);
     double best     = -1.7976931348623157e308;
     int pick = 0, ties = 0;
-    for (int a = 0; a < A; ++a)
+    const int4* row = reinterpret_cast<const int4*>(T.stat + (long long)node * A);
+    // four actions' statistics per round trip. Plain (L1-cached) loads: a line may be a little stale
+    // inside one wave, which only makes concurrent simulations slightly more independent; across waves
+    // (kernel launches) L1 starts clean, so a sequential search (one simulation per wave) is exact
+    for (int a0 = 0; a0 < A; a0 += 4)
     {
-        int const ns = T.n_sel[(long long)node * A + a], nd = T.n_done[(long long)node * A + a];
-        double v;
-        if (ns == 0) v = 1.7976931348623157e308;
-        else
-            v = ((nd > 0) ? T.q_sum[(long long)node * A + a] / (double)nd : 0.0) + T.u * sqrt(lg / (double)ns);
-        if (v > best) best = v, pick = a, ties = 1;
-        else if (v == best && draw_k(g, (uint32_t)++ties) == 0)
-            pick = a;
+        int4 raw[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (a0 + k < A) raw[k] = row[a0 + k];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+        {
+            int const a = a0 + k;
+            if (a >= A) break;
+            int const ns = raw[k].x, nd = raw[k].y;
+            double const qs = __hiloint2double(raw[k].w, raw[k].z);
+            double v;
+            if (ns == 0) v = 1.7976931348623157e308;
+            else
+                v = ((nd > 0) ? qs / (double)nd : 0.0) + T.u * sqrt(lg / (double)ns);
+            if (v > best) best = v, pick = a, ties = 1;
+            else if (v == best && draw_k(g, (uint32_t)++ties) == 0)
+                pick = a;
+        }
     }
     return pick;
 }
@@ -1411,7 +1431,7 @@ __global__ void __launch_bounds__(kThreads)
         {
             a = tree_ucb(T, node, M.A, g);
             atomicAdd(&T.visits[node], 1);
-            atomicAdd(&T.n_sel[(long long)node * M.A + a], 1);
+            atomicAdd(&T.stat[(long long)node * M.A + a].n_sel, 1);
         } else
             a = random_action(M, g);
         int o, s2;
@@ -1476,8 +1496,8 @@ __global__ void __launch_bounds__(kThreads)
     {
         ret = T.path_reward[k * T.n_wave + t] + T.discount * ret;
         long long const cell = (long long)T.path_node[k * T.n_wave + t] * M.A + T.path_action[k * T.n_wave + t];
-        atomicAdd(&T.q_sum[cell], ret);
-        atomicAdd(&T.n_done[cell], 1);
+        atomicAdd(&T.stat[cell].q_sum, ret);
+        atomicAdd(&T.stat[cell].n_done, 1);
     }
 }
 
