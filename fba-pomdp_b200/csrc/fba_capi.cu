@@ -7,6 +7,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "fba_kernels.cuh"
@@ -56,7 +57,8 @@ struct fba_model
     std::vector<uint32_t> t_par, o_par; // host structure table
     std::vector<int> sizes;
     std::vector<Node> h_nodes;
-    std::map<std::string, int> index;
+    std::unordered_map<std::string, int> index; // parent masks (bytes) -> structure id
+    std::string key_buf;                        // reused by add_structures
     Node* d_nodes = nullptr;
     int* d_sizes  = nullptr;
     std::vector<void*> owned; // device copies of the descriptor's tables
@@ -102,6 +104,10 @@ struct fba_belief
     long long* d_quota = nullptr; // device-side offspring quota (fba_belief_shard_resample_async)
     int2* tile_pairs = nullptr;
     bool inplace_last = false; // the last shard resample ran in place (import goes to dead slots)
+    // pinned host mirrors of state / structure ids for the sequential part of reinvigoration
+    int *h_sid = nullptr, *h_state = nullptr;
+    BreedJob* d_jobs   = nullptr; // grow-only
+    long long jobs_cap = 0;
     // rejection sampling wave buffers
     long long wave_cap = 0;
     int *att_src = nullptr, *att_state = nullptr, *att_accept = nullptr, *att_pos = nullptr,
@@ -616,7 +622,8 @@ static int add_structures(fba_model* m, int32_t n, const uint32_t* t_par, const 
     {
         const uint32_t* tp = t_par + (size_t)k * nT;
         const uint32_t* op = o_par + (size_t)k * nO;
-        std::string key((const char*)tp, nT * sizeof(uint32_t));
+        std::string& key = m->key_buf;
+        key.assign((const char*)tp, nT * sizeof(uint32_t));
         key.append((const char*)op, nO * sizeof(uint32_t));
         auto it = m->index.find(key);
         int id;
@@ -765,6 +772,8 @@ extern "C" void fba_belief_destroy(fba_belief* b)
         cudaFree(b->sid[k]);
     }
     cudaFree(b->base);
+    cudaFreeHost(b->h_sid), cudaFreeHost(b->h_state);
+    cudaFree(b->d_jobs);
     cudaFree(b->w), cudaFree(b->aux), cudaFree(b->tile), cudaFree(b->scal), cudaFree(b->anc);
     cudaFree(b->att_src), cudaFree(b->att_state), cudaFree(b->att_accept), cudaFree(b->att_pos);
     cudaFree(b->roll_p), cudaFree(b->roll_s), cudaFree(b->roll_d), cudaFree(b->roll_r);
@@ -1593,11 +1602,18 @@ extern "C" int fba_belief_reinvigorate(fba_belief* b, fba_belief* fc, int64_t am
     REQUIRE(ctx, !D.tabular && b->delta_cap == 0, "reinvigorate: factored models only");
     CU(ctx, cudaSetDevice(ctx->device));
 
-    // host mirrors of the small per-particle arrays the sequential part reads
-    std::vector<int> sid((size_t)b->N), st((size_t)b->N), fc_sid((size_t)fc->N);
-    CU(ctx, cudaMemcpyAsync(sid.data(), b->sid[b->cur], b->N * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaMemcpyAsync(st.data(), b->state[b->cur], b->N * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaMemcpyAsync(fc_sid.data(), fc->sid[fc->cur], fc->N * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    // host mirrors of the small per-particle arrays the sequential part reads (pinned: one DMA each)
+    for (fba_belief* x : {b, fc})
+    {
+        if (!x->h_sid) CU(ctx, cudaMallocHost(&x->h_sid, (size_t)x->N * sizeof(int)));
+        if (!x->h_state) CU(ctx, cudaMallocHost(&x->h_state, (size_t)x->N * sizeof(int)));
+    }
+    int* const sid    = b->h_sid;
+    int* const st     = b->h_state;
+    int* const fc_sid = fc->h_sid;
+    CU(ctx, cudaMemcpyAsync(sid, b->sid[b->cur], b->N * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(st, b->state[b->cur], b->N * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(fc_sid, fc->sid[fc->cur], fc->N * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
 
     int const nT = D.A * D.FS, nO = D.A * D.FO;
@@ -1679,12 +1695,20 @@ extern "C" int fba_belief_reinvigorate(fba_belief* b, fba_belief* fc, int64_t am
 
     std::vector<BreedJob> jobs;
     for (auto const& kv : last_writer) jobs.push_back(kv.second);
-    DevTmp<BreedJob> d_jobs;
-    CU(ctx, cudaMalloc(&d_jobs, jobs.size() * sizeof(BreedJob)));
+    if ((long long)jobs.size() > b->jobs_cap)
+    {
+        cudaFree(b->d_jobs);
+        b->d_jobs   = nullptr;
+        b->jobs_cap = 0;
+        long long const cap = (long long)jobs.size() * 2 + 64;
+        CU(ctx, cudaMalloc(&b->d_jobs, (size_t)cap * sizeof(BreedJob)));
+        b->jobs_cap = cap;
+    }
+    BreedJob* const d_jobs = b->d_jobs;
     CU(ctx, cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(BreedJob), cudaMemcpyHostToDevice, ctx->stream));
     // structures may have been added: the node table pointer is unchanged, its contents were copied
     LAUNCH(ctx, k_breed, (int)jobs.size(), kThreads, D, fc->counts[fc->cur], fc->stride, b->counts[b->cur],
-           b->stride, b->state[b->cur], b->sid[b->cur], (const BreedJob*)d_jobs);
+           b->stride, b->state[b->cur], b->sid[b->cur], d_jobs);
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return FBA_OK;
 }
