@@ -18,7 +18,7 @@ MUT_FACTORED_TIGER, MUT_COLLISION_AVOIDANCE, MUT_SYSADMIN, MUT_GRIDWORLD = range
 RNG_REPLAY, RNG_PHILOX = 0, 1
 
 # every symbol include/fba_pomdp_b200.h declares (tests check the library exports all of them)
-ABI_VERSION = 8  # must equal FBA_ABI_VERSION in include/fba_pomdp_b200.h
+ABI_VERSION = 9  # must equal FBA_ABI_VERSION in include/fba_pomdp_b200.h
 
 SYMBOLS = [
     "fba_abi_version", "fba_ctx_create", "fba_ctx_destroy", "fba_last_error", "fba_ctx_stream", "fba_ctx_synchronize",
@@ -40,7 +40,7 @@ SYMBOLS = [
     "fba_belief_scalars_ptr",
     "fba_tree_create", "fba_tree_destroy", "fba_tree_search",
     "fba_runs_create", "fba_runs_destroy", "fba_runs_belief", "fba_runs_init_sampled",
-    "fba_runs_update_estimation", "fba_runs_reset_domain_states", "fba_runs_sample", "fba_runs_copies", "fba_runs_plan",
+    "fba_runs_update_estimation", "fba_runs_reset_domain_states", "fba_runs_sample", "fba_runs_copies", "fba_runs_plan", "fba_runs_init",
 ]
 
 
@@ -173,6 +173,7 @@ def lib():
             "fba_runs_reset_domain_states": (C.c_int, [vp, vp, vp]),
             "fba_runs_sample": (C.c_int, [vp, vp, vp, vp]),
             "fba_runs_copies": (i64, [vp]),
+            "fba_runs_init": (C.c_int, [vp, i32, vp, vp, vp, vp]),
             "fba_runs_plan": (C.c_int, [vp, i64, vp, dbl, dbl, i32, vp, vp, vp, vp, vp]),
         }
         for name, (res, args) in sig.items():

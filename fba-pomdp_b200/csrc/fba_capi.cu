@@ -2201,6 +2201,20 @@ extern "C" int fba_runs_init_sampled(fba_runs* r, int32_t n_protos, const int32_
     return FBA_OK;
 }
 
+extern "C" int fba_runs_init(fba_runs* r, int32_t n_protos, const int32_t* proto_struct_id, const float* proto_counts,
+                             const int32_t* particle_proto, const int32_t* particle_state)
+{
+    if (!r) return FBA_ERR_INVALID;
+    fba_belief* b = r->b;
+    fba_ctx* ctx  = b->ctx;
+    int const rc  = fba_belief_init(b, n_protos, proto_struct_id, proto_counts, particle_proto, particle_state);
+    if (rc) return rc;
+    LAUNCH(ctx, k_fill, blocks_for(b->N), kThreads, b->w, b->N, 1.0 / (double)r->n); // uniform PER RUN
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    b->suffix_valid = b->cdf_valid = false;
+    return FBA_OK;
+}
+
 static RunsArgs runs_args(fba_runs* r)
 {
     fba_belief* b = r->b;

@@ -64,7 +64,12 @@ class CudaSimulator
 public:
     // delta_capacity: -1 = choose automatically (base+delta storage for tabular models whose dense
     // count block exceeds 256 KB, with room for 2048 increments = 1024 updates per particle)
-    CudaSimulator(BAPOMDP const& sim, int device = 0, int max_structures = 4096, int delta_capacity = -1) :
+    // start_samples > 0: the domain's start-state distribution is estimated from that many draws of the
+    // reference's own domain (BAPOMDP::sampleDomainState) and uploaded as a categorical, so that start
+    // states can be drawn ON the device (fba_runs_reset_domain_states for thousands of runs); 0: start
+    // states always come from the host domain (the single-belief adapters)
+    CudaSimulator(BAPOMDP const& sim, int device = 0, int max_structures = 4096, int delta_capacity = -1,
+                  int start_samples = 0) :
             _sim(sim)
     {
         if (fba_abi_version() != FBA_ABI_VERSION)
@@ -103,6 +108,20 @@ public:
         d.dirichlet_sampling = sampledDirichlets() ? 1 : 0;
         d.action_draw = FBA_ACT_UNIFORM_INT; // rollouts only; all reference domains draw uniformly
         d.start_kind  = FBA_START_CONST;     // unused: start states come from the host domain
+        if (start_samples > 0)
+        {
+            _start_freq.assign((size_t)d.S, 0.0f);
+            for (int i = 0; i < start_samples; ++i)
+            {
+                auto st = sim.sampleDomainState();
+                _start_freq[(size_t)st->index()] += 1.0f;
+                sim.releaseDomainState(st);
+            }
+            d.start_kind   = FBA_START_CATEGORICAL;
+            d.start_ip[0]  = d.S;
+            d.start_values = _start_freq.data();
+            d.start_total  = (double)start_samples;
+        }
 
         check(_ctx, fba_model_create(_ctx, &d, max_structures, &_model), "fba_model_create");
         _steps.reset(new ::bayes_adaptive::factored::BABNModel::Indexing_Steps(
@@ -232,6 +251,7 @@ private:
     ::bayes_adaptive::factored::FBAPOMDP const* _fbapomdp = nullptr;
     fba_ctx* _ctx     = nullptr;
     fba_model* _model = nullptr;
+    std::vector<float> _start_freq;
     mutable fba_tree* _tree     = nullptr;
     mutable int64_t _tree_sims  = 0;
     mutable int _tree_depth     = 0;

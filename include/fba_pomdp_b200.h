@@ -31,7 +31,7 @@ extern "C" {
 
 #define FBA_MAX_FEATURES 16
 /* bumped whenever a struct below changes layout; compare with fba_abi_version() after loading */
-#define FBA_ABI_VERSION 8
+#define FBA_ABI_VERSION 9
 
 typedef struct fba_ctx fba_ctx;
 typedef struct fba_model fba_model;
@@ -329,6 +329,10 @@ fba_belief* fba_runs_belief(fba_runs* runs);
 /* Belief::initiate of every run: as fba_belief_init_sampled */
 int fba_runs_init_sampled(fba_runs* runs, int32_t n_protos, const int32_t* proto_struct_id,
                           const float* proto_counts, const double* proto_probs, fba_rng* rng);
+/* the same from explicit host particles, as fba_belief_init: particle_proto / particle_state have
+ * n_runs * particles_per_run entries (run-major) */
+int fba_runs_init(fba_runs* runs, int32_t n_protos, const int32_t* proto_struct_id, const float* proto_counts,
+                  const int32_t* particle_proto, const int32_t* particle_state);
 /* Belief::updateEstimation of every run (BAImportanceSampling.cpp:74-88): action / observation are
  * n_runs entries on the host; likelihood (n_runs doubles, may be NULL) receives each run's step
  * likelihood */

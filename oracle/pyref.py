@@ -198,6 +198,16 @@ class Ref:
             raise RuntimeError("reference/adapter: " + self.L.ref_error(self.h).decode())
         return out
 
+    def batched_episodes(self, n, runs, sims, episodes, sims_per_wave=1):
+        """fba_b200::runBatchedExperiment -> (returns[episodes, runs], seconds)"""
+        self.L.ref_batched_episodes.restype = C.c_double
+        self.L.ref_batched_episodes.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        out = np.zeros((episodes, runs), np.float64)
+        dt = self.L.ref_batched_episodes(self.h, n, runs, sims, episodes, sims_per_wave, _p(out))
+        if dt < 0:
+            raise RuntimeError("reference/adapter: " + self.L.ref_error(self.h).decode())
+        return out, dt
+
     def plan_seconds(self, kind, n, planner, sims, reps=3):
         """Seconds per Planner::selectAction with `sims` simulations (empty history)."""
         v = self.L.ref_plan_seconds(self.h, kind, n, planner.encode(), sims, reps)

@@ -61,6 +61,7 @@
 // the C++ host adapters of this repo (the drop-in beliefs), compiled against the reference here
 #define FBA_B200_PRIVATE_ACCESS
 #include "CudaBeliefs.hpp"
+#include "CudaExperiment.hpp"
 #include "CudaPlanner.hpp"
 #include "environment/Discount.hpp"
 #include "environment/Horizon.hpp"
@@ -702,6 +703,38 @@ int ref_adapter_episodes(void* hv, int kind, long n, char const* planner, int si
     return 0;
 }
 
+
+// fba_b200::runBatchedExperiment (host/CudaExperiment.hpp): `runs` runs of `episodes` episodes in
+// lockstep on the GPU, n particles and `sims` simulations each. returns: episodes x runs, row-major.
+// Result: seconds of wall time, < 0 on error.
+double ref_batched_episodes(void* hv, long n, int runs, int sims, int episodes, int sims_per_wave, double* returns)
+{
+    auto h = static_cast<Handle*>(hv);
+    try
+    {
+        auto conf                                = h->conf;
+        conf.belief_conf.particle_amount         = n;
+        conf.planner_conf.mcts_simulation_amount = sims;
+        conf.planner_conf.mcts_max_depth         = conf.horizon;
+        conf.num_episodes                        = episodes;
+        auto t0  = std::chrono::steady_clock::now();
+        auto res = fba_b200::runBatchedExperiment(*h->sim, conf, runs, sims_per_wave);
+        double const dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        for (int e = 0; e < episodes; ++e)
+            for (int r = 0; r < runs; ++r) returns[(size_t)e * runs + r] = res[e][r];
+        return dt;
+    } catch (std::string const& e)
+    {
+        h->err = e;
+    } catch (char const* e)
+    {
+        h->err = e;
+    } catch (std::exception const& e)
+    {
+        h->err = e.what();
+    }
+    return -1.0;
+}
 
 // seconds per Planner::selectAction (empty history) with `sims` simulations, belief kind as in
 // ref_adapter_episodes, planner "po-uct" (the reference's RBAPOUCT) or "cuda-po-uct[:wave]".

@@ -81,3 +81,32 @@ def test_reference_episode_loop_with_cuda_planner(domain, kw, n, episodes, sims,
         # random (collision returns are -950 a piece, so allow two standard errors)
         se_r = np.sqrt(rand.var(ddof=1) / len(rand) + ours.var(ddof=1) / len(ours))
         assert ours.mean() > rand.mean() - 2.0 * se_r, (ours.mean(), ref.mean(), rand.mean())
+
+
+BATCH_CASES = [
+    # domain, kwargs, particles, runs, episodes, simulations
+    ("episodic-tiger", dict(), 256, 48, 3, 128),
+    ("episodic-factored-tiger", dict(size=3, factored=True), 128, 32, 2, 96),
+    ("linear-sysadmin", dict(size=3, factored=True), 64, 32, 2, 96),
+    ("gridworld", dict(size=3), 32, 24, 2, 96),
+]
+
+
+@pytest.mark.parametrize("domain,kw,n,runs,episodes,sims", BATCH_CASES)
+def test_many_runs_in_lockstep_match_the_reference_experiment(domain, kw, n, runs, episodes, sims):
+    """fba_b200::runBatchedExperiment (host/CudaExperiment.hpp): experiment::bapomdp::run with its runs
+    advanced TOGETHER — all beliefs in one fba_runs object, all planners device trees, one plan and
+    one update call per time step for every run — against the reference's own experiment loop run
+    once per run (BAImportanceSampling + RBAPOUCT on the CPU): per-episode mean returns over the runs
+    agree within 4 standard errors."""
+    horizon = 8
+    r = pyref.Ref(domain, horizon=horizon, seed="31", **kw)
+    try:
+        ours, _ = r.batched_episodes(n, runs, sims, episodes)
+        ref = np.stack([r.adapter_episodes(0, n, "po-uct", sims, episodes) for _ in range(runs)], axis=1)
+    finally:
+        r.close()
+    assert ours.shape == ref.shape == (episodes, runs) and np.all(np.isfinite(ours))
+    for e in range(episodes):
+        se = np.sqrt(ref[e].var(ddof=1) / runs + ours[e].var(ddof=1) / runs) + 1e-9
+        assert abs(ref[e].mean() - ours[e].mean()) <= 4.0 * se + 1e-6, (e, ref[e].mean(), ours[e].mean(), se)
