@@ -71,35 +71,40 @@ inline std::vector<std::vector<double>> runBatchedExperiment(
     rng.seed    = seed;
     rng.offset  = 0;
 
-    // Belief::initiate of every run: a pool of samples of the reference's own prior (host); distinct
-    // (structure, count block) pairs become prototypes, and every particle of every run draws its
-    // prototype with the pool's frequencies and its domain start state on the device
+    // Belief::initiate of every run = runs x n samples of the reference's own prior (host); distinct
+    // (structure, count block) pairs are uploaded once as prototypes (as CudaParticleBelief::initiate).
+    // A prior that keeps returning the same particle (the tabular priors, the factored ones without a
+    // structure prior) is recognised after the first 4096 samples: then every particle IS that
+    // prototype and only its domain start state is drawn, on the device.
     size_t const total = (size_t)runs * n;
-    size_t const pool  = std::min<size_t>(total, std::max<size_t>(4096, 4 * n));
-    std::vector<int32_t> proto_sid;
-    std::vector<double> proto_freq;
+    size_t const probe = std::min<size_t>(total, 4096);
+    std::vector<int32_t> proto(total), proto_sid;
     std::vector<std::vector<float>> proto_blocks;
     std::map<std::string, int32_t> known;
     std::vector<float> block;
-    size_t stride = 0;
-    for (size_t i = 0; i < pool; ++i)
-    {
-        auto p            = static_cast<BAState const*>(bapomdp.sampleStartState());
-        int32_t const sid = cuda.describe(p, &block);
-        std::string key((char const*)&sid, sizeof(sid));
-        key.append((char const*)block.data(), block.size() * sizeof(float));
-        auto it = known.find(key);
-        if (it == known.end())
+    size_t stride = 0, sampled = 0;
+    auto sample_prior = [&](size_t upto) {
+        for (; sampled < upto; ++sampled)
         {
-            it = known.emplace(std::move(key), (int32_t)proto_sid.size()).first;
-            proto_sid.push_back(sid);
-            proto_freq.push_back(0.0);
-            proto_blocks.push_back(block);
-            stride = std::max(stride, block.size());
+            auto p            = static_cast<BAState const*>(bapomdp.sampleStartState());
+            int32_t const sid = cuda.describe(p, &block);
+            std::string key((char const*)&sid, sizeof(sid));
+            key.append((char const*)block.data(), block.size() * sizeof(float));
+            auto it = known.find(key);
+            if (it == known.end())
+            {
+                it = known.emplace(std::move(key), (int32_t)proto_sid.size()).first;
+                proto_sid.push_back(sid);
+                proto_blocks.push_back(block);
+                stride = std::max(stride, block.size());
+            }
+            proto[sampled] = it->second;
+            bapomdp.releaseState(p);
         }
-        proto_freq[(size_t)it->second] += 1.0;
-        bapomdp.releaseState(p);
-    }
+    };
+    sample_prior(probe);
+    bool const deterministic_prior = proto_sid.size() == 1;
+    if (!deterministic_prior) sample_prior(total);
     struct RunsGuard
     {
         fba_runs* r = nullptr;
@@ -111,10 +116,17 @@ inline std::vector<std::vector<double>> runBatchedExperiment(
         std::vector<float> flat(proto_sid.size() * stride, 0.0f);
         for (size_t k = 0; k < proto_sid.size(); ++k)
             std::copy(proto_blocks[k].begin(), proto_blocks[k].end(), flat.begin() + k * stride);
-        check(ctx,
-              fba_runs_init_sampled(batch.r, (int32_t)proto_sid.size(), proto_sid.data(), flat.data(),
-                                    proto_freq.data(), &rng),
-              "fba_runs_init_sampled");
+        if (deterministic_prior)
+            check(ctx, fba_runs_init_sampled(batch.r, 1, proto_sid.data(), flat.data(), nullptr, &rng),
+                  "fba_runs_init_sampled");
+        else
+        { // domain states are redrawn at the first episode start anyway (resetDomainStateDistribution)
+            std::vector<int32_t> state(total, 0);
+            check(ctx,
+                  fba_runs_init(batch.r, (int32_t)proto_sid.size(), proto_sid.data(), flat.data(), proto.data(),
+                                state.data()),
+                  "fba_runs_init");
+        }
     }
 
     // one environment object serves every run (Environment::step is const and keeps the state outside)

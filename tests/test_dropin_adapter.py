@@ -89,6 +89,8 @@ BATCH_CASES = [
     ("episodic-factored-tiger", dict(size=3, factored=True), 128, 32, 2, 96),
     ("linear-sysadmin", dict(size=3, factored=True), 64, 32, 2, 96),
     ("gridworld", dict(size=3), 32, 24, 2, 96),
+    # a prior that samples a structure per particle: the driver takes the exact per-particle path
+    ("episodic-factored-tiger", dict(size=3, factored=True, structure_prior="match-uniform"), 64, 24, 2, 64),
 ]
 
 
