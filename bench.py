@@ -237,6 +237,50 @@ def rollouts_leg(ctx, fba, args, torch):
     return out
 
 
+def many_runs_leg(ctx, fba, args):
+    """BASELINE.json configs[0] (episodic tiger, 1024 particles) the way the reference's real workloads
+    use it — thousands of independent runs — batched on one GPU (fba_runs_*): belief updates of all
+    runs in one launch (one CTA per run, bit-identical to separate beliefs), and POMCP planning with one
+    device tree per run, each run searching sequentially (one simulation per run per wave)."""
+    import golden_util as G
+    g = G.load("tiger")
+    sim = fba.BAPOMDP(ctx, g.desc, g.t_par, g.o_par)
+    R, n, sims = 4096, 1024, 256
+    script = [(int(a), int(o)) for a, o, f in zip(g.a, g.o, g.flags) if not (f & 1)]
+    batch = fba.BatchedBAImportanceSampling(R, n)
+    rng = fba.Rng.philox(args.seed + 2)
+    batch.initiate_sampled(sim, [0], g["is/init_counts"][:1], None, rng)
+    rs = np.random.RandomState(1)
+    steps = 30
+    picks = rs.randint(0, len(script), (steps + 3, R))
+    acts = np.array([[script[k][0] for k in row] for row in picks], np.int32)
+    obs = np.array([[script[k][1] for k in row] for row in picks], np.int32)
+    for t in range(3):
+        batch.updateEstimation(acts[t], obs[t], rng, want_likelihood=False)
+    ctx.synchronize()
+    l0 = ctx.launches
+    t0 = time.perf_counter()
+    for t in range(3, 3 + steps):
+        batch.updateEstimation(acts[t], obs[t], rng)     # host (a, o) in, likelihoods out, every step
+    dt = (time.perf_counter() - t0) / steps
+    launches = (ctx.launches - l0) / steps
+    batch.selectAction(sims, g.horizon, 5.0, g.discount, rng)   # allocations (tree tables) + warm-up
+    ctx.synchronize()
+    t0 = time.perf_counter()
+    act, q, visits = batch.selectAction(sims, g.horizon, 5.0, g.discount, rng, sims_per_wave=1)
+    dp = time.perf_counter() - t0
+    assert int(visits.sum()) == R * sims
+    batch.free()
+    sim.close()
+    return {"workload": "episodic tiger, %d particles per run, %d runs batched on one GPU" % (n, R),
+            "belief_updates": {"ms_per_batched_update_e2e": dt * 1e3, "run_updates_per_s": R / dt,
+                               "particle_updates_per_s": R * n / dt, "launches_per_update": launches,
+                               "reference_cpu_ms_per_run_update": 1.57},
+            "planning": {"simulations_per_run": sims, "depth": int(g.horizon), "sims_per_run_per_wave": 1,
+                         "s_per_batched_selectAction": dp, "simulations_per_s": R * sims / dp,
+                         "reference_cpu_simulations_per_s": 3.6e5}}
+
+
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -484,6 +528,7 @@ def main_ours(args):
     sim.close()
     if world == 1 and not args.no_rollouts:
         line["rollouts"] = rollouts_leg(ctx, fba, args, torch)
+        line["many_runs"] = many_runs_leg(ctx, fba, args)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n = args.ref_particles
