@@ -524,6 +524,14 @@ extern "C" int fba_model_create(fba_ctx* ctx, const fba_model_desc* d, int32_t m
     for (int f = D.FS - 2; f >= 0; --f) D.step_s[f] = D.step_s[f + 1] * D.feat_s[f + 1];
     D.step_o[D.FO - 1] = 1;
     for (int f = D.FO - 2; f >= 0; --f) D.step_o[f] = D.step_o[f + 1] * D.feat_o[f + 1];
+    auto log2_exact = [](int v) {
+        int k = 0;
+        while ((1 << k) < v) ++k;
+        return ((1 << k) == v) ? k : -1;
+    };
+    D.pow2_s = D.pow2_o = 1;
+    for (int f = 0; f < D.FS; ++f) D.pow2_s &= log2_exact(D.feat_s[f]) >= 0, D.shift_s[f] = std::max(0, log2_exact(D.step_s[f]));
+    for (int f = 0; f < D.FO; ++f) D.pow2_o &= log2_exact(D.feat_o[f]) >= 0, D.shift_o[f] = std::max(0, log2_exact(D.step_o[f]));
     D.tabular = d->tabular, D.domain = d->domain, D.action_draw = d->action_draw;
     D.sampled = d->dirichlet_sampling != 0;
     for (int f = 0; f < D.FS; ++f) m->long_rows |= D.feat_s[f] > 4;

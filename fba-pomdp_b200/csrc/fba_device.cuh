@@ -25,6 +25,9 @@ struct DevModel
     int S, A, O, FS, FO, J; // J = FS + FO nodes per action
     int feat_s[FBA_MAX_FEATURES], feat_o[FBA_MAX_FEATURES];
     int step_s[FBA_MAX_FEATURES], step_o[FBA_MAX_FEATURES]; // indexing::stepSize (index.cpp:18-49)
+    // every feature size a power of two (sysadmin, factored tiger): indices decode with shifts
+    int pow2_s, pow2_o;
+    int shift_s[FBA_MAX_FEATURES], shift_o[FBA_MAX_FEATURES]; // log2(step)
     int tabular, domain, action_draw;
     int sampled; // 1: --dirichlet_sampling_method regular (sample the multinomial from the Dirichlet)
     int dom_ip[32];
@@ -406,12 +409,23 @@ struct Feat
 };
 
 // indexing::projectUsingStepSize (index.cpp:98-119): feature 0 most significant
-__device__ __forceinline__ Feat decode(int v, const int* step, int n)
+__device__ __forceinline__ Feat decode(int v, const int* step, int n, int pow2 = 0, const int* shift = nullptr)
 {
     Feat x{0ull, 0ull};
     if (n == 1)
     {
         x.lo = (unsigned long long)(unsigned)v;
+        return x;
+    }
+    if (pow2)
+    { // no integer divisions: feature f = bits [shift_f, shift_{f-1}) of the index
+        int hi = 31;
+        for (int f = 0; f < n; ++f)
+        {
+            int const sh = shift[f];
+            x.set(f, (int)(((unsigned)v & ((2u << hi) - 1u)) >> sh), false);
+            hi = sh - 1;
+        }
         return x;
     }
     for (int f = 0; f < n; ++f)
@@ -551,7 +565,7 @@ __device__ __forceinline__ int hyper_step(const DevModel& M, const Node* __restr
                                           int* rec)
 {
     bool const single_s = (M.FS == 1), single_o = (M.FO == 1);
-    Feat const x = decode(s, M.step_s, M.FS);
+    Feat const x = decode(s, M.step_s, M.FS, M.pow2_s, M.shift_s);
 
     // sampleStateIndex (BAFlatModel.cpp:83-91 / BABNModel.cpp:292-307): one draw per state
     // feature in feature order, every node conditioned on the OLD state
@@ -620,7 +634,7 @@ __device__ __forceinline__ double obs_probability(const DevModel& M, const Node*
         Node const nd = nodes[M.FS];
         return (double)likelihood_at<SAMPLED>(counts + nd.off + (int)x.lo * M.O, M.O, o, g);
     }
-    Feat const of       = decode(o, M.step_o, M.FO);
+    Feat const of       = decode(o, M.step_o, M.FO, M.pow2_o, M.shift_o);
     bool const single_o = (M.FO == 1);
     double prob         = 1.0;
     for (int q = 0; q < M.FO; ++q)
