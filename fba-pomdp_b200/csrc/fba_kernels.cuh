@@ -1041,7 +1041,7 @@ __global__ void __launch_bounds__(kThreads)
         scale_and_scan_body(t, w, n, tile, total, cdf, sh_d);
         __syncthreads();
     }
-    if (MODE == 3) return; // normalise only: the cdf a planner's root sampling reads
+    // MODE 3: normalise only — the cdf a planner's root sampling reads
     if (MODE == 2)
     { // WeightedFilter::sample on the native cdf (k_pick_native, multinomial, one draw)
         if (threadIdx.x == 0)
@@ -1059,63 +1059,65 @@ __global__ void __launch_bounds__(kThreads)
             }
             A.picked[r] = lo;
         }
-        return;
     }
-    // resample_inplace
-    for (int t = 0; t < A.n_tiles; ++t)
+    if constexpr (MODE < 2)
     {
-        offspring_body(t, cdf, n, n, rr, noff, pairs, sh_a, sh_b);
-        __syncthreads();
-    }
-    ++rr.offset;
-    scan_tile_pairs_body(pairs, A.n_tiles, totals, nullptr, sh_a, sh_b, &cd, &ce);
-    for (long long k = threadIdx.x; k < n; k += kThreads) src_of[k] = -1;
-    __syncthreads();
-    for (int t = 0; t < A.n_tiles; ++t)
-    {
-        offspring_apply_body(t, noff, n, pairs, dead, escan, src_of, n, sh_a, sh_b);
-        __syncthreads();
-    }
-    { // k_copy_inplace, the run's own warps: the k-th extra copy fills the k-th dead slot
-        long long const n_fill = min((long long)totals[0], (long long)totals[1]);
-        if (threadIdx.x == 0 && A.copies) atomicAdd(A.copies, (unsigned long long)n_fill);
-        int const lane = threadIdx.x & 31;
-        for (long long k = threadIdx.x >> 5; k < n_fill; k += kThreads / 32)
+        // resample_inplace
+        for (int t = 0; t < A.n_tiles; ++t)
         {
-            long long i = src_of[k];
-            if (i < 0)
+            offspring_body(t, cdf, n, n, rr, noff, pairs, sh_a, sh_b);
+            __syncthreads();
+        }
+        ++rr.offset;
+        scan_tile_pairs_body(pairs, A.n_tiles, totals, nullptr, sh_a, sh_b, &cd, &ce);
+        for (long long k = threadIdx.x; k < n; k += kThreads) src_of[k] = -1;
+        __syncthreads();
+        for (int t = 0; t < A.n_tiles; ++t)
+        {
+            offspring_apply_body(t, noff, n, pairs, dead, escan, src_of, n, sh_a, sh_b);
+            __syncthreads();
+        }
+        { // k_copy_inplace, the run's own warps: the k-th extra copy fills the k-th dead slot
+            long long const n_fill = min((long long)totals[0], (long long)totals[1]);
+            if (threadIdx.x == 0 && A.copies) atomicAdd(A.copies, (unsigned long long)n_fill);
+            int const lane = threadIdx.x & 31;
+            for (long long k = threadIdx.x >> 5; k < n_fill; k += kThreads / 32)
             {
-                long long lo = 0, hi = n;
-                while (lo < hi)
+                long long i = src_of[k];
+                if (i < 0)
                 {
-                    long long const mid = (lo + hi) >> 1;
-                    if (escan[mid] > (int)k) hi = mid;
-                    else
-                        lo = mid + 1;
+                    long long lo = 0, hi = n;
+                    while (lo < hi)
+                    {
+                        long long const mid = (lo + hi) >> 1;
+                        if (escan[mid] > (int)k) hi = mid;
+                        else
+                            lo = mid + 1;
+                    }
+                    i = lo - 1;
                 }
-                i = lo - 1;
+                int const id      = sid[i];
+                long long const j = dead[k];
+                warp_copy_block(counts + i * A.stride, counts + j * A.stride, (A.struct_size[id] + 3) >> 2, lane);
+                if (lane == 0)
+                {
+                    sid[j]   = id;
+                    state[j] = state[i];
+                }
             }
-            int const id      = sid[i];
-            long long const j = dead[k];
-            warp_copy_block(counts + i * A.stride, counts + j * A.stride, (A.struct_size[id] + 3) >> 2, lane);
-            if (lane == 0)
+        }
+        double const uniform = 1.0 / (double)n;
+        for (long long i = threadIdx.x; i < n; i += kThreads) w[i] = uniform;
+        if (MODE == 1)
+        { // BABelief::resetDomainStateDistribution: fresh start states (k_reset_states)
+            __syncthreads();
+            for (long long i = threadIdx.x; i < n; i += kThreads)
             {
-                sid[j]   = id;
-                state[j] = state[i];
+                auto g   = RngOf<false>::make(rr, i);
+                state[i] = sample_start_state(M, g);
             }
         }
-    }
-    double const uniform = 1.0 / (double)n;
-    for (long long i = threadIdx.x; i < n; i += kThreads) w[i] = uniform;
-    if (MODE == 1)
-    { // BABelief::resetDomainStateDistribution: fresh start states (k_reset_states)
-        __syncthreads();
-        for (long long i = threadIdx.x; i < n; i += kThreads)
-        {
-            auto g   = RngOf<false>::make(rr, i);
-            state[i] = sample_start_state(M, g);
-        }
-    }
+    } // MODE < 2
 }
 
 // fba_runs_init: prototype + start state per particle, run r drawing like a stand-alone
