@@ -524,6 +524,26 @@ def main_ours(args):
         "full_copy": full,
     }
 
+    if world > 1 and not args.no_rollouts:
+        # POMCP leaf evaluation, root-parallel over the shards: every rank runs 2^20
+        # random-policy rollouts (depth 20) from root particles of its own shard in one launch; the
+        # returns of all ranks are all-gathered (8 bytes each). Host requests in, host returns out.
+        per_gpu, depth = 1 << 20, 20
+        b.rollouts(per_gpu * world, depth, 0.95, rng)          # warm-up (buffers, NCCL)
+        barrier()
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            ret = b.rollouts(per_gpu * world, depth, 0.95, rng)
+        barrier()
+        rt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(rt, op=dist.ReduceOp.MAX)
+        line["rollouts"] = {"workload": WORKLOADS[args.workload]["text"].split(",")[0] + ", root-parallel rollouts from "
+                                        "the sharded belief, depth %d" % depth,
+                            "rollouts_per_launch_per_gpu": per_gpu, "n_gpus": world,
+                            "rollouts_per_s_e2e": per_gpu * world * reps / float(rt.item()),
+                            "mean_return": float(ret.mean()), "unit": "rollouts/s",
+                            "note": "includes sampling the root particles, the launch, and the all-gather of the returns"}
     b.free()
     sim.close()
     if world == 1 and not args.no_rollouts:

@@ -11,4 +11,4 @@ from .capi import FbaError, Rng  # noqa: F401
 __all__ = ["capi", "Context", "BAPOMDP", "BAImportanceSampling", "BARejectionSampling", "BatchedBAImportanceSampling", "SearchTree",
            "ReinvigoratingRejectionSampling", "rollouts", "Rng", "FbaError"]
 from .sharded import ShardedBAImportanceSampling, exchange_plan, offspring_quotas  # noqa: F401,E402
-from .sharded import exchange_records  # noqa: F401,E402
+from .sharded import exchange_records, gather_ragged, split_requests  # noqa: F401,E402

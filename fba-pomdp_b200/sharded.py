@@ -69,6 +69,31 @@ def exchange_records(dist, group, plan, rank, src, record_bytes, dst=None):
     return dst
 
 
+def split_requests(n_total, world):
+    """Root-parallel split of n_total planner requests (leaf rollouts / simulations): rank g serves
+    n_total // world of them, the first n_total % world ranks one more. Identical on every rank."""
+    base, rem = divmod(int(n_total), int(world))
+    return np.array([base + (1 if g < rem else 0) for g in range(world)], np.int64)
+
+
+def gather_ragged(dist, group, local, counts, device="cpu"):
+    """All ranks' result vectors (rank g contributes counts[g] doubles) concatenated in rank order, on
+    every rank: one all-gather of fixed-size (max count) slots, 8 bytes per request (SURVEY.md §8e:
+    "results returned by all-gather, 32 KB")."""
+    import torch
+    counts = np.asarray(counts, np.int64)
+    world, slot = len(counts), int(counts.max()) if len(counts) else 0
+    mine = torch.zeros(max(slot, 1), dtype=torch.float64, device=device)
+    loc = torch.as_tensor(np.asarray(local, np.float64))
+    mine[:len(loc)] = loc.to(device)
+    if world == 1:
+        return mine[:counts[0]].cpu().numpy()
+    out = torch.empty(world * max(slot, 1), dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(out, mine, group=group)
+    out = out.cpu().numpy().reshape(world, max(slot, 1))
+    return np.concatenate([out[g, :counts[g]] for g in range(world)])
+
+
 class _RawCuda:
     """Zero-copy view of a device pointer for torch.as_tensor."""
 
@@ -232,6 +257,31 @@ class ShardedBAImportanceSampling(BAImportanceSampling):
             self._local = self._totals = self._totals_host = self._stream = self._event = self._gather_buf = self._barrier = None
             self._bufs = None
         super().free()
+
+    def rollouts(self, n_total, depth, discount, rng, gather=True):
+        """POMCP's leaf evaluation, root-parallel over the shards: the n_total
+        random-policy rollouts (RBAPOUCT::rollout, RBAPOUCT.cpp:295-323) are split evenly over the
+        ranks; each rank draws its share's root particles from ITS shard and runs them in one launch
+        on its own GPU. After a global resample every shard holds the same number of equally weighted
+        particles, so sampling inside the shard is sampling from the global belief. The only traffic
+        is the all-gather of the returns (8 bytes each). -> all n_total returns (rank order) on every
+        rank, or this rank's share if gather is False."""
+        from .beliefs import rollouts as local_rollouts
+        counts = split_requests(n_total, self.world)
+        m = int(counts[self.rank])
+        idx = np.zeros(m, np.int64)
+        st = np.zeros(m, np.int32)
+        if m:
+            _check(self.ctx.h, self.L.fba_belief_sample_batch(self.h, C.byref(rng), m, idx.ctypes.data_as(C.c_void_p)))
+            _check(self.ctx.h, self.L.fba_belief_gather_states(self.h, m, idx.ctypes.data_as(C.c_void_p),
+                                                               st.ctypes.data_as(C.c_void_p)))
+        ret = local_rollouts(self, idx, st, np.full(m, int(depth), np.int32), discount, rng) if m else np.zeros(0)
+        if not gather:
+            return ret
+        import torch
+        device = "cuda:%d" % torch.cuda.current_device() if (self.world > 1 and
+                                                               self.dist.get_backend(self.group) == "nccl") else "cpu"
+        return gather_ragged(self.dist, self.group, ret, counts, device)
 
     def updateEstimation(self, a, o, rng, step_uniform=0.5):
         """One global importance-sampling update + resample. `step_uniform` in [0,1) must be the

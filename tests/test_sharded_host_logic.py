@@ -75,7 +75,11 @@ def _worker(rank, world, port, out):
         for r in range(n_out):
             src[r * rb:(r + 1) * rb] = 16 * rank + r
         got = fba.exchange_records(dist, None, plan, rank, src, rb)
-        out.put((rank, q.tolist(), plan.tolist(), got.numpy().tolist()))
+        # root-parallel rollouts: 7 requests over 2 ranks -> 4 + 3, returns gathered in rank order
+        counts = fba.split_requests(7, world)
+        mine_ret = 100.0 * rank + np.arange(counts[rank], dtype=np.float64)
+        allret = fba.gather_ragged(dist, None, mine_ret, counts)
+        out.put((rank, q.tolist(), plan.tolist(), got.numpy().tolist(), counts.tolist(), allret.tolist()))
     finally:
         dist.destroy_process_group()
 
@@ -91,7 +95,9 @@ def test_gloo_world2_exchange():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    (_, q0, plan0, got0), (_, q1, plan1, got1) = res
+    (_, q0, plan0, got0, c0, r0), (_, q1, plan1, got1, c1, r1) = res
+    assert c0 == c1 == [4, 3]
+    assert r0 == r1 == [0.0, 1.0, 2.0, 3.0, 100.0, 101.0, 102.0]
     assert q0 == q1 == [12, 4] and plan0 == plan1 == [[0, 4], [0, 0]]
     assert got0 == []  # rank 0 is over quota: receives nothing
     assert len(got1) == 4 * 24 and got1[::24] == [0, 1, 2, 3]  # rank 1 received rank 0's 4 records
@@ -103,3 +109,11 @@ def test_python_and_library_plans_agree():
     C side against them. Here: the numpy pair is self-consistent on the edge the C code clamps."""
     q = fba.offspring_quotas([1e-300, 1.0, 1e-300], 30, 0.999)
     assert q.sum() == 30 and q[1] >= 29
+
+
+def test_split_requests_properties():
+    for n in (0, 1, 7, 4096, 4099):
+        for g in (1, 2, 3, 8):
+            c = fba.split_requests(n, g)
+            assert c.sum() == n and c.max() - c.min() <= 1 and list(c) == sorted(c, reverse=True)
+    np.testing.assert_array_equal(fba.gather_ragged(None, None, [1.5, 2.5], [2]), [1.5, 2.5])

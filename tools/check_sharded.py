@@ -1,7 +1,8 @@
 """Multi-GPU invariant check of the sharded belief (run under torchrun, one rank per GPU).
 Every slot of every shard must hold a valid particle after each update — survivors, local
 duplicates and imported records alike: its count block sums to prior + 11 * updates (sysadmin,
-FS + FO = 11), its domain state is in range, nothing was dropped. Exit code 0 = all ranks passed."""
+FS + FO = 11), its domain state is in range, nothing was dropped; root-parallel rollouts return the
+same, bounded values on every rank. Exit code 0 = all ranks passed."""
 import os
 import sys
 
@@ -48,6 +49,17 @@ def main():
         assert d["state"].min() >= 0 and d["state"].max() < sim.S
         np.testing.assert_array_equal(d["w"], np.full(n, 1.0 / n))
         moved += getattr(b, "moved_last", 0)
+    # root-parallel rollouts: 4099 requests split over the ranks, every rank gets all returns, in the
+    # same order; a sysadmin reward is (#computers up) - reboot cost, |r| <= 10 (SysAdminBAExtension.cpp:27-48)
+    ret = b.rollouts(4099, 10, 0.95, rng)
+    assert ret.shape == (4099,) and np.all(np.isfinite(ret))
+    bound = 10.0 * (1 - 0.95 ** 10) / (1 - 0.95)
+    assert ret.min() >= -bound - 1e-9 and ret.max() <= bound + 1e-9 and ret.mean() > 0, (ret.min(), ret.max(), bound)
+    chk = torch.tensor([float(ret.sum()), float(ret[0]), float(ret[-1])], device="cuda", dtype=torch.float64)
+    lo, hi = chk.clone(), chk.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    assert torch.equal(lo, hi), "ranks disagree on the gathered returns"
     dropped = b.L.fba_belief_dropped_records(b.h)
     assert dropped == 0, dropped
     tot = torch.tensor([float(n)], device="cuda")
