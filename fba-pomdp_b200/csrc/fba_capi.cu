@@ -108,6 +108,9 @@ struct fba_belief
     int *h_sid = nullptr, *h_state = nullptr;
     BreedJob* d_jobs   = nullptr; // grow-only
     long long jobs_cap = 0;
+    // in-place rejection sampling: the accepted attempts (N each) and scan scratch, allocated on first use
+    int *rs_src = nullptr, *rs_state = nullptr, *rs_rec = nullptr, *rs_flag = nullptr, *rs_pos = nullptr,
+        *rs_tiles = nullptr;
     // rejection sampling wave buffers
     long long wave_cap = 0;
     int *att_src = nullptr, *att_state = nullptr, *att_accept = nullptr, *att_pos = nullptr,
@@ -782,6 +785,7 @@ extern "C" void fba_belief_destroy(fba_belief* b)
     cudaFree(b->base);
     cudaFreeHost(b->h_sid), cudaFreeHost(b->h_state);
     cudaFree(b->d_jobs);
+    cudaFree(b->rs_src), cudaFree(b->rs_state), cudaFree(b->rs_rec), cudaFree(b->rs_flag), cudaFree(b->rs_pos), cudaFree(b->rs_tiles);
     cudaFree(b->w), cudaFree(b->aux), cudaFree(b->tile), cudaFree(b->scal), cudaFree(b->anc);
     cudaFree(b->att_src), cudaFree(b->att_state), cudaFree(b->att_accept), cudaFree(b->att_pos);
     cudaFree(b->roll_p), cudaFree(b->roll_s), cudaFree(b->roll_d), cudaFree(b->roll_r);
@@ -1475,8 +1479,23 @@ extern "C" int fba_belief_reject_sample(fba_belief* b, int32_t a, int32_t o, fba
     REQUIRE(ctx, o >= 0 && o < D.O, "observation out of range");
     CU(ctx, cudaSetDevice(ctx->device));
     int rc;
-    int const nx        = b->cur ^ 1;
-    if ((rc = ensure_next(b))) return rc;
+    // PHILOX + dense storage: accepted sources keep their slot, only repeated acceptances are copied
+    // (k_rs_*), no second buffer. REPLAY keeps the reference's attempt order in the other buffer.
+    bool const inplace = rng->mode == FBA_RNG_PHILOX && ctx->inplace_resample && b->delta_cap == 0;
+    int const nx       = b->cur ^ 1;
+    if (!inplace)
+    {
+        if ((rc = ensure_next(b))) return rc;
+    } else if (!b->rs_src)
+    {
+        size_t const n = (size_t)b->N;
+        CU(ctx, cudaMalloc(&b->rs_src, n * sizeof(int)));
+        CU(ctx, cudaMalloc(&b->rs_state, n * sizeof(int)));
+        CU(ctx, cudaMalloc(&b->rs_rec, n * (size_t)D.J * sizeof(int)));
+        CU(ctx, cudaMalloc(&b->rs_flag, n * sizeof(int)));
+        CU(ctx, cudaMalloc(&b->rs_pos, n * sizeof(int)));
+        CU(ctx, cudaMalloc(&b->rs_tiles, ((n + kFlagTile - 1) / kFlagTile + 1) * sizeof(int)));
+    }
     long long accepted = 0, attempts = 0;
     long long const cap = 1ll << 22;
     double rate         = 0.5; // running estimate of the acceptance rate
@@ -1536,10 +1555,14 @@ extern "C" int fba_belief_reject_sample(fba_belief* b, int32_t a, int32_t o, fba
             LAUNCH(ctx, k_flag_scan_tiles, 1, kThreads, b->att_tiles, n_ft, b->d_total);
             LAUNCH(ctx, k_flag_scan_apply, n_ft, kThreads, b->att_accept, wave, b->att_tiles, b->att_pos);
         }
-        LAUNCH(ctx, k_rs_commit, stream_grid(ctx, wave), kThreads, b->counts[b->cur], b->counts[nx], b->stride,
-               b->sid[b->cur], b->sid[nx], b->state[nx], b->m->d_sizes, b->N, D.J, wave, b->att_src,
-               b->att_state, b->att_accept, b->att_pos, b->att_rec, accepted, b->delta_cap > 0 ? 1 : 0,
-               b->delta_cap, ctx->d_flag);
+        if (inplace)
+            LAUNCH(ctx, k_rs_collect, blocks_for(wave), kThreads, b->N, D.J, wave, b->att_src, b->att_state,
+                   b->att_accept, b->att_pos, b->att_rec, accepted, b->rs_src, b->rs_state, b->rs_rec);
+        else
+            LAUNCH(ctx, k_rs_commit, stream_grid(ctx, wave), kThreads, b->counts[b->cur], b->counts[nx], b->stride,
+                   b->sid[b->cur], b->sid[nx], b->state[nx], b->m->d_sizes, b->N, D.J, wave, b->att_src,
+                   b->att_state, b->att_accept, b->att_pos, b->att_rec, accepted, b->delta_cap > 0 ? 1 : 0,
+                   b->delta_cap, ctx->d_flag);
         int got = 0;
         CU(ctx, cudaMemcpyAsync(&got, b->d_total, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         if ((rc = check_flag(ctx))) return rc; // synchronises
@@ -1569,7 +1592,29 @@ extern "C" int fba_belief_reject_sample(fba_belief* b, int32_t a, int32_t o, fba
             return ctx->err = "rejection sampling: observation has (near) zero probability under the belief",
                    FBA_ERR_INVALID;
     }
-    flip(b);
+    if (inplace)
+    {
+        long long const N = b->N;
+        int const n_ft    = (int)((N + kFlagTile - 1) / kFlagTile);
+        int* const first  = b->noff;   // N ints
+        int* const extra  = b->escan;  // N ints
+        int* const xpos   = b->src_of; // >= N ints
+        LAUNCH(ctx, k_fill_int, blocks_for(N), kThreads, first, N, 0x7fffffff);
+        LAUNCH(ctx, k_rs_first, blocks_for(N), kThreads, b->rs_src, N, first);
+        LAUNCH(ctx, k_rs_flags, blocks_for(N), kThreads, b->rs_src, first, N, extra, b->rs_flag);
+        LAUNCH(ctx, k_flag_tile_counts, n_ft, kThreads, extra, N, b->rs_tiles);
+        LAUNCH(ctx, k_flag_scan_tiles, 1, kThreads, b->rs_tiles, n_ft, b->d_total);
+        LAUNCH(ctx, k_flag_scan_apply, n_ft, kThreads, extra, N, b->rs_tiles, xpos);
+        LAUNCH(ctx, k_flag_tile_counts, n_ft, kThreads, b->rs_flag, N, b->rs_tiles);
+        LAUNCH(ctx, k_flag_scan_tiles, 1, kThreads, b->rs_tiles, n_ft, b->d_total);
+        LAUNCH(ctx, k_flag_scan_apply, n_ft, kThreads, b->rs_flag, N, b->rs_tiles, b->rs_pos);
+        LAUNCH(ctx, k_rs_empty_list, blocks_for(N), kThreads, b->rs_flag, b->rs_pos, N, b->dead);
+        LAUNCH(ctx, k_rs_place_extras, stream_grid(ctx, N), kThreads, b->counts[b->cur], b->stride, b->sid[b->cur],
+               b->state[b->cur], b->m->d_sizes, N, D.J, b->rs_src, b->rs_state, b->rs_rec, extra, xpos, b->dead);
+        LAUNCH(ctx, k_rs_apply_first, blocks_for(N), kThreads, b->counts[b->cur], b->stride, b->state[b->cur], N,
+               D.J, first, b->rs_state, b->rs_rec);
+    } else
+        flip(b);
     if (attempts_out) *attempts_out = attempts;
     return FBA_OK;
 }
@@ -1706,6 +1751,7 @@ extern "C" int fba_belief_reinvigorate(fba_belief* b, fba_belief* fc, int64_t am
     if ((long long)jobs.size() > b->jobs_cap)
     {
         cudaFree(b->d_jobs);
+    cudaFree(b->rs_src), cudaFree(b->rs_state), cudaFree(b->rs_rec), cudaFree(b->rs_flag), cudaFree(b->rs_pos), cudaFree(b->rs_tiles);
         b->d_jobs   = nullptr;
         b->jobs_cap = 0;
         long long const cap = (long long)jobs.size() * 2 + 64;

@@ -1684,6 +1684,114 @@ __global__ void __launch_bounds__(kThreads)
 }
 
 // ------------------------------------------------------------------------------------------------
+// Rejection sampling IN PLACE (PHILOX mode). The new belief is the first N accepted attempts; a flat
+// filter has no order, so — as with in-place resampling — a source particle that was accepted at
+// least once KEEPS ITS SLOT and takes the increments of its first accepted attempt there, and only the
+// further accepted attempts of the same source are copies, into the slots of the sources that were
+// never accepted. With sources drawn uniformly that is ~37 % of the blocks instead of all of them,
+// and no second buffer. Deterministic: "first" is the smallest accepted index (atomicMin), extras
+// and empty slots are matched in index order by two flag scans.
+//   acc_*: the accepted attempts, compacted in attempt order, k = 0 .. N-1
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+    k_rs_collect(long long N, int J, long long n_attempts, const int* __restrict__ att_src,
+                 const int* __restrict__ att_state, const int* __restrict__ accept, const int* __restrict__ pos,
+                 const int* __restrict__ rec, long long already, int* __restrict__ acc_src,
+                 int* __restrict__ acc_state, int* __restrict__ acc_rec)
+{
+    long long const t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_attempts || !accept[t]) return;
+    long long const k = already + pos[t];
+    if (k >= N) return;
+    acc_src[k]   = att_src[t];
+    acc_state[k] = att_state[t];
+    for (int j = 0; j < J; ++j) acc_rec[k * J + j] = rec[t * J + j];
+}
+
+__global__ void __launch_bounds__(kThreads) k_fill_int(int* __restrict__ p, long long n, int v)
+{
+    long long const i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// first[i] = the smallest accepted attempt whose source is particle i (INT_MAX: never accepted)
+__global__ void __launch_bounds__(kThreads)
+    k_rs_first(const int* __restrict__ acc_src, long long N, int* __restrict__ first)
+{
+    long long const k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < N) atomicMin(&first[acc_src[k]], (int)k);
+}
+
+// extra[k] = attempt k is NOT the first of its source (it needs a copy); empty[i] = slot i has no
+// accepted attempt (it receives one)
+__global__ void __launch_bounds__(kThreads)
+    k_rs_flags(const int* __restrict__ acc_src, const int* __restrict__ first, long long N,
+               int* __restrict__ extra, int* __restrict__ empty)
+{
+    long long const k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= N) return;
+    extra[k] = first[acc_src[k]] != (int)k;
+    empty[k] = first[k] == 0x7fffffff;
+}
+
+__global__ void __launch_bounds__(kThreads)
+    k_rs_empty_list(const int* __restrict__ empty, const int* __restrict__ empty_pos, long long N,
+                    int* __restrict__ empty_slot)
+{
+    long long const i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N && empty[i]) empty_slot[empty_pos[i]] = (int)i;
+}
+
+// the e-th extra attempt becomes the e-th empty slot: copy of its (still untouched) source block plus
+// its own increments. One warp per accepted attempt.
+__global__ void __launch_bounds__(kThreads)
+    k_rs_place_extras(float* counts, long long stride, int* sid, int* state,
+                      const int* __restrict__ struct_size, long long N, int J, const int* __restrict__ acc_src,
+                      const int* __restrict__ acc_state, const int* __restrict__ acc_rec,
+                      const int* __restrict__ extra, const int* __restrict__ extra_pos,
+                      const int* __restrict__ empty_slot)
+{
+    int const lane        = threadIdx.x & 31;
+    long long const warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    long long const nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long k = warp0; k < N; k += nwarp)
+    {
+        if (!extra[k]) continue;
+        long long const i = acc_src[k], j = empty_slot[extra_pos[k]];
+        int const id      = sid[i];
+        const float* sb   = counts + i * stride;
+        float* d          = counts + j * stride;
+        warp_copy_block(sb, d, (struct_size[id] + 3) >> 2, lane);
+        __syncwarp();
+        if (lane < J) d[acc_rec[k * J + lane]] = __fadd_rn(sb[acc_rec[k * J + lane]], 1.0f);
+        if (lane == 0)
+        {
+            sid[j]   = id;
+            state[j] = acc_state[k];
+        }
+    }
+}
+
+// afterwards: every accepted source takes its FIRST accepted attempt's increments where it is
+__global__ void __launch_bounds__(kThreads)
+    k_rs_apply_first(float* counts, long long stride, int* __restrict__ state, long long N, int J,
+                     const int* __restrict__ first, const int* __restrict__ acc_state,
+                     const int* __restrict__ acc_rec)
+{
+    long long const i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int const k = first[i];
+    if (k == 0x7fffffff) return;
+    float* c = counts + i * stride;
+    for (int j = 0; j < J; ++j)
+    {
+        int const cell = acc_rec[(long long)k * J + j];
+        c[cell]        = __fadd_rn(c[cell], 1.0f);
+    }
+    state[i] = acc_state[k];
+}
+
+// ------------------------------------------------------------------------------------------------
 // reinvigoration: BABNModel::marginalizeOut (BABNModel.cpp:205-229) of a fully connected counts
 // donor onto a mutated structure, written into the replaced slot. One block per bred particle.
 // Each destination cell sums its source rows in ascending source-configuration order — the order
