@@ -28,6 +28,7 @@ struct fba_ctx
     int bulk_copy    = 0;  // 1: full-copy gathers go through the TMA engine (k_gather_bulk)
     int rollout_coop = -1; // -1 auto (by batch size and row length), 0 thread per rollout, 1 warp per rollout
     bool inplace_resample = true; // PHILOX mode: survivors keep their slot (fba_ctx_set_option)
+    bool fused_update     = true; // small beliefs: update + resample in ONE launch (k_runs_step, one CTA)
     bool profiling       = false;
     struct Timed
     {
@@ -302,6 +303,11 @@ extern "C" int fba_ctx_set_option(fba_ctx* ctx, const char* name, int64_t value)
     if (!strcmp(name, "inplace_resample"))
     {
         ctx->inplace_resample = value != 0;
+        return FBA_OK;
+    }
+    if (!strcmp(name, "fused_update"))
+    {
+        ctx->fused_update = value != 0;
         return FBA_OK;
     }
     if (!strcmp(name, "bulk_copy"))
@@ -1332,8 +1338,56 @@ extern "C" int fba_belief_resample(fba_belief* b, fba_rng* rng)
     return FBA_OK;
 }
 
+// A belief this small is launch-latency-bound (nine launches, ~40 us): one CTA does the whole
+// update + resample with the very same *_body functions (k_runs_step with one run), bit-identical
+// to the launch-per-phase path (tests/test_cuda_runs.py compares the two).
+constexpr long long kFusedMaxParticles = 2048;
+
 extern "C" int fba_belief_update_estimation(fba_belief* b, int32_t a, int32_t o, fba_rng* rng, double* likelihood)
 {
+    if (b && rng && rng->mode == FBA_RNG_PHILOX && b->ctx->fused_update && b->ctx->inplace_resample &&
+        !b->ctx->profiling && b->weighted && b->delta_cap == 0 && b->N <= kFusedMaxParticles)
+    {
+        fba_ctx* ctx      = b->ctx;
+        DevModel const& D = b->m->dev;
+        REQUIRE(ctx, a >= 0 && a < D.A, "action out of range");
+        REQUIRE(ctx, o >= 0 && o < D.O, "observation out of range");
+        CU(ctx, cudaSetDevice(ctx->device));
+        RunsArgs A{};
+        A.counts = b->counts[b->cur], A.stride = b->stride, A.state = b->state[b->cur], A.sid = b->sid[b->cur];
+        A.w = b->w, A.cdf = b->aux, A.noff = b->noff, A.escan = b->escan, A.dead = b->dead, A.src_of = b->src_of;
+        A.tile = b->tile, A.tile_pairs = b->tile_pairs, A.totals = b->totals, A.scal = b->scal;
+        A.n = b->N, A.n_tiles = (int)((b->N + kTile - 1) / kTile);
+        A.action0 = a, A.observation0 = o;
+        A.struct_size = b->m->d_sizes;
+        A.stats       = b->stats;
+        RngArgs ra{};
+        ra.seed   = rng->seed;
+        ra.offset = rng->offset;
+        rng->offset += 2; // propose + resample, as the two calls below
+        bool const lr = b->m->long_rows;
+        if (D.sampled)
+        {
+            if (lr) LAUNCH(ctx, (k_runs_step<true, true, 0>), 1, kThreads, D, A, ra);
+            else
+                LAUNCH(ctx, (k_runs_step<false, true, 0>), 1, kThreads, D, A, ra);
+        } else
+        {
+            if (lr) LAUNCH(ctx, (k_runs_step<true, false, 0>), 1, kThreads, D, A, ra);
+            else
+                LAUNCH(ctx, (k_runs_step<false, false, 0>), 1, kThreads, D, A, ra);
+        }
+        b->total_weight = 1.0;
+        b->suffix_valid = b->cdf_valid = false;
+        b->inplace_last = true;
+        if (likelihood)
+        {
+            int const rc = read_scal(b);
+            if (rc) return rc;
+            *likelihood = ctx->h_scal[0];
+        }
+        return FBA_OK;
+    }
     int rc = fba_belief_update(b, a, o, rng, likelihood);
     if (rc) return rc;
     return fba_belief_resample(b, rng);

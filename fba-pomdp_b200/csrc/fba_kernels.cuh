@@ -975,10 +975,12 @@ struct RunsArgs
     long long* picked;                 // [R]: MODE 2 result (local particle index)
     long long n;                       // particles per run
     int n_tiles;
-    const int *action, *observation;   // [R] (MODE 0)
+    const int *action, *observation;   // [R] (MODE 0); NULL: every run takes action0 / observation0
+    int action0, observation0;
     const unsigned char* active;       // [R] or NULL: runs with 0 are left untouched
     const int* struct_size;
-    unsigned long long* copies;        // [1]: block copies made, all runs
+    unsigned long long* copies;        // [1]: block copies made, all runs (may be NULL)
+    long long* stats;                  // single belief (R = 1): fba_belief's [copies, resamples] (may be NULL)
 };
 
 template<bool LONG, bool SAMPLED, int MODE>
@@ -1010,7 +1012,7 @@ __global__ void __launch_bounds__(kThreads)
 
     if (MODE == 0)
     { // importance_sampling::update, per-particle part (k_propose)
-        int const a = A.action[r], o = A.observation[r];
+        int const a = A.action ? A.action[r] : A.action0, o = A.observation ? A.observation[r] : A.observation0;
         for (long long i = threadIdx.x; i < n; i += kThreads)
         {
             auto g            = RngOf<false>::make(rr, i);
@@ -1080,6 +1082,7 @@ __global__ void __launch_bounds__(kThreads)
         { // k_copy_inplace, the run's own warps: the k-th extra copy fills the k-th dead slot
             long long const n_fill = min((long long)totals[0], (long long)totals[1]);
             if (threadIdx.x == 0 && A.copies) atomicAdd(A.copies, (unsigned long long)n_fill);
+            if (threadIdx.x == 0 && A.stats) A.stats[0] += n_fill, A.stats[1] += 1;
             int const lane = threadIdx.x & 31;
             for (long long k = threadIdx.x >> 5; k < n_fill; k += kThreads / 32)
             {

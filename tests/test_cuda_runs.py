@@ -16,8 +16,37 @@ pytestmark = pytest.mark.gpu
 def ctx():
     import fba_pomdp_b200 as fba
     c = fba.Context(0)
+    # the stand-alone beliefs the batches are compared with take the launch-per-phase path, whatever
+    # their size (small ones would otherwise use the same fused kernel as the batch)
+    c.set_option("fused_update", 0)
     yield c
     c.close()
+
+
+def test_fused_small_belief_update_equals_launch_per_phase(ctx):
+    """fba_belief_update_estimation on a belief of <= 2048 particles runs update + resample in ONE
+    launch; the result is bit-identical to the nine-launch path."""
+    import fba_pomdp_b200 as fba
+    g = G.load("tiger")
+    sim = fba.BAPOMDP(ctx, g.desc, g.t_par, g.o_par)
+    out = {}
+    for fused in (0, 1):
+        ctx.set_option("fused_update", fused)
+        b = fba.BAImportanceSampling(1500)
+        rng = fba.Rng.philox(11)
+        b.initiate_sampled(sim, [0], g["is/init_counts"][:1], None, rng)
+        l0 = ctx.launches
+        liks = [b.updateEstimation(2, t % 2, rng) for t in range(6)]
+        launches = ctx.launches - l0
+        d = b.download()
+        out[fused] = (liks, d, launches, b.resample_stats())
+        b.free()
+    ctx.set_option("fused_update", 0)
+    assert out[0][0] == out[1][0] and out[0][3] == out[1][3]
+    for k in ("state", "struct_id", "w", "counts"):
+        np.testing.assert_array_equal(out[0][1][k], out[1][1][k])
+    assert out[1][2] == 6 and out[0][2] > 6 * 5
+    sim.close()
 
 
 def _protos(g):
