@@ -2465,7 +2465,7 @@ extern "C" int fba_runs_plan(fba_runs* r, int64_t n_sims, const int32_t* depth, 
     // one node per simulation per run, load factor <= 1/2
     unsigned long long table = 1024;
     while (table < 2ull * (unsigned long long)r->R * (unsigned long long)n_sims) table <<= 1;
-    REQUIRE(ctx, table <= (1ull << 31), "runs_plan: n_runs x n_simulations exceeds 2^30 tree nodes");
+    REQUIRE(ctx, table <= (1ull << 30), "runs_plan: n_runs x n_simulations exceeds 2^29 tree nodes (node ids are 32-bit)");
     if (table > r->table)
     {
         cudaFree(r->keys), cudaFree(r->visits), cudaFree(r->stat);
