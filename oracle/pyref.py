@@ -198,12 +198,13 @@ class Ref:
             raise RuntimeError("reference/adapter: " + self.L.ref_error(self.h).decode())
         return out
 
-    def batched_episodes(self, n, runs, sims, episodes, sims_per_wave=1):
-        """fba_b200::runBatchedExperiment -> (returns[episodes, runs], seconds)"""
-        self.L.ref_batched_episodes.restype = C.c_double
-        self.L.ref_batched_episodes.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    def batched_episodes(self, n, runs, sims, episodes, sims_per_wave=1, device=0, seed=4711):
+        """fba_b200::runBatchedExperiment on GPU `device` -> (returns[episodes, runs], seconds)"""
+        f = self.L.ref_batched_episodes_on
+        f.restype = C.c_double
+        f.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_ulonglong, C.c_void_p]
         out = np.zeros((episodes, runs), np.float64)
-        dt = self.L.ref_batched_episodes(self.h, n, runs, sims, episodes, sims_per_wave, _p(out))
+        dt = f(self.h, n, runs, sims, episodes, sims_per_wave, device, seed, _p(out))
         if dt < 0:
             raise RuntimeError("reference/adapter: " + self.L.ref_error(self.h).decode())
         return out, dt

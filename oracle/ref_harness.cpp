@@ -707,7 +707,16 @@ int ref_adapter_episodes(void* hv, int kind, long n, char const* planner, int si
 // fba_b200::runBatchedExperiment (host/CudaExperiment.hpp): `runs` runs of `episodes` episodes in
 // lockstep on the GPU, n particles and `sims` simulations each. returns: episodes x runs, row-major.
 // Result: seconds of wall time, < 0 on error.
+double ref_batched_episodes_on(void* hv, long n, int runs, int sims, int episodes, int sims_per_wave, int device,
+                               unsigned long long seed, double* returns);
 double ref_batched_episodes(void* hv, long n, int runs, int sims, int episodes, int sims_per_wave, double* returns)
+{
+    return ref_batched_episodes_on(hv, n, runs, sims, episodes, sims_per_wave, 0, 4711ull, returns);
+}
+
+// the same on a given GPU with a given seed: independent runs shard over GPUs with no communication
+double ref_batched_episodes_on(void* hv, long n, int runs, int sims, int episodes, int sims_per_wave, int device,
+                               unsigned long long seed, double* returns)
 {
     auto h = static_cast<Handle*>(hv);
     try
@@ -718,7 +727,7 @@ double ref_batched_episodes(void* hv, long n, int runs, int sims, int episodes, 
         conf.planner_conf.mcts_max_depth         = conf.horizon;
         conf.num_episodes                        = episodes;
         auto t0  = std::chrono::steady_clock::now();
-        auto res = fba_b200::runBatchedExperiment(*h->sim, conf, runs, sims_per_wave);
+        auto res = fba_b200::runBatchedExperiment(*h->sim, conf, runs, sims_per_wave, seed, device);
         double const dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         for (int e = 0; e < episodes; ++e)
             for (int r = 0; r < runs; ++r) returns[(size_t)e * runs + r] = res[e][r];
