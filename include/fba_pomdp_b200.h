@@ -145,8 +145,12 @@ int64_t fba_ctx_launch_count(const fba_ctx* ctx);
 
 /* options: "inplace_resample" (default 1): PHILOX-mode resampling keeps surviving particles in
  * their slot and copies only duplicates; 0 = gather every particle into the second buffer */
-/*          "rollout_coop" (default -1 = choose by batch size and row length): 1 = one warp per rollout
- *          with cooperatively loaded rows, 0 = one thread per rollout */
+/*          "rollout_coop" (default -1 = thread per rollout): 1 = one warp per rollout with
+ *          cooperatively loaded rows, 0 = one thread per rollout
+ *          "fused_update" (default 1): fba_belief_update_estimation on a weighted PHILOX belief of at
+ *          most 2048 particles runs update + resample in ONE launch (bit-identical to the
+ *          launch-per-phase path); 0 = always launch per phase
+ *          "bulk_copy" (default 0): 1 = full-copy gathers go through the TMA engine (cp.async.bulk) */
 int fba_ctx_set_option(fba_ctx* ctx, const char* name, int64_t value);
 
 /* per-kernel CUDA-event timing on the context's stream: begin, run calls, end, then query the
