@@ -576,11 +576,32 @@ __device__ __forceinline__ int hyper_step(const DevModel& M, const Node* __restr
         Node const nd   = nodes[f];
         int const range = M.feat_s[f];
         int const cell  = nd.off + parent_config(M, nd.par, x) * range;
-        int const v     = COOP ? sample_expected_mult_warp(counts + cell, range, draw_u(g))
-                               : sample_row<LONG, SAMPLED>(counts + cell, range, g);
+        int v;
+        if (MODE == STEP_UPDATE && !COOP && !LONG && !SAMPLED && range == 2)
+        { // binary feature, counts updated: ONE 16-byte load and ONE 16-byte store of the aligned chunk
+          // that holds the row (and a neighbouring row of the same particle) instead of an 8-byte load
+          // and a 4-byte store — the write-back of isolated dirty sectors is what bounds this kernel,
+          // and 16-byte stores are the cheapest form of it (tools/exp_granule.cu). Same arithmetic as
+          // sample_expected_mult(row, 2, u).
+            float4* const chunk = reinterpret_cast<float4*>(counts + (cell & ~3));
+            float4 ch           = *chunk;
+            bool const upper    = (cell & 2) != 0;
+            float const r0 = upper ? ch.z : ch.x, r1 = upper ? ch.w : ch.y;
+            double const p = __dmul_rn(draw_u(g), __dadd_rn((double)r0, (double)r1));
+            v              = (p < (double)r0) ? 0 : 1;
+            float const inc = __fadd_rn(v ? r1 : r0, 1.0f);
+            if (upper) (v ? ch.w : ch.z) = inc;
+            else
+                (v ? ch.y : ch.x) = inc;
+            *chunk = ch;
+        } else
+        {
+            v = COOP ? sample_expected_mult_warp(counts + cell, range, draw_u(g))
+                     : sample_row<LONG, SAMPLED>(counts + cell, range, g);
+            if (MODE == STEP_UPDATE) counts[cell + v] = __fadd_rn(counts[cell + v], 1.0f);
+        }
         x2.set(f, v, single_s);
         s2 += v * M.step_s[f];
-        if (MODE == STEP_UPDATE) counts[cell + v] = __fadd_rn(counts[cell + v], 1.0f);
         if (MODE == STEP_RECORD) rec[f] = cell + v;
     }
     if (single_s) s2 = (int)x2.lo;
@@ -613,7 +634,19 @@ __device__ __forceinline__ int hyper_step(const DevModel& M, const Node* __restr
             Node const nd   = nodes[M.FS + q];
             int const range = M.feat_o[q];
             int const cell  = nd.off + parent_config(M, nd.par, xo) * range + of.get(q, single_o);
-            if (MODE == STEP_UPDATE) counts[cell] = __fadd_rn(counts[cell], 1.0f);
+            if (MODE == STEP_UPDATE)
+            {
+                if (!COOP && !LONG && !SAMPLED && range == 2)
+                { // as above: the aligned 16-byte chunk around the cell, read and written whole
+                    float4* const chunk = reinterpret_cast<float4*>(counts + (cell & ~3));
+                    float4 ch           = *chunk;
+                    int const k         = cell & 3;
+                    float& t            = (k == 0) ? ch.x : (k == 1) ? ch.y : (k == 2) ? ch.z : ch.w;
+                    t                   = __fadd_rn(t, 1.0f);
+                    *chunk              = ch;
+                } else
+                    counts[cell] = __fadd_rn(counts[cell], 1.0f);
+            }
             if (MODE == STEP_RECORD) rec[M.FS + q] = cell;
         }
     }
