@@ -366,6 +366,14 @@ class ReinvigoratingRejectionSampling(_ParticleBelief):
             self.fc = None
 
 
+def log_bd_score(belief, prior):
+    """BABNModel::LogBDScore of every particle of `belief` against `prior` (a belief of the same size
+    or of one particle, same structures) -> N doubles."""
+    out = np.zeros(belief.size(), np.float64)
+    _check(belief.ctx.h, belief.L.fba_belief_log_bd_score(belief.h, prior.h, ptr(out)))
+    return out
+
+
 class SearchTree:
     """Device-resident POMCP search tree (fba_tree_*): planners::RBAPOUCT::selectAction
     (RBAPOUCT.cpp:67-153) with whole simulations inside one kernel, `wave` at a time."""

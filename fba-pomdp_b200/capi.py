@@ -18,7 +18,7 @@ MUT_FACTORED_TIGER, MUT_COLLISION_AVOIDANCE, MUT_SYSADMIN, MUT_GRIDWORLD = range
 RNG_REPLAY, RNG_PHILOX = 0, 1
 
 # every symbol include/fba_pomdp_b200.h declares (tests check the library exports all of them)
-ABI_VERSION = 9  # must equal FBA_ABI_VERSION in include/fba_pomdp_b200.h
+ABI_VERSION = 10  # must equal FBA_ABI_VERSION in include/fba_pomdp_b200.h
 
 SYMBOLS = [
     "fba_abi_version", "fba_ctx_create", "fba_ctx_destroy", "fba_last_error", "fba_ctx_stream", "fba_ctx_synchronize",
@@ -38,6 +38,7 @@ SYMBOLS = [
     "fba_belief_export_ptr", "fba_belief_import_ptr", "fba_belief_record_bytes", "fba_belief_import",
     "fba_belief_counts_ptr", "fba_belief_state_ptr", "fba_belief_weight_ptr",
     "fba_belief_scalars_ptr",
+    "fba_belief_log_bd_score",
     "fba_tree_create", "fba_tree_destroy", "fba_tree_search",
     "fba_runs_create", "fba_runs_destroy", "fba_runs_belief", "fba_runs_init_sampled",
     "fba_runs_update_estimation", "fba_runs_reset_domain_states", "fba_runs_sample", "fba_runs_copies", "fba_runs_plan", "fba_runs_init",
@@ -162,6 +163,7 @@ def lib():
             "fba_belief_state_ptr": (vp, [vp]),
             "fba_belief_weight_ptr": (vp, [vp]),
             "fba_belief_scalars_ptr": (vp, [vp]),
+            "fba_belief_log_bd_score": (C.c_int, [vp, vp, vp]),
             "fba_tree_create": (C.c_int, [vp, vp, i64, i32, pp]),
             "fba_tree_destroy": (None, [vp]),
             "fba_tree_search": (C.c_int, [vp, vp, i64, i32, dbl, dbl, i32, vp, vp, vp, vp]),

@@ -2030,6 +2030,29 @@ extern "C" int fba_step_batch(fba_belief* b, int64_t n, const int64_t* particle,
     return FBA_OK;
 }
 
+// ---- Bayesian-Dirichlet score ---------------------------------------------------------------------
+
+extern "C" int fba_belief_log_bd_score(fba_belief* b, fba_belief* prior, double* scores)
+{
+    if (!b || !prior || !scores) return FBA_ERR_INVALID;
+    fba_ctx* ctx      = b->ctx;
+    DevModel const& D = b->m->dev;
+    REQUIRE(ctx, prior->m == b->m && prior->ctx == ctx, "log_bd_score: both beliefs must share one model and context");
+    REQUIRE(ctx, !D.tabular && b->delta_cap == 0, "log_bd_score: factored models with dense storage only");
+    REQUIRE(ctx, prior->N == b->N || prior->N == 1, "log_bd_score: the prior belief has N particles or one");
+    CU(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = clear_flag(ctx))) return rc;
+    LAUNCH(ctx, k_log_bd_score, stream_grid(ctx, b->N), kThreads, D, b->counts[b->cur], b->stride, b->sid[b->cur], b->N,
+           prior->counts[prior->cur], prior->stride, prior->sid[prior->cur], prior->N, b->aux, ctx->d_flag);
+    b->suffix_valid = b->cdf_valid = false; // aux was used as the result buffer
+    CU(ctx, cudaMemcpyAsync(scores, b->aux, (size_t)b->N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    REQUIRE(ctx, *ctx->h_flag == 0, "log_bd_score: a particle and its prior have different structures");
+    return FBA_OK;
+}
+
 // ---- POMCP, tree on the device -------------------------------------------------------------------
 
 struct fba_tree

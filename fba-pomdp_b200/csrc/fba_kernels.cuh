@@ -1687,6 +1687,65 @@ __global__ void __launch_bounds__(kThreads)
 }
 
 // ------------------------------------------------------------------------------------------------
+// BABNModel::LogBDScore(prior) (BABNModel.cpp:451-478, DBNNode.cpp:82-117): log Bayesian-Dirichlet
+// score of every particle's counts against prior counts of the same structure — what the reference's
+// MCMC structure beliefs compare (MHNIPS2018.cpp:237-238, MHwithinGibbs.cpp:352,365).
+//   score = sum over rows [ sum_v (lG(c_v) - lG(p_v)) + lG(sum_v p_v) - lG(sum_v c_v) ],
+//   lG(x) = x < 1 ? 0 : lgamma(x)   (rnd::math::logGamma, random.cpp:127-135)
+// One warp per particle; lanes take the rows of a node in turn, partial sums in double, one shuffle
+// reduction at the end (so the sum order differs from the reference's: agreement to ~1e-12 relative).
+// prior_n = 1: every particle is scored against the same prior particle; otherwise particle i against
+// prior particle i. Structures must match (mismatch -> *flag = 1).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double log_gamma_ref(double x)
+{
+    return (x < 1.0) ? 0.0 : lgamma(x);
+}
+
+__global__ void __launch_bounds__(kThreads)
+    k_log_bd_score(DevModel M, const float* __restrict__ counts, long long stride, const int* __restrict__ sid,
+                   long long N, const float* __restrict__ prior, long long prior_stride,
+                   const int* __restrict__ prior_sid, long long prior_n, double* __restrict__ score,
+                   int* __restrict__ flag)
+{
+    int const lane        = threadIdx.x & 31;
+    long long const warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    long long const nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long i = warp0; i < N; i += nwarp)
+    {
+        long long const j = (prior_n == 1) ? 0 : i;
+        int const id      = sid[i];
+        if (lane == 0 && prior_sid[j] != id) *flag = 1;
+        const float* c    = counts + i * stride;
+        const float* p    = prior + j * prior_stride;
+        const Node* nodes = M.nodes + (long long)id * M.A * M.J;
+        double acc        = 0.0;
+        for (int a = 0; a < M.A; ++a)
+            for (int q = 0; q < M.J; ++q)
+            {
+                Node const nd   = nodes[a * M.J + q];
+                int const range = (q < M.FS) ? M.feat_s[q] : M.feat_o[q - M.FS];
+                int cfgs        = 1;
+                for (uint32_t m = nd.par; m; m &= m - 1) cfgs *= M.feat_s[__ffs(m) - 1];
+                for (int r = lane; r < cfgs; r += 32)
+                {
+                    int const row = nd.off + r * range;
+                    double ct = 0.0, pt = 0.0;
+                    for (int v = 0; v < range; ++v)
+                    {
+                        double const cv = (double)c[row + v], pv = (double)p[row + v];
+                        ct += cv, pt += pv;
+                        acc += log_gamma_ref(cv) - log_gamma_ref(pv);
+                    }
+                    acc += log_gamma_ref(pt) - log_gamma_ref(ct);
+                }
+            }
+        for (int o = 16; o; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+        if (lane == 0) score[i] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Rejection sampling IN PLACE (PHILOX mode). The new belief is the first N accepted attempts; a flat
 // filter has no order, so — as with in-place resampling — a source particle that was accepted at
 // least once KEEPS ITS SLOT and takes the increments of its first accepted attempt there, and only the

@@ -31,7 +31,7 @@ extern "C" {
 
 #define FBA_MAX_FEATURES 16
 /* bumped whenever a struct below changes layout; compare with fba_abi_version() after loading */
-#define FBA_ABI_VERSION 9
+#define FBA_ABI_VERSION 10
 
 typedef struct fba_ctx fba_ctx;
 typedef struct fba_model fba_model;
@@ -295,6 +295,13 @@ void* fba_belief_import_ptr(fba_belief* b, int64_t n_records);
 int64_t fba_belief_record_bytes(const fba_belief* b);
 /* phase 4: place n_records imported records into the slots the local resample left empty */
 int fba_belief_import(fba_belief* b, int64_t n_records);
+
+/* BABNModel::LogBDScore (src/bayes-adaptive/states/factored/BABNModel.cpp:451-478, DBNNode.cpp:82-117):
+ * scores[i] (host, N doubles) = log Bayesian-Dirichlet score of particle i of `b` against the prior
+ * counts in `prior` — particle i of `prior`, or its only particle if it has one. Both beliefs share a
+ * model and the compared particles a structure (FBA_ERR_INVALID otherwise). Factored models, dense
+ * storage. First brick of the reference's MCMC structure beliefs. */
+int fba_belief_log_bd_score(fba_belief* b, fba_belief* prior, double* scores);
 
 /* ---- POMCP with the search tree on the device --------------------------------
  * planners::RBAPOUCT::selectAction (src/planners/bayes-adaptive/RBAPOUCT.cpp:67-153) as waves of

@@ -369,6 +369,45 @@ double orc_obs_prob(const orc_model* m, const uint32_t* t_par, const uint32_t* o
     return prob;
 }
 
+/* rnd::math::logGamma (random.cpp:127-135) */
+static double log_gamma_ref(double x)
+{
+    return (x < 1) ? 0.0 : lgamma(x);
+}
+
+double orc_log_bd_score(const orc_model* m, const uint32_t* t_par, const uint32_t* o_par, const float* counts,
+                        const float* prior_counts)
+{
+    /* BABNModel::LogBDScore: for a, for transition nodes, for observation nodes — the block's own order */
+    double total = 0;
+    int64_t off  = 0;
+    for (int a = 0; a < m->A; ++a)
+        for (int j = 0; j < m->FS + m->FO; ++j)
+        {
+            uint32_t const par = (j < m->FS) ? t_par[a * m->FS + j] : o_par[a * m->FO + (j - m->FS)];
+            int const range    = (j < m->FS) ? m->feat_s[j] : m->feat_o[j - m->FS];
+            int64_t cfgs       = 1;
+            for (int f = 0; f < m->FS; ++f)
+                if (par & (1u << f)) cfgs *= m->feat_s[f];
+            double node = 0; /* DBNNode::LogBDScore */
+            for (int64_t r = 0; r < cfgs; ++r)
+            {
+                double distr_total = 0, prior_total = 0;
+                for (int v = 0; v < range; ++v)
+                {
+                    int64_t const i = off + r * range + v;
+                    distr_total += counts[i];
+                    prior_total += prior_counts[i];
+                    node += log_gamma_ref(counts[i]) - log_gamma_ref(prior_counts[i]);
+                }
+                node += log_gamma_ref(prior_total) - log_gamma_ref(distr_total);
+            }
+            total += node;
+            off += cfgs * range;
+        }
+    return total;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* importance sampling                                                                         */
 /* ------------------------------------------------------------------------------------------ */

@@ -114,6 +114,13 @@ double orc_step(const orc_model* m, const uint32_t* t_par, const uint32_t* o_par
 double orc_obs_prob(const orc_model* m, const uint32_t* t_par, const uint32_t* o_par,
                     const float* counts, int state, int a, int o);
 
+/* BABNModel::LogBDScore(prior) (BABNModel.cpp:451-478, DBNNode.cpp:82-117, logGamma random.cpp:127-135):
+ * log Bayesian-Dirichlet score of a particle's counts against prior counts of the SAME structure — the
+ * quantity the reference's MCMC structure beliefs (MHNIPS2018.cpp:237-238, MHwithinGibbs.cpp:352,365)
+ * compare. Same accumulation order as the reference (per row, per node, nodes in block order). */
+double orc_log_bd_score(const orc_model* m, const uint32_t* t_par, const uint32_t* o_par, const float* counts,
+                        const float* prior_counts);
+
 /* importance_sampling::update (ImportanceSampler.hpp:31-62); returns the un-normalised total */
 double orc_is_update(const orc_model* m, const orc_structs* st, orc_belief* b, int a, int o, orc_rng* g);
 /* WeightedFilter::sample (WeightedFilter.cpp:163-191): index of the drawn particle */

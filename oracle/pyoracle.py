@@ -268,6 +268,17 @@ def step(model, t_par, o_par, counts, state, a, update_counts, rng):
     return int(st[0]), o.value, bool(t.value), r
 
 
+def log_bd_score(model, t_par, o_par, counts, prior_counts):
+    L = lib()
+    L.orc_log_bd_score.restype = C.c_double
+    L.orc_log_bd_score.argtypes = [C.c_void_p] * 5
+    tp = np.ascontiguousarray(t_par, np.uint32)
+    op = np.ascontiguousarray(o_par, np.uint32)
+    c = np.ascontiguousarray(counts, np.float32)
+    pc = np.ascontiguousarray(prior_counts, np.float32)
+    return L.orc_log_bd_score(model.ref(), _p(tp), _p(op), _p(c), _p(pc))
+
+
 def obs_prob(model, t_par, o_par, counts, state, a, o):
     tp = np.ascontiguousarray(t_par, np.uint32)
     op = np.ascontiguousarray(o_par, np.uint32)

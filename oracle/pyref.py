@@ -175,6 +175,11 @@ class Ref:
     def obs_prob(self, filt, i, a, o):
         return self.L.ref_particle_obs_prob(self.h, filt, i, a, o)
 
+    def log_bd_score(self, filt, i, prior_filt, j):
+        self.L.ref_log_bd_score.restype = C.c_double
+        self.L.ref_log_bd_score.argtypes = [C.c_void_p, C.c_int, C.c_long, C.c_int, C.c_long]
+        return self.L.ref_log_bd_score(self.h, filt, i, prior_filt, j)
+
     def rollout(self, filt, i, start_state, depth):
         return self.L.ref_rollout(self.h, filt, i, start_state, depth)
 

@@ -490,6 +490,17 @@ double ref_particle_obs_prob(void* hv, int filter, long i, int a, int o)
     return h->sim->computeObservationProbability(&obs, &act, particleOf(h, filter, i));
 }
 
+/**** BABNModel::LogBDScore (BABNModel.cpp:451-478) of particle i of `filter` against particle j of
+      `prior_filter` (same structure required; factored models only) ****/
+double ref_log_bd_score(void* hv, int filter, long i, int prior_filter, long j)
+{
+    auto h = static_cast<Handle*>(hv);
+    if (!h->factored) return 0.0;
+    auto a = const_cast<FBAPOMDPState*>(static_cast<FBAPOMDPState const*>(particleOf(h, filter, i)))->model();
+    auto b = const_cast<FBAPOMDPState*>(static_cast<FBAPOMDPState const*>(particleOf(h, prior_filter, j)))->model();
+    return a->LogBDScore(*b);
+}
+
 /**** rollouts (RBAPOUCT::rollout, RBAPOUCT.cpp:295-323) ****/
 // Mirrors what selectAction does around a simulation (RBAPOUCT.cpp:86-106): KeepCounts, the
 // particle is not copied, its domain state is set to start_state and restored afterwards.

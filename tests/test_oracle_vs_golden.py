@@ -188,3 +188,18 @@ def test_reinvigoration_replay(name):
     assert done >= 1
     np.testing.assert_array_equal(b.counts, g["reinv/final_b_counts"])
     np.testing.assert_array_equal(fc.counts, g["reinv/final_fc_counts"])
+
+
+@pytest.mark.parametrize("name", ["ftiger", "sysadmin3", "sysadmin", "gridworld3_fba"])
+def test_log_bd_score_bit_exact(name):
+    """orc_log_bd_score against BABNModel::LogBDScore of the unmodified reference
+    (oracle/gen_bd_score.py -> tests/golden/bd_score.npz): same libm, same accumulation order,
+    identical doubles."""
+    import os
+    import pyoracle as O
+    z = np.load(os.path.join(G.GOLDEN_DIR, "bd_score.npz"))
+    g = G.load(name)
+    m = O.Model(g.desc)
+    for i in range(len(z[name + "/score"])):
+        got = O.log_bd_score(m, z[name + "/t_par"], z[name + "/o_par"], z[name + "/counts"][i], z[name + "/prior"])
+        assert got == z[name + "/score"][i], (name, i, got, z[name + "/score"][i])
