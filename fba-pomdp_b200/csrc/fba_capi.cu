@@ -2111,6 +2111,32 @@ extern "C" int fba_tree_create(fba_ctx* ctx, fba_model* m, int64_t max_simulatio
     return FBA_OK;
 }
 
+// The final choice (RBAPOUCT.cpp:112: selectChanceNodeUCB without the exploration term): best mean
+// return, random among ties (RBAPOUCT.cpp:204). An action no simulation has returned from has no
+// estimate: the reference gives it q = 0, which only matters there when n_simulations < A because its
+// sequential search tries every root action first — the ticket scheme of tree_ucb guarantees the same
+// here — so such actions are left out unless nothing was visited at all.
+template<class G>
+static int tree_final_choice(const TreeStat* root, int A, G& g, double* q_out, int64_t* visits_out)
+{
+    bool any = false;
+    for (int a = 0; a < A; ++a) any = any || root[a].n_done > 0;
+    double best = -1.7976931348623157e308;
+    int pick = 0, ties = 0;
+    for (int a = 0; a < A; ++a)
+    {
+        int const n    = root[a].n_done;
+        double const v = n > 0 ? root[a].q_sum / (double)n : 0.0;
+        if (q_out) q_out[a] = v;
+        if (visits_out) visits_out[a] = n;
+        if (any && n == 0) continue;
+        if (v > best) best = v, pick = a, ties = 1;
+        else if (v == best && draw_k(g, (uint32_t)++ties) == 0)
+            pick = a;
+    }
+    return pick;
+}
+
 extern "C" int fba_tree_search(fba_tree* t, fba_belief* b, int64_t n_sims, int32_t depth, double u, double discount,
                                int32_t wave, fba_rng* rng, int32_t* action, double* q_out, int64_t* visits_out)
 {
@@ -2185,21 +2211,11 @@ extern "C" int fba_tree_search(fba_tree* t, fba_belief* b, int64_t n_sims, int32
     std::vector<TreeStat> root(A);
     CU(ctx, cudaMemcpyAsync(root.data(), t->stat + (size_t)t->table * A, A * sizeof(TreeStat), cudaMemcpyDeviceToHost,
                             ctx->stream));
+    CU(ctx, cudaMemcpyAsync(ctx->h_flag, t->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
-    // the final choice: best mean return, no exploration term, random among ties (RBAPOUCT.cpp:204)
+    REQUIRE(ctx, *ctx->h_flag == 0, "tree_search: the node table overflowed");
     PhiloxRng g(rng->seed, 0, rng->offset++);
-    double best = -1.7976931348623157e308;
-    int pick = 0, ties = 0;
-    for (int a = 0; a < D.A; ++a)
-    {
-        double const v = root[a].n_done > 0 ? root[a].q_sum / (double)root[a].n_done : 0.0;
-        if (q_out) q_out[a] = v;
-        if (visits_out) visits_out[a] = root[a].n_done;
-        if (v > best) best = v, pick = a, ties = 1;
-        else if (v == best && draw_k(g, (uint32_t)++ties) == 0)
-            pick = a;
-    }
-    *action = pick;
+    *action = tree_final_choice(root.data(), D.A, g, q_out, visits_out);
     return FBA_OK;
 }
 
@@ -2569,25 +2585,16 @@ extern "C" int fba_runs_plan(fba_runs* r, int64_t n_sims, const int32_t* depth, 
     std::vector<TreeStat> roots((size_t)r->R * A);
     CU(ctx, cudaMemcpyAsync(roots.data(), r->stat + (size_t)table * A, roots.size() * sizeof(TreeStat),
                             cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(ctx->h_flag, r->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    REQUIRE(ctx, *ctx->h_flag == 0, "runs_plan: the node table overflowed");
     unsigned long long const pick_offset = rng->offset++;
     for (int k = 0; k < r->R; ++k)
     {
         if (active && !active[k]) continue;
         PhiloxRng g(rng->seed + (unsigned long long)k, 0, pick_offset);
-        double best = -1.7976931348623157e308;
-        int pick = 0, ties = 0;
-        for (int a = 0; a < D.A; ++a)
-        {
-            int const n    = roots[(size_t)k * A + a].n_done;
-            double const v = n > 0 ? roots[(size_t)k * A + a].q_sum / (double)n : 0.0;
-            if (q_out) q_out[(size_t)k * A + a] = v;
-            if (visits_out) visits_out[(size_t)k * A + a] = n;
-            if (v > best) best = v, pick = a, ties = 1;
-            else if (v == best && draw_k(g, (uint32_t)++ties) == 0)
-                pick = a;
-        }
-        action[k] = pick;
+        action[k] = tree_final_choice(roots.data() + (size_t)k * A, D.A, g, q_out ? q_out + (size_t)k * A : nullptr,
+                                      visits_out ? visits_out + (size_t)k * A : nullptr);
     }
     return FBA_OK;
 }

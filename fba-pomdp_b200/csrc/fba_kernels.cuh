@@ -1345,40 +1345,93 @@ __device__ __forceinline__ unsigned int tree_hash(unsigned long long k)
     return (unsigned int)k;
 }
 
-// argmax_a q(a) + u sqrt(log(visits + 1) / n_sel(a)), +inf for n_sel = 0 (RBAPOUCT.cpp:349-357);
-// ties broken uniformly (RBAPOUCT.cpp:204) with one draw per tie
-template<class R>
-__device__ __forceinline__ int tree_ucb(const TreeArgs& T, int node, int A, R& g)
+// Action choice in a tree node (RBAPOUCT::selectChanceNodeUCB, RBAPOUCT.cpp:162-205, with the table of
+// RBAPOUCT.cpp:349-357): argmax_a q(a) + u sqrt(log(m + 1) / n(a)), +inf for n = 0, ties broken uniformly.
+// The reference is sequential: visitor number m of a node sees the statistics of visitors 0..m-1. Here the
+// simulations of a wave run concurrently, so a visitor first takes an atomic TICKET m = visits[node]++:
+//   * tickets 0..A-1 take the A untried actions, one each, in a random order that is a function of the node
+//     (sampling without replacement = what "uniformly among the +inf candidates" does sequentially) — no two
+//     concurrent visitors can both see the same action as untried, whatever the thread timing;
+//   * later tickets read the statistics through L2 (__ldcg: atomics land in L2, an L1 line could hold a
+//     stale snapshot for the whole kernel and herd every visitor of one SM onto one action) and maximise
+//     the bound with m = their ticket; n(a) counts selections incl. simulations still in flight (virtual
+//     visits), q(a) is the mean of the returns backed up so far (0 while there is none, like an
+//     unvisited ChanceNode's qValue()).
+// With one simulation per wave this is the reference's algorithm exactly. (q_sum, n_done) are two atomics:
+// a concurrent reader may see a mean that is off by one in-flight sample — transient, bounded, and absent
+// when wave = 1.
+__device__ __forceinline__ unsigned long long tree_mix(unsigned long long z)
 {
-    double const lg = log1p((double)T.visits[node]);
-    double best     = -1.7976931348623157e308;
-    int pick = 0, ties = 0;
-    const int4* row = reinterpret_cast<const int4*>(T.stat + (long long)node * A);
-    // four actions' statistics per round trip. Plain (L1-cached) loads: a line may be a little stale
-    // inside one wave, which only makes concurrent simulations slightly more independent; across waves
-    // (kernel launches) L1 starts clean, so a sequential search (one simulation per wave) is exact
-    for (int a0 = 0; a0 < A; a0 += 4)
+    z += 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+
+// k-th element of a random permutation of 0..A-1 keyed by `key` (every visitor of a node derives the
+// same permutation): sampling without replacement over a bitmask for A <= 32, a random affine map otherwise
+__device__ __forceinline__ int tree_untried(unsigned long long key, int A, int k)
+{
+    if (A <= 32)
     {
-        int4 raw[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (a0 + k < A) raw[k] = row[a0 + k];
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
+        unsigned int left = (A == 32) ? 0xffffffffu : ((1u << A) - 1u);
+        int pick = 0;
+        for (int i = 0; i <= k; ++i)
         {
-            int const a = a0 + k;
-            if (a >= A) break;
-            int const ns = raw[k].x, nd = raw[k].y;
-            double const qs = __hiloint2double(raw[k].w, raw[k].z);
-            double v;
-            if (ns == 0) v = 1.7976931348623157e308;
-            else
-                v = ((nd > 0) ? qs / (double)nd : 0.0) + T.u * sqrt(lg / (double)ns);
-            if (v > best) best = v, pick = a, ties = 1;
-            else if (v == best && draw_k(g, (uint32_t)++ties) == 0)
-                pick = a;
+            key = tree_mix(key);
+            unsigned int const r = (unsigned int)(((key >> 32) * (unsigned long long)(A - i)) >> 32);
+            pick = (int)__fns(left, 0, (int)r + 1);
+            left &= ~(1u << pick);
+        }
+        return pick;
+    }
+    key = tree_mix(key);
+    int const off = (int)((key >> 33) % (unsigned long long)A);
+    int step      = 1 + (int)((tree_mix(key) >> 33) % (unsigned long long)(A - 1));
+    for (;; ++step)
+    { // smallest step >= the drawn one that is coprime with A
+        int x = A, y = step % A;
+        while (y) { int const z = x % y; x = y, y = z; }
+        if (x == 1) break;
+    }
+    return (int)(((long long)off + (long long)k * (step % A)) % A);
+}
+
+template<class R>
+__device__ __forceinline__ int tree_ucb(const TreeArgs& T, int node, int A, R& g, unsigned long long perm_key)
+{
+    int const m = atomicAdd(&T.visits[node], 1); // ticket = visits before this one (ActionNode::visited())
+    int pick    = 0;
+    if (m < A) pick = tree_untried(perm_key, A, m);
+    else
+    {
+        double const lg = log1p((double)m);
+        double best     = -1.7976931348623157e308;
+        int ties        = 0;
+        const int4* row = reinterpret_cast<const int4*>(T.stat + (long long)node * A);
+        // four actions' statistics per round trip
+        for (int a0 = 0; a0 < A; a0 += 4)
+        {
+            int4 raw[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (a0 + k < A) raw[k] = __ldcg(row + a0 + k);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+            {
+                int const a = a0 + k;
+                if (a >= A) break;
+                // every action has been handed out (m >= A); its holder's increment may still be on its way
+                int const ns = max(raw[k].x, 1), nd = raw[k].y;
+                double const qs = __hiloint2double(raw[k].w, raw[k].z);
+                double const v  = ((nd > 0) ? qs / (double)nd : 0.0) + T.u * sqrt(lg / (double)ns);
+                if (v > best) best = v, pick = a, ties = 1;
+                else if (v == best && draw_k(g, (uint32_t)++ties) == 0)
+                    pick = a;
+            }
         }
     }
+    atomicAdd(&T.stat[(long long)node * A + pick].n_sel, 1);
     return pick;
 }
 
@@ -1401,6 +1454,10 @@ __global__ void __launch_bounds__(kThreads)
         if (T.depth_r) depth = T.depth_r[r];
     }
     auto g = RngOf<false>::make(ra, sim);
+    // the order in which a node's first visitors try its actions: a function of (seed, search, the
+    // action-observation path from the root to the node) — the same for every visitor of the node and
+    // independent of where the hash table put it
+    unsigned long long perm_key = tree_mix(ra.seed ^ (ra.offset * 0xd1342543de82ef95ull));
     // root particle: Belief::sample()
     long long p;
     if (T.cdf)
@@ -1434,9 +1491,7 @@ __global__ void __launch_bounds__(kThreads)
         int a;
         if (in_tree)
         {
-            a = tree_ucb(T, node, M.A, g);
-            atomicAdd(&T.visits[node], 1);
-            atomicAdd(&T.stat[(long long)node * M.A + a].n_sel, 1);
+            a = tree_ucb(T, node, M.A, g, perm_key);
         } else
             a = random_action(M, g);
         int o, s2;
@@ -1492,7 +1547,10 @@ __global__ void __launch_bounds__(kThreads)
             // the remaining steps of this loop
             if (created || child < 0) in_tree = false;
             else
-                node = child;
+            {
+                node     = child;
+                perm_key = tree_mix(perm_key ^ (key & 0xffffffffull));
+            }
         }
     }
     // back up: ret = r + discount * delayed (RBAPOUCT.cpp:271-272)
