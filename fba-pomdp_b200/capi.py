@@ -17,8 +17,10 @@ START_CONST, START_BOOL, START_UNIFORM_INT, START_SLOW2, START_CATEGORICAL = ran
 MUT_FACTORED_TIGER, MUT_COLLISION_AVOIDANCE, MUT_SYSADMIN, MUT_GRIDWORLD = range(4)
 RNG_REPLAY, RNG_PHILOX = 0, 1
 
+P2P_BLOB_BYTES = 320  # FBA_P2P_BLOB_BYTES
+
 # every symbol include/fba_pomdp_b200.h declares (tests check the library exports all of them)
-ABI_VERSION = 10  # must equal FBA_ABI_VERSION in include/fba_pomdp_b200.h
+ABI_VERSION = 11  # must equal FBA_ABI_VERSION in include/fba_pomdp_b200.h
 
 SYMBOLS = [
     "fba_abi_version", "fba_ctx_create", "fba_ctx_destroy", "fba_last_error", "fba_ctx_stream", "fba_ctx_synchronize",
@@ -33,7 +35,8 @@ SYMBOLS = [
     "fba_belief_sample_batch", "fba_belief_gather_states", "fba_step_batch", "fba_belief_propose",
     "fba_belief_normalize", "fba_belief_resample_shard", "fba_belief_resample_stats",
     "fba_belief_shard_resample", "fba_belief_shard_resample_async", "fba_belief_shard_plan",
-    "fba_belief_ipc_handle", "fba_belief_ipc_open", "fba_belief_shard_resample_p2p", "fba_belief_import_p2p",
+    "fba_belief_p2p_export", "fba_belief_p2p_open", "fba_belief_sharded_update", "fba_belief_p2p_timeouts",
+    "fba_belief_p2p_set_timeout",
     "fba_belief_dropped_records", "fba_belief_reserve_export", "fba_belief_import_from", "fba_belief_export_count",
     "fba_belief_export_ptr", "fba_belief_import_ptr", "fba_belief_record_bytes", "fba_belief_import",
     "fba_belief_counts_ptr", "fba_belief_state_ptr", "fba_belief_weight_ptr",
@@ -118,10 +121,11 @@ def lib():
             "fba_belief_shard_resample": (C.c_int, [vp, vp, i32, i32, dbl, vp, vp, vp]),
             "fba_belief_shard_resample_async": (C.c_int, [vp, vp, i32, i32, dbl, vp]),
             "fba_belief_shard_plan": (C.c_int, [vp, vp, i32, i32, dbl, vp, vp]),
-            "fba_belief_ipc_handle": (C.c_int, [vp, i64, vp]),
-            "fba_belief_ipc_open": (C.c_int, [vp, vp, i32, i32]),
-            "fba_belief_shard_resample_p2p": (C.c_int, [vp, vp, dbl, vp]),
-            "fba_belief_import_p2p": (C.c_int, [vp]),
+            "fba_belief_p2p_export": (C.c_int, [vp, vp]),
+            "fba_belief_p2p_open": (C.c_int, [vp, vp, i32, i32]),
+            "fba_belief_sharded_update": (C.c_int, [vp, i32, i32, vp, dbl, vp]),
+            "fba_belief_p2p_timeouts": (i64, [vp]),
+            "fba_belief_p2p_set_timeout": (C.c_int, [vp, dbl]),
             "fba_belief_dropped_records": (i64, [vp]),
             "fba_belief_reserve_export": (C.c_int, [vp, i64]),
             "fba_belief_import_from": (C.c_int, [vp, vp, i64]),

@@ -96,12 +96,14 @@ struct fba_belief
     long long* stats = nullptr; // [0] copies made by in-place resamples, [1] number of resamples,
                                 // [2] surplus records dropped because the export buffer was full
     long long src_cap = 0;
-    // peer-to-peer exchange
+    // peer-to-peer exchange (fba_belief_p2p_*): control block [P2PCtrl header | dead-slot list], mapped by peers
     PeerTable peers{};
     bool peers_open = false;
     int p2p_ranks = 0, p2p_rank = 0;
     long long* d_plan = nullptr;
-    std::vector<void*> opened; // cudaIpcOpenMemHandle'd pointers
+    char* p2p_block   = nullptr;         // owns b->totals and b->dead once allocated
+    unsigned long long* d_step = nullptr; // step stamp of the sharded updates
+    std::vector<void*> opened; // cudaIpcOpenMemHandle'd base pointers
     long long* d_quota = nullptr; // device-side offspring quota (fba_belief_shard_resample_async)
     int2* tile_pairs = nullptr;
     bool inplace_last = false; // the last shard resample ran in place (import goes to dead slots)
@@ -800,7 +802,11 @@ extern "C" void fba_belief_destroy(fba_belief* b)
     cudaFree(b->d_plan);
     cudaFree(b->att_tiles);
     cudaFree(b->att_rec), cudaFree(b->d_total), cudaFree(b->xport), cudaFree(b->import_buf);
-    cudaFree(b->src_of), cudaFree(b->d_quota), cudaFree(b->stats), cudaFree(b->noff), cudaFree(b->escan), cudaFree(b->dead), cudaFree(b->totals), cudaFree(b->tile_pairs);
+    cudaFree(b->src_of), cudaFree(b->d_quota), cudaFree(b->stats), cudaFree(b->noff), cudaFree(b->escan), cudaFree(b->tile_pairs);
+    if (b->p2p_block) cudaFree(b->p2p_block); // b->dead and b->totals live inside it
+    else
+        cudaFree(b->dead), cudaFree(b->totals);
+    cudaFree(b->d_step);
     delete b;
 }
 
@@ -1297,11 +1303,18 @@ static int resample_inplace(fba_belief* b, fba_rng* rng, long long n_out, const 
     CU(ctx, cudaMemsetAsync(b->src_of, 0xFF, (size_t)b->src_cap * sizeof(int), ctx->stream));
     LAUNCH(ctx, k_offspring_apply, n_tiles, kThreads, b->noff, b->N, b->tile_pairs, b->dead, b->escan, b->src_of,
            b->src_cap);
+    // peer-to-peer: tell every rank that this rank's dead-slot list is complete (senders wait for it)
+    if (p2p) LAUNCH(ctx, k_p2p_signal, 1, 32, b->peers, b->p2p_ranks, b->p2p_rank, 0, b->d_step);
     LAUNCH(ctx, k_copy_inplace, stream_grid(ctx, b->N), kThreads, b->counts[b->cur], b->stride,
            b->state[b->cur], b->sid[b->cur], b->m->d_sizes, b->escan, b->src_of, b->N, b->dead, b->totals,
            b->xport, rb, b->xport_cap, b->stats, b->src_cap, p2p ? b->d_plan : (const long long*)nullptr,
-           b->p2p_ranks, b->p2p_rank, b->peers, b->delta_cap > 0 ? 1 : 0);
+           b->p2p_ranks, b->p2p_rank, b->peers, b->delta_cap > 0 ? 1 : 0, b->d_step);
+    // ... and that this rank's peer stores are done; wait for the ranks that ship records here
+    if (p2p) LAUNCH(ctx, k_p2p_signal, 1, 32, b->peers, b->p2p_ranks, b->p2p_rank, 1, b->d_step);
     LAUNCH(ctx, k_fill, blocks_for(b->N), kThreads, b->w, b->N, 1.0 / (double)b->N);
+    if (p2p)
+        LAUNCH(ctx, k_p2p_wait_landed, 1, 32, (const P2PCtrl*)b->p2p_block, b->p2p_ranks, b->p2p_rank, b->d_plan,
+               b->d_step, b->peers.timeout_ns, b->stats);
     b->total_weight = 1.0;
     b->suffix_valid = b->cdf_valid = false;
     b->inplace_last = true;
@@ -2770,62 +2783,132 @@ extern "C" int fba_belief_import_from(fba_belief* b, const void* records_device,
     CU(ctx, cudaSetDevice(ctx->device));
     LAUNCH(ctx, k_import_inplace, stream_grid(ctx, n_records), kThreads, b->counts[b->cur], b->stride,
            b->state[b->cur], b->sid[b->cur], b->dead, b->totals, b->imported, (long long)n_records,
-           (const char*)records_device, fba_belief_record_bytes(b), (const long long*)nullptr, 0, 0);
+           (const char*)records_device, fba_belief_record_bytes(b));
     b->imported += n_records;
     b->local_kept += n_records;
     return FBA_OK;
 }
 
-// ---- peer-to-peer exchange over NVLink: surplus records are stored by k_copy_inplace directly
-//      into the destination GPU's import buffer (CUDA IPC mapping); no host-visible plan ----
+// ---- peer-to-peer sharded update over NVLink / NVSwitch (one process per GPU, one box) -----------
+// No host, no NCCL on the update path: shard totals, "dead list ready" and "records landed" travel as
+// step-stamped flags through peer-mapped control blocks (fba_kernels.cuh: P2PCtrl), and the surplus
+// blocks of an over-quota shard are stored by k_copy_inplace straight into dead slots of the
+// destination GPU's particle array.
 
-// Allocates this rank's import buffer (cap_records) and returns its 64-byte CUDA IPC handle.
-extern "C" int fba_belief_ipc_handle(fba_belief* b, int64_t cap_records, void* handle64)
+// base pointer + offset of a device pointer inside its allocation (IPC handles name allocations)
+static int ipc_describe(fba_ctx* ctx, const void* p, unsigned char* out72)
 {
-    if (!b || !handle64 || cap_records < 1) return FBA_ERR_INVALID;
-    fba_ctx* ctx = b->ctx;
-    CU(ctx, cudaSetDevice(ctx->device));
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-    if (b->import_cap < cap_records)
+    typedef int (*range_fn)(unsigned long long*, size_t*, unsigned long long);
+    static range_fn get_range = nullptr;
+    if (!get_range)
     {
-        cudaFree(b->import_buf);
-        b->import_buf = nullptr;
-        b->import_cap = 0;
-        CU(ctx, cudaMalloc(&b->import_buf, (size_t)cap_records * fba_belief_record_bytes(b)));
-        b->import_cap = cap_records;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        CU(ctx, cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr));
+        REQUIRE(ctx, fn && qr == cudaDriverEntryPointSuccess, "p2p: cuMemGetAddressRange is not available");
+        get_range = (range_fn)fn;
     }
+    unsigned long long base = 0;
+    size_t size             = 0;
+    REQUIRE(ctx, get_range(&base, &size, (unsigned long long)(uintptr_t)p) == 0, "p2p: cuMemGetAddressRange failed");
     cudaIpcMemHandle_t hnd;
-    CU(ctx, cudaIpcGetMemHandle(&hnd, b->import_buf));
-    memcpy(handle64, &hnd, 64);
+    CU(ctx, cudaIpcGetMemHandle(&hnd, (void*)(uintptr_t)base));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(out72, &hnd, 64);
+    long long const off = (long long)((unsigned long long)(uintptr_t)p - base);
+    memcpy(out72 + 64, &off, 8);
     return FBA_OK;
 }
 
-// handles: n_ranks x 64 bytes (all-gathered); maps every peer's import buffer into this process
-extern "C" int fba_belief_ipc_open(fba_belief* b, const void* handles, int32_t n_ranks, int32_t rank)
+// Allocates this rank's control block (the in-place resampler's dead list and totals move into it)
+// and writes the FBA_P2P_BLOB_BYTES blob peers need to map it and the particle arrays.
+extern "C" int fba_belief_p2p_export(fba_belief* b, void* blob)
 {
-    if (!b || !handles) return FBA_ERR_INVALID;
+    if (!b || !blob) return FBA_ERR_INVALID;
     fba_ctx* ctx = b->ctx;
-    REQUIRE(ctx, n_ranks >= 1 && n_ranks <= kMaxRanks && rank >= 0 && rank < n_ranks, "ipc_open: bad rank");
-    REQUIRE(ctx, b->import_buf, "ipc_open: call fba_belief_ipc_handle first");
+    REQUIRE(ctx, b->weighted, "p2p: importance-sampling (weighted) beliefs only");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!b->p2p_block)
+    {
+        size_t const bytes = (size_t)kP2PDeadOffset + (size_t)b->N * sizeof(int);
+        char* blk          = nullptr;
+        CU(ctx, cudaMalloc(&blk, bytes));
+        CU(ctx, cudaMemset(blk, 0, bytes));
+        cudaFree(b->dead), cudaFree(b->totals);
+        b->p2p_block = blk;
+        b->totals    = reinterpret_cast<P2PCtrl*>(blk)->totals;
+        b->dead      = reinterpret_cast<int*>(blk + kP2PDeadOffset);
+    }
+    if (!b->d_step)
+    {
+        CU(ctx, cudaMalloc(&b->d_step, sizeof(unsigned long long)));
+        CU(ctx, cudaMemset(b->d_step, 0, sizeof(unsigned long long)));
+    }
+    unsigned char* out = (unsigned char*)blob;
+    memset(out, 0, FBA_P2P_BLOB_BYTES);
+    int rc;
+    if ((rc = ipc_describe(ctx, b->p2p_block, out))) return rc;
+    if ((rc = ipc_describe(ctx, b->counts[b->cur], out + 72))) return rc;
+    if ((rc = ipc_describe(ctx, b->state[b->cur], out + 144))) return rc;
+    if ((rc = ipc_describe(ctx, b->sid[b->cur], out + 216))) return rc;
+    long long const shape[2] = {b->N, b->stride};
+    memcpy(out + 288, shape, 16);
+    return FBA_OK;
+}
+
+// blobs: n_ranks x FBA_P2P_BLOB_BYTES (all-gathered by the host, once); maps every peer's control
+// block and particle arrays into this process
+extern "C" int fba_belief_p2p_open(fba_belief* b, const void* blobs, int32_t n_ranks, int32_t rank)
+{
+    if (!b || !blobs) return FBA_ERR_INVALID;
+    fba_ctx* ctx = b->ctx;
+    REQUIRE(ctx, n_ranks >= 1 && n_ranks <= kMaxRanks && rank >= 0 && rank < n_ranks, "p2p_open: bad rank");
+    REQUIRE(ctx, b->p2p_block, "p2p_open: call fba_belief_p2p_export first");
     CU(ctx, cudaSetDevice(ctx->device));
     for (auto p : b->opened) cudaIpcCloseMemHandle(p); // a second call re-maps: drop the old mappings
     b->opened.clear();
     b->peers_open = false;
+    std::map<std::string, void*> mapped; // one mapping per peer allocation
     for (int g = 0; g < n_ranks; ++g)
     {
+        const unsigned char* blob = (const unsigned char*)blobs + (size_t)g * FBA_P2P_BLOB_BYTES;
+        long long shape[2];
+        memcpy(shape, blob + 288, 16);
+        REQUIRE(ctx, shape[0] == b->N && shape[1] == b->stride, "p2p_open: every shard must have the same size and stride");
         if (g == rank)
         {
-            b->peers.import_buf[g] = b->import_buf;
+            b->peers.ctrl[g]   = reinterpret_cast<P2PCtrl*>(b->p2p_block);
+            b->peers.counts[g] = b->counts[b->cur];
+            b->peers.state[g]  = b->state[b->cur];
+            b->peers.sid[g]    = b->sid[b->cur];
             continue;
         }
-        cudaIpcMemHandle_t hnd;
-        memcpy(&hnd, (const char*)handles + (size_t)g * 64, 64);
-        void* p = nullptr;
-        CU(ctx, cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess));
-        b->opened.push_back(p);
-        b->peers.import_buf[g] = (char*)p;
+        void* ptr[4];
+        for (int k = 0; k < 4; ++k)
+        {
+            std::string const key((const char*)blob + 72 * k, 64);
+            auto it = mapped.find(key);
+            void* base = nullptr;
+            if (it != mapped.end()) base = it->second;
+            else
+            {
+                cudaIpcMemHandle_t hnd;
+                memcpy(&hnd, blob + 72 * k, 64);
+                CU(ctx, cudaIpcOpenMemHandle(&base, hnd, cudaIpcMemLazyEnablePeerAccess));
+                b->opened.push_back(base);
+                mapped[key] = base;
+            }
+            long long off;
+            memcpy(&off, blob + 72 * k + 64, 8);
+            ptr[k] = (char*)base + off;
+        }
+        b->peers.ctrl[g]   = (P2PCtrl*)ptr[0];
+        b->peers.counts[g] = (float*)ptr[1];
+        b->peers.state[g]  = (int*)ptr[2];
+        b->peers.sid[g]    = (int*)ptr[3];
     }
-    b->peers.cap = b->import_cap;
+    b->peers.timeout_ns = 20ll * 1000 * 1000 * 1000;
     if (!b->d_plan) CU(ctx, cudaMalloc(&b->d_plan, (size_t)kMaxRanks * kMaxRanks * sizeof(long long)));
     b->p2p_ranks  = n_ranks;
     b->p2p_rank   = rank;
@@ -2833,39 +2916,57 @@ extern "C" int fba_belief_ipc_open(fba_belief* b, const void* handles, int32_t n
     return FBA_OK;
 }
 
-// Phases 2+3 with the plan on device and the surplus stored into peer memory. Asynchronous, and the
-// host never needs the totals. Follow with a cross-rank barrier on the same stream (any small
-// collective), then fba_belief_import_p2p.
-extern "C" int fba_belief_shard_resample_p2p(fba_belief* b, const double* totals_device, double u, fba_rng* rng)
+// One global importance-sampling update + resample of a sharded belief, everything enqueued on the
+// context's stream by this one call: propose, shard total, [totals to peers / plan], normalise by the
+// global total, in-place systematic resample to this shard's quota, surplus blocks stored into the
+// destination GPUs' dead slots, [landed stamps]. u in [0,1) must be the same on every rank.
+// likelihood != NULL: the GLOBAL un-normalised weight total (sum over all shards) is copied back (8
+// bytes, one stream synchronisation); NULL: fully asynchronous.
+extern "C" int fba_belief_sharded_update(fba_belief* b, int32_t a, int32_t o, fba_rng* rng, double u, double* likelihood)
 {
-    if (!b || !totals_device || !rng) return FBA_ERR_INVALID;
+    if (!b || !rng) return FBA_ERR_INVALID;
     fba_ctx* ctx = b->ctx;
-    REQUIRE(ctx, b->peers_open, "shard_resample_p2p: call fba_belief_ipc_open first");
+    REQUIRE(ctx, b->peers_open, "sharded_update: call fba_belief_p2p_open first");
     REQUIRE(ctx, rng->mode == FBA_RNG_PHILOX, "sharded beliefs run in PHILOX mode");
-    REQUIRE(ctx, ctx->inplace_resample, "shard_resample_p2p needs the in-place resampler");
-    REQUIRE(ctx, u >= 0.0 && u < 1.0, "shard_resample_p2p: u must be in [0,1)");
-    CU(ctx, cudaSetDevice(ctx->device));
+    REQUIRE(ctx, ctx->inplace_resample, "sharded_update needs the in-place resampler");
+    REQUIRE(ctx, u >= 0.0 && u < 1.0, "sharded_update: u must be in [0,1)");
+    REQUIRE(ctx, b->peers.counts[b->p2p_rank] == b->counts[b->cur], "sharded_update: the particle buffer changed since p2p_export");
+    int rc = propose(b, a, o, rng, 0);
+    if (rc) return rc;
     int const n_tiles = (int)((b->N + kTile - 1) / kTile);
-    LAUNCH(ctx, k_shard_plan, 1, 1, totals_device, b->p2p_ranks, b->p2p_rank, u, b->N, b->scal + 2, b->d_quota,
-           b->d_plan);
+    LAUNCH(ctx, k_tile_sums, n_tiles, kThreads, b->w, b->N, b->tile);
+    LAUNCH(ctx, k_scan_tile_sums, 1, kThreads, b->tile, n_tiles, b->scal);
+    LAUNCH(ctx, k_p2p_plan, 1, 32, reinterpret_cast<P2PCtrl*>(b->p2p_block), b->peers, b->p2p_ranks, b->p2p_rank,
+           (const double*)b->scal, u, b->N, b->scal + 2, b->d_quota, b->d_plan, b->d_step, b->stats);
     LAUNCH(ctx, k_scale_and_scan, n_tiles, kThreads, b->w, b->N, b->tile, (const double*)(b->scal + 2), 1.0,
            b->aux);
     b->cdf_valid    = true;
     b->suffix_valid = false;
-    return resample_inplace(b, rng, 0, b->d_quota, true);
+    if ((rc = resample_inplace(b, rng, 0, b->d_quota, true))) return rc;
+    if (likelihood)
+    {
+        CU(ctx, cudaMemcpyAsync(ctx->h_scal, b->scal + 2, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        *likelihood = ctx->h_scal[0];
+    }
+    return FBA_OK;
 }
 
-extern "C" int fba_belief_import_p2p(fba_belief* b)
+// waits (cross-rank) that timed out since creation: 0 in a healthy run. Synchronises the stream.
+extern "C" int64_t fba_belief_p2p_timeouts(fba_belief* b)
 {
-    if (!b) return FBA_ERR_INVALID;
-    fba_ctx* ctx = b->ctx;
-    REQUIRE(ctx, b->peers_open && b->inplace_last, "import_p2p: needs fba_belief_shard_resample_p2p first");
-    CU(ctx, cudaSetDevice(ctx->device));
-    // the count is read from the device plan; the grid covers the worst case with a grid-stride loop
-    LAUNCH(ctx, k_import_inplace, stream_grid(ctx, std::min<long long>(b->import_cap, 65536)), kThreads,
-           b->counts[b->cur], b->stride, b->state[b->cur], b->sid[b->cur], b->dead, b->totals, 0ll,
-           b->import_cap, b->import_buf, fba_belief_record_bytes(b), (const long long*)b->d_plan, b->p2p_ranks,
-           b->p2p_rank);
+    if (!b) return -1;
+    long long h[4] = {0, 0, 0, 0};
+    cudaSetDevice(b->ctx->device);
+    if (cudaMemcpyAsync(h, b->stats, sizeof(h), cudaMemcpyDeviceToHost, b->ctx->stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(b->ctx->stream) != cudaSuccess) return -1;
+    return h[3];
+}
+
+extern "C" int fba_belief_p2p_set_timeout(fba_belief* b, double seconds)
+{
+    if (!b || !(seconds > 0)) return FBA_ERR_INVALID;
+    b->peers.timeout_ns = (long long)(seconds * 1e9);
     return FBA_OK;
 }
 
@@ -3049,7 +3150,7 @@ extern "C" int fba_belief_import(fba_belief* b, int64_t n_records)
     {
         LAUNCH(ctx, k_import_inplace, stream_grid(ctx, n_records), kThreads, b->counts[b->cur], b->stride,
                b->state[b->cur], b->sid[b->cur], b->dead, b->totals, 0ll, (long long)n_records, b->import_buf,
-               fba_belief_record_bytes(b), (const long long*)nullptr, 0, 0);
+               fba_belief_record_bytes(b));
         b->local_kept += n_records;
         return FBA_OK; // asynchronous
     }

@@ -681,11 +681,156 @@ __device__ __forceinline__ void p2p_destination(const long long* __restrict__ pl
     dst_rank = -1, dst_off = 0;
 }
 
+// ---- cross-GPU synchronisation through peer-mapped memory (NVLink / NVSwitch) ----
+// Every rank owns one control block in its HBM, mapped by every peer (CUDA IPC). Ranks signal each
+// other by storing a monotonically increasing STEP STAMP with release semantics at system scope
+// into the waiter's own block, and wait by polling their OWN memory with acquire loads — no host,
+// no NCCL, no cross-GPU polling traffic.
+struct P2PCtrl
+{
+    double box[2][kMaxRanks];                  // [step parity][sender]: shard weight totals
+    unsigned long long total_flag[kMaxRanks];  // [sender]: its total for that step is in box
+    unsigned long long dead_flag[kMaxRanks];   // [owner]: that rank's dead-slot list of that step is complete
+    unsigned long long landed_flag[kMaxRanks]; // [sender]: its peer stores of that step are done
+    int totals[2];                             // this rank's (#dead, #extra) of the current resample
+    int pad[2];
+};
+constexpr long long kP2PDeadOffset = 4096; // the rank's dead-slot list (N ints) follows the header
+static_assert(sizeof(P2PCtrl) <= kP2PDeadOffset, "control block header");
+
 struct PeerTable
 {
-    char* import_buf[kMaxRanks]; // peer-mapped import buffers (own entry = local)
-    long long cap;               // records each holds
+    P2PCtrl* ctrl[kMaxRanks]; // own entry = local
+    float* counts[kMaxRanks];
+    int* state[kMaxRanks];
+    int* sid[kMaxRanks];
+    long long timeout_ns; // a wait longer than this is reported in stats[3] and abandoned (never hang the GPU)
 };
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_f64(double* p, double v)
+{
+    asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p)
+{
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ int ld_relaxed_sys_s32(const int* p)
+{
+    int v;
+    asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// polls OWN memory until the flag carries at least `step`; false after timeout_ns
+__device__ __forceinline__ bool p2p_wait(const unsigned long long* flag, unsigned long long step, long long timeout_ns)
+{
+    if (ld_acquire_sys(flag) >= step) return true;
+    unsigned long long const t0 = global_timer_ns();
+    while (ld_acquire_sys(flag) < step)
+    {
+        if ((long long)(global_timer_ns() - t0) > timeout_ns) return false;
+        __nanosleep(64);
+    }
+    return true;
+}
+
+// One warp. Replaces the all-gather of the shard totals AND k_shard_plan: lane g stores this rank's
+// total into rank g's box (value, then stamp with release), polls its own box for rank g's total,
+// and lane 0 computes quotas and the exchange plan — identical on every rank because it is a pure
+// function of the G totals and u. Advances the belief's step stamp.
+__global__ void k_p2p_plan(P2PCtrl* me, PeerTable peers, int n_ranks, int rank, const double* __restrict__ local_total,
+                           double u, long long n_local, double* __restrict__ out_total,
+                           long long* __restrict__ out_quota, long long* __restrict__ plan,
+                           unsigned long long* __restrict__ d_step, long long* __restrict__ stats)
+{
+    __shared__ double tot[kMaxRanks];
+    int const lane                = threadIdx.x;
+    unsigned long long const step = *d_step + 1;
+    __syncwarp();
+    if (lane == 0) *d_step = step;
+    if (lane < n_ranks)
+    {
+        P2PCtrl* peer = peers.ctrl[lane];
+        st_relaxed_sys_f64(&peer->box[step & 1][rank], *local_total);
+        st_release_sys(&peer->total_flag[rank], step);
+        if (!p2p_wait(&me->total_flag[lane], step, peers.timeout_ns)) atomicAdd((unsigned long long*)&stats[3], 1ull);
+        tot[lane] = ld_relaxed_sys_f64(&me->box[step & 1][lane]);
+    }
+    __syncwarp();
+    if (lane != 0) return;
+    double W = 0.0;
+    for (int g = 0; g < n_ranks; ++g) W += tot[g];
+    long long const n_total = n_local * n_ranks;
+    long long quota[kMaxRanks], surplus[kMaxRanks], deficit[kMaxRanks];
+    long long prev = 0;
+    double acc     = 0.0;
+    for (int g = 0; g < n_ranks; ++g)
+    {
+        acc += tot[g];
+        long long edge = (g == n_ranks - 1) ? n_total : (long long)floor(acc / W * (double)n_total - u + 1.0);
+        edge     = min(max(edge, prev), n_total);
+        quota[g] = (W > 0.0) ? edge - prev : n_local;
+        prev     = edge;
+        surplus[g] = max(0ll, quota[g] - n_local);
+        deficit[g] = max(0ll, n_local - quota[g]);
+    }
+    for (int k = 0; k < n_ranks * n_ranks; ++k) plan[k] = 0;
+    int h = 0;
+    for (int g = 0; g < n_ranks; ++g)
+        while (surplus[g] > 0)
+        {
+            while (h < n_ranks && deficit[h] == 0) ++h;
+            if (h >= n_ranks) break;
+            long long const k = min(surplus[g], deficit[h]);
+            plan[g * n_ranks + h] += k;
+            surplus[g] -= k, deficit[h] -= k;
+        }
+    out_total[0] = W;
+    out_quota[0] = quota[rank];
+}
+
+// One warp, after a kernel whose results peers are waiting for: lane g stamps this rank's flag in
+// rank g's control block. which = 0: dead-slot list complete, 1: peer stores done. The fence makes
+// everything the preceding kernels of this stream wrote (peer stores included) visible system-wide
+// before the stamp.
+__global__ void k_p2p_signal(PeerTable peers, int n_ranks, int rank, int which,
+                             const unsigned long long* __restrict__ d_step)
+{
+    int const lane = threadIdx.x;
+    if (lane >= n_ranks) return;
+    __threadfence_system();
+    P2PCtrl* peer = peers.ctrl[lane];
+    st_release_sys(which == 0 ? &peer->dead_flag[rank] : &peer->landed_flag[rank], *d_step);
+}
+
+// One warp: returns once every rank that ships records to this one has stamped "landed" for this
+// step — after this kernel the imported particles are in place.
+__global__ void k_p2p_wait_landed(const P2PCtrl* me, int n_ranks, int rank, const long long* __restrict__ plan,
+                                  const unsigned long long* __restrict__ d_step, long long timeout_ns,
+                                  long long* __restrict__ stats)
+{
+    int const lane = threadIdx.x;
+    if (lane >= n_ranks || plan[lane * n_ranks + rank] == 0) return;
+    if (!p2p_wait(&me->landed_flag[lane], *d_step, timeout_ns)) atomicAdd((unsigned long long*)&stats[3], 1ull);
+}
 
 __device__ __forceinline__ void offspring_body(int tile, const double* __restrict__ cdf, long long N,
                                                long long n_out, const RngArgs& ra, int* __restrict__ noff,
@@ -845,16 +990,8 @@ __global__ void __launch_bounds__(kThreads)
 __global__ void __launch_bounds__(kThreads)
     k_import_inplace(float* __restrict__ dst, long long stride, int* __restrict__ state, int* __restrict__ sid,
                      const int* __restrict__ dead_slot, const int* __restrict__ totals, long long slot_offset,
-                     long long n, const char* __restrict__ in, long long rec_bytes,
-                     const long long* __restrict__ plan, int n_ranks, int rank)
+                     long long n, const char* __restrict__ in, long long rec_bytes)
 {
-    if (plan)
-    { // peer-to-peer: the number of incoming records is this rank's column of the device plan
-        long long const cap = n; // by-value n carries the import buffer capacity in this mode
-        n = 0;
-        for (int g = 0; g < n_ranks; ++g) n += plan[g * n_ranks + rank];
-        n = min(n, cap);
-    }
     int const lane        = threadIdx.x & 31;
     long long const warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     long long const nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -881,7 +1018,8 @@ __global__ void __launch_bounds__(kThreads)
                    const int* __restrict__ extra_scan, const int* __restrict__ src_of, long long N,
                    const int* __restrict__ dead_slot, const int* __restrict__ totals, char* __restrict__ xport,
                    long long rec_bytes, long long xport_cap, long long* __restrict__ stats, long long src_cap,
-                   const long long* __restrict__ plan, int n_ranks, int rank, PeerTable peers, int delta)
+                   const long long* __restrict__ plan, int n_ranks, int rank, PeerTable peers, int delta,
+                   const unsigned long long* __restrict__ d_step)
 {
     long long const n_dead = totals[0];
     long long const n_fill = min(n_dead, (long long)totals[1]); // the rest (if any) is this shard's surplus
@@ -923,19 +1061,43 @@ __global__ void __launch_bounds__(kThreads)
             }
         } else
         {
-            char* rec = xport + (k - n_fill) * rec_bytes;
             if (plan)
-            { // peer-to-peer: store the record straight into the destination GPU's import buffer
+            { // peer-to-peer: the surplus block goes STRAIGHT into a dead slot of the destination GPU's
+              // particle array over NVLink — no staging buffer, no import pass, no capacity limit.
+              // Slot = the destination's dead list at (its own extras + records of lower-ranked
+              // senders + r), read from the destination's control block once that rank has stamped
+              // its list complete for this step.
                 int dst_rank;
                 long long dst_off;
                 p2p_destination(plan, n_ranks, rank, k - n_fill, dst_rank, dst_off);
-                if (dst_rank < 0 || dst_off >= peers.cap)
+                int slot = -1;
+                if (lane == 0 && dst_rank >= 0)
                 {
-                    if (lane == 0) atomicAdd((unsigned long long*)&stats[2], 1ull);
+                    if (p2p_wait(&peers.ctrl[rank]->dead_flag[dst_rank], *d_step, peers.timeout_ns))
+                    {
+                        const P2PCtrl* pc = peers.ctrl[dst_rank];
+                        int const extras  = ld_relaxed_sys_s32(&pc->totals[1]);
+                        const int* dl     = reinterpret_cast<const int*>(reinterpret_cast<const char*>(pc) + kP2PDeadOffset);
+                        slot              = ld_relaxed_sys_s32(dl + extras + dst_off);
+                    }
+                }
+                slot = __shfl_sync(0xffffffffu, slot, 0);
+                if (slot < 0)
+                {
+                    if (lane == 0) atomicAdd((unsigned long long*)&stats[3], 1ull);
                     continue;
                 }
-                rec = peers.import_buf[dst_rank] + dst_off * rec_bytes;
+                int const n_vec = delta ? (reinterpret_cast<const int*>(counts + i * stride)[0] + 1 + 3) >> 2
+                                        : (struct_size[id] + 3) >> 2;
+                warp_copy_block(counts + i * stride, peers.counts[dst_rank] + (long long)slot * stride, n_vec, lane);
+                if (lane == 0)
+                {
+                    peers.sid[dst_rank][slot]   = id;
+                    peers.state[dst_rank][slot] = state[i];
+                }
+                continue;
             }
+            char* rec = xport + (k - n_fill) * rec_bytes;
             warp_copy_block(counts + i * stride, reinterpret_cast<float*>(rec), (int)(stride >> 2), lane);
             if (lane == 0)
             {

@@ -2,12 +2,17 @@
 plumbing (NCCL on GPUs, gloo in the CPU tests of the host logic).
 
 Per belief update the ranks exchange:
-  * an all-gather of one double per rank — the shard's un-normalised weight total — so every rank
-    forms the same global total and the same offspring quotas;
+  * one double per rank — the shard's un-normalised weight total — so every rank forms the same
+    global total and the same offspring quotas;
   * particles only where resampling leaves a rank over / under its capacity: the surplus offspring
-    of over-quota ranks are shipped (all-to-all-v of particle records) into the empty slots of
-    under-quota ranks. With balanced weight shares that is O(sqrt(N/G)) particles per update.
-No collective touches the count blocks otherwise: the data path stays local to each GPU's HBM.
+    of over-quota ranks go into the empty slots of under-quota ranks. With balanced weight shares
+    that is O(sqrt(N/G)) particles per update.
+exchange="p2p" (default): both travel through peer-mapped memory inside the update's own kernels
+(fba_belief_sharded_update: step-stamped flags, surplus blocks stored straight into the destination
+GPU's dead slots over NVLink) — torch.distributed is used ONCE, at setup, to all-gather the CUDA IPC
+handles; the update path has no collective and no host synchronisation.
+exchange="allgather": NCCL all-gather of the totals + fixed-size windows of an export buffer, for
+setups without peer mapping.
 """
 import ctypes as C
 
@@ -152,6 +157,10 @@ class ShardedBAImportanceSampling(BAImportanceSampling):
     def _setup(self):
         import torch
         L, h = self.L, self.h
+        if self.exchange == "p2p" and self._setup_p2p():
+            self._bufs = True
+            return
+        self.exchange = "allgather"
         self._stream = torch.cuda.ExternalStream(self.ctx.stream)
         scal = L.fba_belief_scalars_ptr(h)
         self._local = torch.as_tensor(_RawCuda(scal, 8, "<f8", 8), device="cuda")  # view of scal[0]
@@ -159,8 +168,9 @@ class ShardedBAImportanceSampling(BAImportanceSampling):
         self._totals_host = torch.empty(self.world, dtype=torch.float64).pin_memory()
         self._plan = np.zeros((self.world, self.world), np.int64)
         self._event = torch.cuda.Event()
-        # export staging for the surplus of an over-quota shard: 1/64 of the shard by default;
-        # the exchange window is capped so that the gathered buffer stays <= 1 GiB
+        # export staging for the surplus of an over-quota shard: 1/64 of the shard by default (a
+        # larger surplus raises FBA_ERR_CAPACITY on the over-quota rank); the exchange window is
+        # capped so that the gathered buffer stays <= 1 GiB
         rb = L.fba_belief_record_bytes(h)
         cap = max(1024, self._n // 64)
         self._window_cap = 64
@@ -168,43 +178,6 @@ class ShardedBAImportanceSampling(BAImportanceSampling):
             self._window_cap *= 2
         _check(self.ctx.h, L.fba_belief_reserve_export(h, cap + self._window_cap))
         self._gather_buf = torch.empty(self.world * self._window_cap * rb, dtype=torch.uint8, device="cuda")
-        self._barrier = torch.zeros(1, dtype=torch.float32, device="cuda")
-        if self.exchange == "p2p":
-            # publish / map the import buffers (CUDA IPC): handles travel through one all-gather.
-            # If any rank cannot map its peers (no peer access / IPC in this container), every rank
-            # falls back to the all-gather exchange — the decision is made collectively.
-            ok = 1.0
-            try:
-                mine = np.zeros(64, np.uint8)
-                _check(self.ctx.h, L.fba_belief_ipc_handle(h, cap, mine.ctypes.data_as(C.c_void_p)))
-            except capi.FbaError:
-                ok = 0.0
-            if self.world > 1:
-                all_h = torch.empty(self.world * 64, dtype=torch.uint8, device="cuda")
-                self.dist.all_gather_into_tensor(all_h, torch.from_numpy(mine).cuda(), group=self.group)
-                handles = all_h.cpu().numpy()
-            else:
-                handles = mine
-            handles = np.ascontiguousarray(handles)
-            if ok:
-                try:
-                    _check(self.ctx.h,
-                           L.fba_belief_ipc_open(h, handles.ctypes.data_as(C.c_void_p), self.world, self.rank))
-                except capi.FbaError:
-                    ok = 0.0
-            if self.world > 1:
-                flag = torch.tensor([ok], dtype=torch.float32, device="cuda")
-                self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN, group=self.group)
-                ok = float(flag.item())
-            if ok:
-                if self.world > 1:
-                    self.dist.all_reduce(self._barrier, group=self.group)
-                    self.dist.all_gather_into_tensor(
-                        self._totals, torch.zeros(1, dtype=torch.float64, device="cuda"), group=self.group)
-                torch.cuda.synchronize()
-                self._bufs = True
-                return
-            self.exchange = "allgather"
         if self.world > 1:
             w = 64
             while w <= self._window_cap:  # touch every window size once (NCCL algorithm selection)
@@ -215,6 +188,38 @@ class ShardedBAImportanceSampling(BAImportanceSampling):
                                              group=self.group)
             torch.cuda.synchronize()
         self._bufs = True
+
+    def _setup_p2p(self):
+        """Publishes / maps the control blocks and particle arrays (CUDA IPC): the blobs travel through
+        one all-gather, the only collective of this mode. If any rank cannot map its peers (no peer
+        access / IPC in this container), every rank falls back to the all-gather exchange — the
+        decision is made collectively. -> True when every rank is mapped."""
+        import torch
+        L, h = self.L, self.h
+        ok = 1.0
+        mine = np.zeros(capi.P2P_BLOB_BYTES, np.uint8)
+        try:
+            _check(self.ctx.h, L.fba_belief_p2p_export(h, mine.ctypes.data_as(C.c_void_p)))
+        except capi.FbaError:
+            ok = 0.0
+        if self.world > 1:
+            all_h = torch.empty(self.world * capi.P2P_BLOB_BYTES, dtype=torch.uint8, device="cuda")
+            self.dist.all_gather_into_tensor(all_h, torch.from_numpy(mine).cuda(), group=self.group)
+            blobs = all_h.cpu().numpy()
+        else:
+            blobs = mine
+        blobs = np.ascontiguousarray(blobs)
+        if ok:
+            try:
+                _check(self.ctx.h, L.fba_belief_p2p_open(h, blobs.ctypes.data_as(C.c_void_p), self.world, self.rank))
+            except capi.FbaError:
+                ok = 0.0
+        if self.world > 1:
+            flag = torch.tensor([ok], dtype=torch.float32, device="cuda")
+            self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN, group=self.group)  # also: every rank has mapped
+            ok = float(flag.item())
+        torch.cuda.synchronize()
+        return bool(ok)
 
     def _exchange(self, plan):
         """Ships the surplus records: every rank contributes a fixed-size WINDOW of its export
@@ -254,7 +259,9 @@ class ShardedBAImportanceSampling(BAImportanceSampling):
         import torch
         if self._bufs:
             torch.cuda.synchronize()
-            self._local = self._totals = self._totals_host = self._stream = self._event = self._gather_buf = self._barrier = None
+            if self.world > 1 and self.exchange == "p2p":
+                self.dist.barrier(group=self.group)  # peers may still be storing into this rank's arrays
+            self._local = self._totals = self._totals_host = self._stream = self._event = self._gather_buf = None
             self._bufs = None
         super().free()
 
@@ -283,13 +290,17 @@ class ShardedBAImportanceSampling(BAImportanceSampling):
                                                                self.dist.get_backend(self.group) == "nccl") else "cpu"
         return gather_ragged(self.dist, self.group, ret, counts, device)
 
-    def updateEstimation(self, a, o, rng, step_uniform=0.5):
-        """One global importance-sampling update + resample. `step_uniform` in [0,1) must be the
-        same on every rank (the shared systematic offset of the quota allocation).
+    def updateEstimation(self, a, o, rng, step_uniform=0.5, likelihood=True):
+        """One global importance-sampling update + resample (BAImportanceSampling::updateEstimation,
+        BAImportanceSampling.cpp:74-88, over all shards). `step_uniform` in [0,1) must be the same on
+        every rank (the shared systematic offset of the quota allocation). Returns the GLOBAL step
+        likelihood total (sum of all shards' un-normalised weights; 8 bytes D2H, one stream
+        synchronisation), or None with likelihood=False (nothing waits for the GPU).
 
-        Everything is enqueued on the library's stream without waiting for the GPU; the host only
-        waits for the G shard totals (a D2H copy ordered BEFORE the resampling kernels), which it
-        needs for the all-to-all's split sizes, while the GPU is already resampling."""
+        p2p: ONE C call enqueues the whole update; ranks meet inside the kernels through peer-mapped
+        flags. allgather: the host waits for the G shard totals (a D2H copy ordered BEFORE the
+        resampling kernels), which it needs for the exchange windows, while the GPU is already
+        resampling."""
         import time
         import torch
         L, h, ctx = self.L, self.h, self.ctx
@@ -297,6 +308,11 @@ class ShardedBAImportanceSampling(BAImportanceSampling):
             self._setup()
         u = float(step_uniform)
         t0 = time.perf_counter()
+        if self.exchange == "p2p":
+            tot = C.c_double(0)
+            _check(ctx.h, L.fba_belief_sharded_update(h, a, o, C.byref(rng), u, C.byref(tot) if likelihood else None))
+            self.phase_ms = {"enqueue whole update": (time.perf_counter() - t0) * 1e3}
+            return tot.value if likelihood else None
         trace = self._trace_events() if self.trace is not None else None
         with torch.cuda.stream(self._stream):
             if trace:
@@ -309,22 +325,6 @@ class ShardedBAImportanceSampling(BAImportanceSampling):
                 self.dist.all_gather_into_tensor(self._totals, self._local, group=self.group)
             else:
                 self._totals.copy_(self._local)
-            if self.exchange == "p2p":
-                # plan on device, surplus stored into peer memory by the copy kernel; a tiny
-                # all-reduce is the cross-rank barrier between those stores and the imports
-                if trace:
-                    trace[2].record(self._stream)
-                _check(ctx.h, L.fba_belief_shard_resample_p2p(h, self._totals.data_ptr(), u, C.byref(rng)))
-                if trace:
-                    trace[3].record(self._stream)
-                if self.world > 1:
-                    self.dist.all_reduce(self._barrier, group=self.group)
-                _check(ctx.h, L.fba_belief_import_p2p(h))
-                if trace:
-                    trace[4].record(self._stream)
-                    self.trace.append(trace)
-                self.phase_ms = {"enqueue whole update (no host sync)": (time.perf_counter() - t0) * 1e3}
-                return None
             self._totals_host.copy_(self._totals, non_blocking=True)
             self._event.record(self._stream)
             if trace:
@@ -348,3 +348,8 @@ class ShardedBAImportanceSampling(BAImportanceSampling):
         self.phase_ms = {"enqueue propose..resample + wait for totals": (t1 - t0) * 1e3,
                          "plan + exchange (enqueue)": (time.perf_counter() - t1) * 1e3}
         return tot.value
+
+    def timeouts(self):
+        """Cross-rank waits that were abandoned (p2p): 0 in a healthy run; anything else means a rank
+        fell out of step and this belief is invalid."""
+        return int(self.L.fba_belief_p2p_timeouts(self.h)) if self.exchange == "p2p" and self._bufs else 0

@@ -31,7 +31,7 @@ extern "C" {
 
 #define FBA_MAX_FEATURES 16
 /* bumped whenever a struct below changes layout; compare with fba_abi_version() after loading */
-#define FBA_ABI_VERSION 10
+#define FBA_ABI_VERSION 11
 
 typedef struct fba_ctx fba_ctx;
 typedef struct fba_model fba_model;
@@ -270,17 +270,28 @@ int fba_belief_shard_resample_async(fba_belief* b, const double* totals_device, 
                                     int32_t rank, double u, fba_rng* rng);
 int fba_belief_shard_plan(fba_belief* b, const double* totals_host, int32_t n_ranks, int32_t rank, double u,
                           int64_t* send_plan, double* global_total);
-/* Peer-to-peer exchange over NVLink (one process per GPU, one box): each rank publishes the CUDA IPC
- * handle of its import buffer, maps its peers', and the resampling kernel stores surplus records
- * straight into the destination GPU's import buffer. The plan lives on device, so the host never
- * waits for the GPU during an update. Order per update, all on the context's stream:
- *   fba_belief_propose(.., NULL) -> all-gather of the shard totals (device) ->
- *   fba_belief_shard_resample_p2p -> any small collective as a cross-rank barrier ->
- *   fba_belief_import_p2p. */
-int fba_belief_ipc_handle(fba_belief* b, int64_t cap_records, void* handle64);
-int fba_belief_ipc_open(fba_belief* b, const void* handles, int32_t n_ranks, int32_t rank);
-int fba_belief_shard_resample_p2p(fba_belief* b, const double* totals_device, double u, fba_rng* rng);
-int fba_belief_import_p2p(fba_belief* b);
+/* Peer-to-peer sharded update over NVLink / NVSwitch (one process per GPU, one box). The reference has
+ * no distributed path; this is the multi-GPU form of BAImportanceSampling::updateEstimation
+ * (src/beliefs/bayes-adaptive/BAImportanceSampling.cpp:74-88) named by SURVEY.md §8e. Setup, once:
+ * every rank calls _p2p_export (allocates its control block, returns a blob of CUDA IPC handles), the
+ * host all-gathers the blobs (the only collective, at setup), every rank calls _p2p_open. Per update
+ * ONE call, fba_belief_sharded_update, enqueues everything on the context's stream with no host
+ * synchronisation and no NCCL: the shard totals, "dead-slot list complete" and "records landed" travel
+ * between GPUs as step-stamped flags in peer-mapped memory, and the surplus blocks of an over-quota
+ * shard are stored by the resampling kernel straight into dead slots of the destination GPU's particle
+ * array — no staging buffer, so no capacity limit however skewed the shard weights are.
+ * u in [0,1): the shared systematic offset of the quota allocation, the same on every rank.
+ * likelihood (may be NULL = fully asynchronous): the GLOBAL un-normalised weight total.
+ * Every rank must make the same sequence of sharded_update calls. A cross-rank wait longer than the
+ * timeout (default 20 s) is abandoned and counted (fba_belief_p2p_timeouts; the belief is then
+ * invalid) instead of hanging the GPU. */
+#define FBA_P2P_BLOB_BYTES 320
+int fba_belief_p2p_export(fba_belief* b, void* blob);
+int fba_belief_p2p_open(fba_belief* b, const void* blobs, int32_t n_ranks, int32_t rank);
+int fba_belief_sharded_update(fba_belief* b, int32_t action, int32_t observation, fba_rng* rng, double u,
+                              double* likelihood);
+int64_t fba_belief_p2p_timeouts(fba_belief* b);
+int fba_belief_p2p_set_timeout(fba_belief* b, double seconds);
 /* surplus records that did not fit an export / import buffer since creation (0 in a healthy run) */
 int64_t fba_belief_dropped_records(fba_belief* b);
 int fba_belief_reserve_export(fba_belief* b, int64_t records);
