@@ -49,6 +49,10 @@ class Context:
     def launches(self):
         return self.L.fba_ctx_launch_count(self.h)
 
+    def counter(self, which=0):
+        """device-side counters (0: simulated steps executed by the rollout kernels)."""
+        return int(self.L.fba_ctx_counter(self.h, which))
+
     def synchronize(self):
         _check(self.h, self.L.fba_ctx_synchronize(self.h))
 

@@ -44,6 +44,7 @@ struct fba_ctx
     long long* d_offsets = nullptr;
     size_t offsets_cap   = 0;
     int* d_flag          = nullptr; // overrun flag
+    unsigned long long* d_counters = nullptr; // [0] simulated steps executed by rollout kernels
     int* h_flag          = nullptr; // pinned
     double* h_scal       = nullptr; // pinned, 4 doubles
 };
@@ -254,6 +255,8 @@ extern "C" int fba_ctx_create(int device, fba_ctx** out)
         if (e == cudaSuccess) e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_flag, sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_counters, 4 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(ctx->d_counters, 0, 4 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_flag, sizeof(int));
     if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_scal, 4 * sizeof(double));
     if (e != cudaSuccess)
@@ -274,6 +277,7 @@ extern "C" void fba_ctx_destroy(fba_ctx* ctx)
     cudaFree(ctx->d_words);
     cudaFree(ctx->d_offsets);
     cudaFree(ctx->d_flag);
+    cudaFree(ctx->d_counters);
     cudaFreeHost(ctx->h_flag);
     cudaFreeHost(ctx->h_scal);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -294,6 +298,18 @@ extern "C" int fba_ctx_synchronize(fba_ctx* ctx)
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return FBA_OK;
 }
+// which = 0: simulated steps executed by the rollout kernels since the context was created
+// (rollouts end early at terminal states; the roofline of k_rollouts is quoted on this count)
+extern "C" int64_t fba_ctx_counter(fba_ctx* ctx, int32_t which)
+{
+    if (!ctx || which < 0 || which >= 4) return -1;
+    unsigned long long h = 0;
+    cudaSetDevice(ctx->device);
+    if (cudaMemcpyAsync(&h, ctx->d_counters + which, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
+    return (int64_t)h;
+}
+
 extern "C" int64_t fba_ctx_launch_count(const fba_ctx* ctx)
 {
     return ctx ? ctx->launches : -1;
@@ -1915,16 +1931,16 @@ extern "C" int fba_rollouts(fba_belief* b, int64_t n, const int64_t* particle, c
         if (b->delta_cap > 0)
             LAUNCH_DELTA(ctx, k_rollouts_delta, true, blocks_for(n, tpb), tpb, D, b->base, b->lstride,
                          b->counts[b->cur], b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r,
-                         ctx->d_flag);
+                         ctx->d_flag, ctx->d_counters);
         else if (coop)
             LAUNCH(ctx, (k_rollouts<true, true, false, false>), blocks_for(n * 32), kThreads, D, b->counts[b->cur],
-                   b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag);
+                   b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag, ctx->d_counters);
         else if (b->m->long_rows)
             LAUNCH(ctx, (k_rollouts<true, false, true, false>), blocks_for(n, tpb), tpb, D, b->counts[b->cur],
-                   b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag);
+                   b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag, ctx->d_counters);
         else
             LAUNCH(ctx, (k_rollouts<true, false, false, false>), blocks_for(n, tpb), tpb, D, b->counts[b->cur],
-                   b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag);
+                   b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag, ctx->d_counters);
     } else
     {
         RngArgs const ra = philox_args(rng);
@@ -1932,22 +1948,22 @@ extern "C" int fba_rollouts(fba_belief* b, int64_t n, const int64_t* particle, c
         if (b->delta_cap > 0)
             LAUNCH_DELTA(ctx, k_rollouts_delta, false, blocks_for(n, tpb), tpb, D, b->base, b->lstride,
                          b->counts[b->cur], b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r,
-                         ctx->d_flag);
+                         ctx->d_flag, ctx->d_counters);
         else if (coop && !D.sampled)
             LAUNCH(ctx, (k_rollouts<false, true, false, false>), blocks_for(n * 32), kThreads, D, b->counts[b->cur],
-                   b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag);
+                   b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag, ctx->d_counters);
         else if (D.sampled && lr)
             LAUNCH(ctx, (k_rollouts<false, false, true, true>), blocks_for(n, tpb), tpb, D, b->counts[b->cur],
-                   b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag);
+                   b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag, ctx->d_counters);
         else if (D.sampled)
             LAUNCH(ctx, (k_rollouts<false, false, false, true>), blocks_for(n, tpb), tpb, D, b->counts[b->cur],
-                   b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag);
+                   b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag, ctx->d_counters);
         else if (lr)
             LAUNCH(ctx, (k_rollouts<false, false, true, false>), blocks_for(n, tpb), tpb, D, b->counts[b->cur],
-                   b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag);
+                   b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag, ctx->d_counters);
         else
             LAUNCH(ctx, (k_rollouts<false, false, false, false>), blocks_for(n, tpb), tpb, D, b->counts[b->cur],
-                   b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag);
+                   b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag, ctx->d_counters);
     }
     CU(ctx, cudaMemcpyAsync(returns, d_r, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));

@@ -1334,6 +1334,14 @@ __global__ void __launch_bounds__(kThreads)
 // ------------------------------------------------------------------------------------------------
 // rollouts: RBAPOUCT::rollout (RBAPOUCT.cpp:295-323), one thread per rollout, counts read-only
 // ------------------------------------------------------------------------------------------------
+// simulated steps actually executed (rollouts end early at terminal states): one atomic per warp
+__device__ __forceinline__ void count_steps(unsigned long long* steps_done, int mine)
+{
+    unsigned const active = __activemask();
+    unsigned const total  = __reduce_add_sync(active, (unsigned)mine);
+    if ((threadIdx.x & 31) == (__ffs(active) - 1) && total) atomicAdd(steps_done, (unsigned long long)total);
+}
+
 // COOP = false: one thread per rollout (large batches: most independent work per SM).
 // COOP = true: one warp per rollout, rows loaded cooperatively (small batches are latency-bound:
 // one coalesced request per row instead of `range` dependent ones).
@@ -1342,7 +1350,7 @@ __global__ void __launch_bounds__(kThreads)
     k_rollouts(DevModel M, const float* counts, long long stride, const int* __restrict__ sid,
                long long n, const long long* __restrict__ particle, const int* __restrict__ start,
                const int* __restrict__ depth, double discount, RngArgs ra, double* __restrict__ ret_out,
-               int* __restrict__ overrun)
+               int* __restrict__ overrun, unsigned long long* __restrict__ steps_done)
 {
     long long const t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long const r = COOP ? (t >> 5) : t;
@@ -1373,6 +1381,7 @@ __global__ void __launch_bounds__(kThreads)
         ret_out[r] = ret;
         if (g.overrun) *overrun = 1;
     }
+    count_steps(steps_done, COOP ? ((threadIdx.x & 31) == 0 ? depth[r] - d : 0) : depth[r] - d);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2206,7 +2215,7 @@ __global__ void __launch_bounds__(kThreads)
                      long long stride, const int* __restrict__ sid, long long n,
                      const long long* __restrict__ particle, const int* __restrict__ start,
                      const int* __restrict__ depth, double discount, RngArgs ra, double* __restrict__ ret_out,
-                     int* __restrict__ overrun)
+                     int* __restrict__ overrun, unsigned long long* __restrict__ steps_done)
 {
     long long const r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
@@ -2231,6 +2240,7 @@ __global__ void __launch_bounds__(kThreads)
     }
     ret_out[r] = ret;
     if (g.overrun) *overrun = 1;
+    count_steps(steps_done, depth[r] - d);
 }
 
 template<bool REPLAY, bool SAMPLED>

@@ -349,6 +349,14 @@ class ShardedBAImportanceSampling(BAImportanceSampling):
                          "plan + exchange (enqueue)": (time.perf_counter() - t1) * 1e3}
         return tot.value
 
+    def sample_global(self, rng, shared_uniform):
+        """Belief::sample() of the GLOBAL belief (WeightedFilter::sample, WeightedFilter.cpp:163-191):
+        after a global resample every shard carries the same total weight, so the owning shard is
+        floor(shared_uniform * world) — `shared_uniform` in [0,1) must be the same on every rank — and
+        that rank draws inside its shard. -> (owner rank, local particle index or None on other ranks)."""
+        owner = min(int(float(shared_uniform) * self.world), self.world - 1)
+        return owner, (self.sample(rng) if owner == self.rank else None)
+
     def timeouts(self):
         """Cross-rank waits that were abandoned (p2p): 0 in a healthy run; anything else means a rank
         fell out of step and this belief is invalid."""

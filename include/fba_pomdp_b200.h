@@ -142,6 +142,9 @@ void* fba_ctx_stream(const fba_ctx* ctx);
 int fba_ctx_synchronize(fba_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t fba_ctx_launch_count(const fba_ctx* ctx);
+/* device-side counters since creation. which = 0: simulated steps executed by the rollout kernels
+ * (RBAPOUCT::rollout ends early at terminal states, RBAPOUCT.cpp:306) */
+int64_t fba_ctx_counter(fba_ctx* ctx, int32_t which);
 
 /* options: "inplace_resample" (default 1): PHILOX-mode resampling keeps surviving particles in
  * their slot and copies only duplicates; 0 = gather every particle into the second buffer */
