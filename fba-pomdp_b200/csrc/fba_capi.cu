@@ -29,6 +29,8 @@ struct fba_ctx
     int rollout_coop = -1; // -1 auto (by batch size and row length), 0 thread per rollout, 1 warp per rollout
     bool inplace_resample = true; // PHILOX mode: survivors keep their slot (fba_ctx_set_option)
     bool fused_update     = true; // small beliefs: update + resample in ONE launch (k_runs_step, one CTA)
+    long long parallel_chains_min = 8192; // REPLAY: beliefs at least this large evaluate the reference's
+                                          // sequential weight chains in parallel (bit-identical)
     bool profiling       = false;
     struct Timed
     {
@@ -126,6 +128,10 @@ struct fba_belief
     long long* roll_p  = nullptr;
     int *roll_s = nullptr, *roll_d = nullptr;
     double* roll_r = nullptr;
+    // REPLAY, parallel evaluation of the sequential weight chains: per-segment scratch, grow-once
+    double *seg_start = nullptr, *seg_end = nullptr, *seg_delta = nullptr;
+    unsigned char* seg_tie = nullptr;
+    long long* chain_stats = nullptr; // [0] segments recomputed sequentially, [1] segments walked
     // multi-GPU staging
     char* xport = nullptr;
     long long xport_cap = 0, xport_count = 0;
@@ -331,6 +337,11 @@ extern "C" int fba_ctx_set_option(fba_ctx* ctx, const char* name, int64_t value)
     if (!strcmp(name, "bulk_copy"))
     {
         ctx->bulk_copy = value != 0;
+        return FBA_OK;
+    }
+    if (!strcmp(name, "parallel_chains_min"))
+    { // 0: always the parallel evaluation of the REPLAY weight chains; a huge value: never
+        ctx->parallel_chains_min = value;
         return FBA_OK;
     }
     if (!strcmp(name, "rollout_coop"))
@@ -823,6 +834,7 @@ extern "C" void fba_belief_destroy(fba_belief* b)
     else
         cudaFree(b->dead), cudaFree(b->totals);
     cudaFree(b->d_step);
+    cudaFree(b->seg_start), cudaFree(b->seg_end), cudaFree(b->seg_delta), cudaFree(b->seg_tie), cudaFree(b->chain_stats);
     delete b;
 }
 
@@ -845,6 +857,10 @@ extern "C" void* fba_belief_state_ptr(fba_belief* b)
 extern "C" void* fba_belief_weight_ptr(fba_belief* b)
 {
     return b ? b->w : nullptr;
+}
+extern "C" void* fba_belief_aux_ptr(fba_belief* b)
+{
+    return b ? b->aux : nullptr;
 }
 extern "C" void* fba_belief_scalars_ptr(fba_belief* b)
 {
@@ -1177,6 +1193,57 @@ static int read_scal(fba_belief* b)
     return FBA_OK;
 }
 
+// REPLAY: the reference's sequential chains (k_seq_normalize's A, B, C; only C if !do_normalise, with
+// scal[1] = _total_weight given). Small beliefs: one thread walks them. Large beliefs: segments walked in
+// parallel from speculated starts + a short serial shift / recompute pass — bit-identical results
+// (fba_kernels.cuh, "REPLAY normalisation for LARGE beliefs").
+static int replay_chains(fba_belief* b, bool do_normalise)
+{
+    fba_ctx* ctx = b->ctx;
+    if (b->N < ctx->parallel_chains_min)
+    {
+        LAUNCH(ctx, k_seq_normalize, 1, kThreads, b->w, b->N, b->scal, b->aux, do_normalise ? 1 : 0);
+        return FBA_OK;
+    }
+    int const n_seg = (int)((b->N + kTile - 1) / kTile);
+    if (!b->seg_start)
+    {
+        CU(ctx, cudaMalloc(&b->seg_start, (size_t)n_seg * sizeof(double)));
+        CU(ctx, cudaMalloc(&b->seg_end, (size_t)n_seg * sizeof(double)));
+        CU(ctx, cudaMalloc(&b->seg_delta, (size_t)n_seg * sizeof(double)));
+        CU(ctx, cudaMalloc(&b->seg_tie, (size_t)n_seg));
+        CU(ctx, cudaMalloc(&b->chain_stats, 2 * sizeof(long long)));
+        CU(ctx, cudaMemsetAsync(b->chain_stats, 0, 2 * sizeof(long long), ctx->stream));
+    }
+    int const seg_grid = blocks_for(n_seg, 64);
+    double* const spec_total = b->scal + 3;
+    const double* none       = nullptr;
+    auto sum_chain = [&](double* result) -> int { // exact sequential sum of the current weights
+        LAUNCH(ctx, k_scan_tile_sums, 1, kThreads, b->tile, n_seg, spec_total);
+        LAUNCH(ctx, (k_chain_segments<false>), seg_grid, 64, b->w, b->N, b->tile, spec_total, none, b->seg_start,
+               b->seg_end, b->seg_tie, (double*)nullptr);
+        LAUNCH(ctx, (k_chain_fix<false>), 1, kThreads, b->w, b->N, b->seg_start, b->seg_end, b->seg_tie, none, result,
+               (double*)nullptr, (double*)nullptr, b->chain_stats);
+        return FBA_OK;
+    };
+    int rc;
+    LAUNCH(ctx, k_tile_sums, n_seg, kThreads, b->w, b->N, b->tile);
+    if (do_normalise)
+    {
+        if ((rc = sum_chain(b->scal))) return rc;                                                // A
+        LAUNCH(ctx, k_divide_tile_sums, n_seg, kThreads, b->w, b->N, (const double*)b->scal, b->tile); // B
+        if ((rc = sum_chain(b->scal + 1))) return rc;
+    } else
+        LAUNCH(ctx, k_scan_tile_sums, 1, kThreads, b->tile, n_seg, spec_total);
+    // C: b->tile holds the tree-order prefix of the current weights, spec_total their tree-order total
+    LAUNCH(ctx, (k_chain_segments<true>), seg_grid, 64, b->w, b->N, b->tile, spec_total, (const double*)(b->scal + 1),
+           b->seg_start, b->seg_end, b->seg_tie, b->aux);
+    LAUNCH(ctx, (k_chain_fix<true>), 1, kThreads, b->w, b->N, b->seg_start, b->seg_end, b->seg_tie,
+           (const double*)(b->scal + 1), b->scal + 2, b->seg_delta, b->aux, b->chain_stats);
+    LAUNCH(ctx, k_chain_apply_shift, blocks_for(b->N), kThreads, b->aux, b->N, (const double*)b->seg_delta);
+    return FBA_OK;
+}
+
 extern "C" int fba_belief_update(fba_belief* b, int32_t a, int32_t o, fba_rng* rng, double* likelihood)
 {
     if (!b || !rng) return FBA_ERR_INVALID;
@@ -1185,7 +1252,7 @@ extern "C" int fba_belief_update(fba_belief* b, int32_t a, int32_t o, fba_rng* r
     if (rc) return rc;
     if (rng->mode == FBA_RNG_REPLAY)
     {
-        LAUNCH(ctx, k_seq_normalize, 1, kThreads, b->w, b->N, b->scal, b->aux, 1);
+        if ((rc = replay_chains(b, true))) return rc;
         if ((rc = read_scal(b))) return rc;
         if ((rc = check_flag(ctx))) return rc;
         b->total_weight = ctx->h_scal[1];
@@ -1241,7 +1308,7 @@ static int pick_ancestors(fba_belief* b, fba_rng* rng, long long n_out, long lon
             double const tw = b->total_weight;
             CU(ctx, cudaMemcpyAsync(b->scal + 1, &tw, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
             CU(ctx, cudaStreamSynchronize(ctx->stream));
-            LAUNCH(ctx, k_seq_normalize, 1, kThreads, b->w, b->N, b->scal, b->aux, 0);
+            if ((rc = replay_chains(b, false))) return rc;
             b->suffix_valid = true;
             b->cdf_valid    = false;
         }
@@ -3112,6 +3179,19 @@ extern "C" int64_t fba_belief_dropped_records(fba_belief* b)
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
     cudaMemcpy(&h, b->stats + 2, sizeof(h), cudaMemcpyDeviceToHost);
+    return h;
+}
+
+// REPLAY, large beliefs: segments the serial pass had to recompute since creation (the rest were
+// shifted); -1 if the parallel evaluation never ran
+extern "C" int64_t fba_belief_chain_recomputed(fba_belief* b)
+{
+    if (!b) return -1;
+    if (!b->chain_stats) return -1;
+    long long h = 0;
+    cudaSetDevice(b->ctx->device);
+    if (cudaMemcpyAsync(&h, b->chain_stats, sizeof(h), cudaMemcpyDeviceToHost, b->ctx->stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(b->ctx->stream) != cudaSuccess) return -1;
     return h;
 }
 

@@ -549,6 +549,216 @@ __global__ void __launch_bounds__(kThreads)
     scale_and_scan_body(blockIdx.x, w, N, tile_off, total_ptr ? *total_ptr : divide_by, cdf, sh);
 }
 
+// ------------------------------------------------------------------------------------------------
+// REPLAY normalisation for LARGE beliefs: the reference's three SEQUENTIAL floating-point chains
+// (k_seq_normalize: A total, B total_weight, C remainders) evaluated in parallel with bit-identical
+// results. One thread of k_seq_normalize needs ~8 ns per element and chain (30 ms for 1.25e6
+// particles); here the chains are cut into segments of kTile elements, every segment is walked by its
+// own thread from a SPECULATED start value (a tree-order prefix sum, off by a few ulps from the
+// sequential one), and a short serial pass turns the speculated segments into the exact ones:
+//
+//   Inside one binade all doubles are multiples of u = ulp. If the speculated value s' and the true
+//   value s of the running sum lie in the same binade, s' - s = m u, and the next rounded operation
+//   fl(s + w) = u round(s / u + w / u) commutes with the shift: fl(s' + w) = fl(s + w) + m u — unless
+//   the fractional part of w / u is exactly 1/2 (a tie, resolved by the parity of the neighbour) or
+//   the result leaves the binade (the grid changes). Weights are >= 0, so a chain is monotone: it stays
+//   in one binade iff its first and last value do.
+//
+// So a segment whose speculated walk met no tie, and whose speculated AND true end points all lie in
+// one binade, is EXACTLY the true walk shifted by delta = s'_start - s_start (all differences exact:
+// same binade, Sterbenz). Any other segment — the first one, the dozen in which the running sum
+// crosses a power of two, the one or two per million elements with a tie — is recomputed sequentially
+// from its true start by the serial pass. tests/test_cuda_parity.py compares this path with
+// k_seq_normalize bit for bit (weights, totals, every remainder) on adversarial weight vectors.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int binade_of(double x) // sign + biased exponent
+{
+    return __double2hiint(x) >> 20;
+}
+
+// walks segment `c` (elements [c kTile, min(N, (c+1) kTile)) ascending for the sums, descending for the
+// remainders) from start value s; returns the end value; *tie = the walk met an exact tie or a value
+// too small to test; SUB writes every intermediate value to out[]
+template<bool SUB>
+__device__ __forceinline__ double chain_walk(const double* v, long long lo, long long hi, double s, double* out,
+                                             bool* tie)
+{
+    bool t = false;
+    if (!SUB)
+    {
+        for (long long k = lo; k < hi; ++k)
+        {
+            double const b = v[k];
+            double const x = __dadd_rn(s, b);
+            double const e = __dsub_rn(b, __dsub_rn(x, s)); // exact rounding error when b <= s (Fast2Sum)
+            int const ex   = (__double2hiint(x) >> 20) & 0x7ff;
+            t |= (ex <= 54) | (fabs(e) == __hiloint2double((ex - 53) << 20, 0));
+            s = x;
+        }
+    } else
+    {
+        for (long long k = hi - 1; k >= lo; --k)
+        {
+            double const b = v[k];
+            double const x = __dsub_rn(s, b);
+            double const e = __dsub_rn(__dsub_rn(s, x), b);
+            int const ex   = (__double2hiint(x) >> 20) & 0x7ff;
+            t |= (ex <= 54) | (fabs(e) == __hiloint2double((ex - 53) << 20, 0));
+            s      = x;
+            out[k] = x;
+        }
+    }
+    *tie = t;
+    return s;
+}
+
+// speculative pass, one thread per segment. spec_prefix[c] = tree-order sum of the elements before
+// segment c (k_tile_sums + k_scan_tile_sums), spec[0] = tree-order total. The start of the remainder
+// chain's segment c is top - (elements at and above (c+1) kTile).
+template<bool SUB>
+__global__ void __launch_bounds__(64)
+    k_chain_segments(const double* __restrict__ v, long long N, const double* __restrict__ spec_prefix,
+                     const double* __restrict__ spec_total, const double* __restrict__ top,
+                     double* __restrict__ seg_start, double* __restrict__ seg_end,
+                     unsigned char* __restrict__ seg_tie, double* __restrict__ out)
+{
+    long long const c      = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long const n_seg  = (N + kTile - 1) / kTile;
+    if (c >= n_seg) return;
+    long long const lo = c * kTile, hi = min(N, lo + kTile);
+    double s;
+    if (!SUB) s = spec_prefix[c];
+    else
+        s = (c + 1 < n_seg) ? __dsub_rn(*top, __dsub_rn(*spec_total, spec_prefix[c + 1])) : *top;
+    seg_start[c] = s;
+    bool tie;
+    seg_end[c] = chain_walk<SUB>(v, lo, hi, s, out, &tie);
+    seg_tie[c] = tie ? 1 : 0;
+}
+
+// serial pass, ONE block: thread 0 carries the chain from segment to segment (true start of the first
+// segment = *start0 for the remainders, 0 for the sums), shifting the speculated segments and
+// recomputing the others; the other threads only stage data through shared memory (segment
+// descriptors 256 at a time; the elements of a segment that has to be recomputed). result[0] = the
+// chain's exact end value; SUB: delta[c] = what to subtract from the speculated remainders of segment
+// c (0 where they were recomputed in place).
+template<bool SUB>
+__global__ void __launch_bounds__(kThreads)
+    k_chain_fix(const double* __restrict__ v, long long N, const double* __restrict__ seg_start,
+                const double* __restrict__ seg_end, const unsigned char* __restrict__ seg_tie,
+                const double* __restrict__ start0, double* __restrict__ result, double* __restrict__ delta,
+                double* __restrict__ out, long long* __restrict__ n_recomputed)
+{
+    __shared__ double sh_start[kThreads], sh_end[kThreads], buf[kTile];
+    __shared__ unsigned char sh_tie[kThreads];
+    __shared__ double s_sh;
+    __shared__ int pos_sh, need_sh;
+    int const tid         = threadIdx.x;
+    long long const n_seg = (N + kTile - 1) / kTile;
+    if (tid == 0) s_sh = start0 ? *start0 : 0.0;
+    long long redo = 0;
+    for (long long first = 0; first < n_seg; first += kThreads)
+    { // batch of segments first .. first + n_b - 1 in PROCESSING order (remainders: from the top down)
+        int const n_b = (int)min((long long)kThreads, n_seg - first);
+        if (tid < n_b)
+        {
+            long long const c = SUB ? n_seg - 1 - (first + tid) : first + tid;
+            sh_start[tid] = seg_start[c], sh_end[tid] = seg_end[c], sh_tie[tid] = seg_tie[c];
+        }
+        if (tid == 0) pos_sh = 0;
+        __syncthreads();
+        while (true)
+        {
+            if (tid == 0)
+            {
+                double s = s_sh;
+                int j    = pos_sh;
+                int need = -1;
+                for (; j < n_b; ++j)
+                {
+                    double const sp = sh_start[j], ep = sh_end[j];
+                    int const id    = binade_of(sp);
+                    bool ok         = !sh_tie[j] && binade_of(ep) == id && binade_of(s) == id;
+                    double d = 0.0, e = 0.0;
+                    if (ok)
+                    {
+                        d  = __dsub_rn(sp, s); // exact: same binade
+                        e  = __dsub_rn(ep, d);
+                        ok = binade_of(e) == id;
+                    }
+                    if (!ok)
+                    {
+                        need = j;
+                        break;
+                    }
+                    if (SUB) delta[n_seg - 1 - (first + j)] = d;
+                    s = e;
+                }
+                s_sh = s, pos_sh = j, need_sh = need;
+            }
+            __syncthreads();
+            if (need_sh < 0) break;
+            long long const c  = SUB ? n_seg - 1 - (first + need_sh) : first + need_sh;
+            long long const lo = c * kTile;
+            int const n        = (int)(min(N, lo + kTile) - lo);
+            for (int k = tid; k < n; k += kThreads) buf[k] = v[lo + k];
+            __syncthreads();
+            if (tid == 0)
+            {
+                bool tie;
+                s_sh = chain_walk<SUB>(buf, 0, n, s_sh, buf, &tie); // SUB: buf[k] becomes the remainder
+                if (SUB) delta[c] = 0.0;
+                pos_sh = need_sh + 1;
+                ++redo;
+            }
+            __syncthreads();
+            if (SUB)
+                for (int k = tid; k < n; k += kThreads) out[lo + k] = buf[k];
+            __syncthreads();
+        }
+        __syncthreads();
+    }
+    if (tid == 0)
+    {
+        result[0] = s_sh;
+        if (n_recomputed) *n_recomputed += redo;
+    }
+}
+
+// remainders of the shifted segments: R_k = R'_k - delta (exact: multiples of one ulp, same binade)
+__global__ void __launch_bounds__(kThreads)
+    k_chain_apply_shift(double* __restrict__ R, long long N, const double* __restrict__ delta)
+{
+    long long const k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= N) return;
+    double const d = delta[k / kTile];
+    if (d != 0.0) R[k] = __dsub_rn(R[k], d);
+}
+
+// chain B's element-wise half: w_i /= total (one correctly rounded division each) + tile sums of the result
+__global__ void __launch_bounds__(kThreads)
+    k_divide_tile_sums(double* __restrict__ w, long long N, const double* __restrict__ total,
+                       double* __restrict__ tile_sum)
+{
+    __shared__ double sh[kThreads / 32];
+    long long const base = (long long)blockIdx.x * kTile;
+    double const t       = *total;
+    double v             = 0.0;
+#pragma unroll
+    for (int k = 0; k < kTile / kThreads; ++k)
+    {
+        long long const i = base + threadIdx.x + k * kThreads;
+        if (i < N)
+        {
+            double const x = __ddiv_rn(w[i], t);
+            w[i]           = x;
+            v += x;
+        }
+    }
+    v = block_reduce_sum(v, sh);
+    if (threadIdx.x == 0) tile_sum[blockIdx.x] = v;
+}
+
 // NATIVE ancestor selection over the inclusive cdf (cdf[N-1] ~ 1).
 // systematic: threshold_j = (j + u0) / n_out; multinomial: threshold_j = u_j.
 __global__ void __launch_bounds__(kThreads)

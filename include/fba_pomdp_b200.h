@@ -257,6 +257,11 @@ int fba_belief_normalize(fba_belief* b, double global_total);
 /* phase 3: resample this shard to n_offspring particles, the first min(n_offspring, N) stay here,
  * the surplus lands in an export buffer (fba_belief_export_ptr) for the host to ship over NCCL */
 int fba_belief_resample_shard(fba_belief* b, int64_t n_offspring, fba_rng* rng);
+/* REPLAY mode, beliefs of at least `parallel_chains_min` particles (fba_ctx_set_option, default 8192): the
+ * reference's three sequential double chains (ImportanceSampler.hpp:51, WeightedFilter.cpp:130-143,
+ * 168-183) are evaluated in parallel segments with bit-identical results; this returns how many segments
+ * (of 1024 weights) had to be recomputed sequentially since creation, -1 if that path never ran */
+int64_t fba_belief_chain_recomputed(fba_belief* b);
 /* in-place resampler statistics since creation: count blocks copied, resamples run */
 int fba_belief_resample_stats(fba_belief* b, int64_t* copies, int64_t* resamples);
 /* phases 2+3 with the quota allocation (systematic over ranks, shared offset u in [0,1)) and the
@@ -386,6 +391,8 @@ int64_t fba_runs_copies(fba_runs* runs);
 void* fba_belief_counts_ptr(fba_belief* b);
 void* fba_belief_state_ptr(fba_belief* b);
 void* fba_belief_weight_ptr(fba_belief* b);
+void* fba_belief_aux_ptr(fba_belief* b); /* device double[N]: REPLAY: the remainders R_k of WeightedFilter::sample
+                                           (valid after an update / a pick); PHILOX: the cdf */
 void* fba_belief_scalars_ptr(fba_belief* b); /* device double[4]: [0] = last un-normalised total */
 
 #ifdef __cplusplus

@@ -421,10 +421,13 @@ static const uint32_t* opar_of(const orc_model* m, const orc_structs* st, int id
     return st->o_par + (int64_t)id * m->A * m->FO;
 }
 
-double orc_is_update(const orc_model* m, const orc_structs* st, orc_belief* b, int a, int o, orc_rng* g)
+double orc_is_propose(const orc_model* m, const orc_structs* st, orc_belief* b, int a, int o, orc_rng* g,
+                      double running_total)
 {
-    /* ImportanceSampler.hpp:36-54, particles in index order */
-    double total_weight = 0;
+    /* ImportanceSampler.hpp:36-54, particles in index order. running_total: the sum over the particles
+     * BEFORE this block, so that a belief processed block after block accumulates `total_weight +=
+     * p->w` in exactly the reference's order */
+    double total_weight = running_total;
     for (int64_t i = 0; i < b->N; ++i)
     {
         const uint32_t* tp = tpar_of(m, st, b->struct_id[i]);
@@ -435,15 +438,73 @@ double orc_is_update(const orc_model* m, const orc_structs* st, orc_belief* b, i
         b->w[i] *= orc_obs_prob(m, tp, op, c, b->state[i], a, o);
         total_weight += b->w[i];
     }
-    /* WeightedFilter::normalize(total) (WeightedFilter.cpp:130-143) */
-    double acc = 0;
-    for (int64_t i = 0; i < b->N; ++i)
-    {
-        b->w[i] /= total_weight;
-        acc += b->w[i];
-    }
-    b->total_weight = acc;
     return total_weight;
+}
+
+double orc_normalize(double* w, int64_t n, double total)
+{
+    /* WeightedFilter::normalize(total) (WeightedFilter.cpp:130-143): returns the new _total_weight */
+    double acc = 0;
+    for (int64_t i = 0; i < n; ++i)
+    {
+        w[i] /= total;
+        acc += w[i];
+    }
+    return acc;
+}
+
+double orc_is_update(const orc_model* m, const orc_structs* st, orc_belief* b, int a, int o, orc_rng* g)
+{
+    double const total_weight = orc_is_propose(m, st, b, a, o, g, 0.0);
+    b->total_weight           = orc_normalize(b->w, b->N, total_weight);
+    return total_weight;
+}
+
+void orc_weighted_sample_many(const double* w, int64_t n, double total_weight, orc_rng* g, int64_t n_draws,
+                              int64_t* out)
+{
+    /* n_draws x WeightedFilter::sample (WeightedFilter.cpp:163-191) in O(n + n_draws log n) instead of
+     * O(n n_draws), with IDENTICAL results: the reference walks sample = n-1 .. 1, subtracting
+     * w[sample] from `remaining_weight` (starting at _total_weight) and stops at the first index whose
+     * remainder R[sample] is below the threshold. The remainders do not depend on the draw, so they
+     * are computed once, by the same sequential subtractions; and because every w >= 0, rounding
+     * keeps R non-increasing as the index goes down, so {k >= 1 : R[k] < threshold} is a prefix
+     * 1..m and "first hit walking down" = m = found by binary search (0 if the set is empty).
+     * tests/test_oracle_vs_golden.py pins this against orc_weighted_sample draw by draw. */
+    double* R = (double*)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    double rem = total_weight;
+    for (int64_t k = n - 1; k >= 1; --k)
+    {
+        rem -= w[k];
+        R[k] = rem;
+    }
+    for (int64_t j = 0; j < n_draws; ++j)
+    {
+        double const threshold = orc_uniform01(g) * total_weight;
+        int64_t lo = 1, hi = n; /* number of k in [1, n) with R[k] < threshold, plus one */
+        while (lo < hi)
+        {
+            int64_t const mid = (lo + hi) >> 1;
+            if (threshold > R[mid]) lo = mid + 1;
+            else
+                hi = mid;
+        }
+        out[j] = lo - 1;
+    }
+    free(R);
+}
+
+void orc_block_checksums(const float* counts, int64_t n, int64_t stride, uint64_t* out)
+{
+    /* test helper: a position-sensitive 64-bit checksum of every particle's count block (bit
+     * patterns, wrapping integer arithmetic — reproducible on any device) */
+    for (int64_t i = 0; i < n; ++i)
+    {
+        const uint32_t* c = (const uint32_t*)(counts + i * stride);
+        uint64_t h        = 0;
+        for (int64_t k = 0; k < stride; ++k) h += (uint64_t)c[k] * (2 * (uint64_t)k + 1) * 0x9E3779B97F4A7C15ull;
+        out[i] = h;
+    }
 }
 
 int64_t orc_weighted_sample(const orc_belief* b, orc_rng* g)

@@ -123,6 +123,17 @@ double orc_log_bd_score(const orc_model* m, const uint32_t* t_par, const uint32_
 
 /* importance_sampling::update (ImportanceSampler.hpp:31-62); returns the un-normalised total */
 double orc_is_update(const orc_model* m, const orc_structs* st, orc_belief* b, int a, int o, orc_rng* g);
+/* the same in pieces, for beliefs too large to hold at once: the per-particle loop over one block of
+ * particles (the running total carried from block to block in the reference's order), then
+ * WeightedFilter::normalize (WeightedFilter.cpp:130-143) over all weights */
+double orc_is_propose(const orc_model* m, const orc_structs* st, orc_belief* b, int a, int o, orc_rng* g,
+                      double running_total);
+double orc_normalize(double* w, int64_t n, double total);
+/* n_draws x WeightedFilter::sample with identical results in O(n + n_draws log n) */
+void orc_weighted_sample_many(const double* w, int64_t n, double total_weight, orc_rng* g, int64_t n_draws,
+                              int64_t* out);
+/* test helper: position-sensitive 64-bit checksum of every particle's count block */
+void orc_block_checksums(const float* counts, int64_t n, int64_t stride, uint64_t* out);
 /* WeightedFilter::sample (WeightedFilter.cpp:163-191): index of the drawn particle */
 int64_t orc_weighted_sample(const orc_belief* b, orc_rng* g);
 /* importance_sampling::resample (ImportanceSampler.hpp:71-94) into dst (same N/stride);

@@ -89,6 +89,12 @@ def lib():
         L.orc_is_update.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp]
         L.orc_weighted_sample.restype = i64
         L.orc_weighted_sample.argtypes = [vp, vp]
+        L.orc_is_propose.restype = dbl
+        L.orc_is_propose.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, dbl]
+        L.orc_normalize.restype = dbl
+        L.orc_normalize.argtypes = [vp, i64, dbl]
+        L.orc_weighted_sample_many.argtypes = [vp, i64, dbl, vp, i64, vp]
+        L.orc_block_checksums.argtypes = [vp, i64, i64, vp]
         L.orc_is_resample.argtypes = [vp, vp, vp, vp]
         L.orc_is_reset_domain_states.argtypes = [vp, vp, vp, vp, vp]
         L.orc_reject_sample.restype = i64
@@ -287,6 +293,33 @@ def obs_prob(model, t_par, o_par, counts, state, a, o):
 
 def is_update(model, structs, belief, a, o, rng):
     return lib().orc_is_update(model.ref(), structs.ref(), belief.ref(), a, o, rng.ref())
+
+
+def is_propose(model, structs, belief, a, o, rng, running_total=0.0):
+    """the per-particle loop of importance_sampling::update over one block of particles; returns the
+    running un-normalised total including this block"""
+    return lib().orc_is_propose(model.ref(), structs.ref(), belief.ref(), a, o, rng.ref(), float(running_total))
+
+
+def normalize(w, total):
+    """WeightedFilter::normalize in place; returns the new _total_weight"""
+    assert w.dtype == np.float64 and w.flags.c_contiguous
+    return lib().orc_normalize(_p(w), len(w), float(total))
+
+
+def weighted_sample_many(w, total_weight, rng, n_draws):
+    """n_draws x WeightedFilter::sample, identical results, O(n + n_draws log n)"""
+    w = np.ascontiguousarray(w, np.float64)
+    out = np.zeros(int(n_draws), np.int64)
+    lib().orc_weighted_sample_many(_p(w), len(w), float(total_weight), rng.ref(), int(n_draws), _p(out))
+    return out
+
+
+def block_checksums(counts):
+    c = np.ascontiguousarray(counts, np.float32)
+    out = np.zeros(c.shape[0], np.uint64)
+    lib().orc_block_checksums(_p(c), c.shape[0], c.shape[1], _p(out))
+    return out
 
 
 def is_resample(src, rng):

@@ -203,3 +203,34 @@ def test_log_bd_score_bit_exact(name):
     for i in range(len(z[name + "/score"])):
         got = O.log_bd_score(m, z[name + "/t_par"], z[name + "/o_par"], z[name + "/counts"][i], z[name + "/prior"])
         assert got == z[name + "/score"][i], (name, i, got, z[name + "/score"][i])
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 1000, 16384])
+def test_fast_weighted_sampling_equals_the_reference_scan(n):
+    """orc_weighted_sample_many (one sequential pass for the remainders + binary search per draw) picks
+    exactly the indices WeightedFilter::sample's O(n) scan picks (orc_weighted_sample, pinned against the
+    reference by the golden fixtures), draw by draw, on the same word stream — including weights with
+    zeros, a huge dynamic range, and thresholds that fall exactly on a remainder."""
+    import pyoracle as O
+    rs = np.random.RandomState(n)
+    for kind in range(4):
+        w = rs.random_sample(n)
+        if kind == 1:
+            w[rs.random_sample(n) < 0.5] = 0.0
+            w[0] = max(w[0], 1e-3)
+        elif kind == 2:
+            w = np.exp(rs.normal(0, 12, n))
+        elif kind == 3:
+            w = np.full(n, 1.0 / n)
+        total = O.normalize(w, float(np.cumsum(w)[-1]))
+        b = O.Belief(n, 4)
+        b.w[:] = w
+        b.total_weight = total
+        words = rs.randint(0, 2**32, size=2 * 600 + 8, dtype=np.uint64).astype(np.uint32)
+        if kind == 3 and n > 2:
+            words[:4] = [0, 0, 0, 1 << 31]          # u = 0 and u = 0.5: thresholds on exact remainders
+        r1, r2 = O.Rng(words), O.Rng(words)
+        slow = np.array([O.weighted_sample(b, r1) for _ in range(600)])
+        fast = O.weighted_sample_many(b.w, total, r2, 600)
+        np.testing.assert_array_equal(slow, fast)
+        assert r1.cur == r2.cur
