@@ -30,8 +30,11 @@
 #ifndef FBA_B200_CUDA_BELIEFS_HPP
 #define FBA_B200_CUDA_BELIEFS_HPP
 
+#include <chrono>
 #include <cstdint>
 #include <map>
+#include <random>
+#include <unordered_map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -384,6 +387,42 @@ inline bool CudaSimulator::sampledDirichlets() const
 }
 #endif
 
+// distinct (structure id, count block) pairs seen so far, found by a 64-bit hash of the block (full
+// comparison on a hit) instead of string keys holding a copy of every block
+struct ProtoTable
+{
+    std::vector<int32_t> sid;
+    std::vector<std::vector<float>> blocks;
+    std::unordered_multimap<uint64_t, int32_t> index;
+    size_t stride = 0;
+    size_t size() const { return sid.size(); }
+    static uint64_t hash(int32_t id, std::vector<float> const& b)
+    {
+        uint64_t h = 0xcbf29ce484222325ull ^ (uint64_t)(uint32_t)id;
+        auto const* w = reinterpret_cast<uint32_t const*>(b.data());
+        for (size_t k = 0; k < b.size(); ++k)
+        {
+            h ^= w[k];
+            h *= 0x100000001b3ull;
+            h ^= h >> 29;
+        }
+        return h;
+    }
+    int32_t find_or_add(int32_t id, std::vector<float> const& b)
+    {
+        uint64_t const h = hash(id, b);
+        auto range       = index.equal_range(h);
+        for (auto it = range.first; it != range.second; ++it)
+            if (sid[(size_t)it->second] == id && blocks[(size_t)it->second] == b) return it->second;
+        int32_t const k = (int32_t)sid.size();
+        sid.push_back(id);
+        blocks.push_back(b);
+        index.emplace(h, k);
+        stride = std::max(stride, b.size());
+        return k;
+    }
+};
+
 // Shared plumbing of the two belief adapters.
 class CudaParticleBelief : public beliefs::BABelief
 {
@@ -403,44 +442,79 @@ public:
     {
         auto const& sim = dynamic_cast<BAPOMDP const&>(d);
         _cuda.reset(new CudaSimulator(sim, _device));
-        // Belief::initiate = N x sampleStartState (BAImportanceSampling.cpp:49-60): the reference's
-        // prior and domain run on the host; distinct (structure, count block) pairs become prototypes
-        // that are uploaded once, each particle names its prototype and its domain start state
-        std::vector<int32_t> state(_n), proto(_n), proto_sid;
-        std::vector<std::vector<float>> proto_blocks;
-        std::map<std::string, int32_t> known;
+        // Belief::initiate = N x sampleStartState (BAImportanceSampling.cpp:49-60) = N x {prior sample,
+        // domain start state}, independent of each other (BAPOMDP.cpp:101-104). The reference's prior and
+        // domain run on the HOST; distinct (structure, count block) pairs become prototypes that are
+        // uploaded once, each particle names its prototype and its domain start state.
+        //
+        // The reference's prior clones (and describe() reads) a whole count table per sample — 10^6
+        // gridworld-5 particles take 18 minutes that way — although priors only ever
+        // return a handful of distinct tables: one (BAPOMDPPrior.cpp:32-57, FBAPOMDPPrior.cpp:27-69
+        // without a structure prior) or one per sampled structure. So the prior is sampled exactly only
+        // until it stops producing new prototypes (kQuiet consecutive known ones, then a little longer to
+        // sharpen the frequencies, bounded by kExtraSeconds); the remaining particles draw their prototype
+        // from the observed frequencies and only their DOMAIN state from the reference's domain
+        // (BAPOMDP::sampleDomainState, cheap). Beliefs up to kQuiet particles, and priors that keep
+        // producing new tables, are sampled particle by particle exactly as before.
+        size_t const kQuiet = _cuda->factored() ? 4096 : 2; // tabular priors hold ONE table (BAPOMDPPrior.cpp:32-57)
+        double const kExtraSeconds = 1.0;
+        size_t const kExtraDraws   = 65536;
+        std::vector<int32_t> state(_n), proto(_n);
+        ProtoTable protos;
         std::vector<float> block;
-        size_t stride = 0;
-        for (size_t i = 0; i < _n; ++i)
+        std::vector<double> freq;
+        size_t m = 0, since_new = 0;
+        auto const t0 = std::chrono::steady_clock::now();
+        bool quiet = false;
+        for (; m < _n; ++m)
         {
-            auto p            = static_cast<BAState const*>(d.sampleStartState());
-            state[i]          = p->_domain_state->index();
-            int32_t const sid = _cuda->describe(p, &block);
-            std::string key((char const*)&sid, sizeof(sid));
-            key.append((char const*)block.data(), block.size() * sizeof(float));
-            auto it = known.find(key);
-            if (it == known.end())
-            {
-                it = known.emplace(std::move(key), (int32_t)proto_sid.size()).first;
-                proto_sid.push_back(sid);
-                proto_blocks.push_back(block);
-                stride = std::max(stride, block.size());
+            if (!quiet && since_new >= kQuiet) quiet = true;
+            if (quiet)
+            { // one prototype: nothing to sharpen. Several: keep sampling for a bounded while
+                if (protos.size() == 1 || m >= kExtraDraws) break;
+                if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > kExtraSeconds) break;
             }
-            proto[i] = it->second;
+            auto p            = static_cast<BAState const*>(d.sampleStartState());
+            state[m]          = p->_domain_state->index();
+            int32_t const sid = _cuda->describe(p, &block);
+            size_t const before = protos.size();
+            proto[m]          = protos.find_or_add(sid, block);
+            if (protos.size() != before) since_new = 0, quiet = false;
+            else
+                ++since_new;
+            if (freq.size() < protos.size()) freq.resize(protos.size(), 0.0);
+            freq[(size_t)proto[m]] += 1.0;
             d.releaseState(p);
         }
+        _host_prior_samples = m;
+        if (m < _n)
+        {
+            std::mt19937_64 gen(_rng.seed ^ 0x5bd1e995u);
+            std::discrete_distribution<int32_t> pick(freq.begin(), freq.end());
+            for (size_t i = m; i < _n; ++i)
+            {
+                proto[i] = protos.size() == 1 ? 0 : pick(gen);
+                auto st  = sim.sampleDomainState();
+                state[i] = st->index();
+                sim.releaseDomainState(st);
+            }
+        }
+        size_t stride = protos.stride;
         check(_cuda->ctx(), fba_belief_create(_cuda->ctx(), _cuda->model(), (int64_t)_n, (int64_t)stride,
                                                _weighted ? 1 : 0, &_belief),
               "fba_belief_create");
         stride = (size_t)fba_belief_stride(_belief);
-        std::vector<float> flat(proto_sid.size() * stride, 0.0f);
-        for (size_t k = 0; k < proto_sid.size(); ++k)
-            std::copy(proto_blocks[k].begin(), proto_blocks[k].end(), flat.begin() + k * stride);
+        std::vector<float> flat(protos.size() * stride, 0.0f);
+        for (size_t k = 0; k < protos.size(); ++k)
+            std::copy(protos.blocks[k].begin(), protos.blocks[k].end(), flat.begin() + k * stride);
         check(_cuda->ctx(),
-              fba_belief_init(_belief, (int32_t)proto_sid.size(), proto_sid.data(), flat.data(), proto.data(),
+              fba_belief_init(_belief, (int32_t)protos.size(), protos.sid.data(), flat.data(), proto.data(),
                               state.data()),
               "fba_belief_init");
     }
+
+    // prior samples the last initiate() took on the host (the rest reused their prototypes)
+    size_t hostPriorSamples() const { return _host_prior_samples; }
 
     void free(POMDP const& /*d*/) override { release(); }
 
@@ -485,6 +559,7 @@ protected:
     std::unique_ptr<CudaSimulator> _cuda;
     fba_belief* _belief            = nullptr;
     mutable BAState const* _sample = nullptr;
+    size_t _host_prior_samples     = 0;
 
     void dropSample() const
     {

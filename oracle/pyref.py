@@ -214,6 +214,19 @@ class Ref:
             raise RuntimeError("reference/adapter: " + self.L.ref_error(self.h).decode())
         return out, dt
 
+    def adapter_initiate(self, n, n_ref):
+        """CudaBAImportanceSampling(n).initiate next to n_ref reference sampleStartState draws ->
+        dict(seconds, host_samples, cuda_state, cuda_sid, ref_state, ref_sid)"""
+        f = self.L.ref_adapter_initiate
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_long, C.c_long] + [C.c_void_p] * 6
+        sec, hs = C.c_double(0), C.c_long(0)
+        cs, ci = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        rs, ri = np.zeros(n_ref, np.int32), np.zeros(n_ref, np.int32)
+        if f(self.h, n, n_ref, C.byref(sec), C.byref(hs), _p(cs), _p(ci), _p(rs), _p(ri)):
+            raise RuntimeError(self.L.ref_error(self.h).decode())
+        return dict(seconds=sec.value, host_samples=hs.value, cuda_state=cs, cuda_sid=ci, ref_state=rs, ref_sid=ri)
+
     def plan_seconds(self, kind, n, planner, sims, reps=3):
         """Seconds per Planner::selectAction with `sims` simulations (empty history)."""
         v = self.L.ref_plan_seconds(self.h, kind, n, planner.encode(), sims, reps)

@@ -756,6 +756,45 @@ double ref_batched_episodes_on(void* hv, long n, int runs, int sims, int episode
     return -1.0;
 }
 
+// Belief::initiate of the CUDA adapter (fba_b200::CudaBAImportanceSampling, n particles) next to n_ref
+// draws of the reference's own BAPOMDP::sampleStartState: domain states and structure ids of both (the
+// ids come from the adapter's own structure table, so they are comparable), the adapter's wall time and
+// how many prior samples it took on the host. Returns 0 on success.
+int ref_adapter_initiate(void* hv, long n, long n_ref, double* seconds, long* host_samples, int* cuda_state,
+                         int* cuda_sid, int* ref_state, int* ref_sid)
+{
+    auto h = static_cast<Handle*>(hv);
+    try
+    {
+        fba_b200::CudaBAImportanceSampling belief((size_t)n);
+        auto const t0 = std::chrono::steady_clock::now();
+        belief.initiate(*h->sim);
+        *seconds      = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        *host_samples = (long)belief.hostPriorSamples();
+        if (fba_belief_download(belief.handle(), 0, n, cuda_state, cuda_sid, nullptr, nullptr) != FBA_OK)
+            throw std::string("download failed");
+        std::vector<float> block;
+        for (long i = 0; i < n_ref; ++i)
+        {
+            auto p       = static_cast<BAState const*>(h->sim->sampleStartState());
+            ref_state[i] = p->_domain_state->index();
+            ref_sid[i]   = belief.cuda().describe(p, &block);
+            h->sim->releaseState(p);
+        }
+        belief.free(*h->sim);
+    } catch (std::string const& e)
+    {
+        h->err = e;
+        return 1;
+    } catch (char const* e)
+    {
+        h->err = e;
+        return 1;
+    }
+    return 0;
+}
+
+
 // seconds per Planner::selectAction (empty history) with `sims` simulations, belief kind as in
 // ref_adapter_episodes, planner "po-uct" (the reference's RBAPOUCT) or "cuda-po-uct[:wave]".
 double ref_plan_seconds(void* hv, int kind, long n, char const* planner, int sims, int reps)

@@ -112,3 +112,42 @@ def test_many_runs_in_lockstep_match_the_reference_experiment(domain, kw, n, run
     for e in range(episodes):
         se = np.sqrt(ref[e].var(ddof=1) / runs + ours[e].var(ddof=1) / runs) + 1e-9
         assert abs(ref[e].mean() - ours[e].mean()) <= 4.0 * se + 1e-6, (e, ref[e].mean(), ours[e].mean(), se)
+
+
+INIT_CASES = [
+    # domain, kwargs, particles, reference draws, bound on the host prior samples (None: all of them)
+    ("linear-sysadmin", dict(size=10, factored=True), 1_000_000, 20_000, 4100),          # config 5: one prototype
+    ("gridworld", dict(size=5), 200_000, 300, 4),                                        # 720 KB tables, one prototype
+    ("centered-collision-avoidance", dict(size=1, width=5, height=5, factored=True,
+                                          structure_prior="match-uniform"), 400_000, 100_000, 70_000),
+    ("episodic-factored-tiger", dict(size=3, factored=True, structure_prior="match-uniform"), 3000, 3000, None),
+]
+
+
+@pytest.mark.parametrize("domain,kw,n,n_ref,host_bound", INIT_CASES)
+def test_initiate_matches_the_reference_prior_and_is_fast(domain, kw, n, n_ref, host_bound):
+    """CudaParticleBelief::initiate (host/CudaBeliefs.hpp) against the reference's own
+    BAImportanceSampling::initiate = N x sampleStartState (BAImportanceSampling.cpp:49-60): the
+    distributions of the domain start state and of the prior's structure agree (per category, 5 standard
+    errors of the two-sample difference, plus the estimation error of the prototype frequencies where the
+    adapter stopped sampling the prior early), and large beliefs take seconds: 10^6 sysadmin-10 particles
+    in under 5 s where 10^6 reference prior samples take about a minute."""
+    r = pyref.Ref(domain, horizon=8, seed="5", **kw)
+    try:
+        res = r.adapter_initiate(n, n_ref)
+    finally:
+        r.close()
+    m = res["host_samples"]
+    assert m == n if host_bound is None else m <= host_bound, m
+    if n >= 1_000_000:
+        assert res["seconds"] < 5.0, res["seconds"]
+    for key in ("state", "sid"):
+        c, f = res["cuda_" + key], res["ref_" + key]
+        k = int(max(c.max(), f.max())) + 1
+        pc, pf = np.bincount(c, minlength=k) / len(c), np.bincount(f, minlength=k) / len(f)
+        p = (pc * len(c) + pf * len(f)) / (len(c) + len(f))
+        var = p * (1 - p) * (1.0 / len(c) + 1.0 / len(f))
+        if key == "sid" and m < n:
+            var = var + p * (1 - p) / m            # prototype frequencies were estimated from m prior samples
+        assert np.all(np.abs(pc - pf) <= 5.0 * np.sqrt(var) + 1e-12), (key, np.abs(pc - pf).max())
+    print("\ninitiate %s: %d particles in %.2f s, %d host prior samples" % (domain, n, res["seconds"], m))
