@@ -28,19 +28,28 @@
 
 #include "configurations/BAConf.hpp"
 #include "environment/Environment.hpp"
+#include "experiments/BAPOMDPExperiment.hpp"
 #include "environment/Reward.hpp"
 #include "environment/Terminal.hpp"
 
 namespace fba_b200 {
 
-// returns[episode][run] = discounted return of that episode of that run
+// returns[episode][run] = discounted return of that episode of that run.
+// result (may be NULL): the reference's own experiment::bapomdp::Result (BAPOMDPExperiment.hpp:21-37),
+// filled the way experiment::bapomdp::run fills it (BAPOMDPExperiment.cpp:61-65) — per episode the
+// returns of all runs, in run order, into `ret`, and each run's seconds per step of that episode into
+// `duration` — so that Result::log prints the reference's result file (BAPOMDPExperiment.cpp:20-30:
+// "return mean, return var, return count, return stder, step duration mean") and the analysis/
+// scripts read it unchanged. In lockstep one global step serves every active run at once: its wall
+// time is split evenly over them (the reference's boost::timer is CPU time of one run on one core).
 inline std::vector<std::vector<double>> runBatchedExperiment(
     BAPOMDP const& bapomdp,
     configurations::BAConf const& conf,
     int runs,
-    int sims_per_wave = 1,
-    uint64_t seed     = 4711,
-    int device        = 0)
+    int sims_per_wave                  = 1,
+    uint64_t seed                      = 4711,
+    int device                         = 0,
+    experiment::bapomdp::Result* result = nullptr)
 {
     if (runs < 1) throw std::string("runBatchedExperiment: runs must be at least 1");
     // FBA_B200_TRACE=1: wall time per phase on stderr
@@ -159,10 +168,14 @@ inline std::vector<std::vector<double>> runBatchedExperiment(
     std::vector<uint8_t> active((size_t)runs, 1), starting((size_t)runs), updating((size_t)runs);
     std::vector<int32_t> depth((size_t)runs, 0), act((size_t)runs, 0), obs((size_t)runs, 0);
     std::vector<double> disc((size_t)runs, 1.0);
+    std::vector<std::vector<double>> seconds((size_t)E, std::vector<double>((size_t)runs, 0.0));
+    std::vector<std::vector<int>> length((size_t)E, std::vector<int>((size_t)runs, 0));
+    std::vector<int> serving((size_t)runs, -1); // the episode each run's current global step belongs to
     try
     {
         for (;;)
         {
+            auto const step_t0 = std::chrono::steady_clock::now();
             bool any = false, any_start = false;
             for (int r = 0; r < runs; ++r)
             {
@@ -193,7 +206,10 @@ inline std::vector<std::vector<double>> runBatchedExperiment(
             for (int r = 0; r < runs; ++r)
             {
                 updating[(size_t)r] = 0;
+                serving[(size_t)r]  = -1;
                 if (!active[(size_t)r]) continue;
+                serving[(size_t)r] = episode[(size_t)r];
+                ++length[(size_t)episode[(size_t)r]][(size_t)r];
                 Observation const* o(nullptr);
                 Reward rew(0);
                 auto const terminal = env->step(&s[(size_t)r], action_of[(size_t)act[(size_t)r]], &o, &rew);
@@ -214,6 +230,16 @@ inline std::vector<std::vector<double>> runBatchedExperiment(
             check(ctx, fba_runs_update_estimation(batch.r, act.data(), obs.data(), updating.data(), &rng, nullptr),
                   "fba_runs_update_estimation");
             lap(4);
+            if (result)
+            { // the update call above synchronises only when it returns likelihoods: wait for the step's work
+                check(ctx, fba_ctx_synchronize(ctx), "fba_ctx_synchronize");
+                int served = 0;
+                for (int r = 0; r < runs; ++r) served += serving[(size_t)r] >= 0;
+                double const dt =
+                    std::chrono::duration<double>(std::chrono::steady_clock::now() - step_t0).count() / std::max(served, 1);
+                for (int r = 0; r < runs; ++r)
+                    if (serving[(size_t)r] >= 0) seconds[(size_t)serving[(size_t)r]][(size_t)r] += dt;
+            }
         }
         if (trace)
             std::fprintf(stderr,
@@ -228,6 +254,16 @@ inline std::vector<std::vector<double>> runBatchedExperiment(
         throw;
     }
     for (auto l : legal) bapomdp.releaseAction(l);
+    if (result)
+    {
+        *result = experiment::bapomdp::Result(E);
+        for (int e = 0; e < E; ++e)
+            for (int r = 0; r < runs; ++r)
+            { // BAPOMDPExperiment.cpp:63-64
+                result->r[(size_t)e].ret.add(returns[(size_t)e][(size_t)r]);
+                result->r[(size_t)e].duration.add(seconds[(size_t)e][(size_t)r] / std::max(length[(size_t)e][(size_t)r], 1));
+            }
+    }
     return returns;
 }
 

@@ -214,6 +214,17 @@ class Ref:
             raise RuntimeError("reference/adapter: " + self.L.ref_error(self.h).decode())
         return out, dt
 
+    def batched_experiment_file(self, n, runs, sims, episodes, path, seed=4711):
+        """runBatchedExperiment writing the reference's result file -> (returns[episodes, runs], seconds)"""
+        f = self.L.ref_batched_experiment_file
+        f.restype = C.c_double
+        f.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int, C.c_ulonglong, C.c_char_p, C.c_void_p]
+        out = np.zeros((episodes, runs), np.float64)
+        dt = f(self.h, n, runs, sims, episodes, seed, str(path).encode(), _p(out))
+        if dt < 0:
+            raise RuntimeError(self.L.ref_error(self.h).decode())
+        return out, dt
+
     def adapter_initiate(self, n, n_ref):
         """CudaBAImportanceSampling(n).initiate next to n_ref reference sampleStartState draws ->
         dict(seconds, host_samples, cuda_state, cuda_sid, ref_state, ref_sid)"""

@@ -27,6 +27,7 @@
 #include <chrono>
 #include <cstdint>
 #include <cstring>
+#include <fstream>
 #include <memory>
 #include <string>
 #include <vector>
@@ -742,6 +743,41 @@ double ref_batched_episodes_on(void* hv, long n, int runs, int sims, int episode
         double const dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         for (int e = 0; e < episodes; ++e)
             for (int r = 0; r < runs; ++r) returns[(size_t)e * runs + r] = res[e][r];
+        return dt;
+    } catch (std::string const& e)
+    {
+        h->err = e;
+    } catch (char const* e)
+    {
+        h->err = e;
+    } catch (std::exception const& e)
+    {
+        h->err = e.what();
+    }
+    return -1.0;
+}
+
+// the same, writing the reference's result file (experiment::bapomdp::Result::log, BAPOMDPExperiment.cpp:20-30,
+// what bapomdp.cpp:43-44 writes to --output-file) to `path`
+double ref_batched_experiment_file(void* hv, long n, int runs, int sims, int episodes, unsigned long long seed,
+                                   char const* path, double* returns)
+{
+    auto h = static_cast<Handle*>(hv);
+    try
+    {
+        auto conf                                = h->conf;
+        conf.belief_conf.particle_amount         = n;
+        conf.planner_conf.mcts_simulation_amount = sims;
+        conf.planner_conf.mcts_max_depth         = conf.horizon;
+        conf.num_episodes                        = episodes;
+        experiment::bapomdp::Result result(episodes);
+        auto t0  = std::chrono::steady_clock::now();
+        auto res = fba_b200::runBatchedExperiment(*h->sim, conf, runs, 1, seed, 0, &result);
+        double const dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        for (int e = 0; e < episodes; ++e)
+            for (int r = 0; r < runs; ++r) returns[(size_t)e * runs + r] = res[e][r];
+        std::ofstream f(path);
+        result.log(f);
         return dt;
     } catch (std::string const& e)
     {

@@ -151,3 +151,37 @@ def test_initiate_matches_the_reference_prior_and_is_fast(domain, kw, n, n_ref, 
             var = var + p * (1 - p) / m            # prototype frequencies were estimated from m prior samples
         assert np.all(np.abs(pc - pf) <= 5.0 * np.sqrt(var) + 1e-12), (key, np.abs(pc - pf).max())
     print("\ninitiate %s: %d particles in %.2f s, %d host prior samples" % (domain, n, res["seconds"], m))
+
+
+def test_batched_experiment_writes_the_reference_result_file(tmp_path):
+    """runBatchedExperiment fills the reference's own experiment::bapomdp::Result and Result::log writes
+    the reference's result file (BAPOMDPExperiment.cpp:20-30,61-65): read back the way
+    analysis/preprocess/merge_result_files.py:38 does (np.loadtxt with ',' after two '#' header lines),
+    one row per episode = return mean, sample variance, count = runs, standard error, mean seconds per
+    step — consistent with the raw returns; two such files merge with that script's formula."""
+    runs, episodes = 32, 3
+    r = pyref.Ref("episodic-tiger", horizon=8, seed="3")
+    try:
+        files, rets = [], []
+        for k, seed in enumerate((4711, 9001)):
+            path = tmp_path / ("%d.res" % k)
+            ret, dt = r.batched_experiment_file(128, runs, 64, episodes, path, seed=seed)
+            files.append(path)
+            rets.append(ret)
+    finally:
+        r.close()
+    head = open(files[0]).read().splitlines()[:2]
+    assert head == ["# version 1:",
+                    "# return mean, return var, return count, return stder, step duration mean"]
+    tabs = [np.loadtxt(f, delimiter=",") for f in files]
+    for tab, ret in zip(tabs, rets):
+        assert tab.shape == (episodes, 5)
+        np.testing.assert_allclose(tab[:, 0], ret.mean(1), rtol=1e-5)          # 6 significant digits in the file
+        np.testing.assert_allclose(tab[:, 1], ret.var(1, ddof=1), rtol=1e-4)
+        np.testing.assert_array_equal(tab[:, 2], runs)
+        np.testing.assert_allclose(tab[:, 3], np.sqrt(ret.var(1, ddof=1) / runs), rtol=1e-4)
+        assert np.all(tab[:, 4] > 0) and np.all(tab[:, 4] < 1.0)
+    # merge_result_files.py:63-80 on the two files = the statistics of the pooled runs
+    n = tabs[0][:, 2] + tabs[1][:, 2]
+    mu = (tabs[0][:, 0] * tabs[0][:, 2] + tabs[1][:, 0] * tabs[1][:, 2]) / n
+    np.testing.assert_allclose(mu, np.concatenate(rets, 1).mean(1), rtol=1e-5)
