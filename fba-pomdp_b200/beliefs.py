@@ -240,6 +240,21 @@ class _ParticleBelief:
         _check(self.ctx.h, self.L.fba_belief_sample(self.h, C.byref(rng), C.byref(i)))
         return i.value
 
+    def replay_history(self, episode_len, actions, observations, rng, max_attempts=1_000_000):
+        """computePosterior of the MH structure beliefs (MHNIPS2018.cpp:41-109) on every particle: the whole
+        (action, observation) history replayed with episode retries; each particle's domain state becomes
+        the state after the last step."""
+        ln = np.ascontiguousarray(episode_len, np.int32)
+        ac = np.ascontiguousarray(actions, np.int32)
+        ob = np.ascontiguousarray(observations, np.int32)
+        _check(self.ctx.h, self.L.fba_belief_replay_history(self.h, len(ln), ptr(ln), ptr(ac), ptr(ob), C.byref(rng),
+                                                            int(max_attempts)))
+
+    def assign_from(self, first, src, src_index):
+        """particles src[src_index[j]] -> self[first + j] (MHNIPS2018.cpp:241-246: accepted proposals)"""
+        idx = np.ascontiguousarray(src_index, np.int64)
+        _check(self.ctx.h, self.L.fba_belief_assign_from(self.h, int(first), src.h, len(idx), ptr(idx)))
+
     def resetDomainStateDistribution(self, rng):
         """BABelief::resetDomainStateDistribution (BABelief.hpp:30)."""
         _check(self.ctx.h, self.L.fba_belief_reset_domain_states(self.h, C.byref(rng)))

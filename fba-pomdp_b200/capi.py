@@ -36,7 +36,7 @@ SYMBOLS = [
     "fba_belief_normalize", "fba_belief_resample_shard", "fba_belief_resample_stats",
     "fba_belief_shard_resample", "fba_belief_shard_resample_async", "fba_belief_shard_plan",
     "fba_belief_p2p_export", "fba_belief_p2p_open", "fba_belief_sharded_update", "fba_belief_p2p_timeouts",
-    "fba_belief_p2p_set_timeout", "fba_ctx_counter", "fba_belief_aux_ptr", "fba_belief_chain_recomputed",
+    "fba_belief_p2p_set_timeout", "fba_ctx_counter", "fba_belief_replay_history", "fba_belief_assign_from", "fba_belief_aux_ptr", "fba_belief_chain_recomputed",
     "fba_belief_dropped_records", "fba_belief_reserve_export", "fba_belief_import_from", "fba_belief_export_count",
     "fba_belief_export_ptr", "fba_belief_import_ptr", "fba_belief_record_bytes", "fba_belief_import",
     "fba_belief_counts_ptr", "fba_belief_state_ptr", "fba_belief_weight_ptr",
@@ -122,6 +122,8 @@ def lib():
             "fba_belief_shard_resample_async": (C.c_int, [vp, vp, i32, i32, dbl, vp]),
             "fba_belief_shard_plan": (C.c_int, [vp, vp, i32, i32, dbl, vp, vp]),
             "fba_ctx_counter": (i64, [vp, i32]),
+            "fba_belief_replay_history": (C.c_int, [vp, i32, vp, vp, vp, vp, i64]),
+            "fba_belief_assign_from": (C.c_int, [vp, i64, vp, i64, vp]),
             "fba_belief_aux_ptr": (vp, [vp]),
             "fba_belief_chain_recomputed": (i64, [vp]),
             "fba_belief_p2p_export": (C.c_int, [vp, vp]),

@@ -2149,6 +2149,116 @@ extern "C" int fba_belief_log_bd_score(fba_belief* b, fba_belief* prior, double*
     return FBA_OK;
 }
 
+// ---- MH structure beliefs: history replay on proposal particles, particle transfer between beliefs ----
+
+extern "C" int fba_belief_replay_history(fba_belief* b, int32_t n_episodes, const int32_t* episode_len,
+                                         const int32_t* actions, const int32_t* observations, fba_rng* rng,
+                                         int64_t max_attempts)
+{
+    if (!b || !rng || n_episodes < 0 || (n_episodes && (!episode_len || !actions || !observations))) return FBA_ERR_INVALID;
+    fba_ctx* ctx      = b->ctx;
+    DevModel const& D = b->m->dev;
+    REQUIRE(ctx, b->delta_cap == 0, "replay_history: dense storage only");
+    REQUIRE(ctx, max_attempts >= 1, "replay_history: max_attempts must be at least 1");
+    long long total = 0;
+    int max_len     = 1;
+    for (int e = 0; e < n_episodes; ++e)
+    {
+        REQUIRE(ctx, episode_len[e] >= 0, "replay_history: negative episode length");
+        total += episode_len[e];
+        max_len = std::max(max_len, (int)episode_len[e]);
+    }
+    for (long long k = 0; k < total; ++k)
+    {
+        REQUIRE(ctx, actions[k] >= 0 && actions[k] < D.A, "replay_history: action out of range");
+        REQUIRE(ctx, observations[k] >= 0 && observations[k] < D.O, "replay_history: observation out of range");
+    }
+    CU(ctx, cudaSetDevice(ctx->device));
+    DevTmp<int> d_len, d_act, d_obs, d_rec, d_failed;
+    CU(ctx, cudaMalloc(&d_len, std::max(1, (int)n_episodes) * sizeof(int)));
+    CU(ctx, cudaMalloc(&d_act, std::max(1ll, total) * sizeof(int)));
+    CU(ctx, cudaMalloc(&d_obs, std::max(1ll, total) * sizeof(int)));
+    CU(ctx, cudaMalloc(&d_rec, (size_t)b->N * max_len * D.J * sizeof(int)));
+    CU(ctx, cudaMalloc(&d_failed, sizeof(int)));
+    CU(ctx, cudaMemsetAsync(d_failed, 0, sizeof(int), ctx->stream));
+    if (n_episodes)
+        CU(ctx, cudaMemcpyAsync(d_len, episode_len, n_episodes * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    if (total)
+    {
+        CU(ctx, cudaMemcpyAsync(d_act, actions, total * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(d_obs, observations, total * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    HistoryArgs H{};
+    H.n_episodes = n_episodes, H.max_len = max_len;
+    H.episode_len = d_len, H.actions = d_act, H.observations = d_obs;
+    H.max_attempts = max_attempts;
+    int rc;
+    bool const lr = b->m->long_rows;
+    if (rng->mode == FBA_RNG_REPLAY)
+    { // every particle draws from its own equal slice of the remaining words
+        long long const need = rng->n_words - rng->cursor, per = need / b->N;
+        REQUIRE(ctx, per >= 1, "replay_history: the replay stream is shorter than one word per particle");
+        if ((rc = stage_words(ctx, rng, per * b->N))) return rc;
+        if ((rc = clear_flag(ctx))) return rc;
+        if (lr)
+            LAUNCH(ctx, (k_mh_replay<true, true>), blocks_for(b->N), kThreads, D, b->counts[b->cur], b->stride,
+                   b->state[b->cur], b->sid[b->cur], b->N, H, replay_args(ctx, per * b->N, per, false), (int*)d_rec,
+                   (int*)d_failed, ctx->d_flag);
+        else
+            LAUNCH(ctx, (k_mh_replay<true, false>), blocks_for(b->N), kThreads, D, b->counts[b->cur], b->stride,
+                   b->state[b->cur], b->sid[b->cur], b->N, H, replay_args(ctx, per * b->N, per, false), (int*)d_rec,
+                   (int*)d_failed, ctx->d_flag);
+        rng->cursor += per * b->N;
+    } else
+    {
+        if (lr)
+            LAUNCH(ctx, (k_mh_replay<false, true>), blocks_for(b->N), kThreads, D, b->counts[b->cur], b->stride,
+                   b->state[b->cur], b->sid[b->cur], b->N, H, philox_args(rng), (int*)d_rec, (int*)d_failed,
+                   ctx->d_flag);
+        else
+            LAUNCH(ctx, (k_mh_replay<false, false>), blocks_for(b->N), kThreads, D, b->counts[b->cur], b->stride,
+                   b->state[b->cur], b->sid[b->cur], b->N, H, philox_args(rng), (int*)d_rec, (int*)d_failed,
+                   ctx->d_flag);
+    }
+    CU(ctx, cudaMemcpyAsync(ctx->h_flag, d_failed, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (*ctx->h_flag)
+    {
+        ctx->err = "replay_history: a particle needed more than max_attempts episode attempts (its model gives the "
+                   "observed history almost no probability)";
+        return FBA_ERR_CAPACITY;
+    }
+    if (rng->mode == FBA_RNG_REPLAY && (rc = check_flag(ctx))) return rc;
+    b->suffix_valid = b->cdf_valid = false;
+    return FBA_OK;
+}
+
+extern "C" int fba_belief_assign_from(fba_belief* dst, int64_t first, fba_belief* src, int64_t n,
+                                      const int64_t* src_index)
+{
+    if (!dst || !src || n < 0 || (n && !src_index)) return FBA_ERR_INVALID;
+    fba_ctx* ctx = dst->ctx;
+    REQUIRE(ctx, src->ctx == ctx && src->m == dst->m && src->stride == dst->stride && dst->delta_cap == 0
+                     && src->delta_cap == 0,
+            "assign_from: both beliefs must share context, model and stride (dense storage)");
+    REQUIRE(ctx, first >= 0 && first + n <= dst->N, "assign_from: destination range out of bounds");
+    REQUIRE(ctx, n <= dst->anc_cap, "assign_from: too many particles for one call");
+    if (n == 0) return FBA_OK;
+    std::vector<int> idx((size_t)n);
+    for (int64_t j = 0; j < n; ++j)
+    {
+        REQUIRE(ctx, src_index[j] >= 0 && src_index[j] < src->N, "assign_from: source index out of range");
+        idx[(size_t)j] = (int)src_index[j];
+    }
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpyAsync(dst->anc, idx.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, k_gather, stream_grid(ctx, n), kThreads, src->counts[src->cur], dst->counts[dst->cur] + first * dst->stride,
+           dst->stride, src->state[src->cur], dst->state[dst->cur] + first, src->sid[src->cur], dst->sid[dst->cur] + first,
+           dst->m->d_sizes, (double*)nullptr, 0.0, dst->anc, (long long)n, 0);
+    CU(ctx, cudaStreamSynchronize(ctx->stream)); // idx is a host temporary
+    return FBA_OK;
+}
+
 // ---- POMCP, tree on the device -------------------------------------------------------------------
 
 struct fba_tree

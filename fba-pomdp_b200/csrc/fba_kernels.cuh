@@ -2506,4 +2506,75 @@ __global__ void __launch_bounds__(kThreads)
     if (g.overrun) *overrun = 1;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// MH structure beliefs: computePosterior (MHNIPS2018.cpp:41-109) — the whole
+// (action, observation) history replayed on every PROPOSAL particle, one thread per proposal. Per
+// episode attempt: a domain start state, then per step s' and o sampled from the particle's own counts
+// (expected mode whatever the simulator's, MHNIPS2018.cpp:47); a wrong observation abandons the attempt
+// — the cells incremented so far in this episode get -1, in step order — and the episode is tried again;
+// a right one gets its +1 on the cells hyper_step<STEP_RECORD> recorded (the simulated observation IS
+// the observed one then). state[i] = the state after the last step. rec: per-particle scratch of the
+// current attempt's cells, max_len x J ints.
+// ------------------------------------------------------------------------------------------------
+struct HistoryArgs
+{
+    int n_episodes, max_len;
+    const int* episode_len;
+    const int* actions;
+    const int* observations;
+    long long max_attempts;
+};
+
+template<bool REPLAY, bool LONG>
+__global__ void __launch_bounds__(kThreads)
+    k_mh_replay(DevModel M, float* counts, long long stride, int* __restrict__ state, const int* __restrict__ sid,
+                long long N, HistoryArgs H, RngArgs ra, int* __restrict__ rec_all, int* __restrict__ failed,
+                int* __restrict__ overrun)
+{
+    long long const i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    auto g            = RngOf<REPLAY>::make(ra, i);
+    float* c          = counts + i * stride;
+    const Node* nodes = M.nodes + (long long)sid[i] * M.A * M.J;
+    int* rec          = rec_all + i * (long long)H.max_len * M.J;
+    long long attempts = 0;
+    int new_s = 0, first = 0;
+    for (int e = 0; e < H.n_episodes; ++e)
+    {
+        int const len = H.episode_len[e];
+        for (;;)
+        {
+            if (++attempts > H.max_attempts)
+            {
+                *failed  = 1;
+                state[i] = new_s;
+                return;
+            }
+            int s       = sample_start_state(M, g);
+            int applied = 0;
+            for (int t = 0; t < len; ++t)
+            {
+                int const a = H.actions[first + t];
+                int o;
+                Feat x2;
+                int* r = rec + applied * M.J;
+                int const s2 =
+                    hyper_step<STEP_RECORD, decltype(g), false, LONG, false>(M, nodes + (long long)a * M.J, c, s, g, o, x2, r);
+                new_s = s2;
+                if (o != H.observations[first + t]) break;
+                for (int k = 0; k < M.J; ++k) c[r[k]] = __fadd_rn(c[r[k]], 1.0f);
+                ++applied;
+                s = s2;
+            }
+            if (applied == len) break;
+            for (int t = 0; t < applied; ++t)
+                for (int k = 0; k < M.J; ++k) c[rec[t * M.J + k]] = __fadd_rn(c[rec[t * M.J + k]], -1.0f);
+        }
+        first += len;
+    }
+    state[i] = new_s;
+    if (g.overrun) *overrun = 1;
+}
+
 } // namespace fba

@@ -198,22 +198,60 @@ public:
                     }
             }
         } else
+            return describeModel(const_cast<FBAPOMDPState*>(static_cast<FBAPOMDPState const*>(p))->model(), counts);
+        int32_t id = -1;
+        check(_ctx, fba_model_add_structures(_model, 1, tp.data(), op.data(), &id), "fba_model_add_structures");
+        return id;
+    }
+
+    // the same for a bare factored model (e.g. FBAPOMDPPrior::computePriorModel's result)
+    int32_t describeModel(::bayes_adaptive::factored::BABNModel* model, std::vector<float>* counts) const
+    {
+        std::vector<uint32_t> tp((size_t)A() * FS()), op((size_t)A() * FO());
+        counts->clear();
+        IndexAction a(0);
+        for (int ai = 0; ai < A(); ++ai)
         {
-            auto model = const_cast<FBAPOMDPState*>(static_cast<FBAPOMDPState const*>(p))->model();
-            IndexAction a(0);
-            for (int ai = 0; ai < A(); ++ai)
-            {
-                a.index(ai);
-                for (int f = 0; f < FS(); ++f)
-                    tp[(size_t)ai * FS() + f] = dumpNode(model->transitionNode(&a, f), _feat_s[f], counts);
-                for (int g = 0; g < FO(); ++g)
-                    op[(size_t)ai * FO() + g] = dumpNode(model->observationNode(&a, g), _feat_o[g], counts);
-            }
+            a.index(ai);
+            for (int f = 0; f < FS(); ++f)
+                tp[(size_t)ai * FS() + f] = dumpNode(model->transitionNode(&a, f), _feat_s[f], counts);
+            for (int g = 0; g < FO(); ++g)
+                op[(size_t)ai * FO() + g] = dumpNode(model->observationNode(&a, g), _feat_o[g], counts);
         }
         int32_t id = -1;
         check(_ctx, fba_model_add_structures(_model, 1, tp.data(), op.data(), &id), "fba_model_add_structures");
         return id;
     }
+
+    // structure id <-> the reference's BABNModel::Structure (parents per action and feature, ascending)
+    ::bayes_adaptive::factored::BABNModel::Structure structureOf(int32_t struct_id) const
+    {
+        std::vector<uint32_t> tp((size_t)A() * FS()), op((size_t)A() * FO());
+        check(_ctx, fba_model_get_structure(_model, struct_id, tp.data(), op.data()), "fba_model_get_structure");
+        ::bayes_adaptive::factored::BABNModel::Structure st;
+        st.T.resize((size_t)A()), st.O.resize((size_t)A());
+        for (int a = 0; a < A(); ++a)
+        {
+            for (int f = 0; f < FS(); ++f) st.T[(size_t)a].push_back(parentsOf(tp[(size_t)a * FS() + f]));
+            for (int g = 0; g < FO(); ++g) st.O[(size_t)a].push_back(parentsOf(op[(size_t)a * FO() + g]));
+        }
+        return st;
+    }
+    int32_t structureId(::bayes_adaptive::factored::BABNModel::Structure const& st) const
+    {
+        std::vector<uint32_t> tp((size_t)A() * FS()), op((size_t)A() * FO());
+        for (int a = 0; a < A(); ++a)
+        {
+            for (int f = 0; f < FS(); ++f)
+                for (auto p : st.T[(size_t)a][(size_t)f]) tp[(size_t)a * FS() + f] |= 1u << p;
+            for (int g = 0; g < FO(); ++g)
+                for (auto p : st.O[(size_t)a][(size_t)g]) op[(size_t)a * FO() + g] |= 1u << p;
+        }
+        int32_t id = -1;
+        check(_ctx, fba_model_add_structures(_model, 1, tp.data(), op.data(), &id), "fba_model_add_structures");
+        return id;
+    }
+    ::bayes_adaptive::factored::FBAPOMDP const* fbapomdp() const { return _fbapomdp; }
 
     // the reverse: a host-side reference particle from a downloaded block (Belief::sample())
     BAState* materialise(int32_t struct_id, int32_t state, std::vector<float> const& counts) const
@@ -441,7 +479,7 @@ public:
     void initiate(POMDP const& d) override
     {
         auto const& sim = dynamic_cast<BAPOMDP const&>(d);
-        _cuda.reset(new CudaSimulator(sim, _device));
+        _cuda.reset(new CudaSimulator(sim, _device, 4096, -1, _start_samples));
         // Belief::initiate = N x sampleStartState (BAImportanceSampling.cpp:49-60) = N x {prior sample,
         // domain start state}, independent of each other (BAPOMDP.cpp:101-104). The reference's prior and
         // domain run on the HOST; distinct (structure, count block) pairs become prototypes that are
@@ -499,7 +537,7 @@ public:
                 sim.releaseDomainState(st);
             }
         }
-        size_t stride = protos.stride;
+        size_t stride = std::max(protos.stride, minimumStride(d));
         check(_cuda->ctx(), fba_belief_create(_cuda->ctx(), _cuda->model(), (int64_t)_n, (int64_t)stride,
                                                _weighted ? 1 : 0, &_belief),
               "fba_belief_create");
@@ -560,6 +598,11 @@ protected:
     fba_belief* _belief            = nullptr;
     mutable BAState const* _sample = nullptr;
     size_t _host_prior_samples     = 0;
+    int _start_samples             = 0; // > 0: the simulator learns the domain's start distribution (device draws)
+
+    // cells a particle block must hold beyond what the prior's prototypes need (beliefs that change
+    // structures later override this)
+    virtual size_t minimumStride(POMDP const& /*d*/) const { return 0; }
 
     void dropSample() const
     {

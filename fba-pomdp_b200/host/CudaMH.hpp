@@ -1,0 +1,244 @@
+// Drop-in for beliefs::bayes_adaptive::factored::MHNIPS2018
+// (src/beliefs/bayes-adaptive/factored/MHNIPS2018.{hpp,cpp}), the first of the reference's
+// Metropolis-Hastings structure beliefs, behind the same BABelief interface.
+//
+// What runs where:
+//   * updateEstimation (MHNIPS2018.cpp:166-186) = importance-sampling update + resample on the GPU
+//     (fba_belief_update_estimation, the kernels of SURVEY.md §8 a1/a2), the step likelihood read back to
+//     accumulate the log likelihood on the host, the (action, observation) history kept on the host.
+//   * MH (MHNIPS2018.cpp:188-255), triggered when the log likelihood drops below the threshold: the
+//     reference proposes ONE structure at a time and replays the whole history on it before the next
+//     proposal; proposals are independent of each other, so here a BATCH of proposals is drawn at once —
+//     source particles on the device (fba_belief_sample_batch), the 50/50 keep-or-mutate choice, the
+//     domain's own `mutate` and the prior model of each proposed structure by the reference's own code on
+//     the host (FBAPOMDP::mutate, FBAPOMDPPrior::computePriorModel: small, domain-specific) — and then
+//     every proposal replays the history in its own GPU thread (fba_belief_replay_history =
+//     computePosterior, MHNIPS2018.cpp:41-109) and is scored against its prior with
+//     BABNModel::LogBDScore on the GPU (fba_belief_log_bd_score). Accept / reject (MHNIPS2018.cpp:240) is
+//     one comparison per proposal on the host; accepted proposals, in proposal order, fill the new belief
+//     (fba_belief_assign_from) until it holds `size` particles — the distribution of the new belief is the
+//     reference's, because its proposals are i.i.d. too.
+#ifndef FBA_B200_CUDA_MH_HPP
+#define FBA_B200_CUDA_MH_HPP
+
+#include <cmath>
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "CudaBeliefs.hpp"
+
+#include "bayes-adaptive/priors/FBAPOMDPPrior.hpp"
+
+namespace fba_b200 {
+
+class CudaMHNIPS2018 : public CudaParticleBelief
+{
+public:
+    CudaMHNIPS2018(size_t size, double ll_threshold, uint64_t seed = 42, int device = 0) :
+            CudaParticleBelief(size, true, seed, device), _ll_threshold(ll_threshold)
+    {
+        if (size < 1) throw("MHNIPS2018::cannot initiate MH with size " + std::to_string(size)); // as :114-117
+        if (ll_threshold >= 0)                                                                    // as :119-124
+            throw("MHNIPS2018::cannot initiate with threshold >= 0 (is:" + std::to_string(ll_threshold) + ")");
+        _start_samples = 1 << 16; // computePosterior draws a domain start state per episode attempt, on the device
+    }
+
+    void initiate(POMDP const& d) override
+    {
+        CudaParticleBelief::initiate(d);
+        _history.assign(1, {});
+        _log_likelihood = 0.0;
+        _mh_runs = _proposals = 0;
+    }
+
+    // MHNIPS2018.cpp:132-147: a fresh domain state for every particle (no resampling: the weights are
+    // uniform after every update), and a new episode in the history
+    void resetDomainStateDistribution(BAPOMDP const& bapomdp) override
+    {
+        std::vector<int32_t> state(_n);
+        for (size_t i = 0; i < _n; ++i)
+        {
+            auto s   = bapomdp.sampleDomainState();
+            state[i] = s->index();
+            bapomdp.releaseDomainState(s);
+        }
+        check(_cuda->ctx(), fba_belief_upload(_belief, 0, (int64_t)_n, state.data(), nullptr, nullptr, nullptr),
+              "fba_belief_upload");
+        if (!_history.back().empty()) _history.emplace_back();
+    }
+
+    void updateEstimation(Action const* a, Observation const* o, POMDP const& d) override
+    {
+        double lik = 0.0;
+        check(_cuda->ctx(), fba_belief_update_estimation(_belief, a->index(), o->index(), &_rng, &lik),
+              "fba_belief_update_estimation");
+        _log_likelihood += std::log(lik); // :169
+        _history.back().emplace_back(a->index(), o->index());
+        if (_log_likelihood < _ll_threshold) MH(d); // :175-178
+    }
+
+    double logLikelihood() const { return _log_likelihood; }
+    size_t mhRuns() const { return _mh_runs; }
+    size_t proposals() const { return _proposals; }
+
+protected:
+    // MH may propose any structure the domain's mutate can reach: blocks are sized for the fully
+    // connected one (FBAPOMDP::sampleFullyConnectedState, as the reinvigoration belief does)
+    size_t minimumStride(POMDP const& d) const override
+    {
+        auto const& fbapomdp = dynamic_cast<::bayes_adaptive::factored::FBAPOMDP const&>(d);
+        auto p               = static_cast<BAState const*>(fbapomdp.sampleFullyConnectedState());
+        std::vector<float> block;
+        _cuda->describe(p, &block);
+        d.releaseState(p);
+        return block.size();
+    }
+
+private:
+    double _ll_threshold;
+    double _log_likelihood = 0.0;
+    std::vector<std::vector<std::pair<int32_t, int32_t>>> _history; // [episode][step] = (action, observation)
+    size_t _mh_runs = 0, _proposals = 0;
+
+    struct Beliefs // proposal scratch, released on every exit path
+    {
+        std::vector<fba_belief*> all;
+        ~Beliefs()
+        {
+            for (auto b : all) fba_belief_destroy(b);
+        }
+        fba_belief* make(fba_ctx* ctx, fba_model* m, int64_t n, int64_t stride, int weighted)
+        {
+            fba_belief* b = nullptr;
+            check(ctx, fba_belief_create(ctx, m, n, stride, weighted, &b), "fba_belief_create");
+            all.push_back(b);
+            return b;
+        }
+        void drop(fba_belief* b)
+        {
+            for (auto& x : all)
+                if (x == b) x = nullptr;
+            fba_belief_destroy(b);
+        }
+    };
+
+    void MH(POMDP const& d)
+    {
+        auto const& fbapomdp = dynamic_cast<::bayes_adaptive::factored::FBAPOMDP const&>(d);
+        fba_ctx* ctx         = _cuda->ctx();
+        int64_t const N      = (int64_t)_n;
+        int64_t const stride = fba_belief_stride(_belief);
+        Beliefs tmp;
+
+        // the prior model of a structure, by the reference's own prior, in this repo's layout; cached per id
+        std::vector<int32_t> prior_sid;      // prototype k has structure prior_sid[k] ...
+        std::vector<float> prior_flat;       // ... and counts prior_flat[k * stride ..]
+        std::map<int32_t, int32_t> prior_of; // structure id -> prototype
+        std::vector<float> block;
+        auto priorOf = [&](int32_t id, ::bayes_adaptive::factored::BABNModel::Structure const& st) {
+            auto it = prior_of.find(id);
+            if (it != prior_of.end()) return it->second;
+            auto model         = fbapomdp.prior()->computePriorModel(st);
+            int32_t const got  = _cuda->describeModel(&model, &block);
+            if (got != id) throw std::string("CudaMHNIPS2018: the prior model of a structure has another structure");
+            if ((int64_t)block.size() > stride) throw std::string("CudaMHNIPS2018: structure larger than the particle blocks");
+            int32_t const k = (int32_t)prior_sid.size();
+            prior_sid.push_back(id);
+            prior_flat.resize((size_t)(k + 1) * stride, 0.0f);
+            std::copy(block.begin(), block.end(), prior_flat.begin() + (size_t)k * stride);
+            prior_of.emplace(id, k);
+            return k;
+        };
+        std::map<int32_t, ::bayes_adaptive::factored::BABNModel::Structure> structure_of;
+        auto structureOf = [&](int32_t id) -> ::bayes_adaptive::factored::BABNModel::Structure const& {
+            auto it = structure_of.find(id);
+            if (it == structure_of.end()) it = structure_of.emplace(id, _cuda->structureOf(id)).first;
+            return it->second;
+        };
+        auto priorBelief = [&](std::vector<int32_t> const& proto) { // n particles, particle i = prior prototype proto[i]
+            fba_belief* b = tmp.make(ctx, _cuda->model(), (int64_t)proto.size(), stride, 0);
+            std::vector<int32_t> zeros(proto.size(), 0);
+            check(ctx,
+                  fba_belief_init(b, (int32_t)prior_sid.size(), prior_sid.data(), prior_flat.data(), proto.data(),
+                                  zeros.data()),
+                  "fba_belief_init");
+            return b;
+        };
+
+        // old_score of every particle: LogBDScore against the prior model of ITS structure (:237)
+        std::vector<int32_t> sid((size_t)N), proto((size_t)N);
+        check(ctx, fba_belief_download(_belief, 0, N, nullptr, sid.data(), nullptr, nullptr), "fba_belief_download");
+        for (int64_t i = 0; i < N; ++i) proto[(size_t)i] = priorOf(sid[(size_t)i], structureOf(sid[(size_t)i]));
+        std::vector<double> old_score((size_t)N);
+        {
+            fba_belief* pb = priorBelief(proto);
+            check(ctx, fba_belief_log_bd_score(_belief, pb, old_score.data()), "fba_belief_log_bd_score");
+            tmp.drop(pb);
+        }
+
+        // the history, flattened
+        std::vector<int32_t> len, act, obs;
+        for (auto const& ep : _history)
+        {
+            len.push_back((int32_t)ep.size());
+            for (auto const& st : ep) act.push_back(st.first), obs.push_back(st.second);
+        }
+
+        fba_belief* fresh = tmp.make(ctx, _cuda->model(), N, stride, 1);
+        {
+            std::vector<int32_t> zeros((size_t)N, 0);
+            check(ctx, fba_belief_init(fresh, 1, prior_sid.data(), prior_flat.data(), zeros.data(), zeros.data()),
+                  "fba_belief_init"); // placeholder particles, uniform weights 1/N (:243); every slot is overwritten
+        }
+        int64_t accepted = 0;
+        while (accepted < N)
+        {
+            int64_t const P = std::min<int64_t>(std::max<int64_t>(2 * (N - accepted), 256), std::max<int64_t>(N, 256));
+            std::vector<int64_t> src((size_t)P);
+            check(ctx, fba_belief_sample_batch(_belief, &_rng, P, src.data()), "fba_belief_sample_batch"); // :200
+            std::vector<int32_t> pproto((size_t)P);
+            for (int64_t j = 0; j < P; ++j)
+            {
+                int32_t const id = sid[(size_t)src[(size_t)j]];
+                if (rnd::boolean()) pproto[(size_t)j] = priorOf(id, structureOf(id)); // :206-208: same structure half the time
+                else
+                {
+                    auto st            = fbapomdp.mutate(structureOf(id));
+                    int32_t const nid  = _cuda->structureId(st);
+                    pproto[(size_t)j]  = priorOf(nid, st);
+                }
+            }
+            fba_belief* prop  = priorBelief(pproto);
+            fba_belief* prior = priorBelief(pproto);
+            check(ctx,
+                  fba_belief_replay_history(prop, (int32_t)len.size(), len.data(), act.data(), obs.data(), &_rng,
+                                            1000000),
+                  "fba_belief_replay_history"); // :214-215
+            std::vector<double> new_score((size_t)P);
+            check(ctx, fba_belief_log_bd_score(prop, prior, new_score.data()), "fba_belief_log_bd_score"); // :238
+            std::vector<int64_t> take;
+            for (int64_t j = 0; j < P && accepted + (int64_t)take.size() < N; ++j)
+                if (std::log(rnd::uniform_rand01()) < new_score[(size_t)j] - old_score[(size_t)src[(size_t)j]]) // :240
+                    take.push_back(j);
+            check(ctx, fba_belief_assign_from(fresh, accepted, prop, (int64_t)take.size(), take.data()),
+                  "fba_belief_assign_from");
+            accepted += (int64_t)take.size();
+            _proposals += (size_t)P;
+            tmp.drop(prop), tmp.drop(prior);
+        }
+        // the new belief replaces the old one (:252)
+        for (auto& x : tmp.all)
+            if (x == fresh) x = nullptr;
+        dropSample();
+        fba_belief_destroy(_belief);
+        _belief         = fresh;
+        _log_likelihood = 0.0; // :253
+        ++_mh_runs;
+    }
+};
+
+} // namespace fba_b200
+
+#endif // FBA_B200_CUDA_MH_HPP

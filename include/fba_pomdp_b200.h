@@ -322,6 +322,24 @@ int fba_belief_import(fba_belief* b, int64_t n_records);
  * storage. First brick of the reference's MCMC structure beliefs. */
 int fba_belief_log_bd_score(fba_belief* b, fba_belief* prior, double* scores);
 
+/* ---- MH structure beliefs ----------------------------------------------------
+ * computePosterior of the reference's Metropolis-Hastings structure beliefs
+ * (src/beliefs/bayes-adaptive/factored/MHNIPS2018.cpp:41-109): the whole (action, observation) history —
+ * n_episodes episodes, episode e of episode_len[e] steps, actions / observations concatenated (host) —
+ * replayed on EVERY particle of `b` (the proposals: each holds the prior model of its proposed
+ * structure), one thread per particle: per episode attempt a domain start state, per step s' and o from
+ * the particle's counts (expected Dirichlets), +1 on (s, a, o, s') if o is the observed one, otherwise
+ * the episode's increments are taken back (-1) and the episode is tried again. Each particle's domain
+ * state becomes the state after the last step. More than max_attempts attempts in one particle:
+ * FBA_ERR_CAPACITY. REPLAY mode: particle i draws from the i-th equal slice of the remaining words. */
+int fba_belief_replay_history(fba_belief* b, int32_t n_episodes, const int32_t* episode_len,
+                              const int32_t* actions, const int32_t* observations, fba_rng* rng,
+                              int64_t max_attempts);
+/* particles src[src_index[j]] -> dst[first + j], j < n (count block, domain state, structure id); both
+ * beliefs share context, model and stride. How accepted proposals become the new belief
+ * (MHNIPS2018.cpp:241-246). Weights are untouched. */
+int fba_belief_assign_from(fba_belief* dst, int64_t first, fba_belief* src, int64_t n, const int64_t* src_index);
+
 /* ---- POMCP with the search tree on the device --------------------------------
  * planners::RBAPOUCT::selectAction (src/planners/bayes-adaptive/RBAPOUCT.cpp:67-153) as waves of
  * `wave` concurrent simulations, each one entirely on the device: root particle from the belief

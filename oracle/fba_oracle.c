@@ -343,6 +343,73 @@ double orc_step(const orc_model* m, const uint32_t* t_par, const uint32_t* o_par
     return r;
 }
 
+void orc_increment_counts(const orc_model* m, const uint32_t* t_par, const uint32_t* o_par, float* counts, int s,
+                          int a, int o, int s2, float amount)
+{
+    /* BA{Flat,BN}Model::incrementCountsOf(s, a, o, s', amount) (BAFlatModel.cpp:126-141,
+     * BABNModel.cpp:354-382): one cell per node; the factored observation CPTs are indexed with the
+     * OLD state's features (BABNModel.cpp:366,380) */
+    int x[ORC_MAXF], x2[ORC_MAXF], of[ORC_MAXF];
+    int64_t t_off[ORC_MAXF], o_off[ORC_MAXF];
+    node_offsets_small(m, t_par, o_par, a, t_off, o_off);
+    features_of(s, m->feat_s, m->FS, x);
+    features_of(s2, m->feat_s, m->FS, x2);
+    features_of(o, m->feat_o, m->FO, of);
+    for (int f = 0; f < m->FS; ++f)
+        counts[t_off[f] + (int64_t)parent_config(m, t_par[a * m->FS + f], x) * m->feat_s[f] + x2[f]] += amount;
+    const int* xo = m->tabular ? x2 : x;
+    for (int q = 0; q < m->FO; ++q)
+        counts[o_off[q] + (int64_t)parent_config(m, o_par[a * m->FO + q], xo) * m->feat_o[q] + of[q]] += amount;
+}
+
+int64_t orc_mh_replay_history(const orc_model* m, const uint32_t* t_par, const uint32_t* o_par, float* counts,
+                              int n_episodes, const int32_t* episode_len, const int32_t* actions,
+                              const int32_t* observations, orc_rng* g, int64_t max_attempts, int32_t* last_state)
+{
+    /* computePosterior (MHNIPS2018.cpp:41-109): replay the whole (action, observation) history on a
+     * model, episode by episode. Each attempt of an episode draws a domain start state, then per step
+     * samples s' and o from the model (sampleStateIndex / sampleObservationIndex, expected mode);
+     * a wrong observation abandons the attempt — the increments made so far in this episode are taken
+     * back with amount -1, in step order — and the episode is tried again; a right one increments
+     * (s, a, o, s'). Returns the number of episode attempts (-1 if max_attempts was exceeded);
+     * *last_state = the state after the last step. */
+    int32_t trans_s[4096], trans_s2[4096];
+    int64_t attempts = 0;
+    int32_t new_s    = 0;
+    int64_t first    = 0;
+    for (int e = 0; e < n_episodes; ++e)
+    {
+        int const len = episode_len[e];
+        if (len > 4096) return -2;
+        for (;;)
+        {
+            if (++attempts > max_attempts) return -1;
+            int32_t s   = orc_sample_start_state(m, g);
+            int applied = 0;
+            for (int t = 0; t < len; ++t)
+            {
+                int const a   = actions[first + t];
+                int32_t state = s;
+                int o, term;
+                orc_step(m, t_par, o_par, counts, &state, a, 0, g, &o, &term); /* KeepCounts: draws only */
+                new_s = state;
+                if (o != observations[first + t]) break;
+                orc_increment_counts(m, t_par, o_par, counts, s, a, o, new_s, 1.0f);
+                trans_s[applied] = s, trans_s2[applied] = new_s;
+                ++applied;
+                s = new_s;
+            }
+            if (applied == len) break;
+            for (int t = 0; t < applied; ++t)
+                orc_increment_counts(m, t_par, o_par, counts, trans_s[t], actions[first + t],
+                                     observations[first + t], trans_s2[t], -1.0f);
+        }
+        first += len;
+    }
+    *last_state = new_s;
+    return attempts;
+}
+
 double orc_obs_prob(const orc_model* m, const uint32_t* t_par, const uint32_t* o_par,
                     const float* counts, int state, int a, int o)
 {
@@ -658,6 +725,36 @@ static uint32_t flip_random_edge(uint32_t par, int edge_range, orc_rng* g)
     return par ^ (1u << slow_random_int(g, edge_range));
 }
 
+void orc_mutate_structure(const orc_model* m, uint32_t* tp, uint32_t* op, int mutate_kind, orc_rng* g)
+{
+    /* FBAPOMDP::mutate -> the domain prior's mutate, on parent bitmasks */
+    switch (mutate_kind)
+    {
+        case ORC_MUT_FACTORED_TIGER: /* FactoredTigerPriors.cpp:374-375: O[listen=2][0] */
+            op[2 * m->FO + 0] = flip_random_edge(op[2 * m->FO + 0], m->FS, g);
+            break;
+        case ORC_MUT_COLLISION_AVOIDANCE: { /* CollisionAvoidancePriors.cpp:478-486 */
+            int const a    = orc_uniform_int(g, (uint32_t)m->A);
+            int const obst = 2 + orc_uniform_int(g, (uint32_t)m->dom_ip[2]);
+            tp[a * m->FS + obst] = flip_random_edge(tp[a * m->FS + obst], m->FS, g);
+            break;
+        }
+        case ORC_MUT_SYSADMIN: { /* SysAdminFactoredPrior.cpp:51-52: T[action][comp], the two
+                                    subscripts' draws happen right to left (comp first) */
+            int const comp = orc_uniform_int(g, (uint32_t)m->FS);
+            int const a    = orc_uniform_int(g, (uint32_t)m->A);
+            tp[a * m->FS + comp] = flip_random_edge(tp[a * m->FS + comp], m->FS, g);
+            break;
+        }
+        default: { /* ORC_MUT_GRIDWORLD, GridWorldBAPriors.cpp:200-225: toggle the goal feature */
+            int const a = slow_random_int(g, m->A);
+            int const f = slow_random_int(g, 2);
+            tp[a * m->FS + f] ^= (1u << (m->FS - 1));
+            break;
+        }
+    }
+}
+
 int orc_reinvigorate(const orc_model* m, orc_structs* st, orc_belief* belief, const orc_belief* fc,
                      int64_t amount, int mutate_kind, orc_rng* g)
 {
@@ -678,31 +775,7 @@ int orc_reinvigorate(const orc_model* m, orc_structs* st, orc_belief* belief, co
         memcpy(tp, tpar_of(m, st, belief->struct_id[struct_donor]), sizeof(uint32_t) * nT);
         memcpy(op, opar_of(m, st, belief->struct_id[struct_donor]), sizeof(uint32_t) * nO);
 
-        switch (mutate_kind)
-        {
-            case ORC_MUT_FACTORED_TIGER: /* FactoredTigerPriors.cpp:374-375: O[listen=2][0] */
-                op[2 * m->FO + 0] = flip_random_edge(op[2 * m->FO + 0], m->FS, g);
-                break;
-            case ORC_MUT_COLLISION_AVOIDANCE: { /* CollisionAvoidancePriors.cpp:478-486 */
-                int const a    = orc_uniform_int(g, (uint32_t)m->A);
-                int const obst = 2 + orc_uniform_int(g, (uint32_t)m->dom_ip[2]);
-                tp[a * m->FS + obst] = flip_random_edge(tp[a * m->FS + obst], m->FS, g);
-                break;
-            }
-            case ORC_MUT_SYSADMIN: { /* SysAdminFactoredPrior.cpp:51-52: T[action][comp], the two
-                                        subscripts' draws happen right to left (comp first) */
-                int const comp = orc_uniform_int(g, (uint32_t)m->FS);
-                int const a    = orc_uniform_int(g, (uint32_t)m->A);
-                tp[a * m->FS + comp] = flip_random_edge(tp[a * m->FS + comp], m->FS, g);
-                break;
-            }
-            default: { /* ORC_MUT_GRIDWORLD, GridWorldBAPriors.cpp:200-225: toggle the goal feature */
-                int const a = slow_random_int(g, m->A);
-                int const f = slow_random_int(g, 2);
-                tp[a * m->FS + f] ^= (1u << (m->FS - 1));
-                break;
-            }
-        }
+        orc_mutate_structure(m, tp, op, mutate_kind, g);
 
         /* BABNModel::marginalizeOut (BABNModel.cpp:205-229) of the counts donor onto it */
         const uint32_t* stp = tpar_of(m, st, fc->struct_id[counts_donor]);

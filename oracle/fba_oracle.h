@@ -156,6 +156,17 @@ enum {
     ORC_MUT_SYSADMIN = 2,            /* SysAdminFactoredPrior.cpp:47-55 */
     ORC_MUT_GRIDWORLD = 3            /* GridWorldBAPriors.cpp:200-225 */
 };
+/* FBAPOMDP::mutate (the domain prior's mutate) on the parent bitmasks of one structure, in place */
+void orc_mutate_structure(const orc_model* m, uint32_t* t_par, uint32_t* o_par, int mutate_kind, orc_rng* g);
+/* incrementCountsOf(s, a, o, s', amount) (BAFlatModel.cpp:126-141, BABNModel.cpp:354-382) */
+void orc_increment_counts(const orc_model* m, const uint32_t* t_par, const uint32_t* o_par, float* counts, int s,
+                          int a, int o, int s2, float amount);
+/* computePosterior of the MH structure beliefs (MHNIPS2018.cpp:41-109): replays a history of n_episodes
+ * episodes (episode e has episode_len[e] steps; actions / observations concatenated) on `counts`;
+ * returns the number of episode attempts, -1 if more than max_attempts were needed */
+int64_t orc_mh_replay_history(const orc_model* m, const uint32_t* t_par, const uint32_t* o_par, float* counts,
+                              int n_episodes, const int32_t* episode_len, const int32_t* actions,
+                              const int32_t* observations, orc_rng* g, int64_t max_attempts, int32_t* last_state);
 /* DBNNode::marginalizeOut (DBNNode.cpp:40-80): src node must be fully connected (parents = all
  * state features) or equal to dst. */
 void orc_marginalize_node(const orc_model* m, uint32_t src_par, const float* src, uint32_t dst_par,

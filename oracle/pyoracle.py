@@ -95,6 +95,10 @@ def lib():
         L.orc_normalize.argtypes = [vp, i64, dbl]
         L.orc_weighted_sample_many.argtypes = [vp, i64, dbl, vp, i64, vp]
         L.orc_block_checksums.argtypes = [vp, i64, i64, vp]
+        L.orc_mutate_structure.argtypes = [vp, vp, vp, C.c_int, vp]
+        L.orc_increment_counts.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]
+        L.orc_mh_replay_history.restype = i64
+        L.orc_mh_replay_history.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, i64, vp]
         L.orc_is_resample.argtypes = [vp, vp, vp, vp]
         L.orc_is_reset_domain_states.argtypes = [vp, vp, vp, vp, vp]
         L.orc_reject_sample.restype = i64
@@ -320,6 +324,28 @@ def block_checksums(counts):
     out = np.zeros(c.shape[0], np.uint64)
     lib().orc_block_checksums(_p(c), c.shape[0], c.shape[1], _p(out))
     return out
+
+
+def mutate_structure(model, t_par, o_par, mutate_kind, rng):
+    """FBAPOMDP::mutate on one structure's parent bitmasks -> new (t_par, o_par)"""
+    tp = np.ascontiguousarray(t_par, np.uint32).copy()
+    op = np.ascontiguousarray(o_par, np.uint32).copy()
+    lib().orc_mutate_structure(model.ref(), _p(tp), _p(op), int(mutate_kind), rng.ref())
+    return tp, op
+
+
+def mh_replay_history(model, t_par, o_par, counts, episode_len, actions, observations, rng, max_attempts=1 << 40):
+    """computePosterior (MHNIPS2018.cpp:41-109) in place on `counts` -> (episode attempts, last state)"""
+    tp = np.ascontiguousarray(t_par, np.uint32)
+    op = np.ascontiguousarray(o_par, np.uint32)
+    ln = np.ascontiguousarray(episode_len, np.int32)
+    ac = np.ascontiguousarray(actions, np.int32)
+    ob = np.ascontiguousarray(observations, np.int32)
+    assert counts.dtype == np.float32 and counts.flags.c_contiguous
+    last = C.c_int32(0)
+    n = lib().orc_mh_replay_history(model.ref(), _p(tp), _p(op), _p(counts), len(ln), _p(ln), _p(ac), _p(ob),
+                                    rng.ref(), int(max_attempts), C.byref(last))
+    return int(n), int(last.value)
 
 
 def is_resample(src, rng):

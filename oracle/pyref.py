@@ -214,6 +214,35 @@ class Ref:
             raise RuntimeError("reference/adapter: " + self.L.ref_error(self.h).decode())
         return out, dt
 
+    # ---- MHNIPS2018 ----
+    def mh_init(self, n, threshold=-1e300):
+        self.L.ref_mh_init.restype = C.c_int
+        self.L.ref_mh_init.argtypes = [C.c_void_p, C.c_long, C.c_double]
+        if self.L.ref_mh_init(self.h, n, threshold):
+            raise RuntimeError(self.L.ref_error(self.h).decode())
+
+    def mh_run(self):
+        """the private MHNIPS2018::MH on the belief as it is"""
+        self.L.ref_mh_run.argtypes = [C.c_void_p]
+        self.L.ref_mh_run(self.h)
+
+    def mh_log_likelihood(self):
+        self.L.ref_mh_log_likelihood.restype = C.c_double
+        self.L.ref_mh_log_likelihood.argtypes = [C.c_void_p]
+        return self.L.ref_mh_log_likelihood(self.h)
+
+    def prior_model(self, t_par, o_par, cap=1 << 20):
+        """FBAPOMDPPrior::computePriorModel(structure) -> counts in this repo's layout"""
+        f = self.L.ref_prior_model
+        f.restype = C.c_long
+        f.argtypes = [C.c_void_p] * 4
+        tp, op = np.ascontiguousarray(t_par, np.uint32), np.ascontiguousarray(o_par, np.uint32)
+        out = np.zeros(cap, np.float32)
+        n = f(self.h, _p(tp), _p(op), _p(out))
+        if n < 0:
+            raise RuntimeError(self.L.ref_error(self.h).decode())
+        return out[:n].copy()
+
     def batched_experiment_file(self, n, runs, sims, episodes, path, seed=4711):
         """runBatchedExperiment writing the reference's result file -> (returns[episodes, runs], seconds)"""
         f = self.L.ref_batched_experiment_file

@@ -42,6 +42,7 @@
 #include "bayes-adaptive/states/table/BAPOMDPState.hpp"
 #include "beliefs/bayes-adaptive/BAImportanceSampling.hpp"
 #include "beliefs/bayes-adaptive/BARejectionSampling.hpp"
+#include "beliefs/bayes-adaptive/factored/MHNIPS2018.hpp"
 #include "beliefs/bayes-adaptive/factored/ReinvigoratingRejectionSampling.hpp"
 #include "beliefs/particle_filters/ImportanceSampler.hpp"
 #include "beliefs/particle_filters/RejectionSampling.hpp"
@@ -63,6 +64,7 @@
 #define FBA_B200_PRIVATE_ACCESS
 #include "CudaBeliefs.hpp"
 #include "CudaExperiment.hpp"
+#include "CudaMH.hpp"
 #include "CudaPlanner.hpp"
 #include "environment/Discount.hpp"
 #include "environment/Horizon.hpp"
@@ -74,13 +76,14 @@ INITIALIZE_EASYLOGGINGPP
 
 namespace {
 
-using FBAPOMDP = ::bayes_adaptive::factored::FBAPOMDP;
+using FactoredPOMDP = ::bayes_adaptive::factored::FBAPOMDP;
 using ReinvRS  = ::beliefs::bayes_adaptive::factored::ReinvigoratingRejectionSampling;
+using RefMH    = ::beliefs::bayes_adaptive::factored::MHNIPS2018;
 
 struct Handle
 {
     configurations::FBAConf conf;
-    std::unique_ptr<BAPOMDP> sim; // hyper-state simulator (tabular BAPOMDP or FBAPOMDP)
+    std::unique_ptr<BAPOMDP> sim; // hyper-state simulator (tabular BAPOMDP or FactoredPOMDP)
     std::unique_ptr<Environment> env; // the true domain, for (a,o) scripts
     bool factored = false;
     std::vector<int> feat_s, feat_o;
@@ -88,6 +91,7 @@ struct Handle
     std::unique_ptr<beliefs::BAImportanceSampling> is_belief;
     std::unique_ptr<beliefs::BARejectionSampling> rs_belief;
     std::unique_ptr<ReinvRS> reinv_belief;
+    std::unique_ptr<RefMH> mh_belief;
     std::unique_ptr<planners::RBAPOUCT> planner;
 
     std::mt19937 mark;
@@ -97,7 +101,7 @@ struct Handle
 bool g_rng_initiated = false;
 
 // which particle container a call refers to
-enum Filter { F_IS = 0, F_RS = 1, F_REINV = 2, F_REINV_FC = 3 };
+enum Filter { F_IS = 0, F_RS = 1, F_REINV = 2, F_REINV_FC = 3, F_MH = 4 };
 
 BAState const* particleOf(Handle* h, int filter, long i)
 {
@@ -108,6 +112,7 @@ BAState const* particleOf(Handle* h, int filter, long i)
         case F_RS: return static_cast<BAState const*>(h->rs_belief->_filter.particles()[i]);
         case F_REINV: return h->reinv_belief->_belief.particles()[i];
         case F_REINV_FC: return h->reinv_belief->_fully_connected_belief.particles()[i];
+        case F_MH: return h->mh_belief->_belief.particle(i)->particle;
     }
     return nullptr;
 }
@@ -121,6 +126,7 @@ long filterSize(Handle* h, int filter)
         case F_REINV: return h->reinv_belief ? (long)h->reinv_belief->_belief.size() : 0;
         case F_REINV_FC:
             return h->reinv_belief ? (long)h->reinv_belief->_fully_connected_belief.size() : 0;
+        case F_MH: return h->mh_belief ? (long)h->mh_belief->_belief.size() : 0;
     }
     return 0;
 }
@@ -180,7 +186,7 @@ void* ref_open_ex(
 
         if (factored)
         {
-            auto fs   = static_cast<FBAPOMDP const*>(h->sim.get())->domainFeatureSize();
+            auto fs   = static_cast<FactoredPOMDP const*>(h->sim.get())->domainFeatureSize();
             h->feat_s = fs->_S;
             h->feat_o = fs->_O;
         } else
@@ -229,6 +235,7 @@ void ref_close(void* hv)
         if (h->is_belief) h->is_belief->free(*h->sim);
         if (h->rs_belief) h->rs_belief->free(*h->sim);
         if (h->reinv_belief) h->reinv_belief->free(*h->sim);
+        if (h->mh_belief) h->mh_belief->free(*h->sim);
     }
     delete h;
 }
@@ -408,6 +415,173 @@ void ref_particle_dump(void* hv, int filter, long i, uint32_t* t_par, uint32_t* 
     }
 }
 
+/**** MHNIPS2018 (src/beliefs/bayes-adaptive/factored/MHNIPS2018.cpp) ****/
+// a fresh MHNIPS2018 belief of n particles; threshold < 0 is the log-likelihood below which
+// updateEstimation runs MH. A threshold of -1e300 never triggers it (then ref_mh_run does).
+int ref_mh_init(void* hv, long n, double threshold)
+{
+    auto h = static_cast<Handle*>(hv);
+    try
+    {
+        if (h->mh_belief) h->mh_belief->free(*h->sim);
+        h->mh_belief.reset(new RefMH((size_t)n, threshold));
+        h->mh_belief->initiate(*h->sim);
+    } catch (std::string const& e)
+    {
+        h->err = e;
+        return 1;
+    } catch (char const* e)
+    {
+        h->err = e;
+        return 1;
+    }
+    return 0;
+}
+
+// the private MHNIPS2018::MH (MHNIPS2018.cpp:188-255) on the belief as it is
+void ref_mh_run(void* hv)
+{
+    auto h = static_cast<Handle*>(hv);
+    h->mh_belief->MH(*h->sim);
+}
+
+double ref_mh_log_likelihood(void* hv)
+{
+    return static_cast<Handle*>(hv)->mh_belief->_log_likelihood;
+}
+
+// FBAPOMDPPrior::computePriorModel(structure) (FBAPOMDPPrior.hpp:32 and the domain priors), the
+// structure given as this repo's parent bitmasks; counts in this repo's layout. Returns the number of
+// cells, -1 on error.
+long ref_prior_model(void* hv, uint32_t const* t_par, uint32_t const* o_par, float* counts)
+{
+    auto h = static_cast<Handle*>(hv);
+    try
+    {
+        auto const& fba = dynamic_cast<FactoredPOMDP const&>(*h->sim);
+        int const A = h->sim->domainSize()->_A, FS = (int)h->feat_s.size(), FO = (int)h->feat_o.size();
+        ::bayes_adaptive::factored::BABNModel::Structure st;
+        st.T.resize(A), st.O.resize(A);
+        for (int a = 0; a < A; ++a)
+        {
+            for (int f = 0; f < FS; ++f)
+            {
+                std::vector<int> par;
+                for (int p = 0; p < FS; ++p)
+                    if (t_par[a * FS + f] & (1u << p)) par.push_back(p);
+                st.T[a].push_back(par);
+            }
+            for (int g = 0; g < FO; ++g)
+            {
+                std::vector<int> par;
+                for (int p = 0; p < FS; ++p)
+                    if (o_par[a * FO + g] & (1u << p)) par.push_back(p);
+                st.O[a].push_back(par);
+            }
+        }
+        auto model = fba.prior()->computePriorModel(st);
+        long k     = 0;
+        IndexAction action(0);
+        for (int a = 0; a < A; ++a)
+        {
+            action.index(a);
+            for (int f = 0; f < FS; ++f)
+                for (auto v : model.transitionNode(&action, f)._cpts) counts[k++] = v;
+            for (int g = 0; g < FO; ++g)
+                for (auto v : model.observationNode(&action, g)._cpts) counts[k++] = v;
+        }
+        return k;
+    } catch (std::string const& e)
+    {
+        h->err = e;
+    } catch (char const* e)
+    {
+        h->err = e;
+    }
+    return -1;
+}
+
+// The steps of computePosterior (MHNIPS2018.cpp:41-109) driven from here through the reference's own
+// model API (BABNModel::sampleStateIndex / sampleObservationIndex / incrementCountsOf,
+// FBAPOMDP::sampleDomainState) on computePriorModel(structure): a second opinion on the oracle's
+// orc_mh_replay_history that shares the reference's arithmetic and RNG. Returns episode attempts.
+long ref_mh_posterior_probe(void* hv, uint32_t const* t_par, uint32_t const* o_par, int n_episodes,
+                            int const* episode_len, int const* actions, int const* observations, float* counts,
+                            int* last_state)
+{
+    auto h = static_cast<Handle*>(hv);
+    auto const& fba = dynamic_cast<FactoredPOMDP const&>(*h->sim);
+    int const A = h->sim->domainSize()->_A, FS = (int)h->feat_s.size(), FO = (int)h->feat_o.size();
+    ::bayes_adaptive::factored::BABNModel::Structure st;
+    st.T.resize(A), st.O.resize(A);
+    for (int a = 0; a < A; ++a)
+    {
+        for (int f = 0; f < FS; ++f)
+        {
+            std::vector<int> par;
+            for (int p = 0; p < FS; ++p)
+                if (t_par[a * FS + f] & (1u << p)) par.push_back(p);
+            st.T[a].push_back(par);
+        }
+        for (int g = 0; g < FO; ++g)
+        {
+            std::vector<int> par;
+            for (int p = 0; p < FS; ++p)
+                if (o_par[a * FO + g] & (1u << p)) par.push_back(p);
+            st.O[a].push_back(par);
+        }
+    }
+    auto model  = fba.prior()->computePriorModel(st);
+    auto method = rnd::sample::Dir::sampleFromExpectedMult;
+    IndexState s(0), new_s(0);
+    IndexAction act(0);
+    IndexObservation o(0), real_o(0);
+    long attempts = 0;
+    int first     = 0;
+    for (int e = 0; e < n_episodes; ++e)
+    {
+        for (;;)
+        {
+            ++attempts;
+            auto sampled = fba.sampleDomainState();
+            s.index(sampled->index());
+            fba.releaseDomainState(sampled);
+            std::vector<std::pair<int, int>> done;
+            for (int t = 0; t < episode_len[e]; ++t)
+            {
+                act.index(actions[first + t]);
+                new_s.index(model.sampleStateIndex(&s, &act, method));
+                o.index(model.sampleObservationIndex(&act, &new_s, method));
+                if (o.index() != observations[first + t]) break;
+                model.incrementCountsOf(&s, &act, &o, &new_s);
+                done.emplace_back(s.index(), new_s.index());
+                s.index(new_s.index());
+            }
+            if ((int)done.size() == episode_len[e]) break;
+            for (size_t t = 0; t < done.size(); ++t)
+            {
+                s.index(done[t].first), new_s.index(done[t].second);
+                act.index(actions[first + (int)t]);
+                real_o.index(observations[first + (int)t]);
+                model.incrementCountsOf(&s, &act, &real_o, &new_s, -1);
+            }
+        }
+        first += episode_len[e];
+    }
+    *last_state = new_s.index();
+    long k = 0;
+    IndexAction action(0);
+    for (int a = 0; a < A; ++a)
+    {
+        action.index(a);
+        for (int f = 0; f < FS; ++f)
+            for (auto v : model.transitionNode(&action, f)._cpts) counts[k++] = v;
+        for (int g = 0; g < FO; ++g)
+            for (auto v : model.observationNode(&action, g)._cpts) counts[k++] = v;
+    }
+    return attempts;
+}
+
 /**** importance sampling ****/
 // importance_sampling::update only (weights stay un-resampled); returns the step likelihood
 double ref_is_update(void* hv, int a, int o)
@@ -433,6 +607,12 @@ void ref_update_estimation(void* hv, int kind, int a, int o)
     if (kind == F_IS) h->is_belief->updateEstimation(&act, &obs, *h->sim);
     else if (kind == F_RS)
         h->rs_belief->updateEstimation(&act, &obs, *h->sim);
+    else if (kind == F_MH)
+    { // MHNIPS2018 keeps the pointers in its history (MHNIPS2018.cpp:173) and the domains' copyAction /
+      // copyObservation hand the same pointer back (e.g. FactoredTiger.cpp:49-54,136-141): they must outlive
+      // this call. The belief's free() releases them through the domain.
+        h->mh_belief->updateEstimation(new IndexAction(a), new IndexObservation(o), *h->sim);
+    }
     else
         h->reinv_belief->updateEstimation(&act, &obs, *h->sim);
 }
@@ -443,6 +623,8 @@ void ref_reset_domain_states(void* hv, int kind)
     if (kind == F_IS) h->is_belief->resetDomainStateDistribution(*h->sim);
     else if (kind == F_RS)
         h->rs_belief->resetDomainStateDistribution(*h->sim);
+    else if (kind == F_MH)
+        h->mh_belief->resetDomainStateDistribution(*h->sim);
     else
         h->reinv_belief->resetDomainStateDistribution(*h->sim);
 }
@@ -681,6 +863,10 @@ int ref_adapter_episodes(void* hv, int kind, long n, char const* planner, int si
             belief.reset(new beliefs::BARejectionSampling(n));
         else if (kind == 3)
             belief.reset(new fba_b200::CudaBARejectionSampling(n));
+        else if (kind == 6) // the reference's MHNIPS2018; threshold chosen so that MH runs every few steps
+            belief.reset(new RefMH((size_t)n, -4.0));
+        else if (kind == 7)
+            belief.reset(new fba_b200::CudaMHNIPS2018((size_t)n, -4.0));
         else
         {
             auto const& d  = h->conf.domain_conf.domain;

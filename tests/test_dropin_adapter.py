@@ -27,6 +27,10 @@ CASES = [
     ("centered-collision-avoidance", dict(size=1, width=3, height=3, factored=True,
                                           structure_prior="match-uniform"), (4, 5), 128, 40),
     ("linear-sysadmin", dict(size=3, factored=True), (4, 5), 64, 20),
+    # MHNIPS2018 (threshold -4: MH runs every few steps): the reference's class vs fba_b200::CudaMHNIPS2018
+    ("episodic-factored-tiger", dict(size=3, factored=True, structure_prior="match-uniform"), (6, 7), 96, 40),
+    ("centered-collision-avoidance", dict(size=1, width=3, height=3, factored=True,
+                                          structure_prior="match-uniform"), (6, 7), 64, 30),
     # --dirichlet_sampling_method regular: the adapter reads the mode from the simulator
     ("episodic-tiger", dict(sampled=True), (0, 1), 256, 80),
     ("episodic-factored-tiger", dict(size=3, factored=True, sampled=True), (0, 1), 128, 40),
