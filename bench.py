@@ -374,7 +374,7 @@ def main_reference(args):
 # ------------------------------------------------------------------------------------------------
 # this repo's CUDA path
 # ------------------------------------------------------------------------------------------------
-def belief_leg(wl, args, fba, torch, dist, ctx, world, rank, sampler, steps, headline):
+def belief_leg(wl, args, fba, torch, dist, ctx, world, rank, sampler, steps, headline, journal_updates=0):
     """The importance-sampling belief update of workload `wl` on `world` GPUs. Three passes over the same
     belief, each bracketed by barrier + synchronize:
       1. VALUE: K updates, nothing waits for the GPU, one CUDA event per step on the launching stream
@@ -385,7 +385,10 @@ def belief_leg(wl, args, fba, torch, dist, ctx, world, rank, sampler, steps, hea
          and Belief::sample() materialises one particle on the host of the rank that owns it."""
     g, psid, protos, script = workload(wl)
     n_local = args.particles or WORKLOADS[wl]["particles"]
-    sim = fba.BAPOMDP(ctx, g.desc, g.t_par, g.o_par)
+    J_nodes = len(np.asarray(g.desc["feat_s"]).reshape(-1)) + len(np.asarray(g.desc["feat_o"]).reshape(-1))
+    journal_updates = journal_updates or args.journal_updates
+    desc = dict(g.desc, delta_capacity=J_nodes * journal_updates) if journal_updates else g.desc
+    sim = fba.BAPOMDP(ctx, desc, g.t_par, g.o_par)
     # count cells a particle owns (mean over the prior's structures when they differ)
     C = int(round(np.mean([sim.structure_size(int(i)) for i in psid])))
     bytes_per_particle = 2 * (4 * C + 4 + 8)  # SURVEY.md §8d: counts + state + weight, read + written
@@ -400,8 +403,11 @@ def belief_leg(wl, args, fba, torch, dist, ctx, world, rank, sampler, steps, hea
                        stride=protos.shape[1])
     shared = np.random.RandomState(args.seed)  # same on every rank: quota offsets, owner of the sampled particle
 
+    age = [0]  # updates this belief has been through (= updates every particle's journal holds)
+
     def step(t, likelihood=False):
         a, o = script[t % len(script)]
+        age[0] += 1
         if sharded:
             return b.updateEstimation(a, o, rng, step_uniform=float(shared.random_sample()), likelihood=likelihood)
         return b.updateEstimation(a, o, rng, want_likelihood=likelihood)
@@ -435,11 +441,14 @@ def belief_leg(wl, args, fba, torch, dist, ctx, world, rank, sampler, steps, hea
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return float(tt.item())
 
+    value_age = []
+
     def value_pass(n_steps, t_first):
         barrier()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(n_steps + 1)]
         launches0 = ctx.launches
         copies0 = b.resample_stats()[0]
+        value_age.append(age[0])
         w0 = time.time()
         ev[0].record(stream)
         for t in range(n_steps):
@@ -453,6 +462,7 @@ def belief_leg(wl, args, fba, torch, dist, ctx, world, rank, sampler, steps, hea
 
     def kernel_pass(n_steps, t_first):
         barrier()
+        age0 = age[0]
         copies0 = b.resample_stats()[0]
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ctx.profile_begin()
@@ -469,8 +479,16 @@ def belief_leg(wl, args, fba, torch, dist, ctx, world, rank, sampler, steps, hea
             per_launch = kms / max(cnt, 1)
             if name.startswith("k_gather"):
                 alg = bytes_per_particle * n_local
+            elif name.startswith("k_copy_inplace") and journal_updates:
+                jp = 4 * ((J_nodes + 1 + 3) // 4 * 4)
+                alg = 2 * (16 + jp * (age0 + 1 + (n_steps - 1) / 2.0) + 12) * copies / max(cnt, 1)
             elif name.startswith("k_copy_inplace"):
                 alg = bytes_per_particle * copies / max(cnt, 1)
+            elif name.startswith("k_propose_journal"):
+                # per particle: its journal read once (16 B header + 48 B per earlier update, averaged over the
+                # launches of this pass), 48 B appended, state r+w, weight r+w, prototype id
+                jp = 4 * ((J_nodes + 1 + 3) // 4 * 4)
+                alg = (16 + jp * (age0 + (n_steps - 1) / 2.0) + jp + 8 + 16 + 4) * n_local
             elif name.startswith("k_propose"):
                 alg = bytes_propose * n_local
             else:
@@ -502,6 +520,7 @@ def belief_leg(wl, args, fba, torch, dist, ctx, world, rank, sampler, steps, hea
 
     # ---- pass 1 + 2: the default path, in-place systematic resampling (survivors are not moved) ----
     ms, per_step, launches, copies = value_pass(steps, args.warmup + 2)
+    value_age0 = value_age[0]
     kms_total, table, kcopies = kernel_pass(min(steps, 10), 500)
     value = n_local * world * steps / (ms * 1e-3)
     dominant = max(table, key=lambda k: table[k]["ms_per_launch"] * table[k]["launches"])
@@ -510,6 +529,10 @@ def belief_leg(wl, args, fba, torch, dist, ctx, world, rank, sampler, steps, hea
         roof = roofline_of(table, "k_copy_inplace",
                            "bytes = %d B x copied particles (%.1f%% of the particles per update; survivors "
                            "stay in place)" % (bytes_per_particle, 100 * kcopies / float(n_local * min(steps, 10))))
+    elif journal_updates:
+        roof = roofline_of(table, "k_propose_journal",
+                           "bytes = each particle's journal read once (16 B + 48 B per earlier update; updates %d-%d "
+                           "in this pass) + 48 B appended + state / weight" % (age[0] - min(steps, 10), age[0] - 1))
     else:
         roof = roofline_of(table, "k_propose",
                            "k_propose touches %d algorithmic bytes per particle in %d scattered rows; it is "
@@ -517,6 +540,10 @@ def belief_leg(wl, args, fba, torch, dist, ctx, world, rank, sampler, steps, hea
                            % (bytes_propose, FS + FO))
     # whole update against the roofline: algorithmic bytes of propose + copies per device-second
     step_alg = bytes_propose * n_local + bytes_per_particle * copies / float(steps)
+    if journal_updates:  # journal read + append per particle, copies move journals: averaged over the value pass
+        jp = 4 * ((J_nodes + 1 + 3) // 4 * 4)
+        mean_len = value_age0 + (steps - 1) / 2.0
+        step_alg = (16 + jp * mean_len + jp + 28) * n_local + 2 * (16 + jp * mean_len) * copies / float(steps)
     step_frac = step_alg / (ms / steps * 1e-3) / 1e9 / peak
 
     # ---- the full-copy path (every particle gathered into the second buffer): the algorithm SURVEY.md
@@ -569,6 +596,7 @@ def belief_leg(wl, args, fba, torch, dist, ctx, world, rank, sampler, steps, hea
                           "peak": peak, "unit": "GB/s", "frac": step_frac,
                           "note": "propose + in-place copies, algorithmic bytes per GPU / device time per update"},
         "resampling_copies_per_update_frac": copied_frac, "full_copy": full, "p2p_timeouts": timeouts,
+        "updates_per_particle_during_value_pass": [value_age0, value_age0 + steps - 1],
         "config": {"workload": WORKLOADS[wl]["text"], "structures": int(len(psid)),
                    "particles_per_gpu": n_local, "particles_total": n_local * world,
                    "count_cells_per_particle": C, "rng": "philox4x32-10",
@@ -611,6 +639,11 @@ def main_ours(args):
     if args.workload == "sysadmin" and not args.no_config4 and not args.particles:
         # BASELINE.json configs[3] in the same driver-run record: collision avoidance, 10^6 particles per GPU
         extra = belief_leg("ca", args, fba, torch, dist, ctx, world, rank, sampler, args.steps, False)
+    journal = None
+    if args.workload == "sysadmin" and not args.no_journal and not args.particles and not args.journal_updates:
+        # the same workload with base+journal storage (young beliefs: particle = prototype + its increments)
+        journal = belief_leg("sysadmin", args, fba, torch, dist, ctx, world, rank, sampler, args.steps, False,
+                             journal_updates=96)
     clocks = sampler.finish()
 
     line = {
@@ -633,6 +666,16 @@ def main_ours(args):
                                   particles_per_gpu=extra["config"]["particles_per_gpu"],
                                   structures=extra["config"]["structures"],
                                   clocks=clocks[1] if len(clocks) > 1 else None)
+    if journal is not None:
+        line["journal"] = {k: journal[k] for k in ("value", "ms_per_step", "ms_per_step_spread_rank0", "e2e", "roofline",
+                                                   "step_roofline", "kernels", "resampling_copies_per_update_frac",
+                                                   "updates_per_particle_during_value_pass", "p2p_timeouts")}
+        line["journal"].update(
+            unit=UNIT, n_gpus=world,
+            storage="base + journal (fba_model_desc.delta_capacity = 11 x 96): a particle is its prior prototype + the "
+                    "cells it incremented; valid for the first 96 updates of a belief, bit-identical results "
+                    "(tests/test_cuda_journal.py). The headline `value` is the dense steady state, valid at any age.",
+            clocks=clocks[2 if extra is not None else 1] if len(clocks) > (2 if extra is not None else 1) else None)
     if not args.no_rollouts:
         line["rollouts"] = rollouts_leg(ctx, fba, args, torch, world, rank, dist)
     if world == 1 and not args.no_rollouts:
@@ -675,6 +718,9 @@ def main():
     ap.add_argument("--force-sharded", action="store_true", help="use the sharded code path on 1 GPU")
     ap.add_argument("--no-full-copy", action="store_true", help="skip the full-copy resampling leg")
     ap.add_argument("--no-config4", action="store_true", help="skip the collision-avoidance (configs[3]) leg")
+    ap.add_argument("--no-journal", action="store_true", help="skip the base+journal storage leg")
+    ap.add_argument("--journal-updates", type=int, default=0,
+                    help="> 0: base+journal storage holding this many updates per particle (0: dense blocks)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

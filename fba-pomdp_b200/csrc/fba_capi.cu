@@ -80,6 +80,9 @@ struct fba_belief
     float* base       = nullptr;
     int n_bases       = 0;
     std::vector<float> h_base;
+    long long delta_used = 0;        // increments every particle's list holds (equal for all: one update appends J)
+    int* d_proto_sid  = nullptr;     // prototype (base table) -> structure id
+    std::vector<int> h_proto_sid;
     float* counts[2] = {nullptr, nullptr};
     int* state[2]    = {nullptr, nullptr};
     int* sid[2]      = {nullptr, nullptr};
@@ -545,8 +548,17 @@ extern "C" int fba_model_create(fba_ctx* ctx, const fba_model_desc* d, int32_t m
     REQUIRE(ctx, !d->tabular || (d->n_state_features == 1 && d->n_obs_features == 1),
             "model: tabular models have exactly one state and one observation feature");
     REQUIRE(ctx, d->delta_capacity >= 0, "model: negative delta_capacity");
-    REQUIRE(ctx, d->delta_capacity == 0 || d->tabular, "model: base+delta storage is for tabular models");
-    REQUIRE(ctx, d->delta_capacity == 0 || (d->S <= kMaxDeltaRow && d->O <= kMaxDeltaRow),
+    if (d->delta_capacity > 0 && !d->tabular)
+    { // factored journal: the rows gathered in one pass must fit kMaxJournalCells
+        int sum_s = 0, sum_o = 0;
+        for (int f = 0; f < d->n_state_features; ++f) sum_s += d->state_feature_sizes[f];
+        for (int f = 0; f < d->n_obs_features; ++f) sum_o += d->obs_feature_sizes[f];
+        REQUIRE(ctx, sum_s <= kMaxJournalCells && sum_o <= kMaxJournalCells,
+                "model: base+journal storage needs the feature ranges to sum to at most 96");
+        REQUIRE(ctx, d->delta_capacity % (d->n_state_features + d->n_obs_features) == 0,
+                "model: a factored model's delta_capacity must be a multiple of its number of nodes per action");
+    }
+    REQUIRE(ctx, d->delta_capacity == 0 || !d->tabular || (d->S <= kMaxDeltaRow && d->O <= kMaxDeltaRow),
             "model: base+delta storage supports rows of at most " + std::to_string(kMaxDeltaRow) + " cells");
 
     auto m         = new fba_model();
@@ -760,8 +772,10 @@ extern "C" int fba_belief_create(fba_ctx* ctx, fba_model* m, int64_t N, int64_t 
     long long const lstride = stride;
     if (m->delta_cap > 0)
     {
-        REQUIRE(ctx, m->n_structs == 1, "belief: base+delta storage needs exactly one (tabular) structure");
-        stride = ((long long)m->delta_cap + 1 + 3) & ~3ll; // header + increments, in 4-byte words
+        REQUIRE(ctx, m->n_structs == 1 || !m->dev.tabular, "belief: tabular base+delta storage needs exactly one structure");
+        if (m->dev.tabular) stride = ((long long)m->delta_cap + 1 + 3) & ~3ll; // header + increments, in 4-byte words
+        else // journal: a 4-word header, then delta_cap / J updates of J entries padded to a multiple of 4
+            stride = kJournalHeader + (long long)(m->delta_cap / m->dev.J) * ((m->dev.J + 1 + 3) & ~3);
     }
     CU(ctx, cudaSetDevice(ctx->device));
 
@@ -817,7 +831,7 @@ extern "C" void fba_belief_destroy(fba_belief* b)
         cudaFree(b->state[k]);
         cudaFree(b->sid[k]);
     }
-    cudaFree(b->base);
+    cudaFree(b->base), cudaFree(b->d_proto_sid);
     cudaFreeHost(b->h_sid), cudaFreeHost(b->h_state);
     cudaFree(b->d_jobs);
     cudaFree(b->rs_src), cudaFree(b->rs_state), cudaFree(b->rs_rec), cudaFree(b->rs_flag), cudaFree(b->rs_pos), cudaFree(b->rs_tiles);
@@ -901,12 +915,16 @@ struct DevTmp
 };
 
 // base+delta storage: the prior prototypes become the shared base tables
-static int install_base_tables(fba_belief* b, int n_protos, const float* proto_counts)
+static int install_base_tables(fba_belief* b, int n_protos, const float* proto_counts, const int32_t* proto_struct_id)
 {
     fba_ctx* ctx = b->ctx;
     size_t const n = (size_t)n_protos * b->lstride;
-    cudaFree(b->base);
-    b->base = nullptr;
+    cudaFree(b->base), cudaFree(b->d_proto_sid);
+    b->base = nullptr, b->d_proto_sid = nullptr;
+    b->h_proto_sid.assign(proto_struct_id, proto_struct_id + n_protos);
+    CU(ctx, cudaMalloc(&b->d_proto_sid, (size_t)n_protos * sizeof(int)));
+    CU(ctx, cudaMemcpyAsync(b->d_proto_sid, b->h_proto_sid.data(), (size_t)n_protos * sizeof(int), cudaMemcpyHostToDevice,
+                            ctx->stream));
     CU(ctx, cudaMalloc(&b->base, n * sizeof(float)));
     CU(ctx, cudaMemcpyAsync(b->base, proto_counts, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     b->h_base.assign(proto_counts, proto_counts + n);
@@ -943,10 +961,11 @@ extern "C" int fba_belief_init(fba_belief* b, int32_t n_protos, const int32_t* p
     }
     if (b->delta_cap > 0)
     {
-        int const rc = install_base_tables(b, n_protos, proto_counts);
+        int const rc = install_base_tables(b, n_protos, proto_counts, proto_struct_id);
         if (rc) return rc;
         LAUNCH(ctx, k_init_delta, blocks_for(b->N), kThreads, b->counts[b->cur], b->stride, b->state[b->cur],
-               b->sid[b->cur], b->weighted ? b->w : nullptr, b->N, d_pp, d_ps);
+               b->sid[b->cur], b->weighted ? b->w : nullptr, b->N, d_pp, d_ps, b->m->dev.tabular ? 0 : kJournalHeader - 1);
+        b->delta_used = 0;
         CU(ctx, cudaStreamSynchronize(ctx->stream));
         weights_became_uniform(b);
         return FBA_OK;
@@ -997,10 +1016,11 @@ extern "C" int fba_belief_init_sampled(fba_belief* b, int32_t n_protos, const in
            d_ps, philox_args(rng));
     if (b->delta_cap > 0)
     {
-        int const rc = install_base_tables(b, n_protos, proto_counts);
+        int const rc = install_base_tables(b, n_protos, proto_counts, proto_struct_id);
         if (rc) return rc;
         LAUNCH(ctx, k_init_delta, blocks_for(b->N), kThreads, b->counts[b->cur], b->stride, b->state[b->cur],
-               b->sid[b->cur], b->weighted ? b->w : nullptr, b->N, d_pp, d_ps);
+               b->sid[b->cur], b->weighted ? b->w : nullptr, b->N, d_pp, d_ps, b->m->dev.tabular ? 0 : kJournalHeader - 1);
+        b->delta_used = 0;
         CU(ctx, cudaStreamSynchronize(ctx->stream));
         b->total_weight = 1.0;
         b->suffix_valid = b->cdf_valid = false;
@@ -1091,13 +1111,20 @@ extern "C" int fba_belief_download(fba_belief* b, int64_t first, int64_t count, 
             float* out = counts + i * b->lstride;
             memcpy(out, b->h_base.data() + (size_t)sid_host[i] * b->lstride, (size_t)b->lstride * sizeof(float));
             const int* blk = blocks.data() + (size_t)i * b->stride;
-            for (int e = 1; e <= blk[0]; ++e)
-            {
-                volatile float v = out[blk[e]];
+            auto plus_one  = [&](int cell) {
+                volatile float v = out[cell];
                 v                = v + 1.0f;
-                out[blk[e]]      = v;
+                out[cell]        = v;
+            };
+            if (b->m->dev.tabular)
+                for (int e = 1; e <= blk[0]; ++e) plus_one(blk[e]);
+            else
+            { // journal layout: 4-word header, updates of J entries padded to Jp
+                int const J = b->m->dev.J, Jp = (J + 1 + 3) & ~3, nu = (blk[0] - (kJournalHeader - 1)) / Jp;
+                for (int u = 0; u < nu; ++u)
+                    for (int j = 0; j < J; ++j) plus_one(blk[kJournalHeader + u * Jp + j]);
             }
-            if (struct_id) struct_id[i] = 0; // the only (tabular) structure; sid holds the base table id
+            if (struct_id) struct_id[i] = b->h_proto_sid[(size_t)sid_host[i]]; // sid holds the base table (prototype) id
         }
         return FBA_OK;
     }
@@ -1135,19 +1162,48 @@ static int propose(fba_belief* b, int a, int o, fba_rng* rng, unsigned long long
     int rc;
     if (b->delta_cap > 0)
     {
-        if (rng->mode == FBA_RNG_REPLAY)
+        // every particle's increment list grows by J per update and copies keep the length, so the host
+        // knows when the lists are full without asking the device
+        if (b->delta_used + D.J > b->delta_cap)
         {
-            long long const per = 2ll * D.J, need = per * b->N;
+            ctx->err = "base+delta particles ran out of increment slots after " + std::to_string(b->delta_used / D.J)
+                       + " updates (raise fba_model_desc.delta_capacity)";
+            return FBA_ERR_CAPACITY;
+        }
+        b->delta_used += D.J;
+        bool binary = !D.tabular && !D.sampled && D.FS <= FBA_MAX_FEATURES && D.FO <= 2 && b->delta_cap / D.J <= 255;
+        for (int f = 0; f < D.FS; ++f) binary = binary && D.feat_s[f] == 2;
+        for (int f = 0; f < D.FO; ++f) binary = binary && D.feat_o[f] == 2;
+        if (binary) // the register-only step histograms whole observation CPTs: at most 8 cells = 2 parents
+            for (size_t k = 0; k < b->m->o_par.size(); ++k) binary = binary && __builtin_popcount(b->m->o_par[k]) <= 2;
+#define PROPOSE_DELTA_ARGS(rargs)                                                                              \
+    D, b->base, b->lstride, b->counts[b->cur], b->stride, b->delta_cap, b->state[b->cur], b->sid[b->cur],         \
+        (const int*)b->d_proto_sid, b->w, b->N, a, o, rargs, ctx->d_flag
+        bool const replay = rng->mode == FBA_RNG_REPLAY;
+        long long const per = 2ll * D.J, need = per * b->N;
+        if (replay)
+        {
             if ((rc = stage_words(ctx, rng, need))) return rc;
             if ((rc = clear_flag(ctx))) return rc;
-            LAUNCH_DELTA(ctx, k_propose_delta, true, blocks_for(b->N), kThreads, D, b->base, b->lstride,
-                         b->counts[b->cur], b->stride, b->delta_cap, b->state[b->cur], b->sid[b->cur], b->w, b->N,
-                         a, o, replay_args(ctx, need, per, false), ctx->d_flag);
-            rng->cursor += need;
-        } else
-            LAUNCH_DELTA(ctx, k_propose_delta, false, blocks_for(b->N), kThreads, D, b->base, b->lstride,
-                         b->counts[b->cur], b->stride, b->delta_cap, b->state[b->cur], b->sid[b->cur], b->w, b->N,
-                         a, o, philox_args(rng, stream_base), ctx->d_flag);
+        }
+        RngArgs const ra = replay ? replay_args(ctx, need, per, false) : philox_args(rng, stream_base);
+        if (D.tabular) LAUNCH_DELTA(ctx, k_propose_delta, replay, blocks_for(b->N), kThreads, PROPOSE_DELTA_ARGS(ra));
+        else if (binary)
+        { // all particles hold the same number of updates: (delta_used - J) / J before this one
+            int const nu   = (int)((b->delta_used - D.J) / D.J);
+            int const grid = blocks_for(b->N, kStageWarps * 32);
+            if (replay)
+                LAUNCH(ctx, (k_propose_journal_staged<true>), grid, kStageWarps * 32, PROPOSE_DELTA_ARGS(ra), nu);
+            else
+                LAUNCH(ctx, (k_propose_journal_staged<false>), grid, kStageWarps * 32, PROPOSE_DELTA_ARGS(ra), nu);
+        } else if (replay)
+            LAUNCH(ctx, (k_propose_journal<true, false>), blocks_for(b->N), kThreads, PROPOSE_DELTA_ARGS(ra));
+        else if (D.sampled)
+            LAUNCH(ctx, (k_propose_journal<false, true>), blocks_for(b->N), kThreads, PROPOSE_DELTA_ARGS(ra));
+        else
+            LAUNCH(ctx, (k_propose_journal<false, false>), blocks_for(b->N), kThreads, PROPOSE_DELTA_ARGS(ra));
+#undef PROPOSE_DELTA_ARGS
+        if (replay) rng->cursor += need;
         b->suffix_valid = b->cdf_valid = false;
         return FBA_OK;
     }
@@ -1627,6 +1683,7 @@ extern "C" int fba_belief_reject_sample(fba_belief* b, int32_t a, int32_t o, fba
     DevModel const& D = b->m->dev;
     REQUIRE(ctx, a >= 0 && a < D.A, "action out of range");
     REQUIRE(ctx, o >= 0 && o < D.O, "observation out of range");
+    REQUIRE(ctx, b->delta_cap == 0 || D.tabular, "reject_sample: factored beliefs need dense storage");
     CU(ctx, cudaSetDevice(ctx->device));
     int rc;
     // PHILOX + dense storage: accepted sources keep their slot, only repeated acceptances are copied
@@ -1998,7 +2055,7 @@ extern "C" int fba_rollouts(fba_belief* b, int64_t n, const int64_t* particle, c
         if (b->delta_cap > 0)
             LAUNCH_DELTA(ctx, k_rollouts_delta, true, blocks_for(n, tpb), tpb, D, b->base, b->lstride,
                          b->counts[b->cur], b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r,
-                         ctx->d_flag, ctx->d_counters);
+                         ctx->d_flag, ctx->d_counters, (const int*)b->d_proto_sid);
         else if (coop)
             LAUNCH(ctx, (k_rollouts<true, true, false, false>), blocks_for(n * 32), kThreads, D, b->counts[b->cur],
                    b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag, ctx->d_counters);
@@ -2015,7 +2072,7 @@ extern "C" int fba_rollouts(fba_belief* b, int64_t n, const int64_t* particle, c
         if (b->delta_cap > 0)
             LAUNCH_DELTA(ctx, k_rollouts_delta, false, blocks_for(n, tpb), tpb, D, b->base, b->lstride,
                          b->counts[b->cur], b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r,
-                         ctx->d_flag, ctx->d_counters);
+                         ctx->d_flag, ctx->d_counters, (const int*)b->d_proto_sid);
         else if (coop && !D.sampled)
             LAUNCH(ctx, (k_rollouts<false, true, false, false>), blocks_for(n * 32), kThreads, D, b->counts[b->cur],
                    b->stride, b->sid[b->cur], n, d_p, d_s, d_d, discount, ra, d_r, ctx->d_flag, ctx->d_counters);
@@ -2113,7 +2170,7 @@ extern "C" int fba_step_batch(fba_belief* b, int64_t n, const int64_t* particle,
     if (b->delta_cap > 0)
         LAUNCH_DELTA(ctx, k_step_batch_delta, false, blocks_for(n, tpb), tpb, D, b->base, b->lstride,
                      b->counts[b->cur], b->stride, b->sid[b->cur], (long long)n, b->roll_p, d_s, d_a, philox_args(rng),
-                     d_s2, d_o, b->step_r, d_t, ctx->d_flag);
+                     d_s2, d_o, b->step_r, d_t, ctx->d_flag, (const int*)b->d_proto_sid);
     else
         LAUNCH_RL(ctx, k_step_batch, false, b->m->long_rows, blocks_for(n, tpb), tpb, D, b->counts[b->cur],
                   b->stride, b->sid[b->cur], (long long)n, b->roll_p, d_s, d_a, philox_args(rng), d_s2, d_o,
@@ -2382,7 +2439,7 @@ extern "C" int fba_tree_search(fba_tree* t, fba_belief* b, int64_t n_sims, int32
     T.mask = t->table - 1, T.root = (int)t->table;
     T.counts = b->counts[b->cur], T.stride = b->stride, T.sid = b->sid[b->cur], T.state = b->state[b->cur];
     T.cdf = b->weighted ? b->aux : nullptr, T.N = b->N;
-    T.base = b->base, T.base_stride = b->lstride;
+    T.base = b->base, T.base_stride = b->lstride, T.proto_sid = b->d_proto_sid;
     T.depth = depth, T.u = u, T.discount = discount;
     T.path_node = t->path_node, T.path_action = t->path_action, T.path_reward = t->path_reward;
     T.overflow = t->d_overflow;

@@ -747,6 +747,286 @@ __device__ __forceinline__ double obs_probability_delta(const DevModel& M, const
     delta_row(base, block, nodes[1].off + s2 * M.O, M.O, buf);
     return (double)likelihood_at<SAMPLED>(buf, M.O, o, g);
 }
+
+// ------------------------------------------------------------------------------------------------
+// FACTORED particles stored as SHARED BASE + PRIVATE JOURNAL: every particle of a
+// factored belief descends from one of a few prior prototypes (sysadmin: ONE, SysAdminFactoredPrior.cpp:
+// 34-37,138-267), and one update increments exactly J = FS + FO cells of it — so a young particle is its
+// prototype plus a short list of cells, J per update, in node order. Layout (4-byte words, everything
+// 16-byte aligned so that an update is read and written as whole int4 vectors):
+//   block[0] = 3 + nu Jp   (words that follow the first; the copy kernels move (block[0] + 1 + 3) / 4 vectors)
+//   block[4 + u Jp + j]    = the cell node j's +1 of update u went to, j < J; -1 for j in [J, Jp - 1);
+//   block[4 + u Jp + Jp-1] = -2 - (the update's action)
+// with Jp = J + 1 rounded up to a multiple of 4. Against the dense private block (11.8 KB per sysadmin
+// particle) an update then appends 48 CONTIGUOUS bytes instead of dirtying 11 isolated 32-byte sectors,
+// and a resampling copy moves 16 + 48 t bytes instead of 23.7 KB. A row is the prototype's row plus the
+// particle's own +1s; every increment is exactly +1.0f (DBNNode.cpp:124-127), applied one by one, so sums
+// are bit-identical to the dense block's (tests/test_cuda_journal.py replays the same fixtures).
+// All FS transition rows of a step depend only on the OLD state, so ONE pass over the journal fills them
+// all (entry j of an update can only belong to node j); the observation rows need the new state.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxJournalCells = 96; // sum of the feature ranges the gathered rows may have
+constexpr int kJournalHeader   = 4;  // words before the first update
+
+// J entries + at least one tag slot, rounded up to whole int4 vectors; the LAST slot of an update holds
+// -2 - action, so that a reader skips the updates of other actions after one comparison
+__device__ __forceinline__ int journal_padded(int J) { return (J + 1 + 3) & ~3; }
+__device__ __forceinline__ int journal_tag(int a) { return -2 - a; }
+
+// likelihood != nullptr: also returns P(o_real | a, s') evaluated AFTER the increment, as
+// importance_sampling::update does (ImportanceSampler.hpp:45-46): the observation row of the new state
+// is the row the simulated observation was drawn from, plus the +1 just made if it landed in that row
+template<int MODE, bool SAMPLED, class R>
+__device__ __forceinline__ int hyper_step_journal(const DevModel& M, const Node* __restrict__ nodes,
+                                                  const float* __restrict__ base, int* block, int cap, int s,
+                                                  R& g, int& o_out, int* rec, int* overflow, int o_real,
+                                                  double* likelihood, int a)
+{
+    bool const single_s = (M.FS == 1), single_o = (M.FO == 1);
+    int const J = M.J, Jp = journal_padded(J), nu = (block[0] - (kJournalHeader - 1)) / Jp;
+    const int* upd = block + kJournalHeader;
+    Feat const x = decode(s, M.step_s, M.FS, M.pow2_s, M.shift_s);
+    float row[kMaxJournalCells];
+    int cell0[FBA_MAX_FEATURES], roff[FBA_MAX_FEATURES];
+    int tot = 0;
+    for (int f = 0; f < M.FS; ++f)
+    {
+        Node const nd   = nodes[f];
+        int const range = M.feat_s[f];
+        cell0[f]        = nd.off + parent_config(M, nd.par, x) * range;
+        roff[f]         = tot;
+        for (int v = 0; v < range; ++v) row[tot + v] = base[cell0[f] + v];
+        tot += range;
+    }
+    int const tag = journal_tag(a);
+    for (int u = 0; u < nu; ++u) // entry f of an update can only hit node f's row
+        for (int f = 0; f < M.FS && upd[u * Jp + Jp - 1] == tag; ++f)
+        {
+            unsigned const c = (unsigned)(upd[u * Jp + f] - cell0[f]);
+            if (c < (unsigned)M.feat_s[f]) row[roff[f] + c] = __fadd_rn(row[roff[f] + c], 1.0f);
+        }
+    Feat x2{0ull, 0ull};
+    int s2 = 0;
+    int inc[FBA_MAX_FEATURES * 2];
+    for (int f = 0; f < M.FS; ++f)
+    {
+        int const v = sample_row<true, SAMPLED>(row + roff[f], M.feat_s[f], g);
+        x2.set(f, v, single_s);
+        s2 += v * M.step_s[f];
+        inc[f] = cell0[f] + v;
+    }
+    if (single_s) s2 = (int)x2.lo;
+
+    // observation rows of the NEW state (BABNModel.cpp:309-326)
+    tot = 0;
+    for (int q = 0; q < M.FO; ++q)
+    {
+        Node const nd   = nodes[M.FS + q];
+        int const range = M.feat_o[q];
+        cell0[q]        = nd.off + parent_config(M, nd.par, x2) * range;
+        roff[q]         = tot;
+        for (int v = 0; v < range; ++v) row[tot + v] = base[cell0[q] + v];
+        tot += range;
+    }
+    for (int u = 0; u < nu; ++u)
+        for (int q = 0; q < M.FO && upd[u * Jp + Jp - 1] == tag; ++q)
+        {
+            unsigned const c = (unsigned)(upd[u * Jp + M.FS + q] - cell0[q]);
+            if (c < (unsigned)M.feat_o[q]) row[roff[q] + c] = __fadd_rn(row[roff[q] + c], 1.0f);
+        }
+    int o = 0;
+    Feat of{0ull, 0ull};
+    for (int q = 0; q < M.FO; ++q)
+    {
+        int const v = sample_row<true, SAMPLED>(row + roff[q], M.feat_o[q], g);
+        of.set(q, v, single_o);
+        o += v * M.step_o[q];
+    }
+    if (single_o) o = (int)of.lo;
+    // incrementCountsOf, observation part: the OLD state's parent configuration (BABNModel.cpp:366,380)
+    for (int q = 0; q < M.FO; ++q)
+    {
+        Node const nd = nodes[M.FS + q];
+        inc[M.FS + q] = nd.off + parent_config(M, nd.par, x) * M.feat_o[q] + of.get(q, single_o);
+    }
+    if (MODE == STEP_UPDATE)
+    {
+        if ((nu + 1) * J <= cap)
+        {
+            int* dst = block + kJournalHeader + nu * Jp;
+            for (int j = 0; j < Jp; ++j) dst[j] = (j < J) ? inc[j] : (j == Jp - 1) ? tag : -1;
+            block[0] = (kJournalHeader - 1) + (nu + 1) * Jp;
+        } else
+            *overflow = 2;
+    }
+    if (MODE == STEP_RECORD)
+        for (int j = 0; j < J; ++j) rec[j] = inc[j];
+    if (likelihood)
+    { // BABNModel::computeObservationProbability (BABNModel.cpp:328-352) on the updated counts
+        Feat const fr = decode(o_real, M.step_o, M.FO, M.pow2_o, M.shift_o);
+        double prob   = 1.0;
+        for (int q = 0; q < M.FO; ++q)
+        {
+            int const range = M.feat_o[q];
+            if (MODE == STEP_UPDATE)
+            {
+                unsigned const c = (unsigned)(inc[M.FS + q] - cell0[q]);
+                if (c < (unsigned)range) row[roff[q] + c] = __fadd_rn(row[roff[q] + c], 1.0f);
+            }
+            prob = __dmul_rn(prob, (double)likelihood_at<SAMPLED>(row + roff[q], range, fr.get(q, single_o), g));
+        }
+        *likelihood = prob;
+    }
+    o_out = o;
+    return s2;
+}
+
+// The same step when EVERY feature is binary (sysadmin, factored tiger), expected mode, UpdateCounts,
+// observation CPTs of at most 8 cells, as three phases so that the kernel can feed the journal in
+// chunks STAGED THROUGH SHARED MEMORY (k_propose_journal_staged): begin() fixes the cells of interest —
+// the parent configuration of every transition node is known from the old state — add() counts, in 8-bit
+// fields of four 64-bit registers, how many +1s each of the 2 FS cells of interest received (f is a
+// compile-time constant of the unrolled loop, so the field shifts are too) and histograms the WHOLE CPT of
+// each observation node (<= 8 cells, one 64-bit register each) because their row is only known once the
+// new state is drawn; finish() rebuilds the rows as base, +1.0f, +1.0f, … — the same sequence of rounded
+// adds the dense block went through — draws, and returns the J cells to append. No array in local
+// memory in the hot loop. At most 255 updates per particle.
+struct JournalBinaryStep
+{
+    int cell0[FBA_MAX_FEATURES];
+    int ooff0, ooff1, tag;
+    unsigned long long h0a, h0b, h1a, h1b; // hits of value 0 / 1, features 0-7 / 8-15
+    unsigned long long ho0, ho1;           // per-cell hits of observation node 0 / 1
+    Feat x;
+
+    __device__ __forceinline__ void begin(const DevModel& M, const Node* __restrict__ nodes, int s, int a)
+    {
+        tag = journal_tag(a);
+        x   = decode(s, M.step_s, M.FS, M.pow2_s, M.shift_s);
+#pragma unroll
+        for (int f = 0; f < FBA_MAX_FEATURES; ++f)
+            cell0[f] = (f < M.FS) ? nodes[f].off + parent_config(M, nodes[f].par, x) * 2 : 0x40000000;
+        ooff0 = nodes[M.FS].off, ooff1 = (M.FO > 1) ? nodes[M.FS + 1].off : 0x40000000;
+        h0a = h0b = h1a = h1b = ho0 = ho1 = 0ull;
+    }
+
+    // n_updates updates of nvec int4 vectors each, lying at upd[0 .. n_updates nvec)
+    __device__ __forceinline__ void add(const DevModel& M, const int4* upd, int n_updates, int nvec)
+    {
+        for (int u = 0; u < n_updates; ++u)
+        {
+            if (upd[u * nvec + nvec - 1].w != tag) continue; // another action's update: none of its cells is ours
+#pragma unroll
+            for (int k = 0; k < (FBA_MAX_FEATURES + 4 + 3) / 4; ++k)
+            {
+                if (k >= nvec) break;
+                int4 const v4 = upd[u * nvec + k];
+#pragma unroll
+                for (int l = 0; l < 4; ++l)
+                {
+                    int const j = 4 * k + l; // compile-time
+                    int const e = (l == 0) ? v4.x : (l == 1) ? v4.y : (l == 2) ? v4.z : v4.w;
+                    if (j < FBA_MAX_FEATURES && j < M.FS)
+                    {
+                        int const c = e - cell0[j < FBA_MAX_FEATURES ? j : 0];
+                        unsigned long long const one = 1ull << (8 * (j & 7));
+                        if (j < 8)
+                        {
+                            h0a += (c == 0) ? one : 0ull;
+                            h1a += (c == 1) ? one : 0ull;
+                        } else
+                        {
+                            h0b += (c == 0) ? one : 0ull;
+                            h1b += (c == 1) ? one : 0ull;
+                        }
+                    } else if (j == M.FS)
+                    { // cells of other actions' nodes fall outside [0, 8)
+                        unsigned const d = (unsigned)(e - ooff0);
+                        ho0 += (d < 8u) ? 1ull << (8 * d) : 0ull;
+                    } else if (j == M.FS + 1 && j < M.J)
+                    {
+                        unsigned const d = (unsigned)(e - ooff1);
+                        ho1 += (d < 8u) ? 1ull << (8 * d) : 0ull;
+                    }
+                }
+            }
+        }
+    }
+
+    // draws s' and the simulated observation, fills inc[0..J) with the cells to increment, returns s';
+    // *likelihood = P(o_real | a, s') on the counts AFTER the increment (ImportanceSampler.hpp:45-46)
+    template<class R>
+    __device__ __forceinline__ int finish(const DevModel& M, const Node* __restrict__ nodes,
+                                          const float* __restrict__ base, R& g, int o_real, int* inc,
+                                          double* likelihood) const
+    {
+        Feat x2{0ull, 0ull};
+        int s2 = 0;
+#pragma unroll
+        for (int f = 0; f < FBA_MAX_FEATURES; ++f)
+        {
+            if (f >= M.FS) break;
+            int const k0 = (int)(((f < 8 ? h0a : h0b) >> (8 * (f & 7))) & 0xff);
+            int const k1 = (int)(((f < 8 ? h1a : h1b) >> (8 * (f & 7))) & 0xff);
+            float r0 = base[cell0[f]], r1 = base[cell0[f] + 1];
+            for (int k = 0; k < k0; ++k) r0 = __fadd_rn(r0, 1.0f);
+            for (int k = 0; k < k1; ++k) r1 = __fadd_rn(r1, 1.0f);
+            // sample_expected_mult(row, 2, u): double total, float prefix
+            double const p = __dmul_rn(draw_u(g), __dadd_rn((double)r0, (double)r1));
+            int const v    = (p < (double)r0) ? 0 : 1;
+            x2.set(f, v, M.FS == 1);
+            s2 += v * M.step_s[f];
+            inc[f] = cell0[f] + v;
+        }
+        if (M.FS == 1) s2 = (int)x2.lo;
+        // observation nodes: rows of the NEW state out of the CPT histograms
+        Feat const fr = decode(o_real, M.step_o, M.FO, M.pow2_o, M.shift_o);
+        double prob   = 1.0;
+        for (int q = 0; q < M.FO; ++q)
+        {
+            Node const nd = nodes[M.FS + q];
+            int const r   = parent_config(M, nd.par, x2) * 2; // the row's first cell inside the CPT
+            unsigned long long const h = q ? ho1 : ho0;
+            int const k0 = (int)((h >> (8 * r)) & 0xff), k1 = (int)((h >> (8 * (r + 1))) & 0xff);
+            float r0 = base[nd.off + r], r1 = base[nd.off + r + 1];
+            for (int k = 0; k < k0; ++k) r0 = __fadd_rn(r0, 1.0f);
+            for (int k = 0; k < k1; ++k) r1 = __fadd_rn(r1, 1.0f);
+            double const p = __dmul_rn(draw_u(g), __dadd_rn((double)r0, (double)r1));
+            int const v    = (p < (double)r0) ? 0 : 1;
+            // incrementCountsOf: the OLD state's parent configuration (BABNModel.cpp:366,380)
+            int const ci  = parent_config(M, nd.par, x) * 2 + v;
+            inc[M.FS + q] = nd.off + ci;
+            if (ci == r) r0 = __fadd_rn(r0, 1.0f);
+            if (ci == r + 1) r1 = __fadd_rn(r1, 1.0f);
+            // expectedMult(row)[o_real_q] on the updated row: float sum, float divide (random.cpp:257-279)
+            float const sum = __fadd_rn(r0, r1);
+            float const num = fr.get(q, M.FO == 1) ? r1 : r0;
+            prob = __dmul_rn(prob, ((double)sum <= 1e-300) ? 0.0 : (double)__fdiv_rn(num, sum));
+        }
+        *likelihood = prob;
+        return s2;
+    }
+};
+
+// BAPOMDP::step on a base+delta particle of either kind: tabular (row scans over long rows) or factored
+// (journal). proto = the particle's prior prototype (its base table); proto_sid[proto] = that
+// prototype's structure id (tabular: the only structure).
+template<int MODE, bool SAMPLED, class R>
+__device__ __forceinline__ int step_delta_particle(const DevModel& M, const int* __restrict__ proto_sid, int proto, int a,
+                                                   const float* __restrict__ tb, int* block, int cap, int s, R& g,
+                                                   int& o_out, int* rec, int* overflow, int o_real, double* likelihood)
+{
+    if (M.tabular)
+    {
+        const Node* nodes = M.nodes + (long long)a * M.J;
+        int const s2      = hyper_step_delta<MODE, SAMPLED>(M, nodes, tb, block, cap, s, g, o_out, rec, overflow);
+        if (likelihood) *likelihood = obs_probability_delta<SAMPLED>(M, nodes, tb, block, s2, o_real, g);
+        return s2;
+    }
+    const Node* nodes = M.nodes + ((long long)proto_sid[proto] * M.A + a) * M.J;
+    return hyper_step_journal<MODE, SAMPLED>(M, nodes, tb, block, cap, s, g, o_out, rec, overflow, o_real, likelihood, a);
+}
+
 #endif // __CUDACC__
 
 } // namespace fba
