@@ -2458,7 +2458,8 @@ __global__ void __launch_bounds__(kThreads)
 // lane walks its own particle's row (rows padded to 33 vectors: conflict-free 128-bit reads). All
 // particles of a belief hold the same number of updates nu (one per update, copies keep it), which the
 // host knows, so there is no divergence in the staging loop. Appends are three 16-byte stores per particle.
-constexpr int kStageWarps = 2;
+constexpr int kStageWarps = 4;
+constexpr int kStageVec   = 16; // int4 vectors of one particle's journal per staged chunk
 template<bool REPLAY>
 __global__ void __launch_bounds__(kStageWarps * 32)
     k_propose_journal_staged(DevModel M, const float* __restrict__ base, long long base_stride, float* blocks,
@@ -2466,14 +2467,14 @@ __global__ void __launch_bounds__(kStageWarps * 32)
                              const int* __restrict__ proto_sid, double* __restrict__ w, long long N, int a, int o,
                              RngArgs ra, int* __restrict__ overrun, int nu)
 {
-    __shared__ int4 stage[kStageWarps][32][33];
+    __shared__ int4 stage[kStageWarps][32][kStageVec + 1];
     int const lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     long long const first = ((long long)blockIdx.x * kStageWarps + wib) * 32; // the warp's first particle
     if (first >= N) return;
     long long const i = first + lane;
     bool const valid  = i < N;
     int const J = M.J, Jp = journal_padded(J), nvec = Jp >> 2;
-    int const per_chunk = 32 / nvec; // whole updates per staged chunk
+    int const per_chunk = kStageVec / nvec; // whole updates per staged chunk
     JournalBinaryStep st;
     const Node* nodes = nullptr;
     const float* tb   = nullptr;
