@@ -76,12 +76,15 @@ def main():
     exchange = sys.argv[1] if len(sys.argv) > 1 else "p2p"
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 20000
     fixture = sys.argv[3] if len(sys.argv) > 3 else "sysadmin"
+    journal = len(sys.argv) > 4 and sys.argv[4] == "journal"
     rank, world, local = (int(os.environ[k]) for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     g = G.load(fixture)
     ctx = fba.Context(local)
-    sim = fba.BAPOMDP(ctx, g.desc, g.t_par, g.o_par)
+    J_nodes = len(np.asarray(g.desc["feat_s"]).reshape(-1)) + len(np.asarray(g.desc["feat_o"]).reshape(-1))
+    desc = dict(g.desc, delta_capacity=J_nodes * 16) if journal else g.desc   # base + journal storage, 16 updates
+    sim = fba.BAPOMDP(ctx, desc, g.t_par, g.o_par)
     psid, protos = prototypes(g)
     probs = None if len(psid) == 1 else np.ones(len(psid))
     J = sim.FS + sim.FO
@@ -103,8 +106,11 @@ def main():
 
     def check_slots(b, t_updates, base_sums):
         d = b.download()
+        # a valid particle after t updates sums to a prototype's sum + J t; priors with fractional counts round
+        # a little on every float32 +1, a stale or foreign block is off by at least one whole increment
         sums = d["counts"].astype(np.float64).sum(1) - float(J) * t_updates
-        assert np.isin(sums, base_sums).all(), (rank, t_updates, np.unique(sums)[:5], base_sums[:5])
+        dist_to_proto = np.abs(sums[:, None] - base_sums[None, :]).min(1)
+        assert dist_to_proto.max() < 0.25, (rank, t_updates, dist_to_proto.max(), np.unique(sums)[:5], base_sums[:5])
         assert d["state"].min() >= 0 and d["state"].max() < sim.S
         np.testing.assert_array_equal(d["w"], np.full(n, 1.0 / n))
         return d
@@ -182,7 +188,8 @@ def main():
     ctx.close()
     dist.barrier()
     if rank == 0:
-        print("sharded check ok: exchange=%s world=%d n_local=%d fixture=%s" % (exchange, world, n, fixture))
+        print("sharded check ok: exchange=%s world=%d n_local=%d fixture=%s%s"
+              % (exchange, world, n, fixture, " (journal storage)" if journal else ""))
     dist.destroy_process_group()
 
 
