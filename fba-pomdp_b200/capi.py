@@ -20,7 +20,7 @@ RNG_REPLAY, RNG_PHILOX = 0, 1
 P2P_BLOB_BYTES = 320  # FBA_P2P_BLOB_BYTES
 
 # every symbol include/fba_pomdp_b200.h declares (tests check the library exports all of them)
-ABI_VERSION = 11  # must equal FBA_ABI_VERSION in include/fba_pomdp_b200.h
+ABI_VERSION = 12  # must equal FBA_ABI_VERSION in include/fba_pomdp_b200.h
 
 SYMBOLS = [
     "fba_abi_version", "fba_ctx_create", "fba_ctx_destroy", "fba_last_error", "fba_ctx_stream", "fba_ctx_synchronize",
@@ -45,6 +45,7 @@ SYMBOLS = [
     "fba_tree_create", "fba_tree_destroy", "fba_tree_search",
     "fba_runs_create", "fba_runs_destroy", "fba_runs_belief", "fba_runs_init_sampled",
     "fba_runs_update_estimation", "fba_runs_reset_domain_states", "fba_runs_sample", "fba_runs_copies", "fba_runs_plan", "fba_runs_init",
+    "fba_belief_replace_from", "fba_belief_cheat", "fba_belief_breed_into", "fba_belief_least_likely", "fba_belief_promote", "fba_belief_redraw_domain_states",
 ]
 
 
@@ -186,6 +187,12 @@ def lib():
             "fba_runs_copies": (i64, [vp]),
             "fba_runs_init": (C.c_int, [vp, i32, vp, vp, vp, vp]),
             "fba_runs_plan": (C.c_int, [vp, i64, vp, dbl, dbl, i32, vp, vp, vp, vp, vp]),
+            "fba_belief_replace_from": (C.c_int, [vp, vp, vp, vp, i64]),
+            "fba_belief_cheat": (C.c_int, [vp, vp, i64, vp]),
+            "fba_belief_breed_into": (C.c_int, [vp, vp, i64, vp, vp, i32, vp]),
+            "fba_belief_least_likely": (C.c_int, [vp, i64, vp]),
+            "fba_belief_promote": (C.c_int, [vp, vp, dbl, vp, vp]),
+            "fba_belief_redraw_domain_states": (C.c_int, [vp, vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)

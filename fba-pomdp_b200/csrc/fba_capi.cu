@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <queue>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -1562,14 +1563,16 @@ static long long start_state_words(const DevModel& D, const fba_rng* rng, long l
     }
 }
 
-extern "C" int fba_belief_reset_domain_states(fba_belief* b, fba_rng* rng)
+// with_resample: BAImportanceSampling::resetDomainStateDistribution on a weighted belief (N weighted draws
+// first); otherwise BAPOMDP::resetDomainState on every particle where it is (BAPOMDP.cpp:69-77)
+static int reset_states(fba_belief* b, fba_rng* rng, bool with_resample)
 {
-    if (!b || !rng) return FBA_ERR_INVALID;
     fba_ctx* ctx      = b->ctx;
     DevModel const& D = b->m->dev;
     CU(ctx, cudaSetDevice(ctx->device));
     int rc;
-    int const skip = b->weighted ? 2 : 0; // weighted: one pick uniform precedes the start draws
+    bool const weighted = b->weighted && with_resample;
+    int const skip = weighted ? 2 : 0; // weighted: one pick uniform precedes the start draws
     if (rng->mode == FBA_RNG_REPLAY)
     {
         // item j: [weighted pick u] + start-state draws; the latter may vary in length
@@ -1585,7 +1588,7 @@ extern "C" int fba_belief_reset_domain_states(fba_belief* b, fba_rng* rng)
         if ((rc = stage_words(ctx, rng, need))) return rc;
         if ((rc = stage_offsets(ctx, off))) return rc;
         CU(ctx, cudaStreamSynchronize(ctx->stream)); // `off` is about to go out of scope
-        if (b->weighted)
+        if (weighted)
         {
             if ((rc = pick_ancestors(b, rng, b->N, 0, true, need))) return rc;
             if ((rc = gather_into_next(b, b->N, false))) return rc;
@@ -1596,13 +1599,13 @@ extern "C" int fba_belief_reset_domain_states(fba_belief* b, fba_rng* rng)
                replay_args(ctx, need, 0, true), skip, ctx->d_flag);
         rng->cursor += need;
         if ((rc = check_flag(ctx))) return rc;
-        if (b->weighted) weights_became_uniform(b);
+        if (weighted) weights_became_uniform(b);
     } else
     {
-        if (b->weighted && ctx->inplace_resample)
+        if (weighted && ctx->inplace_resample)
         { // survivors keep their slot (and the back buffer stays unallocated); states are redrawn below
             if ((rc = resample_inplace(b, rng, b->N))) return rc;
-        } else if (b->weighted)
+        } else if (weighted)
         {
             if ((rc = pick_ancestors(b, rng, b->N, 0, false, 0))) return rc;
             if ((rc = gather_into_next(b, b->N, false))) return rc;
@@ -1614,6 +1617,18 @@ extern "C" int fba_belief_reset_domain_states(fba_belief* b, fba_rng* rng)
                philox_args(rng), 0, ctx->d_flag);
     }
     return FBA_OK;
+}
+
+extern "C" int fba_belief_reset_domain_states(fba_belief* b, fba_rng* rng)
+{
+    if (!b || !rng) return FBA_ERR_INVALID;
+    return reset_states(b, rng, true);
+}
+
+extern "C" int fba_belief_redraw_domain_states(fba_belief* b, fba_rng* rng)
+{
+    if (!b || !rng) return FBA_ERR_INVALID;
+    return reset_states(b, rng, false);
 }
 
 extern "C" int fba_belief_sample(fba_belief* b, fba_rng* rng, int64_t* index)
@@ -1850,16 +1865,50 @@ struct HostDraws
 };
 } // namespace
 
-extern "C" int fba_belief_reinvigorate(fba_belief* b, fba_belief* fc, int64_t amount, int32_t mutate_kind,
-                                       fba_rng* rng)
+// WeightedFilter::replace(i, s, dealloc) (WeightedFilter.cpp:71-90) for the slots in `order`, one after the
+// other: the new particle's weight is _total_weight / N and _total_weight moves by the difference. The
+// weights are few and the rule is sequential, so it runs on the host over a copy of the weight array.
+static int host_replace_weights(fba_belief* b, const std::vector<int>& order)
 {
-    if (!b || !fc || !rng) return FBA_ERR_INVALID;
+    fba_ctx* ctx = b->ctx;
+    if (!b->weighted || order.empty()) return FBA_OK;
+    std::vector<double> w((size_t)b->N);
+    CU(ctx, cudaMemcpyAsync(w.data(), b->w, (size_t)b->N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    volatile double total = b->total_weight; // volatile: separately rounded operations, in order
+    for (int slot : order)
+    {
+        double const w_new = total / (double)b->N;
+        volatile double diff = w_new - w[(size_t)slot];
+        w[(size_t)slot] = w_new;
+        total           = total + diff;
+    }
+    CU(ctx, cudaMemcpyAsync(b->w, w.data(), (size_t)b->N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    b->total_weight = total;
+    b->suffix_valid = b->cdf_valid = false;
+    return FBA_OK;
+}
+
+// `amount` x breed (ReinvigoratingRejectionSampling.cpp:24-35): a structure donor from `b`, a counts donor
+// from `fc`, the domain's mutate, marginalizeOut; the bred particle goes to slot dst_slots[k] of `dst`, or,
+// with dst_slots == NULL, to a uniformly drawn slot of dst = b (FlatFilter::replace).
+static int breed_core(fba_belief* dst, const int64_t* dst_slots, fba_belief* b, fba_belief* fc, int64_t amount,
+                      int32_t mutate_kind, fba_rng* rng)
+{
     fba_ctx* ctx      = b->ctx;
     fba_model* m      = b->m;
     DevModel const& D = m->dev;
-    REQUIRE(ctx, fc->m == m && fc->ctx == ctx, "reinvigorate: both beliefs must share one model and context");
+    REQUIRE(ctx, fc->m == m && fc->ctx == ctx && dst->m == m && dst->ctx == ctx,
+            "reinvigorate: the beliefs must share one model and context");
     REQUIRE(ctx, amount >= 1, "reinvigorate: resample size of < 1 (" + std::to_string(amount) + ")");
-    REQUIRE(ctx, !D.tabular && b->delta_cap == 0, "reinvigorate: factored models only");
+    REQUIRE(ctx, !D.tabular && b->delta_cap == 0 && fc->delta_cap == 0 && dst->delta_cap == 0,
+            "reinvigorate: factored models (dense storage) only");
+    REQUIRE(ctx, !b->weighted && !fc->weighted, "reinvigorate: the donor beliefs are flat filters");
+    REQUIRE(ctx, dst_slots || dst == b, "reinvigorate: destination slots missing");
+    if (dst_slots)
+        for (int64_t k = 0; k < amount; ++k)
+            REQUIRE(ctx, dst_slots[k] >= 0 && dst_slots[k] < dst->N, "breed_into: destination slot out of range");
     CU(ctx, cudaSetDevice(ctx->device));
 
     // host mirrors of the small per-particle arrays the sequential part reads (pinned: one DMA each)
@@ -1879,6 +1928,7 @@ extern "C" int fba_belief_reinvigorate(fba_belief* b, fba_belief* fc, int64_t am
     int const nT = D.A * D.FS, nO = D.A * D.FO;
     std::vector<uint32_t> tp(nT), op(nO);
     std::map<int, BreedJob> last_writer; // slot -> job; a later breed overwrites an earlier one
+    std::vector<int> order;              // destination slots in breeding order (weights of a weighted dst)
     HostDraws g(rng);
     int const first_new_struct = m->n_structs;
     struct UploadGuard // whatever the exit path, structures registered on the host reach the device
@@ -1934,18 +1984,22 @@ extern "C" int fba_belief_reinvigorate(fba_belief* b, fba_belief* fc, int64_t am
         int32_t id = -1;
         int rc     = add_structures(m, 1, tp.data(), op.data(), &id, false); // uploaded once, below
         if (rc) return rc;
-        if (m->sizes[id] > b->stride)
+        if (m->sizes[id] > dst->stride)
         {
             ctx->err = "reinvigorate: mutated structure needs " + std::to_string(m->sizes[id])
-                       + " cells, belief stride is " + std::to_string(b->stride);
+                       + " cells, the destination's stride is " + std::to_string(dst->stride);
             return FBA_ERR_CAPACITY;
         }
-        int const slot = g.k((uint32_t)b->N); // FlatFilter::replace, FlatFilter.cpp:39-46
+        int const slot = dst_slots ? (int)dst_slots[k] : g.k((uint32_t)b->N); // FlatFilter::replace, FlatFilter.cpp:39-46
         if (g.overrun()) return ctx->err = "replay stream underrun in reinvigoration", FBA_ERR_RNG_UNDERRUN;
         BreedJob job{counts_donor, fc_sid[counts_donor], id, slot, st[struct_donor]};
         last_writer[slot] = job;
-        sid[slot]         = id;
-        st[slot]          = job.state;
+        order.push_back(slot);
+        if (dst == b)
+        { // a later breed may draw this slot as its structure donor
+            sid[slot] = id;
+            st[slot]  = job.state;
+        }
     }
     g.commit();
     {
@@ -1958,7 +2012,6 @@ extern "C" int fba_belief_reinvigorate(fba_belief* b, fba_belief* fc, int64_t am
     if ((long long)jobs.size() > b->jobs_cap)
     {
         cudaFree(b->d_jobs);
-    cudaFree(b->rs_src), cudaFree(b->rs_state), cudaFree(b->rs_rec), cudaFree(b->rs_flag), cudaFree(b->rs_pos), cudaFree(b->rs_tiles);
         b->d_jobs   = nullptr;
         b->jobs_cap = 0;
         long long const cap = (long long)jobs.size() * 2 + 64;
@@ -1968,10 +2021,24 @@ extern "C" int fba_belief_reinvigorate(fba_belief* b, fba_belief* fc, int64_t am
     BreedJob* const d_jobs = b->d_jobs;
     CU(ctx, cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(BreedJob), cudaMemcpyHostToDevice, ctx->stream));
     // structures may have been added: the node table pointer is unchanged, its contents were copied
-    LAUNCH(ctx, k_breed, (int)jobs.size(), kThreads, D, fc->counts[fc->cur], fc->stride, b->counts[b->cur],
-           b->stride, b->state[b->cur], b->sid[b->cur], d_jobs);
+    LAUNCH(ctx, k_breed, (int)jobs.size(), kThreads, D, fc->counts[fc->cur], fc->stride, dst->counts[dst->cur],
+           dst->stride, dst->state[dst->cur], dst->sid[dst->cur], d_jobs);
     CU(ctx, cudaStreamSynchronize(ctx->stream));
-    return FBA_OK;
+    return host_replace_weights(dst, order);
+}
+
+extern "C" int fba_belief_reinvigorate(fba_belief* b, fba_belief* fc, int64_t amount, int32_t mutate_kind,
+                                       fba_rng* rng)
+{
+    if (!b || !fc || !rng) return FBA_ERR_INVALID;
+    return breed_core(b, nullptr, b, fc, amount, mutate_kind, rng);
+}
+
+extern "C" int fba_belief_breed_into(fba_belief* dst, const int64_t* dst_slot, int64_t n, fba_belief* structure_donors,
+                                     fba_belief* fully_connected, int32_t mutate_kind, fba_rng* rng)
+{
+    if (!dst || !dst_slot || !structure_donors || !fully_connected || !rng) return FBA_ERR_INVALID;
+    return breed_core(dst, dst_slot, structure_donors, fully_connected, n, mutate_kind, rng);
 }
 
 // grow-only device staging of n elements of T
@@ -2313,6 +2380,154 @@ extern "C" int fba_belief_assign_from(fba_belief* dst, int64_t first, fba_belief
            dst->stride, src->state[src->cur], dst->state[dst->cur] + first, src->sid[src->cur], dst->sid[dst->cur] + first,
            dst->m->d_sizes, (double*)nullptr, 0.0, dst->anc, (long long)n, 0);
     CU(ctx, cudaStreamSynchronize(ctx->stream)); // idx is a host temporary
+    return FBA_OK;
+}
+
+// ---- single particles between the filters of the composite beliefs -------------------------------------
+
+static int replace_core(fba_belief* dst, const std::vector<int>& dst_index, fba_belief* src,
+                        const std::vector<int>& src_index)
+{
+    fba_ctx* ctx = dst->ctx;
+    size_t const n = dst_index.size();
+    if (n == 0) return FBA_OK;
+    std::map<int, int> last; // destination slot -> source of its last writer
+    for (size_t j = 0; j < n; ++j) last[dst_index[j]] = src_index[j];
+    std::vector<int2> jobs;
+    jobs.reserve(last.size());
+    for (auto const& kv : last) jobs.push_back(make_int2(kv.second, kv.first));
+    DevTmp<int2> d_jobs;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMalloc(&d_jobs.p, jobs.size() * sizeof(int2)));
+    CU(ctx, cudaMemcpyAsync(d_jobs.p, jobs.data(), jobs.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, k_replace_from, stream_grid(ctx, (long long)jobs.size()), kThreads, src->counts[src->cur],
+           dst->counts[dst->cur], dst->stride, src->state[src->cur], dst->state[dst->cur], src->sid[src->cur],
+           dst->sid[dst->cur], dst->m->d_sizes, (const int2*)d_jobs.p, (long long)jobs.size());
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return host_replace_weights(dst, dst_index);
+}
+
+extern "C" int fba_belief_replace_from(fba_belief* dst, const int64_t* dst_index, fba_belief* src,
+                                       const int64_t* src_index, int64_t n)
+{
+    if (!dst || !src || n < 0 || (n && (!dst_index || !src_index))) return FBA_ERR_INVALID;
+    fba_ctx* ctx = dst->ctx;
+    REQUIRE(ctx, src != dst && src->ctx == ctx && src->m == dst->m && src->stride == dst->stride
+                     && dst->delta_cap == 0 && src->delta_cap == 0,
+            "replace_from: two different beliefs of one context, model and stride (dense storage)");
+    std::vector<int> di((size_t)n), si((size_t)n);
+    for (int64_t j = 0; j < n; ++j)
+    {
+        REQUIRE(ctx, src_index[j] >= 0 && src_index[j] < src->N, "replace_from: source index out of range");
+        REQUIRE(ctx, dst_index[j] >= 0 && dst_index[j] < dst->N, "replace_from: destination index out of range");
+        di[(size_t)j] = (int)dst_index[j], si[(size_t)j] = (int)src_index[j];
+    }
+    return replace_core(dst, di, src, si);
+}
+
+// CheatingReinvigoration::cheat (prototypes/CheatingReinvigoration.cpp:136-147)
+extern "C" int fba_belief_cheat(fba_belief* belief, fba_belief* correct, int64_t amount, fba_rng* rng)
+{
+    if (!belief || !correct || !rng || amount < 0) return FBA_ERR_INVALID;
+    fba_ctx* ctx = belief->ctx;
+    REQUIRE(ctx, belief != correct && correct->ctx == ctx && correct->m == belief->m
+                     && correct->stride == belief->stride && belief->delta_cap == 0 && correct->delta_cap == 0,
+            "cheat: two different beliefs of one context, model and stride (dense storage)");
+    REQUIRE(ctx, belief->weighted && !correct->weighted, "cheat: a weighted belief and a flat correct-structure filter");
+    std::vector<int> di, si;
+    HostDraws g(rng);
+    for (int64_t k = 0; k < amount; ++k)
+    { // _belief.replace(rnd::slowRandomInt(0, size), copyState(_correct_structured_belief.sample()), ...):
+      // g++ evaluates the arguments right to left
+        si.push_back(g.k((uint32_t)correct->N));
+        di.push_back(g.slow((int)belief->N));
+        if (g.overrun()) return ctx->err = "replay stream underrun in cheat", FBA_ERR_RNG_UNDERRUN;
+    }
+    g.commit();
+    return replace_core(belief, di, correct, si);
+}
+
+// WeightedFilter::leastLikely (src/beliefs/particle_filters/WeightedFilter.cpp:206-243), with the same
+// container (std::priority_queue over (weight, index) pairs compared by weight) driven the same way, so
+// that ties come out in the reference's order: seeded with the first n particles, then EVERY particle
+// (the first n again) replaces the current largest if its weight is strictly smaller.
+extern "C" int fba_belief_least_likely(fba_belief* b, int64_t n, int64_t* index)
+{
+    if (!b || !index || n < 0) return FBA_ERR_INVALID;
+    fba_ctx* ctx = b->ctx;
+    REQUIRE(ctx, b->weighted, "least_likely: weighted beliefs only");
+    REQUIRE(ctx, n < b->N, "least_likely: n must be smaller than the belief");
+    if (n == 0) return FBA_OK;
+    std::vector<double> w((size_t)b->N);
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpyAsync(w.data(), b->w, (size_t)b->N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    typedef std::pair<double, int> El;
+    struct Less
+    {
+        bool operator()(El l, El r) const { return l.first < r.first; }
+    };
+    std::priority_queue<El, std::vector<El>, Less> q;
+    for (int64_t i = 0; i < n; ++i) q.push({w[(size_t)i], (int)i});
+    for (int64_t i = 0; i < b->N; ++i)
+        if (w[(size_t)i] < q.top().first)
+        {
+            q.pop();
+            q.push({w[(size_t)i], (int)i});
+        }
+    for (int64_t i = 0; i < n; ++i)
+    {
+        index[i] = q.top().second;
+        q.pop();
+    }
+    return FBA_OK;
+}
+
+// StructureIncubatorSampling::reinvigorateBelief (factored/StructureIncubatorSampling.cpp:155-187): every
+// shadow particle whose normalised weight exceeds the threshold is copied over a uniformly drawn particle
+// of the flat belief (FlatFilter::replace, one draw each, in particle order) and its weight set to zero;
+// if any moved, the shadow weights are normalised (WeightedFilter::normalize, sequential sums).
+extern "C" int fba_belief_promote(fba_belief* shadow, fba_belief* belief, double threshold, fba_rng* rng,
+                                  int64_t* n_promoted)
+{
+    if (!shadow || !belief || !rng) return FBA_ERR_INVALID;
+    fba_ctx* ctx = shadow->ctx;
+    REQUIRE(ctx, belief != shadow && belief->ctx == ctx && belief->m == shadow->m && belief->stride == shadow->stride
+                     && belief->delta_cap == 0 && shadow->delta_cap == 0,
+            "promote: two different beliefs of one context, model and stride (dense storage)");
+    REQUIRE(ctx, shadow->weighted && !belief->weighted, "promote: a weighted shadow belief and a flat belief");
+    std::vector<double> w((size_t)shadow->N);
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpyAsync(w.data(), shadow->w, (size_t)shadow->N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<int> di, si;
+    HostDraws g(rng);
+    for (int64_t i = 0; i < shadow->N; ++i)
+        if (w[(size_t)i] / shadow->total_weight > threshold) // WeightedFilter::normalizedWeight
+        {
+            si.push_back((int)i);
+            di.push_back(g.k((uint32_t)belief->N));
+            if (g.overrun()) return ctx->err = "replay stream underrun in promote", FBA_ERR_RNG_UNDERRUN;
+            w[(size_t)i] = 0.0;
+        }
+    g.commit();
+    if (n_promoted) *n_promoted = (int64_t)si.size();
+    if (si.empty()) return FBA_OK;
+    int rc = replace_core(belief, di, shadow, si);
+    if (rc) return rc;
+    volatile double total = 0.0, acc = 0.0; // normalize(): total, then divide and re-accumulate, in order
+    for (double x : w) total = total + x;
+    REQUIRE(ctx, total > 0.0, "promote: every shadow particle passed the threshold (the reference divides by zero here; "
+                              "choose a threshold above 1 / size)");
+    for (double& x : w)
+    {
+        x   = x / total;
+        acc = acc + x;
+    }
+    CU(ctx, cudaMemcpyAsync(shadow->w, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    shadow->total_weight = acc;
+    shadow->suffix_valid = shadow->cdf_valid = false;
     return FBA_OK;
 }
 

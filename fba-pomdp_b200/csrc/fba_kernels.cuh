@@ -179,6 +179,33 @@ __global__ void __launch_bounds__(kThreads)
     }
 }
 
+// Scattered particle copies between two beliefs: job j copies src[jobs[j].x] into dst[jobs[j].y] (count
+// block, domain state, structure id), one warp per job. How single particles move between the filters of
+// the composite beliefs (CheatingReinvigoration.cpp:136-147, StructureIncubatorSampling.cpp:155-187);
+// the host has already reduced jobs with the same destination to the last one.
+__global__ void __launch_bounds__(kThreads)
+    k_replace_from(const float* __restrict__ src, float* __restrict__ dst, long long stride,
+                   const int* __restrict__ src_state, int* __restrict__ dst_state,
+                   const int* __restrict__ src_sid, int* __restrict__ dst_sid,
+                   const int* __restrict__ struct_size, const int2* __restrict__ jobs, long long n)
+{
+    int const lane        = threadIdx.x & 31;
+    long long const warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    long long const nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long j = warp0; j < n; j += nwarp)
+    {
+        int2 const job  = jobs[j];
+        int const id    = src_sid[job.x];
+        int const n_vec = (int)((stride + 3) >> 2); // the whole block: padding beyond the structure stays zero
+        warp_copy_block<4>(src + (long long)job.x * stride, dst + (long long)job.y * stride, n_vec, lane);
+        if (lane == 0)
+        {
+            dst_sid[job.y]   = id;
+            dst_state[job.y] = src_state[job.x];
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // The same gather through the TMA engine (cp.async.bulk, SASS: UBLKCP): one CTA per SM; its thread 0
 // drives a ring of shared-memory stages — bulk load global -> shared (completion on an mbarrier),

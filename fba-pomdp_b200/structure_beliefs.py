@@ -1,0 +1,177 @@
+"""Host-side mirror of the reference's COMPOSITE structure beliefs over the C ABI: the
+classes whose update is a fixed sequence of the primitives of beliefs.py on two or three particle filters.
+Same names, members and call order as the reference (paths relative to samkatt/fba-pomdp):
+
+  CheatingReinvigoration      src/beliefs/bayes-adaptive/prototypes/CheatingReinvigoration.cpp:27-147
+  StructureIncubatorSampling  src/beliefs/bayes-adaptive/factored/StructureIncubatorSampling.cpp:20-187
+
+Every method ends in CUDA calls on the filters' fba_belief handles; there is no CPU path. One Rng is
+passed per call and consumed by the primitives in the reference's draw order, so that in REPLAY mode a
+whole updateEstimation reproduces the reference's bit for bit (tests/test_cuda_composite.py).
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import capi
+from .beliefs import BAImportanceSampling, BARejectionSampling, _check
+from .capi import FbaError, ptr
+
+
+def _flat(sim, n, particles, stride):
+    b = BARejectionSampling(n)
+    b.initiate(sim, struct_id=particles["struct_id"], counts=particles["counts"], state=particles["state"],
+               stride=stride)
+    return b
+
+
+def _weighted(sim, n, particles, stride):
+    b = BAImportanceSampling(n)
+    b.initiate(sim, struct_id=particles["struct_id"], counts=particles["counts"], state=particles["state"],
+               stride=stride)
+    return b
+
+
+def replace_from(dst, dst_index, src, src_index):
+    """src[src_index[j]] -> dst[dst_index[j]], in order (WeightedFilter::replace / FlatFilter slot writes)."""
+    di = np.ascontiguousarray(dst_index, np.int64)
+    si = np.ascontiguousarray(src_index, np.int64)
+    _check(dst.ctx.h, dst.L.fba_belief_replace_from(dst.h, ptr(di), src.h, ptr(si), len(di)))
+
+
+class CheatingReinvigoration:
+    """beliefs::bayes_adaptive::prototypes::CheatingReinvigoration: a weighted belief tracked by importance
+    sampling next to a flat filter of correctly structured particles tracked by rejection sampling; when the
+    accumulated likelihood drops below the threshold, `cheat_amount` particles of the latter are copied
+    into the former."""
+
+    def __init__(self, size, cheat_amount, resample_threshold):
+        if size < 1 or cheat_amount < 1:  # CheatingReinvigoration.cpp:34-38
+            raise FbaError(capi.ERR_INVALID, "CheatingReinvigoration::cannot initiate belief of size < 1 ("
+                           + str(size) + "), or resample size of < 1 (" + str(cheat_amount) + ")")
+        if resample_threshold >= 0:  # :40-44
+            raise FbaError(capi.ERR_INVALID, "CheatingReinvigoration::cannot initiate with resample_threshold >= 0 (is:"
+                           + str(resample_threshold) + ")")
+        self._size, self._cheat_amount, self._resample_threshold = size, cheat_amount, resample_threshold
+        self._belief = self._correct_structured_belief = None
+        self._likelihood = 1.0
+        self.cheats = 0
+
+    def initiate(self, simulator, *, belief, correct_structured, stride):
+        """belief / correct_structured: dicts (struct_id, counts, state) of what sampleStartState /
+        sampleCorrectGraphState produced on the host (:68-93)."""
+        self._correct_structured_belief = _flat(simulator, self._size, correct_structured, stride)
+        self._belief = _weighted(simulator, self._size, belief, stride)
+        self._likelihood = 1.0
+
+    def updateEstimation(self, a, o, rng):
+        """:107-134"""
+        self._correct_structured_belief.updateEstimation(a, o, rng)
+        l = self._belief.update(a, o, rng)
+        self._belief.resample(rng)
+        self._likelihood *= l
+        if (math.log(self._likelihood) if self._likelihood > 0 else -math.inf) < self._resample_threshold:
+            self.cheat(rng)
+            self._likelihood = 1.0
+
+    def cheat(self, rng):
+        """:136-147"""
+        b = self._belief
+        _check(b.ctx.h, b.L.fba_belief_cheat(b.h, self._correct_structured_belief.h, self._cheat_amount,
+                                             C.byref(rng)))
+        self.cheats += 1
+
+    def sample(self, rng):
+        return self._belief.sample(rng)
+
+    def resetDomainStateDistribution(self, rng):
+        """:50-66: resetDomainState on every particle of the cheating filter, then of the belief (its
+        weights and order stay as they are)."""
+        for b in (self._correct_structured_belief, self._belief):
+            _check(b.ctx.h, b.L.fba_belief_redraw_domain_states(b.h, C.byref(rng)))
+
+    def free(self, _simulator=None):
+        for b in (self._belief, self._correct_structured_belief):
+            if b is not None:
+                b.free()
+        self._belief = self._correct_structured_belief = None
+
+
+class StructureIncubatorSampling:
+    """beliefs::bayes_adaptive::factored::StructureIncubatorSampling: the belief and a fully connected
+    belief (flat, rejection sampling) plus a weighted SHADOW belief of bred particles (importance
+    sampling) whose heavy particles are promoted into the belief."""
+
+    def __init__(self, size, reinvigor_amount, threshold, mutate_kind):
+        if size < 1 or reinvigor_amount < 1:  # StructureIncubatorSampling.cpp:29-34
+            raise FbaError(capi.ERR_INVALID,
+                           "StructureIncubatorSampling::Cannot initiate Incubator belief update with size < 1 ("
+                           + str(size) + ") or resample size < 1 (" + str(reinvigor_amount) + ")")
+        if threshold <= 0 or threshold > 1:  # :36-40
+            raise FbaError(capi.ERR_INVALID, "StructureIncubatorSampling::must initiate with 1 < threshold <= 0 (is:"
+                           + str(threshold) + ")")
+        self._size, self._shadow_reinvigor_amount, self._real_reinvigor_threshold = size, reinvigor_amount, threshold
+        self._mutate = mutate_kind
+        self._belief = self._fully_connected_belief = self._shadow_belief = None
+        self.promoted = 0
+
+    def initiate(self, simulator, *, belief, fully_connected, stride, rng=None, shadow=None):
+        """belief / fully_connected: host particles as above (:65-73). The shadow belief is bred from them
+        (:74-80) with `rng`, or — to start from the reference's own shadow particles — uploaded as is."""
+        self._belief = _flat(simulator, self._size, belief, stride)
+        self._fully_connected_belief = _flat(simulator, self._size, fully_connected, stride)
+        if shadow is not None:
+            self._shadow_belief = _weighted(simulator, self._size, shadow, stride)
+        else:
+            self._shadow_belief = _weighted(simulator, self._size, belief, stride)  # placeholders, all overwritten
+            self._breed_into(np.arange(self._size), rng)
+            w = np.full(self._size, 1.0 / self._size)  # add(s, 1 / size) x size
+            b = self._shadow_belief
+            _check(b.ctx.h, b.L.fba_belief_upload(b.h, 0, self._size, None, None, None, ptr(w)))
+
+    def _breed_into(self, slots, rng):
+        s = np.ascontiguousarray(slots, np.int64)
+        b = self._shadow_belief
+        _check(b.ctx.h, b.L.fba_belief_breed_into(b.h, ptr(s), len(s), self._belief.h, self._fully_connected_belief.h,
+                                                  self._mutate, C.byref(rng)))
+
+    def reinvigorateBelief(self, rng):
+        """:155-187"""
+        n = C.c_int64(0)
+        b = self._shadow_belief
+        _check(b.ctx.h, b.L.fba_belief_promote(b.h, self._belief.h, self._real_reinvigor_threshold, C.byref(rng),
+                                               C.byref(n)))
+        self.promoted += n.value
+        return n.value
+
+    def reinvigorateShadowBelief(self, rng):
+        """:139-153"""
+        idx = np.zeros(self._shadow_reinvigor_amount, np.int64)
+        b = self._shadow_belief
+        _check(b.ctx.h, b.L.fba_belief_least_likely(b.h, len(idx), ptr(idx)))
+        self._breed_into(idx, rng)
+        return idx
+
+    def updateEstimation(self, a, o, rng):
+        """:107-137"""
+        self.reinvigorateBelief(rng)
+        self.reinvigorateShadowBelief(rng)
+        self._belief.updateEstimation(a, o, rng)
+        self._fully_connected_belief.updateEstimation(a, o, rng)
+        self._shadow_belief.update(a, o, rng)
+        self._shadow_belief.resample(rng)
+
+    def sample(self, rng):
+        return self._belief.sample(rng)
+
+    def resetDomainStateDistribution(self, rng):
+        """:46-61: resetDomainState on every particle of the three filters, in this order"""
+        for b in (self._belief, self._fully_connected_belief, self._shadow_belief):
+            _check(b.ctx.h, b.L.fba_belief_redraw_domain_states(b.h, C.byref(rng)))
+
+    def free(self, _simulator=None):
+        for b in (self._belief, self._fully_connected_belief, self._shadow_belief):
+            if b is not None:
+                b.free()
+        self._belief = self._fully_connected_belief = self._shadow_belief = None

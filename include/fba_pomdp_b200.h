@@ -31,7 +31,7 @@ extern "C" {
 
 #define FBA_MAX_FEATURES 16
 /* bumped whenever a struct below changes layout; compare with fba_abi_version() after loading */
-#define FBA_ABI_VERSION 11
+#define FBA_ABI_VERSION 12
 
 typedef struct fba_ctx fba_ctx;
 typedef struct fba_model fba_model;
@@ -214,6 +214,11 @@ int fba_belief_update_estimation(fba_belief* b, int32_t action, int32_t observat
 /* BABelief::resetDomainStateDistribution (src/beliefs/bayes-adaptive/BABelief.hpp:30):
  * weighted: BAImportanceSampling.cpp:90-111; flat: BARejectionSampling.cpp:47-58 */
 int fba_belief_reset_domain_states(fba_belief* b, fba_rng* rng);
+/* BAPOMDP::resetDomainState (src/bayes-adaptive/models/table/BAPOMDP.cpp:69-77) on every particle where it
+ * is: a fresh domain start state each, counts, weights and order untouched — the reset of the beliefs
+ * that keep their weighted filter as it is (MHNIPS2018.cpp:132-147, CheatingReinvigoration.cpp:50-66,
+ * StructureIncubatorSampling.cpp:46-61). For a flat belief the same as fba_belief_reset_domain_states. */
+int fba_belief_redraw_domain_states(fba_belief* b, fba_rng* rng);
 /* Belief::sample (Belief.hpp:34): index of the drawn particle (use fba_belief_download to view it) */
 int fba_belief_sample(fba_belief* b, fba_rng* rng, int64_t* index);
 
@@ -339,6 +344,33 @@ int fba_belief_replay_history(fba_belief* b, int32_t n_episodes, const int32_t* 
  * beliefs share context, model and stride. How accepted proposals become the new belief
  * (MHNIPS2018.cpp:241-246). Weights are untouched. */
 int fba_belief_assign_from(fba_belief* dst, int64_t first, fba_belief* src, int64_t n, const int64_t* src_index);
+
+/* ---- single particles between the filters of the composite structure beliefs ----
+ * src[src_index[j]] -> dst[dst_index[j]] for j = 0 .. n-1 IN ORDER (a later j overwrites an earlier one on
+ * the same slot): count block, domain state, structure id. A weighted dst follows WeightedFilter::replace
+ * (src/beliefs/particle_filters/WeightedFilter.cpp:71-90): the replaced slot's weight becomes
+ * _total_weight / N and _total_weight moves by the difference, slot after slot. Two different beliefs of
+ * one context, model and stride, dense storage. */
+int fba_belief_replace_from(fba_belief* dst, const int64_t* dst_index, fba_belief* src, const int64_t* src_index,
+                            int64_t n);
+/* CheatingReinvigoration::cheat (src/beliefs/bayes-adaptive/prototypes/CheatingReinvigoration.cpp:136-147):
+ * `amount` times, a uniformly drawn particle of the flat correct-structure filter replaces a particle of the
+ * weighted belief at slot slowRandomInt(0, N) (draw order: the source first, as g++ evaluates the call). */
+int fba_belief_cheat(fba_belief* belief, fba_belief* correct, int64_t amount, fba_rng* rng);
+/* beliefs::bayes_adaptive::factored::breed (factored/ReinvigoratingRejectionSampling.cpp:24-35) n times, in
+ * order: counts donor drawn from `fully_connected`, structure donor from `structure_donors` (both flat),
+ * the domain's mutate, BABNModel::marginalizeOut; the j-th bred particle replaces particle dst_slot[j] of
+ * `dst` (weights as fba_belief_replace_from). What StructureIncubatorSampling does to its shadow belief
+ * (factored/StructureIncubatorSampling.cpp:74-80,139-153). */
+int fba_belief_breed_into(fba_belief* dst, const int64_t* dst_slot, int64_t n, fba_belief* structure_donors,
+                          fba_belief* fully_connected, int32_t mutate_kind, fba_rng* rng);
+/* WeightedFilter::leastLikely(n) (WeightedFilter.cpp:206-243): index[0..n) in the reference's order (the
+ * same std::priority_queue, driven the same way, so ties resolve identically). n < N. */
+int fba_belief_least_likely(fba_belief* b, int64_t n, int64_t* index);
+/* StructureIncubatorSampling::reinvigorateBelief (factored/StructureIncubatorSampling.cpp:155-187): shadow
+ * particles whose normalised weight exceeds `threshold` are copied over uniformly drawn particles of the
+ * flat `belief` (one draw each, particle order), their weights zeroed and the shadow weights normalised. */
+int fba_belief_promote(fba_belief* shadow, fba_belief* belief, double threshold, fba_rng* rng, int64_t* n_promoted);
 
 /* ---- POMCP with the search tree on the device --------------------------------
  * planners::RBAPOUCT::selectAction (src/planners/bayes-adaptive/RBAPOUCT.cpp:67-153) as waves of

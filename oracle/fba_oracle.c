@@ -755,8 +755,19 @@ void orc_mutate_structure(const orc_model* m, uint32_t* tp, uint32_t* op, int mu
     }
 }
 
-int orc_reinvigorate(const orc_model* m, orc_structs* st, orc_belief* belief, const orc_belief* fc,
-                     int64_t amount, int mutate_kind, orc_rng* g)
+void orc_replace_weight(orc_belief* b, int64_t slot)
+{
+    /* WeightedFilter::replace(i, s, dealloc) (WeightedFilter.cpp:71-90): the new particle weighs
+     * _total_weight / size and _total_weight moves by the difference */
+    if (!b->w) return;
+    double const w    = b->total_weight / (double)b->N;
+    double const diff = w - b->w[slot];
+    b->w[slot]        = w;
+    b->total_weight += diff;
+}
+
+int orc_breed_into(const orc_model* m, orc_structs* st, orc_belief* dst, const int64_t* dst_slots,
+                   orc_belief* belief, const orc_belief* fc, int64_t amount, int mutate_kind, orc_rng* g)
 {
     /* ReinvigoratingRejectionSampling.cpp:121-131 + breed (:24-35). Draw order (g++ -std=c++11
      * evaluates the call arguments right to left, SURVEY.md §7 hard part 3d):
@@ -765,7 +776,7 @@ int orc_reinvigorate(const orc_model* m, orc_structs* st, orc_belief* belief, co
     uint32_t tp[ORC_MAXF * 64], op[ORC_MAXF * 64];
     int64_t off_src[64 * 2 * ORC_MAXF], off_dst[64 * 2 * ORC_MAXF];
     if (m->A > 64) return -2;
-    float* fresh = (float*)malloc(sizeof(float) * belief->stride);
+    float* fresh = (float*)malloc(sizeof(float) * dst->stride);
 
     for (int64_t k = 0; k < amount; ++k)
     {
@@ -782,12 +793,12 @@ int orc_reinvigorate(const orc_model* m, orc_structs* st, orc_belief* belief, co
         const uint32_t* sop = opar_of(m, st, fc->struct_id[counts_donor]);
         orc_struct_offsets(m, stp, sop, off_src);
         int64_t const sz = orc_struct_offsets(m, tp, op, off_dst);
-        if (sz > belief->stride)
+        if (sz > dst->stride)
         {
             free(fresh);
             return -3;
         }
-        memset(fresh, 0, sizeof(float) * belief->stride);
+        memset(fresh, 0, sizeof(float) * dst->stride);
         const float* src = fc->counts + counts_donor * fc->stride;
         for (int a = 0; a < m->A; ++a)
         {
@@ -806,14 +817,130 @@ int orc_reinvigorate(const orc_model* m, orc_structs* st, orc_belief* belief, co
         }
         int32_t const dom_state = belief->state[struct_donor]; /* breed: structure donor's state */
 
-        /* FlatFilter::replace (FlatFilter.cpp:39-46): uniformly random slot */
-        int64_t const slot = orc_uniform_int(g, (uint32_t)belief->N);
-        memcpy(belief->counts + slot * belief->stride, fresh, sizeof(float) * belief->stride);
-        belief->state[slot]     = dom_state;
-        belief->struct_id[slot] = id;
+        /* FlatFilter::replace (FlatFilter.cpp:39-46): uniformly random slot; or the caller's slot
+         * (StructureIncubatorSampling.cpp:74-80,139-153: WeightedFilter::add / replace) */
+        int64_t const slot = dst_slots ? dst_slots[k] : orc_uniform_int(g, (uint32_t)dst->N);
+        memcpy(dst->counts + slot * dst->stride, fresh, sizeof(float) * dst->stride);
+        dst->state[slot]     = dom_state;
+        dst->struct_id[slot] = id;
+        orc_replace_weight(dst, slot);
     }
     free(fresh);
     return 0;
+}
+
+int orc_reinvigorate(const orc_model* m, orc_structs* st, orc_belief* belief, const orc_belief* fc,
+                     int64_t amount, int mutate_kind, orc_rng* g)
+{
+    /* ReinvigoratingRejectionSampling::reinvigorateParticles (…RejectionSampling.cpp:121-131) */
+    return orc_breed_into(m, st, belief, NULL, belief, fc, amount, mutate_kind, g);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* the composite structure beliefs' own steps                                                  */
+/* ------------------------------------------------------------------------------------------ */
+
+void orc_cheat(orc_belief* belief, const orc_belief* correct, int64_t amount, orc_rng* g)
+{
+    /* CheatingReinvigoration::cheat (prototypes/CheatingReinvigoration.cpp:136-147):
+     * _belief.replace(rnd::slowRandomInt(0, size), copyState(_correct_structured_belief.sample()), ..)
+     * — g++ evaluates the arguments right to left: the source particle is drawn first */
+    for (int64_t k = 0; k < amount; ++k)
+    {
+        int64_t const src  = orc_uniform_int(g, (uint32_t)correct->N);
+        int64_t const slot = slow_random_int(g, (int)belief->N);
+        copy_particle(correct, src, belief, slot);
+        orc_replace_weight(belief, slot);
+    }
+}
+
+/* std::priority_queue<pair<double,int>, vector, Less-on-first> as libstdc++ implements it
+ * (bits/stl_heap.h: __push_heap, __adjust_heap, __pop_heap), because WeightedFilter::leastLikely's
+ * result order on equal weights is whatever that container does */
+typedef struct { double w; int i; } heap_el;
+static void heap_push(heap_el* h, int64_t* n, heap_el v)
+{
+    int64_t hole = (*n)++;
+    int64_t parent = (hole - 1) / 2;
+    while (hole > 0 && h[parent].w < v.w)
+    {
+        h[hole] = h[parent];
+        hole    = parent;
+        parent  = (hole - 1) / 2;
+    }
+    h[hole] = v;
+}
+static heap_el heap_pop(heap_el* h, int64_t* n)
+{
+    /* __pop_heap: the last element's value is sifted in from the root after the top moved out */
+    heap_el const top = h[0];
+    int64_t const len = --(*n);
+    if (len == 0) return top;
+    heap_el const v = h[len];
+    /* __adjust_heap(first, hole = 0, len, v) */
+    int64_t hole = 0, child = 0;
+    while (child < (len - 1) / 2)
+    {
+        child = 2 * (child + 1);
+        if (h[child].w < h[child - 1].w) child--;
+        h[hole] = h[child];
+        hole    = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2)
+    {
+        child   = 2 * (child + 1);
+        h[hole] = h[child - 1];
+        hole    = child - 1;
+    }
+    /* __push_heap(first, hole, top = 0, v) */
+    int64_t parent = (hole - 1) / 2;
+    while (hole > 0 && h[parent].w < v.w)
+    {
+        h[hole] = h[parent];
+        hole    = parent;
+        parent  = (hole - 1) / 2;
+    }
+    h[hole] = v;
+    return top;
+}
+
+void orc_least_likely(const double* w, int64_t n_particles, int64_t n, int64_t* out)
+{
+    /* WeightedFilter::leastLikely (WeightedFilter.cpp:206-243): the queue is seeded with the first n
+     * particles; then EVERY particle (the first n again) replaces the current largest if it is
+     * strictly lighter; the n survivors are popped largest first */
+    heap_el* h = (heap_el*)malloc(sizeof(heap_el) * (size_t)(n + 1));
+    int64_t len = 0;
+    for (int64_t i = 0; i < n; ++i) heap_push(h, &len, (heap_el){w[i], (int)i});
+    for (int64_t i = 0; i < n_particles; ++i)
+        if (w[i] < h[0].w)
+        {
+            heap_pop(h, &len);
+            heap_push(h, &len, (heap_el){w[i], (int)i});
+        }
+    for (int64_t i = 0; i < n; ++i) out[i] = heap_pop(h, &len).i;
+    free(h);
+}
+
+int64_t orc_promote(orc_belief* shadow, orc_belief* belief, double threshold, orc_rng* g)
+{
+    /* StructureIncubatorSampling::reinvigorateBelief (factored/StructureIncubatorSampling.cpp:155-187) */
+    int64_t moved = 0;
+    for (int64_t i = 0; i < shadow->N; ++i)
+        if (shadow->w[i] / shadow->total_weight > threshold) /* WeightedFilter::normalizedWeight */
+        {
+            int64_t const slot = orc_uniform_int(g, (uint32_t)belief->N); /* FlatFilter::replace */
+            copy_particle(shadow, i, belief, slot);
+            shadow->w[i] = 0;
+            ++moved;
+        }
+    if (moved)
+    { /* WeightedFilter::normalize() (WeightedFilter.cpp:118-143) */
+        double total = 0;
+        for (int64_t i = 0; i < shadow->N; ++i) total += shadow->w[i];
+        shadow->total_weight = orc_normalize(shadow->w, shadow->N, total);
+    }
+    return moved;
 }
 
 /* ------------------------------------------------------------------------------------------ */

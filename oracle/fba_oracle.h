@@ -175,6 +175,19 @@ void orc_marginalize_node(const orc_model* m, uint32_t src_par, const float* src
 int orc_reinvigorate(const orc_model* m, orc_structs* st, orc_belief* belief, const orc_belief* fc,
                      int64_t amount, int mutate_kind, orc_rng* g);
 
+/* `amount` x breed (factored/ReinvigoratingRejectionSampling.cpp:24-35): structure donor from `belief`,
+ * counts donor from `fc`; the k-th bred particle goes to dst_slots[k] of `dst` (a weighted dst follows
+ * WeightedFilter::replace), or with dst_slots == NULL to a uniformly drawn slot */
+int orc_breed_into(const orc_model* m, orc_structs* st, orc_belief* dst, const int64_t* dst_slots,
+                   orc_belief* belief, const orc_belief* fc, int64_t amount, int mutate_kind, orc_rng* g);
+void orc_replace_weight(orc_belief* b, int64_t slot);
+/* CheatingReinvigoration::cheat (prototypes/CheatingReinvigoration.cpp:136-147) */
+void orc_cheat(orc_belief* belief, const orc_belief* correct, int64_t amount, orc_rng* g);
+/* WeightedFilter::leastLikely (WeightedFilter.cpp:206-243), ties in libstdc++'s priority_queue order */
+void orc_least_likely(const double* w, int64_t n_particles, int64_t n, int64_t* out);
+/* StructureIncubatorSampling::reinvigorateBelief (factored/StructureIncubatorSampling.cpp:155-187) */
+int64_t orc_promote(orc_belief* shadow, orc_belief* belief, double threshold, orc_rng* g);
+
 /* RBAPOUCT::rollout (RBAPOUCT.cpp:295-323) on a read-only particle (KeepCounts) */
 double orc_rollout(const orc_model* m, const uint32_t* t_par, const uint32_t* o_par,
                    const float* counts, int start_state, int depth, double discount, orc_rng* g);

@@ -109,6 +109,13 @@ def lib():
         L.orc_reinvigorate.argtypes = [vp, vp, vp, vp, i64, C.c_int, vp]
         L.orc_rollout.restype = dbl
         L.orc_rollout.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, dbl, vp]
+        L.orc_breed_into.restype = C.c_int
+        L.orc_breed_into.argtypes = [vp, vp, vp, vp, vp, vp, i64, C.c_int, vp]
+        L.orc_replace_weight.argtypes = [vp, i64]
+        L.orc_cheat.argtypes = [vp, vp, i64, vp]
+        L.orc_least_likely.argtypes = [vp, i64, i64, vp]
+        L.orc_promote.restype = i64
+        L.orc_promote.argtypes = [vp, vp, dbl, vp]
         _lib = L
     return _lib
 
@@ -383,6 +390,30 @@ def reinvigorate(model, structs, belief, fc, amount, mutate_kind, rng):
                                 mutate_kind, rng.ref())
     if rc:
         raise RuntimeError("orc_reinvigorate failed: %d" % rc)
+
+
+def breed_into(model, structs, dst, dst_slots, belief, fc, mutate_kind, rng):
+    """len(dst_slots) x breed into the given slots of dst (structure donors from belief, counts from fc)"""
+    s = np.ascontiguousarray(dst_slots, np.int64)
+    rc = lib().orc_breed_into(model.ref(), structs.ref(), dst.ref(), _p(s), belief.ref(), fc.ref(), len(s),
+                              mutate_kind, rng.ref())
+    if rc:
+        raise RuntimeError("orc_breed_into failed: %d" % rc)
+
+
+def cheat(belief, correct, amount, rng):
+    lib().orc_cheat(belief.ref(), correct.ref(), amount, rng.ref())
+
+
+def least_likely(w, n):
+    w = np.ascontiguousarray(w, np.float64)
+    out = np.zeros(n, np.int64)
+    lib().orc_least_likely(_p(w), len(w), n, _p(out))
+    return out
+
+
+def promote(shadow, belief, threshold, rng):
+    return lib().orc_promote(shadow.ref(), belief.ref(), threshold, rng.ref())
 
 
 def rollout(model, t_par, o_par, counts, start_state, depth, discount, rng):

@@ -9,7 +9,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_ref", "libfba_ref.so")
 
-F_IS, F_RS, F_REINV, F_REINV_FC = 0, 1, 2, 3
+F_IS, F_RS, F_REINV, F_REINV_FC, F_MH = 0, 1, 2, 3, 4
+F_CHEAT, F_CHEAT_CORRECT, F_INC, F_INC_FC, F_INC_SHADOW, F_GIBBS, F_NESTED = 5, 6, 7, 8, 9, 10, 11
 
 
 def available():
@@ -266,6 +267,50 @@ class Ref:
         if f(self.h, n, n_ref, C.byref(sec), C.byref(hs), _p(cs), _p(ci), _p(rs), _p(ri)):
             raise RuntimeError(self.L.ref_error(self.h).decode())
         return dict(seconds=sec.value, host_samples=hs.value, cuda_state=cs, cuda_sid=ci, ref_state=rs, ref_sid=ri)
+
+    # ---- composite structure beliefs (CheatingReinvigoration, StructureIncubatorSampling, MHwithinGibbs, NestedBelief)
+    def composite_init(self, kind, n, amount, threshold):
+        f = self.L.ref_composite_init
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_int, C.c_long, C.c_long, C.c_double]
+        if f(self.h, kind, n, amount, threshold):
+            raise RuntimeError("reference: " + self.L.ref_error(self.h).decode())
+
+    def composite_update(self, kind, a, o):
+        self.L.ref_composite_update.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        self.L.ref_composite_update(self.h, kind, a, o)
+
+    def composite_reset(self, kind):
+        self.L.ref_composite_reset.argtypes = [C.c_void_p, C.c_int]
+        self.L.ref_composite_reset(self.h, kind)
+
+    def weights(self, filt):
+        """(weights, _total_weight) of a weighted filter"""
+        self.L.ref_filter_weights.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        w = np.zeros(self.size(filt), np.float64)
+        tot = np.zeros(1, np.float64)
+        self.L.ref_filter_weights(self.h, filt, _p(w), _p(tot))
+        return w, float(tot[0])
+
+    def cheat_likelihood(self):
+        self.L.ref_cheat_likelihood.restype = C.c_double
+        self.L.ref_cheat_likelihood.argtypes = [C.c_void_p]
+        return self.L.ref_cheat_likelihood(self.h)
+
+    def cheat_only(self):
+        self.L.ref_cheat_only.argtypes = [C.c_void_p]
+        self.L.ref_cheat_only(self.h)
+
+    def incubator_part(self, part, a=0, o=0):
+        f = self.L.ref_incubator_part
+        f.restype = C.c_double
+        f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        return f(self.h, part, a, o)
+
+    def incubator_set_shadow_weights(self, w):
+        w = np.ascontiguousarray(w, np.float64)
+        self.L.ref_incubator_set_shadow_weights.argtypes = [C.c_void_p, C.c_void_p]
+        self.L.ref_incubator_set_shadow_weights(self.h, _p(w))
 
     def plan_seconds(self, kind, n, planner, sims, reps=3):
         """Seconds per Planner::selectAction with `sims` simulations (empty history)."""

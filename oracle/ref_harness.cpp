@@ -42,7 +42,11 @@
 #include "bayes-adaptive/states/table/BAPOMDPState.hpp"
 #include "beliefs/bayes-adaptive/BAImportanceSampling.hpp"
 #include "beliefs/bayes-adaptive/BARejectionSampling.hpp"
+#include "beliefs/bayes-adaptive/NestedBelief.hpp"
 #include "beliefs/bayes-adaptive/factored/MHNIPS2018.hpp"
+#include "beliefs/bayes-adaptive/factored/MHwithinGibbs.hpp"
+#include "beliefs/bayes-adaptive/factored/StructureIncubatorSampling.hpp"
+#include "beliefs/bayes-adaptive/prototypes/CheatingReinvigoration.hpp"
 #include "beliefs/bayes-adaptive/factored/ReinvigoratingRejectionSampling.hpp"
 #include "beliefs/particle_filters/ImportanceSampler.hpp"
 #include "beliefs/particle_filters/RejectionSampling.hpp"
@@ -66,6 +70,7 @@
 #include "CudaExperiment.hpp"
 #include "CudaMH.hpp"
 #include "CudaPlanner.hpp"
+#include "CudaStructureBeliefs.hpp"
 #include "environment/Discount.hpp"
 #include "environment/Horizon.hpp"
 #include "environment/Return.hpp"
@@ -79,6 +84,10 @@ namespace {
 using FactoredPOMDP = ::bayes_adaptive::factored::FBAPOMDP;
 using ReinvRS  = ::beliefs::bayes_adaptive::factored::ReinvigoratingRejectionSampling;
 using RefMH    = ::beliefs::bayes_adaptive::factored::MHNIPS2018;
+using RefCheat = ::beliefs::bayes_adaptive::prototypes::CheatingReinvigoration;
+using RefIncub = ::beliefs::bayes_adaptive::factored::StructureIncubatorSampling;
+using RefGibbs = ::beliefs::bayes_adaptive::factored::MHwithinGibbs;
+using RefNested = ::beliefs::bayes_adaptive::NestedBelief;
 
 struct Handle
 {
@@ -92,6 +101,10 @@ struct Handle
     std::unique_ptr<beliefs::BARejectionSampling> rs_belief;
     std::unique_ptr<ReinvRS> reinv_belief;
     std::unique_ptr<RefMH> mh_belief;
+    std::unique_ptr<RefCheat> cheat_belief;
+    std::unique_ptr<RefIncub> incub_belief;
+    std::unique_ptr<RefGibbs> gibbs_belief;
+    std::unique_ptr<RefNested> nested_belief;
     std::unique_ptr<planners::RBAPOUCT> planner;
 
     std::mt19937 mark;
@@ -101,7 +114,12 @@ struct Handle
 bool g_rng_initiated = false;
 
 // which particle container a call refers to
-enum Filter { F_IS = 0, F_RS = 1, F_REINV = 2, F_REINV_FC = 3, F_MH = 4 };
+enum Filter {
+    F_IS = 0, F_RS = 1, F_REINV = 2, F_REINV_FC = 3, F_MH = 4,
+    F_CHEAT = 5, F_CHEAT_CORRECT = 6,            // CheatingReinvigoration: weighted belief, flat correct-structure filter
+    F_INC = 7, F_INC_FC = 8, F_INC_SHADOW = 9,   // StructureIncubatorSampling: belief, fully connected, weighted shadow
+    F_GIBBS = 10, F_NESTED = 11                  // MHwithinGibbs (weighted), NestedBelief's top filter (weighted)
+};
 
 BAState const* particleOf(Handle* h, int filter, long i)
 {
@@ -113,6 +131,13 @@ BAState const* particleOf(Handle* h, int filter, long i)
         case F_REINV: return h->reinv_belief->_belief.particles()[i];
         case F_REINV_FC: return h->reinv_belief->_fully_connected_belief.particles()[i];
         case F_MH: return h->mh_belief->_belief.particle(i)->particle;
+        case F_CHEAT: return h->cheat_belief->_belief.particle(i)->particle;
+        case F_CHEAT_CORRECT: return h->cheat_belief->_correct_structured_belief.particles()[i];
+        case F_INC: return h->incub_belief->_belief.particles()[i];
+        case F_INC_FC: return h->incub_belief->_fully_connected_belief.particles()[i];
+        case F_INC_SHADOW: return h->incub_belief->_shadow_belief.particle(i)->particle;
+        case F_GIBBS: return h->gibbs_belief->_belief.particle(i)->particle;
+        case F_NESTED: return h->nested_belief->_filter.particle(i)->particle.first;
     }
     return nullptr;
 }
@@ -127,6 +152,13 @@ long filterSize(Handle* h, int filter)
         case F_REINV_FC:
             return h->reinv_belief ? (long)h->reinv_belief->_fully_connected_belief.size() : 0;
         case F_MH: return h->mh_belief ? (long)h->mh_belief->_belief.size() : 0;
+        case F_CHEAT: return h->cheat_belief ? (long)h->cheat_belief->_belief.size() : 0;
+        case F_CHEAT_CORRECT: return h->cheat_belief ? (long)h->cheat_belief->_correct_structured_belief.size() : 0;
+        case F_INC: return h->incub_belief ? (long)h->incub_belief->_belief.size() : 0;
+        case F_INC_FC: return h->incub_belief ? (long)h->incub_belief->_fully_connected_belief.size() : 0;
+        case F_INC_SHADOW: return h->incub_belief ? (long)h->incub_belief->_shadow_belief.size() : 0;
+        case F_GIBBS: return h->gibbs_belief ? (long)h->gibbs_belief->_belief.size() : 0;
+        case F_NESTED: return h->nested_belief ? (long)h->nested_belief->_filter.size() : 0;
     }
     return 0;
 }
@@ -236,6 +268,10 @@ void ref_close(void* hv)
         if (h->rs_belief) h->rs_belief->free(*h->sim);
         if (h->reinv_belief) h->reinv_belief->free(*h->sim);
         if (h->mh_belief) h->mh_belief->free(*h->sim);
+        if (h->cheat_belief) h->cheat_belief->free(*h->sim);
+        if (h->incub_belief) h->incub_belief->free(*h->sim);
+        if (h->gibbs_belief) h->gibbs_belief->free(*h->sim);
+        if (h->nested_belief) h->nested_belief->free(*h->sim);
     }
     delete h;
 }
@@ -338,7 +374,8 @@ void ref_filter_states(void* hv, int filter, int* out)
 {
     auto h = static_cast<Handle*>(hv);
     auto n = filterSize(h, filter);
-    for (long i = 0; i < n; ++i) out[i] = particleOf(h, filter, i)->_domain_state->index();
+    for (long i = 0; i < n; ++i)
+        out[i] = (filter == F_NESTED) ? -1 : particleOf(h, filter, i)->_domain_state->index();
 }
 
 // weights of the importance-sampling filter + its _total_weight
@@ -580,6 +617,154 @@ long ref_mh_posterior_probe(void* hv, uint32_t const* t_par, uint32_t const* o_p
             for (auto v : model.observationNode(&action, g)._cpts) counts[k++] = v;
     }
     return attempts;
+}
+
+/**** the composite structure beliefs ****/
+// kind: F_CHEAT = CheatingReinvigoration(n, amount, threshold < 0), F_INC = StructureIncubatorSampling(n,
+// amount, 0 < threshold <= 1), F_GIBBS = MHwithinGibbs(n, threshold < 0, amount: 0 = MSG, 1 = RS),
+// F_NESTED = NestedBelief(n, amount)
+int ref_composite_init(void* hv, int kind, long n, long amount, double threshold)
+{
+    auto h = static_cast<Handle*>(hv);
+    try
+    {
+        if (kind == F_CHEAT)
+        {
+            if (h->cheat_belief) h->cheat_belief->free(*h->sim);
+            h->cheat_belief.reset(new RefCheat((size_t)n, (size_t)amount, threshold));
+            h->cheat_belief->initiate(*h->sim);
+        } else if (kind == F_INC)
+        {
+            if (h->incub_belief) h->incub_belief->free(*h->sim);
+            h->incub_belief.reset(new RefIncub((size_t)n, (size_t)amount, threshold));
+            h->incub_belief->initiate(*h->sim);
+        } else if (kind == F_GIBBS)
+        {
+            if (h->gibbs_belief) h->gibbs_belief->free(*h->sim);
+            h->gibbs_belief.reset(new RefGibbs((size_t)n, threshold, amount ? RefGibbs::RS : RefGibbs::MSG));
+            h->gibbs_belief->initiate(*h->sim);
+        } else if (kind == F_NESTED)
+        {
+            if (h->nested_belief) h->nested_belief->free(*h->sim);
+            h->nested_belief.reset(new RefNested((size_t)n, (size_t)amount));
+            h->nested_belief->initiate(*h->sim);
+        } else
+        {
+            h->err = "ref_composite_init: unknown kind";
+            return 1;
+        }
+    } catch (std::string const& e)
+    {
+        h->err = e;
+        return 1;
+    } catch (char const* e)
+    {
+        h->err = e;
+        return 1;
+    }
+    return 0;
+}
+
+beliefs::BABelief* compositeOf(Handle* h, int kind)
+{
+    switch (kind)
+    {
+        case F_CHEAT: return h->cheat_belief.get();
+        case F_INC: return h->incub_belief.get();
+        case F_GIBBS: return h->gibbs_belief.get();
+        case F_NESTED: return h->nested_belief.get();
+    }
+    return nullptr;
+}
+
+void ref_composite_update(void* hv, int kind, int a, int o)
+{
+    auto h = static_cast<Handle*>(hv);
+    // MHwithinGibbs keeps the pointers in its history (MHwithinGibbs.cpp:317): heap objects, released by free()
+    if (kind == F_GIBBS) h->gibbs_belief->updateEstimation(new IndexAction(a), new IndexObservation(o), *h->sim);
+    else
+    {
+        IndexAction act(a);
+        IndexObservation obs(o);
+        compositeOf(h, kind)->updateEstimation(&act, &obs, *h->sim);
+    }
+}
+
+void ref_composite_reset(void* hv, int kind)
+{
+    auto h = static_cast<Handle*>(hv);
+    compositeOf(h, kind)->resetDomainStateDistribution(*h->sim);
+}
+
+// weights and _total_weight of a weighted filter (F_IS, F_MH, F_CHEAT, F_INC_SHADOW, F_GIBBS, F_NESTED)
+void ref_filter_weights(void* hv, int filter, double* w, double* total)
+{
+    auto h = static_cast<Handle*>(hv);
+    auto n = filterSize(h, filter);
+#define FBA_W(F)                                              \
+    {                                                         \
+        for (long i = 0; i < n; ++i) w[i] = (F).particle(i)->w; \
+        *total = (F)._total_weight;                           \
+    }
+    switch (filter)
+    {
+        case F_IS: FBA_W(h->is_belief->_filter) break;
+        case F_MH: FBA_W(h->mh_belief->_belief) break;
+        case F_CHEAT: FBA_W(h->cheat_belief->_belief) break;
+        case F_INC_SHADOW: FBA_W(h->incub_belief->_shadow_belief) break;
+        case F_GIBBS: FBA_W(h->gibbs_belief->_belief) break;
+        case F_NESTED: FBA_W(h->nested_belief->_filter) break;
+        default: *total = -1;
+    }
+#undef FBA_W
+}
+
+double ref_cheat_likelihood(void* hv)
+{
+    return static_cast<Handle*>(hv)->cheat_belief->_likelihood;
+}
+
+// the parts of StructureIncubatorSampling::updateEstimation one by one (StructureIncubatorSampling.cpp:107-137)
+// part 0: reinvigorateBelief, 1: reinvigorateShadowBelief, 2: rejectSample(_belief), 3: rejectSample(_fully_connected),
+// 4: importance_sampling::update(_shadow), 5: importance_sampling::resample(_shadow). Returns part 4's likelihood.
+double ref_incubator_part(void* hv, int part, int a, int o)
+{
+    auto h        = static_cast<Handle*>(hv);
+    auto& b       = *h->incub_belief;
+    auto const& f = dynamic_cast<FactoredPOMDP const&>(*h->sim);
+    IndexAction act(a);
+    IndexObservation obs(o);
+    switch (part)
+    {
+        case 0: b.reinvigorateBelief(f); break;
+        case 1: b.reinvigorateShadowBelief(f); break;
+        case 2: ::beliefs::rejectSample(&act, &obs, *h->sim, b._size, b._belief); break;
+        case 3: ::beliefs::rejectSample(&act, &obs, *h->sim, b._size, b._fully_connected_belief); break;
+        case 4: return ::beliefs::importance_sampling::update(b._shadow_belief, &act, &obs, *h->sim);
+        case 5: ::beliefs::importance_sampling::resample(b._shadow_belief, *h->sim, b._size); break;
+    }
+    return 0.0;
+}
+
+// overwrite the weights of the incubator's shadow belief (to exercise promotion and leastLikely on
+// non-uniform weights, which the reference's own update never produces: it resamples every step)
+void ref_incubator_set_shadow_weights(void* hv, double const* w)
+{
+    auto h  = static_cast<Handle*>(hv);
+    auto& f = h->incub_belief->_shadow_belief;
+    double total = 0;
+    for (size_t i = 0; i < f.size(); ++i)
+    {
+        f.particle(i)->w = w[i];
+        total += w[i];
+    }
+    f._total_weight = total;
+}
+
+void ref_cheat_only(void* hv)
+{
+    auto h = static_cast<Handle*>(hv);
+    h->cheat_belief->cheat(*h->sim);
 }
 
 /**** importance sampling ****/
@@ -876,8 +1061,20 @@ int ref_adapter_episodes(void* hv, int kind, long n, char const* planner, int si
                                                                                     : FBA_MUT_GRIDWORLD;
             size_t const k = std::max<size_t>(1, n / 8);
             if (kind == 4) belief.reset(new ReinvRS(n, k));
-            else
+            else if (kind == 5)
                 belief.reset(new fba_b200::CudaReinvigoratingRejectionSampling(n, k, mut));
+            // the composite structure beliefs with the settings of the reference's own integration tests
+            // (test/test.cpp:296-353: cheating threshold -3, incubator threshold .05)
+            else if (kind == 8)
+                belief.reset(new RefCheat((size_t)n, k, -3.0));
+            else if (kind == 9)
+                belief.reset(new fba_b200::CudaCheatingReinvigoration((size_t)n, k, -3.0));
+            else if (kind == 10)
+                belief.reset(new RefIncub((size_t)n, k, 0.05));
+            else if (kind == 11)
+                belief.reset(new fba_b200::CudaStructureIncubatorSampling((size_t)n, k, 0.05, mut));
+            else
+                throw std::string("ref_adapter_episodes: unknown belief kind");
         }
 
         belief->initiate(*h->sim);

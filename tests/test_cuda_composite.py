@@ -1,0 +1,199 @@
+"""GPU: the composite structure beliefs (fba-pomdp_b200/structure_beliefs.py over the C ABI) in REPLAY mode
+against the UNMODIFIED reference's own CheatingReinvigoration and StructureIncubatorSampling through
+tests/golden/composite.npz (oracle/gen_composite.py): fed the exact mt19937 words each call consumed, every
+updateEstimation / resetDomainStateDistribution leaves the reference's filters behind bit for bit — domain
+states, structures, counts, weights, _total_weight, accumulated likelihood — and consumes every word."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "composite.npz")
+MUT_FACTORED_TIGER = 0
+
+
+@pytest.fixture(scope="module")
+def env():
+    import fba_pomdp_b200 as fba
+    g = np.load(GOLDEN)
+    desc = {k[len("model/"):]: g[k] for k in g.files if k.startswith("model/")}
+    ctx = fba.Context(0)
+    sim = fba.BAPOMDP(ctx, desc, g["structs/t_par"], g["structs/o_par"], max_structures=len(g["structs/t_par"]) + 512)
+    yield fba, g, sim
+    sim.close()
+    ctx.close()
+
+
+def particles(g, prefix):
+    return dict(struct_id=g[prefix + "_struct_id"], counts=g[prefix + "_counts"], state=g[prefix + "_state"])
+
+
+def assert_matches(b, g, prefix, weighted=False):
+    d = b.download()
+    np.testing.assert_array_equal(d["state"], g[prefix + "_state"], err_msg=prefix)
+    np.testing.assert_array_equal(d["struct_id"], g[prefix + "_struct_id"], err_msg=prefix)
+    np.testing.assert_array_equal(d["counts"].astype(np.float64).sum(1), g[prefix + "_count_sums"], err_msg=prefix)
+    if (prefix + "_counts") in g.files:
+        np.testing.assert_array_equal(d["counts"], g[prefix + "_counts"], err_msg=prefix)
+    if weighted:
+        np.testing.assert_array_equal(d["w"], g[prefix + "_w"], err_msg=prefix)
+        assert d["total_weight"] == float(g[prefix + "_total_weight"]), prefix
+
+
+def set_weights(b, w, total):
+    from fba_pomdp_b200.capi import ptr
+    w = np.ascontiguousarray(w, np.float64)
+    rc = b.L.fba_belief_upload(b.h, 0, len(w), None, None, None, ptr(w))
+    assert rc == 0
+    assert b.download(counts=False)["total_weight"] == total   # upload re-accumulates in order, as the harness did
+
+
+def test_cheating_reinvigoration_replay(env):
+    fba, g, sim = env
+    from fba_pomdp_b200.structure_beliefs import CheatingReinvigoration
+    N, stride = int(g["meta/N"]), int(g["meta/stride"])
+    b = CheatingReinvigoration(N, int(g["meta/amount"]), float(g["meta/cheat_threshold"]))
+    b.initiate(sim, belief=particles(g, "cheat/init_b"), correct_structured=particles(g, "cheat/init_c"), stride=stride)
+    a_, o_, fl_ = g["script/a"], g["script/o"], g["script/flags"]
+    updates = 0
+    for t in range(len(a_)):
+        if fl_[t] & 2 and t > 0:
+            rng = fba.Rng.replay(g["cheat/%d/reset_words" % t])
+            b.resetDomainStateDistribution(rng)
+            assert rng.exhausted
+            np.testing.assert_array_equal(b._belief.download(counts=False)["state"], g["cheat/%d/reset_b_state" % t])
+            np.testing.assert_array_equal(b._correct_structured_belief.download(counts=False)["state"],
+                                          g["cheat/%d/reset_c_state" % t])
+        if fl_[t] & 1:
+            continue
+        rng = fba.Rng.replay(g["cheat/%d/words" % t])
+        b.updateEstimation(int(a_[t]), int(o_[t]), rng)
+        assert rng.exhausted, t
+        assert b._likelihood == float(g["cheat/%d/likelihood" % t])
+        assert_matches(b._belief, g, "cheat/%d/b" % t, weighted=True)
+        assert_matches(b._correct_structured_belief, g, "cheat/%d/c" % t)
+        updates += 1
+    assert_matches(b._belief, g, "cheat/final_b", weighted=True)
+    assert_matches(b._correct_structured_belief, g, "cheat/final_c")
+    assert updates >= 12 and b.cheats >= 3
+    b.free()
+
+
+def test_structure_incubator_replay(env):
+    fba, g, sim = env
+    from fba_pomdp_b200.structure_beliefs import StructureIncubatorSampling
+    N, stride = int(g["meta/N"]), int(g["meta/stride"])
+    inc = StructureIncubatorSampling(N, int(g["meta/amount"]), float(g["meta/inc_threshold"]), MUT_FACTORED_TIGER)
+    inc.initiate(sim, belief=particles(g, "inc/init_b"), fully_connected=particles(g, "inc/init_fc"), stride=stride,
+                 shadow=particles(g, "inc/init_s"))
+    set_weights(inc._shadow_belief, g["inc/init_s_w"], float(g["inc/init_s_total_weight"]))
+    a_, o_, fl_ = g["script/a"], g["script/o"], g["script/flags"]
+    done = 0
+    for t in range(int(g["inc/last_step"]) + 1):
+        if fl_[t] & 2 and t > 0:
+            rng = fba.Rng.replay(g["inc/%d/reset_words" % t])
+            inc.resetDomainStateDistribution(rng)
+            assert rng.exhausted
+            for tag, b in (("b", inc._belief), ("fc", inc._fully_connected_belief), ("s", inc._shadow_belief)):
+                np.testing.assert_array_equal(b.download(counts=False)["state"], g["inc/%d/reset_%s_state" % (t, tag)])
+        if fl_[t] & 1:
+            continue
+        rng = fba.Rng.replay(g["inc/%d/words" % t])
+        inc.updateEstimation(int(a_[t]), int(o_[t]), rng)
+        assert rng.exhausted, t
+        assert_matches(inc._belief, g, "inc/%d/b" % t)
+        assert_matches(inc._fully_connected_belief, g, "inc/%d/fc" % t)
+        assert_matches(inc._shadow_belief, g, "inc/%d/s" % t, weighted=True)
+        done += 1
+    assert done == 10
+    inc.free()
+
+
+def test_incubator_parts_on_distinct_shadow_weights(env):
+    """promotion into the belief, leastLikely and WeightedFilter::replace weights on NON-uniform shadow weights"""
+    fba, g, sim = env
+    from fba_pomdp_b200.structure_beliefs import StructureIncubatorSampling
+    N, stride = int(g["meta/N"]), int(g["meta/stride"])
+    inc = StructureIncubatorSampling(N, int(g["meta/amount"]), float(g["meta/inc_threshold"]), MUT_FACTORED_TIGER)
+    inc.initiate(sim, belief=particles(g, "inc/parts/before_b"), fully_connected=particles(g, "inc/parts/before_fc"),
+                 stride=stride, shadow=particles(g, "inc/parts/before_s"))
+    set_weights(inc._shadow_belief, g["inc/parts/before_s_w"], float(g["inc/parts/before_s_total_weight"]))
+    a, o = int(g["inc/parts/a"]), int(g["inc/parts/o"])
+    steps = [inc.reinvigorateBelief, inc.reinvigorateShadowBelief,
+             lambda r: inc._belief.updateEstimation(a, o, r), lambda r: inc._fully_connected_belief.updateEstimation(a, o, r),
+             lambda r: inc._shadow_belief.update(a, o, r), lambda r: inc._shadow_belief.resample(r)]
+    for part, fn in enumerate(steps):
+        rng = fba.Rng.replay(g["inc/parts/%d/words" % part])
+        res = fn(rng)
+        assert rng.exhausted, part
+        if part == 0:
+            assert res == 5
+        if part == 4:
+            assert res == float(g["inc/parts/4/likelihood"])
+        assert_matches(inc._belief, g, "inc/parts/%d/b" % part)
+        assert_matches(inc._fully_connected_belief, g, "inc/parts/%d/fc" % part)
+        assert_matches(inc._shadow_belief, g, "inc/parts/%d/s" % part, weighted=True)
+    inc.free()
+
+
+def test_incubator_initiate_breeds_the_shadow_belief(env):
+    """StructureIncubatorSampling::initiate's tail (:74-80): N breeds into the shadow belief with weights
+    1 / N — here in PHILOX mode: every shadow particle has a structure one mutation away from a belief
+    particle's, the domain state of a belief particle, and counts that marginalise a fully connected
+    particle's (equal row sums per node)."""
+    fba, g, sim = env
+    from fba_pomdp_b200.structure_beliefs import StructureIncubatorSampling
+    N, stride = int(g["meta/N"]), int(g["meta/stride"])
+    inc = StructureIncubatorSampling(N, int(g["meta/amount"]), float(g["meta/inc_threshold"]), MUT_FACTORED_TIGER)
+    inc.initiate(sim, belief=particles(g, "inc/init_b"), fully_connected=particles(g, "inc/init_fc"), stride=stride,
+                 rng=fba.Rng.philox(11))
+    d = inc._shadow_belief.download()
+    np.testing.assert_array_equal(d["w"], np.full(N, 1.0 / N))
+    fc_sums = set(np.round(g["inc/init_fc_counts"].astype(np.float64).sum(1), 3).tolist())
+    assert set(np.round(d["counts"].astype(np.float64).sum(1), 3).tolist()) <= fc_sums   # marginalising keeps the mass
+    assert set(d["state"].tolist()) <= set(g["inc/init_b_state"].tolist())
+    belief_structs = {(sim.structure(int(i))[0].tobytes(), sim.structure(int(i))[1].tobytes())
+                      for i in np.unique(g["inc/init_b_struct_id"])}
+    for i in np.unique(d["struct_id"]):
+        t, o = sim.structure(int(i))
+        one_flip = False
+        for bt, bo in belief_structs:
+            diff = np.frombuffer(bo, np.uint32) ^ o.reshape(-1)
+            if bt == t.tobytes() and np.count_nonzero(diff) == 1 and bin(int(diff[diff != 0][0])).count("1") == 1:
+                one_flip = True
+        assert one_flip
+    inc.free()
+
+
+def test_replace_from_and_argument_checks(env):
+    fba, g, sim = env
+    from fba_pomdp_b200.structure_beliefs import replace_from
+    N, stride = int(g["meta/N"]), int(g["meta/stride"])
+    src = fba.BARejectionSampling(N)
+    src.initiate(sim, **particles(g, "cheat/init_c"), stride=stride)
+    dst = fba.BAImportanceSampling(N)
+    dst.initiate(sim, **particles(g, "cheat/init_b"), stride=stride)
+    before = dst.download()
+    s = src.download()
+    replace_from(dst, [5, 7, 5], src, [1, 2, 3])     # slot 5 is written twice: the later one stays
+    d = dst.download()
+    want = before["counts"].copy()
+    want[7], want[5] = s["counts"][2], s["counts"][3]
+    np.testing.assert_array_equal(d["counts"], want)
+    assert d["state"][5] == s["state"][3] and d["struct_id"][7] == s["struct_id"][2]
+    # WeightedFilter::replace weights, slot after slot
+    w, tot = before["w"].copy(), before["total_weight"]
+    for slot in (5, 7, 5):
+        nw = tot / N
+        tot = tot + (nw - w[slot])
+        w[slot] = nw
+    np.testing.assert_array_equal(d["w"], w)
+    assert d["total_weight"] == tot
+    with pytest.raises(fba.FbaError):
+        replace_from(dst, [N], src, [0])
+    with pytest.raises(fba.FbaError):
+        replace_from(dst, [0], dst, [1])
+    src.free()
+    dst.free()

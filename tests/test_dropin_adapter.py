@@ -31,6 +31,15 @@ CASES = [
     ("episodic-factored-tiger", dict(size=3, factored=True, structure_prior="match-uniform"), (6, 7), 96, 40),
     ("centered-collision-avoidance", dict(size=1, width=3, height=3, factored=True,
                                           structure_prior="match-uniform"), (6, 7), 64, 30),
+    # the composite structure beliefs, settings of the reference's own integration tests (test/test.cpp:296-353):
+    # CheatingReinvigoration (threshold -3) and StructureIncubatorSampling (threshold .05) vs the CUDA adapters
+    ("episodic-factored-tiger", dict(size=3, factored=True, structure_prior="match-uniform"), (8, 9), 96, 40),
+    ("centered-collision-avoidance", dict(size=1, width=3, height=3, factored=True,
+                                          structure_prior="match-uniform"), (8, 9), 64, 30),
+    ("episodic-factored-tiger", dict(size=3, factored=True, structure_prior="match-uniform"), (10, 11), 96, 40),
+    ("centered-collision-avoidance", dict(size=1, width=3, height=3, factored=True,
+                                          structure_prior="match-uniform"), (10, 11), 64, 30),
+    ("linear-sysadmin", dict(size=3, factored=True), (10, 11), 64, 20),
     # --dirichlet_sampling_method regular: the adapter reads the mode from the simulator
     ("episodic-tiger", dict(sampled=True), (0, 1), 256, 80),
     ("episodic-factored-tiger", dict(size=3, factored=True, sampled=True), (0, 1), 128, 40),

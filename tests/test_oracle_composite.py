@@ -1,0 +1,134 @@
+"""CPU: the oracle's restatement of the reference's composite structure beliefs (oracle/pycomposite.py over
+oracle/fba_oracle.c) against the UNMODIFIED reference's own classes — CheatingReinvigoration and
+StructureIncubatorSampling — through tests/golden/composite.npz (oracle/gen_composite.py): fed the exact
+mt19937 words each call consumed, every updateEstimation / resetDomainStateDistribution reproduces the
+reference's filters bit for bit (states, structures, counts, weights, _total_weight, likelihood) and
+consumes every word."""
+import os
+
+import numpy as np
+import pytest
+
+import pycomposite as PC
+import pyoracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "composite.npz")
+MUT_FACTORED_TIGER = 0
+
+
+def load():
+    g = np.load(GOLDEN)
+    desc = {k[len("model/"):]: g[k] for k in g.files if k.startswith("model/")}
+    m = O.Model(desc)
+    st = O.Structs(m, g["structs/t_par"], g["structs/o_par"], cap=len(g["structs/t_par"]) + 512)
+    return g, m, st
+
+
+def used(rng):
+    return not rng.overrun and rng.cur == len(rng.words)
+
+
+def test_cheating_reinvigoration_equals_the_reference():
+    g, m, st = load()
+    stride = int(g["meta/stride"])
+    b = PC.Cheating(m, st, PC.belief_from(g, "cheat/init_b", stride, True),
+                    PC.belief_from(g, "cheat/init_c", stride, False), int(g["meta/amount"]),
+                    float(g["meta/cheat_threshold"]))
+    a_, o_, fl_ = g["script/a"], g["script/o"], g["script/flags"]
+    updates = cheated = 0
+    for t in range(len(a_)):
+        if fl_[t] & 2 and t > 0:
+            rng = O.Rng(g["cheat/%d/reset_words" % t])
+            b.reset(rng)
+            assert used(rng)
+            np.testing.assert_array_equal(b.belief.state, g["cheat/%d/reset_b_state" % t])
+            np.testing.assert_array_equal(b.correct.state, g["cheat/%d/reset_c_state" % t])
+        if fl_[t] & 1:
+            continue
+        rng = O.Rng(g["cheat/%d/words" % t])
+        b.update(int(a_[t]), int(o_[t]), rng)
+        assert used(rng), t
+        assert b.likelihood == float(g["cheat/%d/likelihood" % t])
+        PC.assert_matches(b.belief, g, "cheat/%d/b" % t, weighted=True)
+        PC.assert_matches(b.correct, g, "cheat/%d/c" % t)
+        updates += 1
+        cheated += int(b.likelihood == 1.0)
+        if b.likelihood == 1.0:     # a cheat leaves _total_weight / N in the replaced slots: weights are no longer all equal
+            assert len(np.unique(b.belief.w)) > 1
+    PC.assert_matches(b.belief, g, "cheat/final_b", weighted=True)
+    PC.assert_matches(b.correct, g, "cheat/final_c")
+    assert updates >= 12 and cheated >= 3       # the cheat path (WeightedFilter::replace weights) was exercised
+
+
+def test_structure_incubator_equals_the_reference():
+    g, m, st = load()
+    stride, N = int(g["meta/stride"]), int(g["meta/N"])
+    inc = PC.Incubator(m, st, PC.belief_from(g, "inc/init_b", stride, False),
+                       PC.belief_from(g, "inc/init_fc", stride, False),
+                       PC.belief_from(g, "inc/init_s", stride, True), int(g["meta/amount"]),
+                       float(g["meta/inc_threshold"]), MUT_FACTORED_TIGER)
+    a_, o_, fl_ = g["script/a"], g["script/o"], g["script/flags"]
+    done = 0
+    for t in range(int(g["inc/last_step"]) + 1):
+        if fl_[t] & 2 and t > 0:
+            rng = O.Rng(g["inc/%d/reset_words" % t])
+            inc.reset(rng)
+            assert used(rng)
+            for tag, b in (("b", inc.belief), ("fc", inc.fc), ("s", inc.shadow)):
+                np.testing.assert_array_equal(b.state, g["inc/%d/reset_%s_state" % (t, tag)])
+        if fl_[t] & 1:
+            continue
+        rng = O.Rng(g["inc/%d/words" % t])
+        inc.update(int(a_[t]), int(o_[t]), rng)
+        assert used(rng), t
+        PC.assert_matches(inc.belief, g, "inc/%d/b" % t)
+        PC.assert_matches(inc.fc, g, "inc/%d/fc" % t)
+        PC.assert_matches(inc.shadow, g, "inc/%d/s" % t, weighted=True)
+        done += 1
+    assert done == 10
+
+
+def test_incubator_parts_on_distinct_shadow_weights():
+    """promotion into the belief, leastLikely and the replacement weights on NON-uniform shadow weights"""
+    g, m, st = load()
+    stride = int(g["meta/stride"])
+    inc = PC.Incubator(m, st, PC.belief_from(g, "inc/parts/before_b", stride, False),
+                       PC.belief_from(g, "inc/parts/before_fc", stride, False),
+                       PC.belief_from(g, "inc/parts/before_s", stride, True), int(g["meta/amount"]),
+                       float(g["meta/inc_threshold"]), MUT_FACTORED_TIGER)
+    a, o = int(g["inc/parts/a"]), int(g["inc/parts/o"])
+    steps = [lambda r: inc.reinvigorate_belief(r), lambda r: inc.reinvigorate_shadow(r),
+             lambda r: inc.reject("belief", a, o, r), lambda r: inc.reject("fc", a, o, r),
+             lambda r: O.is_update(m, st, inc.shadow, a, o, r),
+             lambda r: setattr(inc, "shadow", O.is_resample(inc.shadow, r)[0])]
+    for part, fn in enumerate(steps):
+        rng = O.Rng(g["inc/parts/%d/words" % part])
+        res = fn(rng)
+        assert used(rng), part
+        if part == 0:
+            assert res == 5                      # the five heavy particles moved into the belief
+        if part == 4:
+            assert res == float(g["inc/parts/4/likelihood"])
+        PC.assert_matches(inc.belief, g, "inc/parts/%d/b" % part)
+        PC.assert_matches(inc.fc, g, "inc/parts/%d/fc" % part)
+        PC.assert_matches(inc.shadow, g, "inc/parts/%d/s" % part, weighted=True)
+
+
+@pytest.mark.parametrize("n,k", [(48, 6), (48, 47), (1000, 1), (1000, 128)])
+def test_least_likely_ties_and_distinct_weights(n, k):
+    """orc_least_likely restates libstdc++'s heap. On distinct weights the result does not depend on the
+    container: WeightedFilter::leastLikely (WeightedFilter.cpp:206-243) seeds its queue with the first k
+    particles and then walks ALL particles again from 0 — so one of the first k can be kept twice —
+    replacing the heaviest kept one whenever a strictly lighter particle comes by; heaviest first."""
+    rs = np.random.RandomState(n + k)
+    w = rs.rand(n)
+    kept = [(w[i], i) for i in range(k)]
+    for i in range(n):
+        top = max(kept)
+        if w[i] < top[0]:
+            kept.remove(top)
+            kept.append((w[i], i))
+    want = [i for _, i in sorted(kept, reverse=True)]
+    np.testing.assert_array_equal(O.least_likely(w, k), want)
+    # all equal: nothing is strictly lighter, the first k stay
+    assert sorted(O.least_likely(np.full(n, 1.0 / n), k).tolist()) == list(range(k))
