@@ -46,6 +46,8 @@ SYMBOLS = [
     "fba_runs_create", "fba_runs_destroy", "fba_runs_belief", "fba_runs_init_sampled",
     "fba_runs_update_estimation", "fba_runs_reset_domain_states", "fba_runs_sample", "fba_runs_copies", "fba_runs_plan", "fba_runs_init",
     "fba_belief_replace_from", "fba_belief_cheat", "fba_belief_breed_into", "fba_belief_least_likely", "fba_belief_promote", "fba_belief_redraw_domain_states",
+    "fba_nested_create", "fba_nested_destroy", "fba_nested_top", "fba_nested_bottom_size", "fba_nested_upload_states",
+    "fba_nested_download_states", "fba_nested_reset_domain_states", "fba_nested_update", "fba_nested_sample",
 ]
 
 
@@ -193,6 +195,15 @@ def lib():
             "fba_belief_least_likely": (C.c_int, [vp, i64, vp]),
             "fba_belief_promote": (C.c_int, [vp, vp, dbl, vp, vp]),
             "fba_belief_redraw_domain_states": (C.c_int, [vp, vp]),
+            "fba_nested_create": (C.c_int, [vp, vp, i64, i64, i64, pp]),
+            "fba_nested_destroy": (None, [vp]),
+            "fba_nested_top": (vp, [vp]),
+            "fba_nested_bottom_size": (i64, [vp]),
+            "fba_nested_upload_states": (C.c_int, [vp, i64, i64, vp]),
+            "fba_nested_download_states": (C.c_int, [vp, i64, i64, vp]),
+            "fba_nested_reset_domain_states": (C.c_int, [vp, vp]),
+            "fba_nested_update": (C.c_int, [vp, i32, i32, vp, i64, vp]),
+            "fba_nested_sample": (C.c_int, [vp, vp, vp, vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)

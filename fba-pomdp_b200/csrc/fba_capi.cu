@@ -2531,6 +2531,237 @@ extern "C" int fba_belief_promote(fba_belief* shadow, fba_belief* belief, double
     return FBA_OK;
 }
 
+// ---- NestedBelief ----------------------------------------------------------------------------------------
+
+struct fba_nested
+{
+    fba_ctx* ctx    = nullptr;
+    fba_model* m    = nullptr;
+    fba_belief* top = nullptr; // the weighted top filter: count blocks, structure ids, weights
+    long long n_top = 0;
+    int n_bottom    = 0;
+    int* states[2]  = {nullptr, nullptr}; // [n_top][n_bottom] domain states, double-buffered per update
+    int cur         = 0;
+    long long* d_attempts = nullptr;
+    int* d_failed   = nullptr;
+};
+
+extern "C" void fba_nested_destroy(fba_nested* n)
+{
+    if (!n) return;
+    cudaSetDevice(n->ctx->device);
+    fba_belief_destroy(n->top);
+    cudaFree(n->states[0]), cudaFree(n->states[1]), cudaFree(n->d_attempts), cudaFree(n->d_failed);
+    delete n;
+}
+
+extern "C" int fba_nested_create(fba_ctx* ctx, fba_model* m, int64_t n_top, int64_t n_bottom, int64_t stride,
+                                 fba_nested** out)
+{
+    if (!ctx || !m || !out) return FBA_ERR_INVALID;
+    *out = nullptr;
+    // NestedBelief.cpp:19-26
+    REQUIRE(ctx, n_top >= 1 && n_bottom >= 1,
+            "NestedBelief: cannot initiate with filter size < 1 (top: " + std::to_string(n_top) + ", bottom: "
+                + std::to_string(n_bottom) + ")");
+    REQUIRE(ctx, n_bottom < (1ll << 31) && n_top * n_bottom < (1ll << 40), "NestedBelief: filters too large");
+    REQUIRE(ctx, m->delta_cap == 0, "NestedBelief: dense storage only");
+    auto n      = new fba_nested();
+    n->ctx      = ctx;
+    n->m        = m;
+    n->n_top    = n_top;
+    n->n_bottom = (int)n_bottom;
+    int rc      = fba_belief_create(ctx, m, n_top, stride, 1, &n->top);
+    if (rc)
+    {
+        delete n;
+        return rc;
+    }
+    cudaError_t e = cudaMalloc(&n->states[0], (size_t)n_top * n_bottom * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&n->states[1], (size_t)n_top * n_bottom * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&n->d_attempts, (size_t)n_top * sizeof(long long));
+    if (e == cudaSuccess) e = cudaMalloc(&n->d_failed, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(n->states[0], 0, (size_t)n_top * n_bottom * sizeof(int));
+    if (e != cudaSuccess)
+    {
+        ctx->err = std::string("nested alloc: ") + cudaGetErrorString(e);
+        fba_nested_destroy(n);
+        return FBA_ERR_CUDA;
+    }
+    *out = n;
+    return FBA_OK;
+}
+
+extern "C" fba_belief* fba_nested_top(fba_nested* n)
+{
+    return n ? n->top : nullptr;
+}
+extern "C" int64_t fba_nested_bottom_size(const fba_nested* n)
+{
+    return n ? n->n_bottom : 0;
+}
+
+extern "C" int fba_nested_upload_states(fba_nested* n, int64_t first_top, int64_t count, const int32_t* states)
+{
+    if (!n || !states) return FBA_ERR_INVALID;
+    fba_ctx* ctx = n->ctx;
+    REQUIRE(ctx, first_top >= 0 && count >= 0 && first_top + count <= n->n_top, "nested upload: range out of bounds");
+    for (int64_t k = 0; k < count * n->n_bottom; ++k)
+        REQUIRE(ctx, states[k] >= 0 && states[k] < n->m->dev.S, "nested upload: domain state out of range");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpyAsync(n->states[n->cur] + first_top * n->n_bottom, states, (size_t)count * n->n_bottom * sizeof(int),
+                            cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return FBA_OK;
+}
+
+extern "C" int fba_nested_download_states(fba_nested* n, int64_t first_top, int64_t count, int32_t* states)
+{
+    if (!n || !states) return FBA_ERR_INVALID;
+    fba_ctx* ctx = n->ctx;
+    REQUIRE(ctx, first_top >= 0 && count >= 0 && first_top + count <= n->n_top, "nested download: range out of bounds");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpyAsync(states, n->states[n->cur] + first_top * n->n_bottom, (size_t)count * n->n_bottom * sizeof(int),
+                            cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return FBA_OK;
+}
+
+// NestedBelief::resetDomainStateDistribution (NestedBelief.cpp:33-61): n_bottom fresh domain start states
+// for every top particle, in particle order — the flat reset kernel over all n_top * n_bottom states
+extern "C" int fba_nested_reset_domain_states(fba_nested* n, fba_rng* rng)
+{
+    if (!n || !rng) return FBA_ERR_INVALID;
+    fba_ctx* ctx      = n->ctx;
+    DevModel const& D = n->m->dev;
+    long long const total = n->n_top * n->n_bottom;
+    CU(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if (rng->mode == FBA_RNG_REPLAY)
+    {
+        std::vector<long long> off((size_t)total);
+        long long pos = rng->cursor;
+        for (long long j = 0; j < total; ++j)
+        {
+            off[(size_t)j] = pos - rng->cursor;
+            pos += start_state_words(D, rng, pos);
+        }
+        long long const need = pos - rng->cursor;
+        if ((rc = stage_words(ctx, rng, need))) return rc;
+        if ((rc = stage_offsets(ctx, off))) return rc;
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        if ((rc = clear_flag(ctx))) return rc;
+        LAUNCH(ctx, k_reset_states<true>, blocks_for(total), kThreads, D, n->states[n->cur], total,
+               replay_args(ctx, need, 0, true), 0, ctx->d_flag);
+        rng->cursor += need;
+        if ((rc = check_flag(ctx))) return rc;
+    } else
+        LAUNCH(ctx, k_reset_states<false>, blocks_for(total), kThreads, D, n->states[n->cur], total, philox_args(rng),
+               0, ctx->d_flag);
+    return FBA_OK;
+}
+
+// WeightedFilter::normalize() on the top filter (WeightedFilter.cpp:118-143), sequential sums on the host
+static int nested_normalize(fba_nested* n)
+{
+    fba_ctx* ctx  = n->ctx;
+    fba_belief* b = n->top;
+    std::vector<double> w((size_t)b->N);
+    CU(ctx, cudaMemcpyAsync(w.data(), b->w, w.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    volatile double total = 0.0, acc = 0.0;
+    for (double x : w) total = total + x;
+    for (double& x : w)
+    {
+        x   = x / total;
+        acc = acc + x;
+    }
+    CU(ctx, cudaMemcpyAsync(b->w, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    b->total_weight = acc;
+    b->suffix_valid = b->cdf_valid = false;
+    return FBA_OK;
+}
+
+#define LAUNCH_NESTED(R, L, S)                                                                                     \
+    LAUNCH(ctx, (k_nested_update<R, L, S>), blocks_for(n->n_top, 32), 32, D, b->counts[b->cur], b->stride,         \
+           b->sid[b->cur], b->w, n->n_top, n->n_bottom, n->states[n->cur], n->states[n->cur ^ 1], (int)action,     \
+           (int)observation, amount, (long long)max_attempts, ra, n->d_attempts, n->d_failed, ctx->d_flag)
+
+extern "C" int fba_nested_update(fba_nested* n, int32_t action, int32_t observation, fba_rng* rng, int64_t max_attempts,
+                                 int64_t* attempts)
+{
+    if (!n || !rng) return FBA_ERR_INVALID;
+    fba_ctx* ctx      = n->ctx;
+    fba_belief* b     = n->top;
+    DevModel const& D = n->m->dev;
+    REQUIRE(ctx, action >= 0 && action < D.A && observation >= 0 && observation < D.O, "nested update: action / observation out of range");
+    REQUIRE(ctx, max_attempts >= 1, "nested update: max_attempts must be positive");
+    REQUIRE(ctx, !(D.sampled && rng->mode == FBA_RNG_REPLAY), "nested update: sampled Dirichlets run in PHILOX mode only");
+    CU(ctx, cudaSetDevice(ctx->device));
+    // update_step = static_cast<float>(1.0 / static_cast<float>(_bottom_filter_size))  (NestedBelief.cpp:133)
+    float const amount = (float)(1.0 / (double)(float)n->n_bottom);
+    bool const lr      = n->m->long_rows;
+    int rc;
+    CU(ctx, cudaMemsetAsync(n->d_failed, 0, sizeof(int), ctx->stream));
+    if (rng->mode == FBA_RNG_REPLAY)
+    { // top particle i draws from the i-th equal slice of the remaining words
+        long long const per = (rng->n_words - rng->cursor) / n->n_top;
+        REQUIRE(ctx, per >= 1, "nested update: the replay stream is shorter than one word per top particle");
+        if ((rc = stage_words(ctx, rng, per * n->n_top))) return rc;
+        if ((rc = clear_flag(ctx))) return rc;
+        RngArgs const ra = replay_args(ctx, per * n->n_top, per, false);
+        if (lr) LAUNCH_NESTED(true, true, false);
+        else
+            LAUNCH_NESTED(true, false, false);
+        rng->cursor += per * n->n_top;
+    } else
+    {
+        RngArgs const ra = philox_args(rng);
+        if (D.sampled)
+        {
+            if (lr) LAUNCH_NESTED(false, true, true);
+            else
+                LAUNCH_NESTED(false, false, true);
+        } else if (lr)
+            LAUNCH_NESTED(false, true, false);
+        else
+            LAUNCH_NESTED(false, false, false);
+    }
+    CU(ctx, cudaMemcpyAsync(ctx->h_flag, n->d_failed, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (attempts)
+        CU(ctx, cudaMemcpyAsync(attempts, n->d_attempts, (size_t)n->n_top * sizeof(long long), cudaMemcpyDeviceToHost,
+                                ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (*ctx->h_flag)
+    {
+        ctx->err = "nested update: a top particle ran out of attempts (max_attempts) or of replay words before "
+                   "its bottom filter was full";
+        return rng->mode == FBA_RNG_REPLAY ? FBA_ERR_RNG_UNDERRUN : FBA_ERR_CAPACITY;
+    }
+    n->cur ^= 1;
+    return nested_normalize(n);
+}
+#undef LAUNCH_NESTED
+
+// NestedBelief::sample (NestedBelief.cpp:117-127): a weighted draw of a top particle, then a uniform draw
+// from its bottom filter
+extern "C" int fba_nested_sample(fba_nested* n, fba_rng* rng, int64_t* top_index, int32_t* state)
+{
+    if (!n || !rng || !top_index || !state) return FBA_ERR_INVALID;
+    fba_ctx* ctx = n->ctx;
+    int rc       = fba_belief_sample(n->top, rng, top_index);
+    if (rc) return rc;
+    HostDraws g(rng);
+    int const j = g.k((uint32_t)n->n_bottom);
+    if (g.overrun()) return ctx->err = "replay stream underrun in nested sample", FBA_ERR_RNG_UNDERRUN;
+    g.commit();
+    CU(ctx, cudaMemcpyAsync(state, n->states[n->cur] + *top_index * n->n_bottom + j, sizeof(int), cudaMemcpyDeviceToHost,
+                            ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return FBA_OK;
+}
+
 // ---- POMCP, tree on the device -------------------------------------------------------------------
 
 struct fba_tree

@@ -2716,4 +2716,55 @@ __global__ void __launch_bounds__(kThreads)
     if (g.overrun) *overrun = 1;
 }
 
+// ------------------------------------------------------------------------------------------------
+// beliefs::bayes_adaptive::NestedBelief::updateEstimation (src/beliefs/bayes-adaptive/NestedBelief.cpp:129-193):
+// a weighted TOP filter of count blocks, each with its own flat BOTTOM filter of n_bottom domain states.
+// One thread per top particle runs the reference's loop as it is written — it is sequential by nature:
+// every accepted bottom particle raises the counts by 1 / n_bottom before the next attempt samples from
+// them. Per attempt: a uniformly drawn bottom state (FlatFilter::sample), BAPOMDP::step in KeepCounts mode,
+// accept iff the simulated observation is the real one, then incrementCountsOf(old, a, o, new, 1 / n_bottom);
+// after n_bottom acceptances the particle's weight is multiplied by 1 / attempts. The top filter is
+// normalised by the caller (sequential sums, a few thousand doubles at most).
+// ------------------------------------------------------------------------------------------------
+template<bool REPLAY, bool LONG, bool SAMPLED>
+__global__ void __launch_bounds__(kThreads)
+    k_nested_update(DevModel M, float* counts, long long stride, const int* __restrict__ sid, double* __restrict__ w,
+                    long long n_top, int n_bottom, const int* __restrict__ states_in, int* __restrict__ states_out,
+                    int action, int observation, float amount, long long max_attempts, RngArgs ra,
+                    long long* __restrict__ attempts_out, int* __restrict__ failed, int* __restrict__ overrun)
+{
+    long long const i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_top) return;
+    auto g            = RngOf<REPLAY>::make(ra, i);
+    float* c          = counts + i * stride;
+    const Node* nodes = M.nodes + ((long long)sid[i] * M.A + action) * M.J;
+    const int* in     = states_in + i * (long long)n_bottom;
+    int* out          = states_out + i * (long long)n_bottom;
+    int rec[2 * FBA_MAX_FEATURES];
+    long long count = 0;
+    int accepted    = 0;
+    while (accepted < n_bottom)
+    {
+        if (count >= max_attempts || g.overrun)
+        {
+            *failed = 1;
+            break;
+        }
+        int const s = in[draw_k(g, (uint32_t)n_bottom)];
+        int o;
+        Feat x2;
+        int const s2 = hyper_step<STEP_RECORD, decltype(g), false, LONG, SAMPLED>(M, nodes, c, s, g, o, x2, rec);
+        if (o == observation)
+        {
+            out[accepted++] = s2;
+            for (int k = 0; k < M.J; ++k) c[rec[k]] = __fadd_rn(c[rec[k]], amount);
+        }
+        ++count;
+    }
+    // _filter.particle(i)->w *= 1.0 / static_cast<double>(count)  (NestedBelief.cpp:183)
+    if (count > 0) w[i] = __dmul_rn(w[i], __ddiv_rn(1.0, (double)count));
+    if (attempts_out) attempts_out[i] = count;
+    if (g.overrun) *overrun = 1;
+}
+
 } // namespace fba

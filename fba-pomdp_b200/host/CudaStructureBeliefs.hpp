@@ -6,6 +6,8 @@
 //                                   (src/beliefs/bayes-adaptive/prototypes/CheatingReinvigoration.{hpp,cpp})
 //   CudaStructureIncubatorSampling  stands in for beliefs::bayes_adaptive::factored::StructureIncubatorSampling
 //                                   (src/beliefs/bayes-adaptive/factored/StructureIncubatorSampling.{hpp,cpp})
+//   CudaNestedBelief                stands in for beliefs::bayes_adaptive::NestedBelief
+//                                   (src/beliefs/bayes-adaptive/NestedBelief.{hpp,cpp})
 //
 // What runs where: initiate samples the reference's own prior on the host (sampleStartState,
 // sampleCorrectGraphState, sampleFullyConnectedState) and uploads the particles; domain start states for
@@ -274,6 +276,122 @@ private:
     double _real_reinvigor_threshold;
     int _mutate;
     size_t _promoted = 0;
+};
+
+// beliefs::bayes_adaptive::NestedBelief (src/beliefs/bayes-adaptive/NestedBelief.{hpp,cpp}) over fba_nested_*:
+// the top filter's count blocks come from the reference's own prior on the host (top_filter_size x
+// sampleStartState), the bottom filters' domain states from the reference's own domain; the update — per top
+// particle a rejection-sampling loop over its bottom filter that raises its counts by 1 / bottom size per
+// accepted state — runs on the GPU, one thread per top particle. Tabular and factored simulators.
+class CudaNestedBelief : public beliefs::BABelief
+{
+public:
+    CudaNestedBelief(size_t top_filter_size, size_t bottom_filter_size, uint64_t seed = 42, int device = 0) :
+            _top(top_filter_size), _bottom(bottom_filter_size), _device(device)
+    {
+        if (top_filter_size < 1 || bottom_filter_size < 1) // as NestedBelief.cpp:19-26
+            throw "NestedBelief: cannot initiate with filter size < 1 (top: " + std::to_string(_top)
+                + ", bottom: " + std::to_string(_bottom) + ")";
+        _rng.mode    = FBA_RNG_PHILOX;
+        _rng.words   = nullptr;
+        _rng.n_words = _rng.cursor = 0;
+        _rng.seed    = seed;
+        _rng.offset  = 0;
+    }
+    ~CudaNestedBelief() override { release(); }
+
+    void initiate(POMDP const& d) override
+    {
+        auto const& bapomdp = dynamic_cast<BAPOMDP const&>(d);
+        _cuda.reset(new CudaSimulator(bapomdp, _device, 4096, 0));
+        // :63-90: per top particle a prior sample (its domain state is dropped) and `bottom` domain start states
+        std::vector<int32_t> sid(_top), states(_top * _bottom);
+        std::vector<std::vector<float>> blocks(_top);
+        size_t stride = 0;
+        for (size_t i = 0; i < _top; ++i)
+        {
+            for (size_t j = 0; j < _bottom; ++j) states[i * _bottom + j] = startState(bapomdp);
+            auto p = static_cast<BAState const*>(bapomdp.sampleStartState());
+            sid[i] = _cuda->describe(p, &blocks[i]);
+            stride = std::max(stride, blocks[i].size());
+            d.releaseState(p);
+        }
+        check(_cuda->ctx(),
+              fba_nested_create(_cuda->ctx(), _cuda->model(), (int64_t)_top, (int64_t)_bottom, (int64_t)stride, &_nested),
+              "fba_nested_create");
+        fba_belief* top = fba_nested_top(_nested);
+        size_t const st = (size_t)fba_belief_stride(top);
+        std::vector<float> flat(_top * st, 0.0f);
+        for (size_t i = 0; i < _top; ++i) std::copy(blocks[i].begin(), blocks[i].end(), flat.begin() + i * st);
+        std::vector<int32_t> zeros(_top, 0);
+        std::vector<double> w(_top, 1.0 / (double)_top);
+        check(_cuda->ctx(), fba_belief_upload(top, 0, (int64_t)_top, zeros.data(), sid.data(), flat.data(), w.data()),
+              "fba_belief_upload");
+        check(_cuda->ctx(), fba_nested_upload_states(_nested, 0, (int64_t)_top, states.data()), "fba_nested_upload_states");
+    }
+
+    void free(POMDP const& /*d*/) override { release(); }
+
+    // :117-127: the drawn top particle's counts with a state of its bottom filter as domain state
+    State const* sample() const override
+    {
+        int64_t i     = 0;
+        int32_t state = 0;
+        check(_cuda->ctx(), fba_nested_sample(_nested, &_rng, &i, &state), "fba_nested_sample");
+        fba_belief* top = fba_nested_top(_nested);
+        std::vector<float> counts((size_t)fba_belief_stride(top));
+        int32_t sid = 0;
+        check(_cuda->ctx(), fba_belief_download(top, i, 1, nullptr, &sid, counts.data(), nullptr), "fba_belief_download");
+        dropSample();
+        _sample = _cuda->materialise(sid, state, counts);
+        return _sample;
+    }
+
+    void updateEstimation(Action const* a, Observation const* o, POMDP const& /*d*/) override
+    { // :129-193
+        check(_cuda->ctx(), fba_nested_update(_nested, a->index(), o->index(), &_rng, (int64_t)1 << 40, nullptr),
+              "fba_nested_update");
+    }
+
+    void resetDomainStateDistribution(BAPOMDP const& bapomdp) override
+    { // :33-61: fresh start states from the reference's own domain in every bottom filter
+        std::vector<int32_t> states(_top * _bottom);
+        for (auto& s : states) s = startState(bapomdp);
+        check(_cuda->ctx(), fba_nested_upload_states(_nested, 0, (int64_t)_top, states.data()), "fba_nested_upload_states");
+    }
+
+    fba_nested* handle() const { return _nested; }
+
+private:
+    size_t _top, _bottom;
+    int _device;
+    mutable fba_rng _rng;
+    std::unique_ptr<CudaSimulator> _cuda;
+    fba_nested* _nested            = nullptr;
+    mutable BAState const* _sample = nullptr;
+
+    static int32_t startState(BAPOMDP const& bapomdp)
+    {
+        auto s          = bapomdp.sampleDomainState();
+        int32_t const i = s->index();
+        bapomdp.releaseDomainState(s);
+        return i;
+    }
+    void dropSample() const
+    {
+        if (_sample)
+        {
+            _cuda->sim().releaseState(_sample);
+            _sample = nullptr;
+        }
+    }
+    void release()
+    {
+        if (_cuda) dropSample();
+        fba_nested_destroy(_nested);
+        _nested = nullptr;
+        _cuda.reset();
+    }
 };
 
 } // namespace fba_b200

@@ -175,3 +175,63 @@ class StructureIncubatorSampling:
             if b is not None:
                 b.free()
         self._belief = self._fully_connected_belief = self._shadow_belief = None
+
+
+class NestedBelief:
+    """beliefs::bayes_adaptive::NestedBelief (src/beliefs/bayes-adaptive/NestedBelief.cpp): a weighted top
+    filter of count blocks, each with its own flat bottom filter of domain states (fba_nested_*)."""
+
+    def __init__(self, top_filter_size, bottom_filter_size):
+        if top_filter_size < 1 or bottom_filter_size < 1:  # NestedBelief.cpp:19-26
+            raise FbaError(capi.ERR_INVALID, "NestedBelief: cannot initiate with filter size < 1 (top: "
+                           + str(top_filter_size) + ", bottom: " + str(bottom_filter_size) + ")")
+        self._top_filter_size, self._bottom_filter_size = top_filter_size, bottom_filter_size
+        self.h = None
+        self.attempts = None
+
+    def initiate(self, simulator, *, struct_id, counts, states, stride=0):
+        """the top particles the host-side prior produced (structure ids, count blocks) and the bottom filters'
+        domain start states [top, bottom] (NestedBelief.cpp:63-90)"""
+        self.sim, self.ctx, self.L = simulator, simulator.ctx, simulator.L
+        h = C.c_void_p()
+        _check(self.ctx.h, self.L.fba_nested_create(self.ctx.h, simulator.h, self._top_filter_size,
+                                                    self._bottom_filter_size, stride, C.byref(h)))
+        self.h = h
+        self._top = BAImportanceSampling(self._top_filter_size)
+        self._top.sim, self._top.ctx, self._top.L = simulator, self.ctx, self.L
+        self._top.h = C.c_void_p(self.L.fba_nested_top(self.h))     # owned by the nested object
+        self._top._init_explicit(self._top.h, struct_id, counts, np.zeros(self._top_filter_size, np.int32))
+        self.upload_states(states)
+
+    def upload_states(self, states):
+        s = np.ascontiguousarray(states, np.int32).reshape(self._top_filter_size, self._bottom_filter_size)
+        _check(self.ctx.h, self.L.fba_nested_upload_states(self.h, 0, self._top_filter_size, ptr(s)))
+
+    def updateEstimation(self, a, o, rng, max_attempts=1 << 40):
+        """:129-193"""
+        att = np.zeros(self._top_filter_size, np.int64)
+        _check(self.ctx.h, self.L.fba_nested_update(self.h, a, o, C.byref(rng), int(max_attempts), ptr(att)))
+        self.attempts = att
+
+    def resetDomainStateDistribution(self, rng):
+        """:33-61"""
+        _check(self.ctx.h, self.L.fba_nested_reset_domain_states(self.h, C.byref(rng)))
+
+    def sample(self, rng):
+        """:117-127 -> (index of the drawn top particle, its domain state)"""
+        i, s = C.c_int64(0), C.c_int32(0)
+        _check(self.ctx.h, self.L.fba_nested_sample(self.h, C.byref(rng), C.byref(i), C.byref(s)))
+        return i.value, s.value
+
+    def download(self):
+        d = self._top.download()
+        s = np.zeros((self._top_filter_size, self._bottom_filter_size), np.int32)
+        _check(self.ctx.h, self.L.fba_nested_download_states(self.h, 0, self._top_filter_size, ptr(s)))
+        d["states"] = s
+        del d["state"]
+        return d
+
+    def free(self, _simulator=None):
+        if self.h:
+            self.L.fba_nested_destroy(self.h)
+            self.h = None

@@ -372,6 +372,36 @@ int fba_belief_least_likely(fba_belief* b, int64_t n, int64_t* index);
  * flat `belief` (one draw each, particle order), their weights zeroed and the shadow weights normalised. */
 int fba_belief_promote(fba_belief* shadow, fba_belief* belief, double threshold, fba_rng* rng, int64_t* n_promoted);
 
+/* ---- NestedBelief ---------------------------------------------------------------
+ * beliefs::bayes_adaptive::NestedBelief (src/beliefs/bayes-adaptive/NestedBelief.{hpp,cpp}): P(counts) x
+ * P(state | counts) as a weighted TOP filter of n_top count blocks, each with its own flat BOTTOM filter of
+ * n_bottom domain states (the factory uses n and n^2, BABelief.cpp:66-69). Tabular and factored models,
+ * dense storage. */
+typedef struct fba_nested fba_nested;
+int fba_nested_create(fba_ctx* ctx, fba_model* m, int64_t n_top, int64_t n_bottom, int64_t stride, fba_nested** out);
+void fba_nested_destroy(fba_nested* n);
+/* the top filter — a weighted fba_belief for init / upload / download of count blocks, structure ids and
+ * weights (its per-particle domain state is unused, as in the reference, NestedBelief.cpp:84-88) */
+fba_belief* fba_nested_top(fba_nested* n);
+int64_t fba_nested_bottom_size(const fba_nested* n);
+/* the bottom filters of top particles [first_top, first_top + count): count x n_bottom domain states */
+int fba_nested_upload_states(fba_nested* n, int64_t first_top, int64_t count, const int32_t* states);
+int fba_nested_download_states(fba_nested* n, int64_t first_top, int64_t count, int32_t* states);
+/* NestedBelief::resetDomainStateDistribution (NestedBelief.cpp:33-61): fresh start states in every bottom
+ * filter, drawn on the device from the model's start-state sampler */
+int fba_nested_reset_domain_states(fba_nested* n, fba_rng* rng);
+/* NestedBelief::updateEstimation (NestedBelief.cpp:129-193): per top particle, rejection sampling of its
+ * bottom filter (KeepCounts steps on the particle's own counts) until n_bottom states are accepted, every
+ * acceptance adding 1 / n_bottom to the counts it went through BEFORE the next attempt; weight *= 1 /
+ * attempts; then WeightedFilter::normalize. One GPU thread per top particle runs that loop as written.
+ * attempts (n_top, may be NULL) receives the attempts per top particle. A particle that needs more than
+ * max_attempts: FBA_ERR_CAPACITY. REPLAY: top particle i draws from the i-th equal slice of the remaining
+ * words (the reference's single stream is data dependent across particles). */
+int fba_nested_update(fba_nested* n, int32_t action, int32_t observation, fba_rng* rng, int64_t max_attempts,
+                      int64_t* attempts);
+/* NestedBelief::sample (NestedBelief.cpp:117-127): a weighted top draw, then a uniform bottom draw */
+int fba_nested_sample(fba_nested* n, fba_rng* rng, int64_t* top_index, int32_t* state);
+
 /* ---- POMCP with the search tree on the device --------------------------------
  * planners::RBAPOUCT::selectAction (src/planners/bayes-adaptive/RBAPOUCT.cpp:67-153) as waves of
  * `wave` concurrent simulations, each one entirely on the device: root particle from the belief

@@ -943,6 +943,33 @@ int64_t orc_promote(orc_belief* shadow, orc_belief* belief, double threshold, or
     return moved;
 }
 
+int64_t orc_nested_update_particle(const orc_model* m, const uint32_t* t_par, const uint32_t* o_par, float* counts,
+                                   const int32_t* states_in, int32_t* states_out, int64_t n_bottom, int a, int o,
+                                   orc_rng* g, int64_t max_attempts)
+{
+    /* NestedBelief::updateEstimation, the body of its loop over top particles (NestedBelief.cpp:142-187):
+     * rejection sampling of the particle's bottom filter on the particle's own counts, each acceptance
+     * raising the counts it went through by 1 / n_bottom before the next attempt. Returns the attempts
+     * (the particle's weight is multiplied by 1.0 / attempts), -1 if max_attempts / the stream ran out. */
+    float const update_step = (float)(1.0 / (float)n_bottom); /* :133 */
+    int64_t count = 0, accepted = 0;
+    while (accepted < n_bottom)
+    {
+        if (count >= max_attempts || g->overrun) return -1;
+        int32_t const old = states_in[orc_uniform_int(g, (uint32_t)n_bottom)]; /* belief.sample(), FlatFilter.cpp:97-102 */
+        int32_t s         = old;
+        int sim_o, term;
+        orc_step(m, t_par, o_par, counts, &s, a, 0, g, &sim_o, &term); /* KeepCounts, :160 */
+        if (sim_o == o)
+        {
+            states_out[accepted++] = s;
+            orc_increment_counts(m, t_par, o_par, counts, old, a, o, s, update_step); /* :168 */
+        }
+        ++count;
+    }
+    return count;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* rollouts                                                                                    */
 /* ------------------------------------------------------------------------------------------ */

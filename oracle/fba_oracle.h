@@ -188,6 +188,11 @@ void orc_least_likely(const double* w, int64_t n_particles, int64_t n, int64_t* 
 /* StructureIncubatorSampling::reinvigorateBelief (factored/StructureIncubatorSampling.cpp:155-187) */
 int64_t orc_promote(orc_belief* shadow, orc_belief* belief, double threshold, orc_rng* g);
 
+/* NestedBelief::updateEstimation for ONE top particle (NestedBelief.cpp:142-187); returns its attempts */
+int64_t orc_nested_update_particle(const orc_model* m, const uint32_t* t_par, const uint32_t* o_par, float* counts,
+                                   const int32_t* states_in, int32_t* states_out, int64_t n_bottom, int a, int o,
+                                   orc_rng* g, int64_t max_attempts);
+
 /* RBAPOUCT::rollout (RBAPOUCT.cpp:295-323) on a read-only particle (KeepCounts) */
 double orc_rollout(const orc_model* m, const uint32_t* t_par, const uint32_t* o_par,
                    const float* counts, int start_state, int depth, double discount, orc_rng* g);

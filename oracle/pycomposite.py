@@ -70,6 +70,45 @@ class Incubator:
             O.flat_reset_domain_states(self.m, b, rng)
 
 
+class Nested:
+    """beliefs::bayes_adaptive::NestedBelief (src/beliefs/bayes-adaptive/NestedBelief.cpp): `top` is a weighted
+    oracle belief (counts, structures, weights), `states` the bottom filters [n_top, n_bottom]"""
+
+    def __init__(self, model, structs, top, states):
+        self.m, self.st, self.top = model, structs, top
+        self.states = np.ascontiguousarray(states, np.int32).copy()
+        self.attempts = np.zeros(top.N, np.int64)
+
+    def update(self, a, o, rng, slice_words=None):
+        """:129-193. rng: ONE stream consumed particle after particle (the reference's order) — or, with
+        slice_words = w, top particle i draws from words [i w, (i + 1) w) (how the GPU kernel splits it)."""
+        for i in range(self.top.N):
+            g = rng if slice_words is None else O.Rng(rng.words[i * slice_words:(i + 1) * slice_words])
+            sid = int(self.top.struct_id[i])
+            new, n = O.nested_update_particle(self.m, self.st.t_par[sid], self.st.o_par[sid], self.top.counts[i],
+                                              self.states[i], a, o, g)
+            assert n > 0
+            self.states[i] = new
+            self.attempts[i] = n
+            self.top.w[i] *= 1.0 / float(n)                                   # :183
+        total = 0.0
+        for x in self.top.w:                                                  # WeightedFilter::normalize()
+            total += x
+        self.top.total_weight = O.normalize(self.top.w, total)
+
+    def reset(self, rng):
+        """:33-61: n_bottom fresh domain start states per top particle"""
+        for i in range(self.top.N):
+            for j in range(self.states.shape[1]):
+                self.states[i, j] = self.m.sample_start_state(rng)
+
+    def sample(self, rng):
+        """:117-127 -> (top index, domain state)"""
+        i = O.weighted_sample(self.top, rng)
+        j = O.lib().orc_uniform_int(rng.ref(), self.states.shape[1])
+        return int(i), int(self.states[i, j])
+
+
 def belief_from(g, prefix, stride, weighted):
     """an oracle belief from a fixture dump with full counts (<prefix>_counts / _state / _struct_id [/ _w])"""
     counts = g[prefix + "_counts"]

@@ -116,6 +116,8 @@ def lib():
         L.orc_least_likely.argtypes = [vp, i64, i64, vp]
         L.orc_promote.restype = i64
         L.orc_promote.argtypes = [vp, vp, dbl, vp]
+        L.orc_nested_update_particle.restype = i64
+        L.orc_nested_update_particle.argtypes = [vp, vp, vp, vp, vp, vp, i64, C.c_int, C.c_int, vp, i64]
         _lib = L
     return _lib
 
@@ -414,6 +416,18 @@ def least_likely(w, n):
 
 def promote(shadow, belief, threshold, rng):
     return lib().orc_promote(shadow.ref(), belief.ref(), threshold, rng.ref())
+
+
+def nested_update_particle(model, t_par, o_par, counts, states_in, a, o, rng, max_attempts=1 << 40):
+    """NestedBelief::updateEstimation for one top particle, counts updated in place -> (new bottom states, attempts)"""
+    tp = np.ascontiguousarray(t_par, np.uint32)
+    op = np.ascontiguousarray(o_par, np.uint32)
+    si = np.ascontiguousarray(states_in, np.int32)
+    so = np.zeros_like(si)
+    assert counts.dtype == np.float32 and counts.flags.c_contiguous
+    n = lib().orc_nested_update_particle(model.ref(), _p(tp), _p(op), _p(counts), _p(si), _p(so), len(si), a, o,
+                                         rng.ref(), int(max_attempts))
+    return so, int(n)
 
 
 def rollout(model, t_par, o_par, counts, start_state, depth, discount, rng):

@@ -312,6 +312,18 @@ class Ref:
         self.L.ref_incubator_set_shadow_weights.argtypes = [C.c_void_p, C.c_void_p]
         self.L.ref_incubator_set_shadow_weights(self.h, _p(w))
 
+    def nested_states(self, n_top, n_bottom):
+        out = np.zeros((n_top, n_bottom), np.int32)
+        self.L.ref_nested_states.argtypes = [C.c_void_p, C.c_void_p]
+        self.L.ref_nested_states(self.h, _p(out))
+        return out
+
+    def nested_sample(self):
+        out = np.zeros(2, np.int32)
+        self.L.ref_nested_sample.argtypes = [C.c_void_p, C.c_void_p]
+        self.L.ref_nested_sample(self.h, _p(out))
+        return int(out[0]), int(out[1])
+
     def plan_seconds(self, kind, n, planner, sims, reps=3):
         """Seconds per Planner::selectAction with `sims` simulations (empty history)."""
         v = self.L.ref_plan_seconds(self.h, kind, n, planner.encode(), sims, reps)

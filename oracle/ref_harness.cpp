@@ -719,6 +719,28 @@ void ref_filter_weights(void* hv, int filter, double* w, double* total)
 #undef FBA_W
 }
 
+// NestedBelief: the bottom filters' domain states, [n_top][n_bottom] row-major
+void ref_nested_states(void* hv, int* out)
+{
+    auto h  = static_cast<Handle*>(hv);
+    auto& f = h->nested_belief->_filter;
+    long k  = 0;
+    for (size_t i = 0; i < f.size(); ++i)
+        for (auto s : f.particle(i)->particle.second.particles()) out[k++] = s->index();
+}
+
+// NestedBelief::sample (NestedBelief.cpp:117-127): out[0] = index of the drawn top particle, out[1] = its domain state
+void ref_nested_sample(void* hv, int* out)
+{
+    auto h   = static_cast<Handle*>(hv);
+    auto s   = static_cast<BAState const*>(h->nested_belief->sample());
+    auto& f  = h->nested_belief->_filter;
+    out[0]   = -1;
+    for (size_t i = 0; i < f.size(); ++i)
+        if (f.particle(i)->particle.first == s) out[0] = (int)i;
+    out[1] = s->_domain_state->index();
+}
+
 double ref_cheat_likelihood(void* hv)
 {
     return static_cast<Handle*>(hv)->cheat_belief->_likelihood;
@@ -1073,6 +1095,11 @@ int ref_adapter_episodes(void* hv, int kind, long n, char const* planner, int si
                 belief.reset(new RefIncub((size_t)n, k, 0.05));
             else if (kind == 11)
                 belief.reset(new fba_b200::CudaStructureIncubatorSampling((size_t)n, k, 0.05, mut));
+            // NestedBelief sized as the factory does (BABelief.cpp:66-69): n top particles, n * n bottom ones each
+            else if (kind == 12)
+                belief.reset(new RefNested((size_t)n, (size_t)(n * n)));
+            else if (kind == 13)
+                belief.reset(new fba_b200::CudaNestedBelief((size_t)n, (size_t)(n * n)));
             else
                 throw std::string("ref_adapter_episodes: unknown belief kind");
         }

@@ -197,3 +197,111 @@ def test_replace_from_and_argument_checks(env):
         replace_from(dst, [0], dst, [1])
     src.free()
     dst.free()
+
+
+# ---- NestedBelief -----------------------------------------------------------------------------------------
+
+NESTED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "nested.npz")
+
+
+def nested_env(name):
+    import fba_pomdp_b200 as fba
+    import pycomposite as PC
+    import pyoracle as O
+    g = np.load(NESTED)
+    P = name + "/"
+    desc = {k[len(P + "model/"):]: g[k] for k in g.files if k.startswith(P + "model/")}
+    m = O.Model(desc)
+    st = O.Structs(m, g[P + "structs/t_par"], g[P + "structs/o_par"])
+    counts = g[P + "init_counts"]
+    top = O.Belief(counts.shape[0], counts.shape[1], True)
+    top.counts[:] = counts
+    top.struct_id[:] = g[P + "init_struct_id"]
+    top.w[:] = g[P + "init_w"]
+    top.total_weight = float(g[P + "init_total_weight"])
+    oracle = PC.Nested(m, st, top, g[P + "init_states"])
+    ctx = fba.Context(0)
+    sim = fba.BAPOMDP(ctx, desc, g[P + "structs/t_par"], g[P + "structs/o_par"])
+    return fba, O, g, P, oracle, ctx, sim
+
+
+@pytest.mark.parametrize("name", ["tiger", "ftiger"])
+def test_nested_belief_replay(name):
+    """fba_nested_* in REPLAY mode against the oracle's NestedBelief (pinned to the reference's class bit for bit by
+    tests/test_oracle_composite.py). The reference consumes ONE stream particle after particle, a data-dependent
+    amount each; the kernel gives top particle i the i-th equal slice of the stream, and the oracle is fed the same
+    slices: bottom filters, counts, attempts, top weights and _total_weight identical. Resets and sample() consume
+    the reference's own words and reproduce the reference's results."""
+    from fba_pomdp_b200.structure_beliefs import NestedBelief
+    fba, O, g, P, oracle, ctx, sim = nested_env(name)
+    n_top, n_bottom = g[P + "init_states"].shape
+    nb = NestedBelief(n_top, n_bottom)
+    nb.initiate(sim, struct_id=g[P + "init_struct_id"], counts=g[P + "init_counts"], states=g[P + "init_states"])
+    a_, o_, fl_ = g[P + "script/a"], g[P + "script/o"], g[P + "script/flags"]
+    rs = np.random.RandomState(5)
+    done = 0
+    for t in range(len(a_)):
+        if fl_[t] & 2 and t > 0:
+            rng = fba.Rng.replay(g[P + "%d/reset_words" % t])
+            nb.resetDomainStateDistribution(rng)
+            assert rng.exhausted
+            np.testing.assert_array_equal(nb.download()["states"], g[P + "%d/reset_states" % t])
+            oracle.states[:] = g[P + "%d/reset_states" % t]
+        if fl_[t] & 1:
+            continue
+        per = 40000
+        words = rs.randint(0, 1 << 32, size=per * n_top, dtype=np.uint64).astype(np.uint32)
+        rng = fba.Rng.replay(words)
+        nb.updateEstimation(int(a_[t]), int(o_[t]), rng)
+        oracle.update(int(a_[t]), int(o_[t]), O.Rng(words), slice_words=per)
+        d = nb.download()
+        np.testing.assert_array_equal(nb.attempts, oracle.attempts)
+        np.testing.assert_array_equal(d["states"], oracle.states)
+        np.testing.assert_array_equal(d["counts"], oracle.top.counts)
+        np.testing.assert_array_equal(d["w"], oracle.top.w)
+        assert d["total_weight"] == oracle.top.total_weight
+        # sample(): the reference's words on the same weights give the oracle's draw
+        sw = g[P + "%d/sample_words" % t]
+        rng = fba.Rng.replay(sw)
+        assert nb.sample(rng) == oracle.sample(O.Rng(sw))
+        assert rng.exhausted
+        done += 1
+    assert done >= 8
+    nb.free()
+    sim.close()
+    ctx.close()
+
+
+def test_nested_belief_philox_matches_the_oracle_statistically():
+    """PHILOX mode, many top particles from one prior: acceptance counts per top particle and the bottom filters'
+    state histogram after an update agree with the oracle's within 5 standard errors; count blocks gain exactly
+    n_bottom x (1 / n_bottom) per node; weights are normalised."""
+    from fba_pomdp_b200.structure_beliefs import NestedBelief
+    fba, O, g, P, oracle, ctx, sim = nested_env("tiger")
+    n_top, n_bottom = 512, 64
+    counts = np.repeat(g[P + "init_counts"][:1], n_top, 0)
+    states = np.random.RandomState(1).randint(0, 2, size=(n_top, n_bottom)).astype(np.int32)
+    nb = NestedBelief(n_top, n_bottom)
+    nb.initiate(sim, struct_id=np.zeros(n_top, np.int32), counts=counts, states=states)
+    a, o = 2, 0       # listen, hear left
+    nb.updateEstimation(a, o, fba.Rng.philox(77))
+    d = nb.download()
+    # oracle on the same inputs, its own words
+    top = O.Belief(n_top, counts.shape[1], True)
+    top.counts[:] = counts
+    top.total_weight = O.sequential_uniform_total(n_top)
+    import pycomposite as PC
+    ob = PC.Nested(oracle.m, oracle.st, top, states)
+    words = np.random.RandomState(2).randint(0, 1 << 32, size=4_000_000, dtype=np.uint64).astype(np.uint32)
+    ob.update(a, o, O.Rng(words))
+    for got, want in ((nb.attempts, ob.attempts), (d["states"].sum(1), ob.states.sum(1))):
+        se = np.sqrt(got.var(ddof=1) / n_top + want.var(ddof=1) / n_top) + 1e-12
+        assert abs(got.mean() - want.mean()) <= 5 * se, (got.mean(), want.mean(), se)
+    gain = d["counts"].astype(np.float64).sum(1) - counts.astype(np.float64).sum(1)
+    np.testing.assert_allclose(gain, 2.0, rtol=1e-4)          # one transition + one observation cell, 64 x 1/64 each
+    assert abs(d["w"].sum() - 1.0) < 1e-12 and d["total_weight"] == pytest.approx(1.0, abs=1e-12)
+    with pytest.raises(fba.FbaError):
+        nb.updateEstimation(a, o, fba.Rng.philox(78), max_attempts=3)
+    nb.free()
+    sim.close()
+    ctx.close()

@@ -40,6 +40,11 @@ CASES = [
     ("centered-collision-avoidance", dict(size=1, width=3, height=3, factored=True,
                                           structure_prior="match-uniform"), (10, 11), 64, 30),
     ("linear-sysadmin", dict(size=3, factored=True), (10, 11), 64, 20),
+    # NestedBelief, n top particles with n^2 bottom states each as the factory sizes it (BABelief.cpp:66-69)
+    ("episodic-tiger", dict(), (12, 13), 10, 60),
+    ("episodic-factored-tiger", dict(size=3, factored=True, structure_prior="match-uniform"), (12, 13), 8, 40),
+    ("gridworld", dict(size=3), (12, 13), 6, 10),
+    ("episodic-tiger", dict(sampled=True), (12, 13), 10, 60),
     # --dirichlet_sampling_method regular: the adapter reads the mode from the simulator
     ("episodic-tiger", dict(sampled=True), (0, 1), 256, 80),
     ("episodic-factored-tiger", dict(size=3, factored=True, sampled=True), (0, 1), 128, 40),

@@ -132,3 +132,51 @@ def test_least_likely_ties_and_distinct_weights(n, k):
     np.testing.assert_array_equal(O.least_likely(w, k), want)
     # all equal: nothing is strictly lighter, the first k stay
     assert sorted(O.least_likely(np.full(n, 1.0 / n), k).tolist()) == list(range(k))
+
+
+NESTED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "nested.npz")
+
+
+def load_nested(name):
+    g = np.load(NESTED)
+    P = name + "/"
+    desc = {k[len(P + "model/"):]: g[k] for k in g.files if k.startswith(P + "model/")}
+    m = O.Model(desc)
+    st = O.Structs(m, g[P + "structs/t_par"], g[P + "structs/o_par"])
+    counts = g[P + "init_counts"]
+    top = O.Belief(counts.shape[0], counts.shape[1], True)
+    top.counts[:] = counts
+    top.struct_id[:] = g[P + "init_struct_id"]
+    top.w[:] = g[P + "init_w"]
+    top.total_weight = float(g[P + "init_total_weight"])
+    return g, P, m, st, PC.Nested(m, st, top, g[P + "init_states"])
+
+
+@pytest.mark.parametrize("name", ["tiger", "ftiger"])
+def test_nested_belief_equals_the_reference(name):
+    """NestedBelief (NestedBelief.cpp) on a tabular and a factored model: bottom filters, counts (raised by
+    1 / n_bottom per accepted bottom particle), top weights and _total_weight, resets and sample() draws"""
+    g, P, m, st, nb = load_nested(name)
+    a_, o_, fl_ = g[P + "script/a"], g[P + "script/o"], g[P + "script/flags"]
+    done = 0
+    for t in range(len(a_)):
+        if fl_[t] & 2 and t > 0:
+            rng = O.Rng(g[P + "%d/reset_words" % t])
+            nb.reset(rng)
+            assert used(rng)
+            np.testing.assert_array_equal(nb.states, g[P + "%d/reset_states" % t])
+        if fl_[t] & 1:
+            continue
+        rng = O.Rng(g[P + "%d/words" % t])
+        nb.update(int(a_[t]), int(o_[t]), rng)
+        assert used(rng), t
+        np.testing.assert_array_equal(nb.states, g[P + "%d/states" % t])
+        np.testing.assert_array_equal(nb.top.counts, g[P + "%d/counts" % t])
+        np.testing.assert_array_equal(nb.top.w, g[P + "%d/w" % t])
+        assert nb.top.total_weight == float(g[P + "%d/total_weight" % t])
+        rng = O.Rng(g[P + "%d/sample_words" % t])
+        assert nb.sample(rng) == tuple(int(x) for x in g[P + "%d/sample" % t])
+        assert used(rng)
+        done += 1
+    assert done >= 8
+    assert len(np.unique(nb.top.w)) > 1      # the top weights moved apart (1 / attempts differs per particle)
