@@ -250,6 +250,31 @@ class _ParticleBelief:
         _check(self.ctx.h, self.L.fba_belief_replay_history(self.h, len(ln), ptr(ln), ptr(ac), ptr(ob), C.byref(rng),
                                                             int(max_attempts)))
 
+    def sample_state_history(self, method, episode_len, actions, observations, rng, state_prior=None,
+                             max_attempts=1_000_000):
+        """MHwithinGibbs' sampleStateHistory (MHwithinGibbs.cpp:38-232) for every particle: method "msg" (backward
+        messages + forward sampling; needs state_prior, S floats) or "rs" (rejection sampling) ->
+        states [N, n_steps + n_episodes]; counts untouched"""
+        ln = np.ascontiguousarray(episode_len, np.int32)
+        ac = np.ascontiguousarray(actions, np.int32)
+        ob = np.ascontiguousarray(observations, np.int32)
+        sp = None if state_prior is None else np.ascontiguousarray(state_prior, np.float32)
+        out = np.zeros((self.size(), int(ln.sum()) + len(ln)), np.int32)
+        _check(self.ctx.h, self.L.fba_belief_sample_state_history(
+            self.h, {"msg": 0, "rs": 1}[method], len(ln), ptr(ln), ptr(ac), ptr(ob), ptr(sp), C.byref(rng),
+            int(max_attempts), ptr(out)))
+        return out
+
+    def add_history_counts(self, episode_len, actions, observations, states):
+        """MHwithinGibbs::computePosteriorCounts (MHwithinGibbs.cpp:397-436): +1 per transition of the state
+        history — states [N, L] (one history per particle) or [L] (one history shared by all particles)"""
+        ln = np.ascontiguousarray(episode_len, np.int32)
+        ac = np.ascontiguousarray(actions, np.int32)
+        ob = np.ascontiguousarray(observations, np.int32)
+        st = np.ascontiguousarray(states, np.int32)
+        _check(self.ctx.h, self.L.fba_belief_add_history_counts(self.h, len(ln), ptr(ln), ptr(ac), ptr(ob), ptr(st),
+                                                                int(st.ndim == 1)))
+
     def assign_from(self, first, src, src_index):
         """particles src[src_index[j]] -> self[first + j] (MHNIPS2018.cpp:241-246: accepted proposals)"""
         idx = np.ascontiguousarray(src_index, np.int64)

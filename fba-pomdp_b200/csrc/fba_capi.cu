@@ -2383,6 +2383,179 @@ extern "C" int fba_belief_assign_from(fba_belief* dst, int64_t first, fba_belief
     return FBA_OK;
 }
 
+// ---- MHwithinGibbs: state histories and their posterior counts -------------------------------------------
+
+namespace {
+// the (action, observation) history on the device + its checks, shared by the calls below
+struct DeviceHistory
+{
+    DevTmp<int> len, act, obs;
+    HistoryArgs H{};
+    long long total = 0;
+    int stage(fba_ctx* ctx, DevModel const& D, int32_t n_episodes, const int32_t* episode_len, const int32_t* actions,
+              const int32_t* observations, bool need_steps)
+    {
+        int max_len = 1;
+        for (int e = 0; e < n_episodes; ++e)
+        {
+            REQUIRE(ctx, episode_len[e] >= (need_steps ? 1 : 0), "history: an episode without steps");
+            total += episode_len[e];
+            max_len = std::max(max_len, (int)episode_len[e]);
+        }
+        for (long long k = 0; k < total; ++k)
+        {
+            REQUIRE(ctx, actions[k] >= 0 && actions[k] < D.A, "history: action out of range");
+            REQUIRE(ctx, observations[k] >= 0 && observations[k] < D.O, "history: observation out of range");
+        }
+        CU(ctx, cudaMalloc(&len, std::max(1, (int)n_episodes) * sizeof(int)));
+        CU(ctx, cudaMalloc(&act, std::max(1ll, total) * sizeof(int)));
+        CU(ctx, cudaMalloc(&obs, std::max(1ll, total) * sizeof(int)));
+        if (n_episodes)
+            CU(ctx, cudaMemcpyAsync(len, episode_len, n_episodes * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        if (total)
+        {
+            CU(ctx, cudaMemcpyAsync(act, actions, total * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            CU(ctx, cudaMemcpyAsync(obs, observations, total * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        }
+        H.n_episodes = n_episodes, H.max_len = max_len;
+        H.episode_len = len, H.actions = act, H.observations = obs;
+        H.max_attempts = 1;
+        return FBA_OK;
+    }
+};
+} // namespace
+
+extern "C" int fba_belief_sample_state_history(fba_belief* b, int32_t method, int32_t n_episodes,
+                                               const int32_t* episode_len, const int32_t* actions,
+                                               const int32_t* observations, const float* state_prior, fba_rng* rng,
+                                               int64_t max_attempts, int32_t* states)
+{
+    if (!b || !rng || !states || n_episodes < 1 || !episode_len || !actions || !observations) return FBA_ERR_INVALID;
+    fba_ctx* ctx      = b->ctx;
+    DevModel const& D = b->m->dev;
+    REQUIRE(ctx, b->delta_cap == 0, "sample_state_history: dense storage only");
+    REQUIRE(ctx, method == 0 || method == 1, "sample_state_history: method 0 (messages) or 1 (rejection sampling)");
+    REQUIRE(ctx, !D.sampled, "sample_state_history: expected-Dirichlet models only (MHwithinGibbs.cpp:223-225)");
+    REQUIRE(ctx, method == 1 || state_prior, "sample_state_history: the message method needs the domain state prior");
+    REQUIRE(ctx, max_attempts >= 1, "sample_state_history: max_attempts must be at least 1");
+    CU(ctx, cudaSetDevice(ctx->device));
+    DeviceHistory h;
+    int rc;
+    if ((rc = h.stage(ctx, D, n_episodes, episode_len, actions, observations, true))) return rc;
+    h.H.max_attempts         = max_attempts;
+    long long const out_len  = h.total + n_episodes;
+    DevTmp<int> d_out, d_failed;
+    CU(ctx, cudaMalloc(&d_out, (size_t)b->N * out_len * sizeof(int)));
+    CU(ctx, cudaMalloc(&d_failed, sizeof(int)));
+    CU(ctx, cudaMemsetAsync(d_failed, 0, sizeof(int), ctx->stream));
+    bool const replay   = rng->mode == FBA_RNG_REPLAY;
+    long long const per = replay ? (rng->n_words - rng->cursor) / b->N : 0;
+    RngArgs ra;
+    if (replay)
+    { // every particle draws from its own equal slice of the remaining words
+        REQUIRE(ctx, per >= 1, "sample_state_history: the replay stream is shorter than one word per particle");
+        if ((rc = stage_words(ctx, rng, per * b->N))) return rc;
+        ra = replay_args(ctx, per * b->N, per, false);
+    } else
+        ra = philox_args(rng);
+    if ((rc = clear_flag(ctx))) return rc;
+    if (method == 1)
+    {
+        bool const lr = b->m->long_rows;
+        if (replay && lr)
+            LAUNCH(ctx, (k_state_history_rs<true, true>), blocks_for(b->N, 32), 32, D, b->counts[b->cur], b->stride,
+                   b->sid[b->cur], b->N, h.H, ra, (int*)d_out, out_len, (int*)d_failed, ctx->d_flag);
+        else if (replay)
+            LAUNCH(ctx, (k_state_history_rs<true, false>), blocks_for(b->N, 32), 32, D, b->counts[b->cur], b->stride,
+                   b->sid[b->cur], b->N, h.H, ra, (int*)d_out, out_len, (int*)d_failed, ctx->d_flag);
+        else if (lr)
+            LAUNCH(ctx, (k_state_history_rs<false, true>), blocks_for(b->N, 32), 32, D, b->counts[b->cur], b->stride,
+                   b->sid[b->cur], b->N, h.H, ra, (int*)d_out, out_len, (int*)d_failed, ctx->d_flag);
+        else
+            LAUNCH(ctx, (k_state_history_rs<false, false>), blocks_for(b->N, 32), 32, D, b->counts[b->cur], b->stride,
+                   b->sid[b->cur], b->N, h.H, ra, (int*)d_out, out_len, (int*)d_failed, ctx->d_flag);
+    } else
+    {
+        // flattenT / flattenO of every particle: A S S + A O S floats each, and (max_len + 2) S doubles of messages
+        double const bytes = (double)b->N * ((double)D.A * D.S * ((double)D.S + D.O) * 4.0 + (h.H.max_len + 2.0) * D.S * 8.0);
+        REQUIRE(ctx, bytes < 64e9, "sample_state_history: the flattened models of these particles do not fit (N A S (S + O) floats)");
+        std::vector<unsigned char> used((size_t)D.A, 0);
+        for (long long k = 0; k < h.total; ++k) used[(size_t)actions[k]] = 1;
+        DevTmp<unsigned char> d_used;
+        DevTmp<float> d_T, d_O, d_prior;
+        DevTmp<double> d_msg;
+        CU(ctx, cudaMalloc(&d_used, (size_t)D.A));
+        CU(ctx, cudaMalloc(&d_T, (size_t)b->N * D.A * D.S * D.S * sizeof(float)));
+        CU(ctx, cudaMalloc(&d_O, (size_t)b->N * D.A * D.O * D.S * sizeof(float)));
+        CU(ctx, cudaMalloc(&d_prior, (size_t)D.S * sizeof(float)));
+        CU(ctx, cudaMalloc(&d_msg, (size_t)b->N * (h.H.max_len + 2) * D.S * sizeof(double)));
+        CU(ctx, cudaMemcpyAsync(d_used, used.data(), used.size(), cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(d_prior, state_prior, (size_t)D.S * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        dim3 const grid((unsigned)std::min<long long>(blocks_for((long long)D.A * D.S), 4 * ctx->sm_count), (unsigned)b->N);
+        LAUNCH(ctx, k_flatten_model, grid, kThreads, D, b->counts[b->cur], b->stride, b->sid[b->cur],
+               (const unsigned char*)d_used, (float*)d_T, (float*)d_O);
+        if (replay)
+            LAUNCH(ctx, (k_state_history_msg<true>), (int)b->N, kThreads, D, b->N, h.H, (const float*)d_T, (const float*)d_O,
+                   (const float*)d_prior, (double*)d_msg, ra, (int*)d_out, out_len, ctx->d_flag);
+        else
+            LAUNCH(ctx, (k_state_history_msg<false>), (int)b->N, kThreads, D, b->N, h.H, (const float*)d_T,
+                   (const float*)d_O, (const float*)d_prior, (double*)d_msg, ra, (int*)d_out, out_len, ctx->d_flag);
+        CU(ctx, cudaStreamSynchronize(ctx->stream)); // the scratch dies with this scope
+    }
+    CU(ctx, cudaMemcpyAsync(ctx->h_flag, d_failed, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(states, d_out, (size_t)b->N * out_len * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (*ctx->h_flag)
+    {
+        ctx->err = "sample_state_history: a particle needed more than max_attempts episode attempts (or ran out of "
+                   "replay words): its model gives the observed history almost no probability";
+        return replay ? FBA_ERR_RNG_UNDERRUN : FBA_ERR_CAPACITY;
+    }
+    if (replay)
+    {
+        if ((rc = check_flag(ctx))) return rc;
+        rng->cursor += per * b->N;
+    }
+    return FBA_OK;
+}
+
+extern "C" int fba_belief_add_history_counts(fba_belief* b, int32_t n_episodes, const int32_t* episode_len,
+                                             const int32_t* actions, const int32_t* observations,
+                                             const int32_t* states, int32_t shared)
+{
+    if (!b || !states || n_episodes < 1 || !episode_len || !actions || !observations) return FBA_ERR_INVALID;
+    fba_ctx* ctx      = b->ctx;
+    DevModel const& D = b->m->dev;
+    REQUIRE(ctx, b->delta_cap == 0, "add_history_counts: dense storage only");
+    CU(ctx, cudaSetDevice(ctx->device));
+    DeviceHistory h;
+    int rc;
+    if ((rc = h.stage(ctx, D, n_episodes, episode_len, actions, observations, false))) return rc;
+    if (h.total == 0) return FBA_OK;
+    long long const seq_len = h.total + n_episodes, n_seq = shared ? 1 : b->N;
+    for (long long k = 0; k < n_seq * seq_len; ++k)
+        REQUIRE(ctx, states[k] >= 0 && states[k] < D.S, "add_history_counts: domain state out of range");
+    std::vector<int> pos((size_t)h.total);
+    { // step t of the flattened history sits at states[pos[t]], its successor right after
+        long long t = 0, p = 0;
+        for (int e = 0; e < n_episodes; ++e)
+        {
+            for (int k = 0; k < episode_len[e]; ++k) pos[(size_t)t++] = (int)(p + k);
+            p += episode_len[e] + 1;
+        }
+    }
+    DevTmp<int> d_pos, d_states;
+    CU(ctx, cudaMalloc(&d_pos, (size_t)h.total * sizeof(int)));
+    CU(ctx, cudaMalloc(&d_states, (size_t)n_seq * seq_len * sizeof(int)));
+    CU(ctx, cudaMemcpyAsync(d_pos, pos.data(), (size_t)h.total * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(d_states, states, (size_t)n_seq * seq_len * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, k_add_history_counts, blocks_for(b->N * h.total), kThreads, D, b->counts[b->cur], b->stride, b->sid[b->cur],
+           b->N, (int)h.total, (const int*)h.act, (const int*)h.obs, (const int*)d_pos, (const int*)d_states,
+           shared ? 0ll : seq_len);
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return FBA_OK;
+}
+
 // ---- single particles between the filters of the composite beliefs -------------------------------------
 
 static int replace_core(fba_belief* dst, const std::vector<int>& dst_index, fba_belief* src,

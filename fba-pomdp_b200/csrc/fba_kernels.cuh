@@ -2767,4 +2767,239 @@ __global__ void __launch_bounds__(kThreads)
     if (g.overrun) *overrun = 1;
 }
 
+// ------------------------------------------------------------------------------------------------
+// MHwithinGibbs (src/beliefs/bayes-adaptive/factored/MHwithinGibbs.cpp): state histories conditioned on a
+// model and the (action, observation) history, and the posterior counts of a state history.
+// ------------------------------------------------------------------------------------------------
+
+// rejectionSampleStateHistory (:38-94), one thread per particle (model): per episode a start state, then s'
+// and o from the particle's counts (expected Dirichlets, counts untouched) step after step; the first wrong
+// observation abandons the attempt. states_out: per particle (n_steps + n_episodes) states.
+template<bool REPLAY, bool LONG>
+__global__ void __launch_bounds__(kThreads)
+    k_state_history_rs(DevModel M, const float* __restrict__ counts, long long stride, const int* __restrict__ sid,
+                       long long N, HistoryArgs H, RngArgs ra, int* __restrict__ states_out, long long out_stride,
+                       int* __restrict__ failed, int* __restrict__ overrun)
+{
+    long long const i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    auto g            = RngOf<REPLAY>::make(ra, i);
+    float* c          = const_cast<float*>(counts) + i * stride; // STEP_KEEP never writes
+    const Node* nodes = M.nodes + (long long)sid[i] * M.A * M.J;
+    int* out          = states_out + i * out_stride;
+    long long attempts = 0;
+    int first = 0, pos = 0;
+    for (int e = 0; e < H.n_episodes; ++e)
+    {
+        int const len = H.episode_len[e];
+        for (;;)
+        {
+            if (++attempts > H.max_attempts || g.overrun)
+            {
+                *failed = 1;
+                return;
+            }
+            int s    = sample_start_state(M, g);
+            out[pos] = s;
+            int t    = 0;
+            for (; t < len; ++t)
+            {
+                int o;
+                Feat x2;
+                s = hyper_step<STEP_KEEP, decltype(g), false, LONG, false>(
+                    M, nodes + (long long)H.actions[first + t] * M.J, c, s, g, o, x2, nullptr);
+                if (o != H.observations[first + t]) break;
+                out[pos + 1 + t] = s;
+            }
+            if (t == len) break;
+        }
+        first += len;
+        pos += len + 1;
+    }
+    if (g.overrun) *overrun = 1;
+}
+
+// BABNModel::flattenT / flattenO (BABNModel.cpp:89-178) of every particle into scratch, laid out for the
+// message passes below: Tt[a][s'][s] (the threads of a pass run over s) and Ot[a][o][s]. Every entry starts
+// at 1.0f and is multiplied, feature after feature, by that node's expected multinomial (float sum, float
+// divide). Only the actions that occur in the history are flattened (used[a]).
+__global__ void __launch_bounds__(kThreads)
+    k_flatten_model(DevModel M, const float* __restrict__ counts, long long stride, const int* __restrict__ sid,
+                    const unsigned char* __restrict__ used, float* __restrict__ Tt_all, float* __restrict__ Ot_all)
+{
+    long long const p = blockIdx.y;
+    const float* c    = counts + p * stride;
+    float* Tt         = Tt_all + p * (long long)M.A * M.S * M.S;
+    float* Ot         = Ot_all + p * (long long)M.A * M.O * M.S;
+    bool const single_s = (M.FS == 1), single_o = (M.FO == 1);
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < (long long)M.A * M.S;
+         k += (long long)gridDim.x * blockDim.x)
+    {
+        int const a = (int)(k / M.S), s = (int)(k - (long long)a * M.S);
+        if (!used[a]) continue;
+        const Node* nodes = M.nodes + ((long long)sid[p] * M.A + a) * M.J;
+        Feat const x      = decode(s, M.step_s, M.FS, M.pow2_s, M.shift_s);
+        for (int s2 = 0; s2 < M.S; ++s2)
+        {
+            Feat const x2 = decode(s2, M.step_s, M.FS, M.pow2_s, M.shift_s);
+            float pr      = 1.0f;
+            for (int f = 0; f < M.FS; ++f)
+            {
+                Node const nd   = nodes[f];
+                int const range = M.feat_s[f];
+                pr = __fmul_rn(pr, expected_mult_at(c + nd.off + parent_config(M, nd.par, x) * range, range,
+                                                    x2.get(f, single_s)));
+            }
+            Tt[((long long)a * M.S + s2) * M.S + s] = pr;
+        }
+        for (int o = 0; o < M.O; ++o)
+        { // the observation's parents are the features of the state it is made in
+            Feat const of = decode(o, M.step_o, M.FO, M.pow2_o, M.shift_o);
+            float pr      = 1.0f;
+            for (int q = 0; q < M.FO; ++q)
+            {
+                Node const nd   = nodes[M.FS + q];
+                int const range = M.feat_o[q];
+                pr = __fmul_rn(pr, expected_mult_at(c + nd.off + parent_config(M, nd.par, x) * range, range,
+                                                    of.get(q, single_o)));
+            }
+            Ot[((long long)a * M.O + o) * M.S + s] = pr;
+        }
+    }
+}
+
+// rnd::sample::Dir::sampleFromMult<double> (random.hpp:93-115)
+template<class R>
+__device__ __forceinline__ int sample_from_mult_d(const double* mult, int n, double total, R& g)
+{
+    double const p = __dmul_rn(draw_u(g), total);
+    double sum     = mult[0];
+    for (int i = 1; i < n; ++i)
+    {
+        if (p < sum) return i - 1;
+        sum = __dadd_rn(sum, mult[i]);
+    }
+    return n - 1;
+}
+
+// msgSampleStateHistory (:96-213), one CTA per particle. Per episode: the backward pass — message[t][s] =
+// sum_s' T[s][a_t][s'] message[t+1][s'] (a sequential double sum per state, as std::inner_product runs it; one
+// thread per state), times the observation factor (or the state prior at t = 0), normalised by the SEQUENTIAL
+// sum over states (thread 0) — then the forward pass: s_0 from message[0], s_t+1 from T[s_t][a_t][.] *
+// message[t+1][.] with its sequential total (thread 0 draws). msg: per particle (max_len + 2) x S doubles of
+// scratch (the last row holds the forward pass's products).
+template<bool REPLAY>
+__global__ void __launch_bounds__(kThreads)
+    k_state_history_msg(DevModel M, long long N, HistoryArgs H, const float* __restrict__ Tt_all,
+                        const float* __restrict__ Ot_all, const float* __restrict__ state_prior,
+                        double* __restrict__ msg_all, RngArgs ra, int* __restrict__ states_out, long long out_stride,
+                        int* __restrict__ overrun)
+{
+    long long const p = blockIdx.x;
+    if (p >= N) return;
+    int const S     = M.S;
+    const float* Tt = Tt_all + p * (long long)M.A * S * S;
+    const float* Ot = Ot_all + p * (long long)M.A * M.O * S;
+    double* msg     = msg_all + p * (long long)(H.max_len + 2) * S;
+    double* probs   = msg + (long long)(H.max_len + 1) * S;
+    int* out        = states_out + p * out_stride;
+    auto g          = RngOf<REPLAY>::make(ra, p);
+    __shared__ double sh_tot;
+    __shared__ int sh_state;
+    int first = 0, pos = 0;
+    for (int e = 0; e < H.n_episodes; ++e)
+    {
+        int const len  = H.episode_len[e];
+        const int* act = H.actions + first;
+        const int* obs = H.observations + first;
+        for (int s = threadIdx.x; s < S; s += blockDim.x)
+            msg[(long long)len * S + s] = (double)Ot[((long long)act[len - 1] * M.O + obs[len - 1]) * S + s];
+        __syncthreads();
+        for (int step = len - 1; step >= 0; --step)
+        {
+            const float* Ta    = Tt + (long long)act[step] * S * S;
+            const double* next = msg + (long long)(step + 1) * S;
+            for (int s = threadIdx.x; s < S; s += blockDim.x)
+            {
+                double acc = 0.0;
+                for (int s2 = 0; s2 < S; ++s2) acc = __dadd_rn(acc, __dmul_rn((double)Ta[(long long)s2 * S + s], next[s2]));
+                float const factor = (step != 0) ? Ot[((long long)act[step - 1] * M.O + obs[step - 1]) * S + s]
+                                                 : state_prior[s];
+                msg[(long long)step * S + s] = __dmul_rn(acc, (double)factor);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0)
+            {
+                double tot = 0.0;
+                for (int s = 0; s < S; ++s) tot = __dadd_rn(tot, msg[(long long)step * S + s]);
+                sh_tot = tot;
+            }
+            __syncthreads();
+            double const tot = sh_tot;
+            for (int s = threadIdx.x; s < S; s += blockDim.x)
+                msg[(long long)step * S + s] = __ddiv_rn(msg[(long long)step * S + s], tot);
+            __syncthreads();
+        }
+        if (threadIdx.x == 0)
+        {
+            sh_state   = sample_from_mult_d(msg, S, 1.0, g);
+            out[pos++] = sh_state;
+        }
+        __syncthreads();
+        for (int step = 0; step < len; ++step)
+        {
+            int const state    = sh_state;
+            const float* Ta    = Tt + (long long)act[step] * S * S;
+            const double* next = msg + (long long)(step + 1) * S;
+            for (int s2 = threadIdx.x; s2 < S; s2 += blockDim.x)
+                probs[s2] = __dmul_rn((double)Ta[(long long)s2 * S + state], next[s2]);
+            __syncthreads();
+            if (threadIdx.x == 0)
+            {
+                double tot = 0.0;
+                for (int s2 = 0; s2 < S; ++s2) tot = __dadd_rn(tot, probs[s2]);
+                sh_state   = sample_from_mult_d(probs, S, tot, g);
+                out[pos++] = sh_state;
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x != 0) pos += len + 1;
+        first += len;
+    }
+    if (threadIdx.x == 0 && g.overrun) *overrun = 1;
+}
+
+// MHwithinGibbs::computePosteriorCounts (:397-436): incrementCountsOf(s_t, a_t, o_t, s_t+1) for every step of
+// every particle's state history, one thread per (particle, step). Every increment is exactly +1.0f, so the
+// atomic adds give the reference's sequence of float sums whatever order they land in.
+__global__ void __launch_bounds__(kThreads)
+    k_add_history_counts(DevModel M, float* counts, long long stride, const int* __restrict__ sid, long long N,
+                         int n_steps, const int* __restrict__ step_action, const int* __restrict__ step_obs,
+                         const int* __restrict__ step_pos, const int* __restrict__ states, long long states_stride)
+{
+    long long const k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= N * n_steps) return;
+    long long const i = k / n_steps;
+    int const t       = (int)(k - i * n_steps);
+    const int* seq    = states + i * states_stride; // states_stride == 0: one history shared by all particles
+    int const s = seq[step_pos[t]], s2 = seq[step_pos[t] + 1], a = step_action[t], o = step_obs[t];
+    const Node* nodes = M.nodes + ((long long)sid[i] * M.A + a) * M.J;
+    float* c          = counts + i * stride;
+    bool const single_s = (M.FS == 1), single_o = (M.FO == 1);
+    Feat const x  = decode(s, M.step_s, M.FS, M.pow2_s, M.shift_s);
+    Feat const x2 = decode(s2, M.step_s, M.FS, M.pow2_s, M.shift_s);
+    Feat const of = decode(o, M.step_o, M.FO, M.pow2_o, M.shift_o);
+    for (int f = 0; f < M.FS; ++f)
+    {
+        Node const nd = nodes[f];
+        atomicAdd(c + nd.off + parent_config(M, nd.par, x) * M.feat_s[f] + x2.get(f, single_s), 1.0f);
+    }
+    Feat const& xo = M.tabular ? x2 : x; // BABNModel.cpp:366,380: the observation CPTs are indexed by the OLD state
+    for (int q = 0; q < M.FO; ++q)
+    {
+        Node const nd = nodes[M.FS + q];
+        atomicAdd(c + nd.off + parent_config(M, nd.par, xo) * M.feat_o[q] + of.get(q, single_o), 1.0f);
+    }
+}
+
 } // namespace fba

@@ -239,6 +239,268 @@ private:
     }
 };
 
+// Drop-in for beliefs::bayes_adaptive::factored::MHwithinGibbs
+// (src/beliefs/bayes-adaptive/factored/MHwithinGibbs.{hpp,cpp}): importance sampling as above, and when the log
+// likelihood drops below the threshold a Gibbs chain over (state history, model) rebuilds the belief
+// (reinvigorate, MHwithinGibbs.cpp:334-395):
+//   * p(states | model): fba_belief_sample_state_history — backward messages + forward sampling over the
+//     flattened model (MSG), or rejection sampling (RS) — on the GPU;
+//   * p(model | states): Metropolis-Hastings over structures — the domain's mutate and the prior model of the
+//     proposed structure by the reference's own code on the host, computePosteriorCounts
+//     (fba_belief_add_history_counts) and BABNModel::LogBDScore (fba_belief_log_bd_score) on the GPU.
+// Between two acceptances the reference's proposals are independent draws from the same structure against the
+// same state history, so they are evaluated in BATCHES; the first accepted one (in proposal order) is taken and
+// the rest of its batch dropped — the chain has the reference's distribution, including its detail that the new
+// state history is sampled from the model BEFORE the move (:377-378).
+class CudaMHwithinGibbs : public CudaParticleBelief
+{
+public:
+    enum SAMPLE_STATE_HISTORY_TYPE { RS, MSG }; // as MHwithinGibbs.hpp
+
+    CudaMHwithinGibbs(size_t size, double ll_threshold, SAMPLE_STATE_HISTORY_TYPE type, uint64_t seed = 42,
+                      int device = 0) :
+            CudaParticleBelief(size, true, seed, device), _ll_threshold(ll_threshold), _type(type)
+    {
+        if (size < 1) throw "MHwithinGibbs::cannot initiate MH with size 0"; // as :242-245
+        if (ll_threshold >= 0)                                                // as :247-251
+            throw("MHwithinGibbs::cannot initiate with threshold >= 0 (is:" + std::to_string(ll_threshold) + ")");
+    }
+
+    void initiate(POMDP const& d) override
+    {
+        CudaParticleBelief::initiate(d);
+        _history.assign(1, {});
+        _log_likelihood = 0.0;
+        _chains = _proposals = 0;
+    }
+
+    // :257-272: a fresh domain state for every particle where it is, and a new episode in the history
+    void resetDomainStateDistribution(BAPOMDP const& bapomdp) override
+    {
+        std::vector<int32_t> state(_n);
+        for (size_t i = 0; i < _n; ++i)
+        {
+            auto s   = bapomdp.sampleDomainState();
+            state[i] = s->index();
+            bapomdp.releaseDomainState(s);
+        }
+        check(_cuda->ctx(), fba_belief_upload(_belief, 0, (int64_t)_n, state.data(), nullptr, nullptr, nullptr),
+              "fba_belief_upload");
+        if (!_history.back().empty()) _history.emplace_back();
+    }
+
+    void updateEstimation(Action const* a, Observation const* o, POMDP const& d) override
+    { // :310-327
+        double lik = 0.0;
+        check(_cuda->ctx(), fba_belief_update_estimation(_belief, a->index(), o->index(), &_rng, &lik),
+              "fba_belief_update_estimation");
+        _log_likelihood += std::log(lik);
+        _history.back().emplace_back(a->index(), o->index());
+        if (_log_likelihood < _ll_threshold) reinvigorate(d);
+    }
+
+    double logLikelihood() const { return _log_likelihood; }
+    size_t chains() const { return _chains; }
+    size_t proposals() const { return _proposals; }
+
+protected:
+    size_t minimumStride(POMDP const& d) const override
+    {
+        auto const& fbapomdp = dynamic_cast<::bayes_adaptive::factored::FBAPOMDP const&>(d);
+        auto p               = static_cast<BAState const*>(fbapomdp.sampleFullyConnectedState());
+        std::vector<float> block;
+        _cuda->describe(p, &block);
+        d.releaseState(p);
+        return block.size();
+    }
+
+private:
+    double _ll_threshold;
+    SAMPLE_STATE_HISTORY_TYPE _type;
+    double _log_likelihood = 0.0;
+    std::vector<std::vector<std::pair<int32_t, int32_t>>> _history;
+    size_t _chains = 0, _proposals = 0;
+
+    struct Scratch // beliefs that die with the call, whichever way it ends
+    {
+        std::vector<fba_belief*> all;
+        ~Scratch()
+        {
+            for (auto b : all) fba_belief_destroy(b);
+        }
+        void drop(fba_belief* b)
+        {
+            for (auto& x : all)
+                if (x == b) x = nullptr;
+            fba_belief_destroy(b);
+        }
+        void keep(fba_belief* b)
+        {
+            for (auto& x : all)
+                if (x == b) x = nullptr;
+        }
+    };
+
+    void reinvigorate(POMDP const& d)
+    {
+        using Structure      = ::bayes_adaptive::factored::BABNModel::Structure;
+        auto const& fbapomdp = dynamic_cast<::bayes_adaptive::factored::FBAPOMDP const&>(d);
+        fba_ctx* ctx         = _cuda->ctx();
+        int64_t const N      = (int64_t)_n;
+        int64_t const stride = fba_belief_stride(_belief);
+        Scratch tmp;
+
+        // the history, flattened; the prior of s_0
+        std::vector<int32_t> len, act, obs;
+        for (auto const& ep : _history)
+        {
+            len.push_back((int32_t)ep.size());
+            for (auto const& st : ep) act.push_back(st.first), obs.push_back(st.second);
+        }
+        int64_t const L = (int64_t)act.size() + (int64_t)len.size();
+        std::vector<float> state_prior((size_t)_cuda->S());
+        for (int s = 0; s < _cuda->S(); ++s) state_prior[(size_t)s] = fbapomdp.domainStatePrior()->prob((size_t)s);
+
+        // prior models by the reference's own prior, cached per structure id (as CudaMHNIPS2018)
+        std::vector<int32_t> prior_sid;
+        std::vector<float> prior_flat, block;
+        std::map<int32_t, int32_t> prior_of;
+        std::map<int32_t, Structure> structure_of;
+        auto priorOf = [&](int32_t id, Structure const& st) {
+            auto it = prior_of.find(id);
+            if (it != prior_of.end()) return it->second;
+            auto model        = fbapomdp.prior()->computePriorModel(st);
+            int32_t const got = _cuda->describeModel(&model, &block);
+            if (got != id) throw std::string("CudaMHwithinGibbs: the prior model of a structure has another structure");
+            if ((int64_t)block.size() > stride) throw std::string("CudaMHwithinGibbs: structure larger than the particle blocks");
+            int32_t const k = (int32_t)prior_sid.size();
+            prior_sid.push_back(id);
+            prior_flat.resize((size_t)(k + 1) * stride, 0.0f);
+            std::copy(block.begin(), block.end(), prior_flat.begin() + (size_t)k * stride);
+            prior_of.emplace(id, k);
+            return k;
+        };
+        auto structureOf = [&](int32_t id) -> Structure const& {
+            auto it = structure_of.find(id);
+            if (it == structure_of.end()) it = structure_of.emplace(id, _cuda->structureOf(id)).first;
+            return it->second;
+        };
+        auto priorBelief = [&](std::vector<int32_t> const& proto) {
+            fba_belief* b = nullptr;
+            check(ctx, fba_belief_create(ctx, _cuda->model(), (int64_t)proto.size(), stride, 0, &b), "fba_belief_create");
+            tmp.all.push_back(b);
+            std::vector<int32_t> zeros(proto.size(), 0);
+            check(ctx, fba_belief_init(b, (int32_t)prior_sid.size(), prior_sid.data(), prior_flat.data(), proto.data(),
+                                       zeros.data()),
+                  "fba_belief_init");
+            return b;
+        };
+        auto sampleHistory = [&](fba_belief* model, std::vector<int32_t>& seq) { // sampleStateHistory, :215-232
+            seq.resize((size_t)L);
+            check(ctx,
+                  fba_belief_sample_state_history(model, _type == MSG ? 0 : 1, (int32_t)len.size(), len.data(), act.data(),
+                                                  obs.data(), state_prior.data(), &_rng, 1000000, seq.data()),
+                  "fba_belief_sample_state_history");
+        };
+        auto posterior = [&](int32_t proto, std::vector<int32_t> const& seq) { // computePosteriorCounts on ONE model
+            fba_belief* b = priorBelief({proto});
+            check(ctx, fba_belief_add_history_counts(b, (int32_t)len.size(), len.data(), act.data(), obs.data(), seq.data(), 1),
+                  "fba_belief_add_history_counts");
+            return b;
+        };
+        auto scoreOf = [&](fba_belief* model, int32_t proto) { // model.LogBDScore(prior_model)
+            fba_belief* pb = priorBelief({proto});
+            double sc      = 0.0;
+            check(ctx, fba_belief_log_bd_score(model, pb, &sc), "fba_belief_log_bd_score");
+            tmp.drop(pb);
+            return sc;
+        };
+
+        // :344-352: the first complete sample, from a particle of the old belief
+        int64_t i0 = 0;
+        check(ctx, fba_belief_sample(_belief, &_rng, &i0), "fba_belief_sample");
+        int32_t cur_sid = 0;
+        {
+            std::vector<float> counts((size_t)stride);
+            int32_t st0 = 0;
+            check(ctx, fba_belief_download(_belief, i0, 1, &st0, &cur_sid, counts.data(), nullptr), "fba_belief_download");
+            fba_belief* first = nullptr;
+            check(ctx, fba_belief_create(ctx, _cuda->model(), 1, stride, 0, &first), "fba_belief_create");
+            tmp.all.push_back(first);
+            check(ctx, fba_belief_upload(first, 0, 1, &st0, &cur_sid, counts.data(), nullptr), "fba_belief_upload");
+            _model = first;
+        }
+        std::vector<int32_t> seq;
+        sampleHistory(_model, seq);
+        int32_t cur_proto = priorOf(cur_sid, structureOf(cur_sid));
+        tmp.drop(_model);
+        _model       = posterior(cur_proto, seq);
+        double score = scoreOf(_model, cur_proto);
+
+        fba_belief* fresh = nullptr;
+        check(ctx, fba_belief_create(ctx, _cuda->model(), N, stride, 1, &fresh), "fba_belief_create");
+        tmp.all.push_back(fresh);
+        {
+            std::vector<int32_t> zeros((size_t)N, 0);
+            check(ctx, fba_belief_init(fresh, 1, prior_sid.data(), prior_flat.data(), zeros.data(), zeros.data()),
+                  "fba_belief_init"); // placeholders with weight 1 / N (:372-374); every slot is overwritten
+        }
+        int64_t accepted = 0;
+        int64_t batch    = 4;
+        while (accepted < N) // the Gibbs loop, :356-391
+        {
+            // :360-365: `batch` proposals mutate(model.structure()), their posterior counts and scores
+            std::vector<int32_t> pproto((size_t)batch), pid((size_t)batch);
+            for (int64_t j = 0; j < batch; ++j)
+            {
+                auto st            = fbapomdp.mutate(structureOf(cur_sid));
+                pid[(size_t)j]     = _cuda->structureId(st);
+                pproto[(size_t)j]  = priorOf(pid[(size_t)j], st);
+            }
+            fba_belief* prop  = priorBelief(pproto);
+            fba_belief* prior = priorBelief(pproto);
+            check(ctx, fba_belief_add_history_counts(prop, (int32_t)len.size(), len.data(), act.data(), obs.data(), seq.data(), 1),
+                  "fba_belief_add_history_counts");
+            std::vector<double> new_score((size_t)batch);
+            check(ctx, fba_belief_log_bd_score(prop, prior, new_score.data()), "fba_belief_log_bd_score");
+            int64_t took = -1;
+            for (int64_t j = 0; j < batch && took < 0; ++j)
+            {
+                ++_proposals;
+                if (std::log(rnd::uniform_rand01()) < new_score[(size_t)j] - score) took = j; // :367
+            }
+            if (took >= 0)
+            {
+                // :370-374: the accepted model joins the belief with the last state of the CURRENT history
+                check(ctx, fba_belief_assign_from(fresh, accepted, prop, 1, &took), "fba_belief_assign_from");
+                int32_t const last = seq.back();
+                check(ctx, fba_belief_upload(fresh, accepted, 1, &last, nullptr, nullptr, nullptr), "fba_belief_upload");
+                ++accepted;
+                // :377-383: a new state history from the model BEFORE the move, then the model of the accepted
+                // structure on that history and its score
+                sampleHistory(_model, seq);
+                tmp.drop(_model);
+                cur_sid   = pid[(size_t)took];
+                cur_proto = pproto[(size_t)took];
+                _model    = posterior(cur_proto, seq);
+                score     = scoreOf(_model, cur_proto);
+                batch     = std::max<int64_t>(2, batch / 2);
+            } else
+                batch = std::min<int64_t>(64, batch * 2);
+            tmp.drop(prop), tmp.drop(prior);
+        }
+        tmp.keep(fresh);
+        dropSample();
+        fba_belief_destroy(_belief);
+        _belief         = fresh;
+        _model          = nullptr;
+        _log_likelihood = 0.0; // :394
+        ++_chains;
+    }
+
+    fba_belief* _model = nullptr; // the chain's current model (scratch of reinvigorate)
+};
+
 } // namespace fba_b200
 
 #endif // FBA_B200_CUDA_MH_HPP

@@ -345,6 +345,29 @@ int fba_belief_replay_history(fba_belief* b, int32_t n_episodes, const int32_t* 
  * (MHNIPS2018.cpp:241-246). Weights are untouched. */
 int fba_belief_assign_from(fba_belief* dst, int64_t first, fba_belief* src, int64_t n, const int64_t* src_index);
 
+/* ---- MHwithinGibbs -------------------------------------------------------------
+ * sampleStateHistory of beliefs::bayes_adaptive::factored::MHwithinGibbs
+ * (src/beliefs/bayes-adaptive/factored/MHwithinGibbs.cpp:38-232): for EVERY particle of `b` (each one a model)
+ * a sequence of domain states for the whole (action, observation) history — episode_len[e] + 1 states per
+ * episode, so states is [N][n_steps + n_episodes] (host) — conditioned on the observations:
+ *   method 0 (MSG, :96-213): BABNModel::flattenT / flattenO as float tables, per episode a backward pass of
+ *     normalised double messages (one GPU thread per domain state, each running the reference's sequential
+ *     inner product; sequential totals) and forward sampling; state_prior = S floats,
+ *     FBAPOMDP::domainStatePrior()->prob(s) (the prior of s_0); one CTA per particle;
+ *   method 1 (RS, :38-94): rejection sampling with the particle's counts, one thread per particle; more than
+ *     max_attempts episode attempts in one particle: FBA_ERR_CAPACITY.
+ * Counts are not modified. REPLAY: particle i draws from the i-th equal slice of the remaining words. */
+int fba_belief_sample_state_history(fba_belief* b, int32_t method, int32_t n_episodes, const int32_t* episode_len,
+                                    const int32_t* actions, const int32_t* observations, const float* state_prior,
+                                    fba_rng* rng, int64_t max_attempts, int32_t* states);
+/* MHwithinGibbs::computePosteriorCounts (MHwithinGibbs.cpp:397-436): every particle of `b` (holding the prior
+ * counts of its structure) gets incrementCountsOf(s_t, a_t, o_t, s_t+1) for every step of its state history:
+ * states [N][n_steps + n_episodes], or with shared = 1 ONE history [n_steps + n_episodes] for all particles
+ * (the proposals of one Gibbs sweep share the current state sequence). */
+int fba_belief_add_history_counts(fba_belief* b, int32_t n_episodes, const int32_t* episode_len,
+                                  const int32_t* actions, const int32_t* observations, const int32_t* states,
+                                  int32_t shared);
+
 /* ---- single particles between the filters of the composite structure beliefs ----
  * src[src_index[j]] -> dst[dst_index[j]] for j = 0 .. n-1 IN ORDER (a later j overwrites an earlier one on
  * the same slot): count block, domain state, structure id. A weighted dst follows WeightedFilter::replace

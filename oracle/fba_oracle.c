@@ -943,6 +943,167 @@ int64_t orc_promote(orc_belief* shadow, orc_belief* belief, double threshold, or
     return moved;
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* MHwithinGibbs: state histories conditioned on a model, posterior counts                     */
+/* ------------------------------------------------------------------------------------------ */
+
+int64_t orc_state_history_rs(const orc_model* m, const uint32_t* t_par, const uint32_t* o_par, const float* counts,
+                             int n_episodes, const int32_t* episode_len, const int32_t* actions,
+                             const int32_t* observations, orc_rng* g, int64_t max_attempts, int32_t* states_out)
+{
+    /* rejectionSampleStateHistory (MHwithinGibbs.cpp:38-94): per episode a domain start state, then
+     * s' and o sampled from the model (expected Dirichlets, counts untouched) step after step; the first
+     * wrong observation abandons the attempt and the episode starts over. states_out receives
+     * episode_len[e] + 1 states per episode. Returns the episode attempts, -1 beyond max_attempts. */
+    int64_t attempts = 0, first = 0, pos = 0;
+    for (int e = 0; e < n_episodes; ++e)
+    {
+        int const len = episode_len[e];
+        for (;;)
+        {
+            if (++attempts > max_attempts || g->overrun) return -1;
+            int32_t s       = orc_sample_start_state(m, g);
+            states_out[pos] = s;
+            int t           = 0;
+            for (; t < len; ++t)
+            {
+                int o, term;
+                orc_step(m, t_par, o_par, (float*)counts, &s, actions[first + t], 0, g, &o, &term);
+                if (o != observations[first + t]) break;
+                states_out[pos + 1 + t] = s;
+            }
+            if (t == len) break;
+        }
+        first += len;
+        pos += len + 1;
+    }
+    return attempts;
+}
+
+static int sample_from_mult_d(const double* mult, int64_t n, double total, orc_rng* g)
+{
+    /* rnd::sample::Dir::sampleFromMult<double> (random.hpp:93-115) */
+    double const p = orc_uniform01(g) * total;
+    double sum     = mult[0];
+    for (int64_t i = 1; i < n; ++i)
+    {
+        if (p < sum) return (int)(i - 1);
+        sum += mult[i];
+    }
+    return (int)(n - 1);
+}
+
+void orc_flatten_model(const orc_model* m, const uint32_t* t_par, const uint32_t* o_par, const float* counts,
+                       float* T /* [S][A][S] */, float* O /* [A][S][O] */)
+{
+    /* BABNModel::flattenT / flattenO (BABNModel.cpp:89-178): every entry starts at 1.0f and is multiplied,
+     * feature after feature, by that node's expected multinomial (DBNNode::expectation = expectedMult:
+     * float sum, float divide) */
+    int x[ORC_MAXF], x2[ORC_MAXF], of[ORC_MAXF];
+    int64_t t_off[ORC_MAXF], o_off[ORC_MAXF];
+    for (int a = 0; a < m->A; ++a)
+    {
+        node_offsets_small(m, t_par, o_par, a, t_off, o_off);
+        for (int s = 0; s < m->S; ++s)
+        {
+            features_of(s, m->feat_s, m->FS, x);
+            for (int s2 = 0; s2 < m->S; ++s2)
+            {
+                features_of(s2, m->feat_s, m->FS, x2);
+                float p = 1.0f;
+                for (int f = 0; f < m->FS; ++f)
+                    p *= expected_mult_at(counts + t_off[f] + (int64_t)parent_config(m, t_par[a * m->FS + f], x) * m->feat_s[f],
+                                          m->feat_s[f], x2[f]);
+                T[((int64_t)s * m->A + a) * m->S + s2] = p;
+            }
+            /* flattenO: parents = the features of the state the observation is made IN */
+            for (int o = 0; o < m->O; ++o)
+            {
+                features_of(o, m->feat_o, m->FO, of);
+                float p = 1.0f;
+                for (int q = 0; q < m->FO; ++q)
+                    p *= expected_mult_at(counts + o_off[q] + (int64_t)parent_config(m, o_par[a * m->FO + q], x) * m->feat_o[q],
+                                          m->feat_o[q], of[q]);
+                O[((int64_t)a * m->S + s) * m->O + o] = p;
+            }
+        }
+    }
+}
+
+int orc_state_history_msg(const orc_model* m, const uint32_t* t_par, const uint32_t* o_par, const float* counts,
+                          const float* state_prior, int n_episodes, const int32_t* episode_len,
+                          const int32_t* actions, const int32_t* observations, orc_rng* g, int32_t* states_out)
+{
+    /* msgSampleStateHistory (MHwithinGibbs.cpp:96-213): per episode a backward pass of normalised
+     * messages p(o_t.. | s_t) in double over the float tables, then forward sampling of s_0 .. s_T */
+    int const S = m->S, A = m->A;
+    float* T = (float*)malloc(sizeof(float) * (size_t)S * A * S);
+    float* O = (float*)malloc(sizeof(float) * (size_t)A * S * m->O);
+    orc_flatten_model(m, t_par, o_par, counts, T, O);
+    int max_len = 0;
+    for (int e = 0; e < n_episodes; ++e) max_len = episode_len[e] > max_len ? episode_len[e] : max_len;
+    double* msg   = (double*)malloc(sizeof(double) * (size_t)(max_len + 1) * S);
+    double* probs = (double*)malloc(sizeof(double) * (size_t)S);
+    int64_t first = 0, pos = 0;
+    for (int e = 0; e < n_episodes; ++e)
+    {
+        int const len      = episode_len[e];
+        const int32_t* act = actions + first;
+        const int32_t* obs = observations + first;
+        for (int s = 0; s < S; ++s) msg[(int64_t)len * S + s] = O[((int64_t)act[len - 1] * S + s) * m->O + obs[len - 1]];
+        for (int step = len - 1; step >= 0; --step)
+        {
+            int const a = act[step];
+            double tot  = 0;
+            for (int s = 0; s < S; ++s)
+            {
+                const float* row = T + ((int64_t)s * A + a) * S;
+                double acc       = 0.0; /* std::inner_product(row, row + S, message[step + 1], 0.0) */
+                for (int s2 = 0; s2 < S; ++s2) acc = acc + row[s2] * msg[(int64_t)(step + 1) * S + s2];
+                if (step != 0) acc *= O[((int64_t)act[step - 1] * S + s) * m->O + obs[step - 1]];
+                else
+                    acc *= state_prior[s];
+                msg[(int64_t)step * S + s] = acc;
+                tot += acc;
+            }
+            for (int s = 0; s < S; ++s) msg[(int64_t)step * S + s] = msg[(int64_t)step * S + s] / tot;
+        }
+        int state          = sample_from_mult_d(msg, S, 1, g);
+        states_out[pos++]  = state;
+        for (int step = 0; step < len; ++step)
+        {
+            double tot = 0;
+            for (int s2 = 0; s2 < S; ++s2)
+            {
+                probs[s2] = T[((int64_t)state * A + act[step]) * S + s2] * msg[(int64_t)(step + 1) * S + s2];
+                tot += probs[s2];
+            }
+            state             = sample_from_mult_d(probs, S, tot, g);
+            states_out[pos++] = state;
+        }
+        first += len;
+    }
+    free(T), free(O), free(msg), free(probs);
+    return g->overrun ? -1 : 0;
+}
+
+void orc_add_history_counts(const orc_model* m, const uint32_t* t_par, const uint32_t* o_par, float* counts,
+                            int n_episodes, const int32_t* episode_len, const int32_t* actions,
+                            const int32_t* observations, const int32_t* states)
+{
+    /* MHwithinGibbs::computePosteriorCounts (MHwithinGibbs.cpp:397-436): incrementCountsOf(s_t, a_t, o_t, s_t+1)
+     * for every step of every episode; `states` holds episode_len[e] + 1 states per episode */
+    int64_t first = 0, pos = 0;
+    for (int e = 0; e < n_episodes; ++e)
+    {
+        for (int t = 0; t < episode_len[e]; ++t)
+            orc_increment_counts(m, t_par, o_par, counts, states[pos + t], actions[first + t], observations[first + t],
+                                 states[pos + t + 1], 1.0f);
+        first += episode_len[e];
+        pos += episode_len[e] + 1;
+    }
+}
+
 int64_t orc_nested_update_particle(const orc_model* m, const uint32_t* t_par, const uint32_t* o_par, float* counts,
                                    const int32_t* states_in, int32_t* states_out, int64_t n_bottom, int a, int o,
                                    orc_rng* g, int64_t max_attempts)

@@ -188,6 +188,22 @@ void orc_least_likely(const double* w, int64_t n_particles, int64_t n, int64_t* 
 /* StructureIncubatorSampling::reinvigorateBelief (factored/StructureIncubatorSampling.cpp:155-187) */
 int64_t orc_promote(orc_belief* shadow, orc_belief* belief, double threshold, orc_rng* g);
 
+/* MHwithinGibbs (factored/MHwithinGibbs.cpp): a state history (episode_len[e] + 1 states per episode)
+ * conditioned on one model and the (action, observation) history — by rejection sampling (:38-94; returns the
+ * episode attempts, -1 beyond max_attempts) or by backward messages + forward sampling (:96-213;
+ * state_prior = FBAPOMDP::domainStatePrior()->prob(s), S floats) — and computePosteriorCounts (:397-436) */
+int64_t orc_state_history_rs(const orc_model* m, const uint32_t* t_par, const uint32_t* o_par, const float* counts,
+                             int n_episodes, const int32_t* episode_len, const int32_t* actions,
+                             const int32_t* observations, orc_rng* g, int64_t max_attempts, int32_t* states_out);
+int orc_state_history_msg(const orc_model* m, const uint32_t* t_par, const uint32_t* o_par, const float* counts,
+                          const float* state_prior, int n_episodes, const int32_t* episode_len,
+                          const int32_t* actions, const int32_t* observations, orc_rng* g, int32_t* states_out);
+/* BABNModel::flattenT / flattenO (BABNModel.cpp:89-178): T[s][a][s'], O[a][s'][o] as floats */
+void orc_flatten_model(const orc_model* m, const uint32_t* t_par, const uint32_t* o_par, const float* counts,
+                       float* T, float* O);
+void orc_add_history_counts(const orc_model* m, const uint32_t* t_par, const uint32_t* o_par, float* counts,
+                            int n_episodes, const int32_t* episode_len, const int32_t* actions,
+                            const int32_t* observations, const int32_t* states);
 /* NestedBelief::updateEstimation for ONE top particle (NestedBelief.cpp:142-187); returns its attempts */
 int64_t orc_nested_update_particle(const orc_model* m, const uint32_t* t_par, const uint32_t* o_par, float* counts,
                                    const int32_t* states_in, int32_t* states_out, int64_t n_bottom, int a, int o,

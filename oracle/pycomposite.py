@@ -131,3 +131,43 @@ def assert_matches(b, g, prefix, weighted=False):
     if weighted:
         np.testing.assert_array_equal(b.w, g[prefix + "_w"], err_msg=prefix)
         assert b.total_weight == float(g[prefix + "_total_weight"]), prefix
+
+
+def gibbs_reinvigorate(m, old, priors, t_par, o_par, hist, rng, method, state_prior, mutate_kind, n_out):
+    """MHwithinGibbs::reinvigorate (factored/MHwithinGibbs.cpp:334-395) over the oracle primitives.
+    old: the weighted oracle belief; priors[k]: FBAPOMDPPrior::computePriorModel of structure k (t_par[k],
+    o_par[k]); hist = (episode lengths, actions, observations). -> (struct ids, states, counts) of the new belief."""
+    key = {(t_par[k].tobytes(), o_par[k].tobytes()): k for k in range(len(t_par))}
+    ln, ac, ob = hist
+
+    def history(k, counts):                                                   # sampleStateHistory, :215-232
+        return O.state_history(m, t_par[k], o_par[k], counts, ln, ac, ob, rng, method, state_prior)
+
+    def posterior(k, seq):                                                    # computePosteriorCounts, :397-436
+        c = priors[k].copy()
+        O.add_history_counts(m, t_par[k], o_par[k], c, ln, ac, ob, seq)
+        return c
+
+    def score(k, c):                                                          # BABNModel::LogBDScore
+        sz = m.struct_size(t_par[k], o_par[k])
+        return O.log_bd_score(m, t_par[k], o_par[k], c[:sz].copy(), priors[k][:sz].copy())
+
+    i = O.weighted_sample(old, rng)                                           # old_belief.sample(), :344
+    k = int(old.struct_id[i])
+    c0 = np.zeros(priors.shape[1], np.float32)
+    c0[:old.counts.shape[1]] = old.counts[i]
+    seq = history(k, c0)                                                      # :345-346
+    model = posterior(k, seq)                                                 # :348-350
+    sc = score(k, model)                                                      # :352
+    sid, state, counts = [], [], []
+    while len(sid) < n_out:                                                   # :356
+        tp2, op2 = O.mutate_structure(m, t_par[k], o_par[k], mutate_kind, rng)    # :360
+        k2 = key[(tp2.tobytes(), op2.tobytes())]
+        new_model = posterior(k2, seq)                                        # :362
+        new_sc = score(k2, new_model)                                         # :365
+        if math.log(O.lib().orc_uniform01(rng.ref())) < new_sc - sc:          # :367
+            sid.append(k2), state.append(int(seq[-1])), counts.append(new_model)  # :370-374
+            seq = history(k, model)                                           # :377-378: from the model BEFORE the move
+            k, model = k2, posterior(k2, seq)                                 # :381
+            sc = score(k2, model)                                             # :383
+    return np.array(sid), np.array(state), np.stack(counts)

@@ -116,6 +116,12 @@ def lib():
         L.orc_least_likely.argtypes = [vp, i64, i64, vp]
         L.orc_promote.restype = i64
         L.orc_promote.argtypes = [vp, vp, dbl, vp]
+        L.orc_state_history_rs.restype = i64
+        L.orc_state_history_rs.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, i64, vp]
+        L.orc_state_history_msg.restype = C.c_int
+        L.orc_state_history_msg.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp]
+        L.orc_flatten_model.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.orc_add_history_counts.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp, vp, vp]
         L.orc_nested_update_particle.restype = i64
         L.orc_nested_update_particle.argtypes = [vp, vp, vp, vp, vp, vp, i64, C.c_int, C.c_int, vp, i64]
         _lib = L
@@ -416,6 +422,51 @@ def least_likely(w, n):
 
 def promote(shadow, belief, threshold, rng):
     return lib().orc_promote(shadow.ref(), belief.ref(), threshold, rng.ref())
+
+
+def _hist(episode_len, actions, observations):
+    return (np.ascontiguousarray(episode_len, np.int32), np.ascontiguousarray(actions, np.int32),
+            np.ascontiguousarray(observations, np.int32))
+
+
+def state_history(model, t_par, o_par, counts, episode_len, actions, observations, rng, method, state_prior=None,
+                  max_attempts=1 << 40):
+    """MHwithinGibbs' sampleStateHistory (MHwithinGibbs.cpp:38-213): method "msg" (backward messages, forward
+    sampling) or "rs" (rejection sampling) -> states, episode_len[e] + 1 per episode"""
+    tp, op = np.ascontiguousarray(t_par, np.uint32), np.ascontiguousarray(o_par, np.uint32)
+    ln, ac, ob = _hist(episode_len, actions, observations)
+    c = np.ascontiguousarray(counts, np.float32)
+    out = np.zeros(int(ln.sum()) + len(ln), np.int32)
+    if method == "rs":
+        n = lib().orc_state_history_rs(model.ref(), _p(tp), _p(op), _p(c), len(ln), _p(ln), _p(ac), _p(ob), rng.ref(),
+                                       int(max_attempts), _p(out))
+        if n < 0:
+            raise RuntimeError("orc_state_history_rs: out of attempts / words")
+    else:
+        sp = np.ascontiguousarray(state_prior, np.float32)
+        if lib().orc_state_history_msg(model.ref(), _p(tp), _p(op), _p(c), _p(sp), len(ln), _p(ln), _p(ac), _p(ob),
+                                       rng.ref(), _p(out)):
+            raise RuntimeError("orc_state_history_msg: out of words")
+    return out
+
+
+def flatten_model(model, t_par, o_par, counts):
+    """BABNModel::flattenT / flattenO -> (T[S, A, S], O[A, S, O]) float32"""
+    tp, op = np.ascontiguousarray(t_par, np.uint32), np.ascontiguousarray(o_par, np.uint32)
+    c = np.ascontiguousarray(counts, np.float32)
+    T = np.zeros((model.S, model.A, model.S), np.float32)
+    Ob = np.zeros((model.A, model.S, model.O), np.float32)
+    lib().orc_flatten_model(model.ref(), _p(tp), _p(op), _p(c), _p(T), _p(Ob))
+    return T, Ob
+
+
+def add_history_counts(model, t_par, o_par, counts, episode_len, actions, observations, states):
+    """MHwithinGibbs::computePosteriorCounts, in place on `counts`"""
+    tp, op = np.ascontiguousarray(t_par, np.uint32), np.ascontiguousarray(o_par, np.uint32)
+    ln, ac, ob = _hist(episode_len, actions, observations)
+    st = np.ascontiguousarray(states, np.int32)
+    assert counts.dtype == np.float32 and counts.flags.c_contiguous
+    lib().orc_add_history_counts(model.ref(), _p(tp), _p(op), _p(counts), len(ln), _p(ln), _p(ac), _p(ob), _p(st))
 
 
 def nested_update_particle(model, t_par, o_par, counts, states_in, a, o, rng, max_attempts=1 << 40):

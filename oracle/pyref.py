@@ -204,6 +204,12 @@ class Ref:
             raise RuntimeError("reference/adapter: " + self.L.ref_error(self.h).decode())
         return out
 
+    def adapter_events(self):
+        """MH runs / Gibbs chains / cheats of the CUDA belief in the last adapter_episodes call (-1: not such a belief)"""
+        self.L.ref_adapter_events.restype = C.c_long
+        self.L.ref_adapter_events.argtypes = [C.c_void_p]
+        return self.L.ref_adapter_events(self.h)
+
     def batched_episodes(self, n, runs, sims, episodes, sims_per_wave=1, device=0, seed=4711):
         """fba_b200::runBatchedExperiment on GPU `device` -> (returns[episodes, runs], seconds)"""
         f = self.L.ref_batched_episodes_on
@@ -323,6 +329,22 @@ class Ref:
         self.L.ref_nested_sample.argtypes = [C.c_void_p, C.c_void_p]
         self.L.ref_nested_sample(self.h, _p(out))
         return int(out[0]), int(out[1])
+
+    def gibbs_run(self):
+        """the private MHwithinGibbs::reinvigorate on the belief as it is"""
+        self.L.ref_gibbs_run.argtypes = [C.c_void_p]
+        self.L.ref_gibbs_run(self.h)
+
+    def gibbs_log_likelihood(self):
+        self.L.ref_gibbs_log_likelihood.restype = C.c_double
+        self.L.ref_gibbs_log_likelihood.argtypes = [C.c_void_p]
+        return self.L.ref_gibbs_log_likelihood(self.h)
+
+    def state_prior(self):
+        out = np.zeros(self.S, np.float32)
+        self.L.ref_state_prior.argtypes = [C.c_void_p, C.c_void_p]
+        self.L.ref_state_prior(self.h, _p(out))
+        return out
 
     def plan_seconds(self, kind, n, planner, sims, reps=3):
         """Seconds per Planner::selectAction with `sims` simulations (empty history)."""

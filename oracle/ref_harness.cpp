@@ -109,6 +109,7 @@ struct Handle
 
     std::mt19937 mark;
     std::string err;
+    long adapter_events = -1; // what the last ref_adapter_episodes' CUDA belief did beyond plain filtering
 };
 
 bool g_rng_initiated = false;
@@ -741,6 +742,27 @@ void ref_nested_sample(void* hv, int* out)
     out[1] = s->_domain_state->index();
 }
 
+// the private MHwithinGibbs::reinvigorate (MHwithinGibbs.cpp:334-395) on the belief as it is
+void ref_gibbs_run(void* hv)
+{
+    auto h = static_cast<Handle*>(hv);
+    h->gibbs_belief->reinvigorate(*h->sim);
+}
+
+double ref_gibbs_log_likelihood(void* hv)
+{
+    return static_cast<Handle*>(hv)->gibbs_belief->_log_likelihood;
+}
+
+// FBAPOMDP::domainStatePrior()->prob(s) for every domain state (the prior of s_0 in msgSampleStateHistory)
+void ref_state_prior(void* hv, float* out)
+{
+    auto h          = static_cast<Handle*>(hv);
+    auto const& fba = dynamic_cast<FactoredPOMDP const&>(*h->sim);
+    auto p          = fba.domainStatePrior();
+    for (int s = 0; s < h->sim->domainSize()->_S; ++s) out[s] = p->prob(s);
+}
+
 double ref_cheat_likelihood(void* hv)
 {
     return static_cast<Handle*>(hv)->cheat_belief->_likelihood;
@@ -1100,6 +1122,12 @@ int ref_adapter_episodes(void* hv, int kind, long n, char const* planner, int si
                 belief.reset(new RefNested((size_t)n, (size_t)(n * n)));
             else if (kind == 13)
                 belief.reset(new fba_b200::CudaNestedBelief((size_t)n, (size_t)(n * n)));
+            // MHwithinGibbs, threshold -4 so that the chain runs every few steps; 14/15 message passing, 16/17 rejection
+            else if (kind == 14 || kind == 16)
+                belief.reset(new RefGibbs((size_t)n, -4.0, kind == 14 ? RefGibbs::MSG : RefGibbs::RS));
+            else if (kind == 15 || kind == 17)
+                belief.reset(new fba_b200::CudaMHwithinGibbs(
+                    (size_t)n, -4.0, kind == 15 ? fba_b200::CudaMHwithinGibbs::MSG : fba_b200::CudaMHwithinGibbs::RS));
             else
                 throw std::string("ref_adapter_episodes: unknown belief kind");
         }
@@ -1112,6 +1140,11 @@ int ref_adapter_episodes(void* hv, int kind, long n, char const* planner, int si
                 *plan, *belief, *h->env, *h->sim, Horizon(conf.horizon), Discount(conf.discount));
             returns[e] = r.ret.toDouble();
         }
+        // how often the structure-learning part of a CUDA belief ran (MH runs, Gibbs chains, cheats)
+        h->adapter_events = -1;
+        if (auto b = dynamic_cast<fba_b200::CudaMHNIPS2018*>(belief.get())) h->adapter_events = (long)b->mhRuns();
+        if (auto b = dynamic_cast<fba_b200::CudaMHwithinGibbs*>(belief.get())) h->adapter_events = (long)b->chains();
+        if (auto b = dynamic_cast<fba_b200::CudaCheatingReinvigoration*>(belief.get())) h->adapter_events = (long)b->cheats();
         belief->free(*h->sim);
     } catch (std::string const& e)
     {
@@ -1123,6 +1156,11 @@ int ref_adapter_episodes(void* hv, int kind, long n, char const* planner, int si
         return 1;
     }
     return 0;
+}
+
+long ref_adapter_events(void* hv)
+{
+    return static_cast<Handle*>(hv)->adapter_events;
 }
 
 

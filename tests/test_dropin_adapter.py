@@ -45,6 +45,11 @@ CASES = [
     ("episodic-factored-tiger", dict(size=3, factored=True, structure_prior="match-uniform"), (12, 13), 8, 40),
     ("gridworld", dict(size=3), (12, 13), 6, 10),
     ("episodic-tiger", dict(sampled=True), (12, 13), 10, 60),
+    # MHwithinGibbs (threshold -4: the Gibbs chain runs every few steps), message passing and rejection sampling
+    ("episodic-factored-tiger", dict(size=3, factored=True, structure_prior="match-uniform"), (14, 15), 64, 40),
+    ("episodic-factored-tiger", dict(size=3, factored=True, structure_prior="match-uniform"), (16, 17), 64, 40),
+    ("centered-collision-avoidance", dict(size=1, width=3, height=3, factored=True,
+                                          structure_prior="match-uniform"), (14, 15), 48, 30),
     # --dirichlet_sampling_method regular: the adapter reads the mode from the simulator
     ("episodic-tiger", dict(sampled=True), (0, 1), 256, 80),
     ("episodic-factored-tiger", dict(size=3, factored=True, sampled=True), (0, 1), 128, 40),
@@ -58,8 +63,11 @@ def test_reference_episode_loop_with_cuda_belief(domain, kw, kinds, n, episodes)
     try:
         ref = r.adapter_episodes(kinds[0], n, "po-uct", 48, episodes)
         ours = r.adapter_episodes(kinds[1], n, "po-uct", 48, episodes)
+        events = r.adapter_events()
     finally:
         r.close()
+    if kinds[1] in (7, 9, 15, 17):      # MH runs / cheats / Gibbs chains did happen during these episodes
+        assert events >= 2, events
     assert np.all(np.isfinite(ours))
     se = np.sqrt(ref.var(ddof=1) / len(ref) + ours.var(ddof=1) / len(ours)) + 1e-9
     assert abs(ref.mean() - ours.mean()) <= 4.0 * se + 1e-6, (ref.mean(), ours.mean(), se)

@@ -180,3 +180,46 @@ def test_nested_belief_equals_the_reference(name):
         done += 1
     assert done >= 8
     assert len(np.unique(nb.top.w)) > 1      # the top weights moved apart (1 / attempts differs per particle)
+
+
+GIBBS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gibbs.npz")
+
+
+def load_gibbs(tag):
+    g = np.load(GIBBS)
+    desc = {k[len("model/"):]: g[k] for k in g.files if k.startswith("model/")}
+    m = O.Model(desc)
+    n = g[tag + "/old_counts"].shape[0]
+    old = O.Belief(n, g[tag + "/old_counts"].shape[1])
+    old.counts[:], old.state[:], old.struct_id[:] = g[tag + "/old_counts"], g[tag + "/old_state"], g[tag + "/old_struct_id"]
+    old.w[:] = g[tag + "/old_w"]
+    old.total_weight = float(g[tag + "/old_total_weight"])
+    return g, m, old
+
+
+@pytest.mark.parametrize("tag", ["msg", "rs"])
+def test_mh_within_gibbs_restated_over_oracle_primitives_equals_the_reference(tag):
+    """MHwithinGibbs::reinvigorate (MHwithinGibbs.cpp:334-395) as a loop over oracle primitives — weighted draw,
+    state history by backward messages / rejection sampling, computePosteriorCounts, the domain's mutate,
+    LogBDScore, the accept test — fed the exact words the reference's private reinvigorate consumed: every word
+    is used and the new belief equals the reference's bit for bit. Pins orc_state_history_msg (float tables,
+    double messages, sequential sums), orc_state_history_rs and orc_add_history_counts."""
+    g, m, old = load_gibbs(tag)
+    rng = O.Rng(g[tag + "/words"])
+    sid, state, counts = PC.gibbs_reinvigorate(
+        m, old, g["priors/counts"], g["structs/t_par"], g["structs/o_par"],
+        (g["history/len"], g["history/a"], g["history/o"]), rng, tag, g["model_state_prior"], MUT_FACTORED_TIGER,
+        len(g[tag + "/new_state"]))
+    assert used(rng)
+    np.testing.assert_array_equal(sid, g[tag + "/new_struct_id"])
+    np.testing.assert_array_equal(state, g[tag + "/new_state"])
+    np.testing.assert_array_equal(counts[:, :g[tag + "/new_counts"].shape[1]], g[tag + "/new_counts"])
+    assert len(np.unique(sid)) > 1
+
+
+def test_flattened_model_rows_are_distributions():
+    g, m, old = load_gibbs("msg")
+    k = int(old.struct_id[0])
+    T, Ob = O.flatten_model(m, g["structs/t_par"][k], g["structs/o_par"][k], old.counts[0])
+    np.testing.assert_allclose(T.sum(2), 1.0, atol=1e-5)
+    np.testing.assert_allclose(Ob.sum(2), 1.0, atol=1e-5)
