@@ -264,6 +264,16 @@ extern "C" int fba_ctx_create(int device, fba_ctx** out)
     if (const char* g = getenv("FBA_B200_L2_FETCH")) // experiment knob: 32 / 64 / 128 bytes
         if (e == cudaSuccess) e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess)
+    { // scratch of the short MCMC calls comes from the stream-ordered pool (PoolTmp): keep up to 256 MB cached
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool)
+        {
+            unsigned long long threshold = 256ull << 20;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+        }
+        cudaGetLastError();
+    }
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_flag, sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_counters, 4 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(ctx->d_counters, 0, 4 * sizeof(unsigned long long));
@@ -913,6 +923,30 @@ struct DevTmp
     DevTmp()              = default;
     DevTmp(DevTmp const&) = delete;
     DevTmp& operator=(DevTmp const&) = delete;
+};
+
+// the same from the device's stream-ordered memory pool (cudaMallocAsync on the context's stream): for the short
+// calls of the MCMC beliefs, which would otherwise spend most of their time in cudaMalloc / cudaFree. Freed in
+// stream order when the call returns; the pool keeps up to 256 MB cached (fba_ctx_create).
+template<class T>
+struct PoolTmp
+{
+    T* p            = nullptr;
+    cudaStream_t st = nullptr;
+    ~PoolTmp()
+    {
+        if (p) cudaFreeAsync(p, st);
+    }
+    operator T*() const { return p; }
+    PoolTmp()               = default;
+    PoolTmp(PoolTmp const&) = delete;
+    PoolTmp& operator=(PoolTmp const&) = delete;
+    int alloc(fba_ctx* ctx, size_t n)
+    {
+        st = ctx->stream;
+        CU(ctx, cudaMallocAsync(&p, std::max<size_t>(n, 1) * sizeof(T), st));
+        return FBA_OK;
+    }
 };
 
 // base+delta storage: the prior prototypes become the shared base tables
@@ -2389,7 +2423,7 @@ namespace {
 // the (action, observation) history on the device + its checks, shared by the calls below
 struct DeviceHistory
 {
-    DevTmp<int> len, act, obs;
+    PoolTmp<int> len, act, obs;
     HistoryArgs H{};
     long long total = 0;
     int stage(fba_ctx* ctx, DevModel const& D, int32_t n_episodes, const int32_t* episode_len, const int32_t* actions,
@@ -2407,9 +2441,9 @@ struct DeviceHistory
             REQUIRE(ctx, actions[k] >= 0 && actions[k] < D.A, "history: action out of range");
             REQUIRE(ctx, observations[k] >= 0 && observations[k] < D.O, "history: observation out of range");
         }
-        CU(ctx, cudaMalloc(&len, std::max(1, (int)n_episodes) * sizeof(int)));
-        CU(ctx, cudaMalloc(&act, std::max(1ll, total) * sizeof(int)));
-        CU(ctx, cudaMalloc(&obs, std::max(1ll, total) * sizeof(int)));
+        int rc;
+        if ((rc = len.alloc(ctx, (size_t)n_episodes)) || (rc = act.alloc(ctx, (size_t)total)) || (rc = obs.alloc(ctx, (size_t)total)))
+            return rc;
         if (n_episodes)
             CU(ctx, cudaMemcpyAsync(len, episode_len, n_episodes * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
         if (total)
@@ -2444,9 +2478,8 @@ extern "C" int fba_belief_sample_state_history(fba_belief* b, int32_t method, in
     if ((rc = h.stage(ctx, D, n_episodes, episode_len, actions, observations, true))) return rc;
     h.H.max_attempts         = max_attempts;
     long long const out_len  = h.total + n_episodes;
-    DevTmp<int> d_out, d_failed;
-    CU(ctx, cudaMalloc(&d_out, (size_t)b->N * out_len * sizeof(int)));
-    CU(ctx, cudaMalloc(&d_failed, sizeof(int)));
+    PoolTmp<int> d_out, d_failed;
+    if ((rc = d_out.alloc(ctx, (size_t)b->N * out_len)) || (rc = d_failed.alloc(ctx, 1))) return rc;
     CU(ctx, cudaMemsetAsync(d_failed, 0, sizeof(int), ctx->stream));
     bool const replay   = rng->mode == FBA_RNG_REPLAY;
     long long const per = replay ? (rng->n_words - rng->cursor) / b->N : 0;
@@ -2481,14 +2514,13 @@ extern "C" int fba_belief_sample_state_history(fba_belief* b, int32_t method, in
         REQUIRE(ctx, bytes < 64e9, "sample_state_history: the flattened models of these particles do not fit (N A S (S + O) floats)");
         std::vector<unsigned char> used((size_t)D.A, 0);
         for (long long k = 0; k < h.total; ++k) used[(size_t)actions[k]] = 1;
-        DevTmp<unsigned char> d_used;
-        DevTmp<float> d_T, d_O, d_prior;
-        DevTmp<double> d_msg;
-        CU(ctx, cudaMalloc(&d_used, (size_t)D.A));
-        CU(ctx, cudaMalloc(&d_T, (size_t)b->N * D.A * D.S * D.S * sizeof(float)));
-        CU(ctx, cudaMalloc(&d_O, (size_t)b->N * D.A * D.O * D.S * sizeof(float)));
-        CU(ctx, cudaMalloc(&d_prior, (size_t)D.S * sizeof(float)));
-        CU(ctx, cudaMalloc(&d_msg, (size_t)b->N * (h.H.max_len + 2) * D.S * sizeof(double)));
+        PoolTmp<unsigned char> d_used;
+        PoolTmp<float> d_T, d_O, d_prior;
+        PoolTmp<double> d_msg;
+        if ((rc = d_used.alloc(ctx, (size_t)D.A)) || (rc = d_T.alloc(ctx, (size_t)b->N * D.A * D.S * D.S))
+            || (rc = d_O.alloc(ctx, (size_t)b->N * D.A * D.O * D.S)) || (rc = d_prior.alloc(ctx, (size_t)D.S))
+            || (rc = d_msg.alloc(ctx, (size_t)b->N * (h.H.max_len + 2) * D.S)))
+            return rc;
         CU(ctx, cudaMemcpyAsync(d_used, used.data(), used.size(), cudaMemcpyHostToDevice, ctx->stream));
         CU(ctx, cudaMemcpyAsync(d_prior, state_prior, (size_t)D.S * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
         dim3 const grid((unsigned)std::min<long long>(blocks_for((long long)D.A * D.S), 4 * ctx->sm_count), (unsigned)b->N);
@@ -2500,7 +2532,6 @@ extern "C" int fba_belief_sample_state_history(fba_belief* b, int32_t method, in
         else
             LAUNCH(ctx, (k_state_history_msg<false>), (int)b->N, kThreads, D, b->N, h.H, (const float*)d_T,
                    (const float*)d_O, (const float*)d_prior, (double*)d_msg, ra, (int*)d_out, out_len, ctx->d_flag);
-        CU(ctx, cudaStreamSynchronize(ctx->stream)); // the scratch dies with this scope
     }
     CU(ctx, cudaMemcpyAsync(ctx->h_flag, d_failed, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaMemcpyAsync(states, d_out, (size_t)b->N * out_len * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -2544,9 +2575,8 @@ extern "C" int fba_belief_add_history_counts(fba_belief* b, int32_t n_episodes, 
             p += episode_len[e] + 1;
         }
     }
-    DevTmp<int> d_pos, d_states;
-    CU(ctx, cudaMalloc(&d_pos, (size_t)h.total * sizeof(int)));
-    CU(ctx, cudaMalloc(&d_states, (size_t)n_seq * seq_len * sizeof(int)));
+    PoolTmp<int> d_pos, d_states;
+    if ((rc = d_pos.alloc(ctx, (size_t)h.total)) || (rc = d_states.alloc(ctx, (size_t)n_seq * seq_len))) return rc;
     CU(ctx, cudaMemcpyAsync(d_pos, pos.data(), (size_t)h.total * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     CU(ctx, cudaMemcpyAsync(d_states, states, (size_t)n_seq * seq_len * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     LAUNCH(ctx, k_add_history_counts, blocks_for(b->N * h.total), kThreads, D, b->counts[b->cur], b->stride, b->sid[b->cur],
@@ -2569,9 +2599,12 @@ static int replace_core(fba_belief* dst, const std::vector<int>& dst_index, fba_
     std::vector<int2> jobs;
     jobs.reserve(last.size());
     for (auto const& kv : last) jobs.push_back(make_int2(kv.second, kv.first));
-    DevTmp<int2> d_jobs;
+    PoolTmp<int2> d_jobs;
     CU(ctx, cudaSetDevice(ctx->device));
-    CU(ctx, cudaMalloc(&d_jobs.p, jobs.size() * sizeof(int2)));
+    {
+        int const rc = d_jobs.alloc(ctx, jobs.size());
+        if (rc) return rc;
+    }
     CU(ctx, cudaMemcpyAsync(d_jobs.p, jobs.data(), jobs.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
     LAUNCH(ctx, k_replace_from, stream_grid(ctx, (long long)jobs.size()), kThreads, src->counts[src->cur],
            dst->counts[dst->cur], dst->stride, src->state[src->cur], dst->state[dst->cur], src->sid[src->cur],

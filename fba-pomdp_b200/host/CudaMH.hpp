@@ -193,9 +193,18 @@ private:
                   "fba_belief_init"); // placeholder particles, uniform weights 1/N (:243); every slot is overwritten
         }
         int64_t accepted = 0;
+        // proposal scratch, created once per MH run (a belief is ~20 device allocations) and re-initialised per batch
+        int64_t const P   = std::max<int64_t>(N, 256);
+        fba_belief* prop  = tmp.make(ctx, _cuda->model(), P, stride, 0);
+        fba_belief* prior = tmp.make(ctx, _cuda->model(), P, stride, 0);
+        std::vector<int32_t> zerosP((size_t)P, 0);
+        auto setPriors = [&](fba_belief* b, std::vector<int32_t> const& proto) {
+            check(ctx, fba_belief_init(b, (int32_t)prior_sid.size(), prior_sid.data(), prior_flat.data(), proto.data(),
+                                       zerosP.data()),
+                  "fba_belief_init");
+        };
         while (accepted < N)
         {
-            int64_t const P = std::min<int64_t>(std::max<int64_t>(2 * (N - accepted), 256), std::max<int64_t>(N, 256));
             std::vector<int64_t> src((size_t)P);
             check(ctx, fba_belief_sample_batch(_belief, &_rng, P, src.data()), "fba_belief_sample_batch"); // :200
             std::vector<int32_t> pproto((size_t)P);
@@ -210,8 +219,8 @@ private:
                     pproto[(size_t)j]  = priorOf(nid, st);
                 }
             }
-            fba_belief* prop  = priorBelief(pproto);
-            fba_belief* prior = priorBelief(pproto);
+            setPriors(prop, pproto);
+            setPriors(prior, pproto);
             check(ctx,
                   fba_belief_replay_history(prop, (int32_t)len.size(), len.data(), act.data(), obs.data(), &_rng,
                                             1000000),
@@ -226,7 +235,6 @@ private:
                   "fba_belief_assign_from");
             accepted += (int64_t)take.size();
             _proposals += (size_t)P;
-            tmp.drop(prop), tmp.drop(prior);
         }
         // the new belief replaces the old one (:252)
         for (auto& x : tmp.all)
@@ -241,25 +249,31 @@ private:
 
 // Drop-in for beliefs::bayes_adaptive::factored::MHwithinGibbs
 // (src/beliefs/bayes-adaptive/factored/MHwithinGibbs.{hpp,cpp}): importance sampling as above, and when the log
-// likelihood drops below the threshold a Gibbs chain over (state history, model) rebuilds the belief
+// likelihood drops below the threshold a Gibbs sampler over (state history, model) rebuilds the belief
 // (reinvigorate, MHwithinGibbs.cpp:334-395):
 //   * p(states | model): fba_belief_sample_state_history — backward messages + forward sampling over the
 //     flattened model (MSG), or rejection sampling (RS) — on the GPU;
 //   * p(model | states): Metropolis-Hastings over structures — the domain's mutate and the prior model of the
 //     proposed structure by the reference's own code on the host, computePosteriorCounts
 //     (fba_belief_add_history_counts) and BABNModel::LogBDScore (fba_belief_log_bd_score) on the GPU.
-// Between two acceptances the reference's proposals are independent draws from the same structure against the
-// same state history, so they are evaluated in BATCHES; the first accepted one (in proposal order) is taken and
-// the rest of its batch dropped — the chain has the reference's distribution, including its detail that the new
-// state history is sampled from the model BEFORE the move (:377-378).
+// The reference runs ONE chain until it has produced `size` models: strictly sequential, a handful of tiny
+// operations per link. Here `chains` independent chains advance in LOCKSTEP, each started from its own draw of
+// the old belief and each following the reference's transition exactly (including its detail that the new state
+// history is sampled from the model BEFORE the move, :377-378): one batched call per operation serves every
+// chain, and the accepted models of all chains, in (sweep, chain) order, fill the new belief. chains = 1 is the
+// reference's algorithm link for link; more chains change the mixing (for the better: independent starts), not
+// the transition kernel. Default: min(size, 256).
 class CudaMHwithinGibbs : public CudaParticleBelief
 {
 public:
     enum SAMPLE_STATE_HISTORY_TYPE { RS, MSG }; // as MHwithinGibbs.hpp
 
     CudaMHwithinGibbs(size_t size, double ll_threshold, SAMPLE_STATE_HISTORY_TYPE type, uint64_t seed = 42,
-                      int device = 0) :
-            CudaParticleBelief(size, true, seed, device), _ll_threshold(ll_threshold), _type(type)
+                      int device = 0, size_t chains = 0) :
+            CudaParticleBelief(size, true, seed, device),
+            _ll_threshold(ll_threshold),
+            _type(type),
+            _n_chains(chains ? std::min(chains, size) : std::min<size_t>(size, 256))
     {
         if (size < 1) throw "MHwithinGibbs::cannot initiate MH with size 0"; // as :242-245
         if (ll_threshold >= 0)                                                // as :247-251
@@ -271,7 +285,7 @@ public:
         CudaParticleBelief::initiate(d);
         _history.assign(1, {});
         _log_likelihood = 0.0;
-        _chains = _proposals = 0;
+        _chains = _proposals = _sweeps = 0;
     }
 
     // :257-272: a fresh domain state for every particle where it is, and a new episode in the history
@@ -300,8 +314,9 @@ public:
     }
 
     double logLikelihood() const { return _log_likelihood; }
-    size_t chains() const { return _chains; }
-    size_t proposals() const { return _proposals; }
+    size_t chains() const { return _chains; }       // reinvigorations run
+    size_t proposals() const { return _proposals; } // structure proposals scored
+    size_t sweeps() const { return _sweeps; }       // lockstep sweeps over the chains
 
 protected:
     size_t minimumStride(POMDP const& d) const override
@@ -317,9 +332,10 @@ protected:
 private:
     double _ll_threshold;
     SAMPLE_STATE_HISTORY_TYPE _type;
+    size_t _n_chains;
     double _log_likelihood = 0.0;
     std::vector<std::vector<std::pair<int32_t, int32_t>>> _history;
-    size_t _chains = 0, _proposals = 0;
+    size_t _chains = 0, _proposals = 0, _sweeps = 0;
 
     struct Scratch // beliefs that die with the call, whichever way it ends
     {
@@ -328,11 +344,12 @@ private:
         {
             for (auto b : all) fba_belief_destroy(b);
         }
-        void drop(fba_belief* b)
+        fba_belief* make(fba_ctx* ctx, fba_model* m, int64_t n, int64_t stride, int weighted)
         {
-            for (auto& x : all)
-                if (x == b) x = nullptr;
-            fba_belief_destroy(b);
+            fba_belief* b = nullptr;
+            check(ctx, fba_belief_create(ctx, m, n, stride, weighted, &b), "fba_belief_create");
+            all.push_back(b);
+            return b;
         }
         void keep(fba_belief* b)
         {
@@ -347,6 +364,7 @@ private:
         auto const& fbapomdp = dynamic_cast<::bayes_adaptive::factored::FBAPOMDP const&>(d);
         fba_ctx* ctx         = _cuda->ctx();
         int64_t const N      = (int64_t)_n;
+        int64_t const C      = (int64_t)_n_chains;
         int64_t const stride = fba_belief_stride(_belief);
         Scratch tmp;
 
@@ -385,120 +403,102 @@ private:
             if (it == structure_of.end()) it = structure_of.emplace(id, _cuda->structureOf(id)).first;
             return it->second;
         };
-        auto priorBelief = [&](std::vector<int32_t> const& proto) {
-            fba_belief* b = nullptr;
-            check(ctx, fba_belief_create(ctx, _cuda->model(), (int64_t)proto.size(), stride, 0, &b), "fba_belief_create");
-            tmp.all.push_back(b);
-            std::vector<int32_t> zeros(proto.size(), 0);
+        std::vector<int32_t> zeros((size_t)std::max(C, N), 0);
+        // every particle of b becomes the prior model its chain names
+        auto setPriors = [&](fba_belief* b, std::vector<int32_t> const& proto) {
             check(ctx, fba_belief_init(b, (int32_t)prior_sid.size(), prior_sid.data(), prior_flat.data(), proto.data(),
                                        zeros.data()),
                   "fba_belief_init");
-            return b;
         };
-        auto sampleHistory = [&](fba_belief* model, std::vector<int32_t>& seq) { // sampleStateHistory, :215-232
-            seq.resize((size_t)L);
+        auto sampleHistories = [&](fba_belief* models, std::vector<int32_t>& seq) { // sampleStateHistory, :215-232
+            seq.resize((size_t)(C * L));
             check(ctx,
-                  fba_belief_sample_state_history(model, _type == MSG ? 0 : 1, (int32_t)len.size(), len.data(), act.data(),
+                  fba_belief_sample_state_history(models, _type == MSG ? 0 : 1, (int32_t)len.size(), len.data(), act.data(),
                                                   obs.data(), state_prior.data(), &_rng, 1000000, seq.data()),
                   "fba_belief_sample_state_history");
         };
-        auto posterior = [&](int32_t proto, std::vector<int32_t> const& seq) { // computePosteriorCounts on ONE model
-            fba_belief* b = priorBelief({proto});
-            check(ctx, fba_belief_add_history_counts(b, (int32_t)len.size(), len.data(), act.data(), obs.data(), seq.data(), 1),
+        auto addCounts = [&](fba_belief* b, std::vector<int32_t> const& seq) { // computePosteriorCounts, :397-436
+            check(ctx, fba_belief_add_history_counts(b, (int32_t)len.size(), len.data(), act.data(), obs.data(), seq.data(), 0),
                   "fba_belief_add_history_counts");
-            return b;
-        };
-        auto scoreOf = [&](fba_belief* model, int32_t proto) { // model.LogBDScore(prior_model)
-            fba_belief* pb = priorBelief({proto});
-            double sc      = 0.0;
-            check(ctx, fba_belief_log_bd_score(model, pb, &sc), "fba_belief_log_bd_score");
-            tmp.drop(pb);
-            return sc;
         };
 
-        // :344-352: the first complete sample, from a particle of the old belief
-        int64_t i0 = 0;
-        check(ctx, fba_belief_sample(_belief, &_rng, &i0), "fba_belief_sample");
-        int32_t cur_sid = 0;
-        {
-            std::vector<float> counts((size_t)stride);
-            int32_t st0 = 0;
-            check(ctx, fba_belief_download(_belief, i0, 1, &st0, &cur_sid, counts.data(), nullptr), "fba_belief_download");
-            fba_belief* first = nullptr;
-            check(ctx, fba_belief_create(ctx, _cuda->model(), 1, stride, 0, &first), "fba_belief_create");
-            tmp.all.push_back(first);
-            check(ctx, fba_belief_upload(first, 0, 1, &st0, &cur_sid, counts.data(), nullptr), "fba_belief_upload");
-            _model = first;
-        }
-        std::vector<int32_t> seq;
-        sampleHistory(_model, seq);
-        int32_t cur_proto = priorOf(cur_sid, structureOf(cur_sid));
-        tmp.drop(_model);
-        _model       = posterior(cur_proto, seq);
-        double score = scoreOf(_model, cur_proto);
+        fba_belief* cur  = tmp.make(ctx, _cuda->model(), C, stride, 0); // every chain's current model
+        fba_belief* prop = tmp.make(ctx, _cuda->model(), C, stride, 0); // proposals / priors, by turns
+        fba_belief* pri  = tmp.make(ctx, _cuda->model(), C, stride, 0);
+        std::vector<int64_t> all((size_t)C);
+        for (int64_t c = 0; c < C; ++c) all[(size_t)c] = c;
 
-        fba_belief* fresh = nullptr;
-        check(ctx, fba_belief_create(ctx, _cuda->model(), N, stride, 1, &fresh), "fba_belief_create");
-        tmp.all.push_back(fresh);
-        {
-            std::vector<int32_t> zeros((size_t)N, 0);
-            check(ctx, fba_belief_init(fresh, 1, prior_sid.data(), prior_flat.data(), zeros.data(), zeros.data()),
-                  "fba_belief_init"); // placeholders with weight 1 / N (:372-374); every slot is overwritten
-        }
+        // :344-352 per chain: a particle of the old belief, a state history from its model, the posterior counts of
+        // its structure's prior on that history, and their score
+        std::vector<int64_t> start((size_t)C);
+        check(ctx, fba_belief_sample_batch(_belief, &_rng, C, start.data()), "fba_belief_sample_batch");
+        check(ctx, fba_belief_assign_from(cur, 0, _belief, C, start.data()), "fba_belief_assign_from");
+        std::vector<int32_t> seq, new_seq, cur_sid((size_t)C), cur_proto((size_t)C);
+        sampleHistories(cur, seq);
+        check(ctx, fba_belief_download(cur, 0, C, nullptr, cur_sid.data(), nullptr, nullptr), "fba_belief_download");
+        for (int64_t c = 0; c < C; ++c) cur_proto[(size_t)c] = priorOf(cur_sid[(size_t)c], structureOf(cur_sid[(size_t)c]));
+        setPriors(pri, cur_proto);
+        addCounts(pri, seq);
+        check(ctx, fba_belief_replace_from(cur, all.data(), pri, all.data(), C), "fba_belief_replace_from");
+        setPriors(prop, cur_proto);
+        std::vector<double> score((size_t)C), new_score((size_t)C);
+        check(ctx, fba_belief_log_bd_score(cur, prop, score.data()), "fba_belief_log_bd_score");
+
+        fba_belief* fresh = tmp.make(ctx, _cuda->model(), N, stride, 1);
+        check(ctx, fba_belief_init(fresh, 1, prior_sid.data(), prior_flat.data(), zeros.data(), zeros.data()),
+              "fba_belief_init"); // placeholders with weight 1 / N (:372-374); every slot is overwritten
         int64_t accepted = 0;
-        int64_t batch    = 4;
-        while (accepted < N) // the Gibbs loop, :356-391
+        std::vector<int32_t> pproto((size_t)C), pid((size_t)C);
+        while (accepted < N) // the Gibbs loop, :356-391, one link of every chain per sweep
         {
-            // :360-365: `batch` proposals mutate(model.structure()), their posterior counts and scores
-            std::vector<int32_t> pproto((size_t)batch), pid((size_t)batch);
-            for (int64_t j = 0; j < batch; ++j)
+            ++_sweeps;
+            // :360-365: every chain's proposal mutate(model.structure()), its posterior counts and score
+            for (int64_t c = 0; c < C; ++c)
             {
-                auto st            = fbapomdp.mutate(structureOf(cur_sid));
-                pid[(size_t)j]     = _cuda->structureId(st);
-                pproto[(size_t)j]  = priorOf(pid[(size_t)j], st);
+                auto st           = fbapomdp.mutate(structureOf(cur_sid[(size_t)c]));
+                pid[(size_t)c]    = _cuda->structureId(st);
+                pproto[(size_t)c] = priorOf(pid[(size_t)c], st);
             }
-            fba_belief* prop  = priorBelief(pproto);
-            fba_belief* prior = priorBelief(pproto);
-            check(ctx, fba_belief_add_history_counts(prop, (int32_t)len.size(), len.data(), act.data(), obs.data(), seq.data(), 1),
-                  "fba_belief_add_history_counts");
-            std::vector<double> new_score((size_t)batch);
-            check(ctx, fba_belief_log_bd_score(prop, prior, new_score.data()), "fba_belief_log_bd_score");
-            int64_t took = -1;
-            for (int64_t j = 0; j < batch && took < 0; ++j)
+            setPriors(prop, pproto);
+            setPriors(pri, pproto);
+            addCounts(prop, seq);
+            check(ctx, fba_belief_log_bd_score(prop, pri, new_score.data()), "fba_belief_log_bd_score");
+            _proposals += (size_t)C;
+            std::vector<int64_t> took;
+            for (int64_t c = 0; c < C; ++c)
+                if (std::log(rnd::uniform_rand01()) < new_score[(size_t)c] - score[(size_t)c]) took.push_back(c); // :367
+            if (took.empty()) continue;
+            // :370-374: the accepted models join the belief with the last state of their chain's CURRENT history
+            int64_t const n_new = std::min<int64_t>((int64_t)took.size(), N - accepted);
+            std::vector<int32_t> last((size_t)n_new);
+            for (int64_t k = 0; k < n_new; ++k) last[(size_t)k] = seq[(size_t)(took[(size_t)k] * L + L - 1)];
+            check(ctx, fba_belief_assign_from(fresh, accepted, prop, n_new, took.data()), "fba_belief_assign_from");
+            check(ctx, fba_belief_upload(fresh, accepted, n_new, last.data(), nullptr, nullptr, nullptr), "fba_belief_upload");
+            accepted += n_new;
+            if (accepted >= N) break;
+            // :377-383: a new state history from the model BEFORE the move, then the model of the accepted structure
+            // on that history and its score (all chains are sampled; only the moved ones take the result)
+            sampleHistories(cur, new_seq);
+            for (auto c : took)
             {
-                ++_proposals;
-                if (std::log(rnd::uniform_rand01()) < new_score[(size_t)j] - score) took = j; // :367
+                std::copy(new_seq.begin() + c * L, new_seq.begin() + (c + 1) * L, seq.begin() + c * L);
+                cur_sid[(size_t)c]   = pid[(size_t)c];
+                cur_proto[(size_t)c] = pproto[(size_t)c];
             }
-            if (took >= 0)
-            {
-                // :370-374: the accepted model joins the belief with the last state of the CURRENT history
-                check(ctx, fba_belief_assign_from(fresh, accepted, prop, 1, &took), "fba_belief_assign_from");
-                int32_t const last = seq.back();
-                check(ctx, fba_belief_upload(fresh, accepted, 1, &last, nullptr, nullptr, nullptr), "fba_belief_upload");
-                ++accepted;
-                // :377-383: a new state history from the model BEFORE the move, then the model of the accepted
-                // structure on that history and its score
-                sampleHistory(_model, seq);
-                tmp.drop(_model);
-                cur_sid   = pid[(size_t)took];
-                cur_proto = pproto[(size_t)took];
-                _model    = posterior(cur_proto, seq);
-                score     = scoreOf(_model, cur_proto);
-                batch     = std::max<int64_t>(2, batch / 2);
-            } else
-                batch = std::min<int64_t>(64, batch * 2);
-            tmp.drop(prop), tmp.drop(prior);
+            addCounts(pri, seq);                 // pri holds every chain's proposed prior: now prior + counts(history)
+            check(ctx, fba_belief_replace_from(cur, took.data(), pri, took.data(), (int64_t)took.size()),
+                  "fba_belief_replace_from");
+            setPriors(prop, cur_proto);
+            check(ctx, fba_belief_log_bd_score(cur, prop, new_score.data()), "fba_belief_log_bd_score");
+            for (auto c : took) score[(size_t)c] = new_score[(size_t)c];
         }
         tmp.keep(fresh);
         dropSample();
         fba_belief_destroy(_belief);
         _belief         = fresh;
-        _model          = nullptr;
         _log_likelihood = 0.0; // :394
         ++_chains;
     }
-
-    fba_belief* _model = nullptr; // the chain's current model (scratch of reinvigorate)
 };
 
 } // namespace fba_b200

@@ -210,6 +210,15 @@ class Ref:
         self.L.ref_adapter_events.argtypes = [C.c_void_p]
         return self.L.ref_adapter_events(self.h)
 
+    def adapter_update_seconds(self):
+        """(seconds inside Belief::updateEstimation, calls) of the last adapter_episodes call"""
+        f = self.L.ref_adapter_update_seconds
+        f.restype = C.c_double
+        f.argtypes = [C.c_void_p, C.c_void_p]
+        n = C.c_long(0)
+        s = f(self.h, C.byref(n))
+        return s, n.value
+
     def batched_episodes(self, n, runs, sims, episodes, sims_per_wave=1, device=0, seed=4711):
         """fba_b200::runBatchedExperiment on GPU `device` -> (returns[episodes, runs], seconds)"""
         f = self.L.ref_batched_episodes_on

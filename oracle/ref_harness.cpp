@@ -110,6 +110,30 @@ struct Handle
     std::mt19937 mark;
     std::string err;
     long adapter_events = -1; // what the last ref_adapter_episodes' CUDA belief did beyond plain filtering
+    double update_seconds = 0; // wall time inside updateEstimation during the last ref_adapter_episodes
+    long update_calls     = 0;
+};
+
+// forwards to a belief and times its updateEstimation calls
+class TimedBelief : public beliefs::BABelief
+{
+public:
+    TimedBelief(beliefs::BABelief* b, Handle* h) : _b(b), _h(h) {}
+    void initiate(POMDP const& d) override { _b->initiate(d); }
+    void free(POMDP const& d) override { _b->free(d); }
+    State const* sample() const override { return _b->sample(); }
+    void resetDomainStateDistribution(BAPOMDP const& b) override { _b->resetDomainStateDistribution(b); }
+    void updateEstimation(Action const* a, Observation const* o, POMDP const& d) override
+    {
+        auto t0 = std::chrono::steady_clock::now();
+        _b->updateEstimation(a, o, d);
+        _h->update_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        ++_h->update_calls;
+    }
+
+private:
+    beliefs::BABelief* _b;
+    Handle* _h;
 };
 
 bool g_rng_initiated = false;
@@ -1133,11 +1157,13 @@ int ref_adapter_episodes(void* hv, int kind, long n, char const* planner, int si
         }
 
         belief->initiate(*h->sim);
+        h->update_seconds = 0, h->update_calls = 0;
+        TimedBelief timed(belief.get(), h);
         for (int e = 0; e < episodes; ++e)
         {
-            belief->resetDomainStateDistribution(*h->sim);
+            timed.resetDomainStateDistribution(*h->sim);
             auto r = episode::run(
-                *plan, *belief, *h->env, *h->sim, Horizon(conf.horizon), Discount(conf.discount));
+                *plan, timed, *h->env, *h->sim, Horizon(conf.horizon), Discount(conf.discount));
             returns[e] = r.ret.toDouble();
         }
         // how often the structure-learning part of a CUDA belief ran (MH runs, Gibbs chains, cheats)
@@ -1161,6 +1187,14 @@ int ref_adapter_episodes(void* hv, int kind, long n, char const* planner, int si
 long ref_adapter_events(void* hv)
 {
     return static_cast<Handle*>(hv)->adapter_events;
+}
+
+// seconds spent inside Belief::updateEstimation during the last ref_adapter_episodes, and the number of calls
+double ref_adapter_update_seconds(void* hv, long* calls)
+{
+    auto h = static_cast<Handle*>(hv);
+    *calls = h->update_calls;
+    return h->update_seconds;
 }
 
 
