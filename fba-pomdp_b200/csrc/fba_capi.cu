@@ -2501,12 +2501,17 @@ extern "C" int fba_belief_sample_state_history(fba_belief* b, int32_t method, in
         else if (replay)
             LAUNCH(ctx, (k_state_history_rs<true, false>), blocks_for(b->N, 32), 32, D, b->counts[b->cur], b->stride,
                    b->sid[b->cur], b->N, h.H, ra, (int*)d_out, out_len, (int*)d_failed, ctx->d_flag);
-        else if (lr)
-            LAUNCH(ctx, (k_state_history_rs<false, true>), blocks_for(b->N, 32), 32, D, b->counts[b->cur], b->stride,
-                   b->sid[b->cur], b->N, h.H, ra, (int*)d_out, out_len, (int*)d_failed, ctx->d_flag);
         else
-            LAUNCH(ctx, (k_state_history_rs<false, false>), blocks_for(b->N, 32), 32, D, b->counts[b->cur], b->stride,
-                   b->sid[b->cur], b->N, h.H, ra, (int*)d_out, out_len, (int*)d_failed, ctx->d_flag);
+        { // PHILOX: one warp per particle, 32 attempts per round (the thread-per-particle kernel is the REPLAY form)
+            PoolTmp<int> d_scratch;
+            if ((rc = d_scratch.alloc(ctx, (size_t)b->N * 32 * (h.H.max_len + 1)))) return rc;
+            if (lr)
+                LAUNCH(ctx, (k_state_history_rs_warp<true>), blocks_for(b->N * 32, 64), 64, D, b->counts[b->cur], b->stride,
+                       b->sid[b->cur], b->N, h.H, ra, (int*)d_out, out_len, (int*)d_scratch, (int*)d_failed);
+            else
+                LAUNCH(ctx, (k_state_history_rs_warp<false>), blocks_for(b->N * 32, 64), 64, D, b->counts[b->cur], b->stride,
+                       b->sid[b->cur], b->N, h.H, ra, (int*)d_out, out_len, (int*)d_scratch, (int*)d_failed);
+        }
     } else
     {
         // flattenT / flattenO of every particle: A S S + A O S floats each, and (max_len + 2) S doubles of messages

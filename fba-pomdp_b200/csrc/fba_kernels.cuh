@@ -2819,6 +2819,65 @@ __global__ void __launch_bounds__(kThreads)
     if (g.overrun) *overrun = 1;
 }
 
+// The same in PHILOX mode with ONE WARP per particle: the attempts of an episode are independent draws, so the 32
+// lanes make one attempt each per round, each from its own Philox stream, and the lowest lane that reproduced the
+// observations supplies the episode's states — the same distribution as attempting one after the other, but a
+// model that explains the history badly (attempts are geometric, the tail is heavy) costs 1/32 of the rounds, which
+// is what a lockstep sweep over many chains waits for. scratch: per lane (max_len + 1) states.
+template<bool LONG>
+__global__ void __launch_bounds__(kThreads)
+    k_state_history_rs_warp(DevModel M, const float* __restrict__ counts, long long stride, const int* __restrict__ sid,
+                            long long N, HistoryArgs H, RngArgs ra, int* __restrict__ states_out, long long out_stride,
+                            int* __restrict__ scratch, int* __restrict__ failed)
+{
+    long long const i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int const lane    = threadIdx.x & 31;
+    if (i >= N) return;
+    PhiloxRng g(ra.seed, ra.stream_base + (unsigned long long)i * 32ull + (unsigned long long)lane, ra.offset);
+    float* c          = const_cast<float*>(counts) + i * stride; // STEP_KEEP never writes
+    const Node* nodes = M.nodes + (long long)sid[i] * M.A * M.J;
+    int* out          = states_out + i * out_stride;
+    int* mine         = scratch + (i * 32 + lane) * (long long)(H.max_len + 1);
+    long long attempts = 0;
+    int first = 0, pos = 0;
+    for (int e = 0; e < H.n_episodes; ++e)
+    {
+        int const len = H.episode_len[e];
+        for (;;)
+        {
+            attempts += 32;
+            if (attempts > H.max_attempts + 31)
+            {
+                if (lane == 0) *failed = 1;
+                return;
+            }
+            int s   = sample_start_state(M, g);
+            mine[0] = s;
+            int t   = 0;
+            for (; t < len; ++t)
+            {
+                int o;
+                Feat x2;
+                s = hyper_step<STEP_KEEP, PhiloxRng, false, LONG, false>(M, nodes + (long long)H.actions[first + t] * M.J, c, s,
+                                                                         g, o, x2, nullptr);
+                if (o != H.observations[first + t]) break;
+                mine[1 + t] = s;
+            }
+            unsigned const ok = __ballot_sync(0xffffffffu, t == len);
+            if (ok)
+            {
+                int const winner  = __ffs(ok) - 1;
+                const int* theirs = scratch + (i * 32 + winner) * (long long)(H.max_len + 1);
+                __syncwarp();
+                for (int k = lane; k <= len; k += 32) out[pos + k] = theirs[k];
+                break;
+            }
+        }
+        first += len;
+        pos += len + 1;
+    }
+}
+
 // BABNModel::flattenT / flattenO (BABNModel.cpp:89-178) of every particle into scratch, laid out for the
 // message passes below: Tt[a][s'][s] (the threads of a pass run over s) and Ot[a][o][s]. Every entry starts
 // at 1.0f and is multiplied, feature after feature, by that node's expected multinomial (float sum, float
