@@ -1159,11 +1159,14 @@ int ref_adapter_episodes(void* hv, int kind, long n, char const* planner, int si
         belief->initiate(*h->sim);
         h->update_seconds = 0, h->update_calls = 0;
         TimedBelief timed(belief.get(), h);
+        // the CUDA planners need to see the CUDA belief itself (they read its device handle): no timing wrapper there
+        bool const cuda_planner = conf.planner.rfind("cuda-", 0) == 0;
+        beliefs::BABelief& used = cuda_planner ? *belief : static_cast<beliefs::BABelief&>(timed);
         for (int e = 0; e < episodes; ++e)
         {
-            timed.resetDomainStateDistribution(*h->sim);
+            used.resetDomainStateDistribution(*h->sim);
             auto r = episode::run(
-                *plan, timed, *h->env, *h->sim, Horizon(conf.horizon), Discount(conf.discount));
+                *plan, used, *h->env, *h->sim, Horizon(conf.horizon), Discount(conf.discount));
             returns[e] = r.ret.toDouble();
         }
         // how often the structure-learning part of a CUDA belief ran (MH runs, Gibbs chains, cheats)
