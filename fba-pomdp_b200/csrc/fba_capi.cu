@@ -28,6 +28,7 @@ struct fba_ctx
     // optional per-kernel CUDA-event timing (fba_ctx_profile_*)
     int bulk_copy    = 0;  // 1: full-copy gathers go through the TMA engine (k_gather_bulk)
     int rollout_coop = -1; // -1 auto (by batch size and row length), 0 thread per rollout, 1 warp per rollout
+    bool nested_exact = false; // PHILOX NestedBelief updates: thread per top particle instead of warp per top particle
     bool inplace_resample = true; // PHILOX mode: survivors keep their slot (fba_ctx_set_option)
     bool fused_update     = true; // small beliefs: update + resample in ONE launch (k_runs_step, one CTA)
     long long parallel_chains_min = 8192; // REPLAY: beliefs at least this large evaluate the reference's
@@ -361,6 +362,11 @@ extern "C" int fba_ctx_set_option(fba_ctx* ctx, const char* name, int64_t value)
     if (!strcmp(name, "rollout_coop"))
     {
         ctx->rollout_coop = (int)value;
+        return FBA_OK;
+    }
+    if (!strcmp(name, "nested_exact"))
+    { // 1: PHILOX-mode NestedBelief updates run the reference's loop attempt by attempt (one thread per top particle)
+        ctx->nested_exact = value != 0;
         return FBA_OK;
     }
     ctx->err = std::string("unknown option ") + name;
@@ -2926,7 +2932,7 @@ extern "C" int fba_nested_update(fba_nested* n, int32_t action, int32_t observat
         else
             LAUNCH_NESTED(true, false, false);
         rng->cursor += per * n->n_top;
-    } else
+    } else if (ctx->nested_exact)
     {
         RngArgs const ra = philox_args(rng);
         if (D.sampled)
@@ -2938,6 +2944,23 @@ extern "C" int fba_nested_update(fba_nested* n, int32_t action, int32_t observat
             LAUNCH_NESTED(false, true, false);
         else
             LAUNCH_NESTED(false, false, false);
+    } else
+    { // one warp per top particle, 32 attempts per round (k_nested_update_warp)
+        RngArgs const ra = philox_args(rng);
+#define LAUNCH_NESTED_WARP(L, S)                                                                                   \
+    LAUNCH(ctx, (k_nested_update_warp<L, S>), blocks_for(n->n_top * 32, 64), 64, D, b->counts[b->cur], b->stride,    \
+           b->sid[b->cur], b->w, n->n_top, n->n_bottom, n->states[n->cur], n->states[n->cur ^ 1], (int)action,     \
+           (int)observation, amount, (long long)max_attempts, ra, n->d_attempts, n->d_failed)
+        if (D.sampled)
+        {
+            if (lr) LAUNCH_NESTED_WARP(true, true);
+            else
+                LAUNCH_NESTED_WARP(false, true);
+        } else if (lr)
+            LAUNCH_NESTED_WARP(true, false);
+        else
+            LAUNCH_NESTED_WARP(false, false);
+#undef LAUNCH_NESTED_WARP
     }
     CU(ctx, cudaMemcpyAsync(ctx->h_flag, n->d_failed, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     if (attempts)

@@ -2767,6 +2767,74 @@ __global__ void __launch_bounds__(kThreads)
     if (g.overrun) *overrun = 1;
 }
 
+// PHILOX mode, one WARP per top particle: the 32 lanes make one attempt each per round, all reading the counts as
+// they stand at the start of the round; the acceptances of a round — the first ones in lane order, up to what the
+// bottom filter still needs — then land together (atomic adds of the same 1 / n_bottom, so the float sums do not
+// depend on their order), and the attempt count is the position of the last one taken. Against the loop above the
+// only difference is that an attempt does not see the (at most 31) increments of 1 / n_bottom made earlier in its own
+// round: a relative change of the sampled rows of order 32 / (n_bottom x row total), invisible at any sample size this
+// belief is run with; REPLAY mode and option "nested_exact" keep the thread-per-particle loop.
+template<bool LONG, bool SAMPLED>
+__global__ void __launch_bounds__(kThreads)
+    k_nested_update_warp(DevModel M, float* counts, long long stride, const int* __restrict__ sid, double* __restrict__ w,
+                         long long n_top, int n_bottom, const int* __restrict__ states_in, int* __restrict__ states_out,
+                         int action, int observation, float amount, long long max_attempts, RngArgs ra,
+                         long long* __restrict__ attempts_out, int* __restrict__ failed)
+{
+    long long const i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int const lane    = threadIdx.x & 31;
+    if (i >= n_top) return;
+    PhiloxRng g(ra.seed, ra.stream_base + (unsigned long long)i * 32ull + (unsigned long long)lane, ra.offset);
+    float* c          = counts + i * stride;
+    const Node* nodes = M.nodes + ((long long)sid[i] * M.A + action) * M.J;
+    const int* in     = states_in + i * (long long)n_bottom;
+    int* out          = states_out + i * (long long)n_bottom;
+    int rec[2 * FBA_MAX_FEATURES];
+    long long count = 0;
+    int accepted    = 0;
+    while (accepted < n_bottom)
+    {
+        if (count >= max_attempts)
+        {
+            if (lane == 0) *failed = 1;
+            break;
+        }
+        int const s = in[draw_k(g, (uint32_t)n_bottom)];
+        int o;
+        Feat x2;
+        int const s2 = hyper_step<STEP_RECORD, PhiloxRng, false, LONG, SAMPLED>(M, nodes, c, s, g, o, x2, rec);
+        unsigned const ok   = __ballot_sync(0xffffffffu, o == observation);
+        int const need      = n_bottom - accepted;
+        int const my_rank   = __popc(ok & ((1u << lane) - 1u));
+        bool const taken    = (o == observation) && my_rank < need;
+        int const n_ok      = __popc(ok);
+        __syncwarp(); // every lane has read the round's counts before any of them changes
+        if (taken)
+        {
+            out[accepted + my_rank] = s2;
+            for (int k = 0; k < M.J; ++k) atomicAdd(c + rec[k], amount);
+        }
+        if (n_ok >= need)
+        { // the attempt that filled the filter is the need-th accepted lane of this round
+            unsigned m = ok;
+            for (int k = 1; k < need; ++k) m &= m - 1;
+            count += __ffs(m);
+            accepted = n_bottom;
+        } else
+        {
+            count += 32;
+            accepted += n_ok;
+        }
+        __syncwarp();
+        __threadfence_block();
+    }
+    if (lane == 0)
+    {
+        if (count > 0) w[i] = __dmul_rn(w[i], __ddiv_rn(1.0, (double)count));
+        if (attempts_out) attempts_out[i] = count;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // MHwithinGibbs (src/beliefs/bayes-adaptive/factored/MHwithinGibbs.cpp): state histories conditioned on a
 // model and the (action, observation) history, and the posterior counts of a state history.

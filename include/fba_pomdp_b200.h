@@ -153,7 +153,10 @@ int64_t fba_ctx_counter(fba_ctx* ctx, int32_t which);
  *          "fused_update" (default 1): fba_belief_update_estimation on a weighted PHILOX belief of at
  *          most 2048 particles runs update + resample in ONE launch (bit-identical to the
  *          launch-per-phase path); 0 = always launch per phase
- *          "bulk_copy" (default 0): 1 = full-copy gathers go through the TMA engine (cp.async.bulk) */
+ *          "bulk_copy" (default 0): 1 = full-copy gathers go through the TMA engine (cp.async.bulk)
+ *          "nested_exact" (default 0): 1 = PHILOX-mode fba_nested_update runs the reference's loop attempt by
+ *          attempt, one thread per top particle (what REPLAY mode always does); 0 = one warp per top particle,
+ *          32 attempts per round that all see the counts as of the start of their round */
 int fba_ctx_set_option(fba_ctx* ctx, const char* name, int64_t value);
 
 /* per-kernel CUDA-event timing on the context's stream: begin, run calls, end, then query the
@@ -417,6 +420,8 @@ int fba_nested_reset_domain_states(fba_nested* n, fba_rng* rng);
  * bottom filter (KeepCounts steps on the particle's own counts) until n_bottom states are accepted, every
  * acceptance adding 1 / n_bottom to the counts it went through BEFORE the next attempt; weight *= 1 /
  * attempts; then WeightedFilter::normalize. One GPU thread per top particle runs that loop as written.
+ * PHILOX mode by default gives each top particle a warp: 32 attempts per round from 32 streams, the round's
+ * acceptances landing together (option "nested_exact" = 1 keeps the attempt-by-attempt loop).
  * attempts (n_top, may be NULL) receives the attempts per top particle. A particle that needs more than
  * max_attempts: FBA_ERR_CAPACITY. REPLAY: top particle i draws from the i-th equal slice of the remaining
  * words (the reference's single stream is data dependent across particles). */

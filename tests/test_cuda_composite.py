@@ -281,10 +281,21 @@ def test_nested_belief_philox_matches_the_oracle_statistically():
     n_top, n_bottom = 512, 64
     counts = np.repeat(g[P + "init_counts"][:1], n_top, 0)
     states = np.random.RandomState(1).randint(0, 2, size=(n_top, n_bottom)).astype(np.int32)
-    nb = NestedBelief(n_top, n_bottom)
-    nb.initiate(sim, struct_id=np.zeros(n_top, np.int32), counts=counts, states=states)
     a, o = 2, 0       # listen, hear left
-    nb.updateEstimation(a, o, fba.Rng.philox(77))
+    # the default PHILOX kernel (a warp per top particle, 32 attempts per round) and the attempt-by-attempt loop
+    # (option "nested_exact") against each other: same acceptance statistics
+    per_kernel = []
+    for exact in (1, 0):
+        ctx.set_option("nested_exact", exact)
+        nb = NestedBelief(n_top, n_bottom)
+        nb.initiate(sim, struct_id=np.zeros(n_top, np.int32), counts=counts, states=states)
+        nb.updateEstimation(a, o, fba.Rng.philox(77))
+        per_kernel.append((nb.attempts.copy(), nb.download()["states"].sum(1)))
+        if exact:
+            nb.free()
+    for got, want in zip(per_kernel[0], per_kernel[1]):
+        se = np.sqrt(got.var(ddof=1) / n_top + want.var(ddof=1) / n_top) + 1e-12
+        assert abs(got.mean() - want.mean()) <= 5 * se, (got.mean(), want.mean(), se)
     d = nb.download()
     # oracle on the same inputs, its own words
     top = O.Belief(n_top, counts.shape[1], True)
