@@ -28,6 +28,8 @@ struct fba_ctx
     // optional per-kernel CUDA-event timing (fba_ctx_profile_*)
     int bulk_copy    = 0;  // 1: full-copy gathers go through the TMA engine (k_gather_bulk)
     int rollout_coop = -1; // -1 auto (by batch size and row length), 0 thread per rollout, 1 warp per rollout
+    void* big_scratch = nullptr; // grow-only: the flattened models + messages of fba_belief_sample_state_history
+    size_t big_scratch_bytes = 0;
     bool nested_exact = false; // PHILOX NestedBelief updates: thread per top particle instead of warp per top particle
     bool inplace_resample = true; // PHILOX mode: survivors keep their slot (fba_ctx_set_option)
     bool fused_update     = true; // small beliefs: update + resample in ONE launch (k_runs_step, one CTA)
@@ -297,6 +299,7 @@ extern "C" void fba_ctx_destroy(fba_ctx* ctx)
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
     cudaFree(ctx->d_words);
     cudaFree(ctx->d_offsets);
+    cudaFree(ctx->big_scratch);
     cudaFree(ctx->d_flag);
     cudaFree(ctx->d_counters);
     cudaFreeHost(ctx->h_flag);
@@ -2520,29 +2523,62 @@ extern "C" int fba_belief_sample_state_history(fba_belief* b, int32_t method, in
         }
     } else
     {
+        {
+            int cells = 0;
+            for (int f = 0; f < D.FS; ++f) cells += D.feat_s[f];
+            for (int f = 0; f < D.FO; ++f) cells += D.feat_o[f];
+            REQUIRE(ctx, cells <= kFlattenCells, "sample_state_history: the feature ranges sum to more than 192");
+        }
         // flattenT / flattenO of every particle: A S S + A O S floats each, and (max_len + 2) S doubles of messages
         double const bytes = (double)b->N * ((double)D.A * D.S * ((double)D.S + D.O) * 4.0 + (h.H.max_len + 2.0) * D.S * 8.0);
         REQUIRE(ctx, bytes < 64e9, "sample_state_history: the flattened models of these particles do not fit (N A S (S + O) floats)");
         std::vector<unsigned char> used((size_t)D.A, 0);
         for (long long k = 0; k < h.total; ++k) used[(size_t)actions[k]] = 1;
         PoolTmp<unsigned char> d_used;
-        PoolTmp<float> d_T, d_O, d_prior;
-        PoolTmp<double> d_msg;
-        if ((rc = d_used.alloc(ctx, (size_t)D.A)) || (rc = d_T.alloc(ctx, (size_t)b->N * D.A * D.S * D.S))
-            || (rc = d_O.alloc(ctx, (size_t)b->N * D.A * D.O * D.S)) || (rc = d_prior.alloc(ctx, (size_t)D.S))
-            || (rc = d_msg.alloc(ctx, (size_t)b->N * (h.H.max_len + 2) * D.S)))
-            return rc;
+        PoolTmp<float> d_prior;
+        if ((rc = d_used.alloc(ctx, (size_t)D.A)) || (rc = d_prior.alloc(ctx, (size_t)D.S))) return rc;
+        // the big pieces live in one grow-only buffer of the context: gigabytes for large S, and allocating them
+        // per call cost several times the kernels
+        size_t const nT = (size_t)b->N * D.A * D.S * D.S, nO = (size_t)b->N * D.A * D.O * D.S,
+                     nM = (size_t)b->N * (h.H.max_len + 2) * D.S;
+        size_t const bytes_needed = nM * sizeof(double) + (nT + nO) * sizeof(float);
+        if (bytes_needed > ctx->big_scratch_bytes)
+        {
+            CU(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->big_scratch);
+            ctx->big_scratch = nullptr, ctx->big_scratch_bytes = 0;
+            CU(ctx, cudaMalloc(&ctx->big_scratch, bytes_needed));
+            ctx->big_scratch_bytes = bytes_needed;
+        }
+        double* const d_msg = (double*)ctx->big_scratch;
+        float* const d_T    = (float*)(d_msg + nM);
+        float* const d_O    = d_T + nT;
         CU(ctx, cudaMemcpyAsync(d_used, used.data(), used.size(), cudaMemcpyHostToDevice, ctx->stream));
         CU(ctx, cudaMemcpyAsync(d_prior, state_prior, (size_t)D.S * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
         dim3 const grid((unsigned)std::min<long long>(blocks_for((long long)D.A * D.S), 4 * ctx->sm_count), (unsigned)b->N);
+        int const msg_threads = (int)std::min<long long>(kMsgThreads, std::max<long long>(64, ((long long)D.S + 31) / 32 * 32));
         LAUNCH(ctx, k_flatten_model, grid, kThreads, D, b->counts[b->cur], b->stride, b->sid[b->cur],
                (const unsigned char*)d_used, (float*)d_T, (float*)d_O);
-        if (replay)
-            LAUNCH(ctx, (k_state_history_msg<true>), (int)b->N, kThreads, D, b->N, h.H, (const float*)d_T, (const float*)d_O,
-                   (const float*)d_prior, (double*)d_msg, ra, (int*)d_out, out_len, ctx->d_flag);
+        bool const sh          = (size_t)D.S * 2 * sizeof(double) <= 48 * 1024; // two message rows in shared memory
+        size_t const sh_bytes  = sh ? (size_t)D.S * 2 * sizeof(double) : 0;
+#define LAUNCH_MSG(R, SHM)                                                                                         \
+    do {                                                                                                           \
+        if (ctx->profiling) profile_mark(ctx, "k_state_history_msg", true);                                        \
+        k_state_history_msg<R, SHM><<<(int)b->N, msg_threads, sh_bytes, ctx->stream>>>(                            \
+            D, b->N, h.H, (const float*)d_T, (const float*)d_O, (const float*)d_prior, (double*)d_msg, ra,         \
+            (int*)d_out, out_len, ctx->d_flag);                                                                    \
+        if (ctx->profiling) profile_mark(ctx, "k_state_history_msg", false);                                       \
+        ++ctx->launches;                                                                                           \
+        CU(ctx, cudaGetLastError());                                                                               \
+    } while (0)
+        if (replay && sh) LAUNCH_MSG(true, true);
+        else if (replay)
+            LAUNCH_MSG(true, false);
+        else if (sh)
+            LAUNCH_MSG(false, true);
         else
-            LAUNCH(ctx, (k_state_history_msg<false>), (int)b->N, kThreads, D, b->N, h.H, (const float*)d_T,
-                   (const float*)d_O, (const float*)d_prior, (double*)d_msg, ra, (int*)d_out, out_len, ctx->d_flag);
+            LAUNCH_MSG(false, false);
+#undef LAUNCH_MSG
     }
     CU(ctx, cudaMemcpyAsync(ctx->h_flag, d_failed, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaMemcpyAsync(states, d_out, (size_t)b->N * out_len * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

@@ -2950,6 +2950,8 @@ __global__ void __launch_bounds__(kThreads)
 // message passes below: Tt[a][s'][s] (the threads of a pass run over s) and Ot[a][o][s]. Every entry starts
 // at 1.0f and is multiplied, feature after feature, by that node's expected multinomial (float sum, float
 // divide). Only the actions that occur in the history are flattened (used[a]).
+constexpr int kFlattenCells = 2 * kMaxJournalCells; // conditional expectations one (action, state) pair may hold
+
 __global__ void __launch_bounds__(kThreads)
     k_flatten_model(DevModel M, const float* __restrict__ counts, long long stride, const int* __restrict__ sid,
                     const unsigned char* __restrict__ used, float* __restrict__ Tt_all, float* __restrict__ Ot_all)
@@ -2966,30 +2968,32 @@ __global__ void __launch_bounds__(kThreads)
         if (!used[a]) continue;
         const Node* nodes = M.nodes + ((long long)sid[p] * M.A + a) * M.J;
         Feat const x      = decode(s, M.step_s, M.FS, M.pow2_s, M.shift_s);
+        // DBNNode::expectation of every node for this (action, parent state), once (BABNModel.cpp:105-111,152-158):
+        // the S (or O) products below only pick entries of these rows
+        float cond[kFlattenCells];
+        int first[2 * FBA_MAX_FEATURES];
+        int n_cells = 0;
+        for (int f = 0; f < M.J; ++f)
+        {
+            Node const nd   = nodes[f];
+            int const range = (f < M.FS) ? M.feat_s[f] : M.feat_o[f - M.FS];
+            const float* row = c + nd.off + parent_config(M, nd.par, x) * range;
+            first[f]         = n_cells;
+            for (int v = 0; v < range; ++v) cond[n_cells + v] = expected_mult_at(row, range, v);
+            n_cells += range;
+        }
         for (int s2 = 0; s2 < M.S; ++s2)
         {
             Feat const x2 = decode(s2, M.step_s, M.FS, M.pow2_s, M.shift_s);
             float pr      = 1.0f;
-            for (int f = 0; f < M.FS; ++f)
-            {
-                Node const nd   = nodes[f];
-                int const range = M.feat_s[f];
-                pr = __fmul_rn(pr, expected_mult_at(c + nd.off + parent_config(M, nd.par, x) * range, range,
-                                                    x2.get(f, single_s)));
-            }
+            for (int f = 0; f < M.FS; ++f) pr = __fmul_rn(pr, cond[first[f] + x2.get(f, single_s)]);
             Tt[((long long)a * M.S + s2) * M.S + s] = pr;
         }
         for (int o = 0; o < M.O; ++o)
         { // the observation's parents are the features of the state it is made in
             Feat const of = decode(o, M.step_o, M.FO, M.pow2_o, M.shift_o);
             float pr      = 1.0f;
-            for (int q = 0; q < M.FO; ++q)
-            {
-                Node const nd   = nodes[M.FS + q];
-                int const range = M.feat_o[q];
-                pr = __fmul_rn(pr, expected_mult_at(c + nd.off + parent_config(M, nd.par, x) * range, range,
-                                                    of.get(q, single_o)));
-            }
+            for (int q = 0; q < M.FO; ++q) pr = __fmul_rn(pr, cond[first[M.FS + q] + of.get(q, single_o)]);
             Ot[((long long)a * M.O + o) * M.S + s] = pr;
         }
     }
@@ -3015,20 +3019,29 @@ __device__ __forceinline__ int sample_from_mult_d(const double* mult, int n, dou
 // sum over states (thread 0) — then the forward pass: s_0 from message[0], s_t+1 from T[s_t][a_t][.] *
 // message[t+1][.] with its sequential total (thread 0 draws). msg: per particle (max_len + 2) x S doubles of
 // scratch (the last row holds the forward pass's products).
-template<bool REPLAY>
-__global__ void __launch_bounds__(kThreads)
+constexpr int kMsgThreads = 1024; // one state per thread up to S = 1024: the passes are bound by loads in flight
+
+// (Measured and dropped: widening the float table entries to double on the integer pipe instead of F2F.F64.F32 —
+// ncu showed the stalls on the converter were the wait for the loads it is the first consumer of, and the extra
+// integer instructions made the pass slower, 9.6 -> 13.4 ms; profiles/r2n_*.)
+// SH: the message row being read and the row being built live in shared memory (2 S doubles) — the sequential
+// parts (thread 0 adds S values in order, then walks them to draw) then run at shared-memory latency instead of
+// L2 latency while the other threads wait; models with more than 3072 states fall back to global rows.
+template<bool REPLAY, bool SH>
+__global__ void __launch_bounds__(kMsgThreads)
     k_state_history_msg(DevModel M, long long N, HistoryArgs H, const float* __restrict__ Tt_all,
                         const float* __restrict__ Ot_all, const float* __restrict__ state_prior,
                         double* __restrict__ msg_all, RngArgs ra, int* __restrict__ states_out, long long out_stride,
                         int* __restrict__ overrun)
 {
+    extern __shared__ double sh_rows[];
     long long const p = blockIdx.x;
     if (p >= N) return;
     int const S     = M.S;
     const float* Tt = Tt_all + p * (long long)M.A * S * S;
     const float* Ot = Ot_all + p * (long long)M.A * M.O * S;
     double* msg     = msg_all + p * (long long)(H.max_len + 2) * S;
-    double* probs   = msg + (long long)(H.max_len + 1) * S;
+    double* work    = SH ? sh_rows + S : msg + (long long)(H.max_len + 1) * S; // the row being built / the forward products
     int* out        = states_out + p * out_stride;
     auto g          = RngOf<REPLAY>::make(ra, p);
     __shared__ double sh_tot;
@@ -3040,36 +3053,70 @@ __global__ void __launch_bounds__(kThreads)
         const int* act = H.actions + first;
         const int* obs = H.observations + first;
         for (int s = threadIdx.x; s < S; s += blockDim.x)
-            msg[(long long)len * S + s] = (double)Ot[((long long)act[len - 1] * M.O + obs[len - 1]) * S + s];
+        {
+            double const v              = (double)Ot[((long long)act[len - 1] * M.O + obs[len - 1]) * S + s];
+            msg[(long long)len * S + s] = v;
+            if (SH) sh_rows[s] = v;
+        }
         __syncthreads();
         for (int step = len - 1; step >= 0; --step)
         {
             const float* Ta    = Tt + (long long)act[step] * S * S;
-            const double* next = msg + (long long)(step + 1) * S;
+            const double* next = SH ? sh_rows : msg + (long long)(step + 1) * S;
             for (int s = threadIdx.x; s < S; s += blockDim.x)
             {
+                // the sum itself is sequential (std::inner_product's order); the loads are not: eight rows of T in
+                // flight per thread before the adds that need them
+                // (software-pipelined: the next eight are requested before the current eight are added, 16 in flight)
                 double acc = 0.0;
-                for (int s2 = 0; s2 < S; ++s2) acc = __dadd_rn(acc, __dmul_rn((double)Ta[(long long)s2 * S + s], next[s2]));
+                int s2     = 0;
+                float t[8], t_next[8];
+                bool have = S >= 8;
+                if (have)
+                {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) t[u] = __ldcs(Ta + (long long)u * S + s);
+                }
+                while (have)
+                {
+                    bool const more = s2 + 16 <= S;
+                    if (more)
+                    {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) t_next[u] = __ldcs(Ta + (long long)(s2 + 8 + u) * S + s);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) acc = __dadd_rn(acc, __dmul_rn((double)t[u], next[s2 + u]));
+                    s2 += 8;
+                    have = more;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) t[u] = t_next[u];
+                }
+                for (; s2 < S; ++s2) acc = __dadd_rn(acc, __dmul_rn((double)Ta[(long long)s2 * S + s], next[s2]));
                 float const factor = (step != 0) ? Ot[((long long)act[step - 1] * M.O + obs[step - 1]) * S + s]
                                                  : state_prior[s];
-                msg[(long long)step * S + s] = __dmul_rn(acc, (double)factor);
+                work[s] = __dmul_rn(acc, (double)factor);
             }
             __syncthreads();
             if (threadIdx.x == 0)
             {
                 double tot = 0.0;
-                for (int s = 0; s < S; ++s) tot = __dadd_rn(tot, msg[(long long)step * S + s]);
+                for (int s = 0; s < S; ++s) tot = __dadd_rn(tot, work[s]);
                 sh_tot = tot;
             }
             __syncthreads();
             double const tot = sh_tot;
             for (int s = threadIdx.x; s < S; s += blockDim.x)
-                msg[(long long)step * S + s] = __ddiv_rn(msg[(long long)step * S + s], tot);
+            {
+                double const v               = __ddiv_rn(work[s], tot);
+                msg[(long long)step * S + s] = v;
+                if (SH) sh_rows[s] = v;
+            }
             __syncthreads();
         }
         if (threadIdx.x == 0)
         {
-            sh_state   = sample_from_mult_d(msg, S, 1.0, g);
+            sh_state   = sample_from_mult_d(SH ? sh_rows : msg, S, 1.0, g);
             out[pos++] = sh_state;
         }
         __syncthreads();
@@ -3079,13 +3126,13 @@ __global__ void __launch_bounds__(kThreads)
             const float* Ta    = Tt + (long long)act[step] * S * S;
             const double* next = msg + (long long)(step + 1) * S;
             for (int s2 = threadIdx.x; s2 < S; s2 += blockDim.x)
-                probs[s2] = __dmul_rn((double)Ta[(long long)s2 * S + state], next[s2]);
+                work[s2] = __dmul_rn((double)Ta[(long long)s2 * S + state], next[s2]);
             __syncthreads();
             if (threadIdx.x == 0)
             {
                 double tot = 0.0;
-                for (int s2 = 0; s2 < S; ++s2) tot = __dadd_rn(tot, probs[s2]);
-                sh_state   = sample_from_mult_d(probs, S, tot, g);
+                for (int s2 = 0; s2 < S; ++s2) tot = __dadd_rn(tot, work[s2]);
+                sh_state   = sample_from_mult_d(work, S, tot, g);
                 out[pos++] = sh_state;
             }
             __syncthreads();
