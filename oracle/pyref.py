@@ -339,6 +339,17 @@ class Ref:
         self.L.ref_nested_sample(self.h, _p(out))
         return int(out[0]), int(out[1])
 
+    def mutate(self, t_par, o_par):
+        """FBAPOMDP::mutate on one structure (parent bitmasks) -> (t_par, o_par) of the mutated structure"""
+        f = self.L.ref_mutate
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p] * 5
+        tp, op = np.ascontiguousarray(t_par, np.uint32), np.ascontiguousarray(o_par, np.uint32)
+        to, oo = np.zeros_like(tp), np.zeros_like(op)
+        if f(self.h, _p(tp), _p(op), _p(to), _p(oo)):
+            raise RuntimeError(self.L.ref_error(self.h).decode())
+        return to, oo
+
     def gibbs_run(self):
         """the private MHwithinGibbs::reinvigorate on the belief as it is"""
         self.L.ref_gibbs_run.argtypes = [C.c_void_p]

@@ -563,6 +563,51 @@ long ref_prior_model(void* hv, uint32_t const* t_par, uint32_t const* o_par, flo
     return -1;
 }
 
+// FBAPOMDP::mutate (the domain prior's mutate, FBAPOMDP.cpp:57-61) on a structure given as parent bitmasks
+int ref_mutate(void* hv, uint32_t const* t_par, uint32_t const* o_par, uint32_t* t_out, uint32_t* o_out)
+{
+    auto h = static_cast<Handle*>(hv);
+    try
+    {
+        auto const& fba = dynamic_cast<FactoredPOMDP const&>(*h->sim);
+        int const A = h->sim->domainSize()->_A, FS = (int)h->feat_s.size(), FO = (int)h->feat_o.size();
+        ::bayes_adaptive::factored::BABNModel::Structure st;
+        st.T.resize(A), st.O.resize(A);
+        for (int a = 0; a < A; ++a)
+        {
+            for (int f = 0; f < FS; ++f)
+            {
+                std::vector<int> par;
+                for (int p = 0; p < FS; ++p)
+                    if (t_par[a * FS + f] & (1u << p)) par.push_back(p);
+                st.T[a].push_back(par);
+            }
+            for (int g = 0; g < FO; ++g)
+            {
+                std::vector<int> par;
+                for (int p = 0; p < FS; ++p)
+                    if (o_par[a * FO + g] & (1u << p)) par.push_back(p);
+                st.O[a].push_back(par);
+            }
+        }
+        auto out = fba.mutate(st);
+        for (int a = 0; a < A; ++a)
+        {
+            for (int f = 0; f < FS; ++f) t_out[a * FS + f] = maskOf(out.T[a][f]);
+            for (int g = 0; g < FO; ++g) o_out[a * FO + g] = maskOf(out.O[a][g]);
+        }
+    } catch (std::string const& e)
+    {
+        h->err = e;
+        return 1;
+    } catch (char const* e)
+    {
+        h->err = e;
+        return 1;
+    }
+    return 0;
+}
+
 // The steps of computePosterior (MHNIPS2018.cpp:41-109) driven from here through the reference's own
 // model API (BABNModel::sampleStateIndex / sampleObservationIndex / incrementCountsOf,
 // FBAPOMDP::sampleDomainState) on computePriorModel(structure): a second opinion on the oracle's

@@ -316,3 +316,59 @@ def test_nested_belief_philox_matches_the_oracle_statistically():
     nb.free()
     sim.close()
     ctx.close()
+
+
+MUTATE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mutate.npz")
+
+
+@pytest.mark.parametrize("name", ["gridworld", "ftiger", "ca", "sysadmin"])
+def test_domain_mutate_replay(name):
+    """The C ABI's mutate (inside fba_belief_breed_into / _reinvigorate) against the reference's FBAPOMDP::mutate on the
+    four domains that have one, the gridworld one included (the reference's reinvigoration cannot reach it): one
+    breed per recorded mutation — a one-particle structure donor holding the input structure, a one-particle fully
+    connected counts donor — fed [2 donor-draw words | the reference's mutate words]: the bred particle has the
+    reference's output structure and every word is consumed."""
+    import fba_pomdp_b200 as fba
+    from fba_pomdp_b200.capi import ptr
+    import ctypes as C
+    g = np.load(MUTATE)
+    P = name + "/"
+    desc = {k[len(P + "model/"):]: g[k] for k in g.files if k.startswith(P + "model/")}
+    A, FS, FO = int(desc["A"]), len(desc["feat_s"]), len(desc["feat_o"])
+    full = (1 << FS) - 1
+    t_all = np.concatenate([np.full((1, A * FS), full, np.uint32), g[P + "t_in"], g[P + "t_out"]])
+    o_all = np.concatenate([np.full((1, A * FO), full, np.uint32), g[P + "o_in"], g[P + "o_out"]])
+    ctx = fba.Context(0)
+    sim = fba.BAPOMDP(ctx, desc, t_all, o_all, max_structures=len(t_all) + 8)
+    key = {}
+    for i in range(sim.num_structures):
+        t, o = sim.structure(i)
+        key[(t.reshape(-1).tobytes(), o.reshape(-1).tobytes())] = i
+    stride = sim.max_structure_size()
+    fc = fba.BARejectionSampling(1)
+    fc.initiate(sim, struct_id=np.array([key[(t_all[0].tobytes(), o_all[0].tobytes())]], np.int32),
+                counts=np.ones((1, stride), np.float32), state=np.zeros(1, np.int32), stride=stride)
+    words, pos = g[P + "words"], 0
+    for k in range(len(g[P + "t_in"])):
+        nw = int(g[P + "n_words"][k])
+        donor = fba.BARejectionSampling(1)
+        donor.initiate(sim, struct_id=np.array([key[(g[P + "t_in"][k].tobytes(), g[P + "o_in"][k].tobytes())]], np.int32),
+                       counts=np.ones((1, stride), np.float32), state=np.array([1], np.int32), stride=stride)
+        dst = fba.BARejectionSampling(1)
+        dst.initiate(sim, struct_id=np.zeros(1, np.int32), counts=np.zeros((1, stride), np.float32),
+                     state=np.zeros(1, np.int32), stride=stride)
+        rng = fba.Rng.replay(np.concatenate([np.array([7, 11], np.uint32), words[pos:pos + nw]]))
+        slot = np.zeros(1, np.int64)
+        rc = ctx.L.fba_belief_breed_into(dst.h, ptr(slot), 1, donor.h, fc.h, int(g[P + "kind"]), C.byref(rng))
+        assert rc == 0, ctx.L.fba_last_error(ctx.h)
+        assert rng.exhausted, k
+        d = dst.download()
+        t, o = sim.structure(int(d["struct_id"][0]))
+        np.testing.assert_array_equal(t.reshape(-1), g[P + "t_out"][k])
+        np.testing.assert_array_equal(o.reshape(-1), g[P + "o_out"][k])
+        assert d["state"][0] == 1                   # breed: the structure donor's domain state
+        pos += nw
+        donor.free(), dst.free()
+    fc.free()
+    sim.close()
+    ctx.close()
