@@ -45,7 +45,7 @@ SYMBOLS = [
     "fba_tree_create", "fba_tree_destroy", "fba_tree_search",
     "fba_runs_create", "fba_runs_destroy", "fba_runs_belief", "fba_runs_init_sampled",
     "fba_runs_update_estimation", "fba_runs_reset_domain_states", "fba_runs_sample", "fba_runs_copies", "fba_runs_plan", "fba_runs_init",
-    "fba_belief_replace_from", "fba_belief_cheat", "fba_belief_breed_into", "fba_belief_least_likely", "fba_belief_promote", "fba_belief_redraw_domain_states", "fba_belief_sample_state_history", "fba_belief_add_history_counts",
+    "fba_belief_replace_from", "fba_belief_cheat", "fba_belief_breed_into", "fba_belief_least_likely", "fba_belief_promote", "fba_belief_compact", "fba_belief_delta_capacity", "fba_belief_redraw_domain_states", "fba_belief_sample_state_history", "fba_belief_add_history_counts",
     "fba_nested_create", "fba_nested_destroy", "fba_nested_top", "fba_nested_bottom_size", "fba_nested_upload_states",
     "fba_nested_download_states", "fba_nested_reset_domain_states", "fba_nested_update", "fba_nested_sample",
 ]
@@ -195,6 +195,8 @@ def lib():
             "fba_belief_least_likely": (C.c_int, [vp, i64, vp]),
             "fba_belief_promote": (C.c_int, [vp, vp, dbl, vp, vp]),
             "fba_belief_redraw_domain_states": (C.c_int, [vp, vp]),
+            "fba_belief_compact": (C.c_int, [vp]),
+            "fba_belief_delta_capacity": (i32, [vp]),
             "fba_belief_sample_state_history": (C.c_int, [vp, i32, i32, vp, vp, vp, vp, vp, i64, vp]),
             "fba_belief_add_history_counts": (C.c_int, [vp, i32, vp, vp, vp, vp, i32]),
             "fba_nested_create": (C.c_int, [vp, vp, i64, i64, i64, pp]),

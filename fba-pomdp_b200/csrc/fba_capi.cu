@@ -30,6 +30,7 @@ struct fba_ctx
     int rollout_coop = -1; // -1 auto (by batch size and row length), 0 thread per rollout, 1 warp per rollout
     void* big_scratch = nullptr; // grow-only: the flattened models + messages of fba_belief_sample_state_history
     size_t big_scratch_bytes = 0;
+    bool auto_compact = true;  // a full journal / delta list turns the belief into dense storage instead of failing
     bool nested_exact = false; // PHILOX NestedBelief updates: thread per top particle instead of warp per top particle
     bool inplace_resample = true; // PHILOX mode: survivors keep their slot (fba_ctx_set_option)
     bool fused_update     = true; // small beliefs: update + resample in ONE launch (k_runs_step, one CTA)
@@ -365,6 +366,11 @@ extern "C" int fba_ctx_set_option(fba_ctx* ctx, const char* name, int64_t value)
     if (!strcmp(name, "rollout_coop"))
     {
         ctx->rollout_coop = (int)value;
+        return FBA_OK;
+    }
+    if (!strcmp(name, "auto_compact"))
+    { // 0: a full increment list is an error (FBA_ERR_CAPACITY), as before
+        ctx->auto_compact = value != 0;
         return FBA_OK;
     }
     if (!strcmp(name, "nested_exact"))
@@ -1191,6 +1197,53 @@ extern "C" int fba_belief_total_weight(fba_belief* b, double* total)
     return FBA_OK;
 }
 
+// base + delta / base + journal storage -> dense private blocks, in place of the belief's storage
+static int compact_to_dense(fba_belief* b)
+{
+    fba_ctx* ctx = b->ctx;
+    if (b->delta_cap == 0) return FBA_OK;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    size_t free_b = 0, total_b = 0;
+    CU(ctx, cudaMemGetInfo(&free_b, &total_b));
+    size_t const need = (size_t)b->N * b->lstride * sizeof(float);
+    if (need + (512ull << 20) > free_b)
+    {
+        ctx->err = "compact: dense storage of this belief needs " + std::to_string(need >> 20) + " MB, "
+                   + std::to_string(free_b >> 20) + " MB are free";
+        return FBA_ERR_CAPACITY;
+    }
+    float* dense = nullptr;
+    CU(ctx, cudaMalloc(&dense, need));
+    LAUNCH(ctx, k_compact, stream_grid(ctx, b->N), kThreads, (const float*)b->base, b->lstride,
+           (const float*)b->counts[b->cur], b->stride, b->sid[b->cur], (const int*)b->d_proto_sid, dense, b->N,
+           b->m->dev.tabular ? 0 : b->m->dev.J);
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    int const nx = b->cur ^ 1;
+    cudaFree(b->counts[b->cur]), cudaFree(b->counts[nx]), cudaFree(b->state[nx]), cudaFree(b->sid[nx]);
+    b->counts[b->cur] = dense;
+    b->counts[nx] = nullptr, b->state[nx] = nullptr, b->sid[nx] = nullptr; // the back buffer returns on first use
+    cudaFree(b->base), cudaFree(b->d_proto_sid);
+    b->base = nullptr, b->d_proto_sid = nullptr;
+    b->h_base.clear(), b->h_base.shrink_to_fit(), b->h_proto_sid.clear();
+    b->n_bases    = 0;
+    b->stride     = b->lstride;
+    b->delta_cap  = 0;
+    b->delta_used = 0;
+    return FBA_OK;
+}
+
+extern "C" int fba_belief_compact(fba_belief* b)
+{
+    if (!b) return FBA_ERR_INVALID;
+    return compact_to_dense(b);
+}
+
+extern "C" int32_t fba_belief_delta_capacity(const fba_belief* b)
+{
+    return b ? b->delta_cap : 0;
+}
+
 // ---- importance sampling ---------------------------------------------------------------------
 
 static int propose(fba_belief* b, int a, int o, fba_rng* rng, unsigned long long stream_base)
@@ -1204,6 +1257,11 @@ static int propose(fba_belief* b, int a, int o, fba_rng* rng, unsigned long long
     REQUIRE(ctx, o >= 0 && o < D.O, "observation out of range");
     CU(ctx, cudaSetDevice(ctx->device));
     int rc;
+    if (b->delta_cap > 0 && b->delta_used + D.J > b->delta_cap && ctx->auto_compact && !b->peers_open)
+    { // the increment lists are full: continue on dense private blocks (if they fit; otherwise the error below)
+        rc = compact_to_dense(b);
+        if (rc && rc != FBA_ERR_CAPACITY) return rc;
+    }
     if (b->delta_cap > 0)
     {
         // every particle's increment list grows by J per update and copies keep the length, so the host

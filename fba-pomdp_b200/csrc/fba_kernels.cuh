@@ -2429,6 +2429,42 @@ __global__ void __launch_bounds__(kThreads)
     if (w) w[i] = 1.0 / (double)N;
 }
 
+// base + delta / base + journal  ->  dense private blocks (fba_belief_compact): one warp per particle copies its
+// base table and then replays its own increments onto the copy — every increment is exactly +1.0f, so atomic adds in
+// any order give the float sums the sequential replay gives. The particle's sid (a base-table index) becomes the
+// structure id the dense kernels expect.
+__global__ void __launch_bounds__(kThreads)
+    k_compact(const float* __restrict__ base, long long base_stride, const float* __restrict__ blocks, long long stride,
+              int* __restrict__ sid, const int* __restrict__ proto_sid, float* __restrict__ dense, long long N,
+              int journal_J /* 0: tabular delta lists */)
+{
+    int const lane        = threadIdx.x & 31;
+    long long const warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    long long const nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long i = warp0; i < N; i += nwarp)
+    {
+        int const proto = sid[i];
+        float* out      = dense + i * base_stride;
+        warp_copy_block<4>(base + (long long)proto * base_stride, out, (int)(base_stride >> 2), lane);
+        for (int k = (int)(base_stride & ~3ll) + lane; k < base_stride; k += 32) out[k] = base[(long long)proto * base_stride + k];
+        __syncwarp();
+        const int* blk = reinterpret_cast<const int*>(blocks + i * stride);
+        if (journal_J == 0)
+            for (int e = 1 + lane; e <= blk[0]; e += 32) atomicAdd(out + blk[e], 1.0f);
+        else
+        {
+            int const Jp = (journal_J + 1 + 3) & ~3, nu = (blk[0] - (kJournalHeader - 1)) / Jp;
+            for (int k = lane; k < nu * journal_J; k += 32)
+            {
+                int const u = k / journal_J, j = k - u * journal_J;
+                atomicAdd(out + blk[kJournalHeader + u * Jp + j], 1.0f);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) sid[i] = proto_sid[proto];
+    }
+}
+
 template<bool REPLAY, bool SAMPLED>
 __global__ void __launch_bounds__(kThreads)
     k_propose_delta(DevModel M, const float* __restrict__ base, long long base_stride, float* blocks,

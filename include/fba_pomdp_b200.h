@@ -154,6 +154,8 @@ int64_t fba_ctx_counter(fba_ctx* ctx, int32_t which);
  *          most 2048 particles runs update + resample in ONE launch (bit-identical to the
  *          launch-per-phase path); 0 = always launch per phase
  *          "bulk_copy" (default 0): 1 = full-copy gathers go through the TMA engine (cp.async.bulk)
+ *          "auto_compact" (default 1): a belief in base + journal / base + delta storage whose increment lists are
+ *          full continues in dense storage (fba_belief_compact) instead of returning FBA_ERR_CAPACITY
  *          "nested_exact" (default 0): 1 = PHILOX-mode fba_nested_update runs the reference's loop attempt by
  *          attempt, one thread per top particle (what REPLAY mode always does); 0 = one warp per top particle,
  *          32 attempts per round that all see the counts as of the start of their round */
@@ -202,6 +204,15 @@ int fba_belief_upload(fba_belief* b, int64_t first, int64_t count, const int32_t
 int fba_belief_download(fba_belief* b, int64_t first, int64_t count, int32_t* state,
                         int32_t* struct_id, float* counts, double* w);
 int fba_belief_total_weight(fba_belief* b, double* total); /* WeightedFilter::_total_weight */
+/* base + delta / base + journal storage -> dense private blocks, in place: every particle's block becomes its base
+ * table with its own increments applied (bit-identical to what fba_belief_download reports), the belief continues as
+ * a dense one of any age. What BAFlatModel::operator= does when a tenth of a table's rows are private
+ * (src/bayes-adaptive/states/table/BAFlatModel.cpp:284-354). Called automatically by the importance-sampling update
+ * when the increment lists are full (option "auto_compact", default 1) if dense storage fits the free memory;
+ * FBA_ERR_CAPACITY if it does not. No-op on a dense belief. */
+int fba_belief_compact(fba_belief* b);
+/* increments a particle of this belief can still hold in total (0: dense storage) */
+int32_t fba_belief_delta_capacity(const fba_belief* b);
 
 /* beliefs::importance_sampling::update (src/beliefs/particle_filters/ImportanceSampler.hpp:31-62):
  * step every particle with `action`, weight by P(observation | action, particle), normalise.

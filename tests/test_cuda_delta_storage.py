@@ -147,6 +147,7 @@ def test_delta_capacity_overflow_is_reported(ctx):
     from fba_pomdp_b200 import capi
     g = G.load("tiger")
     sim = delta_sim(ctx, g, cap=4)  # room for two updates
+    ctx.set_option("auto_compact", 0)   # (by default a full list turns the belief into a dense one: test below)
     b = delta_belief(fba.BAImportanceSampling, sim, g, "is/init")
     words = np.random.RandomState(0).randint(0, 2**32, 6 * 1024, dtype=np.uint64).astype(np.uint32)
     for _ in range(2):
@@ -154,5 +155,33 @@ def test_delta_capacity_overflow_is_reported(ctx):
     with pytest.raises(fba.FbaError) as e:
         b.updateEstimation(2, 0, fba.Rng.replay(words))
     assert e.value.status == capi.ERR_CAPACITY
+    ctx.set_option("auto_compact", 1)
     b.free()
     sim.close()
+
+
+def test_full_delta_lists_continue_in_dense_storage(ctx):
+    """auto_compact (default): when the increment lists are full the belief becomes a dense one in place
+    (fba_belief_compact) and goes on — through the compaction it stays IDENTICAL, update after update, to a belief
+    that was dense from the start (same Philox seed): likelihoods, states, weights, count blocks."""
+    import fba_pomdp_b200 as fba
+    g = G.load("tiger")
+    script = [(int(a), int(o)) for a, o, f in zip(g.a, g.o, g.flags) if not (f & 1)][:7]
+    out = []
+    for cap in (0, 6):                                   # dense / room for three updates
+        sim = fba.BAPOMDP(ctx, dict(g.desc, delta_capacity=cap), g.t_par, g.o_par)
+        b = fba.BAImportanceSampling(4096)
+        rng = fba.Rng.philox(11)
+        b.initiate_sampled(sim, [0], g["is/init_counts"][:1], None, rng)
+        caps, liks = [], []
+        for a, o in script:
+            liks.append(b.updateEstimation(a, o, rng))
+            caps.append(b.L.fba_belief_delta_capacity(b.h))
+        d = b.download()
+        out.append((liks, d["state"], d["w"], d["counts"], caps))
+        b.free()
+        sim.close()
+    assert out[1][4] == [6, 6, 6, 0, 0, 0, 0]            # the fourth update compacted first
+    assert out[0][0] == out[1][0]
+    for k in (1, 2, 3):
+        np.testing.assert_array_equal(out[0][k], out[1][k])

@@ -108,11 +108,13 @@ def test_journal_overflow_is_reported(ctx):
     b = fba.BAImportanceSampling(len(pp))
     b.initiate(sim, proto_struct_id=psid, proto_counts=protos, particle_proto=pp, state=g["is/init_state"])
     rng = fba.Rng.philox(1)
+    ctx.set_option("auto_compact", 0)           # (by default a full journal turns the belief into a dense one)
     b.updateEstimation(0, 0, rng)
     b.updateEstimation(0, 0, rng)
     with pytest.raises(fba.FbaError):
         b.updateEstimation(0, 0, rng)
         b.download()
+    ctx.set_option("auto_compact", 1)
     b.free()
     sim.close()
     with pytest.raises(fba.FbaError):           # capacity must hold whole updates
@@ -129,16 +131,21 @@ def test_sysadmin_at_scale_journal_vs_dense_native(ctx):
     n = 100_000
     script = [(int(a), int(o)) for a, o, f in zip(g.a, g.o, g.flags) if not (f & 1)]
     out = []
-    for cap in (0, J * 16):
+    # dense from the start / a journal that holds all 8 updates / a journal that is full after 5: the belief is
+    # compacted into dense storage in place (fba_belief_compact, automatic) and goes on as a dense one
+    for cap in (0, J * 16, J * 5):
         sim = fba.BAPOMDP(ctx, dict(g.desc, delta_capacity=cap), g.t_par, g.o_par)
         b = fba.BAImportanceSampling(n)
         rng = fba.Rng.philox(5)
         b.initiate_sampled(sim, [0], g["is/init_counts"][:1], None, rng)
         liks = [b.updateEstimation(a, o, rng) for a, o in script[:8]]
         d = b.download()
-        out.append((liks, d["state"], d["w"], d["counts"][:, :g["is/init_counts"].shape[1]]))
+        out.append((liks, d["state"], d["w"], d["counts"][:, :g["is/init_counts"].shape[1]],
+                    b.L.fba_belief_delta_capacity(b.h)))
         b.free()
         sim.close()
-    assert out[0][0] == out[1][0]
-    for k in (1, 2, 3):
-        np.testing.assert_array_equal(out[0][k], out[1][k])
+    assert [o[4] for o in out] == [0, J * 16, 0]
+    for other in (1, 2):
+        assert out[0][0] == out[other][0]
+        for k in (1, 2, 3):
+            np.testing.assert_array_equal(out[0][k], out[other][k])
