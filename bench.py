@@ -347,6 +347,69 @@ def many_runs_leg(ctx, fba, args):
                          "reference_cpu_simulations_per_s": 3.6e5}}
 
 
+def structure_beliefs_leg(ctx, fba, args):
+    """The device bricks of the reference's structure-learning beliefs on sysadmin-10,
+    through the public calls with host arguments and host results (wall clock, median of 5 after a warm-up):
+    MHwithinGibbs' state histories by message passing and its posterior counts for 64 chains, LogBDScore, and a
+    NestedBelief update (128 top particles x 4096 bottom states)."""
+    import golden_util as G
+    from fba_pomdp_b200.structure_beliefs import NestedBelief
+    g = G.load("sysadmin")
+    sim = fba.BAPOMDP(ctx, g.desc, g.t_par, g.o_par)
+    S = int(g.desc["S"])
+    upd = [t for t in range(len(g.a)) if not (g.flags[t] & 1)]
+    acts = np.array([g.a[upd[k % len(upd)]] for k in range(40)], np.int32)
+    obs = np.array([g.o[upd[k % len(upd)]] for k in range(40)], np.int32)
+    hist = (np.array([20, 20], np.int32), acts, obs)
+    prior = np.zeros(S, np.float32)
+    prior[S - 1] = 1.0
+
+    def timed(fn, reps=5):
+        fn()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return float(np.median(ts)) * 1e3
+
+    chains = 64
+    b = fba.BAImportanceSampling(chains)
+    proto = np.repeat(g["is/init_counts"][:1], chains, 0)
+    b.initiate(sim, struct_id=np.zeros(chains, np.int32), counts=proto, state=np.zeros(chains, np.int32))
+    pb = fba.BAImportanceSampling(chains)
+    pb.initiate(sim, struct_id=np.zeros(chains, np.int32), counts=proto, state=np.zeros(chains, np.int32))
+    rng = fba.Rng.philox(args.seed + 5)
+    seq = [None]
+
+    def histories():
+        seq[0] = b.sample_state_history("msg", *hist, rng, state_prior=prior)
+    ms_hist = timed(histories)
+    ms_counts = timed(lambda: b.add_history_counts(*hist, seq[0]))
+    ms_score = timed(lambda: fba.log_bd_score(b, pb))
+    b.free(), pb.free()
+
+    n_top, n_bot = 128, 4096
+    nb = NestedBelief(n_top, n_bot)
+    nb.initiate(sim, struct_id=np.zeros(n_top, np.int32), counts=np.repeat(g["is/init_counts"][:1], n_top, 0),
+                states=np.full((n_top, n_bot), S - 1, np.int32))
+    ms_nested = timed(lambda: nb.updateEstimation(int(acts[0]), int(obs[0]), rng))
+    attempts = float(nb.attempts.mean())
+    nb.free()
+    sim.close()
+    return {"workload": "linear-sysadmin-10 (S = 1024, 20 actions), history of 2 episodes x 20 steps",
+            "gibbs_state_histories_by_messages": {"chains": chains, "ms_per_call": ms_hist,
+                                                  "us_per_history_step_all_chains_in_parallel": 1e3 * ms_hist / 40},
+            "gibbs_posterior_counts": {"chains": chains, "ms_per_call": ms_counts},
+            "log_bd_score": {"models": chains, "ms_per_call": ms_score},
+            "nested_update": {"top": n_top, "bottom": n_bot, "ms_per_update": ms_nested,
+                              "attempts_per_top_particle": attempts,
+                              "bottom_particle_attempts_per_s": n_top * attempts / (ms_nested * 1e-3)},
+            "note": "parity: tests/test_cuda_gibbs.py, tests/test_cuda_composite.py (REPLAY bit-exact vs the oracle pinned "
+                    "to the reference's classes); whole-belief update cost against the reference's core: "
+                    "profiles/r2j_structure_beliefs.jsonl"}
+
+
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -680,6 +743,7 @@ def main_ours(args):
         line["rollouts"] = rollouts_leg(ctx, fba, args, torch, world, rank, dist)
     if world == 1 and not args.no_rollouts:
         line["many_runs"] = many_runs_leg(ctx, fba, args)
+        line["structure_beliefs"] = structure_beliefs_leg(ctx, fba, args)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n = args.ref_particles
