@@ -372,3 +372,61 @@ def test_domain_mutate_replay(name):
     fc.free()
     sim.close()
     ctx.close()
+
+
+def test_argument_checks_of_the_structure_belief_calls(env):
+    """bad arguments come back as FbaError (FBA_ERR_INVALID / _CAPACITY) with the reference's wording where it has one,
+    never as a crash or a silent no-op"""
+    fba, g, sim = env
+    from fba_pomdp_b200 import capi
+    from fba_pomdp_b200.capi import ptr
+    from fba_pomdp_b200.structure_beliefs import (CheatingReinvigoration, NestedBelief, StructureIncubatorSampling,
+                                                  replace_from)
+    import ctypes as C
+    N, stride = int(g["meta/N"]), int(g["meta/stride"])
+    # constructor checks with the reference's messages
+    for bad in (lambda: CheatingReinvigoration(0, 1, -1.0), lambda: CheatingReinvigoration(8, 0, -1.0),
+                lambda: CheatingReinvigoration(8, 1, 0.0), lambda: StructureIncubatorSampling(0, 1, 0.5, 0),
+                lambda: StructureIncubatorSampling(8, 1, 0.0, 0), lambda: StructureIncubatorSampling(8, 1, 1.5, 0),
+                lambda: NestedBelief(0, 4), lambda: NestedBelief(4, 0)):
+        with pytest.raises(fba.FbaError) as e:
+            bad()
+        assert e.value.status == capi.ERR_INVALID
+    flat = fba.BARejectionSampling(N)
+    flat.initiate(sim, **particles(g, "cheat/init_c"), stride=stride)
+    wtd = fba.BAImportanceSampling(N)
+    wtd.initiate(sim, **particles(g, "cheat/init_b"), stride=stride)
+    L, ctx = flat.L, flat.ctx
+    rng = fba.Rng.philox(1)
+    replace_from(wtd, [], flat, [])                                        # empty: a no-op, not an error
+    idx = np.zeros(4, np.int64)
+    assert L.fba_belief_least_likely(wtd.h, N, ptr(idx)) == capi.ERR_INVALID          # n must be < N (WeightedFilter.cpp:208)
+    assert L.fba_belief_least_likely(flat.h, 2, ptr(idx)) == capi.ERR_INVALID         # flat filters have no weights
+    assert L.fba_belief_cheat(flat.h, wtd.h, 2, C.byref(rng)) == capi.ERR_INVALID     # roles swapped
+    assert L.fba_belief_promote(flat.h, wtd.h, 0.5, C.byref(rng), None) == capi.ERR_INVALID
+    slot = np.array([N], np.int64)
+    assert L.fba_belief_breed_into(wtd.h, ptr(slot), 1, flat.h, flat.h, 0, C.byref(rng)) == capi.ERR_INVALID   # slot out of range
+    assert L.fba_belief_breed_into(wtd.h, ptr(idx), 0, flat.h, flat.h, 0, C.byref(rng)) == capi.ERR_INVALID    # amount < 1
+    assert L.fba_belief_breed_into(flat.h, ptr(idx), 1, wtd.h, flat.h, 0, C.byref(rng)) == capi.ERR_INVALID    # weighted donor
+    short = fba.Rng.replay(np.zeros(1, np.uint32))
+    assert L.fba_belief_cheat(wtd.h, flat.h, 2, C.byref(short)) == capi.ERR_RNG_UNDERRUN and short.cursor == 0
+    # a threshold every shadow particle passes: the reference divides by zero there
+    with pytest.raises(fba.FbaError):
+        n = C.c_int64(0)
+        from fba_pomdp_b200.beliefs import _check
+        _check(ctx.h, L.fba_belief_promote(wtd.h, flat.h, 0.5 / N, C.byref(rng), C.byref(n)))
+    # history calls
+    ln, ac, ob = np.array([2], np.int32), np.array([0, 1], np.int32), np.array([0, 0], np.int32)
+    with pytest.raises(fba.FbaError):
+        flat.add_history_counts(ln, ac, ob, np.array([0, 1, 10 ** 6], np.int32))       # state out of range
+    with pytest.raises(fba.FbaError):
+        flat.add_history_counts(ln, np.array([0, 99], np.int32), ob, np.zeros(3, np.int32))   # action out of range
+    with pytest.raises(fba.FbaError):
+        flat.sample_state_history("rs", np.array([0], np.int32), ac[:0], ob[:0], rng)  # an episode without steps
+    nb = NestedBelief(2, 3)
+    with pytest.raises(fba.FbaError):
+        nb.initiate(sim, struct_id=np.zeros(2, np.int32), counts=g["cheat/init_c_counts"][:2],
+                    states=np.full((2, 3), 10 ** 6, np.int32))                          # bottom state out of range
+    nb.free()
+    flat.free()
+    wtd.free()
