@@ -30,6 +30,7 @@ struct fba_ctx
     int rollout_coop = -1; // -1 auto (by batch size and row length), 0 thread per rollout, 1 warp per rollout
     void* big_scratch = nullptr; // grow-only: the flattened models + messages of fba_belief_sample_state_history
     size_t big_scratch_bytes = 0;
+    bool msg_cluster  = true;  // Gibbs message passing: one model over a cluster of CTAs when the model allows it
     bool auto_compact = true;  // a full journal / delta list turns the belief into dense storage instead of failing
     bool nested_exact = false; // PHILOX NestedBelief updates: thread per top particle instead of warp per top particle
     bool inplace_resample = true; // PHILOX mode: survivors keep their slot (fba_ctx_set_option)
@@ -366,6 +367,11 @@ extern "C" int fba_ctx_set_option(fba_ctx* ctx, const char* name, int64_t value)
     if (!strcmp(name, "rollout_coop"))
     {
         ctx->rollout_coop = (int)value;
+        return FBA_OK;
+    }
+    if (!strcmp(name, "msg_cluster"))
+    { // 0: fba_belief_sample_state_history (messages) always runs one CTA per model
+        ctx->msg_cluster = value != 0;
         return FBA_OK;
     }
     if (!strcmp(name, "auto_compact"))
@@ -2629,7 +2635,25 @@ extern "C" int fba_belief_sample_state_history(fba_belief* b, int32_t method, in
         ++ctx->launches;                                                                                           \
         CU(ctx, cudaGetLastError());                                                                               \
     } while (0)
-        if (replay && sh) LAUNCH_MSG(true, true);
+        // one model over a cluster of CTAs when its states split evenly and the rows fit shared memory
+        bool const clustered = sh && ctx->msg_cluster && D.S % kMsgCluster == 0 && D.S / kMsgCluster >= 32;
+        if (clustered)
+        {
+            int const cl_threads = (int)std::min<long long>(kMsgThreads, ((long long)D.S / kMsgCluster + 31) / 32 * 32);
+            if (ctx->profiling) profile_mark(ctx, "k_state_history_msg_cluster", true);
+            if (replay)
+                k_state_history_msg_cluster<true><<<(int)b->N * kMsgCluster, cl_threads, sh_bytes, ctx->stream>>>(
+                    D, b->N, h.H, (const float*)d_T, (const float*)d_O, (const float*)d_prior, (double*)d_msg, ra,
+                    (int*)d_out, out_len, ctx->d_flag);
+            else
+                k_state_history_msg_cluster<false><<<(int)b->N * kMsgCluster, cl_threads, sh_bytes, ctx->stream>>>(
+                    D, b->N, h.H, (const float*)d_T, (const float*)d_O, (const float*)d_prior, (double*)d_msg, ra,
+                    (int*)d_out, out_len, ctx->d_flag);
+            if (ctx->profiling) profile_mark(ctx, "k_state_history_msg_cluster", false);
+            ++ctx->launches;
+            CU(ctx, cudaGetLastError());
+        } else if (replay && sh)
+            LAUNCH_MSG(true, true);
         else if (replay)
             LAUNCH_MSG(true, false);
         else if (sh)

@@ -1,6 +1,7 @@
 // Kernels of the belief / rollout hot path (sm_100a). See DESIGN.md §Kernels for the roofline of
 // each; the host-side C ABI that launches them is in fba_capi.cu.
 #pragma once
+#include <cooperative_groups.h>
 
 #include <cuda_pipeline.h>
 
@@ -3190,6 +3191,141 @@ __global__ void __launch_bounds__(kMsgThreads)
         first += len;
     }
     if (threadIdx.x == 0 && g.overrun) *overrun = 1;
+}
+
+// The same passes with one model spread over a thread-block CLUSTER of kMsgCluster CTAs (sm_90+ distributed
+// shared memory): CTA r owns the states [r S / kMsgCluster, (r + 1) S / kMsgCluster) — their inner products are
+// where the time goes, and they are bound by loads in flight, so four SMs' worth of them per model is the gain —
+// while every CTA keeps a full copy of the current message row in its own shared memory. A backward step: each
+// thread computes its state's new entry and stores it into the work row of ALL CTAs of the cluster
+// (cluster.map_shared_rank), cluster.sync, every CTA's thread 0 adds the S entries in order (the same sum in every
+// CTA, no broadcast needed), every CTA normalises its full copy, cluster.sync. The forward pass is short and runs in
+// CTA 0 alone; a cluster.sync ends the episode. Arithmetic and order are those of the one-CTA kernel: bit-identical.
+constexpr int kMsgCluster = 4;
+
+template<bool REPLAY>
+__global__ void __cluster_dims__(kMsgCluster, 1, 1) __launch_bounds__(kMsgThreads)
+    k_state_history_msg_cluster(DevModel M, long long N, HistoryArgs H, const float* __restrict__ Tt_all,
+                                const float* __restrict__ Ot_all, const float* __restrict__ state_prior,
+                                double* __restrict__ msg_all, RngArgs ra, int* __restrict__ states_out,
+                                long long out_stride, int* __restrict__ overrun)
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ double sh_rows[];
+    unsigned const rank = cluster.block_rank();
+    long long const p   = blockIdx.x / kMsgCluster;
+    int const S         = M.S;
+    int const slice     = S / kMsgCluster, s_lo = (int)rank * slice;
+    double* row         = sh_rows;     // the message row being read (normalised), all S entries
+    double* work        = sh_rows + S; // the row being built (all S entries, filled by every CTA of the cluster)
+    double* work_of[kMsgCluster];
+#pragma unroll
+    for (int r = 0; r < kMsgCluster; ++r) work_of[r] = cluster.map_shared_rank(work, r);
+    const float* Tt = Tt_all + p * (long long)M.A * S * S;
+    const float* Ot = Ot_all + p * (long long)M.A * M.O * S;
+    double* msg     = msg_all + p * (long long)(H.max_len + 2) * S;
+    int* out        = states_out + p * out_stride;
+    auto g          = RngOf<REPLAY>::make(ra, p);
+    __shared__ double sh_tot;
+    __shared__ int sh_state;
+    int first = 0, pos = 0;
+    for (int e = 0; e < H.n_episodes; ++e)
+    {
+        int const len  = H.episode_len[e];
+        const int* act = H.actions + first;
+        const int* obs = H.observations + first;
+        for (int s = threadIdx.x; s < S; s += blockDim.x)
+        {
+            double const v = (double)Ot[((long long)act[len - 1] * M.O + obs[len - 1]) * S + s];
+            row[s]         = v;
+            if (s >= s_lo && s < s_lo + slice) msg[(long long)len * S + s] = v;
+        }
+        __syncthreads();
+        for (int step = len - 1; step >= 0; --step)
+        {
+            const float* Ta = Tt + (long long)act[step] * S * S;
+            for (int s = s_lo + (int)threadIdx.x; s < s_lo + slice; s += blockDim.x)
+            {
+                double acc = 0.0;
+                int s2     = 0;
+                float t[8], t_next[8];
+                bool have = S >= 8;
+                if (have)
+                {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) t[u] = __ldcs(Ta + (long long)u * S + s);
+                }
+                while (have)
+                {
+                    bool const more = s2 + 16 <= S;
+                    if (more)
+                    {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) t_next[u] = __ldcs(Ta + (long long)(s2 + 8 + u) * S + s);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) acc = __dadd_rn(acc, __dmul_rn((double)t[u], row[s2 + u]));
+                    s2 += 8;
+                    have = more;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) t[u] = t_next[u];
+                }
+                for (; s2 < S; ++s2) acc = __dadd_rn(acc, __dmul_rn((double)Ta[(long long)s2 * S + s], row[s2]));
+                float const factor = (step != 0) ? Ot[((long long)act[step - 1] * M.O + obs[step - 1]) * S + s]
+                                                 : state_prior[s];
+                double const v = __dmul_rn(acc, (double)factor);
+#pragma unroll
+                for (int r = 0; r < kMsgCluster; ++r) work_of[r][s] = v;
+            }
+            cluster.sync();
+            if (threadIdx.x == 0)
+            {
+                double tot = 0.0;
+                for (int s = 0; s < S; ++s) tot = __dadd_rn(tot, work[s]);
+                sh_tot = tot;
+            }
+            __syncthreads();
+            double const tot = sh_tot;
+            for (int s = threadIdx.x; s < S; s += blockDim.x)
+            {
+                double const v = __ddiv_rn(work[s], tot);
+                row[s]         = v;
+                if (s >= s_lo && s < s_lo + slice) msg[(long long)step * S + s] = v;
+            }
+            cluster.sync(); // nobody writes the next step's entries into a work row that is still being read
+        }
+        if (rank == 0)
+        { // forward sampling (thread 0 draws; the products of a step by all threads of this CTA)
+            __threadfence();
+            if (threadIdx.x == 0)
+            {
+                sh_state   = sample_from_mult_d(row, S, 1.0, g);
+                out[pos++] = sh_state;
+            }
+            __syncthreads();
+            for (int step = 0; step < len; ++step)
+            {
+                int const state    = sh_state;
+                const float* Ta    = Tt + (long long)act[step] * S * S;
+                const double* next = msg + (long long)(step + 1) * S;
+                for (int s2 = threadIdx.x; s2 < S; s2 += blockDim.x)
+                    work[s2] = __dmul_rn((double)Ta[(long long)s2 * S + state], __ldcg(next + s2));
+                __syncthreads();
+                if (threadIdx.x == 0)
+                {
+                    double tot = 0.0;
+                    for (int s2 = 0; s2 < S; ++s2) tot = __dadd_rn(tot, work[s2]);
+                    sh_state   = sample_from_mult_d(work, S, tot, g);
+                    out[pos++] = sh_state;
+                }
+                __syncthreads();
+            }
+        }
+        cluster.sync(); // the other CTAs start the next episode (and touch CTA 0's work row) only now
+        first += len;
+    }
+    if (rank == 0 && threadIdx.x == 0 && g.overrun) *overrun = 1;
 }
 
 // MHwithinGibbs::computePosteriorCounts (:397-436): incrementCountsOf(s_t, a_t, o_t, s_t+1) for every step of

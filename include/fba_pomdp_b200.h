@@ -156,6 +156,8 @@ int64_t fba_ctx_counter(fba_ctx* ctx, int32_t which);
  *          "bulk_copy" (default 0): 1 = full-copy gathers go through the TMA engine (cp.async.bulk)
  *          "auto_compact" (default 1): a belief in base + journal / base + delta storage whose increment lists are
  *          full continues in dense storage (fba_belief_compact) instead of returning FBA_ERR_CAPACITY
+ *          "msg_cluster" (default 1): fba_belief_sample_state_history by messages spreads one model over a
+ *          thread-block cluster of 4 CTAs (distributed shared memory) when its states split evenly; 0 = one CTA per model
  *          "nested_exact" (default 0): 1 = PHILOX-mode fba_nested_update runs the reference's loop attempt by
  *          attempt, one thread per top particle (what REPLAY mode always does); 0 = one warp per top particle,
  *          32 attempts per round that all see the counts as of the start of their round */

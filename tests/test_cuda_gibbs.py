@@ -85,13 +85,16 @@ def test_posterior_counts_are_bit_exact(env):
         b.free()
 
 
-def test_state_history_on_sysadmin_10(env):
+@pytest.mark.parametrize("cluster", [1, 0])
+def test_state_history_on_sysadmin_10(env, cluster):
     """S = 1024 states, 20 actions: the flattened tables are 80 MB per particle and a backward step is a 1024 x 1024
-    matrix-vector product in the reference's summation order"""
+    matrix-vector product in the reference's summation order — with one model spread over a cluster of 4 CTAs
+    (the default) and with one CTA per model: both bit-identical to the oracle"""
     fba, O, _, _, _ = env
     g = G.load("sysadmin")
     m = O.Model(g.desc)
     ctx = fba.Context(0)
+    ctx.set_option("msg_cluster", cluster)
     sim = fba.BAPOMDP(ctx, g.desc, g.t_par, g.o_par)
     n = 3
     b = fba.BAImportanceSampling(n)
