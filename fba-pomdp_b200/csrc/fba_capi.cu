@@ -103,6 +103,9 @@ struct fba_belief
     double uniform_total = -1;  // sequential sum of N x (1/N), computed on first use
     bool suffix_valid = false;  // aux holds R for the current weights
     bool cdf_valid    = false;  // aux holds the native cdf for the current weights
+    bool uniform_now  = false;  // every weight is 1 / N: set where a resample / init leaves them so, cleared wherever the
+                                // cdf cache is invalidated (i.e. wherever weights may have changed)
+    bool w_escaped    = false;  // fba_belief_weight_ptr handed the weight array out: never assume anything about it
     // in-place resampling
     int *noff = nullptr, *escan = nullptr, *dead = nullptr, *totals = nullptr, *src_of = nullptr;
     long long* stats = nullptr; // [0] copies made by in-place resamples, [1] number of resamples,
@@ -902,6 +905,7 @@ extern "C" void* fba_belief_state_ptr(fba_belief* b)
 }
 extern "C" void* fba_belief_weight_ptr(fba_belief* b)
 {
+    if (b) b->w_escaped = true, b->uniform_now = false; // the host language may write through this pointer
     return b ? b->w : nullptr;
 }
 extern "C" void* fba_belief_aux_ptr(fba_belief* b)
@@ -931,6 +935,7 @@ static void weights_became_uniform(fba_belief* b)
     b->total_weight = uniform_total(b);
     b->suffix_valid = false;
     b->cdf_valid    = false;
+    b->uniform_now  = !b->w_escaped;
 }
 
 // device scratch that dies with the call, whichever way the call returns
@@ -1080,6 +1085,7 @@ extern "C" int fba_belief_init_sampled(fba_belief* b, int32_t n_protos, const in
         CU(ctx, cudaStreamSynchronize(ctx->stream));
         b->total_weight = 1.0;
         b->suffix_valid = b->cdf_valid = false;
+        b->uniform_now = false;
         return FBA_OK;
     }
     LAUNCH(ctx, k_init_from_protos, stream_grid(ctx, b->N), kThreads, b->counts[b->cur], b->stride,
@@ -1088,6 +1094,7 @@ extern "C" int fba_belief_init_sampled(fba_belief* b, int32_t n_protos, const in
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     b->total_weight = 1.0;
     b->suffix_valid = b->cdf_valid = false;
+    b->uniform_now = false;
     return FBA_OK;
 }
 
@@ -1119,6 +1126,7 @@ extern "C" int fba_belief_upload(fba_belief* b, int64_t first, int64_t count, co
     {
         CU(ctx, cudaMemcpyAsync(b->w + first, w, count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         b->suffix_valid = b->cdf_valid = false;
+        b->uniform_now = false;
         if (first == 0 && count == b->N)
         { // WeightedFilter::_total_weight = the sequential sum of the weights as added
             volatile double acc = 0.0;
@@ -1313,6 +1321,7 @@ static int propose(fba_belief* b, int a, int o, fba_rng* rng, unsigned long long
 #undef PROPOSE_DELTA_ARGS
         if (replay) rng->cursor += need;
         b->suffix_valid = b->cdf_valid = false;
+        b->uniform_now = false;
         return FBA_OK;
     }
     if (rng->mode == FBA_RNG_REPLAY)
@@ -1332,6 +1341,7 @@ static int propose(fba_belief* b, int a, int o, fba_rng* rng, unsigned long long
                   ctx->d_flag);
     }
     b->suffix_valid = b->cdf_valid = false;
+    b->uniform_now = false;
     return FBA_OK;
 }
 
@@ -1475,6 +1485,7 @@ static int pick_ancestors(fba_belief* b, fba_rng* rng, long long n_out, long lon
             if ((rc = replay_chains(b, false))) return rc;
             b->suffix_valid = true;
             b->cdf_valid    = false;
+            b->uniform_now = false;
         }
         if ((rc = clear_flag(ctx))) return rc;
         LAUNCH(ctx, k_pick_replay, blocks_for(n_out), kThreads, b->aux, b->N, b->scal,
@@ -1564,6 +1575,7 @@ static int resample_inplace(fba_belief* b, fba_rng* rng, long long n_out, const 
                b->d_step, b->peers.timeout_ns, b->stats);
     b->total_weight = 1.0;
     b->suffix_valid = b->cdf_valid = false;
+    b->uniform_now  = !b->w_escaped; // k_fill: every weight is 1 / N
     b->inplace_last = true;
     return FBA_OK;
 }
@@ -1594,6 +1606,7 @@ extern "C" int fba_belief_resample(fba_belief* b, fba_rng* rng)
     {
         b->total_weight = 1.0;
         b->suffix_valid = b->cdf_valid = false;
+        b->uniform_now  = !b->w_escaped; // the gather wrote 1 / N into every weight
     }
     return FBA_OK;
 }
@@ -1639,6 +1652,7 @@ extern "C" int fba_belief_update_estimation(fba_belief* b, int32_t a, int32_t o,
         }
         b->total_weight = 1.0;
         b->suffix_valid = b->cdf_valid = false;
+        b->uniform_now  = !b->w_escaped; // the fused kernel ends with uniform weights, as the phases do
         b->inplace_last = true;
         if (likelihood)
         {
@@ -1719,6 +1733,7 @@ static int reset_states(fba_belief* b, fba_rng* rng, bool with_resample)
             flip(b);
             b->total_weight = 1.0;
             b->suffix_valid = b->cdf_valid = false;
+            b->uniform_now = false;
         }
         LAUNCH(ctx, k_reset_states<false>, blocks_for(b->N), kThreads, D, b->state[b->cur], b->N,
                philox_args(rng), 0, ctx->d_flag);
@@ -1760,6 +1775,7 @@ extern "C" int fba_belief_sample(fba_belief* b, fba_rng* rng, int64_t* index)
         }
         return FBA_OK;
     }
+    // (no uniform-weights shortcut here: fba_runs_sample promises the index this call returns, tests/test_cuda_runs.py)
     if (rng->mode == FBA_RNG_REPLAY)
     {
         if ((rc = stage_words(ctx, rng, 2))) return rc;
@@ -1994,6 +2010,7 @@ static int host_replace_weights(fba_belief* b, const std::vector<int>& order)
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     b->total_weight = total;
     b->suffix_valid = b->cdf_valid = false;
+    b->uniform_now = false;
     return FBA_OK;
 }
 
@@ -2284,9 +2301,10 @@ extern "C" int fba_belief_sample_batch(fba_belief* b, fba_rng* rng, int64_t n, i
     CU(ctx, cudaSetDevice(ctx->device));
     int rc;
     if ((rc = stage_buf(ctx, &b->roll_p, &b->roll_cap_p, n))) return rc;
-    if (b->weighted && !b->cdf_valid)
+    bool const by_cdf = b->weighted && !b->uniform_now; // uniform weights: uniform picks, no normalisation pass
+    if (by_cdf && !b->cdf_valid)
         if ((rc = native_normalize(b, false, 1.0))) return rc;
-    LAUNCH(ctx, k_sample_batch, blocks_for(n), kThreads, b->weighted ? b->aux : (const double*)nullptr, b->N,
+    LAUNCH(ctx, k_sample_batch, blocks_for(n), kThreads, by_cdf ? b->aux : (const double*)nullptr, b->N,
            (long long)n, philox_args(rng), b->roll_p);
     CU(ctx, cudaMemcpyAsync(indices, b->roll_p, n * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
@@ -2373,6 +2391,7 @@ extern "C" int fba_belief_log_bd_score(fba_belief* b, fba_belief* prior, double*
     LAUNCH(ctx, k_log_bd_score, stream_grid(ctx, b->N), kThreads, D, b->counts[b->cur], b->stride, b->sid[b->cur], b->N,
            prior->counts[prior->cur], prior->stride, prior->sid[prior->cur], prior->N, b->aux, ctx->d_flag);
     b->suffix_valid = b->cdf_valid = false; // aux was used as the result buffer
+    b->uniform_now = false;
     CU(ctx, cudaMemcpyAsync(scores, b->aux, (size_t)b->N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
@@ -2461,6 +2480,7 @@ extern "C" int fba_belief_replay_history(fba_belief* b, int32_t n_episodes, cons
     }
     if (rng->mode == FBA_RNG_REPLAY && (rc = check_flag(ctx))) return rc;
     b->suffix_valid = b->cdf_valid = false;
+    b->uniform_now = false;
     return FBA_OK;
 }
 
@@ -2863,6 +2883,7 @@ extern "C" int fba_belief_promote(fba_belief* shadow, fba_belief* belief, double
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     shadow->total_weight = acc;
     shadow->suffix_valid = shadow->cdf_valid = false;
+    shadow->uniform_now = false;
     return FBA_OK;
 }
 
@@ -3015,6 +3036,7 @@ static int nested_normalize(fba_nested* n)
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     b->total_weight = acc;
     b->suffix_valid = b->cdf_valid = false;
+    b->uniform_now = false;
     return FBA_OK;
 }
 
@@ -3406,6 +3428,7 @@ extern "C" int fba_runs_init_sampled(fba_runs* r, int32_t n_protos, const int32_
     LAUNCH(ctx, k_fill, blocks_for(b->N), kThreads, b->w, b->N, 1.0 / (double)r->n);
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     b->suffix_valid = b->cdf_valid = false;
+    b->uniform_now = false;
     return FBA_OK;
 }
 
@@ -3420,6 +3443,7 @@ extern "C" int fba_runs_init(fba_runs* r, int32_t n_protos, const int32_t* proto
     LAUNCH(ctx, k_fill, blocks_for(b->N), kThreads, b->w, b->N, 1.0 / (double)r->n); // uniform PER RUN
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     b->suffix_valid = b->cdf_valid = false;
+    b->uniform_now = false;
     return FBA_OK;
 }
 
@@ -4100,6 +4124,7 @@ extern "C" int fba_belief_resample_shard(fba_belief* b, int64_t n_offspring, fba
     {
         flip(b);
         b->cdf_valid = false;
+        b->uniform_now = false;
         return FBA_OK;
     }
     if (n_offspring > b->anc_cap)
@@ -4133,6 +4158,7 @@ extern "C" int fba_belief_resample_shard(fba_belief* b, int64_t n_offspring, fba
     flip(b);
     b->total_weight = 1.0;
     b->cdf_valid = b->suffix_valid = false;
+    b->uniform_now = false;
     return FBA_OK;
 }
 
