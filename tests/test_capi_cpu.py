@@ -54,10 +54,25 @@ def test_constructor_errors_mirror_reference():
         fba.ReinvigoratingRejectionSampling(10, 0, 0)
 
 
+def test_structure_belief_constructor_errors_mirror_reference():
+    # CheatingReinvigoration.cpp:34-44, StructureIncubatorSampling.cpp:29-40, NestedBelief.cpp:19-26
+    from fba_pomdp_b200.structure_beliefs import CheatingReinvigoration, NestedBelief, StructureIncubatorSampling
+    with pytest.raises(fba.FbaError, match="CheatingReinvigoration::cannot initiate belief of size < 1"):
+        CheatingReinvigoration(0, 4, -1.0)
+    with pytest.raises(fba.FbaError, match="resample_threshold >= 0"):
+        CheatingReinvigoration(8, 4, 0.5)
+    with pytest.raises(fba.FbaError, match="Cannot initiate Incubator belief update with size < 1"):
+        StructureIncubatorSampling(8, 0, 0.5, 0)
+    with pytest.raises(fba.FbaError, match="must initiate with 1 < threshold <= 0"):
+        StructureIncubatorSampling(8, 2, 1.5, 0)
+    with pytest.raises(fba.FbaError, match="NestedBelief: cannot initiate with filter size < 1"):
+        NestedBelief(3, 0)
+
+
 def test_product_does_not_import_oracle():
     pkg = os.path.join(ROOT, "fba-pomdp_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h")):
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "pyoracle" not in text and "liboracle" not in text and "pyref" not in text, f
