@@ -2190,26 +2190,29 @@ __global__ void __launch_bounds__(kThreads)
         const float* p    = prior + j * prior_stride;
         const Node* nodes = M.nodes + (long long)id * M.A * M.J;
         double acc        = 0.0;
-        for (int a = 0; a < M.A; ++a)
-            for (int q = 0; q < M.J; ++q)
+        // many small nodes (sysadmin-10: 220 nodes of at most 8 rows): a lane per NODE, walking its rows, keeps the
+        // warp busy; few nodes: the lanes share the rows of one node at a time
+        bool const by_node = M.A * M.J >= 32;
+        for (int an = by_node ? lane : 0; an < M.A * M.J; an += by_node ? 32 : 1)
+        {
+            int const q     = an % M.J;
+            Node const nd   = nodes[an];
+            int const range = (q < M.FS) ? M.feat_s[q] : M.feat_o[q - M.FS];
+            int cfgs        = 1;
+            for (uint32_t m = nd.par; m; m &= m - 1) cfgs *= M.feat_s[__ffs(m) - 1];
+            for (int r = by_node ? 0 : lane; r < cfgs; r += by_node ? 1 : 32)
             {
-                Node const nd   = nodes[a * M.J + q];
-                int const range = (q < M.FS) ? M.feat_s[q] : M.feat_o[q - M.FS];
-                int cfgs        = 1;
-                for (uint32_t m = nd.par; m; m &= m - 1) cfgs *= M.feat_s[__ffs(m) - 1];
-                for (int r = lane; r < cfgs; r += 32)
+                int const row = nd.off + r * range;
+                double ct = 0.0, pt = 0.0;
+                for (int v = 0; v < range; ++v)
                 {
-                    int const row = nd.off + r * range;
-                    double ct = 0.0, pt = 0.0;
-                    for (int v = 0; v < range; ++v)
-                    {
-                        double const cv = (double)c[row + v], pv = (double)p[row + v];
-                        ct += cv, pt += pv;
-                        acc += log_gamma_ref(cv) - log_gamma_ref(pv);
-                    }
-                    acc += log_gamma_ref(pt) - log_gamma_ref(ct);
+                    double const cv = (double)c[row + v], pv = (double)p[row + v];
+                    ct += cv, pt += pv;
+                    acc += log_gamma_ref(cv) - log_gamma_ref(pv);
                 }
+                acc += log_gamma_ref(pt) - log_gamma_ref(ct);
             }
+        }
         for (int o = 16; o; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
         if (lane == 0) score[i] = acc;
     }
