@@ -1085,7 +1085,7 @@ extern "C" int fba_belief_init_sampled(fba_belief* b, int32_t n_protos, const in
         CU(ctx, cudaStreamSynchronize(ctx->stream));
         b->total_weight = 1.0;
         b->suffix_valid = b->cdf_valid = false;
-        b->uniform_now = false;
+        b->uniform_now  = !b->w_escaped; // weights 1 / N
         return FBA_OK;
     }
     LAUNCH(ctx, k_init_from_protos, stream_grid(ctx, b->N), kThreads, b->counts[b->cur], b->stride,
@@ -1094,7 +1094,7 @@ extern "C" int fba_belief_init_sampled(fba_belief* b, int32_t n_protos, const in
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     b->total_weight = 1.0;
     b->suffix_valid = b->cdf_valid = false;
-    b->uniform_now = false;
+    b->uniform_now  = !b->w_escaped; // weights 1 / N
     return FBA_OK;
 }
 
@@ -1733,7 +1733,7 @@ static int reset_states(fba_belief* b, fba_rng* rng, bool with_resample)
             flip(b);
             b->total_weight = 1.0;
             b->suffix_valid = b->cdf_valid = false;
-            b->uniform_now = false;
+            b->uniform_now  = !b->w_escaped; // the gather wrote 1 / N into every weight
         }
         LAUNCH(ctx, k_reset_states<false>, blocks_for(b->N), kThreads, D, b->state[b->cur], b->N,
                philox_args(rng), 0, ctx->d_flag);
@@ -1775,7 +1775,15 @@ extern "C" int fba_belief_sample(fba_belief* b, fba_rng* rng, int64_t* index)
         }
         return FBA_OK;
     }
-    // (no uniform-weights shortcut here: fba_runs_sample promises the index this call returns, tests/test_cuda_runs.py)
+    if (rng->mode == FBA_RNG_PHILOX && b->uniform_now)
+    { // every weight is 1 / N (init, resample, reset): a weighted draw is floor(u N) — no normalisation pass, no
+      // launch, no read-back; the same u and the same rule as fba_runs_sample (k_runs_step<.., 2>), so a run stays
+      // bit-identical to its stand-alone belief
+        PhiloxRng g(rng->seed, 0, rng->offset++);
+        double const u = draw_u(g);
+        *index         = std::min<long long>(b->N - 1, (long long)std::floor(u * (double)b->N));
+        return FBA_OK;
+    }
     if (rng->mode == FBA_RNG_REPLAY)
     {
         if ((rc = stage_words(ctx, rng, 2))) return rc;

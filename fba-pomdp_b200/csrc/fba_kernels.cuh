@@ -1412,6 +1412,19 @@ __global__ void __launch_bounds__(kThreads)
     RngArgs rr          = ra; // the run's own random source: a stand-alone belief seeded seed + r
     rr.seed             = ra.seed + (unsigned long long)r;
 
+    if constexpr (MODE == 2)
+    { // Belief::sample of every run. A run's weights are uniform whenever this can be called (init, update +
+      // resample and reset all leave 1 / n), so the weighted draw is floor(u n) — the rule the stand-alone belief
+      // uses in that state (fba_belief_sample), with the same u
+        if (threadIdx.x == 0)
+        {
+            auto g         = RngOf<false>::make(rr, 0);
+            double const u = draw_u(g);
+            A.picked[r]    = min(n - 1, (long long)floor(__dmul_rn(u, (double)n)));
+        }
+        return;
+    }
+
     if (MODE == 0)
     { // importance_sampling::update, per-particle part (k_propose)
         int const a = A.action ? A.action[r] : A.action0, o = A.observation ? A.observation[r] : A.observation0;
