@@ -108,9 +108,12 @@ def test_flat_and_delta_beliefs(ctx):
       upper: -1 + 0.95 * 10 = 8.5 (listen once, then the right door);
       lower: the tree policy below the root is UCB over tried actions after each action was tried once,
              so in expectation it is no worse than the uniformly random policy, whose value is
-             _listen_then_random_value(3) = -38.9. Returns lie in [-96, 8.5]; as a -100/+10 coin their
-             sd is at most 55, so the mean over all seeds must exceed -38.9 - 4 * 55 / sqrt(visits).
-    Eight seeds per storage kind; no single search is judged on its own."""
+             _listen_then_random_value(3) = -38.9.
+    The simulations of one wave are NOT independent samples (they share statistics while in flight), so the unit
+    of the statistical check is the SEARCH: 64 seeds per storage kind, the mean of their Q(listen) must exceed
+    -38.9 minus 4 standard errors of that mean (estimated from the 64 values) minus 2 (measured: mean -39.0,
+    per-search sd 3.7, profiles/r2w_tree_seeds.txt; round 1's herding bug gave -78). No single search is judged
+    on its own — 8 seeds and a bound that assumed independent simulations failed once in twenty suite runs."""
     import fba_pomdp_b200 as fba
     n = 1024
     states = np.ones(n)          # tiger right everywhere: open-right (action 1) pays +10
@@ -119,17 +122,17 @@ def test_flat_and_delta_beliefs(ctx):
     for kw in (dict(), dict(weighted=False), dict(delta=64)):
         g, sim, b = _tiger(ctx, n, states, **kw)
         tree = fba.SearchTree(sim, 4096, 6)
-        tot, cnt = 0.0, 0
-        for seed in range(8):
+        q_listen = []
+        for seed in range(64):
             a, q, visits = tree.selectAction(b, 4096, 3, 30.0, 0.95, 512, fba.Rng.philox(7 + seed))
             assert a == 1 and visits.sum() == 4096 and visits.min() >= 1
             # tiger is episodic here (opening ends the episode): exact terminal values
             assert q[1] == 10.0 and q[0] == -100.0
             assert -96.0 <= q[2] <= 8.5
-            tot += q[2] * visits[2]
-            cnt += int(visits[2])
-        mean = tot / cnt
-        assert mean > q_random - 4.0 * 55.0 / np.sqrt(cnt), (kw, mean, cnt)
+            q_listen.append(q[2])
+        q_listen = np.array(q_listen)
+        se = q_listen.std(ddof=1) / np.sqrt(len(q_listen))
+        assert q_listen.mean() > q_random - 4.0 * se - 2.0, (kw, q_listen.mean(), se, q_listen.min())
         tree.free()
         b.free()
         sim.close()
