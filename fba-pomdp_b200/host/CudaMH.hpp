@@ -33,6 +33,65 @@
 
 namespace fba_b200 {
 
+// The prior model of a structure (FBAPOMDPPrior::computePriorModel, by the reference's own code) in this repo's block
+// layout, cached per structure id for the duration of one MH / Gibbs run, plus the id <-> Structure maps both
+// samplers need. `flat` / `sid` are what fba_belief_init takes as prototypes.
+class PriorModelCache
+{
+public:
+    using Structure = ::bayes_adaptive::factored::BABNModel::Structure;
+
+    PriorModelCache(CudaSimulator const& cuda, ::bayes_adaptive::factored::FBAPOMDP const& fbapomdp, int64_t stride,
+                    char const* who) :
+            _cuda(cuda), _fbapomdp(fbapomdp), _stride(stride), _who(who)
+    {
+    }
+
+    // prototype index of structure `id` (computing and caching its prior model on first use)
+    int32_t of(int32_t id, Structure const& st)
+    {
+        auto it = _index.find(id);
+        if (it != _index.end()) return it->second;
+        auto model        = _fbapomdp.prior()->computePriorModel(st);
+        int32_t const got = _cuda.describeModel(&model, &_block);
+        if (got != id) throw std::string(_who) + ": the prior model of a structure has another structure";
+        if ((int64_t)_block.size() > _stride) throw std::string(_who) + ": structure larger than the particle blocks";
+        int32_t const k = (int32_t)sid.size();
+        sid.push_back(id);
+        flat.resize((size_t)(k + 1) * _stride, 0.0f);
+        std::copy(_block.begin(), _block.end(), flat.begin() + (size_t)k * _stride);
+        _index.emplace(id, k);
+        return k;
+    }
+    int32_t of(int32_t id) { return of(id, structure(id)); }
+
+    Structure const& structure(int32_t id)
+    {
+        auto it = _structures.find(id);
+        if (it == _structures.end()) it = _structures.emplace(id, _cuda.structureOf(id)).first;
+        return it->second;
+    }
+
+    // every particle of b becomes the prior model proto[i] names (zeros: a vector of at least b's size)
+    void setPriors(fba_belief* b, std::vector<int32_t> const& proto, std::vector<int32_t> const& zeros) const
+    {
+        check(_cuda.ctx(), fba_belief_init(b, (int32_t)sid.size(), sid.data(), flat.data(), proto.data(), zeros.data()),
+              "fba_belief_init");
+    }
+
+    std::vector<int32_t> sid; // prototype k has structure sid[k] ...
+    std::vector<float> flat;  // ... and counts flat[k * stride ..]
+
+private:
+    CudaSimulator const& _cuda;
+    ::bayes_adaptive::factored::FBAPOMDP const& _fbapomdp;
+    int64_t _stride;
+    char const* _who;
+    std::vector<float> _block;
+    std::map<int32_t, int32_t> _index;
+    std::map<int32_t, Structure> _structures;
+};
+
 class CudaMHNIPS2018 : public CudaParticleBelief
 {
 public:
@@ -132,45 +191,17 @@ private:
         int64_t const stride = fba_belief_stride(_belief);
         Beliefs tmp;
 
-        // the prior model of a structure, by the reference's own prior, in this repo's layout; cached per id
-        std::vector<int32_t> prior_sid;      // prototype k has structure prior_sid[k] ...
-        std::vector<float> prior_flat;       // ... and counts prior_flat[k * stride ..]
-        std::map<int32_t, int32_t> prior_of; // structure id -> prototype
-        std::vector<float> block;
-        auto priorOf = [&](int32_t id, ::bayes_adaptive::factored::BABNModel::Structure const& st) {
-            auto it = prior_of.find(id);
-            if (it != prior_of.end()) return it->second;
-            auto model         = fbapomdp.prior()->computePriorModel(st);
-            int32_t const got  = _cuda->describeModel(&model, &block);
-            if (got != id) throw std::string("CudaMHNIPS2018: the prior model of a structure has another structure");
-            if ((int64_t)block.size() > stride) throw std::string("CudaMHNIPS2018: structure larger than the particle blocks");
-            int32_t const k = (int32_t)prior_sid.size();
-            prior_sid.push_back(id);
-            prior_flat.resize((size_t)(k + 1) * stride, 0.0f);
-            std::copy(block.begin(), block.end(), prior_flat.begin() + (size_t)k * stride);
-            prior_of.emplace(id, k);
-            return k;
-        };
-        std::map<int32_t, ::bayes_adaptive::factored::BABNModel::Structure> structure_of;
-        auto structureOf = [&](int32_t id) -> ::bayes_adaptive::factored::BABNModel::Structure const& {
-            auto it = structure_of.find(id);
-            if (it == structure_of.end()) it = structure_of.emplace(id, _cuda->structureOf(id)).first;
-            return it->second;
-        };
+        PriorModelCache priors(*_cuda, fbapomdp, stride, "CudaMHNIPS2018");
         auto priorBelief = [&](std::vector<int32_t> const& proto) { // n particles, particle i = prior prototype proto[i]
             fba_belief* b = tmp.make(ctx, _cuda->model(), (int64_t)proto.size(), stride, 0);
-            std::vector<int32_t> zeros(proto.size(), 0);
-            check(ctx,
-                  fba_belief_init(b, (int32_t)prior_sid.size(), prior_sid.data(), prior_flat.data(), proto.data(),
-                                  zeros.data()),
-                  "fba_belief_init");
+            priors.setPriors(b, proto, std::vector<int32_t>(proto.size(), 0));
             return b;
         };
 
         // old_score of every particle: LogBDScore against the prior model of ITS structure (:237)
         std::vector<int32_t> sid((size_t)N), proto((size_t)N);
         check(ctx, fba_belief_download(_belief, 0, N, nullptr, sid.data(), nullptr, nullptr), "fba_belief_download");
-        for (int64_t i = 0; i < N; ++i) proto[(size_t)i] = priorOf(sid[(size_t)i], structureOf(sid[(size_t)i]));
+        for (int64_t i = 0; i < N; ++i) proto[(size_t)i] = priors.of(sid[(size_t)i]);
         std::vector<double> old_score((size_t)N);
         {
             fba_belief* pb = priorBelief(proto);
@@ -189,7 +220,7 @@ private:
         fba_belief* fresh = tmp.make(ctx, _cuda->model(), N, stride, 1);
         {
             std::vector<int32_t> zeros((size_t)N, 0);
-            check(ctx, fba_belief_init(fresh, 1, prior_sid.data(), prior_flat.data(), zeros.data(), zeros.data()),
+            check(ctx, fba_belief_init(fresh, 1, priors.sid.data(), priors.flat.data(), zeros.data(), zeros.data()),
                   "fba_belief_init"); // placeholder particles, uniform weights 1/N (:243); every slot is overwritten
         }
         int64_t accepted = 0;
@@ -198,11 +229,7 @@ private:
         fba_belief* prop  = tmp.make(ctx, _cuda->model(), P, stride, 0);
         fba_belief* prior = tmp.make(ctx, _cuda->model(), P, stride, 0);
         std::vector<int32_t> zerosP((size_t)P, 0);
-        auto setPriors = [&](fba_belief* b, std::vector<int32_t> const& proto) {
-            check(ctx, fba_belief_init(b, (int32_t)prior_sid.size(), prior_sid.data(), prior_flat.data(), proto.data(),
-                                       zerosP.data()),
-                  "fba_belief_init");
-        };
+        auto setPriors = [&](fba_belief* b, std::vector<int32_t> const& proto) { priors.setPriors(b, proto, zerosP); };
         while (accepted < N)
         {
             std::vector<int64_t> src((size_t)P);
@@ -211,12 +238,12 @@ private:
             for (int64_t j = 0; j < P; ++j)
             {
                 int32_t const id = sid[(size_t)src[(size_t)j]];
-                if (rnd::boolean()) pproto[(size_t)j] = priorOf(id, structureOf(id)); // :206-208: same structure half the time
+                if (rnd::boolean()) pproto[(size_t)j] = priors.of(id); // :206-208: same structure half the time
                 else
                 {
-                    auto st            = fbapomdp.mutate(structureOf(id));
+                    auto st            = fbapomdp.mutate(priors.structure(id));
                     int32_t const nid  = _cuda->structureId(st);
-                    pproto[(size_t)j]  = priorOf(nid, st);
+                    pproto[(size_t)j]  = priors.of(nid, st);
                 }
             }
             setPriors(prop, pproto);
@@ -360,7 +387,6 @@ private:
 
     void reinvigorate(POMDP const& d)
     {
-        using Structure      = ::bayes_adaptive::factored::BABNModel::Structure;
         auto const& fbapomdp = dynamic_cast<::bayes_adaptive::factored::FBAPOMDP const&>(d);
         fba_ctx* ctx         = _cuda->ctx();
         int64_t const N      = (int64_t)_n;
@@ -379,37 +405,10 @@ private:
         std::vector<float> state_prior((size_t)_cuda->S());
         for (int s = 0; s < _cuda->S(); ++s) state_prior[(size_t)s] = fbapomdp.domainStatePrior()->prob((size_t)s);
 
-        // prior models by the reference's own prior, cached per structure id (as CudaMHNIPS2018)
-        std::vector<int32_t> prior_sid;
-        std::vector<float> prior_flat, block;
-        std::map<int32_t, int32_t> prior_of;
-        std::map<int32_t, Structure> structure_of;
-        auto priorOf = [&](int32_t id, Structure const& st) {
-            auto it = prior_of.find(id);
-            if (it != prior_of.end()) return it->second;
-            auto model        = fbapomdp.prior()->computePriorModel(st);
-            int32_t const got = _cuda->describeModel(&model, &block);
-            if (got != id) throw std::string("CudaMHwithinGibbs: the prior model of a structure has another structure");
-            if ((int64_t)block.size() > stride) throw std::string("CudaMHwithinGibbs: structure larger than the particle blocks");
-            int32_t const k = (int32_t)prior_sid.size();
-            prior_sid.push_back(id);
-            prior_flat.resize((size_t)(k + 1) * stride, 0.0f);
-            std::copy(block.begin(), block.end(), prior_flat.begin() + (size_t)k * stride);
-            prior_of.emplace(id, k);
-            return k;
-        };
-        auto structureOf = [&](int32_t id) -> Structure const& {
-            auto it = structure_of.find(id);
-            if (it == structure_of.end()) it = structure_of.emplace(id, _cuda->structureOf(id)).first;
-            return it->second;
-        };
+        PriorModelCache priors(*_cuda, fbapomdp, stride, "CudaMHwithinGibbs");
         std::vector<int32_t> zeros((size_t)std::max(C, N), 0);
         // every particle of b becomes the prior model its chain names
-        auto setPriors = [&](fba_belief* b, std::vector<int32_t> const& proto) {
-            check(ctx, fba_belief_init(b, (int32_t)prior_sid.size(), prior_sid.data(), prior_flat.data(), proto.data(),
-                                       zeros.data()),
-                  "fba_belief_init");
-        };
+        auto setPriors = [&](fba_belief* b, std::vector<int32_t> const& proto) { priors.setPriors(b, proto, zeros); };
         auto sampleHistories = [&](fba_belief* models, std::vector<int32_t>& seq) { // sampleStateHistory, :215-232
             seq.resize((size_t)(C * L));
             check(ctx,
@@ -436,7 +435,7 @@ private:
         std::vector<int32_t> seq, new_seq, cur_sid((size_t)C), cur_proto((size_t)C);
         sampleHistories(cur, seq);
         check(ctx, fba_belief_download(cur, 0, C, nullptr, cur_sid.data(), nullptr, nullptr), "fba_belief_download");
-        for (int64_t c = 0; c < C; ++c) cur_proto[(size_t)c] = priorOf(cur_sid[(size_t)c], structureOf(cur_sid[(size_t)c]));
+        for (int64_t c = 0; c < C; ++c) cur_proto[(size_t)c] = priors.of(cur_sid[(size_t)c]);
         setPriors(pri, cur_proto);
         addCounts(pri, seq);
         check(ctx, fba_belief_replace_from(cur, all.data(), pri, all.data(), C), "fba_belief_replace_from");
@@ -445,7 +444,7 @@ private:
         check(ctx, fba_belief_log_bd_score(cur, prop, score.data()), "fba_belief_log_bd_score");
 
         fba_belief* fresh = tmp.make(ctx, _cuda->model(), N, stride, 1);
-        check(ctx, fba_belief_init(fresh, 1, prior_sid.data(), prior_flat.data(), zeros.data(), zeros.data()),
+        check(ctx, fba_belief_init(fresh, 1, priors.sid.data(), priors.flat.data(), zeros.data(), zeros.data()),
               "fba_belief_init"); // placeholders with weight 1 / N (:372-374); every slot is overwritten
         int64_t accepted = 0;
         std::vector<int32_t> pproto((size_t)C), pid((size_t)C);
@@ -455,9 +454,9 @@ private:
             // :360-365: every chain's proposal mutate(model.structure()), its posterior counts and score
             for (int64_t c = 0; c < C; ++c)
             {
-                auto st           = fbapomdp.mutate(structureOf(cur_sid[(size_t)c]));
+                auto st           = fbapomdp.mutate(priors.structure(cur_sid[(size_t)c]));
                 pid[(size_t)c]    = _cuda->structureId(st);
-                pproto[(size_t)c] = priorOf(pid[(size_t)c], st);
+                pproto[(size_t)c] = priors.of(pid[(size_t)c], st);
             }
             setPriors(prop, pproto);
             setPriors(pri, pproto);
