@@ -245,3 +245,30 @@ def test_domain_mutate_equals_the_reference(name):
         np.testing.assert_array_equal(tp, g[P + "t_out"][k])
         np.testing.assert_array_equal(op, g[P + "o_out"][k])
     assert used(rng)
+
+
+def test_oracle_messages_and_rejection_sample_the_same_conditional():
+    """a size-independent property of the two state-history samplers (MHwithinGibbs.cpp:38-213): both draw from
+    p(states | model, actions, observations), so over 3000 draws each, from unrelated word streams, the frequency
+    of every domain state at every position of the history agrees within 5 standard errors"""
+    g, m, old = load_gibbs("msg")
+    k = int(old.struct_id[0])
+    tp, op = g["structs/t_par"][k], g["structs/o_par"][k]
+    counts = np.zeros(g["priors/counts"].shape[1], np.float32)
+    counts[:old.counts.shape[1]] = old.counts[0]
+    hist = (g["history/len"][:3], g["history/a"][:int(g["history/len"][:3].sum())],
+            g["history/o"][:int(g["history/len"][:3].sum())])
+    n = 3000
+    rs = np.random.RandomState(12)
+    out = {}
+    for method, words_per in (("msg", 64), ("rs", 20000)):
+        rows = []
+        for i in range(n):
+            rng = O.Rng(rs.randint(0, 1 << 32, size=words_per, dtype=np.uint64).astype(np.uint32))
+            rows.append(O.state_history(m, tp, op, counts, *hist, rng, method, g["model_state_prior"]))
+        out[method] = np.stack(rows)
+    for pos in range(out["msg"].shape[1]):
+        pa = np.bincount(out["msg"][:, pos], minlength=m.S) / n
+        pr = np.bincount(out["rs"][:, pos], minlength=m.S) / n
+        p = (pa + pr) / 2
+        assert np.all(np.abs(pa - pr) <= 5 * np.sqrt(2 * p * (1 - p) / n) + 1e-9), pos
