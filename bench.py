@@ -407,7 +407,7 @@ def structure_beliefs_leg(ctx, fba, args):
                               "bottom_particle_attempts_per_s": n_top * attempts / (ms_nested * 1e-3)},
             "note": "parity: tests/test_cuda_gibbs.py, tests/test_cuda_composite.py (REPLAY bit-exact vs the oracle pinned "
                     "to the reference's classes); whole-belief update cost against the reference's core: "
-                    "profiles/r2j_structure_beliefs.jsonl"}
+                    "profiles/r2z_structure_beliefs.jsonl"}
 
 
 def main_reference(args):

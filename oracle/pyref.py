@@ -219,6 +219,16 @@ class Ref:
         s = f(self.h, C.byref(n))
         return s, n.value
 
+    def adapter_update_times(self):
+        """seconds of every Belief::updateEstimation call of the last adapter_episodes call"""
+        f = self.L.ref_adapter_update_times
+        f.restype = C.c_long
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_long]
+        n = f(self.h, None, 0)
+        out = np.zeros(max(n, 1), np.float64)
+        f(self.h, _p(out), n)
+        return out[:n]
+
     def batched_episodes(self, n, runs, sims, episodes, sims_per_wave=1, device=0, seed=4711):
         """fba_b200::runBatchedExperiment on GPU `device` -> (returns[episodes, runs], seconds)"""
         f = self.L.ref_batched_episodes_on

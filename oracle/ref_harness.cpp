@@ -112,6 +112,7 @@ struct Handle
     long adapter_events = -1; // what the last ref_adapter_episodes' CUDA belief did beyond plain filtering
     double update_seconds = 0; // wall time inside updateEstimation during the last ref_adapter_episodes
     long update_calls     = 0;
+    std::vector<double> update_times; // ... per call
 };
 
 // forwards to a belief and times its updateEstimation calls
@@ -127,7 +128,9 @@ public:
     {
         auto t0 = std::chrono::steady_clock::now();
         _b->updateEstimation(a, o, d);
-        _h->update_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        double const dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        _h->update_seconds += dt;
+        _h->update_times.push_back(dt);
         ++_h->update_calls;
     }
 
@@ -1203,6 +1206,7 @@ int ref_adapter_episodes(void* hv, int kind, long n, char const* planner, int si
 
         belief->initiate(*h->sim);
         h->update_seconds = 0, h->update_calls = 0;
+        h->update_times.clear();
         TimedBelief timed(belief.get(), h);
         // the CUDA planners need to see the CUDA belief itself (they read its device handle): no timing wrapper there
         bool const cuda_planner = conf.planner.rfind("cuda-", 0) == 0;
@@ -1235,6 +1239,15 @@ int ref_adapter_episodes(void* hv, int kind, long n, char const* planner, int si
 long ref_adapter_events(void* hv)
 {
     return static_cast<Handle*>(hv)->adapter_events;
+}
+
+// per-call seconds inside Belief::updateEstimation during the last ref_adapter_episodes (at most cap of them)
+long ref_adapter_update_times(void* hv, double* out, long cap)
+{
+    auto h = static_cast<Handle*>(hv);
+    long n = std::min<long>(cap, (long)h->update_times.size());
+    for (long i = 0; i < n; ++i) out[i] = h->update_times[(size_t)i];
+    return (long)h->update_times.size();
 }
 
 // seconds spent inside Belief::updateEstimation during the last ref_adapter_episodes, and the number of calls
