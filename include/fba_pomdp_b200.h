@@ -235,7 +235,10 @@ int fba_belief_reset_domain_states(fba_belief* b, fba_rng* rng);
  * that keep their weighted filter as it is (MHNIPS2018.cpp:132-147, CheatingReinvigoration.cpp:50-66,
  * StructureIncubatorSampling.cpp:46-61). For a flat belief the same as fba_belief_reset_domain_states. */
 int fba_belief_redraw_domain_states(fba_belief* b, fba_rng* rng);
-/* Belief::sample (Belief.hpp:34): index of the drawn particle (use fba_belief_download to view it) */
+/* Belief::sample (Belief.hpp:34): index of the drawn particle (use fba_belief_download to view it). PHILOX mode,
+ * right after init / a resample / a reset — every weight is 1 / N, which the library tracks — the weighted draw is
+ * floor(u N) computed on the host: no kernel, no read-back (fba_runs_sample uses the same rule and the same u).
+ * REPLAY mode always evaluates WeightedFilter::sample's arithmetic (WeightedFilter.cpp:163-191). */
 int fba_belief_sample(fba_belief* b, fba_rng* rng, int64_t* index);
 
 /* beliefs::rejectSample (src/beliefs/particle_filters/RejectionSampling.hpp:26-72) on a flat belief */
@@ -508,7 +511,8 @@ int fba_runs_plan(fba_runs* runs, int64_t n_simulations, const int32_t* depth, d
 /* count blocks copied by the in-place resamples of all runs since creation */
 int64_t fba_runs_copies(fba_runs* runs);
 
-/* device pointers of the current particle arrays, for zero-copy views by the host language */
+/* device pointers of the current particle arrays, for zero-copy views by the host language (once the weight pointer
+ * has been handed out the library no longer assumes it knows the weights: the uniform-weights shortcuts are off) */
 void* fba_belief_counts_ptr(fba_belief* b);
 void* fba_belief_state_ptr(fba_belief* b);
 void* fba_belief_weight_ptr(fba_belief* b);
