@@ -3121,6 +3121,7 @@ extern "C" int fba_nested_update(fba_nested* n, int32_t action, int32_t observat
                    "its bottom filter was full";
         return rng->mode == FBA_RNG_REPLAY ? FBA_ERR_RNG_UNDERRUN : FBA_ERR_CAPACITY;
     }
+    if (rng->mode == FBA_RNG_REPLAY && (rc = check_flag(ctx))) return rc; // a slice that ran out inside its last attempt
     n->cur ^= 1;
     return nested_normalize(n);
 }
