@@ -2580,7 +2580,10 @@ extern "C" int fba_belief_sample_state_history(fba_belief* b, int32_t method, in
     h.H.max_attempts         = max_attempts;
     long long const out_len  = h.total + n_episodes;
     PoolTmp<int> d_out, d_failed;
-    if ((rc = d_out.alloc(ctx, (size_t)b->N * out_len)) || (rc = d_failed.alloc(ctx, 1))) return rc;
+    PoolTmp<long long> d_words_used; // REPLAY: words every particle's slice actually handed out
+    if ((rc = d_out.alloc(ctx, (size_t)b->N * out_len)) || (rc = d_failed.alloc(ctx, 1))
+        || (rc = d_words_used.alloc(ctx, (size_t)b->N)))
+        return rc;
     CU(ctx, cudaMemsetAsync(d_failed, 0, sizeof(int), ctx->stream));
     bool const replay   = rng->mode == FBA_RNG_REPLAY;
     long long const per = replay ? (rng->n_words - rng->cursor) / b->N : 0;
@@ -2598,10 +2601,12 @@ extern "C" int fba_belief_sample_state_history(fba_belief* b, int32_t method, in
         bool const lr = b->m->long_rows;
         if (replay && lr)
             LAUNCH(ctx, (k_state_history_rs<true, true>), blocks_for(b->N, 32), 32, D, b->counts[b->cur], b->stride,
-                   b->sid[b->cur], b->N, h.H, ra, (int*)d_out, out_len, (int*)d_failed, ctx->d_flag);
+                   b->sid[b->cur], b->N, h.H, ra, (int*)d_out, out_len, (int*)d_failed, ctx->d_flag,
+                   (long long*)d_words_used);
         else if (replay)
             LAUNCH(ctx, (k_state_history_rs<true, false>), blocks_for(b->N, 32), 32, D, b->counts[b->cur], b->stride,
-                   b->sid[b->cur], b->N, h.H, ra, (int*)d_out, out_len, (int*)d_failed, ctx->d_flag);
+                   b->sid[b->cur], b->N, h.H, ra, (int*)d_out, out_len, (int*)d_failed, ctx->d_flag,
+                   (long long*)d_words_used);
         else
         { // PHILOX: one warp per particle, 32 attempts per round (the thread-per-particle kernel is the REPLAY form)
             PoolTmp<int> d_scratch;
@@ -2658,7 +2663,7 @@ extern "C" int fba_belief_sample_state_history(fba_belief* b, int32_t method, in
         if (ctx->profiling) profile_mark(ctx, "k_state_history_msg", true);                                        \
         k_state_history_msg<R, SHM><<<(int)b->N, msg_threads, sh_bytes, ctx->stream>>>(                            \
             D, b->N, h.H, (const float*)d_T, (const float*)d_O, (const float*)d_prior, (double*)d_msg, ra,         \
-            (int*)d_out, out_len, ctx->d_flag);                                                                    \
+            (int*)d_out, out_len, ctx->d_flag, (long long*)d_words_used);                                          \
         if (ctx->profiling) profile_mark(ctx, "k_state_history_msg", false);                                       \
         ++ctx->launches;                                                                                           \
         CU(ctx, cudaGetLastError());                                                                               \
@@ -2672,11 +2677,11 @@ extern "C" int fba_belief_sample_state_history(fba_belief* b, int32_t method, in
             if (replay)
                 k_state_history_msg_cluster<true><<<(int)b->N * kMsgCluster, cl_threads, sh_bytes, ctx->stream>>>(
                     D, b->N, h.H, (const float*)d_T, (const float*)d_O, (const float*)d_prior, (double*)d_msg, ra,
-                    (int*)d_out, out_len, ctx->d_flag);
+                    (int*)d_out, out_len, ctx->d_flag, (long long*)d_words_used);
             else
                 k_state_history_msg_cluster<false><<<(int)b->N * kMsgCluster, cl_threads, sh_bytes, ctx->stream>>>(
                     D, b->N, h.H, (const float*)d_T, (const float*)d_O, (const float*)d_prior, (double*)d_msg, ra,
-                    (int*)d_out, out_len, ctx->d_flag);
+                    (int*)d_out, out_len, ctx->d_flag, (long long*)nullptr);
             if (ctx->profiling) profile_mark(ctx, "k_state_history_msg_cluster", false);
             ++ctx->launches;
             CU(ctx, cudaGetLastError());
@@ -2702,7 +2707,14 @@ extern "C" int fba_belief_sample_state_history(fba_belief* b, int32_t method, in
     if (replay)
     {
         if ((rc = check_flag(ctx))) return rc;
-        rng->cursor += per * b->N;
+        if (b->N == 1)
+        { // a single model consumes the stream the way the reference does: exactly the words it drew
+            long long used = 0;
+            CU(ctx, cudaMemcpyAsync(&used, (long long*)d_words_used, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(ctx, cudaStreamSynchronize(ctx->stream));
+            rng->cursor += used;
+        } else
+            rng->cursor += per * b->N;
     }
     return FBA_OK;
 }

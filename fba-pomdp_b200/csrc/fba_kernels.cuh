@@ -2893,6 +2893,10 @@ __global__ void __launch_bounds__(kThreads)
 // model and the (action, observation) history, and the posterior counts of a state history.
 // ------------------------------------------------------------------------------------------------
 
+// words a replay source has handed out so far (0 for the counter-based source)
+__device__ __forceinline__ long long rng_words_used(const ReplayRng& g, long long start) { return g.pos - start; }
+__device__ __forceinline__ long long rng_words_used(const PhiloxRng&, long long) { return 0; }
+
 // rejectionSampleStateHistory (:38-94), one thread per particle (model): per episode a start state, then s'
 // and o from the particle's counts (expected Dirichlets, counts untouched) step after step; the first wrong
 // observation abandons the attempt. states_out: per particle (n_steps + n_episodes) states.
@@ -2900,7 +2904,7 @@ template<bool REPLAY, bool LONG>
 __global__ void __launch_bounds__(kThreads)
     k_state_history_rs(DevModel M, const float* __restrict__ counts, long long stride, const int* __restrict__ sid,
                        long long N, HistoryArgs H, RngArgs ra, int* __restrict__ states_out, long long out_stride,
-                       int* __restrict__ failed, int* __restrict__ overrun)
+                       int* __restrict__ failed, int* __restrict__ overrun, long long* __restrict__ words_used)
 {
     long long const i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
@@ -2938,6 +2942,7 @@ __global__ void __launch_bounds__(kThreads)
         pos += len + 1;
     }
     if (g.overrun) *overrun = 1;
+    if (words_used) words_used[i] = rng_words_used(g, i * ra.words_per_item);
 }
 
 // The same in PHILOX mode with ONE WARP per particle: the attempts of an episode are independent draws, so the 32
@@ -3098,7 +3103,7 @@ __global__ void __launch_bounds__(kMsgThreads)
     k_state_history_msg(DevModel M, long long N, HistoryArgs H, const float* __restrict__ Tt_all,
                         const float* __restrict__ Ot_all, const float* __restrict__ state_prior,
                         double* __restrict__ msg_all, RngArgs ra, int* __restrict__ states_out, long long out_stride,
-                        int* __restrict__ overrun)
+                        int* __restrict__ overrun, long long* __restrict__ words_used)
 {
     extern __shared__ double sh_rows[];
     long long const p = blockIdx.x;
@@ -3207,6 +3212,7 @@ __global__ void __launch_bounds__(kMsgThreads)
         first += len;
     }
     if (threadIdx.x == 0 && g.overrun) *overrun = 1;
+    if (threadIdx.x == 0 && words_used) words_used[p] = rng_words_used(g, p * ra.words_per_item);
 }
 
 // The same passes with one model spread over a thread-block CLUSTER of kMsgCluster CTAs (sm_90+ distributed
@@ -3224,7 +3230,7 @@ __global__ void __cluster_dims__(kMsgCluster, 1, 1) __launch_bounds__(kMsgThread
     k_state_history_msg_cluster(DevModel M, long long N, HistoryArgs H, const float* __restrict__ Tt_all,
                                 const float* __restrict__ Ot_all, const float* __restrict__ state_prior,
                                 double* __restrict__ msg_all, RngArgs ra, int* __restrict__ states_out,
-                                long long out_stride, int* __restrict__ overrun)
+                                long long out_stride, int* __restrict__ overrun, long long* __restrict__ words_used)
 {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
@@ -3342,6 +3348,7 @@ __global__ void __cluster_dims__(kMsgCluster, 1, 1) __launch_bounds__(kMsgThread
         first += len;
     }
     if (rank == 0 && threadIdx.x == 0 && g.overrun) *overrun = 1;
+    if (rank == 0 && threadIdx.x == 0 && words_used) words_used[p] = rng_words_used(g, p * ra.words_per_item);
 }
 
 // MHwithinGibbs::computePosteriorCounts (:397-436): incrementCountsOf(s_t, a_t, o_t, s_t+1) for every step of

@@ -375,7 +375,8 @@ int fba_belief_assign_from(fba_belief* dst, int64_t first, fba_belief* src, int6
  *     FBAPOMDP::domainStatePrior()->prob(s) (the prior of s_0); one CTA per particle;
  *   method 1 (RS, :38-94): rejection sampling with the particle's counts, one thread per particle; more than
  *     max_attempts episode attempts in one particle: FBA_ERR_CAPACITY.
- * Counts are not modified. REPLAY: particle i draws from the i-th equal slice of the remaining words. */
+ * Counts are not modified. REPLAY: particle i draws from the i-th equal slice of the remaining words and the call
+ * takes all of them; a belief of ONE particle consumes exactly the words it drew, like the reference. */
 int fba_belief_sample_state_history(fba_belief* b, int32_t method, int32_t n_episodes, const int32_t* episode_len,
                                     const int32_t* actions, const int32_t* observations, const float* state_prior,
                                     fba_rng* rng, int64_t max_attempts, int32_t* states);

@@ -141,3 +141,83 @@ def test_messages_and_rejection_sample_the_same_conditional(env):
     with pytest.raises(fba.FbaError):
         b.sample_state_history("msg", *hist, fba.Rng.philox(7))          # no state prior
     b.free()
+
+
+@pytest.mark.parametrize("tag", ["msg", "rs"])
+def test_whole_reinvigorate_replays_the_reference(env, tag):
+    """MHwithinGibbs::reinvigorate (MHwithinGibbs.cpp:334-395) END TO END on the GPU bricks, one chain, fed the exact
+    mt19937 words the reference's private reinvigorate consumed (tests/golden/gibbs.npz): the weighted draw of the
+    start particle, every state history (a single model consumes exactly the words it draws), the posterior counts
+    and the BD scores run on the device; only the domain's mutate and the accept uniform are drawn on the host, from
+    the same stream at the same cursor. Every word is used and the new belief — structures, domain states, count
+    blocks — is the reference's bit for bit."""
+    import math
+    fba, O, g, m, sim = env
+    words = g[tag + "/words"]
+    rng, orng = fba.Rng.replay(words), O.Rng(words)
+    t_par, o_par, priors = g["structs/t_par"], g["structs/o_par"], g["priors/counts"]
+    key = {(t_par[k].tobytes(), o_par[k].tobytes()): k for k in range(len(t_par))}
+    hist = (g["history/len"], g["history/a"], g["history/o"])
+    stride = priors.shape[1]
+
+    def host(fn):                      # a host-side draw from the shared stream
+        orng.c.cur = rng.cursor
+        out = fn(orng)
+        rng.cursor = orng.c.cur
+        return out
+
+    def single(k, counts):             # a one-particle belief holding (structure k, counts)
+        c = np.zeros((1, stride), np.float32)
+        c[0, :len(counts)] = counts
+        b = fba.BARejectionSampling(1)
+        b.initiate(sim, struct_id=np.array([k], np.int32), counts=c, state=np.zeros(1, np.int32), stride=stride)
+        return b
+
+    def posterior(k, seq):             # computePosteriorCounts on the prior model of structure k
+        b = single(k, priors[k])
+        b.add_history_counts(*hist, seq)
+        return b
+
+    def score(model, k):               # model.LogBDScore(prior_model)
+        pb = single(k, priors[k])
+        s = fba.log_bd_score(model, pb)[0]
+        pb.free()
+        return s
+
+    def history(model):                # sampleStateHistory
+        return model.sample_state_history(tag, *hist, rng, state_prior=g["model_state_prior"])[0]
+
+    old = belief_of(fba, sim, g, tag)
+    from fba_pomdp_b200.capi import ptr
+    w = np.ascontiguousarray(g[tag + "/old_w"], np.float64)
+    assert old.L.fba_belief_upload(old.h, 0, len(w), None, None, None, ptr(w)) == 0
+    i = old.sample(rng)                                                        # :344
+    k = int(g[tag + "/old_struct_id"][i])
+    first = single(k, g[tag + "/old_counts"][i])
+    seq = history(first)                                                       # :345-346
+    first.free()
+    model = posterior(k, seq)                                                  # :348-350
+    sc = score(model, k)
+    n_out = len(g[tag + "/new_state"])
+    sid, state, counts = [], [], []
+    proposals = 0
+    while len(sid) < n_out:                                                    # :356
+        tp2, op2 = host(lambda r: O.mutate_structure(m, t_par[k], o_par[k], 0, r))      # :360
+        k2 = key[(tp2.tobytes(), op2.tobytes())]
+        new_model = posterior(k2, seq)                                         # :362
+        new_sc = score(new_model, k2)
+        proposals += 1
+        if math.log(host(lambda r: O.lib().orc_uniform01(r.ref()))) < new_sc - sc:      # :367
+            sid.append(k2), state.append(int(seq[-1]))
+            counts.append(new_model.download()["counts"][0])
+            seq = history(model)                                               # :377-378: the model BEFORE the move
+            model.free()
+            k, model = k2, posterior(k2, seq)                                  # :381
+            sc = score(model, k2)
+        new_model.free()
+    assert rng.exhausted and proposals > n_out
+    np.testing.assert_array_equal(sid, g[tag + "/new_struct_id"])
+    np.testing.assert_array_equal(state, g[tag + "/new_state"])
+    np.testing.assert_array_equal(np.stack(counts)[:, :g[tag + "/new_counts"].shape[1]], g[tag + "/new_counts"])
+    model.free()
+    old.free()
