@@ -2433,6 +2433,7 @@ extern "C" int fba_belief_replay_history(fba_belief* b, int32_t n_episodes, cons
     }
     CU(ctx, cudaSetDevice(ctx->device));
     DevTmp<int> d_len, d_act, d_obs, d_rec, d_failed;
+    DevTmp<long long> d_words_used;
     CU(ctx, cudaMalloc(&d_len, std::max(1, (int)n_episodes) * sizeof(int)));
     CU(ctx, cudaMalloc(&d_act, std::max(1ll, total) * sizeof(int)));
     CU(ctx, cudaMalloc(&d_obs, std::max(1ll, total) * sizeof(int)));
@@ -2458,25 +2459,33 @@ extern "C" int fba_belief_replay_history(fba_belief* b, int32_t n_episodes, cons
         REQUIRE(ctx, per >= 1, "replay_history: the replay stream is shorter than one word per particle");
         if ((rc = stage_words(ctx, rng, per * b->N))) return rc;
         if ((rc = clear_flag(ctx))) return rc;
+        CU(ctx, cudaMalloc(&d_words_used, (size_t)b->N * sizeof(long long)));
         if (lr)
             LAUNCH(ctx, (k_mh_replay<true, true>), blocks_for(b->N), kThreads, D, b->counts[b->cur], b->stride,
                    b->state[b->cur], b->sid[b->cur], b->N, H, replay_args(ctx, per * b->N, per, false), (int*)d_rec,
-                   (int*)d_failed, ctx->d_flag);
+                   (int*)d_failed, ctx->d_flag, (long long*)d_words_used);
         else
             LAUNCH(ctx, (k_mh_replay<true, false>), blocks_for(b->N), kThreads, D, b->counts[b->cur], b->stride,
                    b->state[b->cur], b->sid[b->cur], b->N, H, replay_args(ctx, per * b->N, per, false), (int*)d_rec,
-                   (int*)d_failed, ctx->d_flag);
-        rng->cursor += per * b->N;
+                   (int*)d_failed, ctx->d_flag, (long long*)d_words_used);
+        if (b->N == 1)
+        { // a single proposal consumes the stream the way the reference does: exactly the words it drew
+            long long used = 0;
+            CU(ctx, cudaMemcpyAsync(&used, (long long*)d_words_used, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(ctx, cudaStreamSynchronize(ctx->stream));
+            rng->cursor += used;
+        } else
+            rng->cursor += per * b->N;
     } else
     {
         if (lr)
             LAUNCH(ctx, (k_mh_replay<false, true>), blocks_for(b->N), kThreads, D, b->counts[b->cur], b->stride,
                    b->state[b->cur], b->sid[b->cur], b->N, H, philox_args(rng), (int*)d_rec, (int*)d_failed,
-                   ctx->d_flag);
+                   ctx->d_flag, (long long*)nullptr);
         else
             LAUNCH(ctx, (k_mh_replay<false, false>), blocks_for(b->N), kThreads, D, b->counts[b->cur], b->stride,
                    b->state[b->cur], b->sid[b->cur], b->N, H, philox_args(rng), (int*)d_rec, (int*)d_failed,
-                   ctx->d_flag);
+                   ctx->d_flag, (long long*)nullptr);
     }
     CU(ctx, cudaMemcpyAsync(ctx->h_flag, d_failed, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));

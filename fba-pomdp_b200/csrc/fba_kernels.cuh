@@ -45,6 +45,10 @@ struct RngOf<false>
     }
 };
 
+// words a replay source has handed out so far (0 for the counter-based source)
+__device__ __forceinline__ long long rng_words_used(const ReplayRng& g, long long start) { return g.pos - start; }
+__device__ __forceinline__ long long rng_words_used(const PhiloxRng&, long long) { return 0; }
+
 // ------------------------------------------------------------------------------------------------
 // particle block copies: one warp per destination particle, 16-byte vectors, streaming hints
 // (every byte is touched once per update, so nothing should be kept in L1)
@@ -2722,7 +2726,7 @@ template<bool REPLAY, bool LONG>
 __global__ void __launch_bounds__(kThreads)
     k_mh_replay(DevModel M, float* counts, long long stride, int* __restrict__ state, const int* __restrict__ sid,
                 long long N, HistoryArgs H, RngArgs ra, int* __restrict__ rec_all, int* __restrict__ failed,
-                int* __restrict__ overrun)
+                int* __restrict__ overrun, long long* __restrict__ words_used)
 {
     long long const i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
@@ -2767,6 +2771,7 @@ __global__ void __launch_bounds__(kThreads)
     }
     state[i] = new_s;
     if (g.overrun) *overrun = 1;
+    if (words_used) words_used[i] = rng_words_used(g, i * ra.words_per_item);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2892,10 +2897,6 @@ __global__ void __launch_bounds__(kThreads)
 // MHwithinGibbs (src/beliefs/bayes-adaptive/factored/MHwithinGibbs.cpp): state histories conditioned on a
 // model and the (action, observation) history, and the posterior counts of a state history.
 // ------------------------------------------------------------------------------------------------
-
-// words a replay source has handed out so far (0 for the counter-based source)
-__device__ __forceinline__ long long rng_words_used(const ReplayRng& g, long long start) { return g.pos - start; }
-__device__ __forceinline__ long long rng_words_used(const PhiloxRng&, long long) { return 0; }
 
 // rejectionSampleStateHistory (:38-94), one thread per particle (model): per episode a start state, then s'
 // and o from the particle's counts (expected Dirichlets, counts untouched) step after step; the first wrong

@@ -355,7 +355,8 @@ int fba_belief_log_bd_score(fba_belief* b, fba_belief* prior, double* scores);
  * the particle's counts (expected Dirichlets), +1 on (s, a, o, s') if o is the observed one, otherwise
  * the episode's increments are taken back (-1) and the episode is tried again. Each particle's domain
  * state becomes the state after the last step. More than max_attempts attempts in one particle:
- * FBA_ERR_CAPACITY. REPLAY mode: particle i draws from the i-th equal slice of the remaining words. */
+ * FBA_ERR_CAPACITY. REPLAY mode: particle i draws from the i-th equal slice of the remaining words (a belief of ONE
+ * particle consumes exactly the words it drew, like the reference). */
 int fba_belief_replay_history(fba_belief* b, int32_t n_episodes, const int32_t* episode_len,
                               const int32_t* actions, const int32_t* observations, fba_rng* rng,
                               int64_t max_attempts);

@@ -118,3 +118,74 @@ def test_history_replay_philox_matches_the_oracle_statistically(ctx):
     assert abs(p_gpu - p_ref) < 5 * se + 0.01, (p_gpu, p_ref, se)
     prop.free()
     sim.close()
+
+
+def test_whole_mh_replays_the_reference(ctx):
+    """MHNIPS2018::MH (MHNIPS2018.cpp:188-255) END TO END on the device bricks, proposal after proposal, fed the exact
+    mt19937 words the reference's private MH consumed (tests/golden/mh.npz, 266 445 words): the weighted draw of the
+    source particle, computePosterior (a single proposal consumes exactly the words it draws) and both BD scores run
+    on the GPU; the keep-or-mutate coin, the domain's mutate and the accept uniform are drawn on the host from the
+    same stream at the same cursor. Every word is used and the new belief — structures, domain states, count blocks —
+    is the reference's bit for bit."""
+    import math
+    import fba_pomdp_b200 as fba
+    import pyoracle as O
+    from fba_pomdp_b200.capi import ptr
+    g = G.load("mh")
+    sim = fba.BAPOMDP(ctx, g.desc, g.t_par, g.o_par, max_structures=len(g.t_par))
+    m = O.Model(g.desc)
+    key = {(g.t_par[k].tobytes(), g.o_par[k].tobytes()): k for k in range(len(g.t_par))}
+    priors = g["priors/counts"]
+    stride = priors.shape[1]
+    hist = (g["history/len"], g["history/a"], g["history/o"])
+    words = g["mh/words"]
+    rng, orng = fba.Rng.replay(words), O.Rng(words)
+
+    def host(fn):                      # a host-side draw from the shared stream
+        orng.c.cur = rng.cursor
+        out = fn(orng)
+        rng.cursor = orng.c.cur
+        return out
+
+    def single(k, counts):
+        c = np.zeros((1, stride), np.float32)
+        c[0, :len(counts)] = counts
+        b = fba.BARejectionSampling(1)
+        b.initiate(sim, struct_id=np.array([k], np.int32), counts=c, state=np.zeros(1, np.int32), stride=stride)
+        return b
+
+    n = g["old/counts"].shape[0]
+    old = fba.BAImportanceSampling(n)
+    old.initiate(sim, struct_id=g["old/struct_id"], counts=g["old/counts"], state=g["old/state"], stride=stride)
+    w = np.ascontiguousarray(g["old/w"], np.float64)
+    assert old.L.fba_belief_upload(old.h, 0, n, None, None, None, ptr(w)) == 0
+    prior_of = {k: single(k, priors[k]) for k in range(len(g.t_par))}
+    sid, state, counts = [], [], []
+    proposals = 0
+    while len(sid) < n:
+        i = old.sample(rng)                                                              # :200
+        k = int(g["old/struct_id"][i])
+        if host(lambda r: O.lib().orc_boolean(r.ref())):                                 # :206-208
+            k2 = k
+        else:
+            tp2, op2 = host(lambda r: O.mutate_structure(m, g.t_par[k], g.o_par[k], 0, r))
+            k2 = key[(tp2.tobytes(), op2.tobytes())]
+        prop = single(k2, priors[k2])
+        prop.replay_history(*hist, rng)                                                  # :215, computePosterior
+        src = single(k, g["old/counts"][i])
+        old_score = fba.log_bd_score(src, prior_of[k])[0]                                # :237
+        new_score = fba.log_bd_score(prop, prior_of[k2])[0]                              # :238
+        proposals += 1
+        if math.log(host(lambda r: O.lib().orc_uniform01(r.ref()))) < new_score - old_score:   # :240
+            d = prop.download()
+            sid.append(k2), state.append(int(d["state"][0])), counts.append(d["counts"][0])
+        prop.free()
+        src.free()
+    assert rng.exhausted and proposals > n
+    np.testing.assert_array_equal(sid, g["new/struct_id"])
+    np.testing.assert_array_equal(state, g["new/state"])
+    np.testing.assert_array_equal(np.stack(counts)[:, :g["new/counts"].shape[1]], g["new/counts"])
+    for b in prior_of.values():
+        b.free()
+    old.free()
+    sim.close()
